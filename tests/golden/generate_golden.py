@@ -1,0 +1,301 @@
+"""Generate golden input/output vectors by running the REAL reference.
+
+Run in the build container only (``/root/reference`` does not exist on the GPU
+box):
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/generate_golden.py
+
+It imports the unmodified reference from ``/root/reference`` (read-only; NumPy
+path, because no Fortran compiler exists here), evaluates the hot-path modules
+on the reference's own mesh files, and stores dense inputs + outputs as small
+``.npz`` files next to this script.  The fixtures travel; the reference does not.
+
+Each ``modules_*.npz`` holds one mesh state:
+  pos (nv,3) f64, tri (nf,3) i32, gamma (nf), is_boundary (nv) bool,
+  fixed (nv) bool, kappa (nv), c0 (nv), tilts (nv,3),
+  body_rows_<i> (facet rows of body i), body_target_<i>,
+and per evaluated module ``E_<tag>``, ``g_<tag>`` (+ ``tg_<tag>`` tilt grads).
+"""
+
+from __future__ import annotations
+
+import importlib.util
+import os
+import sys
+
+import numpy as np
+
+REF = os.environ.get("MEMBRANE_REFERENCE_ROOT", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.dont_write_bytecode = True
+sys.path.insert(0, REF)
+
+from core.parameters.global_parameters import GlobalParameters  # noqa: E402
+from core.parameters.resolver import ParameterResolver  # noqa: E402
+from geometry.bending_derivatives import grad_cotan, grad_triangle_area  # noqa: E402
+from geometry.curvature import compute_curvature_data  # noqa: E402
+from geometry.geom_io import load_data, parse_geometry  # noqa: E402
+from geometry.tilt_operators import p1_triangle_shape_gradients  # noqa: E402
+from modules.constraints import volume as volume_constraint  # noqa: E402
+from modules.energy import bending, bending_tilt, surface, tilt  # noqa: E402
+from modules.energy import volume as volume_energy  # noqa: E402
+from modules.energy.bending_math import _apply_beltrami_laplacian  # noqa: E402
+from modules.energy.bending_utils import _compute_effective_areas, _vertex_normals  # noqa: E402
+from runtime.constraint_manager import ConstraintModuleManager  # noqa: E402
+from runtime.energy_manager import EnergyModuleManager  # noqa: E402
+from runtime.minimizer import Minimizer  # noqa: E402
+from runtime.refinement import refine_triangle_mesh  # noqa: E402
+from runtime.steppers.gradient_descent import GradientDescent  # noqa: E402
+
+
+def _load_ref_test_module(name):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(REF, "tests", name + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+# ------------------------------------------------------------------ kernels
+def kernel_vectors():
+    """Same seeded inputs as the reference's tests/test_fortran_kernels.py:46-376."""
+    out = {}
+    for n in (4, 17):
+        rng = np.random.default_rng(123)
+        u = rng.normal(size=(n, 3))
+        v = rng.normal(size=(n, 3))
+        v += 0.3 * rng.normal(size=(n, 3))
+        gu, gv = grad_cotan(u, v)
+        tu, tv = grad_triangle_area(u, v)
+        out.update({f"gc{n}_u": u, f"gc{n}_v": v, f"gc{n}_gu": gu, f"gc{n}_gv": gv,
+                    f"gc{n}_tu": tu, f"gc{n}_tv": tv})
+    # degenerate grad_cotan rows (S <= 1e-15 -> zeros)
+    u = np.array([[1.0, 0, 0], [0, 0, 0], [1, 2, 3.0]])
+    v = np.array([[2.0, 0, 0], [1, 1, 1], [1, 2, 3.0]])
+    gu, gv = grad_cotan(u, v)
+    out.update(gcd_u=u, gcd_v=v, gcd_gu=gu, gcd_gv=gv)
+
+    rng = np.random.default_rng(456)
+    nv, nf, dim = 11, 8, 3
+    w = rng.normal(size=(nf, 3))
+    tri = rng.integers(0, nv, size=(nf, 3), dtype=np.int32)
+    field = rng.normal(size=(nv, dim))
+    os.environ["MEMBRANE_DISABLE_FORTRAN_BENDING"] = "1"
+    out.update(lap_w=w, lap_tri=tri, lap_field=field,
+               lap_out=_apply_beltrami_laplacian(w, tri, field))
+
+    rng = np.random.default_rng(999)
+    nv, nf = 10, 7
+    pos = rng.normal(size=(nv, 3))
+    tl = rng.normal(size=(nv, 3))
+    tri = rng.integers(0, nv, size=(nf, 3), dtype=np.int32)
+    area, g0, g1, g2 = p1_triangle_shape_gradients(positions=pos, tri_rows=tri)
+    div = (np.einsum("ij,ij->i", tl[tri[:, 0]], g0) + np.einsum("ij,ij->i", tl[tri[:, 1]], g1)
+           + np.einsum("ij,ij->i", tl[tri[:, 2]], g2))
+    out.update(p1_pos=pos, p1_tilts=tl, p1_tri=tri, p1_div=div, p1_area=area,
+               p1_g0=g0, p1_g1=g1, p1_g2=g2)
+
+    ref_test = _load_ref_test_module("test_fortran_kernels")
+    rng = np.random.default_rng(2024)
+    nv, nf = 12, 9
+    pos = rng.normal(size=(nv, 3)).astype(np.float64)
+    tri = rng.integers(0, nv, size=(nf, 3), dtype=np.int32)
+    k, a, wts, va0, va1, va2 = ref_test._curvature_data_reference(pos, tri)
+    out.update(cd_pos=pos, cd_tri=tri, cd_k=k, cd_a=a, cd_w=wts, cd_va0=va0, cd_va1=va1, cd_va2=va2)
+
+    # surface kernel: random soup incl. repeated indices (degenerate facets are skipped)
+    rng = np.random.default_rng(7)
+    nv, nf = 15, 20
+    pos = rng.normal(size=(nv, 3))
+    tri = rng.integers(0, nv, size=(nf, 3), dtype=np.int32)
+    gamma = rng.uniform(0.5, 2.0, size=nf)
+    out.update(sf_pos=pos, sf_tri=tri, sf_gamma=gamma)
+    np.savez_compressed(os.path.join(HERE, "kernels.npz"), **out)
+    print("kernels.npz", len(out), "arrays")
+
+
+# ------------------------------------------------------------------ modules
+def _dense_state(mesh):
+    mesh.build_position_cache()
+    pos = np.array(mesh.positions_view(), dtype=np.float64, order="C")
+    tri, _ = mesh.triangle_row_cache()
+    tri = np.ascontiguousarray(tri, dtype=np.int32)
+    nv = pos.shape[0]
+    idx = mesh.vertex_index_to_row
+    is_b = np.zeros(nv, dtype=bool)
+    for vid in mesh.boundary_vertex_ids:
+        if vid in idx:
+            is_b[idx[vid]] = True
+    fixed = np.zeros(nv, dtype=bool)
+    for vid, v in mesh.vertices.items():
+        if getattr(v, "fixed", False):
+            fixed[idx[int(vid)]] = True
+    state = dict(pos=pos, tri=tri, is_boundary=is_b, fixed=fixed,
+                 gamma=np.asarray(mesh.get_facet_parameter_array("surface_tension"), dtype=np.float64))
+    facet_row = mesh.facet_to_triangle_row
+    for i, body in enumerate(mesh.bodies.values()):
+        rows = np.array([facet_row[abs(int(f))] for f in body.facet_indices], dtype=np.int32)
+        state[f"body_rows_{i}"] = rows
+        tv = body.target_volume
+        if tv is None:
+            tv = body.options.get("target_volume")
+        state[f"body_target_{i}"] = np.float64(np.nan if tv is None else tv)
+    return state
+
+
+def _module_outputs(mesh, gp, state, tag_params):
+    """Evaluate the hot-path modules with the reference's own functions."""
+    resolver = ParameterResolver(gp)
+    pos = mesh.positions_view()
+    idx = mesh.vertex_index_to_row
+    out = {}
+
+    g = np.zeros_like(pos)
+    out["E_surface"] = surface.compute_energy_and_gradient_array(
+        mesh, gp, resolver, positions=pos, index_map=idx, grad_arr=g)
+    out["g_surface"] = g
+
+    if mesh.bodies:
+        gcs = []
+        for body in mesh.bodies.values():
+            gc = np.zeros_like(pos)
+            body.accumulate_volume_gradient(mesh, pos, gc, factor=1.0)
+            gcs.append(gc)
+            out.setdefault("volumes", []).append(body.compute_volume(mesh, positions=np.array(pos)))
+        out["g_volume"] = np.stack(gcs)
+        out["volumes"] = np.array(out["volumes"])
+
+    for tag, (model, mode, kappa, c0) in tag_params.items():
+        gp.set("bending_modulus", kappa)
+        gp.set("spontaneous_curvature", c0)
+        gp.set("bending_energy_model", model)
+        gp.set("bending_gradient_mode", mode)
+        if hasattr(mesh, "_bending_vertex_param_cache"):
+            mesh._bending_vertex_param_cache = None
+        g = np.zeros_like(pos)
+        out[f"E_bending_{tag}"] = bending.compute_energy_and_gradient_array(
+            mesh, gp, resolver, positions=pos, index_map=idx, grad_arr=g)
+        out[f"g_bending_{tag}"] = g
+        out[f"Ev_bending_{tag}"] = bending.compute_energy_array(mesh, gp, pos, idx)
+        if model == "helfrich":
+            tl = state["tilts"]
+            g = np.zeros_like(pos)
+            tg = np.zeros_like(pos)
+            out[f"E_bending_tilt_{tag}"] = bending_tilt.compute_energy_and_gradient_array(
+                mesh, gp, resolver, positions=pos, index_map=idx, grad_arr=g,
+                tilts=tl, tilt_grad_arr=tg)
+            out[f"g_bending_tilt_{tag}"] = g
+            out[f"tg_bending_tilt_{tag}"] = tg
+            tg2 = np.zeros_like(pos)
+            e2 = bending_tilt.compute_energy_and_gradient_array(
+                mesh, gp, resolver, positions=pos, index_map=idx, grad_arr=None,
+                tilts=tl, tilt_grad_arr=tg2)
+            assert abs(e2 - out[f"E_bending_tilt_{tag}"]) <= 1e-12 * max(1.0, abs(e2))
+            out[f"tgonly_bending_tilt_{tag}"] = tg2
+
+    gp.set("tilt_rigidity", 1.7)
+    g = np.zeros_like(pos)
+    tg = np.zeros_like(pos)
+    out["E_tilt"] = tilt.compute_energy_and_gradient_array(
+        mesh, gp, resolver, positions=pos, index_map=idx, grad_arr=g,
+        tilts=state["tilts"], tilt_grad_arr=tg)
+    out["g_tilt"] = g
+    out["tg_tilt"] = tg
+    out["k_tilt"] = np.float64(1.7)
+
+    # intermediates (curvature data, effective areas, normals) for kernel-level parity
+    k_vecs, a_vor, weights, _ = compute_curvature_data(mesh, np.array(pos), idx)
+    a_eff, va0, va1, va2 = _compute_effective_areas(mesh, np.array(pos), state["tri"], weights, idx)
+    out.update(k_vecs=np.array(k_vecs), a_vor=np.array(a_vor), weights=np.array(weights),
+               a_eff=np.array(a_eff), va_eff=np.stack([va0, va1, va2], axis=1),
+               normals=_vertex_normals(mesh, np.array(pos), state["tri"]))
+    return out
+
+
+BENDING_TAGS = {
+    "helfrich_analytic": ("helfrich", "analytic", 1.0, 0.0),
+    "helfrich_c0": ("helfrich", "analytic", 2.5, 0.35),
+    "helfrich_approx": ("helfrich", "approx", 1.0, 0.2),
+    "willmore_analytic": ("willmore", "analytic", 1.3, 0.0),
+}
+
+
+def _save_state(name, mesh, rng, jitter=0.0):
+    gp = mesh.global_parameters
+    if jitter:
+        for v in mesh.vertices.values():
+            v.position = np.asarray(v.position, dtype=float) + jitter * rng.normal(size=3)
+        mesh.increment_version()
+    state = _dense_state(mesh)
+    nv = state["pos"].shape[0]
+    state["tilts"] = 0.1 * rng.normal(size=(nv, 3))
+    params = {}
+    for tag, (model, mode, kappa, c0) in BENDING_TAGS.items():
+        params[f"param_{tag}"] = np.array([kappa, c0])
+    out = _module_outputs(mesh, gp, state, BENDING_TAGS)
+    np.savez_compressed(os.path.join(HERE, f"modules_{name}.npz"), **state, **params, **out)
+    print(f"modules_{name}.npz nv={nv} nf={state['tri'].shape[0]} nb={int(state['is_boundary'].sum())}")
+
+
+def _refined(path, levels):
+    mesh = parse_geometry(load_data(path))
+    for _ in range(levels):
+        mesh = refine_triangle_mesh(mesh)
+    return mesh
+
+
+def module_vectors():
+    rng = np.random.default_rng(20261018)
+    m = os.path.join(REF, "meshes")
+    b = os.path.join(REF, "benchmarks", "inputs")
+    _save_state("cube_r0", _refined(os.path.join(m, "cube.json"), 0), rng)
+    _save_state("cube_r2_jit", _refined(os.path.join(m, "cube.json"), 2), rng, jitter=0.02)
+    _save_state("catenoid_r2", _refined(os.path.join(m, "catenoid.json"), 2), rng)
+    _save_state("catenoid_r2_jit", _refined(os.path.join(m, "catenoid.json"), 2), rng, jitter=0.01)
+    _save_state("bending_cube_r2", _refined(os.path.join(m, "bending_cube.yaml"), 2), rng, jitter=0.01)
+    _save_state("sphere_r1_jit", _refined(os.path.join(b, "bench_bending_analytic.json"), 1), rng, jitter=0.03)
+    _save_state("flat_sheet", _refined(os.path.join(m, "flat_sheet_4x4.yaml"), 1), rng)
+    _save_state("flat_sheet_jit", _refined(os.path.join(m, "flat_sheet_4x4.yaml"), 1), rng, jitter=0.05)
+
+
+# ------------------------------------------------------------- minimizer
+def minimizer_vectors():
+    """Total energy + projected gradient through Minimizer (KKT + fixed mask)."""
+    out = {}
+    for name, path, levels in (
+        ("cube", os.path.join(REF, "meshes", "cube.json"), 1),
+        ("bcube", os.path.join(REF, "meshes", "bending_cube.yaml"), 1),
+    ):
+        mesh = _refined(path, levels)
+        rng = np.random.default_rng(5)
+        for v in mesh.vertices.values():
+            v.position = np.asarray(v.position, dtype=float) + 0.01 * rng.normal(size=3)
+        mesh.increment_version()
+        gp = mesh.global_parameters
+        mini = Minimizer(mesh, gp, GradientDescent(), EnergyModuleManager(mesh.energy_modules),
+                         ConstraintModuleManager(mesh.constraint_modules), quiet=True)
+        e, g = mini.compute_energy_and_gradient_array()
+        st = _dense_state(mesh)
+        for k, v in st.items():
+            out[f"{name}_{k}"] = v
+        out[f"{name}_E"] = np.float64(e)
+        out[f"{name}_g"] = np.array(g)
+        out[f"{name}_modules"] = np.array(list(mesh.energy_modules))
+        out[f"{name}_constraints"] = np.array(list(mesh.constraint_modules))
+        out[f"{name}_mode"] = np.array(str(gp.get("volume_constraint_mode", "lagrange")))
+        out[f"{name}_kvol"] = np.float64(gp.get("volume_stiffness", 0.0) or 0.0)
+        out[f"{name}_kappa"] = np.float64(gp.get("bending_modulus", 0.0) or 0.0)
+        out[f"{name}_c0"] = np.float64(gp.get("spontaneous_curvature", 0.0) or 0.0)
+        out[f"{name}_model"] = np.array(str(gp.get("bending_energy_model", "helfrich")))
+        bd = mini.compute_energy_breakdown()
+        for k, v in bd.items():
+            out[f"{name}_E_{k}"] = np.float64(v)
+        print(name, list(mesh.energy_modules), list(mesh.constraint_modules), e,
+              str(gp.get("volume_constraint_mode", "lagrange")))
+    np.savez_compressed(os.path.join(HERE, "minimizer.npz"), **out)
+
+
+if __name__ == "__main__":
+    _ = (volume_constraint, volume_energy)
+    kernel_vectors()
+    module_vectors()
+    minimizer_vectors()
