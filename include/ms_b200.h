@@ -1,0 +1,197 @@
+/*
+ * membrane_solver_b200 -- C ABI of the B200 (sm_100a) energy+gradient path.
+ *
+ * This is the drop-in boundary: everything the reference binds through
+ * fortran_kernels/loader.py (KernelSpec getters, loader.py:15-20,30,85,139,193,247)
+ * for the per-iteration energy/gradient evaluation is exported here as plain C:
+ * `extern "C"`, raw pointers and sizes, caller-owned memory, int return codes.
+ * 0 = success; any other value is an error and ms_last_error() describes it.
+ * There is no CPU fallback: without a CUDA device every compute entry point fails.
+ *
+ * Array conventions (identical to the reference's dense caches):
+ *   positions / gradients / tilts   (nv,3) C-order float64  (== Fortran (3,nv))
+ *   triangle rows                   (nf,3) C-order int32
+ *   per-facet / per-vertex params   float64; masks uint8 (0/1)
+ * The callee never retains host pointers past the call.
+ */
+#ifndef MS_B200_H
+#define MS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MS_API __attribute__((visibility("default")))
+
+/* ---- module / flag bits for ms_eval_opts ------------------------------------ */
+#define MS_MOD_SURFACE       (1u << 0) /* modules/energy/surface.py:100-239 */
+#define MS_MOD_VOLUME        (1u << 1) /* geometry/body.py:150-252: V and dV/dx of the body */
+#define MS_MOD_BENDING       (1u << 2) /* modules/energy/bending.py:90-181 */
+#define MS_MOD_TILT          (1u << 3) /* modules/energy/tilt.py:99-172 */
+#define MS_MOD_BENDING_TILT  (1u << 4) /* modules/energy/bending_tilt.py:151-482 */
+
+#define MS_FLAG_WILLMORE     (1u << 0) /* bending_energy_model = willmore (bending_params.py:18-21) */
+#define MS_FLAG_APPROX       (1u << 1) /* bending_gradient_mode = approx (bending_params.py:24-31) */
+
+/* ---- scalar slots returned by the evaluation calls (16 doubles) --------------- */
+#define MS_SC_E_SURFACE      0
+#define MS_SC_AREA           1
+#define MS_SC_VOLUME         2
+#define MS_SC_E_BENDING      3
+#define MS_SC_E_TILT         4
+#define MS_SC_E_BENDING_TILT 5
+#define MS_SC_G_G            8
+#define MS_SC_G_GC           9
+#define MS_SC_GC_GC          10
+#define MS_SC_LAMBDA         11
+#define MS_SC_COUNT          16
+
+/* ---- device arrays addressable through ms_ctx_device_ptr / ms_ctx_get_array --- */
+#define MS_ARR_POSITIONS     0  /* (nv,3) */
+#define MS_ARR_GRAD          1  /* (nv,3) shape gradient of the enabled modules */
+#define MS_ARR_VOLGRAD       2  /* (nv,3) dV/dx of the body */
+#define MS_ARR_SEEDS         3  /* (nv,6) pass-A vertex results: fK(3), fA_eff, fA_vor, base */
+#define MS_ARR_TILTS         4  /* (nv,3) */
+#define MS_ARR_TILT_GRAD     5  /* (nv,3) */
+#define MS_ARR_SCALARS       6  /* 16 */
+#define MS_ARR_K_VECS        7  /* (nv,3) integrated curvature vectors (diagnostic) */
+#define MS_ARR_A_VOR         8  /* nv */
+#define MS_ARR_A_EFF         9  /* nv */
+#define MS_ARR_E_VERTEX      10 /* nv  per-vertex bending energy (bending.compute_energy_array) */
+#define MS_ARR_TRIAL         11 /* (nv,3) trial positions x + alpha d */
+#define MS_ARR_DIRECTION     12 /* (nv,3) search direction d */
+
+typedef struct ms_ctx ms_ctx;
+
+typedef struct ms_eval_opts {
+  uint32_t modules;        /* MS_MOD_* */
+  uint32_t flags;          /* MS_FLAG_* */
+  int32_t want_grad;       /* 0: energies only (line-search trial evaluation) */
+  int32_t constraint_mode; /* -1 none; 0 lagrange KKT projection (constraint_manager.py:294-301);
+                              1 penalty  g += k (V-V0) dV/dx (body.py:223-238) */
+  double k_vol;            /* volume_stiffness (penalty mode) */
+  double v_target;         /* body target volume */
+  int32_t apply_fixed;     /* zero the gradient rows of fixed vertices (minimizer.py:988-990) */
+  int32_t use_trial;       /* evaluate at MS_ARR_TRIAL instead of MS_ARR_POSITIONS */
+  int32_t patch_begin;     /* multi-GPU: range of patches this rank evaluates; */
+  int32_t patch_count;     /*            patch_count < 0 means all patches */
+  int32_t diagnostics;     /* also write K_VECS / A_VOR / A_EFF / E_VERTEX */
+  int32_t reserved;
+} ms_eval_opts;
+
+typedef struct ms_pack_info {
+  int32_t nv, nf;
+  int32_t n_patches, threads;
+  int32_t max_owned, max_local, max_rounds;
+  int32_t reserved;
+  int64_t n_slots;   /* record slots streamed per pass */
+  int64_t n_listed;  /* facet listings over all patches (ring facets counted per patch) */
+  int64_t n_valid;   /* facets with all indices in range */
+  int64_t n_halo;    /* halo vertex references over all patches */
+} ms_pack_info;
+
+/* ---- library ------------------------------------------------------------------ */
+MS_API const char* ms_last_error(void);
+MS_API int ms_version(void);
+MS_API int ms_device_count(int* count);
+
+/* ---- stateful context: device-resident mesh (replaces the host caches of
+ *      runtime/energy_context.py:63-276 and Mesh.positions_view/triangle_row_cache) - */
+MS_API int ms_ctx_create(int device, ms_ctx** out);
+MS_API int ms_ctx_destroy(ms_ctx* ctx);
+/* patch geometry used by the next ms_ctx_set_topology (defaults 128 / 512 / 896) */
+MS_API int ms_ctx_set_pack_params(ms_ctx* ctx, int32_t threads, int32_t max_owned, int32_t max_local);
+/* Re-called only after refine / equiangulate / vertex-average changed the topology
+ * (commands/mesh_ops.py:21-78).  is_boundary, body_mask, fixed_mask may be NULL. */
+MS_API int ms_ctx_set_topology(ms_ctx* ctx, int32_t nv, int32_t nf, const int32_t* tri,
+                               const uint8_t* is_boundary, const uint8_t* body_mask,
+                               const uint8_t* fixed_mask);
+MS_API int ms_ctx_pack_info(const ms_ctx* ctx, ms_pack_info* info);
+/* patch p owns vertex rows [v_lo[p], v_lo[p+1]); v_lo has n_patches+1 entries */
+MS_API int ms_ctx_patch_ranges(const ms_ctx* ctx, int32_t* v_lo);
+/* halo vertex rows referenced by patches [patch_begin, patch_begin+patch_count) that lie
+ * outside [own_lo, own_hi): sorted unique; returns the count through n (out may be NULL) */
+MS_API int ms_ctx_halo_rows(const ms_ctx* ctx, int32_t patch_begin, int32_t patch_count,
+                            int32_t own_lo, int32_t own_hi, int32_t* out, int64_t* n);
+/* gamma == NULL: uniform surface tension (Mesh.get_facet_parameter_array, mesh.py:234-265) */
+MS_API int ms_ctx_set_surface_tension(ms_ctx* ctx, const double* gamma, double gamma_uniform);
+/* kappa / c0 == NULL: uniform (bending_params.py:41-115) */
+MS_API int ms_ctx_set_bending_params(ms_ctx* ctx, const double* kappa, const double* c0,
+                                     double kappa_uniform, double c0_uniform);
+MS_API int ms_ctx_set_tilt_rigidity(ms_ctx* ctx, double k_tilt);
+MS_API int ms_ctx_set_positions(ms_ctx* ctx, const double* pos_host);
+MS_API int ms_ctx_set_tilts(ms_ctx* ctx, const double* tilts_host);
+/* generic host<->device copies of a named array (count doubles from element offset) */
+MS_API int ms_ctx_upload(ms_ctx* ctx, int which, const double* host, int64_t offset, int64_t count);
+MS_API int ms_ctx_get_array(ms_ctx* ctx, int which, double* host, int64_t offset, int64_t count);
+MS_API void* ms_ctx_device_ptr(ms_ctx* ctx, int which);
+MS_API int64_t ms_ctx_array_len(const ms_ctx* ctx, int which);
+MS_API int ms_ctx_set_stream(ms_ctx* ctx, void* cuda_stream);
+
+/* One evaluation with everything resident: pass A (+ pass B when want_grad), scalar
+ * reduction, optional KKT/penalty/fixed post-processing.  Asynchronous on the context
+ * stream; results stay on the device. */
+MS_API int ms_ctx_eval_async(ms_ctx* ctx, const ms_eval_opts* opts);
+/* the two halves, for the multi-GPU path (seed halo exchange happens between them) */
+MS_API int ms_ctx_eval_pass_a(ms_ctx* ctx, const ms_eval_opts* opts);
+MS_API int ms_ctx_eval_pass_b(ms_ctx* ctx, const ms_eval_opts* opts);
+MS_API int ms_ctx_eval_finish(ms_ctx* ctx, const ms_eval_opts* opts);
+/* synchronise and copy the 16 scalars to the host */
+MS_API int ms_ctx_read_scalars(ms_ctx* ctx, double* scalars16);
+/* ms_ctx_eval_async + ms_ctx_read_scalars */
+MS_API int ms_ctx_eval(ms_ctx* ctx, const ms_eval_opts* opts, double* scalars16);
+/* End-to-end call with HOST buffers (what a plugin module does): H2D positions, evaluate,
+ * D2H scalars and, when non-NULL, the gradient / volume gradient / tilt gradient. */
+MS_API int ms_ctx_eval_host(ms_ctx* ctx, const ms_eval_opts* opts, const double* pos_host,
+                            double* scalars16, double* grad_host, double* volgrad_host,
+                            double* tilt_grad_host);
+/* trial = positions + alpha * direction (line_search.py:358-382), on the device */
+MS_API int ms_ctx_make_trial(ms_ctx* ctx, double alpha);
+/* positions <- trial (accept the step) */
+MS_API int ms_ctx_accept_trial(ms_ctx* ctx);
+/* deterministic <g,g>, <g,gC>, <gC,gC> into the scalar vector */
+MS_API int ms_ctx_dots(ms_ctx* ctx);
+
+/* timing on the context stream (CUDA events) and an L2 flush for benchmarks */
+MS_API int ms_ctx_timer_start(ms_ctx* ctx);
+MS_API int ms_ctx_timer_stop(ms_ctx* ctx, float* milliseconds);
+MS_API int ms_ctx_sync(ms_ctx* ctx);
+/* a pool of CUDA events recorded on the context stream, for per-kernel timing */
+MS_API int ms_ctx_event_record(ms_ctx* ctx, int32_t index);
+MS_API int ms_ctx_event_elapsed(ms_ctx* ctx, int32_t from_index, int32_t to_index, float* milliseconds);
+/* write `bytes` of scratch device memory (evicts L2 between timed iterations) */
+MS_API int ms_ctx_flush_l2(ms_ctx* ctx, int64_t bytes);
+MS_API int ms_host_register(void* ptr, int64_t bytes);
+MS_API int ms_host_unregister(void* ptr);
+
+/* ---- stateless shims: one per reference kernel, host pointers in and out ------ */
+/* fortran_kernels/surface_energy.f90:27-99 -- grad is accumulated (+=), E returned */
+MS_API int ms_surface_energy_and_gradient(int32_t nv, int32_t nf, const double* pos,
+                                          const int32_t* tri, const double* gamma, double* grad,
+                                          double* energy, int32_t zero_based);
+/* fortran_kernels/bending_kernels.f90:32-74 */
+MS_API int ms_grad_cotan_batch(int32_t n, const double* u, const double* v, double* grad_u,
+                               double* grad_v);
+/* fortran_kernels/bending_kernels.f90:87-131 -- out is overwritten */
+MS_API int ms_apply_beltrami_laplacian(int32_t dim, int32_t nv, int32_t nf, const double* weights,
+                                       const int32_t* tri, const double* field, double* out,
+                                       int32_t zero_based);
+/* fortran_kernels/tilt_kernels.f90:26-86 */
+MS_API int ms_p1_triangle_divergence(int32_t nv, int32_t nf, const double* pos,
+                                     const double* tilts, const int32_t* tri, double* div_tri,
+                                     double* area, double* g0, double* g1, double* g2,
+                                     int32_t zero_based);
+/* fortran_kernels/tilt_kernels.f90:88-190 -- va0/va1/va2 may be NULL */
+MS_API int ms_compute_curvature_data(int32_t nv, int32_t nf, const double* pos, const int32_t* tri,
+                                     double* k_vecs, double* vertex_areas, double* weights,
+                                     int32_t zero_based, double* va0, double* va1, double* va2);
+/* geometry/body.py:150-252 -- volume of the facets given; grad (may be NULL) += factor*dV/dx */
+MS_API int ms_volume_and_gradient(int32_t nv, int32_t nf, const double* pos, const int32_t* tri,
+                                  double factor, double* grad, double* volume);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MS_B200_H */

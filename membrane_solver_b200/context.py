@@ -1,0 +1,273 @@
+"""Device-resident mesh context: the B200 twin of ``runtime/energy_context.py``.
+
+``DeviceMesh`` owns one ``ms_ctx`` (C ABI): packed topology, positions, tilts,
+per-entity parameters and all outputs live in HBM across minimiser steps and are
+re-uploaded only when the reference bumps the matching version counter
+(SURVEY.md section 3.5): topology <- ``_facet_loops_version`` / ``_vertex_ids_version``
+/ ``_topology_version``; positions <- every evaluation that passes a host array.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib as L
+
+
+@dataclass
+class EvalResult:
+    """Host copy of the scalar vector of one evaluation."""
+
+    scalars: np.ndarray
+
+    @property
+    def e_surface(self) -> float:
+        return float(self.scalars[L.SC_E_SURFACE])
+
+    @property
+    def area(self) -> float:
+        return float(self.scalars[L.SC_AREA])
+
+    @property
+    def volume(self) -> float:
+        return float(self.scalars[L.SC_VOLUME])
+
+    @property
+    def e_bending(self) -> float:
+        return float(self.scalars[L.SC_E_BENDING])
+
+    @property
+    def e_tilt(self) -> float:
+        return float(self.scalars[L.SC_E_TILT])
+
+    @property
+    def kkt_lambda(self) -> float:
+        return float(self.scalars[L.SC_LAMBDA])
+
+
+class _CudaArrayView:
+    """Exposes a device buffer of the context through ``__cuda_array_interface__``
+    so that ``torch.as_tensor(view, device=...)`` aliases it without a copy."""
+
+    def __init__(self, ptr: int, shape, owner):
+        self._owner = owner  # keeps the context alive
+        self.__cuda_array_interface__ = {
+            "shape": tuple(int(s) for s in shape),
+            "typestr": "<f8",
+            "data": (int(ptr), False),
+            "version": 3,
+            "strides": None,
+        }
+
+
+class DeviceMesh:
+    """One mesh resident on one GPU."""
+
+    def __init__(self, device: int = 0, *, threads: int | None = None, max_owned: int | None = None,
+                 max_local: int | None = None):
+        self._lib = L.lib()
+        handle = ctypes.c_void_p()
+        L.check(self._lib.ms_ctx_create(int(device), ctypes.byref(handle)))
+        self._h = handle
+        self.device = int(device)
+        self.nv = 0
+        self.nf = 0
+        if threads is not None or max_owned is not None or max_local is not None:
+            L.check(self._lib.ms_ctx_set_pack_params(self._h, int(threads or 128), int(max_owned or 512),
+                                                     int(max_local or 896)))
+
+    # -- lifetime -----------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.ms_ctx_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- topology and parameters --------------------------------------------
+    def set_topology(self, nv: int, tri: np.ndarray, *, is_boundary=None, body_mask=None,
+                     fixed_mask=None) -> None:
+        tri = np.ascontiguousarray(tri, dtype=np.int32).reshape(-1, 3)
+        keep = [tri]
+
+        def mask(a, n):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dtype=np.uint8)
+            if a.shape != (n,):
+                raise ValueError(f"mask must have shape ({n},)")
+            keep.append(a)
+            return a
+
+        b = mask(is_boundary, nv)
+        bm = mask(body_mask, tri.shape[0])
+        fx = mask(fixed_mask, nv)
+        L.check(self._lib.ms_ctx_set_topology(self._h, int(nv), int(tri.shape[0]), L.iptr(tri),
+                                              L.bptr(b), L.bptr(bm), L.bptr(fx)))
+        self.nv = int(nv)
+        self.nf = int(tri.shape[0])
+
+    def pack_info(self) -> dict:
+        info = L.PackInfo()
+        L.check(self._lib.ms_ctx_pack_info(self._h, ctypes.byref(info)))
+        return {name: int(getattr(info, name)) for name, _ in L.PackInfo._fields_ if name != "reserved"}
+
+    def patch_ranges(self) -> np.ndarray:
+        n = self.pack_info()["n_patches"]
+        out = np.empty(n + 1, dtype=np.int32)
+        L.check(self._lib.ms_ctx_patch_ranges(self._h, L.iptr(out)))
+        return out
+
+    def halo_rows(self, patch_begin: int, patch_count: int, own_lo: int, own_hi: int) -> np.ndarray:
+        n = ctypes.c_int64(0)
+        L.check(self._lib.ms_ctx_halo_rows(self._h, patch_begin, patch_count, own_lo, own_hi, None,
+                                           ctypes.byref(n)))
+        out = np.empty(int(n.value), dtype=np.int32)
+        if out.size:
+            L.check(self._lib.ms_ctx_halo_rows(self._h, patch_begin, patch_count, own_lo, own_hi,
+                                               L.iptr(out), ctypes.byref(n)))
+        return out
+
+    def set_surface_tension(self, gamma) -> None:
+        """Scalar (uniform) or per-facet array, as ``Mesh.get_facet_parameter_array`` builds it."""
+        if np.ndim(gamma) == 0:
+            L.check(self._lib.ms_ctx_set_surface_tension(self._h, None, float(gamma)))
+            return
+        g = L.as_f64(gamma, (self.nf,))
+        if g.size and np.all(g == g[0]):
+            L.check(self._lib.ms_ctx_set_surface_tension(self._h, None, float(g[0])))
+        else:
+            L.check(self._lib.ms_ctx_set_surface_tension(self._h, L.dptr(g), 0.0))
+
+    def set_bending_params(self, kappa, c0) -> None:
+        def split(x):
+            if np.ndim(x) == 0:
+                return None, float(x)
+            a = L.as_f64(x, (self.nv,))
+            if a.size and np.all(a == a[0]):
+                return None, float(a[0])
+            return a, 0.0
+
+        ka, ku = split(kappa)
+        ca, cu = split(c0)
+        L.check(self._lib.ms_ctx_set_bending_params(self._h, L.dptr(ka), L.dptr(ca), ku, cu))
+
+    def set_tilt_rigidity(self, k_tilt: float) -> None:
+        L.check(self._lib.ms_ctx_set_tilt_rigidity(self._h, float(k_tilt)))
+
+    # -- state --------------------------------------------------------------
+    def upload(self, which: int, host: np.ndarray) -> None:
+        a = L.as_f64(host)
+        L.check(self._lib.ms_ctx_upload(self._h, which, L.dptr(a), 0, a.size))
+        # the copy is asynchronous on the context stream; the source must stay valid
+        L.check(self._lib.ms_ctx_sync(self._h))
+
+    def set_positions(self, pos: np.ndarray) -> None:
+        self.upload(L.ARR_POSITIONS, L.as_f64(pos, (self.nv, 3)))
+
+    def set_tilts(self, tilts: np.ndarray) -> None:
+        self.upload(L.ARR_TILTS, L.as_f64(tilts, (self.nv, 3)))
+
+    def set_direction(self, d: np.ndarray) -> None:
+        self.upload(L.ARR_DIRECTION, L.as_f64(d, (self.nv, 3)))
+
+    def download(self, which: int) -> np.ndarray:
+        n = int(self._lib.ms_ctx_array_len(self._h, which))
+        out = np.empty(n, dtype=np.float64)
+        L.check(self._lib.ms_ctx_get_array(self._h, which, L.dptr(out), 0, n))
+        w = L.ARRAY_WIDTH[which]
+        return out.reshape(-1, w) if w > 1 else out
+
+    def device_view(self, which: int) -> _CudaArrayView:
+        ptr = self._lib.ms_ctx_device_ptr(self._h, which)
+        if not ptr:
+            raise L.B200Error(f"array {which} is not available")
+        n = int(self._lib.ms_ctx_array_len(self._h, which))
+        w = L.ARRAY_WIDTH[which]
+        return _CudaArrayView(ptr, (n // w, w) if w > 1 else (n,), self)
+
+    # -- evaluation ---------------------------------------------------------
+    @staticmethod
+    def options(modules: int, *, flags: int = 0, want_grad: bool = True, constraint_mode: int = -1,
+                k_vol: float = 0.0, v_target: float = 0.0, apply_fixed: bool = False,
+                use_trial: bool = False, patch_begin: int = 0, patch_count: int = -1,
+                diagnostics: bool = False) -> L.EvalOpts:
+        return L.EvalOpts(modules=modules, flags=flags, want_grad=int(want_grad),
+                          constraint_mode=constraint_mode, k_vol=k_vol, v_target=v_target,
+                          apply_fixed=int(apply_fixed), use_trial=int(use_trial),
+                          patch_begin=patch_begin, patch_count=patch_count,
+                          diagnostics=int(diagnostics), reserved=0)
+
+    def eval(self, opts: L.EvalOpts) -> EvalResult:
+        """Evaluate with everything resident; only the 16 scalars come back."""
+        sc = np.zeros(L.SC_COUNT)
+        L.check(self._lib.ms_ctx_eval(self._h, ctypes.byref(opts), L.dptr(sc)))
+        return EvalResult(sc)
+
+    def eval_async(self, opts: L.EvalOpts) -> None:
+        L.check(self._lib.ms_ctx_eval_async(self._h, ctypes.byref(opts)))
+
+    def eval_pass_a(self, opts: L.EvalOpts) -> None:
+        L.check(self._lib.ms_ctx_eval_pass_a(self._h, ctypes.byref(opts)))
+
+    def eval_pass_b(self, opts: L.EvalOpts) -> None:
+        L.check(self._lib.ms_ctx_eval_pass_b(self._h, ctypes.byref(opts)))
+
+    def eval_finish(self, opts: L.EvalOpts) -> None:
+        L.check(self._lib.ms_ctx_eval_finish(self._h, ctypes.byref(opts)))
+
+    def read_scalars(self) -> EvalResult:
+        sc = np.zeros(L.SC_COUNT)
+        L.check(self._lib.ms_ctx_read_scalars(self._h, L.dptr(sc)))
+        return EvalResult(sc)
+
+    def eval_host(self, opts: L.EvalOpts, pos: np.ndarray | None, *, grad: np.ndarray | None = None,
+                  volgrad: np.ndarray | None = None, tilt_grad: np.ndarray | None = None) -> EvalResult:
+        """End-to-end evaluation with HOST buffers: H2D positions, kernels, D2H results."""
+        sc = np.zeros(L.SC_COUNT)
+        for a in (grad, volgrad, tilt_grad):
+            if a is not None and (a.dtype != np.float64 or not a.flags["C_CONTIGUOUS"] or a.shape != (self.nv, 3)):
+                raise ValueError("output arrays must be C-contiguous float64 (nv,3)")
+        p = None if pos is None else L.as_f64(pos, (self.nv, 3))
+        L.check(self._lib.ms_ctx_eval_host(self._h, ctypes.byref(opts), L.dptr(p), L.dptr(sc),
+                                           L.dptr(grad), L.dptr(volgrad), L.dptr(tilt_grad)))
+        return EvalResult(sc)
+
+    def make_trial(self, alpha: float) -> None:
+        L.check(self._lib.ms_ctx_make_trial(self._h, float(alpha)))
+
+    def accept_trial(self) -> None:
+        L.check(self._lib.ms_ctx_accept_trial(self._h))
+
+    def dots(self) -> None:
+        L.check(self._lib.ms_ctx_dots(self._h))
+
+    # -- timing -------------------------------------------------------------
+    def timer_start(self) -> None:
+        L.check(self._lib.ms_ctx_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = ctypes.c_float(0.0)
+        L.check(self._lib.ms_ctx_timer_stop(self._h, ctypes.byref(ms)))
+        return float(ms.value)
+
+    def event_record(self, index: int) -> None:
+        L.check(self._lib.ms_ctx_event_record(self._h, int(index)))
+
+    def event_elapsed(self, i: int, j: int) -> float:
+        ms = ctypes.c_float(0.0)
+        L.check(self._lib.ms_ctx_event_elapsed(self._h, int(i), int(j), ctypes.byref(ms)))
+        return float(ms.value)
+
+    def flush_l2(self, nbytes: int = 256 << 20) -> None:
+        L.check(self._lib.ms_ctx_flush_l2(self._h, int(nbytes)))
+
+    def sync(self) -> None:
+        L.check(self._lib.ms_ctx_sync(self._h))

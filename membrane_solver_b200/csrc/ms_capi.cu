@@ -1,0 +1,800 @@
+// C-ABI layer (include/ms_b200.h): context with device-resident mesh buffers and
+// the stateless per-kernel shims.  Replaces the dispatch of
+// fortran_kernels/loader.py for the energy+gradient path.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ms_b200.h"
+#include "ms_kernels.cuh"
+#include "ms_pack.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CU(expr)                                                                         \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess)                                                               \
+      return fail(-100 - int(_e), std::string(#expr) + ": " + cudaGetErrorString(_e));   \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  int ensure(size_t count) {
+    if (count <= n && p) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+    if (count == 0) return 0;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T));
+    if (e != cudaSuccess) return fail(-100 - int(e), std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    n = count;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  ~DevBuf() { release(); }
+};
+
+bool g_configured[64] = {false};
+
+}  // namespace
+
+struct ms_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool have_topology = false;
+  int32_t nv = 0, nf = 0;
+  ms::PackParams pack_params;
+  ms::PackedMesh packed;  // recs / slot_facet kept on the host for gamma repacking
+  std::vector<int32_t> v_lo;
+
+  DevBuf<ms::PatchHeader> d_patches;
+  DevBuf<int32_t> d_halo, d_round_ptr;
+  DevBuf<ms::FacetRec> d_recs;
+  DevBuf<double> d_slot_gamma;
+  DevBuf<uint8_t> d_boundary, d_fixed;
+  DevBuf<double> d_kappa, d_c0;
+  DevBuf<double> d_pos, d_trial, d_dir, d_tilts, d_seeds, d_partials, d_grad, d_volgrad,
+      d_tilt_grad, d_scalars, d_dot_partials, d_kvecs, d_avor, d_aeff, d_evert;
+  bool has_gamma = false, has_kappa = false, has_c0 = false, has_boundary = false,
+       has_fixed = false, has_body = false;
+  double gamma_u = 1.0, kappa_u = 0.0, c0_u = 0.0, k_tilt = 0.0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<cudaEvent_t> events;
+  DevBuf<uint8_t> d_flush;
+};
+
+namespace {
+
+constexpr int kDotBlocks = 592;  // 4 CTAs per SM on 148 SMs
+
+int use_device(const ms_ctx* c) {
+  CU(cudaSetDevice(c->device));
+  return 0;
+}
+
+int check_ctx(const ms_ctx* c, bool need_topology) {
+  if (!c) return fail(-1, "null context");
+  if (need_topology && !c->have_topology) return fail(-2, "ms_ctx_set_topology has not been called");
+  return use_device(c);
+}
+
+double* array_ptr(ms_ctx* c, int which, int64_t* len) {
+  const int64_t nv = c->nv;
+  switch (which) {
+    case MS_ARR_POSITIONS: *len = 3 * nv; return c->d_pos.p;
+    case MS_ARR_GRAD: *len = 3 * nv; return c->d_grad.p;
+    case MS_ARR_VOLGRAD: *len = 3 * nv; return c->d_volgrad.p;
+    case MS_ARR_SEEDS: *len = ms::kSeedStride * nv; return c->d_seeds.p;
+    case MS_ARR_TILTS: *len = 3 * nv; return c->d_tilts.p;
+    case MS_ARR_TILT_GRAD: *len = 3 * nv; return c->d_tilt_grad.p;
+    case MS_ARR_SCALARS: *len = MS_SC_COUNT; return c->d_scalars.p;
+    case MS_ARR_K_VECS: *len = 3 * nv; return c->d_kvecs.p;
+    case MS_ARR_A_VOR: *len = nv; return c->d_avor.p;
+    case MS_ARR_A_EFF: *len = nv; return c->d_aeff.p;
+    case MS_ARR_E_VERTEX: *len = nv; return c->d_evert.p;
+    case MS_ARR_TRIAL: *len = 3 * nv; return c->d_trial.p;
+    case MS_ARR_DIRECTION: *len = 3 * nv; return c->d_dir.p;
+    default: *len = 0; return nullptr;
+  }
+}
+
+// Lazily allocate the optional arrays the first time they are addressed.
+int ensure_array(ms_ctx* c, int which) {
+  const size_t nv = size_t(c->nv);
+  switch (which) {
+    case MS_ARR_TILTS: return c->d_tilts.ensure(3 * nv);
+    case MS_ARR_TILT_GRAD: return c->d_tilt_grad.ensure(3 * nv);
+    case MS_ARR_K_VECS: return c->d_kvecs.ensure(3 * nv);
+    case MS_ARR_A_VOR: return c->d_avor.ensure(nv);
+    case MS_ARR_A_EFF: return c->d_aeff.ensure(nv);
+    case MS_ARR_E_VERTEX: return c->d_evert.ensure(nv);
+    case MS_ARR_TRIAL: return c->d_trial.ensure(3 * nv);
+    case MS_ARR_DIRECTION: return c->d_dir.ensure(3 * nv);
+    default: return 0;
+  }
+}
+
+int fill_launch(ms_ctx* c, const ms_eval_opts* o, ms::PatchLaunch& a) {
+  const int n_patches = int(c->packed.patches.size());
+  int begin = o->patch_count < 0 ? 0 : o->patch_begin;
+  int count = o->patch_count < 0 ? n_patches : o->patch_count;
+  if (begin < 0 || count < 0 || begin + count > n_patches) return fail(-3, "patch range out of bounds");
+  std::memset(&a, 0, sizeof(a));
+  a.patches = c->d_patches.p;
+  a.halo_ids = c->d_halo.p;
+  a.recs = c->d_recs.p;
+  a.round_ptr = c->d_round_ptr.p;
+  a.slot_gamma = c->has_gamma ? c->d_slot_gamma.p : nullptr;
+  a.patch_begin = begin;
+  a.patch_count = count;
+  a.threads = c->packed.params.threads;
+  a.max_owned = c->packed.max_owned;
+  a.max_local = c->packed.max_local;
+  if (o->use_trial) {
+    if (!c->d_trial.p) return fail(-4, "use_trial set but no trial positions exist (ms_ctx_make_trial)");
+    a.pos = c->d_trial.p;
+  } else {
+    a.pos = c->d_pos.p;
+  }
+  a.tilts = c->d_tilts.p;
+  a.is_boundary = c->has_boundary ? c->d_boundary.p : nullptr;
+  a.kappa = c->has_kappa ? c->d_kappa.p : nullptr;
+  a.c0 = c->has_c0 ? c->d_c0.p : nullptr;
+  a.gamma_u = c->gamma_u;
+  a.kappa_u = c->kappa_u;
+  a.c0_u = c->c0_u;
+  a.k_tilt = c->k_tilt;
+  a.modules = o->modules;
+  a.flags = o->flags;
+  a.seeds = c->d_seeds.p;
+  a.partials = c->d_partials.p;
+  a.grad = c->d_grad.p;
+  a.volgrad = c->d_volgrad.p;
+  if ((o->modules & MS_MOD_TILT)) {
+    if (!c->d_tilts.p) return fail(-5, "tilt module requested but no tilts were uploaded");
+    if (o->want_grad) {
+      if (int rc = ensure_array(c, MS_ARR_TILT_GRAD)) return rc;
+      a.tilt_grad = c->d_tilt_grad.p;
+    }
+  }
+  if (o->diagnostics) {
+    for (int w : {MS_ARR_K_VECS, MS_ARR_A_VOR, MS_ARR_A_EFF, MS_ARR_E_VERTEX})
+      if (int rc = ensure_array(c, w)) return rc;
+    a.k_vecs = c->d_kvecs.p;
+    a.a_vor = c->d_avor.p;
+    a.a_eff = c->d_aeff.p;
+    a.e_vertex = c->d_evert.p;
+  }
+  if (o->modules & MS_MOD_BENDING_TILT) return fail(-6, "bending_tilt is not available in the patch path yet");
+  return 0;
+}
+
+bool needs_bending(const ms_eval_opts* o) { return (o->modules & MS_MOD_BENDING) != 0; }
+
+}  // namespace
+
+extern "C" {
+
+const char* ms_last_error(void) { return g_err.c_str(); }
+int ms_version(void) { return 100; }
+
+int ms_device_count(int* count) {
+  if (!count) return fail(-1, "null argument");
+  cudaError_t e = cudaGetDeviceCount(count);
+  if (e != cudaSuccess) {
+    *count = 0;
+    return fail(-100 - int(e), std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+  }
+  return 0;
+}
+
+int ms_ctx_create(int device, ms_ctx** out) {
+  if (!out) return fail(-1, "null argument");
+  *out = nullptr;
+  int n = 0;
+  if (int rc = ms_device_count(&n)) return rc;
+  if (n <= 0) return fail(-7, "no CUDA device: the B200 path has no CPU fallback");
+  if (device < 0 || device >= n) return fail(-1, "device index out of range");
+  CU(cudaSetDevice(device));
+  if (device < 64 && !g_configured[device]) {
+    CU(ms::configure_kernels());
+    g_configured[device] = true;
+  }
+  ms_ctx* c = new ms_ctx();
+  c->device = device;
+  CU(cudaEventCreate(&c->ev0));
+  CU(cudaEventCreate(&c->ev1));
+  if (int rc = c->d_scalars.ensure(MS_SC_COUNT)) { delete c; return rc; }
+  CU(cudaMemset(c->d_scalars.p, 0, MS_SC_COUNT * sizeof(double)));
+  if (int rc = c->d_dot_partials.ensure(3 * kDotBlocks)) { delete c; return rc; }
+  *out = c;
+  return 0;
+}
+
+int ms_ctx_destroy(ms_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  for (cudaEvent_t e : c->events)
+    if (e) cudaEventDestroy(e);
+  delete c;
+  return 0;
+}
+
+int ms_ctx_set_stream(ms_ctx* c, void* s) {
+  if (!c) return fail(-1, "null context");
+  c->stream = reinterpret_cast<cudaStream_t>(s);
+  return 0;
+}
+
+int ms_ctx_set_pack_params(ms_ctx* c, int32_t threads, int32_t max_owned, int32_t max_local) {
+  if (!c) return fail(-1, "null context");
+  if (threads < 32 || threads > 256 || threads % 32) return fail(-1, "threads must be a multiple of 32 in [32,256]");
+  if (max_owned < 1 || max_local < max_owned || max_local > 65535) return fail(-1, "bad patch sizes");
+  const size_t worst = ms::pass_b_smem_bytes(max_owned, max_local, true, true);
+  if (worst > 227 * 1024) return fail(-1, "patch does not fit in 227 KB of shared memory");
+  c->pack_params.threads = threads;
+  c->pack_params.max_owned = max_owned;
+  c->pack_params.max_local = max_local;
+  return 0;
+}
+
+int ms_ctx_set_topology(ms_ctx* c, int32_t nv, int32_t nf, const int32_t* tri,
+                        const uint8_t* is_boundary, const uint8_t* body_mask,
+                        const uint8_t* fixed_mask) {
+  if (int rc = check_ctx(c, false)) return rc;
+  if (nv < 0 || nf < 0 || (nf > 0 && !tri)) return fail(-1, "bad topology arguments");
+  c->have_topology = false;
+  const int prc = ms::pack_patches(nv, nf, tri, body_mask, c->pack_params, c->packed);
+  if (prc == -2) return fail(-8, "a vertex neighbourhood exceeds max_local; raise it with ms_ctx_set_pack_params");
+  if (prc) return fail(-1, "pack_patches failed");
+  c->nv = nv;
+  c->nf = nf;
+  const ms::PackedMesh& pk = c->packed;
+  const size_t np = pk.patches.size();
+  c->v_lo.resize(np + 1);
+  for (size_t p = 0; p < np; ++p) c->v_lo[p] = pk.patches[p].v_lo;
+  c->v_lo[np] = nv;
+
+  if (int rc = c->d_patches.ensure(np)) return rc;
+  if (int rc = c->d_halo.ensure(pk.halo_ids.size())) return rc;
+  if (int rc = c->d_recs.ensure(pk.recs.size())) return rc;
+  if (int rc = c->d_round_ptr.ensure(pk.round_ptr.size())) return rc;
+  if (!pk.round_ptr.empty())
+    CU(cudaMemcpy(c->d_round_ptr.p, pk.round_ptr.data(), pk.round_ptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  if (np) CU(cudaMemcpy(c->d_patches.p, pk.patches.data(), np * sizeof(ms::PatchHeader), cudaMemcpyHostToDevice));
+  if (!pk.halo_ids.empty())
+    CU(cudaMemcpy(c->d_halo.p, pk.halo_ids.data(), pk.halo_ids.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  if (!pk.recs.empty())
+    CU(cudaMemcpy(c->d_recs.p, pk.recs.data(), pk.recs.size() * sizeof(ms::FacetRec), cudaMemcpyHostToDevice));
+
+  c->has_boundary = is_boundary != nullptr;
+  c->has_fixed = fixed_mask != nullptr;
+  c->has_body = body_mask != nullptr;
+  if (is_boundary) {
+    if (int rc = c->d_boundary.ensure(size_t(nv))) return rc;
+    if (nv) CU(cudaMemcpy(c->d_boundary.p, is_boundary, size_t(nv), cudaMemcpyHostToDevice));
+  }
+  if (fixed_mask) {
+    if (int rc = c->d_fixed.ensure(size_t(nv))) return rc;
+    if (nv) CU(cudaMemcpy(c->d_fixed.p, fixed_mask, size_t(nv), cudaMemcpyHostToDevice));
+  }
+  const size_t n3 = 3 * size_t(nv);
+  if (int rc = c->d_pos.ensure(n3)) return rc;
+  if (int rc = c->d_grad.ensure(n3)) return rc;
+  if (int rc = c->d_volgrad.ensure(n3)) return rc;
+  if (int rc = c->d_seeds.ensure(size_t(ms::kSeedStride) * size_t(nv))) return rc;
+  if (int rc = c->d_partials.ensure(np * ms::kPartialStride)) return rc;
+  if (np) CU(cudaMemset(c->d_partials.p, 0, np * ms::kPartialStride * sizeof(double)));
+  if (n3) {
+    CU(cudaMemset(c->d_grad.p, 0, n3 * sizeof(double)));
+    CU(cudaMemset(c->d_volgrad.p, 0, n3 * sizeof(double)));
+  }
+  // per-entity parameter arrays belong to the previous topology
+  c->has_gamma = c->has_kappa = c->has_c0 = false;
+  c->d_tilts.release();
+  c->d_tilt_grad.release();
+  c->d_trial.release();
+  c->d_dir.release();
+  c->d_kvecs.release();
+  c->d_avor.release();
+  c->d_aeff.release();
+  c->d_evert.release();
+  c->have_topology = true;
+  return 0;
+}
+
+int ms_ctx_pack_info(const ms_ctx* c, ms_pack_info* info) {
+  if (!c || !info) return fail(-1, "null argument");
+  if (!c->have_topology) return fail(-2, "ms_ctx_set_topology has not been called");
+  const ms::PackedMesh& pk = c->packed;
+  info->nv = c->nv;
+  info->nf = c->nf;
+  info->n_patches = int32_t(pk.patches.size());
+  info->threads = pk.params.threads;
+  info->max_owned = pk.max_owned;
+  info->max_local = pk.max_local;
+  info->max_rounds = pk.max_rounds;
+  info->reserved = 0;
+  info->n_slots = int64_t(pk.recs.size());
+  info->n_listed = pk.n_listed;
+  info->n_valid = pk.n_valid;
+  info->n_halo = int64_t(pk.halo_ids.size());
+  return 0;
+}
+
+int ms_ctx_patch_ranges(const ms_ctx* c, int32_t* v_lo) {
+  if (!c || !v_lo) return fail(-1, "null argument");
+  if (!c->have_topology) return fail(-2, "ms_ctx_set_topology has not been called");
+  std::memcpy(v_lo, c->v_lo.data(), c->v_lo.size() * sizeof(int32_t));
+  return 0;
+}
+
+int ms_ctx_halo_rows(const ms_ctx* c, int32_t patch_begin, int32_t patch_count, int32_t own_lo,
+                     int32_t own_hi, int32_t* out, int64_t* n) {
+  if (!c || !n) return fail(-1, "null argument");
+  if (!c->have_topology) return fail(-2, "ms_ctx_set_topology has not been called");
+  const ms::PackedMesh& pk = c->packed;
+  if (patch_begin < 0 || patch_count < 0 || size_t(patch_begin) + size_t(patch_count) > pk.patches.size())
+    return fail(-3, "patch range out of bounds");
+  std::vector<uint8_t> seen(size_t(c->nv), 0);
+  for (int32_t p = patch_begin; p < patch_begin + patch_count; ++p) {
+    const ms::PatchHeader& h = pk.patches[size_t(p)];
+    for (int32_t j = 0; j < h.n_halo; ++j) {
+      const int32_t v = pk.halo_ids[size_t(h.halo_off) + size_t(j)];
+      if (v < own_lo || v >= own_hi) seen[size_t(v)] = 1;
+    }
+  }
+  int64_t k = 0;
+  for (int32_t v = 0; v < c->nv; ++v)
+    if (seen[size_t(v)]) {
+      if (out) out[k] = v;
+      ++k;
+    }
+  *n = k;
+  return 0;
+}
+
+int ms_ctx_set_surface_tension(ms_ctx* c, const double* gamma, double gamma_uniform) {
+  if (int rc = check_ctx(c, true)) return rc;
+  c->gamma_u = gamma_uniform;
+  c->has_gamma = false;
+  if (!gamma) return 0;
+  const ms::PackedMesh& pk = c->packed;
+  std::vector<double> slot_gamma(pk.slot_facet.size(), 0.0);
+  for (size_t s = 0; s < slot_gamma.size(); ++s)
+    if (pk.slot_facet[s] >= 0) slot_gamma[s] = gamma[pk.slot_facet[s]];
+  if (int rc = c->d_slot_gamma.ensure(slot_gamma.size())) return rc;
+  if (!slot_gamma.empty())
+    CU(cudaMemcpy(c->d_slot_gamma.p, slot_gamma.data(), slot_gamma.size() * sizeof(double), cudaMemcpyHostToDevice));
+  c->has_gamma = true;
+  return 0;
+}
+
+int ms_ctx_set_bending_params(ms_ctx* c, const double* kappa, const double* c0, double kappa_u,
+                              double c0_u) {
+  if (int rc = check_ctx(c, true)) return rc;
+  c->kappa_u = kappa_u;
+  c->c0_u = c0_u;
+  c->has_kappa = kappa != nullptr;
+  c->has_c0 = c0 != nullptr;
+  const size_t nv = size_t(c->nv);
+  if (kappa) {
+    if (int rc = c->d_kappa.ensure(nv)) return rc;
+    if (nv) CU(cudaMemcpy(c->d_kappa.p, kappa, nv * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  if (c0) {
+    if (int rc = c->d_c0.ensure(nv)) return rc;
+    if (nv) CU(cudaMemcpy(c->d_c0.p, c0, nv * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+
+int ms_ctx_set_tilt_rigidity(ms_ctx* c, double k_tilt) {
+  if (!c) return fail(-1, "null context");
+  c->k_tilt = k_tilt;
+  return 0;
+}
+
+int ms_ctx_upload(ms_ctx* c, int which, const double* host, int64_t offset, int64_t count) {
+  if (int rc = check_ctx(c, true)) return rc;
+  if (!host && count > 0) return fail(-1, "null host pointer");
+  if (int rc = ensure_array(c, which)) return rc;
+  int64_t len = 0;
+  double* d = array_ptr(c, which, &len);
+  if (!d && len > 0) return fail(-1, "array is not allocated");
+  if (offset < 0 || count < 0 || offset + count > len) return fail(-1, "upload range out of bounds");
+  if (count) CU(cudaMemcpyAsync(d + offset, host, size_t(count) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  return 0;
+}
+
+int ms_ctx_get_array(ms_ctx* c, int which, double* host, int64_t offset, int64_t count) {
+  if (int rc = check_ctx(c, true)) return rc;
+  if (!host && count > 0) return fail(-1, "null host pointer");
+  int64_t len = 0;
+  double* d = array_ptr(c, which, &len);
+  if (!d && len > 0) return fail(-1, "array has not been produced yet");
+  if (offset < 0 || count < 0 || offset + count > len) return fail(-1, "download range out of bounds");
+  if (count) CU(cudaMemcpyAsync(host, d + offset, size_t(count) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+void* ms_ctx_device_ptr(ms_ctx* c, int which) {
+  if (!c || !c->have_topology) return nullptr;
+  if (use_device(c)) return nullptr;
+  if (ensure_array(c, which)) return nullptr;
+  int64_t len = 0;
+  return array_ptr(c, which, &len);
+}
+
+int64_t ms_ctx_array_len(const ms_ctx* c, int which) {
+  if (!c || !c->have_topology) return 0;
+  int64_t len = 0;
+  array_ptr(const_cast<ms_ctx*>(c), which, &len);
+  return len;
+}
+
+int ms_ctx_set_positions(ms_ctx* c, const double* pos_host) {
+  return ms_ctx_upload(c, MS_ARR_POSITIONS, pos_host, 0, 3 * int64_t(c ? c->nv : 0));
+}
+
+int ms_ctx_set_tilts(ms_ctx* c, const double* tilts_host) {
+  return ms_ctx_upload(c, MS_ARR_TILTS, tilts_host, 0, 3 * int64_t(c ? c->nv : 0));
+}
+
+int ms_ctx_eval_pass_a(ms_ctx* c, const ms_eval_opts* o) {
+  if (int rc = check_ctx(c, true)) return rc;
+  if (!o) return fail(-1, "null options");
+  ms::PatchLaunch a;
+  if (int rc = fill_launch(c, o, a)) return rc;
+  // Pass A is needed for the bending seeds and for energies; surface/volume-only
+  // gradient evaluations do everything in pass B.
+  if (needs_bending(o) || !o->want_grad) CU(ms::launch_pass_a(a, c->stream));
+  return 0;
+}
+
+int ms_ctx_eval_pass_b(ms_ctx* c, const ms_eval_opts* o) {
+  if (int rc = check_ctx(c, true)) return rc;
+  if (!o) return fail(-1, "null options");
+  if (!o->want_grad) return 0;
+  ms::PatchLaunch a;
+  if (int rc = fill_launch(c, o, a)) return rc;
+  CU(ms::launch_pass_b(a, needs_bending(o), !needs_bending(o), c->stream));
+  return 0;
+}
+
+int ms_ctx_eval_finish(ms_ctx* c, const ms_eval_opts* o) {
+  if (int rc = check_ctx(c, true)) return rc;
+  if (!o) return fail(-1, "null options");
+  const int n_patches = int(c->packed.patches.size());
+  CU(ms::launch_reduce_partials(c->d_partials.p, n_patches, c->d_scalars.p, c->stream));
+  if (o->want_grad && (o->constraint_mode >= 0 || o->apply_fixed)) {
+    const double* gc = (o->constraint_mode >= 0 && (o->modules & MS_MOD_VOLUME)) ? c->d_volgrad.p : nullptr;
+    if (gc && o->constraint_mode == 0)
+      CU(ms::launch_dots(c->d_grad.p, gc, 3 * int64_t(c->nv), c->d_dot_partials.p, kDotBlocks,
+                         c->d_scalars.p, c->stream));
+    const uint8_t* fixed = (o->apply_fixed && c->has_fixed) ? c->d_fixed.p : nullptr;
+    if (gc || fixed)
+      CU(ms::launch_project(c->d_grad.p, gc, fixed, c->nv, c->d_scalars.p, o->constraint_mode,
+                            o->k_vol, o->v_target, c->stream));
+  }
+  return 0;
+}
+
+int ms_ctx_eval_async(ms_ctx* c, const ms_eval_opts* o) {
+  if (int rc = ms_ctx_eval_pass_a(c, o)) return rc;
+  if (int rc = ms_ctx_eval_pass_b(c, o)) return rc;
+  return ms_ctx_eval_finish(c, o);
+}
+
+int ms_ctx_read_scalars(ms_ctx* c, double* scalars16) {
+  if (int rc = check_ctx(c, false)) return rc;
+  if (!scalars16) return fail(-1, "null argument");
+  CU(cudaMemcpyAsync(scalars16, c->d_scalars.p, MS_SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int ms_ctx_eval(ms_ctx* c, const ms_eval_opts* o, double* scalars16) {
+  if (int rc = ms_ctx_eval_async(c, o)) return rc;
+  return ms_ctx_read_scalars(c, scalars16);
+}
+
+int ms_ctx_eval_host(ms_ctx* c, const ms_eval_opts* o, const double* pos_host, double* scalars16,
+                     double* grad_host, double* volgrad_host, double* tilt_grad_host) {
+  if (int rc = check_ctx(c, true)) return rc;
+  if (!o || !scalars16) return fail(-1, "null argument");
+  const int64_t n3 = 3 * int64_t(c->nv);
+  if (pos_host)
+    if (int rc = ms_ctx_upload(c, o->use_trial ? MS_ARR_TRIAL : MS_ARR_POSITIONS, pos_host, 0, n3)) return rc;
+  if (int rc = ms_ctx_eval_async(c, o)) return rc;
+  const size_t bytes = size_t(n3) * sizeof(double);
+  if (o->want_grad && grad_host && n3)
+    CU(cudaMemcpyAsync(grad_host, c->d_grad.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+  if (o->want_grad && volgrad_host && n3 && (o->modules & MS_MOD_VOLUME))
+    CU(cudaMemcpyAsync(volgrad_host, c->d_volgrad.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+  if (o->want_grad && tilt_grad_host && n3 && c->d_tilt_grad.p)
+    CU(cudaMemcpyAsync(tilt_grad_host, c->d_tilt_grad.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+  return ms_ctx_read_scalars(c, scalars16);
+}
+
+int ms_ctx_make_trial(ms_ctx* c, double alpha) {
+  if (int rc = check_ctx(c, true)) return rc;
+  if (!c->d_dir.p) return fail(-4, "no search direction uploaded (MS_ARR_DIRECTION)");
+  if (int rc = ensure_array(c, MS_ARR_TRIAL)) return rc;
+  CU(ms::launch_axpy(c->d_pos.p, c->d_dir.p, alpha, c->d_trial.p, 3 * int64_t(c->nv), c->stream));
+  return 0;
+}
+
+int ms_ctx_accept_trial(ms_ctx* c) {
+  if (int rc = check_ctx(c, true)) return rc;
+  if (!c->d_trial.p) return fail(-4, "no trial positions exist");
+  CU(cudaMemcpyAsync(c->d_pos.p, c->d_trial.p, 3 * size_t(c->nv) * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  return 0;
+}
+
+int ms_ctx_dots(ms_ctx* c) {
+  if (int rc = check_ctx(c, true)) return rc;
+  CU(ms::launch_dots(c->d_grad.p, c->d_volgrad.p, 3 * int64_t(c->nv), c->d_dot_partials.p, kDotBlocks,
+                     c->d_scalars.p, c->stream));
+  return 0;
+}
+
+int ms_ctx_timer_start(ms_ctx* c) {
+  if (int rc = check_ctx(c, false)) return rc;
+  CU(cudaEventRecord(c->ev0, c->stream));
+  return 0;
+}
+
+int ms_ctx_timer_stop(ms_ctx* c, float* ms_out) {
+  if (int rc = check_ctx(c, false)) return rc;
+  if (!ms_out) return fail(-1, "null argument");
+  CU(cudaEventRecord(c->ev1, c->stream));
+  CU(cudaEventSynchronize(c->ev1));
+  CU(cudaEventElapsedTime(ms_out, c->ev0, c->ev1));
+  return 0;
+}
+
+int ms_ctx_sync(ms_ctx* c) {
+  if (int rc = check_ctx(c, false)) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int ms_ctx_event_record(ms_ctx* c, int32_t index) {
+  if (int rc = check_ctx(c, false)) return rc;
+  if (index < 0 || index >= (1 << 16)) return fail(-1, "event index out of range");
+  if (size_t(index) >= c->events.size()) c->events.resize(size_t(index) + 1, nullptr);
+  if (!c->events[size_t(index)]) CU(cudaEventCreate(&c->events[size_t(index)]));
+  CU(cudaEventRecord(c->events[size_t(index)], c->stream));
+  return 0;
+}
+
+int ms_ctx_event_elapsed(ms_ctx* c, int32_t from, int32_t to, float* ms_out) {
+  if (int rc = check_ctx(c, false)) return rc;
+  if (!ms_out || from < 0 || to < 0 || size_t(from) >= c->events.size() || size_t(to) >= c->events.size() ||
+      !c->events[size_t(from)] || !c->events[size_t(to)])
+    return fail(-1, "event was never recorded");
+  CU(cudaEventSynchronize(c->events[size_t(to)]));
+  CU(cudaEventElapsedTime(ms_out, c->events[size_t(from)], c->events[size_t(to)]));
+  return 0;
+}
+
+int ms_ctx_flush_l2(ms_ctx* c, int64_t bytes) {
+  if (int rc = check_ctx(c, false)) return rc;
+  if (bytes <= 0) return 0;
+  if (int rc = c->d_flush.ensure(size_t(bytes))) return rc;
+  CU(cudaMemsetAsync(c->d_flush.p, 1, size_t(bytes), c->stream));
+  return 0;
+}
+
+int ms_host_register(void* ptr, int64_t bytes) {
+  CU(cudaHostRegister(ptr, size_t(bytes), cudaHostRegisterDefault));
+  return 0;
+}
+
+int ms_host_unregister(void* ptr) {
+  CU(cudaHostUnregister(ptr));
+  return 0;
+}
+
+// --------------------------------------------------------------------------
+// Stateless shims.  Each call: copy in, build the corner CSR on the host, run
+// the facet kernel + deterministic gather, copy out.  No state is kept.
+// --------------------------------------------------------------------------
+namespace {
+
+struct SoupDev {
+  DevBuf<double> pos;
+  DevBuf<int32_t> tri, ptr, idx;
+  ms::SoupArgs args;
+};
+
+int soup_setup(int32_t nv, int32_t nf, const double* pos, const int32_t* tri, int32_t zero_based,
+               bool need_csr, SoupDev& d) {
+  int n = 0;
+  if (int rc = ms_device_count(&n)) return rc;
+  if (n <= 0) return fail(-7, "no CUDA device: the B200 path has no CPU fallback");
+  if (nv < 0 || nf < 0 || (nv > 0 && !pos) || (nf > 0 && !tri)) return fail(-1, "bad arguments");
+  if (int rc = d.pos.ensure(3 * size_t(nv) + 1)) return rc;
+  if (int rc = d.tri.ensure(3 * size_t(nf) + 1)) return rc;
+  if (nv) CU(cudaMemcpy(d.pos.p, pos, 3 * size_t(nv) * sizeof(double), cudaMemcpyHostToDevice));
+  if (nf) CU(cudaMemcpy(d.tri.p, tri, 3 * size_t(nf) * sizeof(int32_t), cudaMemcpyHostToDevice));
+  const int32_t shift = zero_based ? 0 : -1;
+  if (need_csr) {
+    std::vector<int32_t> t;
+    const int32_t* tz = tri;
+    if (shift) {
+      t.assign(tri, tri + 3 * size_t(nf));
+      for (auto& x : t) x += shift;
+      tz = t.data();
+    }
+    std::vector<int32_t> ptr, idx;
+    ms::build_corner_csr(nv, nf, tz, ptr, idx);
+    if (int rc = d.ptr.ensure(ptr.size())) return rc;
+    if (int rc = d.idx.ensure(idx.size() + 1)) return rc;
+    CU(cudaMemcpy(d.ptr.p, ptr.data(), ptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    if (!idx.empty()) CU(cudaMemcpy(d.idx.p, idx.data(), idx.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  }
+  d.args.nv = nv;
+  d.args.nf = nf;
+  d.args.pos = d.pos.p;
+  d.args.tri = d.tri.p;
+  d.args.csr_ptr = d.ptr.p;
+  d.args.csr_idx = d.idx.p;
+  d.args.shift = shift;
+  return 0;
+}
+
+int to_dev(DevBuf<double>& b, const double* host, size_t n) {
+  if (int rc = b.ensure(n + 1)) return rc;
+  if (n) CU(cudaMemcpy(b.p, host, n * sizeof(double), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int to_host(double* host, const DevBuf<double>& b, size_t n) {
+  if (n && host) CU(cudaMemcpy(host, b.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+}  // namespace
+
+int ms_surface_energy_and_gradient(int32_t nv, int32_t nf, const double* pos, const int32_t* tri,
+                                   const double* gamma, double* grad, double* energy,
+                                   int32_t zero_based) {
+  if (!energy || (nv > 0 && !grad) || (nf > 0 && !gamma)) return fail(-1, "null argument");
+  SoupDev d;
+  if (int rc = soup_setup(nv, nf, pos, tri, zero_based, true, d)) return rc;
+  DevBuf<double> d_gamma, d_corner, d_fe, d_grad, d_e;
+  if (int rc = to_dev(d_gamma, gamma, size_t(nf))) return rc;
+  if (int rc = to_dev(d_grad, grad, 3 * size_t(nv))) return rc;
+  if (int rc = d_corner.ensure(9 * size_t(nf) + 1)) return rc;
+  if (int rc = d_fe.ensure(size_t(nf) + 1)) return rc;
+  if (int rc = d_e.ensure(1)) return rc;
+  CU(ms::launch_soup_surface(d.args, d_gamma.p, d_corner.p, d_fe.p, d_grad.p, d_e.p, nullptr));
+  CU(cudaDeviceSynchronize());
+  if (int rc = to_host(grad, d_grad, 3 * size_t(nv))) return rc;
+  return to_host(energy, d_e, 1);
+}
+
+int ms_volume_and_gradient(int32_t nv, int32_t nf, const double* pos, const int32_t* tri,
+                           double factor, double* grad, double* volume) {
+  if (!volume) return fail(-1, "null argument");
+  SoupDev d;
+  if (int rc = soup_setup(nv, nf, pos, tri, 1, true, d)) return rc;
+  DevBuf<double> d_corner, d_fv, d_grad, d_v;
+  if (grad)
+    if (int rc = to_dev(d_grad, grad, 3 * size_t(nv))) return rc;
+  if (int rc = d_corner.ensure(9 * size_t(nf) + 1)) return rc;
+  if (int rc = d_fv.ensure(size_t(nf) + 1)) return rc;
+  if (int rc = d_v.ensure(1)) return rc;
+  CU(ms::launch_soup_volume(d.args, factor, d_corner.p, d_fv.p, grad ? d_grad.p : nullptr, d_v.p, nullptr));
+  CU(cudaDeviceSynchronize());
+  if (grad)
+    if (int rc = to_host(grad, d_grad, 3 * size_t(nv))) return rc;
+  return to_host(volume, d_v, 1);
+}
+
+int ms_grad_cotan_batch(int32_t n, const double* u, const double* v, double* gu, double* gv) {
+  int nd = 0;
+  if (int rc = ms_device_count(&nd)) return rc;
+  if (nd <= 0) return fail(-7, "no CUDA device: the B200 path has no CPU fallback");
+  if (n < 0 || (n > 0 && (!u || !v || !gu || !gv))) return fail(-1, "bad arguments");
+  DevBuf<double> du, dv, dgu, dgv;
+  if (int rc = to_dev(du, u, 3 * size_t(n))) return rc;
+  if (int rc = to_dev(dv, v, 3 * size_t(n))) return rc;
+  if (int rc = dgu.ensure(3 * size_t(n) + 1)) return rc;
+  if (int rc = dgv.ensure(3 * size_t(n) + 1)) return rc;
+  CU(ms::launch_grad_cotan(n, du.p, dv.p, dgu.p, dgv.p, nullptr));
+  CU(cudaDeviceSynchronize());
+  if (int rc = to_host(gu, dgu, 3 * size_t(n))) return rc;
+  return to_host(gv, dgv, 3 * size_t(n));
+}
+
+int ms_apply_beltrami_laplacian(int32_t dim, int32_t nv, int32_t nf, const double* weights,
+                                const int32_t* tri, const double* field, double* out,
+                                int32_t zero_based) {
+  if (dim < 1 || (nf > 0 && !weights) || (nv > 0 && (!field || !out))) return fail(-1, "bad arguments");
+  SoupDev d;
+  DevBuf<double> dummy;
+  if (int rc = dummy.ensure(4)) return rc;
+  // positions are not used by this kernel; pass the field buffer shape-compatibly
+  std::vector<double> zero_pos(3 * size_t(nv), 0.0);
+  if (int rc = soup_setup(nv, nf, zero_pos.data(), tri, zero_based, true, d)) return rc;
+  DevBuf<double> d_w, d_f, d_corner, d_out;
+  if (int rc = to_dev(d_w, weights, 3 * size_t(nf))) return rc;
+  if (int rc = to_dev(d_f, field, size_t(dim) * size_t(nv))) return rc;
+  if (int rc = d_corner.ensure(3 * size_t(dim) * size_t(nf) + 1)) return rc;
+  if (int rc = d_out.ensure(size_t(dim) * size_t(nv) + 1)) return rc;
+  CU(ms::launch_soup_laplacian(d.args, dim, d_w.p, d_f.p, d_corner.p, d_out.p, nullptr));
+  CU(cudaDeviceSynchronize());
+  return to_host(out, d_out, size_t(dim) * size_t(nv));
+}
+
+int ms_p1_triangle_divergence(int32_t nv, int32_t nf, const double* pos, const double* tilts,
+                              const int32_t* tri, double* div_tri, double* area, double* g0,
+                              double* g1, double* g2, int32_t zero_based) {
+  if ((nv > 0 && !tilts) || (nf > 0 && (!div_tri || !area || !g0 || !g1 || !g2))) return fail(-1, "null argument");
+  SoupDev d;
+  if (int rc = soup_setup(nv, nf, pos, tri, zero_based, false, d)) return rc;
+  DevBuf<double> d_t, d_div, d_area, d_g0, d_g1, d_g2;
+  if (int rc = to_dev(d_t, tilts, 3 * size_t(nv))) return rc;
+  if (int rc = d_div.ensure(size_t(nf) + 1)) return rc;
+  if (int rc = d_area.ensure(size_t(nf) + 1)) return rc;
+  if (int rc = d_g0.ensure(3 * size_t(nf) + 1)) return rc;
+  if (int rc = d_g1.ensure(3 * size_t(nf) + 1)) return rc;
+  if (int rc = d_g2.ensure(3 * size_t(nf) + 1)) return rc;
+  CU(ms::launch_p1_divergence(d.args, d_t.p, d_div.p, d_area.p, d_g0.p, d_g1.p, d_g2.p, nullptr));
+  CU(cudaDeviceSynchronize());
+  if (int rc = to_host(div_tri, d_div, size_t(nf))) return rc;
+  if (int rc = to_host(area, d_area, size_t(nf))) return rc;
+  if (int rc = to_host(g0, d_g0, 3 * size_t(nf))) return rc;
+  if (int rc = to_host(g1, d_g1, 3 * size_t(nf))) return rc;
+  return to_host(g2, d_g2, 3 * size_t(nf));
+}
+
+int ms_compute_curvature_data(int32_t nv, int32_t nf, const double* pos, const int32_t* tri,
+                              double* k_vecs, double* vertex_areas, double* weights,
+                              int32_t zero_based, double* va0, double* va1, double* va2) {
+  if ((nv > 0 && (!k_vecs || !vertex_areas)) || (nf > 0 && !weights)) return fail(-1, "null argument");
+  SoupDev d;
+  if (int rc = soup_setup(nv, nf, pos, tri, zero_based, true, d)) return rc;
+  DevBuf<double> d_corner, d_k, d_a, d_w, d_va0, d_va1, d_va2;
+  if (int rc = d_corner.ensure(12 * size_t(nf) + 1)) return rc;
+  if (int rc = d_k.ensure(3 * size_t(nv) + 1)) return rc;
+  if (int rc = d_a.ensure(size_t(nv) + 1)) return rc;
+  if (int rc = d_w.ensure(3 * size_t(nf) + 1)) return rc;
+  if (int rc = d_va0.ensure(size_t(nf) + 1)) return rc;
+  if (int rc = d_va1.ensure(size_t(nf) + 1)) return rc;
+  if (int rc = d_va2.ensure(size_t(nf) + 1)) return rc;
+  CU(ms::launch_soup_curvature(d.args, d_corner.p, d_k.p, d_a.p, d_w.p, d_va0.p, d_va1.p, d_va2.p, nullptr));
+  CU(cudaDeviceSynchronize());
+  if (int rc = to_host(k_vecs, d_k, 3 * size_t(nv))) return rc;
+  if (int rc = to_host(vertex_areas, d_a, size_t(nv))) return rc;
+  if (int rc = to_host(weights, d_w, 3 * size_t(nf))) return rc;
+  if (int rc = to_host(va0, d_va0, size_t(nf))) return rc;
+  if (int rc = to_host(va1, d_va1, size_t(nf))) return rc;
+  return to_host(va2, d_va2, size_t(nf));
+}
+
+}  // extern "C"

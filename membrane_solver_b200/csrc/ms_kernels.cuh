@@ -1,0 +1,113 @@
+// Kernel launch interface between the C-ABI layer (ms_capi.cu) and the kernels
+// (ms_kernels.cu).  Plain structs of device pointers; no torch types.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ms_b200.h"
+#include "ms_math.cuh"
+#include "ms_pack.h"
+
+namespace ms {
+
+// Slots of the per-evaluation scalar vector (device, 16 doubles).
+enum ScalarSlot : int {
+  SC_E_SURFACE = 0,
+  SC_AREA = 1,
+  SC_VOLUME = 2,       // body volume (already divided by 6)
+  SC_E_BENDING = 3,
+  SC_E_TILT = 4,
+  SC_E_BENDING_TILT = 5,
+  SC_G_G = 8,          // <g,g>
+  SC_G_GC = 9,         // <g,gC>
+  SC_GC_GC = 10,       // <gC,gC>
+  SC_LAMBDA = 11,      // KKT multiplier applied
+  SC_COUNT = 16,
+};
+constexpr int kPartialStride = 8;  // per-patch partial sums: slots 0..7 above
+
+constexpr int kSeedStride = 6;  // per-vertex pass-A output: fK(3), fA_eff, fA_vor, base term
+
+struct PatchLaunch {
+  // packed topology (device)
+  const PatchHeader* patches;
+  const int32_t* halo_ids;
+  const FacetRec* recs;
+  const int32_t* round_ptr;   // per patch: n_rounds+1 slot offsets (see PatchHeader)
+  const double* slot_gamma;   // per-slot surface tension, or nullptr -> gamma_u
+  int32_t patch_begin, patch_count;
+  int32_t threads;            // CTA size == record slots per round
+  int32_t max_owned, max_local;
+  // mesh state (device)
+  const double* pos;          // (nv,3)
+  const double* tilts;        // (nv,3) or nullptr
+  const uint8_t* is_boundary; // nv or nullptr
+  const double* kappa;        // nv or nullptr -> kappa_u
+  const double* c0;           // nv or nullptr -> c0_u
+  double gamma_u, kappa_u, c0_u, k_tilt;
+  uint32_t modules, flags;
+  // outputs (device)
+  double* seeds;      // (nv,kSeedStride)  pass A -> pass B
+  double* partials;   // (n_patches_total, kPartialStride), indexed by absolute patch id
+  double* grad;       // (nv,3)   pass B
+  double* volgrad;    // (nv,3)   pass B, when MS_MOD_VOLUME
+  double* tilt_grad;  // (nv,3)   pass B, when tilt modules with tilt gradients requested
+  // optional diagnostics written by pass A when non-null
+  double* k_vecs;     // (nv,3)
+  double* a_vor;      // nv
+  double* a_eff;      // nv
+  double* e_vertex;   // nv   per-vertex bending energy (bending.compute_energy_array)
+};
+
+size_t pass_a_smem_bytes(int max_owned, int max_local, bool tilt);
+size_t pass_b_smem_bytes(int max_owned, int max_local, bool bending, bool tilt);
+
+// scalars_here: also sum the per-facet scalars (surface energy, area, volume).
+cudaError_t launch_pass_a(const PatchLaunch& a, cudaStream_t st);
+cudaError_t launch_pass_b(const PatchLaunch& a, bool bending, bool scalars_here, cudaStream_t st);
+// scalars[0..7] = fixed-order sum over patches of partials; volume slot divided by 6.
+cudaError_t launch_reduce_partials(const double* partials, int n_patches, double* scalars,
+                                   cudaStream_t st);
+cudaError_t configure_kernels();  // opt-in to large dynamic shared memory (once per device)
+
+// --- dense vector helpers on (n) doubles: KKT projection of the volume constraint ---
+// scalars[SC_G_G, SC_G_GC, SC_GC_GC] <- deterministic dot products.
+cudaError_t launch_dots(const double* g, const double* gc, int64_t n, double* block_partials,
+                        int n_blocks, double* scalars, cudaStream_t st);
+// mode 0: lagrange  g -= (<g,gC>/<gC,gC>) gC if <gC,gC> > 1e-18 (constraint_manager.py:294-301)
+// mode 1: penalty   g += k (V - V0) gC (body.py:223-238); then g[fixed] = 0 in both modes.
+cudaError_t launch_project(double* g, const double* gc, const uint8_t* fixed, int64_t nv,
+                           double* scalars, int mode, double k_vol, double v_target,
+                           cudaStream_t st);
+// x_out = x + alpha * d  (trial positions of the line search, line_search.py:358-382)
+cudaError_t launch_axpy(const double* x, const double* d, double alpha, double* out, int64_t n,
+                        cudaStream_t st);
+
+// --- generic (any triangle soup) kernels behind the stateless KernelSpec shims ---
+struct SoupArgs {
+  int32_t nv, nf;
+  const double* pos;
+  const int32_t* tri;
+  const int32_t* csr_ptr;  // vertex -> corners
+  const int32_t* csr_idx;
+  int32_t shift;           // 0 for zero-based indices, -1 for one-based
+};
+cudaError_t launch_soup_surface(const SoupArgs& s, const double* gamma, double* corner /*nf*9*/,
+                                double* facet_e /*nf*/, double* grad /*nv*3, +=*/,
+                                double* energy_out, cudaStream_t st);
+cudaError_t launch_soup_volume(const SoupArgs& s, double factor, double* corner, double* facet_v,
+                               double* grad /*+=*/, double* volume_out, cudaStream_t st);
+cudaError_t launch_soup_curvature(const SoupArgs& s, double* corner /*nf*12*/, double* k_vecs,
+                                  double* vertex_areas, double* weights, double* va0, double* va1,
+                                  double* va2, cudaStream_t st);
+cudaError_t launch_soup_laplacian(const SoupArgs& s, int32_t dim, const double* weights,
+                                  const double* field, double* corner /*nf*3*dim*/, double* out,
+                                  cudaStream_t st);
+cudaError_t launch_grad_cotan(int32_t n, const double* u, const double* v, double* gu, double* gv,
+                              cudaStream_t st);
+cudaError_t launch_p1_divergence(const SoupArgs& s, const double* tilts, double* div, double* area,
+                                 double* g0, double* g1, double* g2, cudaStream_t st);
+cudaError_t launch_sum(const double* x, int64_t n, double scale, double* out, cudaStream_t st);
+
+}  // namespace ms

@@ -1,0 +1,303 @@
+// Per-facet fp64 math of the energy+gradient path, shared by the device kernels
+// and (compiled for the host) by the test-only emulator in tests/emul/.
+//
+// Notation follows SURVEY.md Appendix A: facet (v0,v1,v2), e0=v2-v1, e1=v0-v2,
+// e2=v1-v0 (edge k is opposite corner k), n=e1 x e2, S=|n|, q_k = e_k x n.
+//
+// Reference semantics restated here (file:line relative to the reference root):
+//   surface tension      modules/energy/surface.py:181-221, fortran_kernels/surface_energy.f90:51-98
+//   body volume          geometry/body.py:192-252
+//   curvature data       geometry/curvature.py:254-332, fortran_kernels/tilt_kernels.f90:122-189
+//   effective areas      modules/energy/bending_utils.py:83-171
+//   vertex stage         modules/energy/bending.py:112-158
+//   analytic back-prop   modules/energy/bending_gradient.py:17-175,
+//                        geometry/bending_derivatives.py:48-102
+//   tilt magnitude       modules/energy/tilt.py:99-172
+//   P1 divergence        geometry/tilt_operators.py:158-175, fortran_kernels/tilt_kernels.f90:26-86
+//   bending-tilt         modules/energy/bending_tilt.py:151-482
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define MS_HD __host__ __device__ __forceinline__
+#else
+#define MS_HD inline
+#endif
+
+namespace ms {
+
+struct d3 {
+  double x, y, z;
+};
+
+MS_HD d3 make_d3(double x, double y, double z) { d3 r; r.x = x; r.y = y; r.z = z; return r; }
+MS_HD d3 operator+(d3 a, d3 b) { return make_d3(a.x + b.x, a.y + b.y, a.z + b.z); }
+MS_HD d3 operator-(d3 a, d3 b) { return make_d3(a.x - b.x, a.y - b.y, a.z - b.z); }
+MS_HD d3 operator-(d3 a) { return make_d3(-a.x, -a.y, -a.z); }
+MS_HD d3 operator*(double s, d3 a) { return make_d3(s * a.x, s * a.y, s * a.z); }
+MS_HD double dot(d3 a, d3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+MS_HD d3 cross(d3 a, d3 b) {
+  return make_d3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+// r + s*a
+MS_HD d3 axpy(double s, d3 a, d3 r) { return make_d3(r.x + s * a.x, r.y + s * a.y, r.z + s * a.z); }
+
+// Thresholds of the reference (SURVEY.md §7 hard part 6).
+constexpr double kSurfaceSkip = 1.0e-12;   // surface.py:190: facet skipped if |n| < 1e-12
+constexpr double kAreaClamp = 1.0e-12;     // curvature.py:271: 2A = max(|e1 x e2|, 1e-12)
+constexpr double kCotGradEps = 1.0e-15;    // bending_derivatives.py:62: grad cot = 0 if S <= 1e-15
+constexpr double kP1Clamp = 1.0e-20;       // tilt_operators.py:164: max(|n|^2, 1e-20)
+
+// Geometry every per-facet routine starts from.
+struct FacetGeom {
+  d3 e0, e1, e2, n;
+  double S;  // |n| = twice the facet area
+};
+
+MS_HD FacetGeom facet_geom(d3 v0, d3 v1, d3 v2) {
+  FacetGeom g;
+  g.e0 = v2 - v1;
+  g.e1 = v0 - v2;
+  g.e2 = v1 - v0;
+  g.n = cross(g.e1, g.e2);
+  g.S = sqrt(dot(g.n, g.n));
+  return g;
+}
+
+// ---------------------------------------------------------------------------
+// Pass A: cotangents, curvature-vector and mixed-Voronoi corner contributions.
+// ---------------------------------------------------------------------------
+struct CornerA {
+  d3 K0, K1, K2;        // contributions to the integrated curvature vector K_v
+  double va0, va1, va2; // raw mixed-Voronoi corner areas (A_vor)
+  double ve0, ve1, ve2; // effective corner areas (A_eff, boundary-redistributed)
+  double c0, c1, c2;    // cotangents
+};
+
+MS_HD void mixed_voronoi(double l0, double l1, double l2, double c0, double c1, double c2,
+                         double T, double& va0, double& va1, double& va2) {
+  const bool o0 = c0 < 0.0, o1 = c1 < 0.0, o2 = c2 < 0.0;
+  if (!(o0 || o1 || o2)) {
+    va0 = (l1 * c1 + l2 * c2) * 0.125;
+    va1 = (l2 * c2 + l0 * c0) * 0.125;
+    va2 = (l0 * c0 + l1 * c1) * 0.125;
+  } else {
+    // own-angle T/2, then ANY other obtuse corner overrides with T/4 (curvature.py:308-315)
+    va0 = (o1 || o2) ? 0.25 * T : (o0 ? 0.5 * T : 0.0);
+    va1 = (o0 || o2) ? 0.25 * T : (o1 ? 0.5 * T : 0.0);
+    va2 = (o0 || o1) ? 0.25 * T : (o2 ? 0.5 * T : 0.0);
+  }
+}
+
+// b0..b2: corner is a boundary vertex.
+MS_HD CornerA facet_pass_a(const FacetGeom& g, bool b0, bool b1, bool b2) {
+  CornerA r;
+  const double D = fmax(g.S, kAreaClamp);
+  const double invD = 1.0 / D;
+  r.c0 = -dot(g.e1, g.e2) * invD;
+  r.c1 = -dot(g.e2, g.e0) * invD;
+  r.c2 = -dot(g.e0, g.e1) * invD;
+  // K[i0] += 1/2 (c1 (-e1) + c2 e2), cyclic
+  r.K0 = 0.5 * (r.c2 * g.e2 - r.c1 * g.e1);
+  r.K1 = 0.5 * (r.c0 * g.e0 - r.c2 * g.e2);
+  r.K2 = 0.5 * (r.c1 * g.e1 - r.c0 * g.e0);
+  const double l0 = dot(g.e0, g.e0), l1 = dot(g.e1, g.e1), l2 = dot(g.e2, g.e2);
+  mixed_voronoi(l0, l1, l2, r.c0, r.c1, r.c2, 0.5 * D, r.va0, r.va1, r.va2);
+  // bending_utils.py:101-102 clamps the AREA (not twice the area) for A_eff
+  const double Te = fmax(0.5 * g.S, kAreaClamp);
+  if (Te == 0.5 * D) {
+    r.ve0 = r.va0; r.ve1 = r.va1; r.ve2 = r.va2;
+  } else {
+    mixed_voronoi(l0, l1, l2, r.c0, r.c1, r.c2, Te, r.ve0, r.ve1, r.ve2);
+  }
+  const int nb = int(b0) + int(b1) + int(b2);
+  if (nb == 1 || nb == 2) {
+    // boundary corner areas move, in equal shares, to the interior corners (bending_utils.py:121-153)
+    const double moved = (b0 ? r.ve0 : 0.0) + (b1 ? r.ve1 : 0.0) + (b2 ? r.ve2 : 0.0);
+    const double extra = moved / double(3 - nb);
+    r.ve0 = b0 ? 0.0 : r.ve0 + extra;
+    r.ve1 = b1 ? 0.0 : r.ve1 + extra;
+    r.ve2 = b2 ? 0.0 : r.ve2 + extra;
+  }
+  return r;
+}
+
+// ---------------------------------------------------------------------------
+// Vertex stage: densities and back-propagation seeds (bending.py:112-158).
+// ---------------------------------------------------------------------------
+struct VertexSeed {
+  d3 fK;        // K_dir * kappa*term*ratio
+  double fAe;   // dE/dA_eff
+  double fAv;   // dE/dA_vor
+  double E;     // energy contribution of this vertex
+  double H;     // |K| / (2 A_vor)
+};
+
+// tau_add: extra curvature term added to the Helfrich term at interior vertices
+// (area-averaged divergence for bending_tilt, bending_tilt.py:254-258); 0 for bending.
+// energy_from_vertex=false leaves E=0 (bending_tilt assembles its energy per facet).
+MS_HD VertexSeed vertex_stage(d3 K, double a_vor, double a_eff, double kappa, double c0,
+                              bool boundary, bool willmore, d3 normal, double tau_add) {
+  VertexSeed s;
+  const double safe = fmax(a_vor, 1.0e-12);
+  const double kmag = sqrt(dot(K, K));
+  const double H = kmag / (2.0 * safe);
+  const double ratio = (safe > 1.0e-15) ? a_eff / safe : 0.0;
+  double scale;
+  if (!willmore) {
+    const double term = boundary ? 0.0 : (2.0 * H - c0) + tau_add;
+    s.E = 0.5 * (kappa * (term * term) * a_eff);
+    scale = kappa * term * ratio;
+    s.fAe = 0.5 * kappa * (term * term);
+    s.fAv = -2.0 * kappa * term * ratio * H;
+  } else {
+    const double He = boundary ? 0.0 : H;
+    s.E = kappa * (He * He) * a_eff;
+    scale = kappa * He * ratio;
+    s.fAe = kappa * (He * He);
+    s.fAv = -2.0 * kappa * (He * He) * ratio;
+  }
+  d3 dir = (kmag > 1.0e-15) ? (1.0 / kmag) * K : normal;
+  s.fK = scale * dir;
+  s.H = H;
+  return s;
+}
+
+// ---------------------------------------------------------------------------
+// Pass B: all shape-gradient contributions of one facet to its three corners.
+// ---------------------------------------------------------------------------
+struct BendIn {
+  d3 f0, f1, f2;          // fK at the corners
+  double fe0, fe1, fe2;   // fA_eff
+  double fv0, fv1, fv2;   // fA_vor
+  bool i0, i1, i2;        // corner is an interior vertex
+};
+
+struct CornerG {
+  d3 g0, g1, g2;
+};
+
+// gamma_eff: surface tension of the facet (0 when the surface module is off).
+// area_coeff: extra dE/dT of this facet (tilt magnitude: q_f of tilt.py:146), also
+// multiplied by dT/dx = -q_m/(2S); applied under the same |n| >= 1e-12 rule.
+template <bool BENDING>
+MS_HD CornerG facet_pass_b(const FacetGeom& g, double gamma_eff, double area_coeff,
+                           const BendIn& b, bool approx) {
+  CornerG r;
+  const d3 q0 = cross(g.e0, g.n), q1 = cross(g.e1, g.n), q2 = cross(g.e2, g.n);
+  double Bq = 0.0;  // coefficient of q_m, identical for the three corners
+  // coefficients of e0,e1,e2 per corner
+  double k00 = 0, k01 = 0, k02 = 0, k10 = 0, k11 = 0, k12 = 0, k20 = 0, k21 = 0, k22 = 0;
+  r.g0 = make_d3(0, 0, 0); r.g1 = r.g0; r.g2 = r.g0;
+  const double invS = (g.S > kCotGradEps) ? 1.0 / g.S : 0.0;
+  if (g.S >= kSurfaceSkip) Bq -= 0.5 * (gamma_eff + area_coeff) * invS;
+
+  if (BENDING) {
+    const double D = fmax(g.S, kAreaClamp);
+    const double invD = 1.0 / D;
+    const double C0 = -dot(g.e1, g.e2), C1 = -dot(g.e2, g.e0), C2 = -dot(g.e0, g.e1);
+    const double c0 = C0 * invD, c1 = C1 * invD, c2 = C2 * invD;
+    const d3 d12 = b.f1 - b.f2, d20 = b.f2 - b.f0, d01 = b.f0 - b.f1;
+    // term 1: g -= L fK  (bending_math.py:111-118)
+    r.g0 = 0.5 * (c1 * d20 - c2 * d01);
+    r.g1 = 0.5 * (c2 * d01 - c0 * d12);
+    r.g2 = 0.5 * (c0 * d12 - c1 * d20);
+    if (!approx) {
+      // term 2 weights: dE/dc_k = -1/2 (fK_i - fK_j).(v_i - v_j)
+      double a0 = 0.5 * dot(d12, g.e0);
+      double a1 = 0.5 * dot(d20, g.e1);
+      double a2 = 0.5 * dot(d01, g.e2);
+      // term 3: chi_k = (interior ? fA_eff : mean over interior corners) + fA_vor
+      const int ni = int(b.i0) + int(b.i1) + int(b.i2);
+      const double sum_i = (b.i0 ? b.fe0 : 0.0) + (b.i1 ? b.fe1 : 0.0) + (b.i2 ? b.fe2 : 0.0);
+      const double mean_i = ni > 0 ? sum_i / double(ni) : 0.0;
+      const double x0 = (b.i0 ? b.fe0 : mean_i) + b.fv0;
+      const double x1 = (b.i1 ? b.fe1 : mean_i) + b.fv1;
+      const double x2 = (b.i2 ? b.fe2 : mean_i) + b.fv2;
+      const bool o0 = c0 < 0.0, o1 = c1 < 0.0, o2 = c2 < 0.0;
+      double m0 = 0.0, m1 = 0.0, m2 = 0.0;
+      if (!(o0 || o1 || o2)) {
+        const double l0 = dot(g.e0, g.e0), l1 = dot(g.e1, g.e1), l2 = dot(g.e2, g.e2);
+        a0 += 0.125 * l0 * (x1 + x2);
+        a1 += 0.125 * l1 * (x0 + x2);
+        a2 += 0.125 * l2 * (x0 + x1);
+        m0 = 0.25 * c0 * (x1 + x2);
+        m1 = 0.25 * c1 * (x0 + x2);
+        m2 = 0.25 * c2 * (x0 + x1);
+      } else {
+        // each obtuse corner k adds (1/2 chi_k + 1/4 chi_a + 1/4 chi_b) dT/dx
+        double phi = 0.0;
+        if (o0) phi += 0.5 * x0 + 0.25 * x1 + 0.25 * x2;
+        if (o1) phi += 0.5 * x1 + 0.25 * x0 + 0.25 * x2;
+        if (o2) phi += 0.5 * x2 + 0.25 * x0 + 0.25 * x1;
+        Bq -= 0.5 * phi * invS;
+      }
+      // grad cot_k = 0 when S <= 1e-15 (invS == 0 then)
+      const double invS3 = invS * invS * invS;
+      Bq += (a0 * C0 + a1 * C1 + a2 * C2) * invS3;
+      const double aa0 = a0 * invS, aa1 = a1 * invS, aa2 = a2 * invS;
+      k00 = aa1 - aa2; k01 = aa0 + m1;  k02 = -aa0 - m2;
+      k11 = aa2 - aa0; k12 = aa1 + m2;  k10 = -aa1 - m0;
+      k22 = aa0 - aa1; k20 = aa2 + m0;  k21 = -aa2 - m1;
+    }
+  }
+  r.g0 = axpy(Bq, q0, r.g0);
+  r.g1 = axpy(Bq, q1, r.g1);
+  r.g2 = axpy(Bq, q2, r.g2);
+  if (BENDING && !approx) {
+    r.g0 = axpy(k00, g.e0, axpy(k01, g.e1, axpy(k02, g.e2, r.g0)));
+    r.g1 = axpy(k10, g.e0, axpy(k11, g.e1, axpy(k12, g.e2, r.g1)));
+    r.g2 = axpy(k20, g.e0, axpy(k21, g.e1, axpy(k22, g.e2, r.g2)));
+  }
+  return r;
+}
+
+// Volume: V6 = (v1 x v2).v0 (divide the total by 6); dV/dv0 = (v1 x v2)/6, cyclic.
+MS_HD double facet_volume6(d3 v0, d3 v1, d3 v2) { return dot(cross(v1, v2), v0); }
+
+MS_HD CornerG facet_volume_grad(d3 v0, d3 v1, d3 v2) {
+  CornerG r;
+  const double s = 1.0 / 6.0;
+  r.g0 = s * cross(v1, v2);
+  r.g1 = s * cross(v2, v0);
+  r.g2 = s * cross(v0, v1);
+  return r;
+}
+
+// P1 divergence (ambient_v1): g_k = n x e_k / max(|n|^2, 1e-20), div = sum t_k . g_k.
+struct P1 {
+  d3 g0, g1, g2;
+  double div, area;
+};
+
+MS_HD P1 facet_p1(const FacetGeom& g, d3 t0, d3 t1, d3 t2) {
+  P1 r;
+  const double n2 = dot(g.n, g.n);
+  const double inv = 1.0 / fmax(n2, kP1Clamp);
+  r.g0 = inv * cross(g.n, g.e0);
+  r.g1 = inv * cross(g.n, g.e1);
+  r.g2 = inv * cross(g.n, g.e2);
+  r.div = dot(t0, r.g0) + dot(t1, r.g1) + dot(t2, r.g2);
+  r.area = 0.5 * sqrt(fmax(n2, 0.0));
+  return r;
+}
+
+// grad cot(u,v) (bending_derivatives.py:48-79), for the stateless shim.
+MS_HD void grad_cotan(d3 u, d3 v, d3& gu, d3& gv) {
+  const double C = dot(u, v);
+  const d3 w = cross(u, v);
+  const double S = sqrt(dot(w, w));
+  if (S <= kCotGradEps) {
+    gu = make_d3(0, 0, 0);
+    gv = gu;
+    return;
+  }
+  const double invS = 1.0 / S;
+  const double k = C / (S * S * S);
+  gu = axpy(-k, cross(v, w), invS * v);
+  gv = axpy(-k, cross(w, u), invS * u);
+}
+
+}  // namespace ms

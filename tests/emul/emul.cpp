@@ -1,0 +1,161 @@
+// TEST-ONLY host emulator of the patch kernels.
+//
+// Runs the SAME per-record / per-vertex bodies (ms_patch_body.cuh) and the SAME
+// packer (ms_pack.cpp) as the device path, serially on the host, so that the
+// packing, the round schedule and the fp64 math can be validated against the
+// oracle in the no-GPU test tier.  It is NOT a product path: nothing under
+// membrane_solver_b200/ loads it, and the product fails loudly without a GPU.
+#include <cstring>
+#include <vector>
+
+#include "../../membrane_solver_b200/csrc/ms_patch_body.cuh"
+
+using namespace ms;
+
+namespace {
+int local_row(const PackedMesh& pk, const PatchHeader& h, int j) {
+  return j < h.n_owned ? h.v_lo + j : pk.halo_ids[size_t(h.halo_off) + size_t(j - h.n_owned)];
+}
+}  // namespace
+
+extern "C" {
+
+// scalars8: PS_* sums with the volume slot already divided by 6.
+// Optional outputs may be null.  Returns the pack return code.
+int emul_eval(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* is_boundary,
+              const uint8_t* body_mask, const double* pos, const double* tilts, const double* gamma,
+              double gamma_u, const double* kappa, const double* c0, double kappa_u, double c0_u,
+              double k_tilt, uint32_t modules, uint32_t flags, int32_t want_grad, int32_t threads,
+              int32_t max_owned, int32_t max_local, double* scalars8, double* grad, double* volgrad,
+              double* tilt_grad, double* seeds, double* k_vecs, double* a_vor, double* a_eff,
+              double* e_vertex, int64_t* pack_stats /*[n_patches,n_slots,n_listed,max_rounds,max_local]*/) {
+  PackParams prm;
+  prm.threads = threads;
+  prm.max_owned = max_owned;
+  prm.max_local = max_local;
+  PackedMesh pk;
+  const int rc = pack_patches(nv, nf, tri, body_mask, prm, pk);
+  if (rc) return rc;
+  if (pack_stats) {
+    pack_stats[0] = int64_t(pk.patches.size());
+    pack_stats[1] = int64_t(pk.recs.size());
+    pack_stats[2] = pk.n_listed;
+    pack_stats[3] = pk.max_rounds;
+    pack_stats[4] = pk.max_local;
+  }
+  const bool bending = (modules & MS_MOD_BENDING) != 0;
+  const bool do_tilt = (modules & MS_MOD_TILT) && tilts;
+  const bool willmore = (flags & MS_FLAG_WILLMORE) != 0;
+  std::vector<double> seed_store(size_t(nv) * kSeedStrideBody, 0.0);
+  double total[PS_COUNT] = {0};
+  const int T = threads;
+
+  // ---- pass A -------------------------------------------------------------
+  if (bending || !want_grad) {
+    for (const PatchHeader& h : pk.patches) {
+      const int P = h.n_owned, L = h.n_owned + h.n_halo;
+      std::vector<double> lpos(3 * size_t(L)), t2(size_t(L), 0.0), accK(3 * size_t(P), 0.0),
+          accAv(size_t(P), 0.0), accAe(size_t(P), 0.0), nrm(3 * size_t(P), 0.0);
+      std::vector<uint8_t> bfl(size_t(L), 0);
+      for (int j = 0; j < L; ++j) {
+        const int row = local_row(pk, h, j);
+        for (int k = 0; k < 3; ++k) lpos[3 * size_t(j) + k] = pos[3 * size_t(row) + k];
+        bfl[size_t(j)] = is_boundary ? is_boundary[row] : 0;
+        if (do_tilt) {
+          const double* t = tilts + 3 * size_t(row);
+          t2[size_t(j)] = t[0] * t[0] + t[1] * t[1] + t[2] * t[2];
+        }
+      }
+      LocalA loc;
+      loc.pos = lpos.data(); loc.bfl = bfl.data(); loc.t2 = do_tilt ? t2.data() : nullptr;
+      loc.accK = accK.data(); loc.accAv = accAv.data(); loc.accAe = accAe.data(); loc.P = P;
+      double sums[PS_COUNT] = {0};
+      const int32_t* rp = pk.round_ptr.data() + h.round_off;
+      for (int r = 0; r < h.n_rounds; ++r)
+        for (int t = rp[r]; t < rp[r + 1]; ++t) {
+          if (rp[r + 1] - rp[r] > T) return -90;
+          const size_t slot = size_t(h.slot_off) + size_t(t);
+          const FacetRec rec = pk.recs[slot];
+          const double gam = gamma ? gamma[pk.slot_facet[slot]] : gamma_u;
+          facet_body_a(rec, gam, loc, modules, k_tilt, sums);
+        }
+      if (bending) {
+        bool any_need = false;
+        for (int i = 0; i < P; ++i) any_need |= vertex_needs_normal(loc, i);
+        if (any_need)
+          for (int r = 0; r < h.n_rounds; ++r)
+            for (int t = rp[r]; t < rp[r + 1]; ++t)
+              normal_body(pk.recs[size_t(h.slot_off) + size_t(t)], lpos.data(), nrm.data(), P);
+        for (int i = 0; i < P; ++i) {
+          const size_t row = size_t(h.v_lo) + i;
+          const VertexSeed sd = vertex_body_a(i, loc, nrm.data(), any_need, kappa ? kappa[row] : kappa_u,
+                                              c0 ? c0[row] : c0_u, willmore);
+          sums[PS_E_BENDING] += sd.E;
+          double* o = seed_store.data() + row * kSeedStrideBody;
+          o[0] = sd.fK.x; o[1] = sd.fK.y; o[2] = sd.fK.z; o[3] = sd.fAe; o[4] = sd.fAv; o[5] = 0.0;
+          if (k_vecs) for (int k = 0; k < 3; ++k) k_vecs[3 * row + k] = accK[3 * size_t(i) + k];
+          if (a_vor) a_vor[row] = accAv[size_t(i)];
+          if (a_eff) a_eff[row] = accAe[size_t(i)];
+          if (e_vertex) e_vertex[row] = sd.E;
+        }
+      }
+      for (int k = 0; k < PS_COUNT; ++k) total[k] += sums[k];
+    }
+  }
+  if (seeds) std::memcpy(seeds, seed_store.data(), seed_store.size() * sizeof(double));
+
+  // ---- pass B -------------------------------------------------------------
+  if (want_grad) {
+    const bool scalars_here = !bending;
+    double total_b[PS_COUNT] = {0};
+    for (const PatchHeader& h : pk.patches) {
+      const int P = h.n_owned, L = h.n_owned + h.n_halo;
+      std::vector<double> lpos(3 * size_t(L)), lseed(size_t(kSeedStrideBody) * size_t(L), 0.0),
+          t2(size_t(L), 0.0), accG(3 * size_t(P), 0.0), accV(3 * size_t(P), 0.0), accAb(size_t(P), 0.0);
+      std::vector<uint8_t> bfl(size_t(L), 0);
+      for (int j = 0; j < L; ++j) {
+        const int row = local_row(pk, h, j);
+        for (int k = 0; k < 3; ++k) lpos[3 * size_t(j) + k] = pos[3 * size_t(row) + k];
+        for (int k = 0; k < kSeedStrideBody; ++k)
+          lseed[size_t(kSeedStrideBody) * j + k] = seed_store[size_t(row) * kSeedStrideBody + k];
+        bfl[size_t(j)] = is_boundary ? is_boundary[row] : 0;
+        if (do_tilt) {
+          const double* t = tilts + 3 * size_t(row);
+          t2[size_t(j)] = t[0] * t[0] + t[1] * t[1] + t[2] * t[2];
+        }
+      }
+      LocalB loc;
+      loc.pos = lpos.data(); loc.seed = lseed.data(); loc.bfl = bfl.data();
+      loc.t2 = do_tilt ? t2.data() : nullptr;
+      loc.accG = accG.data(); loc.accV = accV.data(); loc.accAb = accAb.data(); loc.P = P;
+      double sums[PS_COUNT] = {0};
+      const int32_t* rp = pk.round_ptr.data() + h.round_off;
+      for (int r = 0; r < h.n_rounds; ++r)
+        for (int t = rp[r]; t < rp[r + 1]; ++t) {
+          const size_t slot = size_t(h.slot_off) + size_t(t);
+          const FacetRec rec = pk.recs[slot];
+          const double gam = gamma ? gamma[pk.slot_facet[slot]] : gamma_u;
+          if (bending)
+            facet_body_b<true>(rec, gam, loc, modules, flags, k_tilt, scalars_here, sums);
+          else
+            facet_body_b<false>(rec, gam, loc, modules, flags, k_tilt, scalars_here, sums);
+        }
+      for (int j = 0; j < 3 * P; ++j) {
+        const size_t o = size_t(h.v_lo) * 3 + size_t(j);
+        if (grad) grad[o] = accG[size_t(j)];
+        if (volgrad && (modules & MS_MOD_VOLUME)) volgrad[o] = accV[size_t(j)];
+        if (tilt_grad && do_tilt) tilt_grad[o] = k_tilt * tilts[o] * accAb[size_t(j) / 3];
+      }
+      for (int k = 0; k < PS_COUNT; ++k) total_b[k] += sums[k];
+    }
+    if (scalars_here)
+      for (int k = 0; k < PS_COUNT; ++k) total[k] = total_b[k];
+    else
+      total[PS_E_TILT] = total_b[PS_E_TILT];
+  }
+  total[PS_VOLUME6] /= 6.0;
+  for (int k = 0; k < PS_COUNT; ++k) scalars8[k] = total[k];
+  return 0;
+}
+
+}  // extern "C"

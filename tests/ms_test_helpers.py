@@ -25,3 +25,82 @@ def rel_err(a, b):
         return 0.0
     scale = max(float(np.max(np.abs(b))), 1e-300)
     return float(np.max(np.abs(a - b))) / scale
+
+
+# --------------------------------------------------------------------------
+# Host emulator of the patch kernels (tests/emul/emul.cpp) -- TEST ONLY.
+# --------------------------------------------------------------------------
+import ctypes
+import subprocess
+
+MOD_SURFACE, MOD_VOLUME, MOD_BENDING, MOD_TILT, MOD_BENDING_TILT = 1, 2, 4, 8, 16
+FLAG_WILLMORE, FLAG_APPROX = 1, 2
+_EMUL = None
+
+
+def build_emulator():
+    src = os.path.join(ROOT, "tests", "emul", "emul.cpp")
+    csrc = os.path.join(ROOT, "membrane_solver_b200", "csrc")
+    out = os.path.join(ROOT, "tests", "emul", "_build", "libms_emul.so")
+    deps = [src] + [os.path.join(csrc, f) for f in ("ms_pack.cpp", "ms_pack.h", "ms_math.cuh", "ms_patch_body.cuh")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", out, src,
+                               os.path.join(csrc, "ms_pack.cpp")])
+    return out
+
+
+def emulate(pos, tri, *, modules, flags=0, want_grad=True, is_boundary=None, body_mask=None,
+            tilts=None, gamma=None, gamma_u=1.0, kappa=None, c0=None, kappa_u=0.0, c0_u=0.0,
+            k_tilt=0.0, threads=128, max_owned=512, max_local=896):
+    """Run the emulator; returns a dict of scalars and arrays."""
+    global _EMUL
+    if _EMUL is None:
+        _EMUL = ctypes.CDLL(build_emulator())
+        _EMUL.emul_eval.restype = ctypes.c_int
+    pos = np.ascontiguousarray(pos, dtype=np.float64)
+    tri = np.ascontiguousarray(tri, dtype=np.int32)
+    nv, nf = pos.shape[0], tri.shape[0]
+
+    def dptr(a):
+        return None if a is None else a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+    def bptr(a):
+        return None if a is None else a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))
+
+    keep = []
+
+    def f64(a):
+        if a is None:
+            return None
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        keep.append(a)
+        return a
+
+    def u8(a):
+        if a is None:
+            return None
+        a = np.ascontiguousarray(a, dtype=np.uint8)
+        keep.append(a)
+        return a
+
+    scal = np.zeros(8)
+    out = dict(grad=np.zeros((nv, 3)), volgrad=np.zeros((nv, 3)), tilt_grad=np.zeros((nv, 3)),
+               seeds=np.zeros((nv, 6)), k_vecs=np.zeros((nv, 3)), a_vor=np.zeros(nv),
+               a_eff=np.zeros(nv), e_vertex=np.zeros(nv))
+    stats = np.zeros(5, dtype=np.int64)
+    rc = _EMUL.emul_eval(
+        ctypes.c_int32(nv), ctypes.c_int32(nf), tri.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+        bptr(u8(is_boundary)), bptr(u8(body_mask)), dptr(pos), dptr(f64(tilts)), dptr(f64(gamma)),
+        ctypes.c_double(gamma_u), dptr(f64(kappa)), dptr(f64(c0)), ctypes.c_double(kappa_u),
+        ctypes.c_double(c0_u), ctypes.c_double(k_tilt), ctypes.c_uint32(modules), ctypes.c_uint32(flags),
+        ctypes.c_int32(1 if want_grad else 0), ctypes.c_int32(threads), ctypes.c_int32(max_owned),
+        ctypes.c_int32(max_local), dptr(scal), dptr(out["grad"]), dptr(out["volgrad"]),
+        dptr(out["tilt_grad"]), dptr(out["seeds"]), dptr(out["k_vecs"]), dptr(out["a_vor"]),
+        dptr(out["a_eff"]), dptr(out["e_vertex"]), stats.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)))
+    if rc:
+        raise RuntimeError(f"emul_eval failed: {rc}")
+    out.update(E_surface=scal[0], area=scal[1], volume=scal[2], E_bending=scal[3], E_tilt=scal[4],
+               pack=dict(n_patches=int(stats[0]), n_slots=int(stats[1]), n_listed=int(stats[2]),
+                         max_rounds=int(stats[3]), max_local=int(stats[4])))
+    return out

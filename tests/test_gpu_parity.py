@@ -1,0 +1,346 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the
+CPU oracle (pinned to the reference by tests/test_oracle_golden.py) and against
+the golden vectors produced by the real reference.
+
+Tolerance: 1e-12 relative (fp64), measured as max|a-b|/max|b| for vectors
+(BASELINE.json north_star; SURVEY.md section 7 hard part 5).
+"""
+
+import ctypes
+
+import numpy as np
+import pytest
+
+from ms_test_helpers import golden_ids, golden_module_files, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+BENDING_TAGS = {
+    "helfrich_analytic": (0, 0),
+    "helfrich_c0": (0, 0),
+    "helfrich_approx": (0, 2),
+    "willmore_analytic": (1, 0),
+}
+
+
+@pytest.fixture(scope="module")
+def L():
+    from membrane_solver_b200 import _lib
+
+    if _lib.device_count() < 1:
+        pytest.fail("no CUDA device visible: the gpu tier must run on the B200 box")
+    return _lib
+
+
+def _ctx(nv, tri, **kw):
+    from membrane_solver_b200.context import DeviceMesh
+
+    pack = {k: kw.pop(k) for k in ("threads", "max_owned", "max_local") if k in kw}
+    dm = DeviceMesh(0, **pack)
+    dm.set_topology(nv, tri, **kw)
+    return dm
+
+
+def _scalar_close(a, b, tol=TOL):
+    assert abs(a - b) <= tol * max(1.0, abs(b)), (a, b)
+
+
+# ------------------------------------------------------------------ shims
+def test_shim_grad_cotan(L, kernels_golden):
+    g = kernels_golden
+    for tag in ("gc4", "gc17", "gcd"):
+        u, v = np.ascontiguousarray(g[f"{tag}_u"]), np.ascontiguousarray(g[f"{tag}_v"])
+        gu, gv = np.empty_like(u), np.empty_like(v)
+        L.check(L.lib().ms_grad_cotan_batch(u.shape[0], L.dptr(u), L.dptr(v), L.dptr(gu), L.dptr(gv)))
+        assert rel_err(gu, g[f"{tag}_gu"]) <= TOL
+        assert rel_err(gv, g[f"{tag}_gv"]) <= TOL
+    assert np.array_equal(gu[2], np.zeros(3))
+
+
+def test_shim_laplacian(L, kernels_golden):
+    g = kernels_golden
+    w, tri, field = (np.ascontiguousarray(g[k]) for k in ("lap_w", "lap_tri", "lap_field"))
+    out = np.full_like(field, np.nan)
+    L.check(L.lib().ms_apply_beltrami_laplacian(field.shape[1], field.shape[0], tri.shape[0], L.dptr(w),
+                                                L.iptr(tri), L.dptr(field), L.dptr(out), 1))
+    assert rel_err(out, g["lap_out"]) <= TOL
+    # one-based indices give the same answer
+    tri1 = np.ascontiguousarray(tri + 1)
+    out1 = np.empty_like(field)
+    L.check(L.lib().ms_apply_beltrami_laplacian(field.shape[1], field.shape[0], tri.shape[0], L.dptr(w),
+                                                L.iptr(tri1), L.dptr(field), L.dptr(out1), 0))
+    assert np.array_equal(out, out1)
+
+
+def test_shim_p1_divergence(L, kernels_golden):
+    g = kernels_golden
+    pos, tl, tri = (np.ascontiguousarray(g[k]) for k in ("p1_pos", "p1_tilts", "p1_tri"))
+    nf = tri.shape[0]
+    div, area = np.empty(nf), np.empty(nf)
+    g0, g1, g2 = np.empty((nf, 3)), np.empty((nf, 3)), np.empty((nf, 3))
+    L.check(L.lib().ms_p1_triangle_divergence(pos.shape[0], nf, L.dptr(pos), L.dptr(tl), L.iptr(tri),
+                                              L.dptr(div), L.dptr(area), L.dptr(g0), L.dptr(g1), L.dptr(g2), 1))
+    for a, name in ((div, "p1_div"), (area, "p1_area"), (g0, "p1_g0"), (g1, "p1_g1"), (g2, "p1_g2")):
+        assert rel_err(a, g[name]) <= TOL, name
+
+
+def test_shim_curvature_data(L, kernels_golden):
+    g = kernels_golden
+    pos, tri = np.ascontiguousarray(g["cd_pos"]), np.ascontiguousarray(g["cd_tri"])
+    nv, nf = pos.shape[0], tri.shape[0]
+    k, a, w = np.empty((nv, 3)), np.empty(nv), np.empty((nf, 3))
+    va = [np.empty(nf) for _ in range(3)]
+    L.check(L.lib().ms_compute_curvature_data(nv, nf, L.dptr(pos), L.iptr(tri), L.dptr(k), L.dptr(a),
+                                              L.dptr(w), 1, L.dptr(va[0]), L.dptr(va[1]), L.dptr(va[2])))
+    for x, name in ((k, "cd_k"), (a, "cd_a"), (w, "cd_w"), (va[0], "cd_va0"), (va[1], "cd_va1"), (va[2], "cd_va2")):
+        assert rel_err(x, g[name]) <= TOL, name
+    # the optional corner outputs may be omitted (tilt_kernels.f90:96)
+    L.check(L.lib().ms_compute_curvature_data(nv, nf, L.dptr(pos), L.iptr(tri), L.dptr(k), L.dptr(a),
+                                              L.dptr(w), 1, None, None, None))
+    assert rel_err(k, g["cd_k"]) <= TOL
+
+
+def test_shim_surface_soup(L, kernels_golden):
+    """Random triangle soup incl. repeated indices; out-of-range facets are skipped."""
+    from oracle import ref_modules as ref
+
+    g = kernels_golden
+    pos, tri, gamma = (np.ascontiguousarray(g[k]) for k in ("sf_pos", "sf_tri", "sf_gamma"))
+    grad_ref = np.ones_like(pos)
+    e_ref = ref.surface_energy_and_gradient(pos, tri, gamma, grad_ref)
+    grad = np.ones_like(pos)  # the kernel accumulates into the caller's array
+    e = ctypes.c_double(0.0)
+    L.check(L.lib().ms_surface_energy_and_gradient(pos.shape[0], tri.shape[0], L.dptr(pos), L.iptr(tri),
+                                                   L.dptr(gamma), L.dptr(grad), ctypes.byref(e), 1))
+    _scalar_close(e.value, e_ref)
+    assert rel_err(grad, grad_ref) <= TOL
+    bad = tri.copy()
+    bad[3, 1] = pos.shape[0] + 5
+    bad[4, 0] = -1
+    keep = np.ones(len(tri), bool)
+    keep[[3, 4]] = False
+    grad_ref = np.zeros_like(pos)
+    e_ref = ref.surface_energy_and_gradient(pos, tri[keep], gamma[keep], grad_ref)
+    grad = np.zeros_like(pos)
+    L.check(L.lib().ms_surface_energy_and_gradient(pos.shape[0], bad.shape[0], L.dptr(pos), L.iptr(bad),
+                                                   L.dptr(gamma), L.dptr(grad), ctypes.byref(e), 1))
+    _scalar_close(e.value, e_ref)
+    assert rel_err(grad, grad_ref) <= TOL
+
+
+def test_shim_empty_inputs(L):
+    e = ctypes.c_double(1.0)
+    pos = np.zeros((3, 3))
+    grad = np.zeros((3, 3))
+    L.check(L.lib().ms_surface_energy_and_gradient(3, 0, L.dptr(pos), None, None, L.dptr(grad), ctypes.byref(e), 1))
+    assert e.value == 0.0 and not grad.any()
+    L.check(L.lib().ms_grad_cotan_batch(0, None, None, None, None))
+
+
+# ------------------------------------------------------------- golden meshes
+@pytest.mark.parametrize("path", golden_module_files(), ids=golden_ids())
+def test_context_vs_reference_golden(L, path):
+    g = dict(np.load(path))
+    pos, tri = g["pos"], g["tri"]
+    nv, nf = pos.shape[0], tri.shape[0]
+    body = np.zeros(nf, np.uint8)
+    if "body_rows_0" in g:
+        body[g["body_rows_0"]] = 1
+    for pack in (dict(), dict(threads=32, max_owned=16, max_local=120)):
+        dm = _ctx(nv, tri, is_boundary=g["is_boundary"], body_mask=body, **pack)
+        dm.set_surface_tension(g["gamma"])
+        dm.set_positions(pos)
+        dm.set_tilts(g["tilts"])
+        dm.set_tilt_rigidity(float(g["k_tilt"]))
+
+        r = dm.eval(dm.options(L.MOD_SURFACE | L.MOD_VOLUME))
+        _scalar_close(r.e_surface, float(g["E_surface"]))
+        assert rel_err(dm.download(L.ARR_GRAD), g["g_surface"]) <= TOL
+        if "g_volume" in g:
+            _scalar_close(r.volume, float(g["volumes"][0]))
+            assert rel_err(dm.download(L.ARR_VOLGRAD), g["g_volume"][0]) <= TOL
+
+        for tag, (wil, apx) in BENDING_TAGS.items():
+            kappa, c0 = g[f"param_{tag}"]
+            dm.set_bending_params(kappa, c0)
+            r = dm.eval(dm.options(L.MOD_BENDING, flags=wil | apx, diagnostics=True))
+            _scalar_close(r.e_bending, float(g[f"E_bending_{tag}"]))
+            grad = dm.download(L.ARR_GRAD)
+            if apx:
+                grad[g["is_boundary"]] = 0.0  # bending.py:163-167, applied by the host module
+            assert rel_err(grad, g[f"g_bending_{tag}"]) <= 2e-12, tag
+            assert rel_err(dm.download(L.ARR_E_VERTEX), g[f"Ev_bending_{tag}"]) <= TOL
+            # energy-only evaluation (line search) gives the same energy
+            r2 = dm.eval(dm.options(L.MOD_BENDING, flags=wil | apx, want_grad=False))
+            assert r2.e_bending == r.e_bending
+        assert rel_err(dm.download(L.ARR_K_VECS), g["k_vecs"]) <= TOL
+        assert rel_err(dm.download(L.ARR_A_VOR), g["a_vor"]) <= TOL
+        assert rel_err(dm.download(L.ARR_A_EFF), g["a_eff"]) <= TOL
+
+        r = dm.eval(dm.options(L.MOD_TILT))
+        _scalar_close(r.e_tilt, float(g["E_tilt"]))
+        assert rel_err(dm.download(L.ARR_GRAD), g["g_tilt"]) <= TOL
+        assert rel_err(dm.download(L.ARR_TILT_GRAD), g["tg_tilt"]) <= TOL
+        r2 = dm.eval(dm.options(L.MOD_TILT, want_grad=False))
+        _scalar_close(r2.e_tilt, float(g["E_tilt"]))
+        dm.close()
+
+
+def test_minimizer_golden(L, minimizer_golden):
+    """Fused evaluation + KKT / penalty / fixed-mask post-processing against
+    Minimizer.compute_energy_and_gradient_array of the reference."""
+    g = minimizer_golden
+    # cube: surface + volume penalty
+    pos, tri = g["cube_pos"], g["cube_tri"]
+    body = np.zeros(len(tri), np.uint8)
+    body[g["cube_body_rows_0"]] = 1
+    dm = _ctx(pos.shape[0], tri, is_boundary=g["cube_is_boundary"], body_mask=body, fixed_mask=g["cube_fixed"])
+    dm.set_surface_tension(g["cube_gamma"])
+    dm.set_positions(pos)
+    k, v0 = float(g["cube_kvol"]), float(g["cube_body_target_0"])
+    r = dm.eval(dm.options(L.MOD_SURFACE | L.MOD_VOLUME, constraint_mode=1, k_vol=k, v_target=v0, apply_fixed=True))
+    e = r.e_surface + 0.5 * k * (r.volume - v0) ** 2
+    _scalar_close(e, float(g["cube_E"]))
+    assert rel_err(dm.download(L.ARR_GRAD), g["cube_g"]) <= TOL
+    dm.close()
+    # bending cube: bending + lagrange volume constraint
+    pos, tri = g["bcube_pos"], g["bcube_tri"]
+    body = np.zeros(len(tri), np.uint8)
+    body[g["bcube_body_rows_0"]] = 1
+    dm = _ctx(pos.shape[0], tri, is_boundary=g["bcube_is_boundary"], body_mask=body, fixed_mask=g["bcube_fixed"])
+    dm.set_bending_params(float(g["bcube_kappa"]), float(g["bcube_c0"]))
+    dm.set_positions(pos)
+    r = dm.eval(dm.options(L.MOD_BENDING | L.MOD_VOLUME, constraint_mode=0, apply_fixed=True))
+    _scalar_close(r.e_bending, float(g["bcube_E"]))
+    assert rel_err(dm.download(L.ARR_GRAD), g["bcube_g"]) <= 2e-12
+    dm.close()
+
+
+# -------------------------------------------------------------- synthetic
+@pytest.mark.parametrize("n,pack", [(6, dict()), (40, dict()), (40, dict(threads=64, max_owned=200, max_local=420)),
+                                    (120, dict(threads=256, max_owned=1024, max_local=1600))])
+def test_icosphere_fused_vs_oracle(L, n, pack):
+    from membrane_solver_b200.synthetic import icosphere
+    from oracle import ref_modules as ref
+
+    pos, tri = icosphere(n)
+    nv, nf = pos.shape[0], tri.shape[0]
+    ref_out = ref.fused_surface_bending_volume(pos, tri, np.ones(nf), 1.0, 0.05, np.zeros(nv, bool))
+    dm = _ctx(nv, tri, body_mask=np.ones(nf, np.uint8), **pack)
+    dm.set_bending_params(1.0, 0.05)
+    dm.set_positions(pos)
+    r = dm.eval(dm.options(L.MOD_SURFACE | L.MOD_BENDING | L.MOD_VOLUME))
+    _scalar_close(r.e_surface, ref_out["E_surface"])
+    _scalar_close(r.e_bending, ref_out["E_bending"])
+    _scalar_close(r.volume, ref_out["volume"])
+    _scalar_close(r.area, ref_out["area"])
+    g1 = dm.download(L.ARR_GRAD)
+    assert rel_err(g1, ref_out["grad"]) <= TOL
+    assert rel_err(dm.download(L.ARR_VOLGRAD), ref_out["vol_grad"]) <= TOL
+    # run-to-run reproducibility: bitwise identical results
+    r2 = dm.eval(dm.options(L.MOD_SURFACE | L.MOD_BENDING | L.MOD_VOLUME))
+    assert np.array_equal(r.scalars, r2.scalars)
+    assert np.array_equal(g1, dm.download(L.ARR_GRAD))
+    # end-to-end call with host buffers returns the same numbers
+    grad = np.empty_like(pos)
+    volgrad = np.empty_like(pos)
+    r3 = dm.eval_host(dm.options(L.MOD_SURFACE | L.MOD_BENDING | L.MOD_VOLUME), pos, grad=grad, volgrad=volgrad)
+    assert np.array_equal(r3.scalars[:6], r.scalars[:6])
+    assert np.array_equal(grad, g1)
+    dm.close()
+
+
+def test_open_sheet_boundary_and_flat_normals(L):
+    """Open flat sheet: boundary redistribution + |K|=0 normal fallback with c0 != 0."""
+    from membrane_solver_b200.synthetic import open_sheet
+    from oracle import ref_modules as ref
+
+    for jitter in (0.0, 0.08):
+        pos, tri = open_sheet(9, 7, jitter=jitter)
+        nv = pos.shape[0]
+        is_b = ref.boundary_mask_from_triangles(tri, nv)
+        grad_ref = np.zeros_like(pos)
+        e_ref = ref.bending_energy_and_gradient(pos, tri, 1.5, 0.3, is_b, grad_ref)
+        dm = _ctx(nv, tri, is_boundary=is_b, threads=32, max_owned=24, max_local=100)
+        dm.set_bending_params(1.5, 0.3)
+        dm.set_positions(pos)
+        r = dm.eval(dm.options(L.MOD_BENDING))
+        _scalar_close(r.e_bending, e_ref)
+        assert rel_err(dm.download(L.ARR_GRAD), grad_ref) <= TOL
+        dm.close()
+
+
+def test_per_entity_parameters(L):
+    """Per-facet surface tension and per-vertex kappa / c0 arrays."""
+    from membrane_solver_b200.synthetic import icosphere
+    from oracle import ref_modules as ref
+
+    pos, tri = icosphere(12)
+    nv, nf = pos.shape[0], tri.shape[0]
+    rng = np.random.default_rng(11)
+    gamma = rng.uniform(0.5, 2.0, nf)
+    kappa = rng.uniform(0.5, 2.0, nv)
+    c0 = rng.uniform(-0.3, 0.3, nv)
+    grad_ref = np.zeros_like(pos)
+    e_s = ref.surface_energy_and_gradient(pos, tri, gamma, grad_ref)
+    e_b = ref.bending_energy_and_gradient(pos, tri, kappa, c0, np.zeros(nv, bool), grad_ref)
+    dm = _ctx(nv, tri)
+    dm.set_surface_tension(gamma)
+    dm.set_bending_params(kappa, c0)
+    dm.set_positions(pos)
+    r = dm.eval(dm.options(L.MOD_SURFACE | L.MOD_BENDING))
+    _scalar_close(r.e_surface, e_s)
+    _scalar_close(r.e_bending, e_b)
+    assert rel_err(dm.download(L.ARR_GRAD), grad_ref) <= TOL
+    dm.close()
+
+
+def test_degenerate_and_empty_meshes(L):
+    from oracle import ref_modules as ref
+
+    # empty mesh
+    dm = _ctx(0, np.zeros((0, 3), np.int32))
+    r = dm.eval(dm.options(L.MOD_SURFACE | L.MOD_BENDING | L.MOD_VOLUME))
+    assert not r.scalars[:6].any()
+    dm.close()
+    # vertices without facets + degenerate (repeated index, zero area) facets
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0.2], [5, 5, 5], [2, 0, 0]], dtype=float)
+    tri = np.array([[0, 1, 2], [1, 3, 2], [0, 0, 1], [0, 1, 5]], dtype=np.int32)
+    grad_ref = np.zeros_like(pos)
+    e_s = ref.surface_energy_and_gradient(pos, tri, np.ones(4), grad_ref)
+    is_b = ref.boundary_mask_from_triangles(tri[:2], 6)
+    e_b = ref.bending_energy_and_gradient(pos, tri, 1.0, 0.1, is_b, grad_ref)
+    dm = _ctx(6, tri, is_boundary=is_b)
+    dm.set_bending_params(1.0, 0.1)
+    dm.set_positions(pos)
+    r = dm.eval(dm.options(L.MOD_SURFACE | L.MOD_BENDING))
+    _scalar_close(r.e_surface, e_s)
+    _scalar_close(r.e_bending, e_b)
+    assert rel_err(dm.download(L.ARR_GRAD), grad_ref) <= TOL
+    dm.close()
+
+
+def test_trial_positions_energy_only(L):
+    """x + alpha d on the device, energy-only evaluation (line_search.py:358-382)."""
+    from membrane_solver_b200.synthetic import icosphere
+    from oracle import ref_modules as ref
+
+    pos, tri = icosphere(10)
+    nv, nf = pos.shape[0], tri.shape[0]
+    rng = np.random.default_rng(4)
+    d = 0.01 * rng.normal(size=pos.shape)
+    dm = _ctx(nv, tri, body_mask=np.ones(nf, np.uint8))
+    dm.set_bending_params(1.0, 0.0)
+    dm.set_positions(pos)
+    dm.set_direction(d)
+    dm.make_trial(0.37)
+    r = dm.eval(dm.options(L.MOD_SURFACE | L.MOD_BENDING | L.MOD_VOLUME, want_grad=False, use_trial=True))
+    x = pos + 0.37 * d
+    ref_out = ref.fused_surface_bending_volume(x, tri, np.ones(nf), 1.0, 0.0, np.zeros(nv, bool))
+    _scalar_close(r.e_surface, ref_out["E_surface"])
+    _scalar_close(r.e_bending, ref_out["E_bending"])
+    _scalar_close(r.volume, ref_out["volume"])
+    dm.accept_trial()
+    assert rel_err(dm.download(L.ARR_POSITIONS), x) <= 1e-15
+    dm.close()
