@@ -85,11 +85,12 @@ typedef struct ms_pack_info {
   int32_t nv, nf;
   int32_t n_patches, threads;
   int32_t max_owned, max_local, max_rounds;
-  int32_t reserved;
+  int32_t max_slots; /* largest record count of a patch */
   int64_t n_slots;   /* record slots streamed per pass */
   int64_t n_listed;  /* facet listings over all patches (ring facets counted per patch) */
   int64_t n_valid;   /* facets with all indices in range */
   int64_t n_halo;    /* halo vertex references over all patches */
+  int64_t n_round_slots; /* sum over patches of rounds x threads: n_slots / this = lane fill */
 } ms_pack_info;
 
 /* ---- library ------------------------------------------------------------------ */

@@ -56,9 +56,10 @@ class PackInfo(ctypes.Structure):
         ("nv", ctypes.c_int32), ("nf", ctypes.c_int32),
         ("n_patches", ctypes.c_int32), ("threads", ctypes.c_int32),
         ("max_owned", ctypes.c_int32), ("max_local", ctypes.c_int32),
-        ("max_rounds", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("max_rounds", ctypes.c_int32), ("max_slots", ctypes.c_int32),
         ("n_slots", ctypes.c_int64), ("n_listed", ctypes.c_int64),
         ("n_valid", ctypes.c_int64), ("n_halo", ctypes.c_int64),
+        ("n_round_slots", ctypes.c_int64),
     ]
 
 

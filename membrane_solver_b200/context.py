@@ -117,7 +117,7 @@ class DeviceMesh:
     def pack_info(self) -> dict:
         info = L.PackInfo()
         L.check(self._lib.ms_ctx_pack_info(self._h, ctypes.byref(info)))
-        return {name: int(getattr(info, name)) for name, _ in L.PackInfo._fields_ if name != "reserved"}
+        return {name: int(getattr(info, name)) for name, _ in L.PackInfo._fields_}
 
     def patch_ranges(self) -> np.ndarray:
         n = self.pack_info()["n_patches"]

@@ -147,6 +147,8 @@ int fill_launch(ms_ctx* c, const ms_eval_opts* o, ms::PatchLaunch& a) {
   a.threads = c->packed.params.threads;
   a.max_owned = c->packed.max_owned;
   a.max_local = c->packed.max_local;
+  a.max_slots = c->packed.max_slots;
+  a.max_rounds = c->packed.max_rounds;
   if (o->use_trial) {
     if (!c->d_trial.p) return fail(-4, "use_trial set but no trial positions exist (ms_ctx_make_trial)");
     a.pos = c->d_trial.p;
@@ -250,8 +252,14 @@ int ms_ctx_set_pack_params(ms_ctx* c, int32_t threads, int32_t max_owned, int32_
   if (!c) return fail(-1, "null context");
   if (threads < 32 || threads > 256 || threads % 32) return fail(-1, "threads must be a multiple of 32 in [32,256]");
   if (max_owned < 1 || max_local < max_owned || max_local > 65535) return fail(-1, "bad patch sizes");
-  const size_t worst = ms::pass_b_smem_bytes(max_owned, max_local, true, true);
-  if (worst > 227 * 1024) return fail(-1, "patch does not fit in 227 KB of shared memory");
+  ms::PatchLaunch probe;
+  std::memset(&probe, 0, sizeof(probe));
+  probe.max_owned = max_owned;
+  probe.max_local = max_local;
+  probe.max_slots = 3 * max_owned;  // a triangulated patch lists ~2.3 facets per owned vertex
+  probe.max_rounds = 64;
+  if (ms::pass_b_smem_bytes(probe, true, true) > 227 * 1024)
+    return fail(-1, "patch does not fit in 227 KB of shared memory");
   c->pack_params.threads = threads;
   c->pack_params.max_owned = max_owned;
   c->pack_params.max_local = max_local;
@@ -275,13 +283,33 @@ int ms_ctx_set_topology(ms_ctx* c, int32_t nv, int32_t nf, const int32_t* tri,
   for (size_t p = 0; p < np; ++p) c->v_lo[p] = pk.patches[p].v_lo;
   c->v_lo[np] = nv;
 
-  if (int rc = c->d_patches.ensure(np)) return rc;
+  {  // the packed patch must fit the shared-memory window of the widest kernel variant
+    ms::PatchLaunch probe;
+    std::memset(&probe, 0, sizeof(probe));
+    probe.max_owned = pk.max_owned;
+    probe.max_local = pk.max_local;
+    probe.max_slots = pk.max_slots;
+    probe.max_rounds = pk.max_rounds;
+    if (ms::pass_b_smem_bytes(probe, true, true) > 227 * 1024)
+      return fail(-8, "a patch exceeds 227 KB of shared memory; lower max_owned/max_local with ms_ctx_set_pack_params");
+  }
+  if (int rc = c->d_patches.ensure(np + 1)) return rc;
   if (int rc = c->d_halo.ensure(pk.halo_ids.size())) return rc;
   if (int rc = c->d_recs.ensure(pk.recs.size())) return rc;
   if (int rc = c->d_round_ptr.ensure(pk.round_ptr.size())) return rc;
   if (!pk.round_ptr.empty())
     CU(cudaMemcpy(c->d_round_ptr.p, pk.round_ptr.data(), pk.round_ptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-  if (np) CU(cudaMemcpy(c->d_patches.p, pk.patches.data(), np * sizeof(ms::PatchHeader), cudaMemcpyHostToDevice));
+  {  // sentinel header: closes the record range of the last patch
+    std::vector<ms::PatchHeader> hdr(pk.patches);
+    ms::PatchHeader end;
+    std::memset(&end, 0, sizeof(end));
+    end.v_lo = nv;
+    end.halo_off = int32_t(pk.halo_ids.size());
+    end.slot_off = int64_t(pk.recs.size());
+    end.round_off = int32_t(pk.round_ptr.size());
+    hdr.push_back(end);
+    CU(cudaMemcpy(c->d_patches.p, hdr.data(), hdr.size() * sizeof(ms::PatchHeader), cudaMemcpyHostToDevice));
+  }
   if (!pk.halo_ids.empty())
     CU(cudaMemcpy(c->d_halo.p, pk.halo_ids.data(), pk.halo_ids.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   if (!pk.recs.empty())
@@ -334,11 +362,12 @@ int ms_ctx_pack_info(const ms_ctx* c, ms_pack_info* info) {
   info->max_owned = pk.max_owned;
   info->max_local = pk.max_local;
   info->max_rounds = pk.max_rounds;
-  info->reserved = 0;
+  info->max_slots = pk.max_slots;
   info->n_slots = int64_t(pk.recs.size());
   info->n_listed = pk.n_listed;
   info->n_valid = pk.n_valid;
   info->n_halo = int64_t(pk.halo_ids.size());
+  info->n_round_slots = pk.n_round_slots;
   return 0;
 }
 

@@ -48,58 +48,88 @@ __device__ __forceinline__ void block_sum(double (&v)[N], double* red) {
   }
 }
 
-__device__ __forceinline__ int local_row(const PatchHeader& h, const int32_t* __restrict__ halo_ids,
-                                         int j) {
-  return j < h.n_owned ? h.v_lo + j : halo_ids[h.halo_off + j - h.n_owned];
-}
-
-// Stage AoS rows (stride doubles per vertex) of owned + halo vertices into smem.
-// Owned rows are one flat, fully coalesced copy; halo rows are gathered.
-__device__ __forceinline__ void stage_rows(double* dst, const double* __restrict__ src, int stride,
-                                           const PatchHeader& h,
-                                           const int32_t* __restrict__ halo_ids) {
-  const int n_flat = h.n_owned * stride;
-  const double* owned = src + size_t(h.v_lo) * stride;
-  for (int j = threadIdx.x; j < n_flat; j += blockDim.x) dst[j] = owned[j];
-  const int n_h = h.n_halo * stride;
-  for (int j = threadIdx.x; j < n_h; j += blockDim.x) {
-    const int v = j / stride, c = j - v * stride;
-    dst[n_flat + j] = src[size_t(halo_ids[h.halo_off + v]) * stride + c];
+// ---------------------------------------------------------------------------
+// Staging.  Everything a patch needs is brought into shared memory up front with
+// independent, coalesced loads (three dependent latency levels in total: headers ->
+// {round table, records, halo ids, owned rows} -> halo rows), so that the round loop
+// itself touches shared memory only.
+// ---------------------------------------------------------------------------
+// Bump allocator over the dynamic shared memory window (16-byte granularity).
+struct Carver {
+  unsigned char* p;
+  __device__ explicit Carver(void* base) : p(static_cast<unsigned char*>(base)) {}
+  template <typename T>
+  __device__ T* take(size_t count) {
+    T* r = reinterpret_cast<T*>(p);
+    p += (count * sizeof(T) + 15) / 16 * 16;
+    return r;
   }
+};
+inline size_t carve_bytes(size_t count, size_t elem) { return (count * elem + 15) / 16 * 16; }
+
+// Ampere-style asynchronous copies (LDGSTS): global -> shared without a register
+// round trip, so every staging load of a patch is in flight at once.
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(unsigned(__cvta_generic_to_shared(dst))), "l"(src));
+}
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(unsigned(__cvta_generic_to_shared(dst))), "l"(src));
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(unsigned(__cvta_generic_to_shared(dst))), "l"(src));
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
 __device__ __forceinline__ void stage_flags(uint8_t* dst, const uint8_t* __restrict__ src,
-                                            const PatchHeader& h,
-                                            const int32_t* __restrict__ halo_ids) {
+                                            const PatchHeader& h, const int32_t* halo_local) {
   const int L = h.n_owned + h.n_halo;
-  for (int j = threadIdx.x; j < L; j += blockDim.x) dst[j] = src ? src[local_row(h, halo_ids, j)] : uint8_t(0);
+  for (int j = threadIdx.x; j < L; j += blockDim.x) {
+    const int row = j < h.n_owned ? h.v_lo + j : halo_local[j - h.n_owned];
+    dst[j] = src ? src[row] : uint8_t(0);
+  }
 }
 
 __device__ __forceinline__ void stage_tilt_sq(double* dst, const double* __restrict__ tilts,
-                                              const PatchHeader& h,
-                                              const int32_t* __restrict__ halo_ids) {
+                                              const PatchHeader& h, const int32_t* halo_local) {
   const int L = h.n_owned + h.n_halo;
   for (int j = threadIdx.x; j < L; j += blockDim.x) {
-    const size_t row = size_t(local_row(h, halo_ids, j));
+    const size_t row = size_t(j < h.n_owned ? h.v_lo + j : halo_local[j - h.n_owned]);
     const double x = tilts[3 * row], y = tilts[3 * row + 1], z = tilts[3 * row + 2];
     dst[j] = x * x + y * y + z * z;
   }
+}
+
+// First latency level: records, round table, halo ids (all contiguous per patch).
+__device__ __forceinline__ void stage_topology(const PatchLaunch& a, const PatchHeader& h, int n_slots,
+                                               FacetRec* recs, int32_t* rp, int32_t* halo_local) {
+  const FacetRec* src = a.recs + h.slot_off;
+  for (int j = threadIdx.x; j < n_slots; j += blockDim.x) cp_async8(recs + j, src + j);
+  for (int j = threadIdx.x; j <= h.n_rounds; j += blockDim.x) cp_async4(rp + j, a.round_ptr + h.round_off + j);
+  for (int j = threadIdx.x; j < h.n_halo; j += blockDim.x) cp_async4(halo_local + j, a.halo_ids + h.halo_off + j);
 }
 
 constexpr int kRedDoubles = 8 * PS_COUNT;  // block_sum scratch: warps x values
 
 struct SmemA {
   double *pos, *t2, *accK, *accAv, *accAe, *nrm, *red;
+  FacetRec* recs;
+  int32_t *rp, *halo;
   uint8_t* bfl;
-  __device__ SmemA(double* base, int max_owned, int max_local, bool tilt) {
-    pos = base;
-    t2 = pos + 3 * max_local;
-    accK = t2 + (tilt ? max_local : 0);
-    accAv = accK + 3 * max_owned;
-    accAe = accAv + max_owned;
-    nrm = accAe + max_owned;
-    red = nrm + 3 * max_owned;
-    bfl = reinterpret_cast<uint8_t*>(red + kRedDoubles);
+  __device__ SmemA(void* base, const PatchLaunch& a, bool tilt) {
+    Carver c(base);
+    pos = c.take<double>(3 * size_t(a.max_local));
+    t2 = c.take<double>(tilt ? a.max_local : 0);
+    accK = c.take<double>(5 * size_t(a.max_owned));  // K(3P) | A_vor(P) | A_eff(P), zeroed together
+    accAv = accK + 3 * a.max_owned;
+    accAe = accAv + a.max_owned;
+    nrm = c.take<double>(3 * size_t(a.max_owned));
+    red = c.take<double>(kRedDoubles);
+    recs = c.take<FacetRec>(a.max_slots);
+    rp = c.take<int32_t>(size_t(a.max_rounds) + 1);
+    halo = c.take<int32_t>(size_t(a.max_local));
+    bfl = c.take<uint8_t>(a.max_local);
   }
 };
 
@@ -109,18 +139,30 @@ struct SmemA {
 // + bending energy.  Alone, it is the energy-only evaluation of the line search.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kMaxThreads) k_pass_a(PatchLaunch a) {
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int pid = a.patch_begin + blockIdx.x;
   const PatchHeader h = a.patches[pid];
+  const int n_slots = int(a.patches[pid + 1].slot_off - h.slot_off);  // sentinel header at the end
   const int P = h.n_owned;
   const bool do_tilt = (a.modules & MS_MOD_TILT) && a.tilts != nullptr;
   const bool do_bending = a.modules & (MS_MOD_BENDING | MS_MOD_BENDING_TILT);
-  SmemA s(smem, a.max_owned, a.max_local, do_tilt);
+  SmemA s(smem_raw, a, do_tilt);
 
-  stage_rows(s.pos, a.pos, 3, h, a.halo_ids);
-  stage_flags(s.bfl, a.is_boundary, h, a.halo_ids);
-  if (do_tilt) stage_tilt_sq(s.t2, a.tilts, h, a.halo_ids);
+  stage_topology(a, h, n_slots, s.recs, s.rp, s.halo);
+  {  // owned rows do not depend on the halo ids: issue them in the same latency level
+    const double* owned = a.pos + size_t(h.v_lo) * 3;
+    for (int j = threadIdx.x; j < 3 * P; j += blockDim.x) cp_async8(s.pos + j, owned + j);
+  }
   for (int j = threadIdx.x; j < 5 * a.max_owned; j += blockDim.x) s.accK[j] = 0.0;
+  cp_async_wait_all();
+  __syncthreads();
+  for (int j = threadIdx.x; j < 3 * h.n_halo; j += blockDim.x) {
+    const int v = j / 3, c = j - v * 3;
+    cp_async8(s.pos + 3 * P + j, a.pos + size_t(s.halo[v]) * 3 + c);
+  }
+  stage_flags(s.bfl, a.is_boundary, h, s.halo);
+  if (do_tilt) stage_tilt_sq(s.t2, a.tilts, h, s.halo);
+  cp_async_wait_all();
   __syncthreads();
 
   LocalA loc;
@@ -130,15 +172,13 @@ __global__ void __launch_bounds__(kMaxThreads) k_pass_a(PatchLaunch a) {
 #pragma unroll
   for (int k = 0; k < PS_COUNT; ++k) sums[k] = 0.0;
 
-  const FacetRec* recs = a.recs + h.slot_off;
   const double* slot_gamma = a.slot_gamma ? a.slot_gamma + h.slot_off : nullptr;
-  const int32_t* rp = a.round_ptr + h.round_off;
   for (int r = 0; r < h.n_rounds; ++r) {
-    const int beg = rp[r], cnt = rp[r + 1] - beg;
+    const int beg = s.rp[r], cnt = s.rp[r + 1] - beg;
     if (threadIdx.x < cnt) {
       const int slot = beg + threadIdx.x;
       const double gam = slot_gamma ? slot_gamma[slot] : a.gamma_u;
-      facet_body_a(recs[slot], gam, loc, a.modules, a.k_tilt, sums);
+      facet_body_a(s.recs[slot], gam, loc, a.modules, a.k_tilt, sums);
     }
     __syncthreads();
   }
@@ -152,8 +192,8 @@ __global__ void __launch_bounds__(kMaxThreads) k_pass_a(PatchLaunch a) {
       for (int j = threadIdx.x; j < 3 * P; j += blockDim.x) s.nrm[j] = 0.0;
       __syncthreads();
       for (int r = 0; r < h.n_rounds; ++r) {
-        const int beg = rp[r], cnt = rp[r + 1] - beg;
-        if (threadIdx.x < cnt) normal_body(recs[beg + threadIdx.x], s.pos, s.nrm, P);
+        const int beg = s.rp[r], cnt = s.rp[r + 1] - beg;
+        if (threadIdx.x < cnt) normal_body(s.recs[beg + threadIdx.x], s.pos, s.nrm, P);
         __syncthreads();
       }
     }
@@ -164,9 +204,10 @@ __global__ void __launch_bounds__(kMaxThreads) k_pass_a(PatchLaunch a) {
       const VertexSeed sd = vertex_body_a(i, loc, s.nrm, any_need != 0, kap, c0, willmore);
       sums[PS_E_BENDING] += sd.E;
       if (a.seeds) {
-        double* o = a.seeds + row * kSeedStride;
-        o[0] = sd.fK.x; o[1] = sd.fK.y; o[2] = sd.fK.z;
-        o[3] = sd.fAe; o[4] = sd.fAv; o[5] = 0.0;
+        dd2* o = reinterpret_cast<dd2*>(a.seeds + row * kSeedStride);
+        dd2 w0, w1, w2;
+        w0.a = sd.fK.x; w0.b = sd.fK.y; w1.a = sd.fK.z; w1.b = sd.fAe; w2.a = sd.fAv; w2.b = 0.0;
+        o[0] = w0; o[1] = w1; o[2] = w2;
       }
       if (a.k_vecs) {
         a.k_vecs[3 * row] = s.accK[3 * i];
@@ -189,16 +230,22 @@ __global__ void __launch_bounds__(kMaxThreads) k_pass_a(PatchLaunch a) {
 
 struct SmemB {
   double *pos, *seed, *t2, *accG, *accV, *accAb, *red;
+  FacetRec* recs;
+  int32_t *rp, *halo;
   uint8_t* bfl;
-  __device__ SmemB(double* base, int max_owned, int max_local, bool bending, bool tilt) {
-    pos = base;
-    seed = pos + 3 * max_local;
-    t2 = seed + (bending ? kSeedStride * max_local : 0);
-    accG = t2 + (tilt ? max_local : 0);
-    accV = accG + 3 * max_owned;
-    accAb = accV + 3 * max_owned;
-    red = accAb + (tilt ? max_owned : 0);
-    bfl = reinterpret_cast<uint8_t*>(red + kRedDoubles);
+  __device__ SmemB(void* base, const PatchLaunch& a, bool bending, bool tilt) {
+    Carver c(base);
+    seed = c.take<double>(bending ? size_t(kSeedStride) * a.max_local : 0);
+    pos = c.take<double>(3 * size_t(a.max_local));
+    t2 = c.take<double>(tilt ? a.max_local : 0);
+    accG = c.take<double>(6 * size_t(a.max_owned));  // grad(3P) | dV/dx(3P), zeroed together
+    accV = accG + 3 * a.max_owned;
+    accAb = c.take<double>(tilt ? a.max_owned : 0);
+    red = c.take<double>(kRedDoubles);
+    recs = c.take<FacetRec>(a.max_slots);
+    rp = c.take<int32_t>(size_t(a.max_rounds) + 1);
+    halo = c.take<int32_t>(size_t(a.max_local));
+    bfl = c.take<uint8_t>(a.max_local);
   }
 };
 
@@ -207,24 +254,45 @@ struct SmemB {
 // ---------------------------------------------------------------------------
 template <bool BENDING>
 __global__ void __launch_bounds__(kMaxThreads) k_pass_b(PatchLaunch a, bool scalars_here) {
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int pid = a.patch_begin + blockIdx.x;
   const PatchHeader h = a.patches[pid];
+  const int n_slots = int(a.patches[pid + 1].slot_off - h.slot_off);
   const int P = h.n_owned;
   const bool do_volume = a.modules & MS_MOD_VOLUME;
   const bool do_tilt = (a.modules & MS_MOD_TILT) && a.tilts != nullptr;
-  SmemB s(smem, a.max_owned, a.max_local, BENDING, do_tilt);
+  SmemB s(smem_raw, a, BENDING, do_tilt);
 
-  stage_rows(s.pos, a.pos, 3, h, a.halo_ids);
-  if (BENDING) {
-    stage_rows(s.seed, a.seeds, kSeedStride, h, a.halo_ids);
-    stage_flags(s.bfl, a.is_boundary, h, a.halo_ids);
-  }
-  if (do_tilt) {
-    stage_tilt_sq(s.t2, a.tilts, h, a.halo_ids);
-    for (int j = threadIdx.x; j < P; j += blockDim.x) s.accAb[j] = 0.0;
+  stage_topology(a, h, n_slots, s.recs, s.rp, s.halo);
+  {
+    const double* owned = a.pos + size_t(h.v_lo) * 3;
+    for (int j = threadIdx.x; j < 3 * P; j += blockDim.x) cp_async8(s.pos + j, owned + j);
+    if (BENDING) {
+      const dd2* so = reinterpret_cast<const dd2*>(a.seeds) + size_t(h.v_lo) * 3;
+      dd2* sd = reinterpret_cast<dd2*>(s.seed);
+      for (int j = threadIdx.x; j < 3 * P; j += blockDim.x) cp_async16(sd + j, so + j);
+    }
   }
   for (int j = threadIdx.x; j < 6 * a.max_owned; j += blockDim.x) s.accG[j] = 0.0;
+  if (do_tilt)
+    for (int j = threadIdx.x; j < P; j += blockDim.x) s.accAb[j] = 0.0;
+  cp_async_wait_all();
+  __syncthreads();
+  for (int j = threadIdx.x; j < 3 * h.n_halo; j += blockDim.x) {
+    const int v = j / 3, c = j - v * 3;
+    cp_async8(s.pos + 3 * P + j, a.pos + size_t(s.halo[v]) * 3 + c);
+  }
+  if (BENDING) {
+    const dd2* s2 = reinterpret_cast<const dd2*>(a.seeds);
+    dd2* d2 = reinterpret_cast<dd2*>(s.seed) + 3 * P;
+    for (int j = threadIdx.x; j < 3 * h.n_halo; j += blockDim.x) {
+      const int v = j / 3, c = j - v * 3;
+      cp_async16(d2 + j, s2 + size_t(s.halo[v]) * 3 + c);
+    }
+    stage_flags(s.bfl, a.is_boundary, h, s.halo);
+  }
+  if (do_tilt) stage_tilt_sq(s.t2, a.tilts, h, s.halo);
+  cp_async_wait_all();
   __syncthreads();
 
   LocalB loc;
@@ -234,15 +302,13 @@ __global__ void __launch_bounds__(kMaxThreads) k_pass_b(PatchLaunch a, bool scal
 #pragma unroll
   for (int k = 0; k < PS_COUNT; ++k) sums[k] = 0.0;
 
-  const FacetRec* recs = a.recs + h.slot_off;
   const double* slot_gamma = a.slot_gamma ? a.slot_gamma + h.slot_off : nullptr;
-  const int32_t* rp = a.round_ptr + h.round_off;
   for (int r = 0; r < h.n_rounds; ++r) {
-    const int beg = rp[r], cnt = rp[r + 1] - beg;
+    const int beg = s.rp[r], cnt = s.rp[r + 1] - beg;
     if (threadIdx.x < cnt) {
       const int slot = beg + threadIdx.x;
       const double gam = slot_gamma ? slot_gamma[slot] : a.gamma_u;
-      facet_body_b<BENDING>(recs[slot], gam, loc, a.modules, a.flags, a.k_tilt, scalars_here, sums);
+      facet_body_b<BENDING>(s.recs[slot], gam, loc, a.modules, a.flags, a.k_tilt, scalars_here, sums);
     }
     __syncthreads();
   }
@@ -520,17 +586,23 @@ inline int blocks_for(int64_t n, int t) { return int((n + t - 1) / t); }
 
 }  // namespace
 
-size_t pass_a_smem_bytes(int max_owned, int max_local, bool tilt) {
-  size_t d = size_t(3) * max_local + size_t(8) * max_owned + kRedDoubles;
-  if (tilt) d += size_t(max_local);
-  return sizeof(double) * d + size_t(max_local + 15) / 16 * 16;
+static size_t topo_smem_bytes(const PatchLaunch& a) {
+  return carve_bytes(kRedDoubles, 8) + carve_bytes(size_t(a.max_slots), sizeof(FacetRec)) +
+         carve_bytes(size_t(a.max_rounds) + 1, 4) + carve_bytes(size_t(a.max_local), 4) +
+         carve_bytes(size_t(a.max_local), 1);
 }
 
-size_t pass_b_smem_bytes(int max_owned, int max_local, bool bending, bool tilt) {
-  size_t d = size_t(3) * max_local + size_t(6) * max_owned + kRedDoubles;
-  if (bending) d += size_t(kSeedStride) * max_local;
-  if (tilt) d += size_t(max_local) + size_t(max_owned);
-  return sizeof(double) * d + size_t(max_local + 15) / 16 * 16;
+size_t pass_a_smem_bytes(const PatchLaunch& a, bool tilt) {
+  return carve_bytes(3 * size_t(a.max_local), 8) + carve_bytes(tilt ? a.max_local : 0, 8) +
+         carve_bytes(5 * size_t(a.max_owned), 8) + carve_bytes(3 * size_t(a.max_owned), 8) +
+         topo_smem_bytes(a);
+}
+
+size_t pass_b_smem_bytes(const PatchLaunch& a, bool bending, bool tilt) {
+  return carve_bytes(bending ? size_t(kSeedStride) * a.max_local : 0, 8) +
+         carve_bytes(3 * size_t(a.max_local), 8) + carve_bytes(tilt ? a.max_local : 0, 8) +
+         carve_bytes(6 * size_t(a.max_owned), 8) + carve_bytes(tilt ? a.max_owned : 0, 8) +
+         topo_smem_bytes(a);
 }
 
 cudaError_t configure_kernels() {
@@ -544,7 +616,7 @@ cudaError_t configure_kernels() {
 
 cudaError_t launch_pass_a(const PatchLaunch& a, cudaStream_t st) {
   if (a.patch_count <= 0) return cudaSuccess;
-  const size_t smem = pass_a_smem_bytes(a.max_owned, a.max_local, (a.modules & MS_MOD_TILT) && a.tilts);
+  const size_t smem = pass_a_smem_bytes(a, (a.modules & MS_MOD_TILT) && a.tilts);
   k_pass_a<<<a.patch_count, a.threads, smem, st>>>(a);
   return cudaGetLastError();
 }
@@ -552,7 +624,7 @@ cudaError_t launch_pass_a(const PatchLaunch& a, cudaStream_t st) {
 cudaError_t launch_pass_b(const PatchLaunch& a, bool bending, bool scalars_here, cudaStream_t st) {
   if (a.patch_count <= 0) return cudaSuccess;
   const bool tilt = (a.modules & MS_MOD_TILT) && a.tilts;
-  const size_t smem = pass_b_smem_bytes(a.max_owned, a.max_local, bending, tilt);
+  const size_t smem = pass_b_smem_bytes(a, bending, tilt);
   if (bending)
     k_pass_b<true><<<a.patch_count, a.threads, smem, st>>>(a, scalars_here);
   else

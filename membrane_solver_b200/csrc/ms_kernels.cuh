@@ -31,7 +31,7 @@ constexpr int kSeedStride = 6;  // per-vertex pass-A output: fK(3), fA_eff, fA_v
 
 struct PatchLaunch {
   // packed topology (device)
-  const PatchHeader* patches;
+  const PatchHeader* patches;  // n_patches + 1 entries: a sentinel closes the slot ranges
   const int32_t* halo_ids;
   const FacetRec* recs;
   const int32_t* round_ptr;   // per patch: n_rounds+1 slot offsets (see PatchHeader)
@@ -39,6 +39,7 @@ struct PatchLaunch {
   int32_t patch_begin, patch_count;
   int32_t threads;            // CTA size == record slots per round
   int32_t max_owned, max_local;
+  int32_t max_slots, max_rounds;  // largest record count / round count of any patch
   // mesh state (device)
   const double* pos;          // (nv,3)
   const double* tilts;        // (nv,3) or nullptr
@@ -60,8 +61,9 @@ struct PatchLaunch {
   double* e_vertex;   // nv   per-vertex bending energy (bending.compute_energy_array)
 };
 
-size_t pass_a_smem_bytes(int max_owned, int max_local, bool tilt);
-size_t pass_b_smem_bytes(int max_owned, int max_local, bool bending, bool tilt);
+// only max_owned / max_local / max_slots / max_rounds of the launch descriptor are read
+size_t pass_a_smem_bytes(const PatchLaunch& a, bool tilt);
+size_t pass_b_smem_bytes(const PatchLaunch& a, bool bending, bool tilt);
 
 // scalars_here: also sum the per-facet scalars (surface energy, area, volume).
 cudaError_t launch_pass_a(const PatchLaunch& a, cudaStream_t st);

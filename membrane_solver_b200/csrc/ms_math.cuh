@@ -32,6 +32,11 @@ struct d3 {
   double x, y, z;
 };
 
+// 16-byte pair: shared/global rows of 2k doubles move as k vectors
+struct alignas(16) dd2 {
+  double a, b;
+};
+
 MS_HD d3 make_d3(double x, double y, double z) { d3 r; r.x = x; r.y = y; r.z = z; return r; }
 MS_HD d3 operator+(d3 a, d3 b) { return make_d3(a.x + b.x, a.y + b.y, a.z + b.z); }
 MS_HD d3 operator-(d3 a, d3 b) { return make_d3(a.x - b.x, a.y - b.y, a.z - b.z); }

@@ -202,6 +202,8 @@ int pack_patches(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* body
     out.max_owned = std::max(out.max_owned, n);
     out.max_local = std::max(out.max_local, int32_t(n_local));
     out.max_rounds = std::max(out.max_rounds, n_rounds);
+    out.max_slots = std::max(out.max_slots, int32_t(nfac));
+    out.n_round_slots += int64_t(n_rounds) * int64_t(T);
     out.n_listed += int64_t(nfac);
     v_lo += n;
   }

@@ -54,7 +54,8 @@ struct PackedMesh {
   std::vector<FacetRec> recs;
   std::vector<int32_t> round_ptr;   // per patch n_rounds+1 slot offsets relative to slot_off
   std::vector<int32_t> slot_facet;  // facet row of each slot
-  int32_t max_owned = 0, max_local = 0, max_rounds = 0;
+  int32_t max_owned = 0, max_local = 0, max_rounds = 0, max_slots = 0;
+  int64_t n_round_slots = 0;  // sum over patches of n_rounds * threads (lane-fill denominator)
   int64_t n_listed = 0;   // facet listings over all patches (>= valid facets)
   int64_t n_valid = 0;    // facets with all indices in range
 };

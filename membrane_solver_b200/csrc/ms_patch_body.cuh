@@ -127,12 +127,16 @@ MS_HD void facet_body_b(FacetRec rec, double gam, const LocalB& s, uint32_t modu
   }
   BendIn b;
   if (BENDING) {
-    const double* sa = s.seed + kSeedStrideBody * rec.a;
-    const double* sb = s.seed + kSeedStrideBody * rec.b;
-    const double* sc = s.seed + kSeedStrideBody * rec.c;
-    b.f0 = make_d3(sa[0], sa[1], sa[2]); b.fe0 = sa[3]; b.fv0 = sa[4];
-    b.f1 = make_d3(sb[0], sb[1], sb[2]); b.fe1 = sb[3]; b.fv1 = sb[4];
-    b.f2 = make_d3(sc[0], sc[1], sc[2]); b.fe2 = sc[3]; b.fv2 = sc[4];
+    // seed rows are 48 bytes, 16-byte aligned: three vector loads per corner
+    const dd2* sa = reinterpret_cast<const dd2*>(s.seed) + 3 * rec.a;
+    const dd2* sb = reinterpret_cast<const dd2*>(s.seed) + 3 * rec.b;
+    const dd2* sc = reinterpret_cast<const dd2*>(s.seed) + 3 * rec.c;
+    const dd2 a0 = sa[0], a1 = sa[1], a2 = sa[2];
+    const dd2 b0 = sb[0], b1 = sb[1], b2 = sb[2];
+    const dd2 c0 = sc[0], c1 = sc[1], c2 = sc[2];
+    b.f0 = make_d3(a0.a, a0.b, a1.a); b.fe0 = a1.b; b.fv0 = a2.a;
+    b.f1 = make_d3(b0.a, b0.b, b1.a); b.fe1 = b1.b; b.fv1 = b2.a;
+    b.f2 = make_d3(c0.a, c0.b, c1.a); b.fe2 = c1.b; b.fv2 = c2.a;
     b.i0 = !s.bfl[rec.a]; b.i1 = !s.bfl[rec.b]; b.i2 = !s.bfl[rec.c];
   } else {
     b.f0 = b.f1 = b.f2 = make_d3(0, 0, 0);
