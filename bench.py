@@ -215,7 +215,8 @@ def run_b200(args):
     pos, tri = icosphere(n)
     nv, nf = pos.shape[0], tri.shape[0]
     t_gen = time.perf_counter() - t_setup
-    dm = DeviceMesh(local, threads=args.threads, max_owned=args.max_owned, max_local=args.max_local)
+    dm = DeviceMesh(local, threads=args.threads, max_owned=args.max_owned, max_local=args.max_local,
+                    groups=args.groups)
     t0 = time.perf_counter()
     dm.set_topology(nv, tri, body_mask=np.ones(nf, np.uint8))
     t_pack = time.perf_counter() - t0
@@ -225,7 +226,7 @@ def run_b200(args):
     info = dm.pack_info()
     mods = L.MOD_SURFACE | L.MOD_BENDING | L.MOD_VOLUME
     opts = dm.options(mods, constraint_mode=0, apply_fixed=False)
-    launches_per_step = 6  # pass A, pass B, reduce, dots, dots_final, project
+    launches_per_step = 4  # pass A, pass B, reduce, project
 
     sampler = ClockSampler(local)
     for _ in range(max(3, args.warmup)):
@@ -337,6 +338,7 @@ def main():
     ap.add_argument("--threads", type=int, default=None)
     ap.add_argument("--max-owned", type=int, default=None)
     ap.add_argument("--max-local", type=int, default=None)
+    ap.add_argument("--groups", type=int, default=None)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

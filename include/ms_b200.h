@@ -52,7 +52,7 @@ extern "C" {
 #define MS_ARR_POSITIONS     0  /* (nv,3) */
 #define MS_ARR_GRAD          1  /* (nv,3) shape gradient of the enabled modules */
 #define MS_ARR_VOLGRAD       2  /* (nv,3) dV/dx of the body */
-#define MS_ARR_SEEDS         3  /* (nv,6) pass-A vertex results: fK(3), fA_eff, fA_vor, base */
+#define MS_ARR_SEEDS         3  /* (nv,5) pass-A vertex results: fK(3), fA_eff, fA_vor */
 #define MS_ARR_TILTS         4  /* (nv,3) */
 #define MS_ARR_TILT_GRAD     5  /* (nv,3) */
 #define MS_ARR_SCALARS       6  /* 16 */
@@ -90,7 +90,8 @@ typedef struct ms_pack_info {
   int64_t n_listed;  /* facet listings over all patches (ring facets counted per patch) */
   int64_t n_valid;   /* facets with all indices in range */
   int64_t n_halo;    /* halo vertex references over all patches */
-  int64_t n_round_slots; /* sum over patches of rounds x threads: n_slots / this = lane fill */
+  int64_t n_round_slots; /* sum over patches of rounds x threads (= n_slots) */
+  int64_t n_lane_conflicts; /* corner placements sharing a bank residue within a half-warp */
 } ms_pack_info;
 
 /* ---- library ------------------------------------------------------------------ */
@@ -104,6 +105,10 @@ MS_API int ms_ctx_create(int device, ms_ctx** out);
 MS_API int ms_ctx_destroy(ms_ctx* ctx);
 /* patch geometry used by the next ms_ctx_set_topology (defaults 128 / 512 / 896) */
 MS_API int ms_ctx_set_pack_params(ms_ctx* ctx, int32_t threads, int32_t max_owned, int32_t max_local);
+/* thread groups per CTA (default 2): group g computes round r0+g of a patch while the other
+ * groups compute theirs, and the groups then accumulate one after the other; the CTA has
+ * groups*threads threads (clamped to 256) */
+MS_API int ms_ctx_set_groups(ms_ctx* ctx, int32_t groups);
 /* Re-called only after refine / equiangulate / vertex-average changed the topology
  * (commands/mesh_ops.py:21-78).  is_boundary, body_mask, fixed_mask may be NULL. */
 MS_API int ms_ctx_set_topology(ms_ctx* ctx, int32_t nv, int32_t nf, const int32_t* tri,

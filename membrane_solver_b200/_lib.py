@@ -25,7 +25,7 @@ SC_G_G, SC_G_GC, SC_GC_GC, SC_LAMBDA, SC_COUNT = 8, 9, 10, 11, 16
 
 ARR_POSITIONS, ARR_GRAD, ARR_VOLGRAD, ARR_SEEDS, ARR_TILTS, ARR_TILT_GRAD = 0, 1, 2, 3, 4, 5
 ARR_SCALARS, ARR_K_VECS, ARR_A_VOR, ARR_A_EFF, ARR_E_VERTEX, ARR_TRIAL, ARR_DIRECTION = 6, 7, 8, 9, 10, 11, 12
-ARRAY_WIDTH = {ARR_POSITIONS: 3, ARR_GRAD: 3, ARR_VOLGRAD: 3, ARR_SEEDS: 6, ARR_TILTS: 3,
+ARRAY_WIDTH = {ARR_POSITIONS: 3, ARR_GRAD: 3, ARR_VOLGRAD: 3, ARR_SEEDS: 5, ARR_TILTS: 3,
                ARR_TILT_GRAD: 3, ARR_SCALARS: 1, ARR_K_VECS: 3, ARR_A_VOR: 1, ARR_A_EFF: 1,
                ARR_E_VERTEX: 1, ARR_TRIAL: 3, ARR_DIRECTION: 3}
 
@@ -59,7 +59,7 @@ class PackInfo(ctypes.Structure):
         ("max_rounds", ctypes.c_int32), ("max_slots", ctypes.c_int32),
         ("n_slots", ctypes.c_int64), ("n_listed", ctypes.c_int64),
         ("n_valid", ctypes.c_int64), ("n_halo", ctypes.c_int64),
-        ("n_round_slots", ctypes.c_int64),
+        ("n_round_slots", ctypes.c_int64), ("n_lane_conflicts", ctypes.c_int64),
     ]
 
 
@@ -77,6 +77,7 @@ SIGNATURES = {
     "ms_ctx_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_V)]),
     "ms_ctx_destroy": (ctypes.c_int, [_V]),
     "ms_ctx_set_pack_params": (ctypes.c_int, [_V, _i32, _i32, _i32]),
+    "ms_ctx_set_groups": (ctypes.c_int, [_V, _i32]),
     "ms_ctx_set_topology": (ctypes.c_int, [_V, _i32, _i32, _I, _B, _B, _B]),
     "ms_ctx_pack_info": (ctypes.c_int, [_V, ctypes.POINTER(PackInfo)]),
     "ms_ctx_patch_ranges": (ctypes.c_int, [_V, _I]),

@@ -67,7 +67,7 @@ class DeviceMesh:
     """One mesh resident on one GPU."""
 
     def __init__(self, device: int = 0, *, threads: int | None = None, max_owned: int | None = None,
-                 max_local: int | None = None):
+                 max_local: int | None = None, groups: int | None = None):
         self._lib = L.lib()
         handle = ctypes.c_void_p()
         L.check(self._lib.ms_ctx_create(int(device), ctypes.byref(handle)))
@@ -78,6 +78,8 @@ class DeviceMesh:
         if threads is not None or max_owned is not None or max_local is not None:
             L.check(self._lib.ms_ctx_set_pack_params(self._h, int(threads or 128), int(max_owned or 512),
                                                      int(max_local or 896)))
+        if groups is not None:
+            L.check(self._lib.ms_ctx_set_groups(self._h, int(groups)))
 
     # -- lifetime -----------------------------------------------------------
     def close(self) -> None:

@@ -61,11 +61,12 @@ struct ms_ctx {
   bool have_topology = false;
   int32_t nv = 0, nf = 0;
   ms::PackParams pack_params;
+  int32_t groups = 2;  // thread groups per CTA (see PatchLaunch::groups)
   ms::PackedMesh packed;  // recs / slot_facet kept on the host for gamma repacking
   std::vector<int32_t> v_lo;
 
   DevBuf<ms::PatchHeader> d_patches;
-  DevBuf<int32_t> d_halo, d_round_ptr;
+  DevBuf<int32_t> d_halo;
   DevBuf<ms::FacetRec> d_recs;
   DevBuf<double> d_slot_gamma;
   DevBuf<uint8_t> d_boundary, d_fixed;
@@ -140,11 +141,12 @@ int fill_launch(ms_ctx* c, const ms_eval_opts* o, ms::PatchLaunch& a) {
   a.patches = c->d_patches.p;
   a.halo_ids = c->d_halo.p;
   a.recs = c->d_recs.p;
-  a.round_ptr = c->d_round_ptr.p;
   a.slot_gamma = c->has_gamma ? c->d_slot_gamma.p : nullptr;
   a.patch_begin = begin;
   a.patch_count = count;
   a.threads = c->packed.params.threads;
+  a.groups = c->groups;
+  while (a.groups > 1 && a.groups * a.threads > 256) --a.groups;
   a.max_owned = c->packed.max_owned;
   a.max_local = c->packed.max_local;
   a.max_slots = c->packed.max_slots;
@@ -266,6 +268,13 @@ int ms_ctx_set_pack_params(ms_ctx* c, int32_t threads, int32_t max_owned, int32_
   return 0;
 }
 
+int ms_ctx_set_groups(ms_ctx* c, int32_t groups) {
+  if (!c) return fail(-1, "null context");
+  if (groups < 1 || groups > 8) return fail(-1, "groups must be in [1,8]");
+  c->groups = groups;
+  return 0;
+}
+
 int ms_ctx_set_topology(ms_ctx* c, int32_t nv, int32_t nf, const int32_t* tri,
                         const uint8_t* is_boundary, const uint8_t* body_mask,
                         const uint8_t* fixed_mask) {
@@ -296,9 +305,6 @@ int ms_ctx_set_topology(ms_ctx* c, int32_t nv, int32_t nf, const int32_t* tri,
   if (int rc = c->d_patches.ensure(np + 1)) return rc;
   if (int rc = c->d_halo.ensure(pk.halo_ids.size())) return rc;
   if (int rc = c->d_recs.ensure(pk.recs.size())) return rc;
-  if (int rc = c->d_round_ptr.ensure(pk.round_ptr.size())) return rc;
-  if (!pk.round_ptr.empty())
-    CU(cudaMemcpy(c->d_round_ptr.p, pk.round_ptr.data(), pk.round_ptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   {  // sentinel header: closes the record range of the last patch
     std::vector<ms::PatchHeader> hdr(pk.patches);
     ms::PatchHeader end;
@@ -306,7 +312,6 @@ int ms_ctx_set_topology(ms_ctx* c, int32_t nv, int32_t nf, const int32_t* tri,
     end.v_lo = nv;
     end.halo_off = int32_t(pk.halo_ids.size());
     end.slot_off = int64_t(pk.recs.size());
-    end.round_off = int32_t(pk.round_ptr.size());
     hdr.push_back(end);
     CU(cudaMemcpy(c->d_patches.p, hdr.data(), hdr.size() * sizeof(ms::PatchHeader), cudaMemcpyHostToDevice));
   }
@@ -368,6 +373,7 @@ int ms_ctx_pack_info(const ms_ctx* c, ms_pack_info* info) {
   info->n_valid = pk.n_valid;
   info->n_halo = int64_t(pk.halo_ids.size());
   info->n_round_slots = pk.n_round_slots;
+  info->n_lane_conflicts = pk.n_lane_conflicts;
   return 0;
 }
 
@@ -516,12 +522,13 @@ int ms_ctx_eval_finish(ms_ctx* c, const ms_eval_opts* o) {
   if (int rc = check_ctx(c, true)) return rc;
   if (!o) return fail(-1, "null options");
   const int n_patches = int(c->packed.patches.size());
-  CU(ms::launch_reduce_partials(c->d_partials.p, n_patches, c->d_scalars.p, c->stream));
+  const int begin = o->patch_count < 0 ? 0 : o->patch_begin;
+  const int count = o->patch_count < 0 ? n_patches : o->patch_count;
+  if (begin < 0 || count < 0 || begin + count > n_patches) return fail(-3, "patch range out of bounds");
+  // energies, area, volume and (after pass B) <g,g>, <g,gC>, <gC,gC> in one fixed-order sum
+  CU(ms::launch_reduce_partials(c->d_partials.p, begin, count, c->d_scalars.p, c->stream));
   if (o->want_grad && (o->constraint_mode >= 0 || o->apply_fixed)) {
     const double* gc = (o->constraint_mode >= 0 && (o->modules & MS_MOD_VOLUME)) ? c->d_volgrad.p : nullptr;
-    if (gc && o->constraint_mode == 0)
-      CU(ms::launch_dots(c->d_grad.p, gc, 3 * int64_t(c->nv), c->d_dot_partials.p, kDotBlocks,
-                         c->d_scalars.p, c->stream));
     const uint8_t* fixed = (o->apply_fixed && c->has_fixed) ? c->d_fixed.p : nullptr;
     if (gc || fixed)
       CU(ms::launch_project(c->d_grad.p, gc, fixed, c->nv, c->d_scalars.p, o->constraint_mode,

@@ -18,8 +18,10 @@ namespace ms {
 namespace {
 
 constexpr int kMaxThreads = 256;
+constexpr int kMaxWarps = kMaxThreads / 32;
 static_assert(kSeedStride == kSeedStrideBody, "seed row layout");
-static_assert(int(SC_E_BENDING_TILT) == int(PS_E_BENDING_TILT) && kPartialStride == PS_COUNT, "partial layout");
+static_assert(int(SC_E_BENDING_TILT) == int(PS_E_BENDING_TILT) && int(SC_G_G) == int(PS_G_G) &&
+                  int(SC_GC_GC) == int(PS_GC_GC) && kPartialStride == PS_COUNT, "partial layout");
 
 // Deterministic block sum of N values per thread; result valid in thread 0.
 template <int N>
@@ -103,19 +105,18 @@ __device__ __forceinline__ void stage_tilt_sq(double* dst, const double* __restr
 
 // First latency level: records, round table, halo ids (all contiguous per patch).
 __device__ __forceinline__ void stage_topology(const PatchLaunch& a, const PatchHeader& h, int n_slots,
-                                               FacetRec* recs, int32_t* rp, int32_t* halo_local) {
+                                               FacetRec* recs, int32_t* halo_local) {
   const FacetRec* src = a.recs + h.slot_off;
   for (int j = threadIdx.x; j < n_slots; j += blockDim.x) cp_async8(recs + j, src + j);
-  for (int j = threadIdx.x; j <= h.n_rounds; j += blockDim.x) cp_async4(rp + j, a.round_ptr + h.round_off + j);
   for (int j = threadIdx.x; j < h.n_halo; j += blockDim.x) cp_async4(halo_local + j, a.halo_ids + h.halo_off + j);
 }
 
-constexpr int kRedDoubles = 8 * PS_COUNT;  // block_sum scratch: warps x values
+constexpr int kRedDoubles = kMaxWarps * PS_COUNT;  // block_sum scratch: warps x values
 
 struct SmemA {
   double *pos, *t2, *accK, *accAv, *accAe, *nrm, *red;
   FacetRec* recs;
-  int32_t *rp, *halo;
+  int32_t* halo;
   uint8_t* bfl;
   __device__ SmemA(void* base, const PatchLaunch& a, bool tilt) {
     Carver c(base);
@@ -127,7 +128,6 @@ struct SmemA {
     nrm = c.take<double>(3 * size_t(a.max_owned));
     red = c.take<double>(kRedDoubles);
     recs = c.take<FacetRec>(a.max_slots);
-    rp = c.take<int32_t>(size_t(a.max_rounds) + 1);
     halo = c.take<int32_t>(size_t(a.max_local));
     bfl = c.take<uint8_t>(a.max_local);
   }
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(kMaxThreads) k_pass_a(PatchLaunch a) {
   const bool do_bending = a.modules & (MS_MOD_BENDING | MS_MOD_BENDING_TILT);
   SmemA s(smem_raw, a, do_tilt);
 
-  stage_topology(a, h, n_slots, s.recs, s.rp, s.halo);
+  stage_topology(a, h, n_slots, s.recs, s.halo);
   {  // owned rows do not depend on the halo ids: issue them in the same latency level
     const double* owned = a.pos + size_t(h.v_lo) * 3;
     for (int j = threadIdx.x; j < 3 * P; j += blockDim.x) cp_async8(s.pos + j, owned + j);
@@ -173,15 +173,28 @@ __global__ void __launch_bounds__(kMaxThreads) k_pass_a(PatchLaunch a) {
   for (int k = 0; k < PS_COUNT; ++k) sums[k] = 0.0;
 
   const double* slot_gamma = a.slot_gamma ? a.slot_gamma + h.slot_off : nullptr;
-  for (int r = 0; r < h.n_rounds; ++r) {
-    const int beg = s.rp[r], cnt = s.rp[r + 1] - beg;
-    if (threadIdx.x < cnt) {
-      const int slot = beg + threadIdx.x;
-      const double gam = slot_gamma ? slot_gamma[slot] : a.gamma_u;
-      facet_body_a(s.recs[slot], gam, loc, a.modules, a.k_tilt, sums);
+  const int grp = threadIdx.x / a.threads, lane = threadIdx.x - grp * a.threads;
+  for (int r0 = 0; r0 < h.n_rounds; r0 += a.groups) {
+    // every group computes one round (reads only), then the groups accumulate in turn
+    const int r = r0 + grp;
+    bool act = false;
+    FacetRec rec;
+    CornerA ca;
+    if (r < h.n_rounds) {
+      const int slot = r * a.threads + lane;
+      rec = s.recs[slot];
+      if (rec.flags & REC_VALID) {
+        act = true;
+        const double gam = slot_gamma ? slot_gamma[slot] : a.gamma_u;
+        ca = facet_compute_a(rec, gam, loc, a.modules, a.k_tilt, sums);
+      }
     }
-    __syncthreads();
+    for (int g = 0; g < a.groups; ++g) {
+      __syncthreads();
+      if (act && g == grp) facet_accumulate_a(rec, ca, loc, a.modules);
+    }
   }
+  __syncthreads();
 
   if (do_bending) {
     const bool willmore = a.flags & MS_FLAG_WILLMORE;
@@ -191,9 +204,11 @@ __global__ void __launch_bounds__(kMaxThreads) k_pass_a(PatchLaunch a) {
     if (any_need) {
       for (int j = threadIdx.x; j < 3 * P; j += blockDim.x) s.nrm[j] = 0.0;
       __syncthreads();
-      for (int r = 0; r < h.n_rounds; ++r) {
-        const int beg = s.rp[r], cnt = s.rp[r + 1] - beg;
-        if (threadIdx.x < cnt) normal_body(s.recs[beg + threadIdx.x], s.pos, s.nrm, P);
+      for (int r = 0; r < h.n_rounds; ++r) {  // rare path (flat patches): group 0 only
+        if (grp == 0) {
+          const FacetRec rec = s.recs[r * a.threads + lane];
+          if (rec.flags & REC_VALID) normal_body(rec, s.pos, s.nrm, P);
+        }
         __syncthreads();
       }
     }
@@ -204,10 +219,8 @@ __global__ void __launch_bounds__(kMaxThreads) k_pass_a(PatchLaunch a) {
       const VertexSeed sd = vertex_body_a(i, loc, s.nrm, any_need != 0, kap, c0, willmore);
       sums[PS_E_BENDING] += sd.E;
       if (a.seeds) {
-        dd2* o = reinterpret_cast<dd2*>(a.seeds + row * kSeedStride);
-        dd2 w0, w1, w2;
-        w0.a = sd.fK.x; w0.b = sd.fK.y; w1.a = sd.fK.z; w1.b = sd.fAe; w2.a = sd.fAv; w2.b = 0.0;
-        o[0] = w0; o[1] = w1; o[2] = w2;
+        double* o = a.seeds + row * kSeedStride;
+        o[0] = sd.fK.x; o[1] = sd.fK.y; o[2] = sd.fK.z; o[3] = sd.fAe; o[4] = sd.fAv;
       }
       if (a.k_vecs) {
         a.k_vecs[3 * row] = s.accK[3 * i];
@@ -231,7 +244,7 @@ __global__ void __launch_bounds__(kMaxThreads) k_pass_a(PatchLaunch a) {
 struct SmemB {
   double *pos, *seed, *t2, *accG, *accV, *accAb, *red;
   FacetRec* recs;
-  int32_t *rp, *halo;
+  int32_t* halo;
   uint8_t* bfl;
   __device__ SmemB(void* base, const PatchLaunch& a, bool bending, bool tilt) {
     Carver c(base);
@@ -243,7 +256,6 @@ struct SmemB {
     accAb = c.take<double>(tilt ? a.max_owned : 0);
     red = c.take<double>(kRedDoubles);
     recs = c.take<FacetRec>(a.max_slots);
-    rp = c.take<int32_t>(size_t(a.max_rounds) + 1);
     halo = c.take<int32_t>(size_t(a.max_local));
     bfl = c.take<uint8_t>(a.max_local);
   }
@@ -253,7 +265,7 @@ struct SmemB {
 // Pass B: shape gradient of surface + bending (+ tilt magnitude) and dV/dx.
 // ---------------------------------------------------------------------------
 template <bool BENDING>
-__global__ void __launch_bounds__(kMaxThreads) k_pass_b(PatchLaunch a, bool scalars_here) {
+__global__ void __launch_bounds__(kMaxThreads, 2) k_pass_b(PatchLaunch a, bool scalars_here) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int pid = a.patch_begin + blockIdx.x;
   const PatchHeader h = a.patches[pid];
@@ -263,14 +275,13 @@ __global__ void __launch_bounds__(kMaxThreads) k_pass_b(PatchLaunch a, bool scal
   const bool do_tilt = (a.modules & MS_MOD_TILT) && a.tilts != nullptr;
   SmemB s(smem_raw, a, BENDING, do_tilt);
 
-  stage_topology(a, h, n_slots, s.recs, s.rp, s.halo);
+  stage_topology(a, h, n_slots, s.recs, s.halo);
   {
     const double* owned = a.pos + size_t(h.v_lo) * 3;
     for (int j = threadIdx.x; j < 3 * P; j += blockDim.x) cp_async8(s.pos + j, owned + j);
     if (BENDING) {
-      const dd2* so = reinterpret_cast<const dd2*>(a.seeds) + size_t(h.v_lo) * 3;
-      dd2* sd = reinterpret_cast<dd2*>(s.seed);
-      for (int j = threadIdx.x; j < 3 * P; j += blockDim.x) cp_async16(sd + j, so + j);
+      const double* so = a.seeds + size_t(h.v_lo) * kSeedStride;
+      for (int j = threadIdx.x; j < kSeedStride * P; j += blockDim.x) cp_async8(s.seed + j, so + j);
     }
   }
   for (int j = threadIdx.x; j < 6 * a.max_owned; j += blockDim.x) s.accG[j] = 0.0;
@@ -283,11 +294,10 @@ __global__ void __launch_bounds__(kMaxThreads) k_pass_b(PatchLaunch a, bool scal
     cp_async8(s.pos + 3 * P + j, a.pos + size_t(s.halo[v]) * 3 + c);
   }
   if (BENDING) {
-    const dd2* s2 = reinterpret_cast<const dd2*>(a.seeds);
-    dd2* d2 = reinterpret_cast<dd2*>(s.seed) + 3 * P;
-    for (int j = threadIdx.x; j < 3 * h.n_halo; j += blockDim.x) {
-      const int v = j / 3, c = j - v * 3;
-      cp_async16(d2 + j, s2 + size_t(s.halo[v]) * 3 + c);
+    double* d2 = s.seed + kSeedStride * P;
+    for (int j = threadIdx.x; j < kSeedStride * h.n_halo; j += blockDim.x) {
+      const int v = j / kSeedStride, c = j - v * kSeedStride;
+      cp_async8(d2 + j, a.seeds + size_t(s.halo[v]) * kSeedStride + c);
     }
     stage_flags(s.bfl, a.is_boundary, h, s.halo);
   }
@@ -303,22 +313,43 @@ __global__ void __launch_bounds__(kMaxThreads) k_pass_b(PatchLaunch a, bool scal
   for (int k = 0; k < PS_COUNT; ++k) sums[k] = 0.0;
 
   const double* slot_gamma = a.slot_gamma ? a.slot_gamma + h.slot_off : nullptr;
-  for (int r = 0; r < h.n_rounds; ++r) {
-    const int beg = s.rp[r], cnt = s.rp[r + 1] - beg;
-    if (threadIdx.x < cnt) {
-      const int slot = beg + threadIdx.x;
-      const double gam = slot_gamma ? slot_gamma[slot] : a.gamma_u;
-      facet_body_b<BENDING>(s.recs[slot], gam, loc, a.modules, a.flags, a.k_tilt, scalars_here, sums);
+  const int grp = threadIdx.x / a.threads, lane = threadIdx.x - grp * a.threads;
+  for (int r0 = 0; r0 < h.n_rounds; r0 += a.groups) {
+    const int r = r0 + grp;
+    bool act = false;
+    FacetRec rec;
+    FacetOutB out;
+    if (r < h.n_rounds) {
+      const int slot = r * a.threads + lane;
+      rec = s.recs[slot];
+      if (rec.flags & REC_VALID) {
+        act = true;
+        const double gam = slot_gamma ? slot_gamma[slot] : a.gamma_u;
+        out = facet_compute_b<BENDING>(rec, gam, loc, a.modules, a.flags, a.k_tilt, scalars_here, sums);
+      }
     }
-    __syncthreads();
+    for (int g = 0; g < a.groups; ++g) {
+      __syncthreads();
+      if (act && g == grp) facet_accumulate_b(rec, out, loc);
+    }
   }
+  __syncthreads();
 
-  // owned-vertex results leave as flat, coalesced copies
+  // owned-vertex results leave as flat, coalesced copies; the dot products of the KKT
+  // projection (constraint_manager.py:294-301) are summed on the way out
   double* gout = a.grad + size_t(h.v_lo) * 3;
-  for (int j = threadIdx.x; j < 3 * P; j += blockDim.x) gout[j] = s.accG[j];
-  if (do_volume && a.volgrad) {
-    double* vout = a.volgrad + size_t(h.v_lo) * 3;
-    for (int j = threadIdx.x; j < 3 * P; j += blockDim.x) vout[j] = s.accV[j];
+  const bool vol_out = do_volume && a.volgrad;
+  double* vout = vol_out ? a.volgrad + size_t(h.v_lo) * 3 : nullptr;
+  for (int j = threadIdx.x; j < 3 * P; j += blockDim.x) {
+    const double gj = s.accG[j];
+    gout[j] = gj;
+    sums[PS_G_G] += gj * gj;
+    if (vol_out) {
+      const double vj = s.accV[j];
+      vout[j] = vj;
+      sums[PS_G_GC] += gj * vj;
+      sums[PS_GC_GC] += vj * vj;
+    }
   }
   if (do_tilt && a.tilt_grad) {
     // tilt.py:163-170: dE/dt_v = k_t t_v A_bary(v)
@@ -334,25 +365,29 @@ __global__ void __launch_bounds__(kMaxThreads) k_pass_b(PatchLaunch a, bool scal
       for (int k = 0; k < PS_COUNT; ++k) p[k] = sums[k];
     } else {
       p[PS_E_TILT] = sums[PS_E_TILT];
+      p[PS_G_G] = sums[PS_G_G];
+      p[PS_G_GC] = sums[PS_G_GC];
+      p[PS_GC_GC] = sums[PS_GC_GC];
     }
   }
 }
 
-// Fixed-order reduction of the per-patch partial sums (one CTA).
-__global__ void __launch_bounds__(256) k_reduce_partials(const double* __restrict__ partials,
-                                                         int n_patches, double* scalars) {
-  __shared__ double red[32 * kPartialStride];
-  double v[kPartialStride];
-#pragma unroll
-  for (int k = 0; k < kPartialStride; ++k) v[k] = 0.0;
-  for (int p = threadIdx.x; p < n_patches; p += blockDim.x) {
-#pragma unroll
-    for (int k = 0; k < kPartialStride; ++k) v[k] += partials[size_t(p) * kPartialStride + k];
-  }
-  block_sum<kPartialStride>(v, red);
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int k = 0; k < kPartialStride; ++k) scalars[k] = (k == PS_VOLUME6) ? v[k] / 6.0 : v[k];
+// Fixed-order reduction of the per-patch partial sums (one CTA of 64 x 12 threads:
+// thread (row, k) sums slot k of patches row, row+64, ... -- coalesced -- and 12 threads
+// then add the 64 row sums in index order).
+constexpr int kReduceRows = 64;
+__global__ void __launch_bounds__(kReduceRows* kPartialStride)
+    k_reduce_partials(const double* __restrict__ partials, int begin, int count, double* scalars) {
+  __shared__ double part[kReduceRows][kPartialStride];
+  const int k = threadIdx.x % kPartialStride, row = threadIdx.x / kPartialStride;
+  double v = 0.0;
+  for (int p = row; p < count; p += kReduceRows) v += partials[size_t(begin + p) * kPartialStride + k];
+  part[row][k] = v;
+  __syncthreads();
+  if (threadIdx.x < kPartialStride) {
+    double t = 0.0;
+    for (int r = 0; r < kReduceRows; ++r) t += part[r][threadIdx.x];
+    scalars[threadIdx.x] = (threadIdx.x == PS_VOLUME6) ? t / 6.0 : t;
   }
 }
 
@@ -588,7 +623,7 @@ inline int blocks_for(int64_t n, int t) { return int((n + t - 1) / t); }
 
 static size_t topo_smem_bytes(const PatchLaunch& a) {
   return carve_bytes(kRedDoubles, 8) + carve_bytes(size_t(a.max_slots), sizeof(FacetRec)) +
-         carve_bytes(size_t(a.max_rounds) + 1, 4) + carve_bytes(size_t(a.max_local), 4) +
+         carve_bytes(size_t(a.max_local), 4) +
          carve_bytes(size_t(a.max_local), 1);
 }
 
@@ -617,7 +652,7 @@ cudaError_t configure_kernels() {
 cudaError_t launch_pass_a(const PatchLaunch& a, cudaStream_t st) {
   if (a.patch_count <= 0) return cudaSuccess;
   const size_t smem = pass_a_smem_bytes(a, (a.modules & MS_MOD_TILT) && a.tilts);
-  k_pass_a<<<a.patch_count, a.threads, smem, st>>>(a);
+  k_pass_a<<<a.patch_count, a.threads * a.groups, smem, st>>>(a);
   return cudaGetLastError();
 }
 
@@ -626,15 +661,15 @@ cudaError_t launch_pass_b(const PatchLaunch& a, bool bending, bool scalars_here,
   const bool tilt = (a.modules & MS_MOD_TILT) && a.tilts;
   const size_t smem = pass_b_smem_bytes(a, bending, tilt);
   if (bending)
-    k_pass_b<true><<<a.patch_count, a.threads, smem, st>>>(a, scalars_here);
+    k_pass_b<true><<<a.patch_count, a.threads * a.groups, smem, st>>>(a, scalars_here);
   else
-    k_pass_b<false><<<a.patch_count, a.threads, smem, st>>>(a, scalars_here);
+    k_pass_b<false><<<a.patch_count, a.threads * a.groups, smem, st>>>(a, scalars_here);
   return cudaGetLastError();
 }
 
-cudaError_t launch_reduce_partials(const double* partials, int n_patches, double* scalars,
+cudaError_t launch_reduce_partials(const double* partials, int begin, int count, double* scalars,
                                    cudaStream_t st) {
-  k_reduce_partials<<<1, 256, 0, st>>>(partials, n_patches, scalars);
+  k_reduce_partials<<<1, kReduceRows * kPartialStride, 0, st>>>(partials, begin, count, scalars);
   return cudaGetLastError();
 }
 

@@ -25,19 +25,20 @@ enum ScalarSlot : int {
   SC_LAMBDA = 11,      // KKT multiplier applied
   SC_COUNT = 16,
 };
-constexpr int kPartialStride = 8;  // per-patch partial sums: slots 0..7 above
+constexpr int kPartialStride = 12;  // per-patch partial sums: slots 0..11 above
 
-constexpr int kSeedStride = 6;  // per-vertex pass-A output: fK(3), fA_eff, fA_vor, base term
+constexpr int kSeedStride = 5;  // per-vertex pass-A output: fK(3), fA_eff, fA_vor (odd stride: no bank conflicts)
 
 struct PatchLaunch {
   // packed topology (device)
   const PatchHeader* patches;  // n_patches + 1 entries: a sentinel closes the slot ranges
   const int32_t* halo_ids;
   const FacetRec* recs;
-  const int32_t* round_ptr;   // per patch: n_rounds+1 slot offsets (see PatchHeader)
   const double* slot_gamma;   // per-slot surface tension, or nullptr -> gamma_u
   int32_t patch_begin, patch_count;
-  int32_t threads;            // CTA size == record slots per round
+  int32_t threads;            // record slots per round
+  int32_t groups;             // thread groups per CTA (CTA size = groups * threads): group g computes
+                              // round r0+g while the others compute theirs; accumulation is serialised
   int32_t max_owned, max_local;
   int32_t max_slots, max_rounds;  // largest record count / round count of any patch
   // mesh state (device)
@@ -68,8 +69,8 @@ size_t pass_b_smem_bytes(const PatchLaunch& a, bool bending, bool tilt);
 // scalars_here: also sum the per-facet scalars (surface energy, area, volume).
 cudaError_t launch_pass_a(const PatchLaunch& a, cudaStream_t st);
 cudaError_t launch_pass_b(const PatchLaunch& a, bool bending, bool scalars_here, cudaStream_t st);
-// scalars[0..7] = fixed-order sum over patches of partials; volume slot divided by 6.
-cudaError_t launch_reduce_partials(const double* partials, int n_patches, double* scalars,
+// scalars[0..11] = fixed-order sum over patches [begin, begin+count) of partials; volume slot / 6.
+cudaError_t launch_reduce_partials(const double* partials, int begin, int count, double* scalars,
                                    cudaStream_t st);
 cudaError_t configure_kernels();  // opt-in to large dynamic shared memory (once per device)
 

@@ -160,49 +160,91 @@ int pack_patches(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* body
       n_rounds = kept;
     }
 
-    // --- emit header, halo list and the records, round after round ---
+    // --- emit header, halo list and the records ---
+    // Round r owns the T record slots [slot_off + r*T, slot_off + (r+1)*T).  Inside a round the
+    // records are placed so that, within every half-warp (16 consecutive lanes), the local
+    // vertex indices seen at corner 0, at corner 1 and at corner 2 are pairwise distinct
+    // modulo 16 (or identical).  All per-vertex rows in shared memory have an odd stride in
+    // doubles (3 or 5), so such a half-warp performs its 64-bit gathers and its
+    // read-modify-writes without bank conflicts.  A facet may be rotated cyclically to fit
+    // (the per-facet math is invariant under cyclic relabelling); unused slots stay invalid.
     PatchHeader h;
     h.v_lo = v_lo;
     h.n_owned = n;
     h.halo_off = int32_t(out.halo_ids.size());
     h.n_halo = int32_t(s.halo.size());
     h.slot_off = int64_t(out.recs.size());
-    h.round_off = int32_t(out.round_ptr.size());
+    h.reserved = 0;
     h.n_rounds = n_rounds;
     out.patches.push_back(h);
     out.halo_ids.insert(out.halo_ids.end(), s.halo.begin(), s.halo.end());
 
     const size_t base = out.recs.size();
-    std::vector<int32_t> start(size_t(n_rounds) + 1, 0);
-    for (int32_t r = 0; r < n_rounds; ++r) start[size_t(r) + 1] = start[r] + round_fill[r];
-    out.round_ptr.insert(out.round_ptr.end(), start.begin(), start.end());
-    out.recs.resize(base + nfac);
-    out.slot_facet.resize(base + nfac, -1);
-    std::vector<int32_t> cursor(start.begin(), start.end() - 1);
+    const size_t n_slots = size_t(n_rounds) * size_t(T);
+    FacetRec empty;
+    empty.a = empty.b = empty.c = 0;
+    empty.flags = 0;
+    out.recs.resize(base + n_slots, empty);
+    out.slot_facet.resize(base + n_slots, -1);
+
+    const int n_hw = (T + 15) / 16;
+    // occupant[(round*n_hw + hw)*48 + corner*16 + residue] = local index or -1
+    std::vector<int32_t> occupant(size_t(n_rounds) * size_t(n_hw) * 48, -1);
+    std::vector<int32_t> hw_fill(size_t(n_rounds) * size_t(n_hw), 0);
     for (size_t i = 0; i < nfac; ++i) {
       const int32_t f = s.facets[i];
       const int32_t* t = tri + 3 * size_t(f);
-      uint16_t loc[3];
+      int32_t loc[3];
       for (int k = 0; k < 3; ++k) {
         const int32_t u = t[k];
         // halo slots were assigned by the last collect() call of this patch
-        loc[k] = (u >= v_lo && u < v_hi) ? uint16_t(u - v_lo) : uint16_t(n + s.vert_local[u]);
+        loc[k] = (u >= v_lo && u < v_hi) ? (u - v_lo) : (n + s.vert_local[u]);
       }
+      uint16_t flags = REC_VALID;
+      if (t[0] >= v_lo && t[0] < v_hi) flags |= REC_PRIMARY;
+      if (body_mask && body_mask[f]) flags |= REC_BODY;
+      const int32_t r = round_of[i];
+      int best_hw = -1, best_rot = 0, best_cost = 1 << 30;
+      for (int hw = 0; hw < n_hw && best_cost > 0; ++hw) {
+        const int cap = std::min(16, T - hw * 16);
+        if (hw_fill[size_t(r) * n_hw + hw] >= cap) continue;
+        const int32_t* occ = occupant.data() + (size_t(r) * n_hw + hw) * 48;
+        for (int rot = 0; rot < 3; ++rot) {
+          int cost = 0;
+          for (int k = 0; k < 3; ++k) {
+            const int32_t idx = loc[(k + rot) % 3];
+            const int32_t o = occ[k * 16 + (idx & 15)];
+            cost += (o >= 0 && o != idx) ? 1 : 0;
+          }
+          if (cost < best_cost) {
+            best_cost = cost;
+            best_hw = hw;
+            best_rot = rot;
+            if (cost == 0) break;
+          }
+        }
+      }
+      // a round never holds more than T facets, so some half-warp has a free lane
+      int32_t* occ = occupant.data() + (size_t(r) * n_hw + best_hw) * 48;
+      for (int k = 0; k < 3; ++k) {
+        const int32_t idx = loc[(k + best_rot) % 3];
+        if (occ[k * 16 + (idx & 15)] < 0) occ[k * 16 + (idx & 15)] = idx;
+      }
+      const int lane = hw_fill[size_t(r) * n_hw + best_hw]++;
+      out.n_lane_conflicts += best_cost;
       FacetRec rec;
-      rec.a = loc[0];
-      rec.b = loc[1];
-      rec.c = loc[2];
-      rec.flags = REC_VALID;
-      if (t[0] >= v_lo && t[0] < v_hi) rec.flags |= REC_PRIMARY;
-      if (body_mask && body_mask[f]) rec.flags |= REC_BODY;
-      const size_t slot = base + size_t(cursor[round_of[i]]++);
+      rec.a = uint16_t(loc[best_rot % 3]);
+      rec.b = uint16_t(loc[(1 + best_rot) % 3]);
+      rec.c = uint16_t(loc[(2 + best_rot) % 3]);
+      rec.flags = flags;
+      const size_t slot = base + size_t(r) * size_t(T) + size_t(best_hw) * 16 + size_t(lane);
       out.recs[slot] = rec;
       out.slot_facet[slot] = f;
     }
     out.max_owned = std::max(out.max_owned, n);
     out.max_local = std::max(out.max_local, int32_t(n_local));
     out.max_rounds = std::max(out.max_rounds, n_rounds);
-    out.max_slots = std::max(out.max_slots, int32_t(nfac));
+    out.max_slots = std::max(out.max_slots, int32_t(n_slots));
     out.n_round_slots += int64_t(n_rounds) * int64_t(T);
     out.n_listed += int64_t(nfac);
     v_lo += n;

@@ -24,14 +24,15 @@ struct PatchHeader {  // 32 bytes
   int32_t halo_off;   // first entry of this patch in halo_ids
   int32_t n_halo;     // local index n_owned + j  ->  vertex row halo_ids[halo_off + j]
   int64_t slot_off;   // first record slot of this patch
-  int32_t round_off;  // round r of this patch holds the record slots
-                      //   [slot_off + round_ptr[round_off + r], slot_off + round_ptr[round_off + r + 1])
-  int32_t n_rounds;   // (at most `threads` records per round; no padding slots)
+  int32_t reserved;
+  int32_t n_rounds;   // round r holds the `threads` slots [slot_off + r*threads, slot_off + (r+1)*threads);
+                      // slots without a facet carry flags == 0
 };
 static_assert(sizeof(PatchHeader) == 32, "PatchHeader layout");
 
-// One record slot.  flags bit0: valid (always set; kept for robustness); bit1: primary (this patch owns corner 0, so
-// per-facet scalars are summed here exactly once); bit2: facet belongs to the body.
+// One record slot.  flags bit0: valid (0 marks an empty slot); bit1: primary (this patch owns
+// the facet's first vertex, so per-facet scalars are summed here exactly once); bit2: facet
+// belongs to the body.  (a,b,c) may be a cyclic rotation of the facet's vertex order.
 struct FacetRec {
   uint16_t a, b, c;  // patch-local vertex indices (owned first, then halo)
   uint16_t flags;
@@ -52,10 +53,10 @@ struct PackedMesh {
   std::vector<PatchHeader> patches;
   std::vector<int32_t> halo_ids;
   std::vector<FacetRec> recs;
-  std::vector<int32_t> round_ptr;   // per patch n_rounds+1 slot offsets relative to slot_off
   std::vector<int32_t> slot_facet;  // facet row of each slot
   int32_t max_owned = 0, max_local = 0, max_rounds = 0, max_slots = 0;
-  int64_t n_round_slots = 0;  // sum over patches of n_rounds * threads (lane-fill denominator)
+  int64_t n_round_slots = 0;  // sum over patches of n_rounds * threads (== recs.size())
+  int64_t n_lane_conflicts = 0;  // corner placements that share a bank residue inside a half-warp
   int64_t n_listed = 0;   // facet listings over all patches (>= valid facets)
   int64_t n_valid = 0;    // facets with all indices in range
 };

@@ -24,7 +24,10 @@ enum PartialSlot : int {
   PS_E_BENDING = 3,
   PS_E_TILT = 4,
   PS_E_BENDING_TILT = 5,
-  PS_COUNT = 8,
+  PS_G_G = 8,       // <g,g>, <g,gC>, <gC,gC> over the owned rows (pass B, before projection)
+  PS_G_GC = 9,
+  PS_GC_GC = 10,
+  PS_COUNT = 12,
 };
 
 struct LocalA {
@@ -37,9 +40,11 @@ struct LocalA {
   int P;               // owned vertices; local indices >= P are halo (read-only)
 };
 
-// Per-facet scalars (primary listing only) + pass-A corner accumulation.
-MS_HD void facet_body_a(FacetRec rec, double gam, const LocalA& s, uint32_t modules, double k_tilt,
-                        double* sums) {
+// Per-facet scalars (primary listing only) + pass-A corner contributions, computed in
+// registers; the accumulation into the owned-vertex arrays is a separate step so that
+// several thread groups can compute concurrently and accumulate one after the other.
+MS_HD CornerA facet_compute_a(FacetRec rec, double gam, const LocalA& s, uint32_t modules,
+                              double k_tilt, double* sums) {
   const d3 v0 = ld3(s.pos, rec.a), v1 = ld3(s.pos, rec.b), v2 = ld3(s.pos, rec.c);
   const FacetGeom g = facet_geom(v0, v1, v2);
   if (rec.flags & REC_PRIMARY) {
@@ -52,12 +57,24 @@ MS_HD void facet_body_a(FacetRec rec, double gam, const LocalA& s, uint32_t modu
     }
     if ((modules & MS_MOD_VOLUME) && (rec.flags & REC_BODY)) sums[PS_VOLUME6] += facet_volume6(v0, v1, v2);
   }
+  CornerA c;
+  if (modules & (MS_MOD_BENDING | MS_MOD_BENDING_TILT))
+    c = facet_pass_a(g, s.bfl[rec.a] != 0, s.bfl[rec.b] != 0, s.bfl[rec.c] != 0);
+  return c;
+}
+
+MS_HD void facet_accumulate_a(FacetRec rec, const CornerA& c, const LocalA& s, uint32_t modules) {
   if (modules & (MS_MOD_BENDING | MS_MOD_BENDING_TILT)) {
-    const CornerA c = facet_pass_a(g, s.bfl[rec.a] != 0, s.bfl[rec.b] != 0, s.bfl[rec.c] != 0);
     if (rec.a < s.P) { add3(s.accK, rec.a, c.K0); s.accAv[rec.a] += c.va0; s.accAe[rec.a] += c.ve0; }
     if (rec.b < s.P) { add3(s.accK, rec.b, c.K1); s.accAv[rec.b] += c.va1; s.accAe[rec.b] += c.ve1; }
     if (rec.c < s.P) { add3(s.accK, rec.c, c.K2); s.accAv[rec.c] += c.va2; s.accAe[rec.c] += c.ve2; }
   }
+}
+
+MS_HD void facet_body_a(FacetRec rec, double gam, const LocalA& s, uint32_t modules, double k_tilt,
+                        double* sums) {
+  const CornerA c = facet_compute_a(rec, gam, s, modules, k_tilt, sums);
+  facet_accumulate_a(rec, c, s, modules);
 }
 
 // Area-weighted vertex-normal accumulation (bending_utils.py:13-34), only run for
@@ -98,61 +115,81 @@ struct LocalB {
   int P;
 };
 
-constexpr int kSeedStrideBody = 6;
+constexpr int kSeedStrideBody = 5;
+
+// Results of one facet in pass B, held in registers between compute and accumulation.
+struct FacetOutB {
+  CornerG cg;     // shape gradient contributions
+  CornerG vg;     // dV/dx contributions (valid when in_body)
+  double third;   // T/3 for the barycentric area (tilt), 0 when the facet is skipped
+  bool in_body;
+};
 
 template <bool BENDING>
-MS_HD void facet_body_b(FacetRec rec, double gam, const LocalB& s, uint32_t modules, uint32_t flags,
-                        double k_tilt, bool scalars_here, double* sums) {
+MS_HD FacetOutB facet_compute_b(FacetRec rec, double gam, const LocalB& s, uint32_t modules,
+                                uint32_t flags, double k_tilt, bool scalars_here, double* sums) {
+  FacetOutB o;
   const d3 v0 = ld3(s.pos, rec.a), v1 = ld3(s.pos, rec.b), v2 = ld3(s.pos, rec.c);
   const FacetGeom g = facet_geom(v0, v1, v2);
   const double T = 0.5 * g.S;
   const bool primary = (rec.flags & REC_PRIMARY) != 0;
-  const bool in_body = (modules & MS_MOD_VOLUME) && (rec.flags & REC_BODY);
+  o.in_body = (modules & MS_MOD_VOLUME) && (rec.flags & REC_BODY);
+  o.third = 0.0;
   if (!(modules & MS_MOD_SURFACE)) gam = 0.0;
   double coeff = 0.0;
   if ((modules & MS_MOD_TILT) && s.t2) {
     coeff = 0.5 * k_tilt * ((s.t2[rec.a] + s.t2[rec.b] + s.t2[rec.c]) / 3.0);
     if (g.S >= kSurfaceSkip) {
       if (primary) sums[PS_E_TILT] += coeff * T;
-      const double third = T / 3.0;
-      if (rec.a < s.P) s.accAb[rec.a] += third;
-      if (rec.b < s.P) s.accAb[rec.b] += third;
-      if (rec.c < s.P) s.accAb[rec.c] += third;
+      o.third = T / 3.0;
     }
   }
   if (scalars_here && primary) {
     sums[PS_AREA] += T;
     if ((modules & MS_MOD_SURFACE) && g.S >= kSurfaceSkip) sums[PS_E_SURFACE] += gam * T;
-    if (in_body) sums[PS_VOLUME6] += facet_volume6(v0, v1, v2);
+    if (o.in_body) sums[PS_VOLUME6] += facet_volume6(v0, v1, v2);
   }
   BendIn b;
   if (BENDING) {
-    // seed rows are 48 bytes, 16-byte aligned: three vector loads per corner
-    const dd2* sa = reinterpret_cast<const dd2*>(s.seed) + 3 * rec.a;
-    const dd2* sb = reinterpret_cast<const dd2*>(s.seed) + 3 * rec.b;
-    const dd2* sc = reinterpret_cast<const dd2*>(s.seed) + 3 * rec.c;
-    const dd2 a0 = sa[0], a1 = sa[1], a2 = sa[2];
-    const dd2 b0 = sb[0], b1 = sb[1], b2 = sb[2];
-    const dd2 c0 = sc[0], c1 = sc[1], c2 = sc[2];
-    b.f0 = make_d3(a0.a, a0.b, a1.a); b.fe0 = a1.b; b.fv0 = a2.a;
-    b.f1 = make_d3(b0.a, b0.b, b1.a); b.fe1 = b1.b; b.fv1 = b2.a;
-    b.f2 = make_d3(c0.a, c0.b, c1.a); b.fe2 = c1.b; b.fv2 = c2.a;
+    // seed rows: 5 doubles (odd stride, see ms_pack.cpp on bank conflicts)
+    const double* sa = s.seed + kSeedStrideBody * rec.a;
+    const double* sb = s.seed + kSeedStrideBody * rec.b;
+    const double* sc = s.seed + kSeedStrideBody * rec.c;
+    b.f0 = make_d3(sa[0], sa[1], sa[2]); b.fe0 = sa[3]; b.fv0 = sa[4];
+    b.f1 = make_d3(sb[0], sb[1], sb[2]); b.fe1 = sb[3]; b.fv1 = sb[4];
+    b.f2 = make_d3(sc[0], sc[1], sc[2]); b.fe2 = sc[3]; b.fv2 = sc[4];
     b.i0 = !s.bfl[rec.a]; b.i1 = !s.bfl[rec.b]; b.i2 = !s.bfl[rec.c];
   } else {
     b.f0 = b.f1 = b.f2 = make_d3(0, 0, 0);
     b.fe0 = b.fe1 = b.fe2 = b.fv0 = b.fv1 = b.fv2 = 0.0;
     b.i0 = b.i1 = b.i2 = true;
   }
-  const CornerG cg = facet_pass_b<BENDING>(g, gam, coeff, b, (flags & MS_FLAG_APPROX) != 0);
-  if (rec.a < s.P) add3(s.accG, rec.a, cg.g0);
-  if (rec.b < s.P) add3(s.accG, rec.b, cg.g1);
-  if (rec.c < s.P) add3(s.accG, rec.c, cg.g2);
-  if (in_body) {
-    const CornerG vg = facet_volume_grad(v0, v1, v2);
-    if (rec.a < s.P) add3(s.accV, rec.a, vg.g0);
-    if (rec.b < s.P) add3(s.accV, rec.b, vg.g1);
-    if (rec.c < s.P) add3(s.accV, rec.c, vg.g2);
+  o.cg = facet_pass_b<BENDING>(g, gam, coeff, b, (flags & MS_FLAG_APPROX) != 0);
+  if (o.in_body) o.vg = facet_volume_grad(v0, v1, v2);
+  return o;
+}
+
+MS_HD void facet_accumulate_b(FacetRec rec, const FacetOutB& o, const LocalB& s) {
+  if (rec.a < s.P) add3(s.accG, rec.a, o.cg.g0);
+  if (rec.b < s.P) add3(s.accG, rec.b, o.cg.g1);
+  if (rec.c < s.P) add3(s.accG, rec.c, o.cg.g2);
+  if (o.in_body) {
+    if (rec.a < s.P) add3(s.accV, rec.a, o.vg.g0);
+    if (rec.b < s.P) add3(s.accV, rec.b, o.vg.g1);
+    if (rec.c < s.P) add3(s.accV, rec.c, o.vg.g2);
   }
+  if (s.t2 && o.third != 0.0) {
+    if (rec.a < s.P) s.accAb[rec.a] += o.third;
+    if (rec.b < s.P) s.accAb[rec.b] += o.third;
+    if (rec.c < s.P) s.accAb[rec.c] += o.third;
+  }
+}
+
+template <bool BENDING>
+MS_HD void facet_body_b(FacetRec rec, double gam, const LocalB& s, uint32_t modules, uint32_t flags,
+                        double k_tilt, bool scalars_here, double* sums) {
+  const FacetOutB o = facet_compute_b<BENDING>(rec, gam, s, modules, flags, k_tilt, scalars_here, sums);
+  facet_accumulate_b(rec, o, s);
 }
 
 }  // namespace ms

@@ -28,7 +28,7 @@ int emul_eval(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* is_boun
               double k_tilt, uint32_t modules, uint32_t flags, int32_t want_grad, int32_t threads,
               int32_t max_owned, int32_t max_local, double* scalars8, double* grad, double* volgrad,
               double* tilt_grad, double* seeds, double* k_vecs, double* a_vor, double* a_eff,
-              double* e_vertex, int64_t* pack_stats /*[n_patches,n_slots,n_listed,max_rounds,max_local]*/) {
+              double* e_vertex, int64_t* pack_stats /*[n_patches,n_slots,n_listed,max_rounds,max_local,lane_conflicts]*/) {
   PackParams prm;
   prm.threads = threads;
   prm.max_owned = max_owned;
@@ -42,6 +42,7 @@ int emul_eval(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* is_boun
     pack_stats[2] = pk.n_listed;
     pack_stats[3] = pk.max_rounds;
     pack_stats[4] = pk.max_local;
+    pack_stats[5] = pk.n_lane_conflicts;
   }
   const bool bending = (modules & MS_MOD_BENDING) != 0;
   const bool do_tilt = (modules & MS_MOD_TILT) && tilts;
@@ -70,12 +71,11 @@ int emul_eval(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* is_boun
       loc.pos = lpos.data(); loc.bfl = bfl.data(); loc.t2 = do_tilt ? t2.data() : nullptr;
       loc.accK = accK.data(); loc.accAv = accAv.data(); loc.accAe = accAe.data(); loc.P = P;
       double sums[PS_COUNT] = {0};
-      const int32_t* rp = pk.round_ptr.data() + h.round_off;
       for (int r = 0; r < h.n_rounds; ++r)
-        for (int t = rp[r]; t < rp[r + 1]; ++t) {
-          if (rp[r + 1] - rp[r] > T) return -90;
-          const size_t slot = size_t(h.slot_off) + size_t(t);
+        for (int t = 0; t < T; ++t) {
+          const size_t slot = size_t(h.slot_off) + size_t(r) * size_t(T) + size_t(t);
           const FacetRec rec = pk.recs[slot];
+          if (!(rec.flags & REC_VALID)) continue;
           const double gam = gamma ? gamma[pk.slot_facet[slot]] : gamma_u;
           facet_body_a(rec, gam, loc, modules, k_tilt, sums);
         }
@@ -84,15 +84,17 @@ int emul_eval(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* is_boun
         for (int i = 0; i < P; ++i) any_need |= vertex_needs_normal(loc, i);
         if (any_need)
           for (int r = 0; r < h.n_rounds; ++r)
-            for (int t = rp[r]; t < rp[r + 1]; ++t)
-              normal_body(pk.recs[size_t(h.slot_off) + size_t(t)], lpos.data(), nrm.data(), P);
+            for (int t = 0; t < T; ++t) {
+              const FacetRec rec = pk.recs[size_t(h.slot_off) + size_t(r) * size_t(T) + size_t(t)];
+              if (rec.flags & REC_VALID) normal_body(rec, lpos.data(), nrm.data(), P);
+            }
         for (int i = 0; i < P; ++i) {
           const size_t row = size_t(h.v_lo) + i;
           const VertexSeed sd = vertex_body_a(i, loc, nrm.data(), any_need, kappa ? kappa[row] : kappa_u,
                                               c0 ? c0[row] : c0_u, willmore);
           sums[PS_E_BENDING] += sd.E;
           double* o = seed_store.data() + row * kSeedStrideBody;
-          o[0] = sd.fK.x; o[1] = sd.fK.y; o[2] = sd.fK.z; o[3] = sd.fAe; o[4] = sd.fAv; o[5] = 0.0;
+          o[0] = sd.fK.x; o[1] = sd.fK.y; o[2] = sd.fK.z; o[3] = sd.fAe; o[4] = sd.fAv;
           if (k_vecs) for (int k = 0; k < 3; ++k) k_vecs[3 * row + k] = accK[3 * size_t(i) + k];
           if (a_vor) a_vor[row] = accAv[size_t(i)];
           if (a_eff) a_eff[row] = accAe[size_t(i)];
@@ -129,11 +131,11 @@ int emul_eval(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* is_boun
       loc.t2 = do_tilt ? t2.data() : nullptr;
       loc.accG = accG.data(); loc.accV = accV.data(); loc.accAb = accAb.data(); loc.P = P;
       double sums[PS_COUNT] = {0};
-      const int32_t* rp = pk.round_ptr.data() + h.round_off;
       for (int r = 0; r < h.n_rounds; ++r)
-        for (int t = rp[r]; t < rp[r + 1]; ++t) {
-          const size_t slot = size_t(h.slot_off) + size_t(t);
+        for (int t = 0; t < T; ++t) {
+          const size_t slot = size_t(h.slot_off) + size_t(r) * size_t(T) + size_t(t);
           const FacetRec rec = pk.recs[slot];
+          if (!(rec.flags & REC_VALID)) continue;
           const double gam = gamma ? gamma[pk.slot_facet[slot]] : gamma_u;
           if (bending)
             facet_body_b<true>(rec, gam, loc, modules, flags, k_tilt, scalars_here, sums);
@@ -154,7 +156,7 @@ int emul_eval(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* is_boun
       total[PS_E_TILT] = total_b[PS_E_TILT];
   }
   total[PS_VOLUME6] /= 6.0;
-  for (int k = 0; k < PS_COUNT; ++k) scalars8[k] = total[k];
+  for (int k = 0; k < 8; ++k) scalars8[k] = total[k];
   return 0;
 }
 

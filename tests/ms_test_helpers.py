@@ -86,9 +86,9 @@ def emulate(pos, tri, *, modules, flags=0, want_grad=True, is_boundary=None, bod
 
     scal = np.zeros(8)
     out = dict(grad=np.zeros((nv, 3)), volgrad=np.zeros((nv, 3)), tilt_grad=np.zeros((nv, 3)),
-               seeds=np.zeros((nv, 6)), k_vecs=np.zeros((nv, 3)), a_vor=np.zeros(nv),
+               seeds=np.zeros((nv, 5)), k_vecs=np.zeros((nv, 3)), a_vor=np.zeros(nv),
                a_eff=np.zeros(nv), e_vertex=np.zeros(nv))
-    stats = np.zeros(5, dtype=np.int64)
+    stats = np.zeros(6, dtype=np.int64)
     rc = _EMUL.emul_eval(
         ctypes.c_int32(nv), ctypes.c_int32(nf), tri.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
         bptr(u8(is_boundary)), bptr(u8(body_mask)), dptr(pos), dptr(f64(tilts)), dptr(f64(gamma)),
@@ -102,5 +102,6 @@ def emulate(pos, tri, *, modules, flags=0, want_grad=True, is_boundary=None, bod
         raise RuntimeError(f"emul_eval failed: {rc}")
     out.update(E_surface=scal[0], area=scal[1], volume=scal[2], E_bending=scal[3], E_tilt=scal[4],
                pack=dict(n_patches=int(stats[0]), n_slots=int(stats[1]), n_listed=int(stats[2]),
-                         max_rounds=int(stats[3]), max_local=int(stats[4])))
+                         max_rounds=int(stats[3]), max_local=int(stats[4]),
+                         lane_conflicts=int(stats[5])))
     return out
