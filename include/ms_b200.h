@@ -105,10 +105,10 @@ MS_API int ms_ctx_create(int device, ms_ctx** out);
 MS_API int ms_ctx_destroy(ms_ctx* ctx);
 /* patch geometry used by the next ms_ctx_set_topology (defaults 128 / 512 / 896) */
 MS_API int ms_ctx_set_pack_params(ms_ctx* ctx, int32_t threads, int32_t max_owned, int32_t max_local);
-/* thread groups per CTA (default 2): group g computes round r0+g of a patch while the other
- * groups compute theirs, and the groups then accumulate one after the other; the CTA has
- * groups*threads threads (clamped to 256) */
-MS_API int ms_ctx_set_groups(ms_ctx* ctx, int32_t groups);
+/* thread groups per CTA in pass A / pass B (defaults 1 / 2): group g computes round r0+g of a
+ * patch while the other groups compute theirs, and the groups then accumulate one after the
+ * other; the CTA has groups*threads threads (clamped to 256) */
+MS_API int ms_ctx_set_groups(ms_ctx* ctx, int32_t groups_a, int32_t groups_b);
 /* Re-called only after refine / equiangulate / vertex-average changed the topology
  * (commands/mesh_ops.py:21-78).  is_boundary, body_mask, fixed_mask may be NULL. */
 MS_API int ms_ctx_set_topology(ms_ctx* ctx, int32_t nv, int32_t nf, const int32_t* tri,

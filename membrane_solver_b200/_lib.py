@@ -77,7 +77,7 @@ SIGNATURES = {
     "ms_ctx_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_V)]),
     "ms_ctx_destroy": (ctypes.c_int, [_V]),
     "ms_ctx_set_pack_params": (ctypes.c_int, [_V, _i32, _i32, _i32]),
-    "ms_ctx_set_groups": (ctypes.c_int, [_V, _i32]),
+    "ms_ctx_set_groups": (ctypes.c_int, [_V, _i32, _i32]),
     "ms_ctx_set_topology": (ctypes.c_int, [_V, _i32, _i32, _I, _B, _B, _B]),
     "ms_ctx_pack_info": (ctypes.c_int, [_V, ctypes.POINTER(PackInfo)]),
     "ms_ctx_patch_ranges": (ctypes.c_int, [_V, _I]),

@@ -67,7 +67,7 @@ class DeviceMesh:
     """One mesh resident on one GPU."""
 
     def __init__(self, device: int = 0, *, threads: int | None = None, max_owned: int | None = None,
-                 max_local: int | None = None, groups: int | None = None):
+                 max_local: int | None = None, groups: tuple[int, int] | None = None):
         self._lib = L.lib()
         handle = ctypes.c_void_p()
         L.check(self._lib.ms_ctx_create(int(device), ctypes.byref(handle)))
@@ -79,7 +79,7 @@ class DeviceMesh:
             L.check(self._lib.ms_ctx_set_pack_params(self._h, int(threads or 128), int(max_owned or 512),
                                                      int(max_local or 896)))
         if groups is not None:
-            L.check(self._lib.ms_ctx_set_groups(self._h, int(groups)))
+            L.check(self._lib.ms_ctx_set_groups(self._h, int(groups[0]), int(groups[1])))
 
     # -- lifetime -----------------------------------------------------------
     def close(self) -> None:

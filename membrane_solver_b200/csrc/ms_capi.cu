@@ -61,7 +61,7 @@ struct ms_ctx {
   bool have_topology = false;
   int32_t nv = 0, nf = 0;
   ms::PackParams pack_params;
-  int32_t groups = 2;  // thread groups per CTA (see PatchLaunch::groups)
+  int32_t groups_a = 1, groups_b = 2;  // thread groups per CTA in pass A / pass B (PatchLaunch::groups)
   ms::PackedMesh packed;  // recs / slot_facet kept on the host for gamma repacking
   std::vector<int32_t> v_lo;
 
@@ -145,8 +145,7 @@ int fill_launch(ms_ctx* c, const ms_eval_opts* o, ms::PatchLaunch& a) {
   a.patch_begin = begin;
   a.patch_count = count;
   a.threads = c->packed.params.threads;
-  a.groups = c->groups;
-  while (a.groups > 1 && a.groups * a.threads > 256) --a.groups;
+  a.groups = 1;  // set by the pass entry points
   a.max_owned = c->packed.max_owned;
   a.max_local = c->packed.max_local;
   a.max_slots = c->packed.max_slots;
@@ -268,10 +267,11 @@ int ms_ctx_set_pack_params(ms_ctx* c, int32_t threads, int32_t max_owned, int32_
   return 0;
 }
 
-int ms_ctx_set_groups(ms_ctx* c, int32_t groups) {
+int ms_ctx_set_groups(ms_ctx* c, int32_t groups_a, int32_t groups_b) {
   if (!c) return fail(-1, "null context");
-  if (groups < 1 || groups > 8) return fail(-1, "groups must be in [1,8]");
-  c->groups = groups;
+  if (groups_a < 1 || groups_a > 8 || groups_b < 1 || groups_b > 8) return fail(-1, "groups must be in [1,8]");
+  c->groups_a = groups_a;
+  c->groups_b = groups_b;
   return 0;
 }
 
@@ -504,6 +504,8 @@ int ms_ctx_eval_pass_a(ms_ctx* c, const ms_eval_opts* o) {
   if (int rc = fill_launch(c, o, a)) return rc;
   // Pass A is needed for the bending seeds and for energies; surface/volume-only
   // gradient evaluations do everything in pass B.
+  a.groups = c->groups_a;
+  while (a.groups > 1 && a.groups * a.threads > 256) --a.groups;
   if (needs_bending(o) || !o->want_grad) CU(ms::launch_pass_a(a, c->stream));
   return 0;
 }
@@ -514,6 +516,8 @@ int ms_ctx_eval_pass_b(ms_ctx* c, const ms_eval_opts* o) {
   if (!o->want_grad) return 0;
   ms::PatchLaunch a;
   if (int rc = fill_launch(c, o, a)) return rc;
+  a.groups = c->groups_b;
+  while (a.groups > 1 && a.groups * a.threads > 256) --a.groups;
   CU(ms::launch_pass_b(a, needs_bending(o), !needs_bending(o), c->stream));
   return 0;
 }

@@ -160,13 +160,13 @@ __global__ void __launch_bounds__(kMaxThreads) k_pass_a(PatchLaunch a) {
     const int v = j / 3, c = j - v * 3;
     cp_async8(s.pos + 3 * P + j, a.pos + size_t(s.halo[v]) * 3 + c);
   }
-  stage_flags(s.bfl, a.is_boundary, h, s.halo);
+  if (a.is_boundary) stage_flags(s.bfl, a.is_boundary, h, s.halo);
   if (do_tilt) stage_tilt_sq(s.t2, a.tilts, h, s.halo);
   cp_async_wait_all();
   __syncthreads();
 
   LocalA loc;
-  loc.pos = s.pos; loc.bfl = s.bfl; loc.t2 = do_tilt ? s.t2 : nullptr;
+  loc.pos = s.pos; loc.bfl = a.is_boundary ? s.bfl : nullptr; loc.t2 = do_tilt ? s.t2 : nullptr;
   loc.accK = s.accK; loc.accAv = s.accAv; loc.accAe = s.accAe; loc.P = P;
   double sums[PS_COUNT];
 #pragma unroll
@@ -299,14 +299,14 @@ __global__ void __launch_bounds__(kMaxThreads, 2) k_pass_b(PatchLaunch a, bool s
       const int v = j / kSeedStride, c = j - v * kSeedStride;
       cp_async8(d2 + j, a.seeds + size_t(s.halo[v]) * kSeedStride + c);
     }
-    stage_flags(s.bfl, a.is_boundary, h, s.halo);
+    if (a.is_boundary) stage_flags(s.bfl, a.is_boundary, h, s.halo);
   }
   if (do_tilt) stage_tilt_sq(s.t2, a.tilts, h, s.halo);
   cp_async_wait_all();
   __syncthreads();
 
   LocalB loc;
-  loc.pos = s.pos; loc.seed = s.seed; loc.bfl = s.bfl; loc.t2 = do_tilt ? s.t2 : nullptr;
+  loc.pos = s.pos; loc.seed = s.seed; loc.bfl = a.is_boundary ? s.bfl : nullptr; loc.t2 = do_tilt ? s.t2 : nullptr;
   loc.accG = s.accG; loc.accV = s.accV; loc.accAb = s.accAb; loc.P = P;
   double sums[PS_COUNT];
 #pragma unroll

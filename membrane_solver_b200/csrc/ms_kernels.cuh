@@ -39,6 +39,7 @@ struct PatchLaunch {
   int32_t threads;            // record slots per round
   int32_t groups;             // thread groups per CTA (CTA size = groups * threads): group g computes
                               // round r0+g while the others compute theirs; accumulation is serialised
+                              // (set per launch: pass A and pass B use different values)
   int32_t max_owned, max_local;
   int32_t max_slots, max_rounds;  // largest record count / round count of any patch
   // mesh state (device)

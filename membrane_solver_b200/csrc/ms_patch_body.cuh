@@ -32,7 +32,7 @@ enum PartialSlot : int {
 
 struct LocalA {
   const double* pos;   // (L,3)
-  const uint8_t* bfl;  // L  boundary flags
+  const uint8_t* bfl;  // L  boundary flags; nullptr = closed mesh (no boundary vertex)
   const double* t2;    // L  |tilt|^2 (tilt module only)
   double* accK;        // (P,3)
   double* accAv;       // P
@@ -59,7 +59,8 @@ MS_HD CornerA facet_compute_a(FacetRec rec, double gam, const LocalA& s, uint32_
   }
   CornerA c;
   if (modules & (MS_MOD_BENDING | MS_MOD_BENDING_TILT))
-    c = facet_pass_a(g, s.bfl[rec.a] != 0, s.bfl[rec.b] != 0, s.bfl[rec.c] != 0);
+    c = s.bfl ? facet_pass_a(g, s.bfl[rec.a] != 0, s.bfl[rec.b] != 0, s.bfl[rec.c] != 0)
+              : facet_pass_a(g, false, false, false);
   return c;
 }
 
@@ -89,7 +90,7 @@ MS_HD void normal_body(FacetRec rec, const double* pos, double* nrm, int P) {
 
 MS_HD bool vertex_needs_normal(const LocalA& s, int i) {
   const d3 K = ld3(s.accK, i);
-  return !(sqrt(dot(K, K)) > 1.0e-15) && !s.bfl[i];
+  return !(sqrt(dot(K, K)) > 1.0e-15) && !(s.bfl && s.bfl[i]);
 }
 
 MS_HD VertexSeed vertex_body_a(int i, const LocalA& s, const double* nrm, bool use_normal,
@@ -101,13 +102,13 @@ MS_HD VertexSeed vertex_body_a(int i, const LocalA& s, const double* nrm, bool u
     if (m > 1.0e-15) n = (1.0 / m) * n;
   }
   return vertex_stage(ld3(s.accK, i), s.accAv[i], s.accAe[i], kappa, willmore ? 0.0 : c0,
-                      s.bfl[i] != 0, willmore, n, 0.0);
+                      s.bfl && s.bfl[i] != 0, willmore, n, 0.0);
 }
 
 struct LocalB {
   const double* pos;   // (L,3)
   const double* seed;  // (L,kSeedStride)   bending only
-  const uint8_t* bfl;  // L                 bending only
+  const uint8_t* bfl;  // L                 bending only; nullptr = closed mesh
   const double* t2;    // L                 tilt only
   double* accG;        // (P,3) shape gradient
   double* accV;        // (P,3) dV/dx
@@ -158,7 +159,11 @@ MS_HD FacetOutB facet_compute_b(FacetRec rec, double gam, const LocalB& s, uint3
     b.f0 = make_d3(sa[0], sa[1], sa[2]); b.fe0 = sa[3]; b.fv0 = sa[4];
     b.f1 = make_d3(sb[0], sb[1], sb[2]); b.fe1 = sb[3]; b.fv1 = sb[4];
     b.f2 = make_d3(sc[0], sc[1], sc[2]); b.fe2 = sc[3]; b.fv2 = sc[4];
-    b.i0 = !s.bfl[rec.a]; b.i1 = !s.bfl[rec.b]; b.i2 = !s.bfl[rec.c];
+    if (s.bfl) {
+      b.i0 = !s.bfl[rec.a]; b.i1 = !s.bfl[rec.b]; b.i2 = !s.bfl[rec.c];
+    } else {
+      b.i0 = b.i1 = b.i2 = true;
+    }
   } else {
     b.f0 = b.f1 = b.f2 = make_d3(0, 0, 0);
     b.fe0 = b.fe1 = b.fe2 = b.fv0 = b.fv1 = b.fv2 = 0.0;

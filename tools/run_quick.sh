@@ -5,8 +5,8 @@ mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -40 gpurun_out/pytest_gpu.log | cut -c1-220
 for cfg in "${@:-128 512 896}"; do
   set -- $cfg
-  echo "== threads=$1 owned=$2 local=$3 groups=${4:-default}"
-  python bench.py --steps 20 --warmup 3 --no-cpu --threads $1 --max-owned $2 --max-local $3 ${4:+--groups $4} 2>>gpurun_out/bench.err | python -c "
+  echo "== threads=$1 owned=$2 local=$3 groups=${4:-default} ${5:-}"
+  python bench.py --steps 20 --warmup 3 --no-cpu --threads $1 --max-owned $2 --max-local $3 ${4:+--groups $4 $5} 2>>gpurun_out/bench.err | python -c "
 import sys, json
 for l in sys.stdin:
     d = json.loads(l); p = d['pack']
