@@ -114,6 +114,17 @@ MS_API int ms_ctx_set_groups(ms_ctx* ctx, int32_t groups_a, int32_t groups_b);
 MS_API int ms_ctx_set_topology(ms_ctx* ctx, int32_t nv, int32_t nf, const int32_t* tri,
                                const uint8_t* is_boundary, const uint8_t* body_mask,
                                const uint8_t* fixed_mask);
+/* Multi-GPU partition: vertex rows [0, n_owned) are owned by this context, rows
+ * [n_owned, nv) are ghost copies of vertices owned by other partitions (one ring around the
+ * owned range).  Only owned rows get results; ghost rows of MS_ARR_POSITIONS (before an
+ * evaluation) and MS_ARR_SEEDS (between pass A and pass B) are filled by the halo exchange. */
+MS_API int ms_ctx_set_topology_partition(ms_ctx* ctx, int32_t nv, int32_t n_owned, int32_t nf,
+                                         const int32_t* tri, const uint8_t* is_boundary,
+                                         const uint8_t* body_mask, const uint8_t* fixed_mask);
+/* rows of this partition that other partitions hold as ghosts (concatenated per destination) */
+MS_API int ms_ctx_set_send_rows(ms_ctx* ctx, const int32_t* rows, int64_t n);
+/* out_device[i, :] = array[send_rows[i], :] on the context stream (out is a DEVICE pointer) */
+MS_API int ms_ctx_pack_send(ms_ctx* ctx, int which, void* out_device);
 MS_API int ms_ctx_pack_info(const ms_ctx* ctx, ms_pack_info* info);
 /* patch p owns vertex rows [v_lo[p], v_lo[p+1]); v_lo has n_patches+1 entries */
 MS_API int ms_ctx_patch_ranges(const ms_ctx* ctx, int32_t* v_lo);
@@ -144,6 +155,10 @@ MS_API int ms_ctx_eval_async(ms_ctx* ctx, const ms_eval_opts* opts);
 MS_API int ms_ctx_eval_pass_a(ms_ctx* ctx, const ms_eval_opts* opts);
 MS_API int ms_ctx_eval_pass_b(ms_ctx* ctx, const ms_eval_opts* opts);
 MS_API int ms_ctx_eval_finish(ms_ctx* ctx, const ms_eval_opts* opts);
+/* ms_ctx_eval_finish = reduce (per-patch partial sums -> 12 scalars on the device) followed by
+ * project (KKT / penalty / fixed mask).  Multi-GPU: all-reduce MS_ARR_SCALARS[0..11] between. */
+MS_API int ms_ctx_eval_reduce(ms_ctx* ctx, const ms_eval_opts* opts);
+MS_API int ms_ctx_eval_project(ms_ctx* ctx, const ms_eval_opts* opts);
 /* synchronise and copy the 16 scalars to the host */
 MS_API int ms_ctx_read_scalars(ms_ctx* ctx, double* scalars16);
 /* ms_ctx_eval_async + ms_ctx_read_scalars */

@@ -79,6 +79,9 @@ SIGNATURES = {
     "ms_ctx_set_pack_params": (ctypes.c_int, [_V, _i32, _i32, _i32]),
     "ms_ctx_set_groups": (ctypes.c_int, [_V, _i32, _i32]),
     "ms_ctx_set_topology": (ctypes.c_int, [_V, _i32, _i32, _I, _B, _B, _B]),
+    "ms_ctx_set_topology_partition": (ctypes.c_int, [_V, _i32, _i32, _i32, _I, _B, _B, _B]),
+    "ms_ctx_set_send_rows": (ctypes.c_int, [_V, _I, _i64]),
+    "ms_ctx_pack_send": (ctypes.c_int, [_V, ctypes.c_int, _V]),
     "ms_ctx_pack_info": (ctypes.c_int, [_V, ctypes.POINTER(PackInfo)]),
     "ms_ctx_patch_ranges": (ctypes.c_int, [_V, _I]),
     "ms_ctx_halo_rows": (ctypes.c_int, [_V, _i32, _i32, _i32, _i32, _I, ctypes.POINTER(_i64)]),
@@ -96,6 +99,8 @@ SIGNATURES = {
     "ms_ctx_eval_pass_a": (ctypes.c_int, [_V, ctypes.POINTER(EvalOpts)]),
     "ms_ctx_eval_pass_b": (ctypes.c_int, [_V, ctypes.POINTER(EvalOpts)]),
     "ms_ctx_eval_finish": (ctypes.c_int, [_V, ctypes.POINTER(EvalOpts)]),
+    "ms_ctx_eval_reduce": (ctypes.c_int, [_V, ctypes.POINTER(EvalOpts)]),
+    "ms_ctx_eval_project": (ctypes.c_int, [_V, ctypes.POINTER(EvalOpts)]),
     "ms_ctx_read_scalars": (ctypes.c_int, [_V, _D]),
     "ms_ctx_eval": (ctypes.c_int, [_V, ctypes.POINTER(EvalOpts), _D]),
     "ms_ctx_eval_host": (ctypes.c_int, [_V, ctypes.POINTER(EvalOpts), _D, _D, _D, _D, _D]),

@@ -75,6 +75,7 @@ class DeviceMesh:
         self.device = int(device)
         self.nv = 0
         self.nf = 0
+        self.n_owned = 0
         if threads is not None or max_owned is not None or max_local is not None:
             L.check(self._lib.ms_ctx_set_pack_params(self._h, int(threads or 128), int(max_owned or 512),
                                                      int(max_local or 896)))
@@ -95,7 +96,8 @@ class DeviceMesh:
 
     # -- topology and parameters --------------------------------------------
     def set_topology(self, nv: int, tri: np.ndarray, *, is_boundary=None, body_mask=None,
-                     fixed_mask=None) -> None:
+                     fixed_mask=None, n_owned: int | None = None) -> None:
+        """``n_owned`` < nv marks rows [n_owned, nv) as ghosts of other partitions (multi-GPU)."""
         tri = np.ascontiguousarray(tri, dtype=np.int32).reshape(-1, 3)
         keep = [tri]
 
@@ -111,8 +113,9 @@ class DeviceMesh:
         b = mask(is_boundary, nv)
         bm = mask(body_mask, tri.shape[0])
         fx = mask(fixed_mask, nv)
-        L.check(self._lib.ms_ctx_set_topology(self._h, int(nv), int(tri.shape[0]), L.iptr(tri),
-                                              L.bptr(b), L.bptr(bm), L.bptr(fx)))
+        self.n_owned = int(nv if n_owned is None else n_owned)
+        L.check(self._lib.ms_ctx_set_topology_partition(self._h, int(nv), self.n_owned, int(tri.shape[0]),
+                                                        L.iptr(tri), L.bptr(b), L.bptr(bm), L.bptr(fx)))
         self.nv = int(nv)
         self.nf = int(tri.shape[0])
 
@@ -224,6 +227,20 @@ class DeviceMesh:
 
     def eval_finish(self, opts: L.EvalOpts) -> None:
         L.check(self._lib.ms_ctx_eval_finish(self._h, ctypes.byref(opts)))
+
+    def eval_reduce(self, opts: L.EvalOpts) -> None:
+        L.check(self._lib.ms_ctx_eval_reduce(self._h, ctypes.byref(opts)))
+
+    def eval_project(self, opts: L.EvalOpts) -> None:
+        L.check(self._lib.ms_ctx_eval_project(self._h, ctypes.byref(opts)))
+
+    # -- halo exchange helpers (multi-GPU partitions) -------------------------
+    def set_send_rows(self, rows: np.ndarray) -> None:
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        L.check(self._lib.ms_ctx_set_send_rows(self._h, L.iptr(rows), int(rows.size)))
+
+    def pack_send(self, which: int, out_device_ptr: int) -> None:
+        L.check(self._lib.ms_ctx_pack_send(self._h, int(which), ctypes.c_void_p(int(out_device_ptr))))
 
     def read_scalars(self) -> EvalResult:
         sc = np.zeros(L.SC_COUNT)

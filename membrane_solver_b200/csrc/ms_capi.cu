@@ -60,6 +60,7 @@ struct ms_ctx {
   cudaStream_t stream = nullptr;
   bool have_topology = false;
   int32_t nv = 0, nf = 0;
+  int32_t n_owned = 0;  // vertex rows owned by this context's patches (== nv unless partitioned)
   ms::PackParams pack_params;
   int32_t groups_a = 1, groups_b = 2;  // thread groups per CTA in pass A / pass B (PatchLaunch::groups)
   ms::PackedMesh packed;  // recs / slot_facet kept on the host for gamma repacking
@@ -79,6 +80,8 @@ struct ms_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<cudaEvent_t> events;
   DevBuf<uint8_t> d_flush;
+  DevBuf<int32_t> d_send_rows;  // rows other partitions read from this one (halo exchange)
+  int64_t n_send_rows = 0;
 };
 
 namespace {
@@ -278,10 +281,18 @@ int ms_ctx_set_groups(ms_ctx* c, int32_t groups_a, int32_t groups_b) {
 int ms_ctx_set_topology(ms_ctx* c, int32_t nv, int32_t nf, const int32_t* tri,
                         const uint8_t* is_boundary, const uint8_t* body_mask,
                         const uint8_t* fixed_mask) {
+  return ms_ctx_set_topology_partition(c, nv, nv, nf, tri, is_boundary, body_mask, fixed_mask);
+}
+
+int ms_ctx_set_topology_partition(ms_ctx* c, int32_t nv, int32_t n_owned, int32_t nf,
+                                  const int32_t* tri, const uint8_t* is_boundary,
+                                  const uint8_t* body_mask, const uint8_t* fixed_mask) {
   if (int rc = check_ctx(c, false)) return rc;
-  if (nv < 0 || nf < 0 || (nf > 0 && !tri)) return fail(-1, "bad topology arguments");
+  if (nv < 0 || nf < 0 || (nf > 0 && !tri) || n_owned < 0 || n_owned > nv)
+    return fail(-1, "bad topology arguments");
   c->have_topology = false;
-  const int prc = ms::pack_patches(nv, nf, tri, body_mask, c->pack_params, c->packed);
+  c->n_owned = n_owned;
+  const int prc = ms::pack_patches(nv, nf, tri, body_mask, c->pack_params, c->packed, n_owned);
   if (prc == -2) return fail(-8, "a vertex neighbourhood exceeds max_local; raise it with ms_ctx_set_pack_params");
   if (prc) return fail(-1, "pack_patches failed");
   c->nv = nv;
@@ -290,7 +301,7 @@ int ms_ctx_set_topology(ms_ctx* c, int32_t nv, int32_t nf, const int32_t* tri,
   const size_t np = pk.patches.size();
   c->v_lo.resize(np + 1);
   for (size_t p = 0; p < np; ++p) c->v_lo[p] = pk.patches[p].v_lo;
-  c->v_lo[np] = nv;
+  c->v_lo[np] = n_owned;
 
   {  // the packed patch must fit the shared-memory window of the widest kernel variant
     ms::PatchLaunch probe;
@@ -309,7 +320,7 @@ int ms_ctx_set_topology(ms_ctx* c, int32_t nv, int32_t nf, const int32_t* tri,
     std::vector<ms::PatchHeader> hdr(pk.patches);
     ms::PatchHeader end;
     std::memset(&end, 0, sizeof(end));
-    end.v_lo = nv;
+    end.v_lo = n_owned;
     end.halo_off = int32_t(pk.halo_ids.size());
     end.slot_off = int64_t(pk.recs.size());
     hdr.push_back(end);
@@ -523,6 +534,11 @@ int ms_ctx_eval_pass_b(ms_ctx* c, const ms_eval_opts* o) {
 }
 
 int ms_ctx_eval_finish(ms_ctx* c, const ms_eval_opts* o) {
+  if (int rc = ms_ctx_eval_reduce(c, o)) return rc;
+  return ms_ctx_eval_project(c, o);
+}
+
+int ms_ctx_eval_reduce(ms_ctx* c, const ms_eval_opts* o) {
   if (int rc = check_ctx(c, true)) return rc;
   if (!o) return fail(-1, "null options");
   const int n_patches = int(c->packed.patches.size());
@@ -531,11 +547,17 @@ int ms_ctx_eval_finish(ms_ctx* c, const ms_eval_opts* o) {
   if (begin < 0 || count < 0 || begin + count > n_patches) return fail(-3, "patch range out of bounds");
   // energies, area, volume and (after pass B) <g,g>, <g,gC>, <gC,gC> in one fixed-order sum
   CU(ms::launch_reduce_partials(c->d_partials.p, begin, count, c->d_scalars.p, c->stream));
+  return 0;
+}
+
+int ms_ctx_eval_project(ms_ctx* c, const ms_eval_opts* o) {
+  if (int rc = check_ctx(c, true)) return rc;
+  if (!o) return fail(-1, "null options");
   if (o->want_grad && (o->constraint_mode >= 0 || o->apply_fixed)) {
     const double* gc = (o->constraint_mode >= 0 && (o->modules & MS_MOD_VOLUME)) ? c->d_volgrad.p : nullptr;
     const uint8_t* fixed = (o->apply_fixed && c->has_fixed) ? c->d_fixed.p : nullptr;
     if (gc || fixed)
-      CU(ms::launch_project(c->d_grad.p, gc, fixed, c->nv, c->d_scalars.p, o->constraint_mode,
+      CU(ms::launch_project(c->d_grad.p, gc, fixed, c->n_owned, c->d_scalars.p, o->constraint_mode,
                             o->k_vol, o->v_target, c->stream));
   }
   return 0;
@@ -578,6 +600,28 @@ int ms_ctx_eval_host(ms_ctx* c, const ms_eval_opts* o, const double* pos_host, d
   return ms_ctx_read_scalars(c, scalars16);
 }
 
+int ms_ctx_set_send_rows(ms_ctx* c, const int32_t* rows, int64_t n) {
+  if (int rc = check_ctx(c, true)) return rc;
+  if (n < 0 || (n > 0 && !rows)) return fail(-1, "bad arguments");
+  for (int64_t i = 0; i < n; ++i)
+    if (rows[i] < 0 || rows[i] >= c->nv) return fail(-1, "send row out of range");
+  if (int rc = c->d_send_rows.ensure(size_t(n) + 1)) return rc;
+  if (n) CU(cudaMemcpy(c->d_send_rows.p, rows, size_t(n) * sizeof(int32_t), cudaMemcpyHostToDevice));
+  c->n_send_rows = n;
+  return 0;
+}
+
+int ms_ctx_pack_send(ms_ctx* c, int which, void* out_device) {
+  if (int rc = check_ctx(c, true)) return rc;
+  int64_t len = 0;
+  const double* src = array_ptr(c, which, &len);
+  if (!src || c->nv <= 0 || len % c->nv) return fail(-1, "array is not a per-vertex array");
+  if (c->n_send_rows > 0 && !out_device) return fail(-1, "null output buffer");
+  CU(ms::launch_gather_rows(src, int(len / c->nv), c->d_send_rows.p, c->n_send_rows,
+                            static_cast<double*>(out_device), c->stream));
+  return 0;
+}
+
 int ms_ctx_make_trial(ms_ctx* c, double alpha) {
   if (int rc = check_ctx(c, true)) return rc;
   if (!c->d_dir.p) return fail(-4, "no search direction uploaded (MS_ARR_DIRECTION)");
@@ -595,7 +639,7 @@ int ms_ctx_accept_trial(ms_ctx* c) {
 
 int ms_ctx_dots(ms_ctx* c) {
   if (int rc = check_ctx(c, true)) return rc;
-  CU(ms::launch_dots(c->d_grad.p, c->d_volgrad.p, 3 * int64_t(c->nv), c->d_dot_partials.p, kDotBlocks,
+  CU(ms::launch_dots(c->d_grad.p, c->d_volgrad.p, 3 * int64_t(c->n_owned), c->d_dot_partials.p, kDotBlocks,
                      c->d_scalars.p, c->stream));
   return 0;
 }

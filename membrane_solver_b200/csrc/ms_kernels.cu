@@ -455,6 +455,16 @@ __global__ void __launch_bounds__(256) k_project(double* g, const double* __rest
   g[i] = x;
 }
 
+__global__ void __launch_bounds__(256) k_gather_rows(const double* __restrict__ src, int width,
+                                                     const int32_t* __restrict__ rows, int64_t n,
+                                                     double* out) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n * width) return;
+  const int64_t r = i / width;
+  const int c = int(i - r * width);
+  out[i] = src[size_t(rows[r]) * width + c];
+}
+
 __global__ void __launch_bounds__(256) k_axpy(const double* __restrict__ x,
                                               const double* __restrict__ d, double alpha,
                                               double* out, int64_t n) {
@@ -685,6 +695,13 @@ cudaError_t launch_project(double* g, const double* gc, const uint8_t* fixed, in
                            cudaStream_t st) {
   if (nv <= 0) return cudaSuccess;
   k_project<<<blocks_for(3 * nv, 256), 256, 0, st>>>(g, gc, fixed, nv, scalars, mode, k_vol, v_target);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gather_rows(const double* src, int width, const int32_t* rows, int64_t n,
+                               double* out, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  k_gather_rows<<<blocks_for(n * width, 256), 256, 0, st>>>(src, width, rows, n, out);
   return cudaGetLastError();
 }
 

@@ -84,6 +84,9 @@ cudaError_t launch_dots(const double* g, const double* gc, int64_t n, double* bl
 cudaError_t launch_project(double* g, const double* gc, const uint8_t* fixed, int64_t nv,
                            double* scalars, int mode, double k_vol, double v_target,
                            cudaStream_t st);
+// out[i*width + c] = src[rows[i]*width + c]: packs the rows a neighbouring partition needs
+cudaError_t launch_gather_rows(const double* src, int width, const int32_t* rows, int64_t n,
+                               double* out, cudaStream_t st);
 // x_out = x + alpha * d  (trial positions of the line search, line_search.py:358-382)
 cudaError_t launch_axpy(const double* x, const double* d, double alpha, double* out, int64_t n,
                         cudaStream_t st);

@@ -69,7 +69,8 @@ int64_t collect(int32_t v_lo, int32_t n, int32_t stamp, const int32_t* tri,
 }  // namespace
 
 int pack_patches(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* body_mask,
-                 const PackParams& prm, PackedMesh& out) {
+                 const PackParams& prm, PackedMesh& out, int32_t n_owned_vertices) {
+  if (n_owned_vertices < 0 || n_owned_vertices > nv) n_owned_vertices = nv;
   if (nv < 0 || nf < 0 || (nf > 0 && !tri) || prm.threads <= 0 || prm.max_owned <= 0 ||
       prm.max_local <= 0 || prm.max_local > 65535)
     return -1;
@@ -94,8 +95,9 @@ int pack_patches(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* body
   std::vector<int32_t> round_of;   // per listed facet
   int32_t stamp = 0;
 
-  for (int32_t v_lo = 0; v_lo < nv;) {
-    int32_t n = std::min(prm.max_owned, nv - v_lo);
+  out.n_owned_vertices = n_owned_vertices;
+  for (int32_t v_lo = 0; v_lo < n_owned_vertices;) {
+    int32_t n = std::min(prm.max_owned, n_owned_vertices - v_lo);
     int64_t n_local = collect(v_lo, n, stamp++, tri, vptr, vfac, s);
     while (n_local > prm.max_local && n > 1) {
       n = std::max(1, n / 2);

@@ -49,6 +49,7 @@ struct PackParams {
 
 struct PackedMesh {
   int32_t nv = 0, nf = 0;
+  int32_t n_owned_vertices = 0;  // rows [0, n_owned_vertices) belong to patches
   PackParams params;
   std::vector<PatchHeader> patches;
   std::vector<int32_t> halo_ids;
@@ -65,8 +66,11 @@ struct PackedMesh {
 // Facets with an index outside [0,nv) are skipped, like surface_energy.f90:57-59.
 // Returns 0, or a negative error code (-1 bad arguments, -2 a single vertex needs
 // more than max_local local vertices).
+// n_owned_vertices (multi-GPU partitions): only vertex rows [0, n_owned_vertices) are owned
+// by patches; rows beyond are ghost vertices of neighbouring partitions, referenced as halo
+// only.  Facets without an owned vertex are not listed.  -1 = all vertices are owned.
 int pack_patches(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* body_mask,
-                 const PackParams& params, PackedMesh& out);
+                 const PackParams& params, PackedMesh& out, int32_t n_owned_vertices = -1);
 
 // Vertex -> corner incidence in CSR form, facet-major order, for the generic
 // (stateless) kernels.  corner id = 3*facet + column.

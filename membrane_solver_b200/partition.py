@@ -1,0 +1,296 @@
+"""Multi-GPU evaluation of one mesh: contiguous vertex partitions with one-ring ghosts.
+
+SURVEY.md section 8(e).  The reference has no distributed path at all; this is the
+B200-native extension BASELINE.json's north_star asks for.  The mesh is ordered along
+a space-filling curve (``synthetic.sfc_order``), so a contiguous vertex range is a
+compact surface region.  Rank ``r`` owns the vertex rows ``[cuts[r], cuts[r+1])`` and
+lists every facet touching an owned vertex; the facet's other vertices that belong to
+neighbouring ranks are *ghost* rows appended after the owned rows (sorted by global id,
+hence grouped by owner rank, so receives land in place without a scatter).
+
+One evaluation on every rank::
+
+    halo(positions)  ->  pass A  ->  halo(seeds)  ->  pass B  ->  reduce
+                     ->  all-reduce(12 scalars)  ->  project (KKT with the global lambda)
+
+The two halo exchanges move ``24`` and ``40`` bytes per ghost vertex (O(sqrt(nv/P))
+ghosts per rank); the all-reduce moves 96 bytes.  ``torch.distributed`` (NCCL over
+NVLink on the GPU box, gloo in the CPU tests) is the transport; the gather of the rows
+a neighbour needs is a kernel of this library (``ms_ctx_pack_send``).
+
+Only numpy is needed to build the partition (``split_mesh``), so the plan is unit
+tested on the CPU; ``PartitionedMesh`` needs a GPU per rank.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+
+@dataclass
+class LocalMesh:
+    """The part of the global mesh one rank holds (local row numbering)."""
+
+    rank: int
+    world: int
+    cuts: np.ndarray            # (world+1,) global vertex cut points
+    n_owned: int
+    ghost_ids: np.ndarray       # (n_ghost,) global ids of the ghost rows, ascending
+    tri: np.ndarray             # (nf_local,3) int32 local rows
+    facet_ids: np.ndarray       # (nf_local,) global facet rows
+    recv_blocks: list = field(default_factory=list)   # [(src_rank, first_ghost, count)]
+
+    @property
+    def nv_local(self) -> int:
+        return self.n_owned + int(self.ghost_ids.size)
+
+    @property
+    def lo(self) -> int:
+        return int(self.cuts[self.rank])
+
+    def global_rows(self) -> np.ndarray:
+        return np.concatenate([np.arange(self.lo, self.lo + self.n_owned, dtype=np.int64),
+                               self.ghost_ids.astype(np.int64)])
+
+
+def vertex_cuts(nv: int, world: int) -> np.ndarray:
+    """Even contiguous split of the vertex rows."""
+    return np.array([(nv * r) // world for r in range(world + 1)], dtype=np.int64)
+
+
+def split_mesh(nv: int, tri: np.ndarray, world: int, rank: int, cuts: np.ndarray | None = None) -> LocalMesh:
+    """Local mesh of ``rank``: owned range, ghosts, facets touching the owned range."""
+    cuts = vertex_cuts(nv, world) if cuts is None else np.asarray(cuts, dtype=np.int64)
+    lo, hi = int(cuts[rank]), int(cuts[rank + 1])
+    tri = np.asarray(tri)
+    inside = (tri >= lo) & (tri < hi)
+    keep = inside.any(axis=1)
+    facet_ids = np.nonzero(keep)[0]
+    t = tri[facet_ids].astype(np.int64)
+    ins = inside[facet_ids]
+    ghost_ids = np.unique(t[~ins])
+    local = np.where(ins, t - lo, 0)
+    if ghost_ids.size:
+        local = np.where(ins, local, (hi - lo) + np.searchsorted(ghost_ids, t))
+    owners = np.searchsorted(cuts, ghost_ids, side="right") - 1
+    blocks = []
+    for src in np.unique(owners):
+        idx = np.nonzero(owners == src)[0]
+        blocks.append((int(src), int(idx[0]), int(idx.size)))  # ascending ids => contiguous block
+    return LocalMesh(rank=rank, world=world, cuts=cuts, n_owned=hi - lo, ghost_ids=ghost_ids,
+                     tri=np.ascontiguousarray(local, dtype=np.int32), facet_ids=facet_ids,
+                     recv_blocks=blocks)
+
+
+def send_lists(local: LocalMesh, all_ghost_ids: list[np.ndarray]) -> list[tuple[int, np.ndarray]]:
+    """Rows of ``local`` (local numbering) that each other rank holds as ghosts.
+
+    ``all_ghost_ids[r]`` is rank r's ``ghost_ids``.  Returned in destination-rank order;
+    the rows for one destination are in ascending global id, which is the order of that
+    destination's receive block.
+    """
+    out = []
+    lo, hi = local.lo, local.lo + local.n_owned
+    for dst, ghosts in enumerate(all_ghost_ids):
+        if dst == local.rank:
+            continue
+        g = np.asarray(ghosts, dtype=np.int64)
+        mine = g[(g >= lo) & (g < hi)]
+        if mine.size:
+            out.append((dst, (mine - lo).astype(np.int32)))
+    return out
+
+
+class HaloExchange:
+    """Exchanges the ghost rows of per-vertex arrays between ranks (torch.distributed).
+
+    ``tensor_of(which)`` must return a 2-D torch tensor view of the whole local array
+    (owned rows then ghost rows); ``pack(which, out)`` must fill ``out`` (n_send, width)
+    with the rows listed in ``send_rows`` (concatenated per destination).
+    """
+
+    def __init__(self, local: LocalMesh, sends: list[tuple[int, np.ndarray]], dist, torch, device):
+        self.local = local
+        self.dist = dist
+        self.torch = torch
+        self.device = device
+        self.sends = sends
+        self.send_rows = (np.concatenate([rows for _, rows in sends]) if sends
+                          else np.zeros(0, dtype=np.int32)).astype(np.int32)
+        self.send_offsets = np.concatenate([[0], np.cumsum([rows.size for _, rows in sends])]).astype(np.int64)
+        self._buffers = {}
+
+    def _buffer(self, width: int):
+        buf = self._buffers.get(width)
+        if buf is None:
+            buf = self.torch.empty((max(1, int(self.send_rows.size)), width), dtype=self.torch.float64,
+                                   device=self.device)
+            self._buffers[width] = buf
+        return buf
+
+    def exchange(self, tensor, pack) -> None:
+        """Fill the ghost rows of ``tensor`` from their owners."""
+        dist, local = self.dist, self.local
+        width = int(tensor.shape[1])
+        buf = self._buffer(width)
+        pack(buf)
+        ops = []
+        for k, (dst, rows) in enumerate(self.sends):
+            a, b = int(self.send_offsets[k]), int(self.send_offsets[k + 1])
+            ops.append(dist.P2POp(dist.isend, buf[a:b], dst))
+        for src, first, count in local.recv_blocks:
+            a = local.n_owned + first
+            ops.append(dist.P2POp(dist.irecv, tensor[a:a + count], src))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+
+
+class PartitionedMesh:
+    """One rank's share of a mesh on its GPU plus the exchange plumbing."""
+
+    def __init__(self, local: LocalMesh, device_index: int, *, body_mask=None, is_boundary=None,
+                 fixed_mask=None, pack=None):
+        import torch
+        import torch.distributed as dist
+
+        from . import _lib as L
+        from .context import DeviceMesh
+
+        self.L = L
+        self.torch = torch
+        self.dist = dist
+        self.local = local
+        self.device = torch.device("cuda", device_index)
+        self.dm = DeviceMesh(device_index, **(pack or {}))
+        self.dm.set_topology(local.nv_local, local.tri, n_owned=local.n_owned, body_mask=body_mask,
+                             is_boundary=is_boundary, fixed_mask=fixed_mask)
+        gathered = [None] * local.world
+        dist.all_gather_object(gathered, local.ghost_ids)
+        sends = send_lists(local, gathered)
+        self.halo = HaloExchange(local, sends, dist, torch, self.device)
+        self.dm.set_send_rows(self.halo.send_rows)
+        # the context launches on the legacy default stream; torch's current stream is the
+        # same stream unless the caller changed it, so kernels and NCCL calls stay ordered
+        self._views = {}
+
+    def view(self, which: int):
+        t = self._views.get(which)
+        if t is None:
+            t = self.torch.as_tensor(self.dm.device_view(which), device=self.device)
+            self._views[which] = t
+        return t
+
+    def exchange(self, which: int) -> None:
+        self.halo.exchange(self.view(which), lambda buf: self.dm.pack_send(which, buf.data_ptr()))
+
+    def eval_async(self, opts, *, exchange_positions: bool = True) -> None:
+        """One distributed evaluation; results stay on the devices (scalars are global)."""
+        L, dm = self.L, self.dm
+        if exchange_positions:
+            self.exchange(L.ARR_TRIAL if opts.use_trial else L.ARR_POSITIONS)
+        dm.eval_pass_a(opts)
+        if opts.want_grad and (opts.modules & L.MOD_BENDING):
+            self.exchange(L.ARR_SEEDS)
+        dm.eval_pass_b(opts)
+        dm.eval_reduce(opts)
+        sc = self.view(L.ARR_SCALARS)
+        self.dist.all_reduce(sc[:12], op=self.dist.ReduceOp.SUM)
+        dm.eval_project(opts)
+
+    def eval(self, opts, **kw):
+        self.eval_async(opts, **kw)
+        return self.dm.read_scalars()
+
+
+def bench_multi_gpu(args, rank: int, world: int, local_rank: int, bench):
+    """N>1 arm of bench.py: weak scaling, ``args.facets`` facets per GPU."""
+    import json
+    import os
+    import time
+
+    import torch
+    import torch.distributed as dist
+
+    from . import _lib as L
+    from .synthetic import frequency_for_facets, icosphere
+
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n = frequency_for_facets(args.facets * world)
+    shm = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+    path = os.path.join(shm, f"ms_b200_bench_{os.environ.get('MASTER_PORT', '0')}_n{n}.npz")
+    t0 = time.perf_counter()
+    if rank == 0:
+        pos, tri = icosphere(n)
+        np.savez(path, pos=pos, tri=tri)
+    dist.barrier()
+    if rank != 0:
+        with np.load(path) as z:
+            pos, tri = z["pos"], z["tri"]
+    dist.barrier()
+    if rank == 0:
+        os.remove(path)
+    t_gen = time.perf_counter() - t0
+    nv, nf = pos.shape[0], tri.shape[0]
+    local = split_mesh(nv, tri, world, rank)
+    del tri
+    pm = PartitionedMesh(local, local_rank, body_mask=np.ones(local.tri.shape[0], np.uint8),
+                         pack=dict(threads=args.threads, max_owned=args.max_owned, max_local=args.max_local,
+                                   groups=tuple(args.groups) if args.groups else None))
+    dm = pm.dm
+    dm.set_surface_tension(1.0)
+    dm.set_bending_params(1.0, 0.0)
+    dm.set_positions(pos[local.global_rows()])
+    del pos
+    opts = dm.options(L.MOD_SURFACE | L.MOD_BENDING | L.MOD_VOLUME, constraint_mode=0)
+
+    sampler = bench.ClockSampler(local_rank)
+    for _ in range(max(3, args.warmup)):
+        pm.eval_async(opts)
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.active.set()
+    ev0.record()
+    for _ in range(args.steps):
+        pm.eval_async(opts)
+    ev1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sampler.active.clear()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=pm.device)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_step = float(ms.item()) / args.steps
+    res = dm.read_scalars()
+    ghosts = torch.tensor([local.ghost_ids.size, pm.halo.send_rows.size], dtype=torch.float64, device=pm.device)
+    dist.all_reduce(ghosts, op=dist.ReduceOp.MAX)
+    sampler.close()
+    if rank == 0:
+        peak, peak_kind = bench._peaks()
+        value = nf / (ms_step * 1e-3) / 1e9
+        line = {
+            "metric": bench.METRIC, "value": value, "unit": bench.UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {**bench.workload_config(args, world), "parallelism": f"vertex-partition x{world}, 1-ring ghosts",
+                       "max_ghost_rows_per_rank": int(ghosts[0].item())},
+            "roofline": {"bound": "hbm", "kernel": "whole step (all ranks)", "achieved": bench.B_STEP * value,
+                         "peak": peak * world, "unit": "GB/s", "frac": bench.B_STEP * value / (peak * world),
+                         "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({peak_kind}) x {world} GPUs",
+                         "bytes_per_facet": bench.B_STEP},
+            "e2e": None,
+            "collectives_per_step": {"halo_exchanges": 2, "all_reduce": 1,
+                                     "halo_bytes_per_rank": int(ghosts[0].item()) * (24 + 40)},
+            "gpu_launches": 6 * args.steps,  # pass A, pass B, reduce, project + 2 halo gathers
+            "clocks": sampler.summary(),
+            "energies": {"surface": res.e_surface, "bending": res.e_bending, "volume": res.volume},
+            "setup_seconds": t_gen,
+        }
+        print(json.dumps(line))
+    dist.destroy_process_group()
+    return 0

@@ -28,13 +28,14 @@ int emul_eval(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* is_boun
               double k_tilt, uint32_t modules, uint32_t flags, int32_t want_grad, int32_t threads,
               int32_t max_owned, int32_t max_local, double* scalars8, double* grad, double* volgrad,
               double* tilt_grad, double* seeds, double* k_vecs, double* a_vor, double* a_eff,
-              double* e_vertex, int64_t* pack_stats /*[n_patches,n_slots,n_listed,max_rounds,max_local,lane_conflicts]*/) {
+              double* e_vertex, int64_t* pack_stats /*[n_patches,n_slots,n_listed,max_rounds,max_local,lane_conflicts]*/,
+              int32_t n_owned /* -1: all */, int32_t phase /* 0: A+B, 1: A only, 2: B only (seeds are input) */) {
   PackParams prm;
   prm.threads = threads;
   prm.max_owned = max_owned;
   prm.max_local = max_local;
   PackedMesh pk;
-  const int rc = pack_patches(nv, nf, tri, body_mask, prm, pk);
+  const int rc = pack_patches(nv, nf, tri, body_mask, prm, pk, n_owned);
   if (rc) return rc;
   if (pack_stats) {
     pack_stats[0] = int64_t(pk.patches.size());
@@ -48,11 +49,12 @@ int emul_eval(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* is_boun
   const bool do_tilt = (modules & MS_MOD_TILT) && tilts;
   const bool willmore = (flags & MS_FLAG_WILLMORE) != 0;
   std::vector<double> seed_store(size_t(nv) * kSeedStrideBody, 0.0);
+  if (phase == 2 && seeds) std::memcpy(seed_store.data(), seeds, seed_store.size() * sizeof(double));
   double total[PS_COUNT] = {0};
   const int T = threads;
 
   // ---- pass A -------------------------------------------------------------
-  if (bending || !want_grad) {
+  if ((bending || !want_grad) && phase != 2) {
     for (const PatchHeader& h : pk.patches) {
       const int P = h.n_owned, L = h.n_owned + h.n_halo;
       std::vector<double> lpos(3 * size_t(L)), t2(size_t(L), 0.0), accK(3 * size_t(P), 0.0),
@@ -104,10 +106,10 @@ int emul_eval(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* is_boun
       for (int k = 0; k < PS_COUNT; ++k) total[k] += sums[k];
     }
   }
-  if (seeds) std::memcpy(seeds, seed_store.data(), seed_store.size() * sizeof(double));
+  if (seeds && phase != 2) std::memcpy(seeds, seed_store.data(), seed_store.size() * sizeof(double));
 
   // ---- pass B -------------------------------------------------------------
-  if (want_grad) {
+  if (want_grad && phase != 1) {
     const bool scalars_here = !bending;
     double total_b[PS_COUNT] = {0};
     for (const PatchHeader& h : pk.patches) {

@@ -52,7 +52,7 @@ def build_emulator():
 
 def emulate(pos, tri, *, modules, flags=0, want_grad=True, is_boundary=None, body_mask=None,
             tilts=None, gamma=None, gamma_u=1.0, kappa=None, c0=None, kappa_u=0.0, c0_u=0.0,
-            k_tilt=0.0, threads=128, max_owned=512, max_local=896):
+            k_tilt=0.0, threads=128, max_owned=512, max_local=896, n_owned=-1, phase=0, seeds=None):
     """Run the emulator; returns a dict of scalars and arrays."""
     global _EMUL
     if _EMUL is None:
@@ -86,7 +86,8 @@ def emulate(pos, tri, *, modules, flags=0, want_grad=True, is_boundary=None, bod
 
     scal = np.zeros(8)
     out = dict(grad=np.zeros((nv, 3)), volgrad=np.zeros((nv, 3)), tilt_grad=np.zeros((nv, 3)),
-               seeds=np.zeros((nv, 5)), k_vecs=np.zeros((nv, 3)), a_vor=np.zeros(nv),
+               seeds=(np.zeros((nv, 5)) if seeds is None else np.ascontiguousarray(seeds, dtype=np.float64).copy()),
+               k_vecs=np.zeros((nv, 3)), a_vor=np.zeros(nv),
                a_eff=np.zeros(nv), e_vertex=np.zeros(nv))
     stats = np.zeros(6, dtype=np.int64)
     rc = _EMUL.emul_eval(
@@ -97,7 +98,8 @@ def emulate(pos, tri, *, modules, flags=0, want_grad=True, is_boundary=None, bod
         ctypes.c_int32(1 if want_grad else 0), ctypes.c_int32(threads), ctypes.c_int32(max_owned),
         ctypes.c_int32(max_local), dptr(scal), dptr(out["grad"]), dptr(out["volgrad"]),
         dptr(out["tilt_grad"]), dptr(out["seeds"]), dptr(out["k_vecs"]), dptr(out["a_vor"]),
-        dptr(out["a_eff"]), dptr(out["e_vertex"]), stats.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)))
+        dptr(out["a_eff"]), dptr(out["e_vertex"]), stats.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+        ctypes.c_int32(n_owned), ctypes.c_int32(phase))
     if rc:
         raise RuntimeError(f"emul_eval failed: {rc}")
     out.update(E_surface=scal[0], area=scal[1], volume=scal[2], E_bending=scal[3], E_tilt=scal[4],
