@@ -1,0 +1,13 @@
+"""B200 twins of the reference's hot-path energy plugins.
+
+Each module keeps the reference contract::
+
+    compute_energy_and_gradient_array(mesh, global_params, param_resolver, *,
+                                      positions, index_map, grad_arr[, tilts, tilt_grad_arr]) -> float
+
+accumulating (``+=``) into the caller-owned arrays, plus the optional
+``compute_energy_array`` and the legacy dict API ``compute_energy_and_gradient``.  On top
+of that each module exposes ``B200_MODULE`` (its kernel bit) and ``b200_configure`` /
+``b200_energy`` so that ``runtime.evaluation_manager.EvaluationManager`` can evaluate all
+loaded B200 modules in ONE fused device pass.
+"""

@@ -1,0 +1,171 @@
+"""Device twin of one reference ``Mesh``: the B200 counterpart of ``GeometryCache``
+(``runtime/energy_context.py:63-276``).
+
+The reference keys its dense host caches on version counters:
+topology <- ``(id(mesh), _facet_loops_version, _vertex_ids_version, _topology_version)``,
+positions <- ``_version``.  ``DeviceState`` mirrors that: the packed topology (patches,
+records, masks) is rebuilt on the device only when the topology key changes (after
+``r`` / ``u`` / a new ``Mesh``); positions are uploaded per evaluation (the line search
+evaluates at arrays that are not the mesh cache, ``line_search.py:358-382``); per-entity
+parameters are re-sent only when their values change.
+
+The state object is attached to the mesh as ``mesh._b200_state`` -- the same way the
+reference's modules attach their memo attributes.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from .. import _lib as L
+from ..context import DeviceMesh
+
+# Test seam: a callable returning an object with the DeviceMesh interface.
+DEVICE_MESH_FACTORY = DeviceMesh
+DEFAULT_DEVICE = 0
+
+
+def _version(mesh, name):
+    return int(getattr(mesh, name, 0) or 0)
+
+
+def topology_key(mesh):
+    return (id(mesh), _version(mesh, "_facet_loops_version"), _version(mesh, "_vertex_ids_version"),
+            _version(mesh, "_topology_version"))
+
+
+def triangle_rows(mesh) -> np.ndarray:
+    """``mesh.triangle_row_cache()`` (``mesh.py:597-624``) as (nf,3) int32; raises for polygons."""
+    tri, _ = mesh.triangle_row_cache()
+    if tri is None:
+        if len(getattr(mesh, "facets", ())) == 0:
+            return np.zeros((0, 3), dtype=np.int32)
+        raise L.B200Error("the B200 path needs a pure triangle mesh (triangle_row_cache() is None); "
+                          "there is no CPU fallback")
+    return np.ascontiguousarray(tri, dtype=np.int32).reshape(-1, 3)
+
+
+def boundary_mask(mesh, nv: int) -> np.ndarray | None:
+    """Rows of ``mesh.boundary_vertex_ids`` (``mesh.py:304-319``); None for a closed mesh."""
+    vids = getattr(mesh, "boundary_vertex_ids", None)
+    if not vids:
+        return None
+    idx = mesh.vertex_index_to_row
+    rows = [idx[v] for v in vids if v in idx]
+    if not rows:
+        return None
+    m = np.zeros(nv, dtype=np.uint8)
+    m[np.asarray(rows, dtype=np.int64)] = 1
+    return m
+
+
+def fixed_mask(mesh, nv: int) -> np.ndarray | None:
+    fm = getattr(mesh, "fixed_mask", None)
+    if fm is None:
+        return None
+    fm = np.asarray(fm() if callable(fm) else fm, dtype=bool)
+    if fm.shape != (nv,) or not fm.any():
+        return None
+    return fm.astype(np.uint8)
+
+
+def body_entries(mesh):
+    """[(body, facet rows, target volume or None)] for every body of the mesh."""
+    out = []
+    for body in getattr(mesh, "bodies", {}).values():
+        rows = body._get_triangle_rows(mesh)
+        target = getattr(body, "target_volume", None)
+        if target is None:
+            target = (getattr(body, "options", None) or {}).get("target_volume")
+        out.append((body, None if rows is None else np.asarray(rows, dtype=np.int64), target))
+    return out
+
+
+class DeviceState:
+    """Packed topology + parameters of one mesh on one GPU."""
+
+    def __init__(self, device: int | None = None):
+        self.dm = DEVICE_MESH_FACTORY(DEFAULT_DEVICE if device is None else device)
+        self.key = None
+        self.nv = 0
+        self.nf = 0
+        self.has_boundary = False
+        self.boundary = None
+        self.body_rows = None      # facet rows flagged REC_BODY on the device
+        self._gamma_key = None
+        self._bend_key = None
+        self._tilt_key = None
+        self._k_tilt = None
+        self.uploads = 0           # topology uploads (tests assert residency with this)
+
+    # -- topology -------------------------------------------------------------
+    def sync_topology(self, mesh, positions: np.ndarray) -> None:
+        key = topology_key(mesh)
+        nv = int(positions.shape[0])
+        if key == self.key and nv == self.nv:
+            return
+        tri = triangle_rows(mesh)
+        bodies = body_entries(mesh)
+        body = None
+        self.body_rows = None
+        if len(bodies) == 1 and bodies[0][1] is not None:
+            body = np.zeros(tri.shape[0], dtype=np.uint8)
+            body[bodies[0][1]] = 1
+            self.body_rows = bodies[0][1]
+        self.boundary = boundary_mask(mesh, nv)
+        self.has_boundary = self.boundary is not None
+        self.dm.set_topology(nv, tri, is_boundary=self.boundary, body_mask=body, fixed_mask=fixed_mask(mesh, nv))
+        self.key, self.nv, self.nf = key, nv, int(tri.shape[0])
+        self._gamma_key = self._bend_key = self._tilt_key = self._k_tilt = None
+        self.uploads += 1
+
+    # -- parameters (sent only when they change) ------------------------------
+    def set_gamma(self, gamma) -> None:
+        g = np.asarray(gamma, dtype=np.float64)
+        key = (g.shape, float(g.sum()), float(g[0]) if g.size else 0.0, float(g[-1]) if g.size else 0.0)
+        if key != self._gamma_key:
+            self.dm.set_surface_tension(g if g.ndim else float(g))
+            self._gamma_key = key
+
+    def set_bending(self, kappa, c0) -> None:
+        k = np.asarray(kappa, dtype=np.float64)
+        c = np.asarray(c0, dtype=np.float64)
+        key = (k.shape, float(k.sum()), float(np.abs(k).max(initial=0.0)), c.shape, float(c.sum()),
+               float(np.abs(c).max(initial=0.0)))
+        if key != self._bend_key:
+            self.dm.set_bending_params(k if k.ndim else float(k), c if c.ndim else float(c))
+            self._bend_key = key
+
+    def set_tilts(self, tilts, k_tilt: float) -> None:
+        t = np.ascontiguousarray(tilts, dtype=np.float64)  # tilts_view() is F-ordered (mesh.py:407)
+        if t.shape != (self.nv, 3):
+            raise ValueError("tilts must have shape (N_vertices, 3)")
+        self.dm.set_tilts(t)
+        if k_tilt != self._k_tilt:
+            self.dm.set_tilt_rigidity(float(k_tilt))
+            self._k_tilt = float(k_tilt)
+
+
+def get_state(mesh, positions: np.ndarray) -> DeviceState:
+    """The mesh's device state, with its topology brought up to date."""
+    st = getattr(mesh, "_b200_state", None)
+    if st is None:
+        st = DeviceState()
+        try:
+            setattr(mesh, "_b200_state", st)
+        except AttributeError:  # slotted mesh objects: keep a side table
+            _SIDE_TABLE[id(mesh)] = st
+    st.sync_topology(mesh, positions)
+    return st
+
+
+_SIDE_TABLE: dict[int, DeviceState] = {}
+
+
+def positions_array(positions) -> np.ndarray:
+    p = np.asarray(positions)
+    if p.dtype != np.float64:
+        raise TypeError("positions must be float64")
+    if p.ndim != 2 or p.shape[1] != 3:
+        raise ValueError("positions must have shape (N_vertices, 3)")
+    return np.ascontiguousarray(p)
