@@ -91,7 +91,9 @@ typedef struct ms_pack_info {
   int64_t n_valid;   /* facets with all indices in range */
   int64_t n_halo;    /* halo vertex references over all patches */
   int64_t n_round_slots; /* sum over patches of rounds x threads (= n_slots) */
-  int64_t n_lane_conflicts; /* corner placements sharing a bank residue within a half-warp */
+  int64_t n_lane_conflicts; /* facets sharing a bank residue with another facet of their half-warp */
+  int64_t n_hw_groups;      /* (round, half-warp, corner) gather groups holding at least one facet */
+  int64_t n_hw_excess;      /* extra shared-memory wavefronts over those groups (0 = conflict free) */
 } ms_pack_info;
 
 /* ---- library ------------------------------------------------------------------ */
@@ -103,11 +105,15 @@ MS_API int ms_device_count(int* count);
  *      runtime/energy_context.py:63-276 and Mesh.positions_view/triangle_row_cache) - */
 MS_API int ms_ctx_create(int device, ms_ctx** out);
 MS_API int ms_ctx_destroy(ms_ctx* ctx);
-/* patch geometry used by the next ms_ctx_set_topology (defaults 128 / 512 / 896) */
+/* patch geometry used by the next ms_ctx_set_topology (defaults 128 / 512 / 896; these are
+ * also the compiled shared-memory capacities, so values may only be lowered) */
 MS_API int ms_ctx_set_pack_params(ms_ctx* ctx, int32_t threads, int32_t max_owned, int32_t max_local);
-/* thread groups per CTA in pass A / pass B (defaults 1 / 2): group g computes round r0+g of a
- * patch while the other groups compute theirs, and the groups then accumulate one after the
- * other; the CTA has groups*threads threads (clamped to 256) */
+/* packer tuning for the next ms_ctx_set_topology: target share (percent) of record slots that
+ * hold a facet (default 90; lower = more free lanes = fewer shared-memory bank clashes) and
+ * the number of lane-placement repair passes (default 0) */
+MS_API int ms_ctx_set_pack_tuning(ms_ctx* ctx, int32_t fill_pct, int32_t repair_sweeps);
+/* kept for ABI stability; the persistent kernels derive the thread-group count from the CTA
+ * size (consumer threads / threads-per-round) */
 MS_API int ms_ctx_set_groups(ms_ctx* ctx, int32_t groups_a, int32_t groups_b);
 /* Re-called only after refine / equiangulate / vertex-average changed the topology
  * (commands/mesh_ops.py:21-78).  is_boundary, body_mask, fixed_mask may be NULL. */
@@ -155,7 +161,7 @@ MS_API int ms_ctx_eval_async(ms_ctx* ctx, const ms_eval_opts* opts);
 MS_API int ms_ctx_eval_pass_a(ms_ctx* ctx, const ms_eval_opts* opts);
 MS_API int ms_ctx_eval_pass_b(ms_ctx* ctx, const ms_eval_opts* opts);
 MS_API int ms_ctx_eval_finish(ms_ctx* ctx, const ms_eval_opts* opts);
-/* ms_ctx_eval_finish = reduce (per-patch partial sums -> 12 scalars on the device) followed by
+/* ms_ctx_eval_finish = reduce (per-CTA running sums -> 12 scalars on the device) followed by
  * project (KKT / penalty / fixed mask).  Multi-GPU: all-reduce MS_ARR_SCALARS[0..11] between. */
 MS_API int ms_ctx_eval_reduce(ms_ctx* ctx, const ms_eval_opts* opts);
 MS_API int ms_ctx_eval_project(ms_ctx* ctx, const ms_eval_opts* opts);

@@ -60,6 +60,7 @@ class PackInfo(ctypes.Structure):
         ("n_slots", ctypes.c_int64), ("n_listed", ctypes.c_int64),
         ("n_valid", ctypes.c_int64), ("n_halo", ctypes.c_int64),
         ("n_round_slots", ctypes.c_int64), ("n_lane_conflicts", ctypes.c_int64),
+        ("n_hw_groups", ctypes.c_int64), ("n_hw_excess", ctypes.c_int64),
     ]
 
 
@@ -77,6 +78,7 @@ SIGNATURES = {
     "ms_ctx_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_V)]),
     "ms_ctx_destroy": (ctypes.c_int, [_V]),
     "ms_ctx_set_pack_params": (ctypes.c_int, [_V, _i32, _i32, _i32]),
+    "ms_ctx_set_pack_tuning": (ctypes.c_int, [_V, _i32, _i32]),
     "ms_ctx_set_groups": (ctypes.c_int, [_V, _i32, _i32]),
     "ms_ctx_set_topology": (ctypes.c_int, [_V, _i32, _i32, _I, _B, _B, _B]),
     "ms_ctx_set_topology_partition": (ctypes.c_int, [_V, _i32, _i32, _i32, _I, _B, _B, _B]),

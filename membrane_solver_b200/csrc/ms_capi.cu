@@ -62,7 +62,6 @@ struct ms_ctx {
   int32_t nv = 0, nf = 0;
   int32_t n_owned = 0;  // vertex rows owned by this context's patches (== nv unless partitioned)
   ms::PackParams pack_params;
-  int32_t groups_a = 1, groups_b = 2;  // thread groups per CTA in pass A / pass B (PatchLaunch::groups)
   ms::PackedMesh packed;  // recs / slot_facet kept on the host for gamma repacking
   std::vector<int32_t> v_lo;
 
@@ -72,8 +71,9 @@ struct ms_ctx {
   DevBuf<double> d_slot_gamma;
   DevBuf<uint8_t> d_boundary, d_fixed;
   DevBuf<double> d_kappa, d_c0;
-  DevBuf<double> d_pos, d_trial, d_dir, d_tilts, d_seeds, d_partials, d_grad, d_volgrad,
+  DevBuf<double> d_pos, d_trial, d_dir, d_tilts, d_seeds, d_partials_a, d_partials_b, d_grad, d_volgrad,
       d_tilt_grad, d_scalars, d_dot_partials, d_kvecs, d_avor, d_aeff, d_evert;
+  bool ran_pass_a = false;  // the last evaluation ran pass A (its per-CTA sums are current)
   bool has_gamma = false, has_kappa = false, has_c0 = false, has_boundary = false,
        has_fixed = false, has_body = false;
   double gamma_u = 1.0, kappa_u = 0.0, c0_u = 0.0, k_tilt = 0.0;
@@ -148,7 +148,6 @@ int fill_launch(ms_ctx* c, const ms_eval_opts* o, ms::PatchLaunch& a) {
   a.patch_begin = begin;
   a.patch_count = count;
   a.threads = c->packed.params.threads;
-  a.groups = 1;  // set by the pass entry points
   a.max_owned = c->packed.max_owned;
   a.max_local = c->packed.max_local;
   a.max_slots = c->packed.max_slots;
@@ -170,7 +169,7 @@ int fill_launch(ms_ctx* c, const ms_eval_opts* o, ms::PatchLaunch& a) {
   a.modules = o->modules;
   a.flags = o->flags;
   a.seeds = c->d_seeds.p;
-  a.partials = c->d_partials.p;
+  a.partials = nullptr;  // set by the pass entry points
   a.grad = c->d_grad.p;
   a.volgrad = c->d_volgrad.p;
   if ((o->modules & MS_MOD_TILT)) {
@@ -255,26 +254,27 @@ int ms_ctx_set_stream(ms_ctx* c, void* s) {
 int ms_ctx_set_pack_params(ms_ctx* c, int32_t threads, int32_t max_owned, int32_t max_local) {
   if (!c) return fail(-1, "null context");
   if (threads < 32 || threads > 256 || threads % 32) return fail(-1, "threads must be a multiple of 32 in [32,256]");
-  if (max_owned < 1 || max_local < max_owned || max_local > 65535) return fail(-1, "bad patch sizes");
-  ms::PatchLaunch probe;
-  std::memset(&probe, 0, sizeof(probe));
-  probe.max_owned = max_owned;
-  probe.max_local = max_local;
-  probe.max_slots = 3 * max_owned;  // a triangulated patch lists ~2.3 facets per owned vertex
-  probe.max_rounds = 64;
-  if (ms::pass_b_smem_bytes(probe, true, true) > 227 * 1024)
-    return fail(-1, "patch does not fit in 227 KB of shared memory");
+  if (max_owned < 1 || max_local < max_owned) return fail(-1, "bad patch sizes");
+  if (max_owned > ms::kPatchOwnedCap || max_local > ms::kPatchLocalCap)
+    return fail(-1, "patch sizes exceed the compiled shared-memory capacities (512 owned / 896 local)");
   c->pack_params.threads = threads;
   c->pack_params.max_owned = max_owned;
   c->pack_params.max_local = max_local;
   return 0;
 }
 
+int ms_ctx_set_pack_tuning(ms_ctx* c, int32_t fill_pct, int32_t repair_sweeps) {
+  if (!c) return fail(-1, "null context");
+  if (fill_pct < 10 || fill_pct > 100 || repair_sweeps < 0 || repair_sweeps > 8) return fail(-1, "bad tuning values");
+  c->pack_params.fill_pct = fill_pct;
+  c->pack_params.repair_sweeps = repair_sweeps;
+  return 0;
+}
+
 int ms_ctx_set_groups(ms_ctx* c, int32_t groups_a, int32_t groups_b) {
+  // kept for ABI stability: the persistent kernels derive the group count from the CTA size
   if (!c) return fail(-1, "null context");
   if (groups_a < 1 || groups_a > 8 || groups_b < 1 || groups_b > 8) return fail(-1, "groups must be in [1,8]");
-  c->groups_a = groups_a;
-  c->groups_b = groups_b;
   return 0;
 }
 
@@ -294,6 +294,7 @@ int ms_ctx_set_topology_partition(ms_ctx* c, int32_t nv, int32_t n_owned, int32_
   c->n_owned = n_owned;
   const int prc = ms::pack_patches(nv, nf, tri, body_mask, c->pack_params, c->packed, n_owned);
   if (prc == -2) return fail(-8, "a vertex neighbourhood exceeds max_local; raise it with ms_ctx_set_pack_params");
+  if (prc == -3) return fail(-8, "a vertex neighbourhood needs more record slots than a patch can hold");
   if (prc) return fail(-1, "pack_patches failed");
   c->nv = nv;
   c->nf = nf;
@@ -303,16 +304,8 @@ int ms_ctx_set_topology_partition(ms_ctx* c, int32_t nv, int32_t n_owned, int32_
   for (size_t p = 0; p < np; ++p) c->v_lo[p] = pk.patches[p].v_lo;
   c->v_lo[np] = n_owned;
 
-  {  // the packed patch must fit the shared-memory window of the widest kernel variant
-    ms::PatchLaunch probe;
-    std::memset(&probe, 0, sizeof(probe));
-    probe.max_owned = pk.max_owned;
-    probe.max_local = pk.max_local;
-    probe.max_slots = pk.max_slots;
-    probe.max_rounds = pk.max_rounds;
-    if (ms::pass_b_smem_bytes(probe, true, true) > 227 * 1024)
-      return fail(-8, "a patch exceeds 227 KB of shared memory; lower max_owned/max_local with ms_ctx_set_pack_params");
-  }
+  if (prc == 0 && (pk.max_owned > ms::kPatchOwnedCap || pk.max_local > ms::kPatchLocalCap || pk.max_slots > ms::kPatchSlotCap))
+    return fail(-8, "a patch exceeds the compiled shared-memory capacities");
   if (int rc = c->d_patches.ensure(np + 1)) return rc;
   if (int rc = c->d_halo.ensure(pk.halo_ids.size())) return rc;
   if (int rc = c->d_recs.ensure(pk.recs.size())) return rc;
@@ -347,8 +340,13 @@ int ms_ctx_set_topology_partition(ms_ctx* c, int32_t nv, int32_t n_owned, int32_
   if (int rc = c->d_grad.ensure(n3)) return rc;
   if (int rc = c->d_volgrad.ensure(n3)) return rc;
   if (int rc = c->d_seeds.ensure(size_t(ms::kSeedStride) * size_t(nv))) return rc;
-  if (int rc = c->d_partials.ensure(np * ms::kPartialStride)) return rc;
-  if (np) CU(cudaMemset(c->d_partials.p, 0, np * ms::kPartialStride * sizeof(double)));
+  {  // one row of running sums per persistent CTA and pass (at most one CTA per SM; 1024 is ample)
+    const size_t rows = 1024;
+    if (int rc = c->d_partials_a.ensure(rows * ms::kPartialStride)) return rc;
+    if (int rc = c->d_partials_b.ensure(rows * ms::kPartialStride)) return rc;
+    CU(cudaMemset(c->d_partials_a.p, 0, rows * ms::kPartialStride * sizeof(double)));
+    CU(cudaMemset(c->d_partials_b.p, 0, rows * ms::kPartialStride * sizeof(double)));
+  }
   if (n3) {
     CU(cudaMemset(c->d_grad.p, 0, n3 * sizeof(double)));
     CU(cudaMemset(c->d_volgrad.p, 0, n3 * sizeof(double)));
@@ -385,6 +383,8 @@ int ms_ctx_pack_info(const ms_ctx* c, ms_pack_info* info) {
   info->n_halo = int64_t(pk.halo_ids.size());
   info->n_round_slots = pk.n_round_slots;
   info->n_lane_conflicts = pk.n_lane_conflicts;
+  info->n_hw_groups = pk.n_hw_groups;
+  info->n_hw_excess = pk.n_hw_excess;
   return 0;
 }
 
@@ -515,9 +515,9 @@ int ms_ctx_eval_pass_a(ms_ctx* c, const ms_eval_opts* o) {
   if (int rc = fill_launch(c, o, a)) return rc;
   // Pass A is needed for the bending seeds and for energies; surface/volume-only
   // gradient evaluations do everything in pass B.
-  a.groups = c->groups_a;
-  while (a.groups > 1 && a.groups * a.threads > 256) --a.groups;
-  if (needs_bending(o) || !o->want_grad) CU(ms::launch_pass_a(a, c->stream));
+  a.partials = c->d_partials_a.p;
+  c->ran_pass_a = needs_bending(o) || !o->want_grad;
+  if (c->ran_pass_a) CU(ms::launch_pass_a(a, c->stream));
   return 0;
 }
 
@@ -527,8 +527,7 @@ int ms_ctx_eval_pass_b(ms_ctx* c, const ms_eval_opts* o) {
   if (!o->want_grad) return 0;
   ms::PatchLaunch a;
   if (int rc = fill_launch(c, o, a)) return rc;
-  a.groups = c->groups_b;
-  while (a.groups > 1 && a.groups * a.threads > 256) --a.groups;
+  a.partials = c->d_partials_b.p;
   CU(ms::launch_pass_b(a, needs_bending(o), !needs_bending(o), c->stream));
   return 0;
 }
@@ -541,12 +540,19 @@ int ms_ctx_eval_finish(ms_ctx* c, const ms_eval_opts* o) {
 int ms_ctx_eval_reduce(ms_ctx* c, const ms_eval_opts* o) {
   if (int rc = check_ctx(c, true)) return rc;
   if (!o) return fail(-1, "null options");
-  const int n_patches = int(c->packed.patches.size());
-  const int begin = o->patch_count < 0 ? 0 : o->patch_begin;
-  const int count = o->patch_count < 0 ? n_patches : o->patch_count;
-  if (begin < 0 || count < 0 || begin + count > n_patches) return fail(-3, "patch range out of bounds");
-  // energies, area, volume and (after pass B) <g,g>, <g,gC>, <gC,gC> in one fixed-order sum
-  CU(ms::launch_reduce_partials(c->d_partials.p, begin, count, c->d_scalars.p, c->stream));
+  ms::PatchLaunch a;
+  if (int rc = fill_launch(c, o, a)) return rc;
+  const int rows = ms::patch_grid(a);
+  // energies, area, volume come from pass A when it ran, else from pass B; <g,g>, <g,gC>, <gC,gC>
+  // and the tilt energy come from pass B when a gradient was requested -- one fixed-order sum
+  const bool ran_a = needs_bending(o) || !o->want_grad;
+  unsigned b_mask = 0;
+  if (o->want_grad) {
+    b_mask = (1u << MS_SC_G_G) | (1u << MS_SC_G_GC) | (1u << MS_SC_GC_GC);
+    if (!ran_a) b_mask = 0xfffu;
+  }
+  CU(ms::launch_reduce_partials(c->d_partials_a.p, ran_a ? rows : 0, c->d_partials_b.p, o->want_grad ? rows : 0,
+                                b_mask, c->d_scalars.p, c->stream));
   return 0;
 }
 

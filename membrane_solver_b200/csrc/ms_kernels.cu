@@ -1,12 +1,24 @@
 // sm_100a kernels of the energy+gradient path.
 //
-// Patch kernels (pass A / pass B): one CTA per vertex patch.  The CTA stages the
-// positions (and pass-A vertex results) of its owned + halo vertices in shared
-// memory, walks the patch's facet records round by round -- each thread computes
-// one facet per round, once, entirely in registers -- and adds the corner
-// contributions to shared-memory accumulators of the OWNED vertices with plain
-// read-modify-writes.  Rounds are conflict-free by construction (ms_pack.cpp), so
-// no atomics are needed and the summation order is fixed at pack time.
+// Patch kernels (pass A / pass B): PERSISTENT CTAs, one per SM, each walking its share of
+// the vertex patches.  A CTA is warp-specialised:
+//
+//   * one PRODUCER warp stages patch j+1 into the second shared-memory buffer with
+//     asynchronous copies (cp.async / LDGSTS) while patch j is being computed: records,
+//     halo ids and owned rows first, the halo rows (which need the ids) second.  Global rows
+//     are (nv,3) / (nv,5) arrays-of-structures; they land in shared memory as structure of
+//     arrays, so every component of a local vertex is one address register + an immediate.
+//   * the CONSUMER threads form G groups of `threads` lanes.  The patch's facet records are
+//     scheduled in ROUNDS (ms_pack.cpp): within a round no two facets write the same owned
+//     vertex and the lanes of a half-warp gather from distinct bank pairs.  Group g takes
+//     every G-th round: it computes its facets entirely in registers, then waits for a
+//     token (named barrier), adds the corner contributions to the shared accumulators with
+//     plain read-modify-writes, and passes the token on.  Accumulation therefore happens in
+//     round order -- fixed at pack time, no atomics, run-to-run reproducible -- while the
+//     other groups are computing.  After the last round come the patch's EPILOGUE turns
+//     (vertex stage + seeds in pass A; gradient rows + KKT dot products in pass B), taken by
+//     the groups in the same rotation; accumulators are double buffered so that the next
+//     patch's rounds overlap them.
 //
 // Reference functions replaced: see the header of ms_math.cuh.
 #include "ms_kernels.cuh"
@@ -17,28 +29,27 @@ namespace ms {
 
 namespace {
 
-constexpr int kMaxThreads = 256;
-constexpr int kMaxWarps = kMaxThreads / 32;
 static_assert(kSeedStride == kSeedStrideBody, "seed row layout");
 static_assert(int(SC_E_BENDING_TILT) == int(PS_E_BENDING_TILT) && int(SC_G_G) == int(PS_G_G) &&
                   int(SC_GC_GC) == int(PS_GC_GC) && kPartialStride == PS_COUNT, "partial layout");
 
-// Deterministic block sum of N values per thread; result valid in thread 0.
+// Deterministic block sum of N values per thread over the first n_threads threads (a multiple
+// of 32) synchronised through named barrier `bar`; result valid in thread 0.
 template <int N>
-__device__ __forceinline__ void block_sum(double (&v)[N], double* red) {
+__device__ __forceinline__ void block_sum(double (&v)[N], double* red, int n_threads, int bar) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int n_warps = (blockDim.x + 31) >> 5;
+  const int n_warps = n_threads >> 5;
 #pragma unroll
   for (int k = 0; k < N; ++k) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], off);
   }
-  __syncthreads();  // red may still be read by a previous use
+  asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(n_threads) : "memory");  // red may still be read
   if (lane == 0) {
 #pragma unroll
     for (int k = 0; k < N; ++k) red[warp * N + k] = v[k];
   }
-  __syncthreads();
+  asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(n_threads) : "memory");
   if (warp == 0) {
 #pragma unroll
     for (int k = 0; k < N; ++k) {
@@ -50,338 +61,382 @@ __device__ __forceinline__ void block_sum(double (&v)[N], double* red) {
   }
 }
 
-// ---------------------------------------------------------------------------
-// Staging.  Everything a patch needs is brought into shared memory up front with
-// independent, coalesced loads (three dependent latency levels in total: headers ->
-// {round table, records, halo ids, owned rows} -> halo rows), so that the round loop
-// itself touches shared memory only.
-// ---------------------------------------------------------------------------
-// Bump allocator over the dynamic shared memory window (16-byte granularity).
-struct Carver {
-  unsigned char* p;
-  __device__ explicit Carver(void* base) : p(static_cast<unsigned char*>(base)) {}
-  template <typename T>
-  __device__ T* take(size_t count) {
-    T* r = reinterpret_cast<T*>(p);
-    p += (count * sizeof(T) + 15) / 16 * 16;
-    return r;
-  }
-};
-inline size_t carve_bytes(size_t count, size_t elem) { return (count * elem + 15) / 16 * 16; }
-
-// Ampere-style asynchronous copies (LDGSTS): global -> shared without a register
-// round trip, so every staging load of a patch is in flight at once.
+// ---- asynchronous copies (LDGSTS): global -> shared without a register round trip ----
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return unsigned(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(unsigned(__cvta_generic_to_shared(dst))), "l"(src));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src));
 }
 __device__ __forceinline__ void cp_async8(void* dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(unsigned(__cvta_generic_to_shared(dst))), "l"(src));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src));
 }
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(unsigned(__cvta_generic_to_shared(dst))), "l"(src));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src));
 }
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
-__device__ __forceinline__ void stage_flags(uint8_t* dst, const uint8_t* __restrict__ src,
-                                            const PatchHeader& h, const int32_t* halo_local) {
-  const int L = h.n_owned + h.n_halo;
-  for (int j = threadIdx.x; j < L; j += blockDim.x) {
-    const int row = j < h.n_owned ? h.v_lo + j : halo_local[j - h.n_owned];
-    dst[j] = src ? src[row] : uint8_t(0);
-  }
+// ---- mbarriers (producer <-> consumers) and named barriers (token ring) ----
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  const unsigned addr = smem_u32(bar);
+  unsigned ok = 0;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void named_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
-__device__ __forceinline__ void stage_tilt_sq(double* dst, const double* __restrict__ tilts,
-                                              const PatchHeader& h, const int32_t* halo_local) {
-  const int L = h.n_owned + h.n_halo;
-  for (int j = threadIdx.x; j < L; j += blockDim.x) {
-    const size_t row = size_t(j < h.n_owned ? h.v_lo + j : halo_local[j - h.n_owned]);
-    const double x = tilts[3 * row], y = tilts[3 * row + 1], z = tilts[3 * row + 2];
-    dst[j] = x * x + y * y + z * z;
-  }
-}
+// ---------------------------------------------------------------------------
+// Shared-memory plan.  Capacities are compile-time so that strides fold into immediates;
+// the run-time pack parameters must stay within them (checked by the C-ABI layer).
+// ---------------------------------------------------------------------------
+constexpr int kACap = kPatchOwnedCap + kDumpRows;  // accumulator stride (owned rows + dump rows)
+static_assert(kPatchOwnedCap % 16 == 0 && kPatchLocalCap % 16 == 0 && kPatchSlotCap % 32 == 0, "capacities");
+using DevStrides = StaticStrides<kPatchLocalCap, kACap>;
 
-// First latency level: records, round table, halo ids (all contiguous per patch).
-__device__ __forceinline__ void stage_topology(const PatchLaunch& a, const PatchHeader& h, int n_slots,
-                                               FacetRec* recs, int32_t* halo_local) {
-  const FacetRec* src = a.recs + h.slot_off;
-  for (int j = threadIdx.x; j < n_slots; j += blockDim.x) cp_async8(recs + j, src + j);
-  for (int j = threadIdx.x; j < h.n_halo; j += blockDim.x) cp_async4(halo_local + j, a.halo_ids + h.halo_off + j);
-}
-
-constexpr int kRedDoubles = kMaxWarps * PS_COUNT;  // block_sum scratch: warps x values
-
-struct SmemA {
-  double *pos, *t2, *accK, *accAv, *accAe, *nrm, *red;
-  FacetRec* recs;
-  int32_t* halo;
-  uint8_t* bfl;
-  __device__ SmemA(void* base, const PatchLaunch& a, bool tilt) {
-    Carver c(base);
-    pos = c.take<double>(3 * size_t(a.max_local));
-    t2 = c.take<double>(tilt ? a.max_local : 0);
-    accK = c.take<double>(5 * size_t(a.max_owned));  // K(3P) | A_vor(P) | A_eff(P), zeroed together
-    accAv = accK + 3 * a.max_owned;
-    accAe = accAv + a.max_owned;
-    nrm = c.take<double>(3 * size_t(a.max_owned));
-    red = c.take<double>(kRedDoubles);
-    recs = c.take<FacetRec>(a.max_slots);
-    halo = c.take<int32_t>(size_t(a.max_local));
-    bfl = c.take<uint8_t>(a.max_local);
-  }
+struct PatchHdrS {  // header of the staged patch, written by the producer
+  int32_t v_lo, n_owned, n_halo, n_rounds;
+  int32_t n_slots, pad;
+  int64_t slot_off;
 };
 
-// ---------------------------------------------------------------------------
-// Pass A: facet -> owned-vertex accumulation of K, A_vor, A_eff; per-facet scalars
-// (surface energy, area, volume, tilt energy); vertex stage -> seeds for pass B
-// + bending energy.  Alone, it is the energy-only evaluation of the line search.
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kMaxThreads) k_pass_a(PatchLaunch a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int pid = a.patch_begin + blockIdx.x;
-  const PatchHeader h = a.patches[pid];
-  const int n_slots = int(a.patches[pid + 1].slot_off - h.slot_off);  // sentinel header at the end
-  const int P = h.n_owned;
-  const bool do_tilt = (a.modules & MS_MOD_TILT) && a.tilts != nullptr;
-  const bool do_bending = a.modules & (MS_MOD_BENDING | MS_MOD_BENDING_TILT);
-  SmemA s(smem_raw, a, do_tilt);
+template <int PASS>
+struct Plan {
+  static constexpr int kInDoubles = (PASS == 0 ? 3 : 3 + kSeedStride) * kPatchLocalCap;  // pos (+ seeds)
+  static constexpr int kAccRows = PASS == 0 ? 5 : 6;
+  // byte offsets inside one input buffer
+  static constexpr size_t oPos = 0;
+  static constexpr size_t oSeed = size_t(3) * kPatchLocalCap * 8;
+  static constexpr size_t oRecs = size_t(kInDoubles) * 8;
+  static constexpr size_t oIds = oRecs + size_t(kPatchSlotCap) * sizeof(FacetRec);
+  static constexpr size_t oHdr = oIds + size_t(kPatchLocalCap) * 4;
+  static constexpr size_t kInBytes = oHdr + 32;
+  // whole window: in[2] | acc[2] | mbarriers | reduction scratch | optional arrays
+  static constexpr size_t oAcc = 2 * kInBytes;
+  static constexpr size_t kAccBytes = size_t(kAccRows) * kACap * 8;
+  static constexpr size_t oBars = oAcc + 2 * kAccBytes;
+  static constexpr size_t oRed = oBars + 64;
+  static constexpr size_t oOpt = oRed + size_t(kMaxConsumerWarps) * PS_COUNT * 8;
+};
+// optional arrays (after the fixed part): bfl[2][L] u8, t2[2][L] f64, accAb[2][ACap] f64
+__host__ __device__ inline size_t opt_bytes(bool boundary, bool tilt, bool tilt_acc) {
+  size_t n = 0;
+  if (boundary) n += 2 * size_t(kPatchLocalCap);
+  if (tilt) n += 2 * size_t(kPatchLocalCap) * 8;
+  if (tilt_acc) n += 2 * size_t(kACap) * 8;
+  return n;
+}
 
-  stage_topology(a, h, n_slots, s.recs, s.halo);
-  {  // owned rows do not depend on the halo ids: issue them in the same latency level
-    const double* owned = a.pos + size_t(h.v_lo) * 3;
-    for (int j = threadIdx.x; j < 3 * P; j += blockDim.x) cp_async8(s.pos + j, owned + j);
+__device__ __forceinline__ FacetRec load_rec(const FacetRec* p) {
+  const uint2 w = *reinterpret_cast<const uint2*>(p);
+  FacetRec r;
+  r.a = uint16_t(w.x & 0xffffu);
+  r.b = uint16_t(w.x >> 16);
+  r.c = uint16_t(w.y & 0xffffu);
+  r.flags = uint16_t(w.y >> 16);
+  return r;
+}
+
+// ---------------------------------------------------------------------------
+// The persistent patch kernel.  PASS 0 = pass A (curvature accumulation, per-facet scalars,
+// vertex stage -> seeds; alone it is the energy-only evaluation of the line search);
+// PASS 1 = pass B (shape gradient of surface + bending (+ tilt magnitude) and dV/dx).
+// FAST fixes the configuration of the headline workload at compile time: closed mesh,
+// uniform gamma / kappa / c0, surface + Helfrich bending (analytic) + volume, no tilt.
+// ---------------------------------------------------------------------------
+constexpr uint32_t kFastModules = MS_MOD_SURFACE | MS_MOD_BENDING | MS_MOD_VOLUME;
+
+template <int PASS, bool FAST, int NC>
+__global__ void __launch_bounds__(NC + 32, 1) k_patch(PatchLaunch a, bool bending_b, bool scalars_here_arg) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  using P = Plan<PASS>;
+  const DevStrides ST{};
+  const int tid = threadIdx.x;
+  const int T = a.threads;
+  int G = NC / T;
+  if (G > kMaxGroups) G = kMaxGroups;
+  const int n_active = G * T;  // consumer threads that take turns
+  const int n_my = a.patch_count > int(blockIdx.x) ? (a.patch_count - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x) : 0;
+
+  const uint32_t modules = FAST ? kFastModules : a.modules;
+  const uint32_t flags = FAST ? 0u : a.flags;
+  const bool do_tilt = !FAST && (modules & MS_MOD_TILT) && a.tilts != nullptr;
+  const bool has_boundary = !FAST && a.is_boundary != nullptr;
+  const bool do_bending = FAST ? true : (PASS == 0 ? (modules & (MS_MOD_BENDING | MS_MOD_BENDING_TILT)) != 0 : bending_b);
+  const bool do_volume = FAST ? true : (modules & MS_MOD_VOLUME) != 0;
+  const bool scalars_here = FAST ? false : scalars_here_arg;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P::oBars);  // full[0], full[1], empty[0], empty[1]
+  double* red = reinterpret_cast<double*>(smem + P::oRed);
+  unsigned char* opt = smem + P::oOpt;
+  uint8_t* bfl_base = nullptr;
+  double* t2_base = nullptr;
+  double* ab_base = nullptr;
+  if (has_boundary) { bfl_base = opt; opt += 2 * size_t(kPatchLocalCap); }
+  if (do_tilt) { t2_base = reinterpret_cast<double*>(opt); opt += 2 * size_t(kPatchLocalCap) * 8; }
+  if (do_tilt && PASS == 1) { ab_base = reinterpret_cast<double*>(opt); }
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 32);
+    mbar_init(&bars[1], 32);
+    mbar_init(&bars[2], unsigned(n_active / 32));
+    mbar_init(&bars[3], unsigned(n_active / 32));
   }
-  for (int j = threadIdx.x; j < 5 * a.max_owned; j += blockDim.x) s.accK[j] = 0.0;
-  cp_async_wait_all();
-  __syncthreads();
-  for (int j = threadIdx.x; j < 3 * h.n_halo; j += blockDim.x) {
-    const int v = j / 3, c = j - v * 3;
-    cp_async8(s.pos + 3 * P + j, a.pos + size_t(s.halo[v]) * 3 + c);
+  {  // zero both accumulator buffers (and the tilt area accumulators)
+    double* acc0 = reinterpret_cast<double*>(smem + P::oAcc);
+    for (int j = tid; j < 2 * P::kAccRows * kACap; j += NC + 32) acc0[j] = 0.0;
+    if (ab_base)
+      for (int j = tid; j < 2 * kACap; j += NC + 32) ab_base[j] = 0.0;
   }
-  if (a.is_boundary) stage_flags(s.bfl, a.is_boundary, h, s.halo);
-  if (do_tilt) stage_tilt_sq(s.t2, a.tilts, h, s.halo);
-  cp_async_wait_all();
   __syncthreads();
 
-  LocalA loc;
-  loc.pos = s.pos; loc.bfl = a.is_boundary ? s.bfl : nullptr; loc.t2 = do_tilt ? s.t2 : nullptr;
-  loc.accK = s.accK; loc.accAv = s.accAv; loc.accAe = s.accAe; loc.P = P;
+  if (tid >= NC) {
+    // =========================== producer warp ===========================
+    const int lane = tid - NC;
+    for (int j = 0; j < n_my; ++j) {
+      const int b = j & 1;
+      const int pid = a.patch_begin + int(blockIdx.x) + j * int(gridDim.x);
+      if (j >= 2) mbar_wait(&bars[2 + b], unsigned(((j >> 1) - 1) & 1));
+      const PatchHeader h = a.patches[pid];
+      const int n_slots = int(a.patches[pid + 1].slot_off - h.slot_off);  // sentinel header at the end
+      unsigned char* in = smem + size_t(b) * P::kInBytes;
+      double* pos = reinterpret_cast<double*>(in + P::oPos);
+      double* seed = reinterpret_cast<double*>(in + P::oSeed);
+      FacetRec* recs = reinterpret_cast<FacetRec*>(in + P::oRecs);
+      int32_t* ids = reinterpret_cast<int32_t*>(in + P::oIds);
+      if (lane == 0) {
+        PatchHdrS* hs = reinterpret_cast<PatchHdrS*>(in + P::oHdr);
+        hs->v_lo = h.v_lo; hs->n_owned = h.n_owned; hs->n_halo = h.n_halo; hs->n_rounds = h.n_rounds;
+        hs->n_slots = n_slots; hs->pad = 0; hs->slot_off = h.slot_off;
+      }
+      const int Pn = h.n_owned;
+      {  // level 1: records (16-byte copies: slot_off and n_slots are multiples of 32), halo ids, owned rows
+        const FacetRec* src = a.recs + h.slot_off;
+        for (int k = lane; k < (n_slots >> 1); k += 32) cp_async16(recs + 2 * k, src + 2 * k);
+        const int32_t* hsrc = a.halo_ids + h.halo_off;
+        for (int k = lane; k < h.n_halo; k += 32) cp_async4(ids + k, hsrc + k);
+        const double* prow = a.pos + size_t(h.v_lo) * 3;
+        for (int i = lane; i < Pn; i += 32) {
+          cp_async8(pos + i, prow + 3 * i);
+          cp_async8(pos + kPatchLocalCap + i, prow + 3 * i + 1);
+          cp_async8(pos + 2 * kPatchLocalCap + i, prow + 3 * i + 2);
+        }
+        if (PASS == 1 && do_bending) {
+          const double* srow = a.seeds + size_t(h.v_lo) * kSeedStride;
+          for (int i = lane; i < Pn; i += 32) {
+#pragma unroll
+            for (int c = 0; c < kSeedStride; ++c) cp_async8(seed + c * kPatchLocalCap + i, srow + kSeedStride * i + c);
+          }
+        }
+      }
+      cp_async_wait_all();
+      __syncwarp();
+      // level 2: halo rows
+      for (int k = lane; k < h.n_halo; k += 32) {
+        const size_t row = size_t(ids[k]);
+        const int i = Pn + k;
+        const double* prow = a.pos + row * 3;
+        cp_async8(pos + i, prow);
+        cp_async8(pos + kPatchLocalCap + i, prow + 1);
+        cp_async8(pos + 2 * kPatchLocalCap + i, prow + 2);
+        if (PASS == 1 && do_bending) {
+          const double* srow = a.seeds + row * kSeedStride;
+#pragma unroll
+          for (int c = 0; c < kSeedStride; ++c) cp_async8(seed + c * kPatchLocalCap + i, srow + c);
+        }
+      }
+      if (has_boundary || do_tilt) {
+        const int L = Pn + h.n_halo;
+        for (int i = lane; i < L; i += 32) {
+          const size_t row = size_t(i < Pn ? h.v_lo + i : ids[i - Pn]);
+          if (has_boundary) bfl_base[size_t(b) * kPatchLocalCap + i] = a.is_boundary[row];
+          if (do_tilt) {
+            const double x = a.tilts[3 * row], y = a.tilts[3 * row + 1], z = a.tilts[3 * row + 2];
+            t2_base[size_t(b) * kPatchLocalCap + i] = x * x + y * y + z * z;
+          }
+        }
+      }
+      cp_async_wait_all();
+      mbar_arrive(&bars[b]);
+    }
+    return;
+  }
+
+  // ============================= consumers =============================
   double sums[PS_COUNT];
 #pragma unroll
   for (int k = 0; k < PS_COUNT; ++k) sums[k] = 0.0;
 
-  const double* slot_gamma = a.slot_gamma ? a.slot_gamma + h.slot_off : nullptr;
-  const int grp = threadIdx.x / a.threads, lane = threadIdx.x - grp * a.threads;
-  for (int r0 = 0; r0 < h.n_rounds; r0 += a.groups) {
-    // every group computes one round (reads only), then the groups accumulate in turn
-    const int r = r0 + grp;
-    bool act = false;
-    FacetRec rec;
-    CornerA ca;
-    if (r < h.n_rounds) {
-      const int slot = r * a.threads + lane;
-      rec = s.recs[slot];
-      if (rec.flags & REC_VALID) {
-        act = true;
-        const double gam = slot_gamma ? slot_gamma[slot] : a.gamma_u;
-        ca = facet_compute_a(rec, gam, loc, a.modules, a.k_tilt, sums);
-      }
-    }
-    for (int g = 0; g < a.groups; ++g) {
-      __syncthreads();
-      if (act && g == grp) facet_accumulate_a(rec, ca, loc, a.modules);
-    }
-  }
-  __syncthreads();
+  if (tid < n_active) {
+    const int grp = tid / T, lane = tid - grp * T;
+    const int bar_mine = 1 + grp, bar_next = 1 + (grp + 1 == G ? 0 : grp + 1);
+    const int ring = 2 * T;
+    const bool use_ring = G > 1;
+    const bool willmore = (flags & MS_FLAG_WILLMORE) != 0;
+    if (use_ring && grp == G - 1) named_arrive(1, ring);  // group 0 owns the first token
+    int t_rel = grp;   // my next turn, relative to the first turn of the current patch
+    int64_t turns_done = 0;
+    for (int j = 0; j < n_my; ++j) {
+      const int b = j & 1;
+      mbar_wait(&bars[b], unsigned((j >> 1) & 1));
+      unsigned char* in = smem + size_t(b) * P::kInBytes;
+      const PatchHdrS hs = *reinterpret_cast<const PatchHdrS*>(in + P::oHdr);
+      const FacetRec* recs = reinterpret_cast<const FacetRec*>(in + P::oRecs);
+      double* acc = reinterpret_cast<double*>(smem + P::oAcc + size_t(b) * P::kAccBytes);
+      const int Pn = hs.n_owned;
+      const bool want_epi = PASS == 1 || do_bending;
+      const int n_epi = want_epi ? (Pn + T - 1) / T : 0;
+      const int n_turns = hs.n_rounds + n_epi;
+      const double* slot_gamma = (!FAST && a.slot_gamma) ? a.slot_gamma + hs.slot_off : nullptr;
 
-  if (do_bending) {
-    const bool willmore = a.flags & MS_FLAG_WILLMORE;
-    int need = 0;
-    for (int i = threadIdx.x; i < P; i += blockDim.x) need |= vertex_needs_normal(loc, i) ? 1 : 0;
-    const int any_need = __syncthreads_or(need);
-    if (any_need) {
-      for (int j = threadIdx.x; j < 3 * P; j += blockDim.x) s.nrm[j] = 0.0;
-      __syncthreads();
-      for (int r = 0; r < h.n_rounds; ++r) {  // rare path (flat patches): group 0 only
-        if (grp == 0) {
-          const FacetRec rec = s.recs[r * a.threads + lane];
-          if (rec.flags & REC_VALID) normal_body(rec, s.pos, s.nrm, P);
+      LocalA la;
+      LocalB lb;
+      if (PASS == 0) {
+        la.pos = reinterpret_cast<const double*>(in + P::oPos);
+        la.bfl = has_boundary ? bfl_base + size_t(b) * kPatchLocalCap : nullptr;
+        la.t2 = do_tilt ? t2_base + size_t(b) * kPatchLocalCap : nullptr;
+        la.acc = acc;
+        la.P = Pn;
+      } else {
+        lb.pos = reinterpret_cast<const double*>(in + P::oPos);
+        lb.seed = reinterpret_cast<const double*>(in + P::oSeed);
+        lb.bfl = has_boundary ? bfl_base + size_t(b) * kPatchLocalCap : nullptr;
+        lb.t2 = do_tilt ? t2_base + size_t(b) * kPatchLocalCap : nullptr;
+        lb.acc = acc;
+        lb.accAb = ab_base ? ab_base + size_t(b) * kACap : nullptr;
+        lb.P = Pn;
+      }
+
+      for (; t_rel < n_turns; t_rel += G) {
+        if (t_rel < hs.n_rounds) {
+          // ---------------- facet round ----------------
+          const int slot = t_rel * T + lane;
+          const FacetRec rec = load_rec(recs + slot);
+          const bool valid = (rec.flags & REC_VALID) != 0;
+          if (PASS == 0) {
+            CornerA ca;
+            if (valid) {
+              const double gam = slot_gamma ? slot_gamma[slot] : a.gamma_u;
+              ca = facet_compute_a(ST, rec, gam, la, modules, a.k_tilt, sums);
+            }
+            if (use_ring) named_sync(bar_mine, ring); else named_sync(1, T);
+            if (valid && do_bending) facet_accumulate_a(ST, rec, ca, la, modules);
+            if (use_ring) named_arrive(bar_next, ring);
+          } else {
+            FacetOutB out;
+            if (valid) {
+              const double gam = slot_gamma ? slot_gamma[slot] : a.gamma_u;
+              out = do_bending ? facet_compute_b<true>(ST, rec, gam, lb, modules, flags, a.k_tilt, scalars_here, sums)
+                               : facet_compute_b<false>(ST, rec, gam, lb, modules, flags, a.k_tilt, scalars_here, sums);
+            }
+            if (use_ring) named_sync(bar_mine, ring); else named_sync(1, T);
+            if (valid) facet_accumulate_b(ST, rec, out, lb, do_volume, do_tilt);
+            if (use_ring) named_arrive(bar_next, ring);
+          }
+        } else {
+          // ---------------- epilogue turn: owned vertices [e*T, (e+1)*T) ----------------
+          // all earlier turns have accumulated once the token arrives; this slice of the
+          // accumulator belongs to this thread alone from here on, so the token moves on at once
+          if (use_ring) { named_sync(bar_mine, ring); named_arrive(bar_next, ring); } else named_sync(1, T);
+          const int i = (t_rel - hs.n_rounds) * T + lane;
+          if (i < Pn) {
+            const size_t row = size_t(hs.v_lo) + i;
+            if (PASS == 0) {
+              const double kap = (!FAST && a.kappa) ? a.kappa[row] : a.kappa_u;
+              const double c0 = (!FAST && a.c0) ? a.c0[row] : a.c0_u;
+              const VertexSeed sd = vertex_body_a(ST, i, la, recs, hs.n_slots, kap, c0, willmore);
+              sums[PS_E_BENDING] += sd.E;
+              if (a.seeds) {
+                double* o = a.seeds + row * kSeedStride;
+                o[0] = sd.fK.x; o[1] = sd.fK.y; o[2] = sd.fK.z; o[3] = sd.fAe; o[4] = sd.fAv;
+              }
+              if (!FAST) {
+                if (a.k_vecs) {
+                  a.k_vecs[3 * row] = acc[i];
+                  a.k_vecs[3 * row + 1] = acc[kACap + i];
+                  a.k_vecs[3 * row + 2] = acc[2 * kACap + i];
+                }
+                if (a.a_vor) a.a_vor[row] = acc[3 * kACap + i];
+                if (a.a_eff) a.a_eff[row] = acc[4 * kACap + i];
+                if (a.e_vertex) a.e_vertex[row] = sd.E;
+              }
+#pragma unroll
+              for (int c = 0; c < 5; ++c) acc[c * kACap + i] = 0.0;
+            } else {
+              const double gx = acc[i], gy = acc[kACap + i], gz = acc[2 * kACap + i];
+              double* go = a.grad + 3 * row;
+              go[0] = gx; go[1] = gy; go[2] = gz;
+              sums[PS_G_G] += gx * gx + gy * gy + gz * gz;
+              acc[i] = 0.0; acc[kACap + i] = 0.0; acc[2 * kACap + i] = 0.0;
+              if (do_volume && a.volgrad) {
+                const double vx = acc[3 * kACap + i], vy = acc[4 * kACap + i], vz = acc[5 * kACap + i];
+                double* vo = a.volgrad + 3 * row;
+                vo[0] = vx; vo[1] = vy; vo[2] = vz;
+                sums[PS_G_GC] += gx * vx + gy * vy + gz * vz;
+                sums[PS_GC_GC] += vx * vx + vy * vy + vz * vz;
+                acc[3 * kACap + i] = 0.0; acc[4 * kACap + i] = 0.0; acc[5 * kACap + i] = 0.0;
+              }
+              if (do_tilt && lb.accAb) {
+                if (a.tilt_grad) {  // tilt.py:163-170: dE/dt_v = k_t t_v A_bary(v)
+                  const double ab = lb.accAb[i];
+                  a.tilt_grad[3 * row] = a.k_tilt * a.tilts[3 * row] * ab;
+                  a.tilt_grad[3 * row + 1] = a.k_tilt * a.tilts[3 * row + 1] * ab;
+                  a.tilt_grad[3 * row + 2] = a.k_tilt * a.tilts[3 * row + 2] * ab;
+                }
+                lb.accAb[i] = 0.0;
+              }
+            }
+          }
         }
-        __syncthreads();
       }
+      t_rel -= n_turns;
+      turns_done += n_turns;
+      // leaving the patch: its input buffer and accumulator may be reused two patches on
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(&bars[2 + b]);
     }
-    for (int i = threadIdx.x; i < P; i += blockDim.x) {
-      const size_t row = size_t(h.v_lo) + i;
-      const double kap = a.kappa ? a.kappa[row] : a.kappa_u;
-      const double c0 = a.c0 ? a.c0[row] : a.c0_u;
-      const VertexSeed sd = vertex_body_a(i, loc, s.nrm, any_need != 0, kap, c0, willmore);
-      sums[PS_E_BENDING] += sd.E;
-      if (a.seeds) {
-        double* o = a.seeds + row * kSeedStride;
-        o[0] = sd.fK.x; o[1] = sd.fK.y; o[2] = sd.fK.z; o[3] = sd.fAe; o[4] = sd.fAv;
-      }
-      if (a.k_vecs) {
-        a.k_vecs[3 * row] = s.accK[3 * i];
-        a.k_vecs[3 * row + 1] = s.accK[3 * i + 1];
-        a.k_vecs[3 * row + 2] = s.accK[3 * i + 2];
-      }
-      if (a.a_vor) a.a_vor[row] = s.accAv[i];
-      if (a.a_eff) a.a_eff[row] = s.accAe[i];
-      if (a.e_vertex) a.e_vertex[row] = sd.E;
-    }
+    // swallow the token left over by the last turn
+    if (use_ring && int(turns_done % G) == grp) named_sync(bar_mine, ring);
   }
 
-  block_sum<PS_COUNT>(sums, s.red);
-  if (threadIdx.x == 0) {
-    double* p = a.partials + size_t(pid) * kPartialStride;
+  block_sum<PS_COUNT>(sums, red, NC, 15);
+  if (tid == 0) {
+    double* p = a.partials + size_t(blockIdx.x) * kPartialStride;
 #pragma unroll
     for (int k = 0; k < PS_COUNT; ++k) p[k] = sums[k];
   }
 }
 
-struct SmemB {
-  double *pos, *seed, *t2, *accG, *accV, *accAb, *red;
-  FacetRec* recs;
-  int32_t* halo;
-  uint8_t* bfl;
-  __device__ SmemB(void* base, const PatchLaunch& a, bool bending, bool tilt) {
-    Carver c(base);
-    seed = c.take<double>(bending ? size_t(kSeedStride) * a.max_local : 0);
-    pos = c.take<double>(3 * size_t(a.max_local));
-    t2 = c.take<double>(tilt ? a.max_local : 0);
-    accG = c.take<double>(6 * size_t(a.max_owned));  // grad(3P) | dV/dx(3P), zeroed together
-    accV = accG + 3 * a.max_owned;
-    accAb = c.take<double>(tilt ? a.max_owned : 0);
-    red = c.take<double>(kRedDoubles);
-    recs = c.take<FacetRec>(a.max_slots);
-    halo = c.take<int32_t>(size_t(a.max_local));
-    bfl = c.take<uint8_t>(a.max_local);
-  }
-};
-
-// ---------------------------------------------------------------------------
-// Pass B: shape gradient of surface + bending (+ tilt magnitude) and dV/dx.
-// ---------------------------------------------------------------------------
-template <bool BENDING>
-__global__ void __launch_bounds__(kMaxThreads, 2) k_pass_b(PatchLaunch a, bool scalars_here) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int pid = a.patch_begin + blockIdx.x;
-  const PatchHeader h = a.patches[pid];
-  const int n_slots = int(a.patches[pid + 1].slot_off - h.slot_off);
-  const int P = h.n_owned;
-  const bool do_volume = a.modules & MS_MOD_VOLUME;
-  const bool do_tilt = (a.modules & MS_MOD_TILT) && a.tilts != nullptr;
-  SmemB s(smem_raw, a, BENDING, do_tilt);
-
-  stage_topology(a, h, n_slots, s.recs, s.halo);
-  {
-    const double* owned = a.pos + size_t(h.v_lo) * 3;
-    for (int j = threadIdx.x; j < 3 * P; j += blockDim.x) cp_async8(s.pos + j, owned + j);
-    if (BENDING) {
-      const double* so = a.seeds + size_t(h.v_lo) * kSeedStride;
-      for (int j = threadIdx.x; j < kSeedStride * P; j += blockDim.x) cp_async8(s.seed + j, so + j);
-    }
-  }
-  for (int j = threadIdx.x; j < 6 * a.max_owned; j += blockDim.x) s.accG[j] = 0.0;
-  if (do_tilt)
-    for (int j = threadIdx.x; j < P; j += blockDim.x) s.accAb[j] = 0.0;
-  cp_async_wait_all();
-  __syncthreads();
-  for (int j = threadIdx.x; j < 3 * h.n_halo; j += blockDim.x) {
-    const int v = j / 3, c = j - v * 3;
-    cp_async8(s.pos + 3 * P + j, a.pos + size_t(s.halo[v]) * 3 + c);
-  }
-  if (BENDING) {
-    double* d2 = s.seed + kSeedStride * P;
-    for (int j = threadIdx.x; j < kSeedStride * h.n_halo; j += blockDim.x) {
-      const int v = j / kSeedStride, c = j - v * kSeedStride;
-      cp_async8(d2 + j, a.seeds + size_t(s.halo[v]) * kSeedStride + c);
-    }
-    if (a.is_boundary) stage_flags(s.bfl, a.is_boundary, h, s.halo);
-  }
-  if (do_tilt) stage_tilt_sq(s.t2, a.tilts, h, s.halo);
-  cp_async_wait_all();
-  __syncthreads();
-
-  LocalB loc;
-  loc.pos = s.pos; loc.seed = s.seed; loc.bfl = a.is_boundary ? s.bfl : nullptr; loc.t2 = do_tilt ? s.t2 : nullptr;
-  loc.accG = s.accG; loc.accV = s.accV; loc.accAb = s.accAb; loc.P = P;
-  double sums[PS_COUNT];
-#pragma unroll
-  for (int k = 0; k < PS_COUNT; ++k) sums[k] = 0.0;
-
-  const double* slot_gamma = a.slot_gamma ? a.slot_gamma + h.slot_off : nullptr;
-  const int grp = threadIdx.x / a.threads, lane = threadIdx.x - grp * a.threads;
-  for (int r0 = 0; r0 < h.n_rounds; r0 += a.groups) {
-    const int r = r0 + grp;
-    bool act = false;
-    FacetRec rec;
-    FacetOutB out;
-    if (r < h.n_rounds) {
-      const int slot = r * a.threads + lane;
-      rec = s.recs[slot];
-      if (rec.flags & REC_VALID) {
-        act = true;
-        const double gam = slot_gamma ? slot_gamma[slot] : a.gamma_u;
-        out = facet_compute_b<BENDING>(rec, gam, loc, a.modules, a.flags, a.k_tilt, scalars_here, sums);
-      }
-    }
-    for (int g = 0; g < a.groups; ++g) {
-      __syncthreads();
-      if (act && g == grp) facet_accumulate_b(rec, out, loc);
-    }
-  }
-  __syncthreads();
-
-  // owned-vertex results leave as flat, coalesced copies; the dot products of the KKT
-  // projection (constraint_manager.py:294-301) are summed on the way out
-  double* gout = a.grad + size_t(h.v_lo) * 3;
-  const bool vol_out = do_volume && a.volgrad;
-  double* vout = vol_out ? a.volgrad + size_t(h.v_lo) * 3 : nullptr;
-  for (int j = threadIdx.x; j < 3 * P; j += blockDim.x) {
-    const double gj = s.accG[j];
-    gout[j] = gj;
-    sums[PS_G_G] += gj * gj;
-    if (vol_out) {
-      const double vj = s.accV[j];
-      vout[j] = vj;
-      sums[PS_G_GC] += gj * vj;
-      sums[PS_GC_GC] += vj * vj;
-    }
-  }
-  if (do_tilt && a.tilt_grad) {
-    // tilt.py:163-170: dE/dt_v = k_t t_v A_bary(v)
-    const size_t base = size_t(h.v_lo) * 3;
-    for (int j = threadIdx.x; j < 3 * P; j += blockDim.x)
-      a.tilt_grad[base + j] = a.k_tilt * a.tilts[base + j] * s.accAb[j / 3];
-  }
-  block_sum<PS_COUNT>(sums, s.red);
-  if (threadIdx.x == 0) {
-    double* p = a.partials + size_t(pid) * kPartialStride;
-    if (scalars_here) {
-#pragma unroll
-      for (int k = 0; k < PS_COUNT; ++k) p[k] = sums[k];
-    } else {
-      p[PS_E_TILT] = sums[PS_E_TILT];
-      p[PS_G_G] = sums[PS_G_G];
-      p[PS_G_GC] = sums[PS_G_GC];
-      p[PS_GC_GC] = sums[PS_GC_GC];
-    }
-  }
-}
-
-// Fixed-order reduction of the per-patch partial sums (one CTA of 64 x 12 threads:
-// thread (row, k) sums slot k of patches row, row+64, ... -- coalesced -- and 12 threads
-// then add the 64 row sums in index order).
+// Fixed-order reduction of the per-CTA partial sums of pass A and pass B (one CTA of
+// 64 x 12 threads: thread (row, k) sums slot k of rows row, row+64, ... and 12 threads then
+// add the 64 row sums in index order).  Slot k comes from pass B's rows when bit k of
+// b_mask is set, else from pass A's.
 constexpr int kReduceRows = 64;
 __global__ void __launch_bounds__(kReduceRows* kPartialStride)
-    k_reduce_partials(const double* __restrict__ partials, int begin, int count, double* scalars) {
+    k_reduce_partials(const double* __restrict__ pa, int rows_a, const double* __restrict__ pb, int rows_b,
+                      unsigned b_mask, double* scalars) {
   __shared__ double part[kReduceRows][kPartialStride];
   const int k = threadIdx.x % kPartialStride, row = threadIdx.x / kPartialStride;
+  const bool from_b = (b_mask >> k) & 1u;
+  const double* src = from_b ? pb : pa;
+  const int count = from_b ? rows_b : rows_a;
   double v = 0.0;
-  for (int p = row; p < count; p += kReduceRows) v += partials[size_t(begin + p) * kPartialStride + k];
+  for (int p = row; p < count; p += kReduceRows) v += src[size_t(p) * kPartialStride + k];
   part[row][k] = v;
   __syncthreads();
   if (threadIdx.x < kPartialStride) {
@@ -408,7 +463,7 @@ __global__ void __launch_bounds__(256) k_dots(const double* __restrict__ g,
     v[1] += a * b;
     v[2] += b * b;
   }
-  block_sum<3>(v, red);
+  block_sum<3>(v, red, 256, 0);
   if (threadIdx.x == 0) {
     block_partials[3 * blockIdx.x] = v[0];
     block_partials[3 * blockIdx.x + 1] = v[1];
@@ -425,7 +480,7 @@ __global__ void __launch_bounds__(256) k_dots_final(const double* __restrict__ b
     v[1] += block_partials[3 * p + 1];
     v[2] += block_partials[3 * p + 2];
   }
-  block_sum<3>(v, red);
+  block_sum<3>(v, red, 256, 0);
   if (threadIdx.x == 0) {
     scalars[SC_G_G] = v[0];
     scalars[SC_G_GC] = v[1];
@@ -623,7 +678,7 @@ __global__ void __launch_bounds__(256) k_sum(const double* __restrict__ x, int64
   __shared__ double red[32];
   double v[1] = {0.0};
   for (int64_t i = threadIdx.x; i < n; i += blockDim.x) v[0] += x[i];
-  block_sum<1>(v, red);
+  block_sum<1>(v, red, 256, 0);
   if (threadIdx.x == 0) *out = v[0] * scale;
 }
 
@@ -631,55 +686,70 @@ inline int blocks_for(int64_t n, int t) { return int((n + t - 1) / t); }
 
 }  // namespace
 
-static size_t topo_smem_bytes(const PatchLaunch& a) {
-  return carve_bytes(kRedDoubles, 8) + carve_bytes(size_t(a.max_slots), sizeof(FacetRec)) +
-         carve_bytes(size_t(a.max_local), 4) +
-         carve_bytes(size_t(a.max_local), 1);
+namespace {
+int g_num_sms = 0;
+
+template <int PASS>
+size_t patch_smem_bytes(const PatchLaunch& a) {
+  const bool tilt = (a.modules & MS_MOD_TILT) && a.tilts;
+  return Plan<PASS>::oOpt + opt_bytes(a.is_boundary != nullptr, tilt, tilt && PASS == 1);
 }
 
-size_t pass_a_smem_bytes(const PatchLaunch& a, bool tilt) {
-  return carve_bytes(3 * size_t(a.max_local), 8) + carve_bytes(tilt ? a.max_local : 0, 8) +
-         carve_bytes(5 * size_t(a.max_owned), 8) + carve_bytes(3 * size_t(a.max_owned), 8) +
-         topo_smem_bytes(a);
+bool fast_config(const PatchLaunch& a) {
+  return a.modules == kFastModules && a.flags == 0 && !a.is_boundary && !a.slot_gamma && !a.kappa && !a.c0 &&
+         !a.k_vecs && !a.a_vor && !a.a_eff && !a.e_vertex && a.seeds && a.volgrad;
 }
+}  // namespace
 
-size_t pass_b_smem_bytes(const PatchLaunch& a, bool bending, bool tilt) {
-  return carve_bytes(bending ? size_t(kSeedStride) * a.max_local : 0, 8) +
-         carve_bytes(3 * size_t(a.max_local), 8) + carve_bytes(tilt ? a.max_local : 0, 8) +
-         carve_bytes(6 * size_t(a.max_owned), 8) + carve_bytes(tilt ? a.max_owned : 0, 8) +
-         topo_smem_bytes(a);
-}
+size_t pass_a_smem_bytes(const PatchLaunch& a) { return patch_smem_bytes<0>(a); }
+size_t pass_b_smem_bytes(const PatchLaunch& a) { return patch_smem_bytes<1>(a); }
 
 cudaError_t configure_kernels() {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return e;
   const int max_dyn = 227 * 1024;
-  cudaError_t e = cudaFuncSetAttribute(k_pass_a, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_pass_b<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(k_pass_b<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
+  const void* fns[] = {(const void*)k_patch<0, false, kConsumerThreads>, (const void*)k_patch<0, true, kConsumerThreads>,
+                       (const void*)k_patch<1, false, kConsumerThreads>, (const void*)k_patch<1, true, kConsumerThreads>};
+  for (const void* f : fns) {
+    e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+int patch_grid(const PatchLaunch& a) {
+  const int sms = g_num_sms > 0 ? g_num_sms : 148;
+  return a.patch_count < sms ? a.patch_count : sms;
 }
 
 cudaError_t launch_pass_a(const PatchLaunch& a, cudaStream_t st) {
   if (a.patch_count <= 0) return cudaSuccess;
-  const size_t smem = pass_a_smem_bytes(a, (a.modules & MS_MOD_TILT) && a.tilts);
-  k_pass_a<<<a.patch_count, a.threads * a.groups, smem, st>>>(a);
+  const size_t smem = patch_smem_bytes<0>(a);
+  const int grid = patch_grid(a);
+  if (fast_config(a))
+    k_patch<0, true, kConsumerThreads><<<grid, kConsumerThreads + 32, smem, st>>>(a, true, false);
+  else
+    k_patch<0, false, kConsumerThreads><<<grid, kConsumerThreads + 32, smem, st>>>(a, false, false);
   return cudaGetLastError();
 }
 
 cudaError_t launch_pass_b(const PatchLaunch& a, bool bending, bool scalars_here, cudaStream_t st) {
   if (a.patch_count <= 0) return cudaSuccess;
-  const bool tilt = (a.modules & MS_MOD_TILT) && a.tilts;
-  const size_t smem = pass_b_smem_bytes(a, bending, tilt);
-  if (bending)
-    k_pass_b<true><<<a.patch_count, a.threads * a.groups, smem, st>>>(a, scalars_here);
+  const size_t smem = patch_smem_bytes<1>(a);
+  const int grid = patch_grid(a);
+  if (fast_config(a) && bending && !scalars_here)
+    k_patch<1, true, kConsumerThreads><<<grid, kConsumerThreads + 32, smem, st>>>(a, true, false);
   else
-    k_pass_b<false><<<a.patch_count, a.threads * a.groups, smem, st>>>(a, scalars_here);
+    k_patch<1, false, kConsumerThreads><<<grid, kConsumerThreads + 32, smem, st>>>(a, bending, scalars_here);
   return cudaGetLastError();
 }
 
-cudaError_t launch_reduce_partials(const double* partials, int begin, int count, double* scalars,
-                                   cudaStream_t st) {
-  k_reduce_partials<<<1, kReduceRows * kPartialStride, 0, st>>>(partials, begin, count, scalars);
+cudaError_t launch_reduce_partials(const double* pa, int rows_a, const double* pb, int rows_b, unsigned b_mask,
+                                   double* scalars, cudaStream_t st) {
+  k_reduce_partials<<<1, kReduceRows * kPartialStride, 0, st>>>(pa, rows_a, pb, rows_b, b_mask, scalars);
   return cudaGetLastError();
 }
 

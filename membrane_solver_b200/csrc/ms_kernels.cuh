@@ -27,7 +27,19 @@ enum ScalarSlot : int {
 };
 constexpr int kPartialStride = 12;  // per-patch partial sums: slots 0..11 above
 
-constexpr int kSeedStride = 5;  // per-vertex pass-A output: fK(3), fA_eff, fA_vor (odd stride: no bank conflicts)
+constexpr int kSeedStride = 5;  // per-vertex pass-A output: fK(3), fA_eff, fA_vor
+
+// Compile-time capacities of a patch in shared memory (strides of the structure-of-arrays
+// staging buffers).  The run-time pack parameters must not exceed them.
+constexpr int kPatchOwnedCap = 512;   // owned vertices per patch
+constexpr int kPatchLocalCap = 896;   // owned + halo vertices per patch
+constexpr int kPatchSlotCap = 1536;   // record slots per patch (rounds x threads)
+#ifndef MS_CONSUMER_THREADS
+#define MS_CONSUMER_THREADS 480
+#endif
+constexpr int kConsumerThreads = MS_CONSUMER_THREADS;  // + one producer warp per CTA
+constexpr int kMaxConsumerWarps = kConsumerThreads / 32;
+constexpr int kMaxGroups = 8;         // thread groups taking turns (named barriers 1..8)
 
 struct PatchLaunch {
   // packed topology (device)
@@ -36,10 +48,7 @@ struct PatchLaunch {
   const FacetRec* recs;
   const double* slot_gamma;   // per-slot surface tension, or nullptr -> gamma_u
   int32_t patch_begin, patch_count;
-  int32_t threads;            // record slots per round
-  int32_t groups;             // thread groups per CTA (CTA size = groups * threads): group g computes
-                              // round r0+g while the others compute theirs; accumulation is serialised
-                              // (set per launch: pass A and pass B use different values)
+  int32_t threads;            // record slots per round = lanes of one consumer group
   int32_t max_owned, max_local;
   int32_t max_slots, max_rounds;  // largest record count / round count of any patch
   // mesh state (device)
@@ -52,7 +61,7 @@ struct PatchLaunch {
   uint32_t modules, flags;
   // outputs (device)
   double* seeds;      // (nv,kSeedStride)  pass A -> pass B
-  double* partials;   // (n_patches_total, kPartialStride), indexed by absolute patch id
+  double* partials;   // (grid, kPartialStride): one row of running sums per persistent CTA
   double* grad;       // (nv,3)   pass B
   double* volgrad;    // (nv,3)   pass B, when MS_MOD_VOLUME
   double* tilt_grad;  // (nv,3)   pass B, when tilt modules with tilt gradients requested
@@ -63,17 +72,18 @@ struct PatchLaunch {
   double* e_vertex;   // nv   per-vertex bending energy (bending.compute_energy_array)
 };
 
-// only max_owned / max_local / max_slots / max_rounds of the launch descriptor are read
-size_t pass_a_smem_bytes(const PatchLaunch& a, bool tilt);
-size_t pass_b_smem_bytes(const PatchLaunch& a, bool bending, bool tilt);
+size_t pass_a_smem_bytes(const PatchLaunch& a);
+size_t pass_b_smem_bytes(const PatchLaunch& a);
+int patch_grid(const PatchLaunch& a);  // persistent CTAs launched for this patch range (= partial rows)
 
 // scalars_here: also sum the per-facet scalars (surface energy, area, volume).
 cudaError_t launch_pass_a(const PatchLaunch& a, cudaStream_t st);
 cudaError_t launch_pass_b(const PatchLaunch& a, bool bending, bool scalars_here, cudaStream_t st);
-// scalars[0..11] = fixed-order sum over patches [begin, begin+count) of partials; volume slot / 6.
-cudaError_t launch_reduce_partials(const double* partials, int begin, int count, double* scalars,
-                                   cudaStream_t st);
-cudaError_t configure_kernels();  // opt-in to large dynamic shared memory (once per device)
+// scalars[0..11] = fixed-order sums of the per-CTA rows: slot k from pb when bit k of b_mask is set,
+// else from pa; volume slot / 6.
+cudaError_t launch_reduce_partials(const double* pa, int rows_a, const double* pb, int rows_b, unsigned b_mask,
+                                   double* scalars, cudaStream_t st);
+cudaError_t configure_kernels();  // SM count + opt-in to large dynamic shared memory (once per device)
 
 // --- dense vector helpers on (n) doubles: KKT projection of the volume constraint ---
 // scalars[SC_G_G, SC_G_GC, SC_GC_GC] <- deterministic dot products.

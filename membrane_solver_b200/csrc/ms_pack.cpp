@@ -72,7 +72,7 @@ int pack_patches(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* body
                  const PackParams& prm, PackedMesh& out, int32_t n_owned_vertices) {
   if (n_owned_vertices < 0 || n_owned_vertices > nv) n_owned_vertices = nv;
   if (nv < 0 || nf < 0 || (nf > 0 && !tri) || prm.threads <= 0 || prm.max_owned <= 0 ||
-      prm.max_local <= 0 || prm.max_local > 65535)
+      prm.max_local <= 0 || prm.max_local > 65535 || prm.max_slots < prm.threads || prm.fill_pct < 10 || prm.fill_pct > 100)
     return -1;
   out = PackedMesh();
   out.nv = nv;
@@ -96,153 +96,274 @@ int pack_patches(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* body
   int32_t stamp = 0;
 
   out.n_owned_vertices = n_owned_vertices;
+  bool too_many_slots = false;
+  int32_t forced_n = 0;  // retry size after a patch exceeded the slot capacity
   for (int32_t v_lo = 0; v_lo < n_owned_vertices;) {
-    int32_t n = std::min(prm.max_owned, n_owned_vertices - v_lo);
+    int32_t n = std::min(forced_n > 0 ? forced_n : prm.max_owned, n_owned_vertices - v_lo);
     int64_t n_local = collect(v_lo, n, stamp++, tri, vptr, vfac, s);
     while (n_local > prm.max_local && n > 1) {
       n = std::max(1, n / 2);
       n_local = collect(v_lo, n, stamp++, tri, vptr, vfac, s);
     }
     if (n_local > prm.max_local) return -2;
+    // Trim the patch so that its facets fill a whole number of rounds to the target: a patch
+    // with 9.2 rounds' worth of facets would otherwise run 10 rounds at 92 % of the target fill.
+    if (forced_n == 0 && n == prm.max_owned && n > 64) {
+      const double per_round = double(T) * double(prm.fill_pct) / 100.0;
+      const int64_t whole = int64_t(double(s.facets.size()) / per_round);
+      int64_t target = int64_t(double(whole) * per_round);
+      for (int it = 0; it < 4 && whole >= 4 && int64_t(s.facets.size()) > target; ++it) {
+        n = std::max<int32_t>(64, int32_t(double(n) * double(target) / double(s.facets.size())) - (it > 0 ? 2 : 0));
+        n_local = collect(v_lo, n, stamp++, tri, vptr, vfac, s);
+      }
+    }
 
-    // --- schedule the facets into conflict-free rounds ---
-    // A facet may join a round if none of its OWNED corners is written in that round
-    // and the round holds fewer than T facets.  Among the feasible rounds the least
-    // filled one is taken, so rounds stay balanced; a new round opens only when needed.
+    // --- schedule the facets into conflict-free rounds AND bank-conflict-free lanes ---
+    // A facet may join a round if none of its OWNED corners is written in that round and the
+    // round has a free slot.  Round r owns the T record slots [slot_off + r*T, slot_off + (r+1)*T),
+    // i.e. T/16 half-warps.  All patch-local arrays in shared memory are structure-of-arrays with
+    // 8-byte elements, so a 64-bit gather / read-modify-write by a half-warp is conflict free
+    // exactly when the local vertex indices it uses at one corner position are pairwise distinct
+    // modulo 16 (or identical -> broadcast).  ONE clash costs the whole half-warp an extra
+    // wavefront, so the placement looks for a (round, half-warp, rotation) with NO clash at any of
+    // the three corner positions -- the per-facet math is invariant under cyclic relabelling --
+    // preferring the least-filled round; only when none exists does it take the cheapest one.
     const size_t nfac = s.facets.size();
     const int32_t v_hi = v_lo + n;
-    int32_t n_rounds = std::max<int32_t>(int32_t((nfac + size_t(T) - 1) / size_t(T)), std::min<int32_t>(7, int32_t(nfac)));
+    const int n_hw = (T + 15) / 16;
+    int32_t n_rounds = std::max<int32_t>(int32_t((nfac * 100 + size_t(T) * size_t(prm.fill_pct) - 1) / (size_t(T) * size_t(prm.fill_pct))),
+                                         std::min<int32_t>(7, int32_t(nfac)));
     int32_t words = (n_rounds + 63) / 64 + 1;
     used.assign(size_t(n) * size_t(words), 0);
     round_fill.assign(size_t(n_rounds), 0);
-    round_of.assign(nfac, 0);
+    // cnt[((r*n_hw + hw)*3 + k)*16 + residue] = facets of that half-warp whose corner k has that residue
+    std::vector<uint8_t> cnt(size_t(n_rounds) * size_t(n_hw) * 48, 0);
+    std::vector<int32_t> members(size_t(n_rounds) * size_t(n_hw) * 16, -1);  // facet slots of a half-warp
+    std::vector<int32_t> hw_fill(size_t(n_rounds) * size_t(n_hw), 0);
+    struct Place { int32_t r, hw, rot, lane; };
+    std::vector<Place> place(nfac);
+    std::vector<int32_t> floc(3 * nfac);     // local vertex indices of the facets
+    std::vector<int32_t> fown(nfac);         // number of owned corners
     for (size_t i = 0; i < nfac; ++i) {
       const int32_t* t = tri + 3 * size_t(s.facets[i]);
-      int32_t own[3];
       int n_own = 0;
+      for (int k = 0; k < 3; ++k) {
+        const int32_t u = t[k];
+        const bool own = u >= v_lo && u < v_hi;
+        n_own += own ? 1 : 0;
+        floc[3 * i + k] = own ? u - v_lo : n + s.vert_local[u];  // halo slots come from the last collect()
+      }
+      fown[i] = n_own;
+    }
+    auto grow_round = [&]() {
+      ++n_rounds;
+      round_fill.push_back(0);
+      cnt.resize(size_t(n_rounds) * size_t(n_hw) * 48, 0);
+      members.resize(size_t(n_rounds) * size_t(n_hw) * 16, -1);
+      hw_fill.resize(size_t(n_rounds) * size_t(n_hw), 0);
+      if (n_rounds > words * 64) {  // grow the per-vertex masks by one word
+        std::vector<uint64_t> grown(size_t(n) * size_t(words + 1), 0);
+        for (int32_t v = 0; v < n; ++v)
+          for (int32_t w = 0; w < words; ++w)
+            grown[size_t(v) * size_t(words + 1) + w] = used[size_t(v) * size_t(words) + w];
+        used.swap(grown);
+        ++words;
+      }
+    };
+    auto round_free = [&](size_t i, int32_t r) {  // no owned corner of facet i is written in round r
+      for (int k = 0; k < 3; ++k) {
+        const int32_t l = floc[3 * i + k];
+        if (l < n && ((used[size_t(l) * size_t(words) + size_t(r >> 6)] >> (r & 63)) & 1u)) return false;
+      }
+      return true;
+    };
+    auto mark_round = [&](size_t i, int32_t r, bool on) {
+      for (int k = 0; k < 3; ++k) {
+        const int32_t l = floc[3 * i + k];
+        if (l >= n) continue;
+        uint64_t& w = used[size_t(l) * size_t(words) + size_t(r >> 6)];
+        if (on) w |= uint64_t(1) << (r & 63); else w &= ~(uint64_t(1) << (r & 63));
+      }
+    };
+    auto cost_at = [&](size_t i, int32_t r, int hw, int rot) {  // clashing corner positions
+      const uint8_t* c = cnt.data() + (size_t(r) * n_hw + hw) * 48;
+      int cost = 0;
+      for (int k = 0; k < 3; ++k) cost += c[k * 16 + (floc[3 * i + (k + rot) % 3] & 15)] ? 1 : 0;
+      return cost;
+    };
+    auto insert = [&](size_t i, int32_t r, int hw, int rot) {
+      uint8_t* c = cnt.data() + (size_t(r) * n_hw + hw) * 48;
+      for (int k = 0; k < 3; ++k) ++c[k * 16 + (floc[3 * i + (k + rot) % 3] & 15)];
+      int32_t* m = members.data() + (size_t(r) * n_hw + hw) * 16;
+      for (int l = 0; l < 16; ++l)
+        if (m[l] < 0) { m[l] = int32_t(i); break; }
+      ++hw_fill[size_t(r) * n_hw + hw];
+      ++round_fill[r];
+      place[i].r = r; place[i].hw = hw; place[i].rot = rot;
+      mark_round(i, r, true);
+    };
+    auto remove = [&](size_t i) {
+      const Place pl = place[i];
+      uint8_t* c = cnt.data() + (size_t(pl.r) * n_hw + pl.hw) * 48;
+      for (int k = 0; k < 3; ++k) --c[k * 16 + (floc[3 * i + (k + pl.rot) % 3] & 15)];
+      int32_t* m = members.data() + (size_t(pl.r) * n_hw + pl.hw) * 16;
+      for (int l = 0; l < 16; ++l)
+        if (m[l] == int32_t(i)) { m[l] = -1; break; }
+      --hw_fill[size_t(pl.r) * n_hw + pl.hw];
+      --round_fill[pl.r];
+      mark_round(i, pl.r, false);
+    };
+    auto is_bad = [&](size_t i) {  // shares a residue with another facet of its half-warp
+      const Place pl = place[i];
+      const uint8_t* c = cnt.data() + (size_t(pl.r) * n_hw + pl.hw) * 48;
       for (int k = 0; k < 3; ++k)
-        if (t[k] >= v_lo && t[k] < v_hi) own[n_own++] = t[k] - v_lo;
-      int32_t best = -1;
+        if (c[k * 16 + (floc[3 * i + (k + pl.rot) % 3] & 15)] > 1) return true;
+      return false;
+    };
+    // best (round, half-warp, rotation) with a free lane; returns the cost or -1 if no round is feasible
+    auto find_slot = [&](size_t i, int32_t& br, int& bhw, int& brot, int stop_cost) {
+      int best_cost = 1 << 30, best_fill = 1 << 30;
+      br = -1;
       for (int32_t r = 0; r < n_rounds; ++r) {
         if (round_fill[r] >= T) continue;
-        if (best >= 0 && round_fill[r] >= round_fill[best]) continue;
-        bool clash = false;
-        for (int k = 0; k < n_own; ++k)
-          clash |= (used[size_t(own[k]) * size_t(words) + size_t(r >> 6)] >> (r & 63)) & 1u;
-        if (!clash) best = r;
-      }
-      if (best < 0) {
-        best = n_rounds++;
-        round_fill.push_back(0);
-        if (n_rounds > words * 64) {  // grow the per-vertex masks by one word
-          std::vector<uint64_t> grown(size_t(n) * size_t(words + 1), 0);
-          for (int32_t v = 0; v < n; ++v)
-            for (int32_t w = 0; w < words; ++w)
-              grown[size_t(v) * size_t(words + 1) + w] = used[size_t(v) * size_t(words) + w];
-          used.swap(grown);
-          ++words;
+        if (best_cost <= stop_cost && round_fill[r] >= best_fill) continue;
+        if (!round_free(i, r)) continue;
+        for (int hw = 0; hw < n_hw; ++hw) {
+          if (hw_fill[size_t(r) * n_hw + hw] >= std::min(16, T - hw * 16)) continue;
+          bool done = false;
+          for (int rot = 0; rot < 3; ++rot) {
+            const int cost = cost_at(i, r, hw, rot);
+            if (cost < best_cost || (cost == best_cost && round_fill[r] < best_fill)) {
+              best_cost = cost; best_fill = round_fill[r];
+              br = r; bhw = hw; brot = rot;
+            }
+            if (cost == 0) { done = true; break; }
+          }
+          if (done) break;  // this round cannot do better
         }
       }
-      ++round_fill[best];
-      round_of[i] = best;
-      for (int k = 0; k < n_own; ++k)
-        used[size_t(own[k]) * size_t(words) + size_t(best >> 6)] |= uint64_t(1) << (best & 63);
+      return br < 0 ? -1 : best_cost;
+    };
+    for (size_t i = 0; i < nfac; ++i) {
+      int32_t r; int hw, rot;
+      if (find_slot(i, r, hw, rot, 0) < 0) {
+        grow_round();
+        find_slot(i, r, hw, rot, 0);
+      }
+      insert(i, r, hw, rot);
     }
+    // repair: relocate facets that still clash -- to a clash-free free lane anywhere, or by
+    // exchanging places with a facet of another half-warp of the same round
+    for (int sweep = 0; sweep < prm.repair_sweeps; ++sweep) {
+      int64_t fixed = 0;
+      for (size_t i = 0; i < nfac; ++i) {
+        if (!is_bad(i)) continue;
+        const Place old = place[i];
+        remove(i);
+        int32_t r; int hw, rot;
+        if (find_slot(i, r, hw, rot, 0) == 0) {
+          insert(i, r, hw, rot);
+          ++fixed;
+          continue;
+        }
+        bool swapped = false;
+        for (int hw2 = 0; hw2 < n_hw && !swapped; ++hw2) {
+          if (hw2 == old.hw) continue;
+          for (int l = 0; l < 16 && !swapped; ++l) {
+            const int32_t j = members[(size_t(old.r) * n_hw + hw2) * 16 + l];
+            if (j < 0) continue;
+            const Place pj = place[size_t(j)];
+            remove(size_t(j));
+            int rot_i = -1, rot_j = -1;
+            for (int q = 0; q < 3 && rot_i < 0; ++q)
+              if (cost_at(i, old.r, hw2, q) == 0) rot_i = q;
+            for (int q = 0; q < 3 && rot_i >= 0 && rot_j < 0; ++q)
+              if (cost_at(size_t(j), old.r, old.hw, q) == 0) rot_j = q;
+            if (rot_i >= 0 && rot_j >= 0) {
+              insert(i, old.r, hw2, rot_i);
+              insert(size_t(j), old.r, old.hw, rot_j);
+              swapped = true;
+              ++fixed;
+            } else {
+              insert(size_t(j), pj.r, pj.hw, pj.rot);
+            }
+          }
+        }
+        if (!swapped) insert(i, old.r, old.hw, old.rot);
+      }
+      if (fixed == 0) break;
+    }
+    // lanes: position inside the half-warp's member list
+    for (int32_t r = 0; r < n_rounds; ++r)
+      for (int hw = 0; hw < n_hw; ++hw) {
+        int lane = 0;
+        const int32_t* m = members.data() + (size_t(r) * n_hw + hw) * 16;
+        for (int l = 0; l < 16; ++l)
+          if (m[l] >= 0) place[size_t(m[l])].lane = lane++;
+      }
+    int64_t patch_clashes = 0;
+    for (size_t i = 0; i < nfac; ++i) patch_clashes += is_bad(i) ? 1 : 0;
     // drop rounds that stayed empty (tiny patches)
+    std::vector<int32_t> remap(size_t(n_rounds), -1);
     {
-      std::vector<int32_t> remap(size_t(n_rounds), -1);
       int32_t kept = 0;
       for (int32_t r = 0; r < n_rounds; ++r)
         if (round_fill[r] > 0) remap[r] = kept++;
-      for (size_t i = 0; i < nfac; ++i) round_of[i] = remap[round_of[i]];
-      std::vector<int32_t> fill2(size_t(kept), 0);
-      for (int32_t r = 0; r < n_rounds; ++r)
-        if (remap[r] >= 0) fill2[remap[r]] = round_fill[r];
-      round_fill.swap(fill2);
       n_rounds = kept;
     }
+    if (size_t(n_rounds) * size_t(T) > size_t(prm.max_slots) && n > 1) {  // over the slot capacity: halve
+      too_many_slots = true;
+    } else {
+      if (size_t(n_rounds) * size_t(T) > size_t(prm.max_slots)) return -3;
+      // --- emit header, halo list and the records ---
+      PatchHeader h;
+      h.v_lo = v_lo;
+      h.n_owned = n;
+      h.halo_off = int32_t(out.halo_ids.size());
+      h.n_halo = int32_t(s.halo.size());
+      h.slot_off = int64_t(out.recs.size());
+      h.reserved = 0;
+      h.n_rounds = n_rounds;
+      out.patches.push_back(h);
+      out.halo_ids.insert(out.halo_ids.end(), s.halo.begin(), s.halo.end());
 
-    // --- emit header, halo list and the records ---
-    // Round r owns the T record slots [slot_off + r*T, slot_off + (r+1)*T).  Inside a round the
-    // records are placed so that, within every half-warp (16 consecutive lanes), the local
-    // vertex indices seen at corner 0, at corner 1 and at corner 2 are pairwise distinct
-    // modulo 16 (or identical).  All per-vertex rows in shared memory have an odd stride in
-    // doubles (3 or 5), so such a half-warp performs its 64-bit gathers and its
-    // read-modify-writes without bank conflicts.  A facet may be rotated cyclically to fit
-    // (the per-facet math is invariant under cyclic relabelling); unused slots stay invalid.
-    PatchHeader h;
-    h.v_lo = v_lo;
-    h.n_owned = n;
-    h.halo_off = int32_t(out.halo_ids.size());
-    h.n_halo = int32_t(s.halo.size());
-    h.slot_off = int64_t(out.recs.size());
-    h.reserved = 0;
-    h.n_rounds = n_rounds;
-    out.patches.push_back(h);
-    out.halo_ids.insert(out.halo_ids.end(), s.halo.begin(), s.halo.end());
-
-    const size_t base = out.recs.size();
-    const size_t n_slots = size_t(n_rounds) * size_t(T);
-    FacetRec empty;
-    empty.a = empty.b = empty.c = 0;
-    empty.flags = 0;
-    out.recs.resize(base + n_slots, empty);
-    out.slot_facet.resize(base + n_slots, -1);
-
-    const int n_hw = (T + 15) / 16;
-    // occupant[(round*n_hw + hw)*48 + corner*16 + residue] = local index or -1
-    std::vector<int32_t> occupant(size_t(n_rounds) * size_t(n_hw) * 48, -1);
-    std::vector<int32_t> hw_fill(size_t(n_rounds) * size_t(n_hw), 0);
-    for (size_t i = 0; i < nfac; ++i) {
-      const int32_t f = s.facets[i];
-      const int32_t* t = tri + 3 * size_t(f);
-      int32_t loc[3];
-      for (int k = 0; k < 3; ++k) {
-        const int32_t u = t[k];
-        // halo slots were assigned by the last collect() call of this patch
-        loc[k] = (u >= v_lo && u < v_hi) ? (u - v_lo) : (n + s.vert_local[u]);
-      }
-      uint16_t flags = REC_VALID;
-      if (t[0] >= v_lo && t[0] < v_hi) flags |= REC_PRIMARY;
-      if (body_mask && body_mask[f]) flags |= REC_BODY;
-      const int32_t r = round_of[i];
-      int best_hw = -1, best_rot = 0, best_cost = 1 << 30;
-      for (int hw = 0; hw < n_hw && best_cost > 0; ++hw) {
-        const int cap = std::min(16, T - hw * 16);
-        if (hw_fill[size_t(r) * n_hw + hw] >= cap) continue;
-        const int32_t* occ = occupant.data() + (size_t(r) * n_hw + hw) * 48;
-        for (int rot = 0; rot < 3; ++rot) {
-          int cost = 0;
-          for (int k = 0; k < 3; ++k) {
-            const int32_t idx = loc[(k + rot) % 3];
-            const int32_t o = occ[k * 16 + (idx & 15)];
-            cost += (o >= 0 && o != idx) ? 1 : 0;
-          }
-          if (cost < best_cost) {
-            best_cost = cost;
-            best_hw = hw;
-            best_rot = rot;
-            if (cost == 0) break;
-          }
+      const size_t base = out.recs.size();
+      const size_t n_slots = size_t(n_rounds) * size_t(T);
+      FacetRec empty;
+      empty.a = empty.b = empty.c = 0;
+      empty.flags = 0;
+      out.recs.resize(base + n_slots, empty);
+      out.slot_facet.resize(base + n_slots, -1);
+      for (size_t i = 0; i < nfac; ++i) {
+        const int32_t f = s.facets[i];
+        const int32_t* t = tri + 3 * size_t(f);
+        int32_t loc[3];
+        for (int k = 0; k < 3; ++k) {
+          const int32_t u = t[k];
+          loc[k] = (u >= v_lo && u < v_hi) ? (u - v_lo) : (n + s.vert_local[u]);
         }
+        uint16_t flags = REC_VALID;
+        if (t[0] >= v_lo && t[0] < v_hi) flags |= REC_PRIMARY;
+        if (body_mask && body_mask[f]) flags |= REC_BODY;
+        const Place& pl = place[i];
+        FacetRec rec;
+        rec.a = uint16_t(loc[pl.rot % 3]);
+        rec.b = uint16_t(loc[(1 + pl.rot) % 3]);
+        rec.c = uint16_t(loc[(2 + pl.rot) % 3]);
+        rec.flags = flags;
+        const size_t slot = base + size_t(remap[pl.r]) * size_t(T) + size_t(pl.hw) * 16 + size_t(pl.lane);
+        out.recs[slot] = rec;
+        out.slot_facet[slot] = f;
       }
-      // a round never holds more than T facets, so some half-warp has a free lane
-      int32_t* occ = occupant.data() + (size_t(r) * n_hw + best_hw) * 48;
-      for (int k = 0; k < 3; ++k) {
-        const int32_t idx = loc[(k + best_rot) % 3];
-        if (occ[k * 16 + (idx & 15)] < 0) occ[k * 16 + (idx & 15)] = idx;
-      }
-      const int lane = hw_fill[size_t(r) * n_hw + best_hw]++;
-      out.n_lane_conflicts += best_cost;
-      FacetRec rec;
-      rec.a = uint16_t(loc[best_rot % 3]);
-      rec.b = uint16_t(loc[(1 + best_rot) % 3]);
-      rec.c = uint16_t(loc[(2 + best_rot) % 3]);
-      rec.flags = flags;
-      const size_t slot = base + size_t(r) * size_t(T) + size_t(best_hw) * 16 + size_t(lane);
-      out.recs[slot] = rec;
-      out.slot_facet[slot] = f;
     }
+    if (too_many_slots) {
+      too_many_slots = false;
+      forced_n = std::max(1, n / 2);
+      continue;
+    }
+    forced_n = 0;
+    out.n_lane_conflicts += patch_clashes;
+    const size_t n_slots = size_t(n_rounds) * size_t(T);
     out.max_owned = std::max(out.max_owned, n);
     out.max_local = std::max(out.max_local, int32_t(n_local));
     out.max_rounds = std::max(out.max_rounds, n_rounds);
@@ -250,6 +371,37 @@ int pack_patches(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* body
     out.n_round_slots += int64_t(n_rounds) * int64_t(T);
     out.n_listed += int64_t(nfac);
     v_lo += n;
+  }
+  // exact statistic: extra shared-memory wavefronts per (round, half-warp, corner position) =
+  // (largest number of DISTINCT local indices sharing one residue mod 16) - 1
+  out.n_hw_groups = 0;
+  out.n_hw_excess = 0;
+  for (const PatchHeader& h : out.patches) {
+    const int n_hwp = (T + 15) / 16;
+    for (int32_t r = 0; r < h.n_rounds; ++r)
+      for (int hw = 0; hw < n_hwp; ++hw) {
+        const FacetRec* rr = out.recs.data() + size_t(h.slot_off) + size_t(r) * size_t(T) + size_t(hw) * 16;
+        const int cap = std::min(16, T - hw * 16);
+        bool any = false;
+        for (int l = 0; l < cap; ++l) any |= (rr[l].flags & REC_VALID) != 0;
+        if (!any) continue;
+        for (int k = 0; k < 3; ++k) {
+          int32_t seen[16][16];
+          int cnt[16] = {0};
+          for (int l = 0; l < cap; ++l) {
+            if (!(rr[l].flags & REC_VALID)) continue;
+            const int32_t idx = k == 0 ? rr[l].a : (k == 1 ? rr[l].b : rr[l].c);
+            const int res = idx & 15;
+            bool dup = false;
+            for (int j = 0; j < cnt[res]; ++j) dup |= seen[res][j] == idx;
+            if (!dup) seen[res][cnt[res]++] = idx;
+          }
+          int mx = 1;
+          for (int q = 0; q < 16; ++q) mx = std::max(mx, cnt[q]);
+          out.n_hw_groups += 1;
+          out.n_hw_excess += mx - 1;
+        }
+      }
   }
   return 0;
 }

@@ -42,9 +42,12 @@ static_assert(sizeof(FacetRec) == 8, "FacetRec layout");
 enum : uint16_t { REC_VALID = 1, REC_PRIMARY = 2, REC_BODY = 4 };
 
 struct PackParams {
-  int32_t threads = 128;     // record slots per round (= CTA size)
+  int32_t threads = 96;      // record slots per round (= lanes of one consumer group)
   int32_t max_owned = 512;   // owned vertices per patch
   int32_t max_local = 896;   // owned + halo vertices per patch (shared-memory budget)
+  int32_t max_slots = 1536;  // record slots per patch (rounds x threads; shared-memory budget)
+  int32_t repair_sweeps = 0; // lane-placement repair passes (0 = greedy only)
+  int32_t fill_pct = 90;     // target share of valid slots: lower = more free lanes = fewer bank clashes
 };
 
 struct PackedMesh {
@@ -58,6 +61,8 @@ struct PackedMesh {
   int32_t max_owned = 0, max_local = 0, max_rounds = 0, max_slots = 0;
   int64_t n_round_slots = 0;  // sum over patches of n_rounds * threads (== recs.size())
   int64_t n_lane_conflicts = 0;  // corner placements that share a bank residue inside a half-warp
+  int64_t n_hw_groups = 0;  // (round, half-warp, corner position) gather groups holding a facet
+  int64_t n_hw_excess = 0;  // extra shared-memory wavefronts over those groups (0 = conflict free)
   int64_t n_listed = 0;   // facet listings over all patches (>= valid facets)
   int64_t n_valid = 0;    // facets with all indices in range
 };
@@ -65,7 +70,7 @@ struct PackedMesh {
 // body_mask: nf bytes (nonzero = facet in the body) or nullptr (no facet flagged).
 // Facets with an index outside [0,nv) are skipped, like surface_energy.f90:57-59.
 // Returns 0, or a negative error code (-1 bad arguments, -2 a single vertex needs
-// more than max_local local vertices).
+// more than max_local local vertices, -3 a single vertex needs more than max_slots slots).
 // n_owned_vertices (multi-GPU partitions): only vertex rows [0, n_owned_vertices) are owned
 // by patches; rows beyond are ghost vertices of neighbouring partitions, referenced as halo
 // only.  Facets without an owned vertex are not listed.  -1 = all vertices are owned.

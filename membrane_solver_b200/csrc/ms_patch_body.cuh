@@ -1,6 +1,11 @@
 // Per-record and per-vertex bodies of the patch kernels, written against
-// patch-LOCAL arrays so that the device kernels (shared memory) and the test-only
-// host emulator (tests/emul/emul.cpp, heap arrays) execute the very same code.
+// patch-LOCAL structure-of-arrays so that the device kernels (shared memory,
+// compile-time strides) and the test-only host emulator (tests/emul/emul.cpp, heap
+// arrays, run-time strides) execute the very same code.
+//
+// Layout of a patch-local array family: component k of local vertex i lives at
+// base[k * stride + i].  With a compile-time stride every component of a vertex is
+// reached from ONE address register plus an immediate offset.
 #pragma once
 
 #include "../../include/ms_b200.h"
@@ -9,14 +14,7 @@
 
 namespace ms {
 
-MS_HD d3 ld3(const double* p, int i) { return make_d3(p[3 * i], p[3 * i + 1], p[3 * i + 2]); }
-MS_HD void add3(double* p, int i, d3 v) {
-  p[3 * i] += v.x;
-  p[3 * i + 1] += v.y;
-  p[3 * i + 2] += v.z;
-}
-
-// Per-patch partial sums (one row of PatchLaunch::partials).
+// Per-thread running sums (reduced once per kernel; one row per CTA in PatchLaunch::partials).
 enum PartialSlot : int {
   PS_E_SURFACE = 0,
   PS_AREA = 1,
@@ -30,22 +28,49 @@ enum PartialSlot : int {
   PS_COUNT = 12,
 };
 
+constexpr int kSeedStrideBody = 5;  // global seed rows: fK(3), fA_eff, fA_vor
+constexpr int kDumpRows = 16;       // accumulator rows that swallow halo-corner contributions
+
+// Strides of the patch-local arrays.  Device: compile-time constants; emulator: run-time.
+template <int LS, int AS>
+struct StaticStrides {
+  static constexpr int L = LS;  // per-local-vertex inputs (positions, seeds, flags)
+  static constexpr int A = AS;  // owned-vertex accumulators (+ kDumpRows)
+};
+struct DynamicStrides {
+  int L, A;
+};
+
+// array-of-structures row i of an (n,3) array (global memory, stateless kernels)
+MS_HD d3 ld3(const double* p, int i) { return make_d3(p[3 * i], p[3 * i + 1], p[3 * i + 2]); }
+MS_HD d3 ld3s(const double* p, int stride, int i) {
+  return make_d3(p[i], p[stride + i], p[2 * stride + i]);
+}
+MS_HD void add3s(double* p, int stride, int i, d3 v) {
+  p[i] += v.x;
+  p[stride + i] += v.y;
+  p[2 * stride + i] += v.z;
+}
+
+// Accumulator row of a corner: owned vertices have their own row; halo corners go to one of
+// kDumpRows scratch rows chosen by the SAME residue the gather used, so a half-warp that
+// gathers without bank conflicts also accumulates without them, with no branch.
+// The dump rows are the LAST kDumpRows rows of the accumulator stride (a multiple of 16).
+MS_HD int acc_row(int local, int P, int A) { return local < P ? local : (A - kDumpRows) + (local & (kDumpRows - 1)); }
+
 struct LocalA {
-  const double* pos;   // (L,3)
+  const double* pos;   // 3 x L
   const uint8_t* bfl;  // L  boundary flags; nullptr = closed mesh (no boundary vertex)
   const double* t2;    // L  |tilt|^2 (tilt module only)
-  double* accK;        // (P,3)
-  double* accAv;       // P
-  double* accAe;       // P
+  double* acc;         // 5 x A: K.x K.y K.z A_vor A_eff
   int P;               // owned vertices; local indices >= P are halo (read-only)
 };
 
-// Per-facet scalars (primary listing only) + pass-A corner contributions, computed in
-// registers; the accumulation into the owned-vertex arrays is a separate step so that
-// several thread groups can compute concurrently and accumulate one after the other.
-MS_HD CornerA facet_compute_a(FacetRec rec, double gam, const LocalA& s, uint32_t modules,
+// Per-facet scalars (primary listing only) + pass-A corner contributions, in registers.
+template <class S>
+MS_HD CornerA facet_compute_a(const S& st, FacetRec rec, double gam, const LocalA& s, uint32_t modules,
                               double k_tilt, double* sums) {
-  const d3 v0 = ld3(s.pos, rec.a), v1 = ld3(s.pos, rec.b), v2 = ld3(s.pos, rec.c);
+  const d3 v0 = ld3s(s.pos, st.L, rec.a), v1 = ld3s(s.pos, st.L, rec.b), v2 = ld3s(s.pos, st.L, rec.c);
   const FacetGeom g = facet_geom(v0, v1, v2);
   if (rec.flags & REC_PRIMARY) {
     const double T = 0.5 * g.S;
@@ -64,59 +89,57 @@ MS_HD CornerA facet_compute_a(FacetRec rec, double gam, const LocalA& s, uint32_
   return c;
 }
 
-MS_HD void facet_accumulate_a(FacetRec rec, const CornerA& c, const LocalA& s, uint32_t modules) {
+template <class S>
+MS_HD void facet_accumulate_a(const S& st, FacetRec rec, const CornerA& c, const LocalA& s, uint32_t modules) {
   if (modules & (MS_MOD_BENDING | MS_MOD_BENDING_TILT)) {
-    if (rec.a < s.P) { add3(s.accK, rec.a, c.K0); s.accAv[rec.a] += c.va0; s.accAe[rec.a] += c.ve0; }
-    if (rec.b < s.P) { add3(s.accK, rec.b, c.K1); s.accAv[rec.b] += c.va1; s.accAe[rec.b] += c.ve1; }
-    if (rec.c < s.P) { add3(s.accK, rec.c, c.K2); s.accAv[rec.c] += c.va2; s.accAe[rec.c] += c.ve2; }
+    const int ia = acc_row(rec.a, s.P, st.A), ib = acc_row(rec.b, s.P, st.A), ic = acc_row(rec.c, s.P, st.A);
+    double* av = s.acc + 3 * st.A;
+    double* ae = s.acc + 4 * st.A;
+    add3s(s.acc, st.A, ia, c.K0); av[ia] += c.va0; ae[ia] += c.ve0;
+    add3s(s.acc, st.A, ib, c.K1); av[ib] += c.va1; ae[ib] += c.ve1;
+    add3s(s.acc, st.A, ic, c.K2); av[ic] += c.va2; ae[ic] += c.ve2;
   }
 }
 
-MS_HD void facet_body_a(FacetRec rec, double gam, const LocalA& s, uint32_t modules, double k_tilt,
-                        double* sums) {
-  const CornerA c = facet_compute_a(rec, gam, s, modules, k_tilt, sums);
-  facet_accumulate_a(rec, c, s, modules);
-}
-
-// Area-weighted vertex-normal accumulation (bending_utils.py:13-34), only run for
-// patches where some interior vertex has |K| <= 1e-15 (bending.py:154-158).
-MS_HD void normal_body(FacetRec rec, const double* pos, double* nrm, int P) {
-  const d3 v0 = ld3(pos, rec.a), v1 = ld3(pos, rec.b), v2 = ld3(pos, rec.c);
-  const d3 n = cross(v1 - v0, v2 - v0);
-  if (rec.a < P) add3(nrm, rec.a, n);
-  if (rec.b < P) add3(nrm, rec.b, n);
-  if (rec.c < P) add3(nrm, rec.c, n);
-}
-
-MS_HD bool vertex_needs_normal(const LocalA& s, int i) {
-  const d3 K = ld3(s.accK, i);
-  return !(sqrt(dot(K, K)) > 1.0e-15) && !(s.bfl && s.bfl[i]);
-}
-
-MS_HD VertexSeed vertex_body_a(int i, const LocalA& s, const double* nrm, bool use_normal,
-                               double kappa, double c0, bool willmore) {
+// Area-weighted vertex normal of owned vertex i (bending_utils.py:13-34): only needed where an
+// interior vertex has |K| <= 1e-15 (bending.py:154-158), i.e. on flat regions.  Scans the
+// patch's records in slot order (fixed summation order).
+template <class S>
+MS_HD d3 vertex_normal_scan(const S& st, const FacetRec* recs, int n_slots, const double* pos, int i) {
   d3 n = make_d3(0, 0, 0);
-  if (use_normal) {
-    n = ld3(nrm, i);
-    const double m = sqrt(dot(n, n));
-    if (m > 1.0e-15) n = (1.0 / m) * n;
+  for (int k = 0; k < n_slots; ++k) {
+    const FacetRec rec = recs[k];
+    if (!(rec.flags & REC_VALID)) continue;
+    if (rec.a != i && rec.b != i && rec.c != i) continue;
+    const d3 v0 = ld3s(pos, st.L, rec.a), v1 = ld3s(pos, st.L, rec.b), v2 = ld3s(pos, st.L, rec.c);
+    n = n + cross(v1 - v0, v2 - v0);
   }
-  return vertex_stage(ld3(s.accK, i), s.accAv[i], s.accAe[i], kappa, willmore ? 0.0 : c0,
-                      s.bfl && s.bfl[i] != 0, willmore, n, 0.0);
+  const double m = sqrt(dot(n, n));
+  if (m > 1.0e-15) n = (1.0 / m) * n;
+  return n;
+}
+
+// Vertex stage of owned vertex i (bending.py:112-158).
+template <class S>
+MS_HD VertexSeed vertex_body_a(const S& st, int i, const LocalA& s, const FacetRec* recs, int n_slots,
+                               double kappa, double c0, bool willmore) {
+  const d3 K = ld3s(s.acc, st.A, i);
+  const bool boundary = s.bfl && s.bfl[i] != 0;
+  d3 n = make_d3(0, 0, 0);
+  if (!(sqrt(dot(K, K)) > 1.0e-15) && !boundary) n = vertex_normal_scan(st, recs, n_slots, s.pos, i);
+  return vertex_stage(K, s.acc[3 * st.A + i], s.acc[4 * st.A + i], kappa, willmore ? 0.0 : c0, boundary,
+                      willmore, n, 0.0);
 }
 
 struct LocalB {
-  const double* pos;   // (L,3)
-  const double* seed;  // (L,kSeedStride)   bending only
-  const uint8_t* bfl;  // L                 bending only; nullptr = closed mesh
-  const double* t2;    // L                 tilt only
-  double* accG;        // (P,3) shape gradient
-  double* accV;        // (P,3) dV/dx
-  double* accAb;       // P     barycentric vertex area (tilt gradient)
+  const double* pos;   // 3 x L
+  const double* seed;  // 5 x L   bending only: fK.x fK.y fK.z fA_eff fA_vor
+  const uint8_t* bfl;  // L       bending only; nullptr = closed mesh
+  const double* t2;    // L       tilt only
+  double* acc;         // 6 x A: shape gradient (3), dV/dx (3)
+  double* accAb;       // A       barycentric vertex area (tilt gradient)
   int P;
 };
-
-constexpr int kSeedStrideBody = 5;
 
 // Results of one facet in pass B, held in registers between compute and accumulation.
 struct FacetOutB {
@@ -126,11 +149,11 @@ struct FacetOutB {
   bool in_body;
 };
 
-template <bool BENDING>
-MS_HD FacetOutB facet_compute_b(FacetRec rec, double gam, const LocalB& s, uint32_t modules,
+template <bool BENDING, class S>
+MS_HD FacetOutB facet_compute_b(const S& st, FacetRec rec, double gam, const LocalB& s, uint32_t modules,
                                 uint32_t flags, double k_tilt, bool scalars_here, double* sums) {
   FacetOutB o;
-  const d3 v0 = ld3(s.pos, rec.a), v1 = ld3(s.pos, rec.b), v2 = ld3(s.pos, rec.c);
+  const d3 v0 = ld3s(s.pos, st.L, rec.a), v1 = ld3s(s.pos, st.L, rec.b), v2 = ld3s(s.pos, st.L, rec.c);
   const FacetGeom g = facet_geom(v0, v1, v2);
   const double T = 0.5 * g.S;
   const bool primary = (rec.flags & REC_PRIMARY) != 0;
@@ -152,13 +175,10 @@ MS_HD FacetOutB facet_compute_b(FacetRec rec, double gam, const LocalB& s, uint3
   }
   BendIn b;
   if (BENDING) {
-    // seed rows: 5 doubles (odd stride, see ms_pack.cpp on bank conflicts)
-    const double* sa = s.seed + kSeedStrideBody * rec.a;
-    const double* sb = s.seed + kSeedStrideBody * rec.b;
-    const double* sc = s.seed + kSeedStrideBody * rec.c;
-    b.f0 = make_d3(sa[0], sa[1], sa[2]); b.fe0 = sa[3]; b.fv0 = sa[4];
-    b.f1 = make_d3(sb[0], sb[1], sb[2]); b.fe1 = sb[3]; b.fv1 = sb[4];
-    b.f2 = make_d3(sc[0], sc[1], sc[2]); b.fe2 = sc[3]; b.fv2 = sc[4];
+    const double* q = s.seed;
+    b.f0 = ld3s(q, st.L, rec.a); b.fe0 = q[3 * st.L + rec.a]; b.fv0 = q[4 * st.L + rec.a];
+    b.f1 = ld3s(q, st.L, rec.b); b.fe1 = q[3 * st.L + rec.b]; b.fv1 = q[4 * st.L + rec.b];
+    b.f2 = ld3s(q, st.L, rec.c); b.fe2 = q[3 * st.L + rec.c]; b.fv2 = q[4 * st.L + rec.c];
     if (s.bfl) {
       b.i0 = !s.bfl[rec.a]; b.i1 = !s.bfl[rec.b]; b.i2 = !s.bfl[rec.c];
     } else {
@@ -174,27 +194,24 @@ MS_HD FacetOutB facet_compute_b(FacetRec rec, double gam, const LocalB& s, uint3
   return o;
 }
 
-MS_HD void facet_accumulate_b(FacetRec rec, const FacetOutB& o, const LocalB& s) {
-  if (rec.a < s.P) add3(s.accG, rec.a, o.cg.g0);
-  if (rec.b < s.P) add3(s.accG, rec.b, o.cg.g1);
-  if (rec.c < s.P) add3(s.accG, rec.c, o.cg.g2);
-  if (o.in_body) {
-    if (rec.a < s.P) add3(s.accV, rec.a, o.vg.g0);
-    if (rec.b < s.P) add3(s.accV, rec.b, o.vg.g1);
-    if (rec.c < s.P) add3(s.accV, rec.c, o.vg.g2);
+template <class S>
+MS_HD void facet_accumulate_b(const S& st, FacetRec rec, const FacetOutB& o, const LocalB& s, bool do_volume,
+                              bool do_tilt) {
+  const int ia = acc_row(rec.a, s.P, st.A), ib = acc_row(rec.b, s.P, st.A), ic = acc_row(rec.c, s.P, st.A);
+  add3s(s.acc, st.A, ia, o.cg.g0);
+  add3s(s.acc, st.A, ib, o.cg.g1);
+  add3s(s.acc, st.A, ic, o.cg.g2);
+  if (do_volume && o.in_body) {
+    double* v = s.acc + 3 * st.A;
+    add3s(v, st.A, ia, o.vg.g0);
+    add3s(v, st.A, ib, o.vg.g1);
+    add3s(v, st.A, ic, o.vg.g2);
   }
-  if (s.t2 && o.third != 0.0) {
-    if (rec.a < s.P) s.accAb[rec.a] += o.third;
-    if (rec.b < s.P) s.accAb[rec.b] += o.third;
-    if (rec.c < s.P) s.accAb[rec.c] += o.third;
+  if (do_tilt && o.third != 0.0) {
+    s.accAb[ia] += o.third;
+    s.accAb[ib] += o.third;
+    s.accAb[ic] += o.third;
   }
-}
-
-template <bool BENDING>
-MS_HD void facet_body_b(FacetRec rec, double gam, const LocalB& s, uint32_t modules, uint32_t flags,
-                        double k_tilt, bool scalars_here, double* sums) {
-  const FacetOutB o = facet_compute_b<BENDING>(rec, gam, s, modules, flags, k_tilt, scalars_here, sums);
-  facet_accumulate_b(rec, o, s);
 }
 
 }  // namespace ms

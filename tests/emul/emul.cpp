@@ -28,7 +28,7 @@ int emul_eval(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* is_boun
               double k_tilt, uint32_t modules, uint32_t flags, int32_t want_grad, int32_t threads,
               int32_t max_owned, int32_t max_local, double* scalars8, double* grad, double* volgrad,
               double* tilt_grad, double* seeds, double* k_vecs, double* a_vor, double* a_eff,
-              double* e_vertex, int64_t* pack_stats /*[n_patches,n_slots,n_listed,max_rounds,max_local,lane_conflicts]*/,
+              double* e_vertex, int64_t* pack_stats /*[n_patches,n_slots,n_listed,max_rounds,max_local,lane_conflicts,hw_groups,hw_excess]*/,
               int32_t n_owned /* -1: all */, int32_t phase /* 0: A+B, 1: A only, 2: B only (seeds are input) */) {
   PackParams prm;
   prm.threads = threads;
@@ -44,6 +44,8 @@ int emul_eval(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* is_boun
     pack_stats[3] = pk.max_rounds;
     pack_stats[4] = pk.max_local;
     pack_stats[5] = pk.n_lane_conflicts;
+    pack_stats[6] = pk.n_hw_groups;
+    pack_stats[7] = pk.n_hw_excess;
   }
   const bool bending = (modules & MS_MOD_BENDING) != 0;
   const bool do_tilt = (modules & MS_MOD_TILT) && tilts;
@@ -57,12 +59,16 @@ int emul_eval(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* is_boun
   if ((bending || !want_grad) && phase != 2) {
     for (const PatchHeader& h : pk.patches) {
       const int P = h.n_owned, L = h.n_owned + h.n_halo;
-      std::vector<double> lpos(3 * size_t(L)), t2(size_t(L), 0.0), accK(3 * size_t(P), 0.0),
-          accAv(size_t(P), 0.0), accAe(size_t(P), 0.0), nrm(3 * size_t(P), 0.0);
+      DynamicStrides st;
+      st.L = L;
+      st.A = (P + 15) / 16 * 16 + kDumpRows;
+      const int n_slots = h.n_rounds * T;
+      const FacetRec* recs = pk.recs.data() + size_t(h.slot_off);
+      std::vector<double> lpos(3 * size_t(L)), t2(size_t(L), 0.0), acc(5 * size_t(st.A), 0.0);
       std::vector<uint8_t> bfl(size_t(L), 0);
       for (int j = 0; j < L; ++j) {
         const int row = local_row(pk, h, j);
-        for (int k = 0; k < 3; ++k) lpos[3 * size_t(j) + k] = pos[3 * size_t(row) + k];
+        for (int k = 0; k < 3; ++k) lpos[size_t(k) * L + j] = pos[3 * size_t(row) + k];
         bfl[size_t(j)] = is_boundary ? is_boundary[row] : 0;
         if (do_tilt) {
           const double* t = tilts + 3 * size_t(row);
@@ -71,35 +77,26 @@ int emul_eval(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* is_boun
       }
       LocalA loc;
       loc.pos = lpos.data(); loc.bfl = bfl.data(); loc.t2 = do_tilt ? t2.data() : nullptr;
-      loc.accK = accK.data(); loc.accAv = accAv.data(); loc.accAe = accAe.data(); loc.P = P;
+      loc.acc = acc.data(); loc.P = P;
       double sums[PS_COUNT] = {0};
-      for (int r = 0; r < h.n_rounds; ++r)
-        for (int t = 0; t < T; ++t) {
-          const size_t slot = size_t(h.slot_off) + size_t(r) * size_t(T) + size_t(t);
-          const FacetRec rec = pk.recs[slot];
-          if (!(rec.flags & REC_VALID)) continue;
-          const double gam = gamma ? gamma[pk.slot_facet[slot]] : gamma_u;
-          facet_body_a(rec, gam, loc, modules, k_tilt, sums);
-        }
+      for (int slot = 0; slot < n_slots; ++slot) {
+        const FacetRec rec = recs[slot];
+        if (!(rec.flags & REC_VALID)) continue;
+        const double gam = gamma ? gamma[pk.slot_facet[size_t(h.slot_off) + slot]] : gamma_u;
+        const CornerA c = facet_compute_a(st, rec, gam, loc, modules, k_tilt, sums);
+        facet_accumulate_a(st, rec, c, loc, modules);
+      }
       if (bending) {
-        bool any_need = false;
-        for (int i = 0; i < P; ++i) any_need |= vertex_needs_normal(loc, i);
-        if (any_need)
-          for (int r = 0; r < h.n_rounds; ++r)
-            for (int t = 0; t < T; ++t) {
-              const FacetRec rec = pk.recs[size_t(h.slot_off) + size_t(r) * size_t(T) + size_t(t)];
-              if (rec.flags & REC_VALID) normal_body(rec, lpos.data(), nrm.data(), P);
-            }
         for (int i = 0; i < P; ++i) {
           const size_t row = size_t(h.v_lo) + i;
-          const VertexSeed sd = vertex_body_a(i, loc, nrm.data(), any_need, kappa ? kappa[row] : kappa_u,
+          const VertexSeed sd = vertex_body_a(st, i, loc, recs, n_slots, kappa ? kappa[row] : kappa_u,
                                               c0 ? c0[row] : c0_u, willmore);
           sums[PS_E_BENDING] += sd.E;
           double* o = seed_store.data() + row * kSeedStrideBody;
           o[0] = sd.fK.x; o[1] = sd.fK.y; o[2] = sd.fK.z; o[3] = sd.fAe; o[4] = sd.fAv;
-          if (k_vecs) for (int k = 0; k < 3; ++k) k_vecs[3 * row + k] = accK[3 * size_t(i) + k];
-          if (a_vor) a_vor[row] = accAv[size_t(i)];
-          if (a_eff) a_eff[row] = accAe[size_t(i)];
+          if (k_vecs) for (int k = 0; k < 3; ++k) k_vecs[3 * row + k] = acc[size_t(k) * st.A + i];
+          if (a_vor) a_vor[row] = acc[3 * size_t(st.A) + i];
+          if (a_eff) a_eff[row] = acc[4 * size_t(st.A) + i];
           if (e_vertex) e_vertex[row] = sd.E;
         }
       }
@@ -111,17 +108,23 @@ int emul_eval(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* is_boun
   // ---- pass B -------------------------------------------------------------
   if (want_grad && phase != 1) {
     const bool scalars_here = !bending;
+    const bool do_volume = (modules & MS_MOD_VOLUME) != 0;
     double total_b[PS_COUNT] = {0};
     for (const PatchHeader& h : pk.patches) {
       const int P = h.n_owned, L = h.n_owned + h.n_halo;
+      DynamicStrides st;
+      st.L = L;
+      st.A = (P + 15) / 16 * 16 + kDumpRows;
+      const int n_slots = h.n_rounds * T;
+      const FacetRec* recs = pk.recs.data() + size_t(h.slot_off);
       std::vector<double> lpos(3 * size_t(L)), lseed(size_t(kSeedStrideBody) * size_t(L), 0.0),
-          t2(size_t(L), 0.0), accG(3 * size_t(P), 0.0), accV(3 * size_t(P), 0.0), accAb(size_t(P), 0.0);
+          t2(size_t(L), 0.0), acc(6 * size_t(st.A), 0.0), accAb(size_t(st.A), 0.0);
       std::vector<uint8_t> bfl(size_t(L), 0);
       for (int j = 0; j < L; ++j) {
         const int row = local_row(pk, h, j);
-        for (int k = 0; k < 3; ++k) lpos[3 * size_t(j) + k] = pos[3 * size_t(row) + k];
+        for (int k = 0; k < 3; ++k) lpos[size_t(k) * L + j] = pos[3 * size_t(row) + k];
         for (int k = 0; k < kSeedStrideBody; ++k)
-          lseed[size_t(kSeedStrideBody) * j + k] = seed_store[size_t(row) * kSeedStrideBody + k];
+          lseed[size_t(k) * L + j] = seed_store[size_t(row) * kSeedStrideBody + k];
         bfl[size_t(j)] = is_boundary ? is_boundary[row] : 0;
         if (do_tilt) {
           const double* t = tilts + 3 * size_t(row);
@@ -131,25 +134,24 @@ int emul_eval(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* is_boun
       LocalB loc;
       loc.pos = lpos.data(); loc.seed = lseed.data(); loc.bfl = bfl.data();
       loc.t2 = do_tilt ? t2.data() : nullptr;
-      loc.accG = accG.data(); loc.accV = accV.data(); loc.accAb = accAb.data(); loc.P = P;
+      loc.acc = acc.data(); loc.accAb = accAb.data(); loc.P = P;
       double sums[PS_COUNT] = {0};
-      for (int r = 0; r < h.n_rounds; ++r)
-        for (int t = 0; t < T; ++t) {
-          const size_t slot = size_t(h.slot_off) + size_t(r) * size_t(T) + size_t(t);
-          const FacetRec rec = pk.recs[slot];
-          if (!(rec.flags & REC_VALID)) continue;
-          const double gam = gamma ? gamma[pk.slot_facet[slot]] : gamma_u;
-          if (bending)
-            facet_body_b<true>(rec, gam, loc, modules, flags, k_tilt, scalars_here, sums);
-          else
-            facet_body_b<false>(rec, gam, loc, modules, flags, k_tilt, scalars_here, sums);
-        }
-      for (int j = 0; j < 3 * P; ++j) {
-        const size_t o = size_t(h.v_lo) * 3 + size_t(j);
-        if (grad) grad[o] = accG[size_t(j)];
-        if (volgrad && (modules & MS_MOD_VOLUME)) volgrad[o] = accV[size_t(j)];
-        if (tilt_grad && do_tilt) tilt_grad[o] = k_tilt * tilts[o] * accAb[size_t(j) / 3];
+      for (int slot = 0; slot < n_slots; ++slot) {
+        const FacetRec rec = recs[slot];
+        if (!(rec.flags & REC_VALID)) continue;
+        const double gam = gamma ? gamma[pk.slot_facet[size_t(h.slot_off) + slot]] : gamma_u;
+        const FacetOutB o = bending
+            ? facet_compute_b<true>(st, rec, gam, loc, modules, flags, k_tilt, scalars_here, sums)
+            : facet_compute_b<false>(st, rec, gam, loc, modules, flags, k_tilt, scalars_here, sums);
+        facet_accumulate_b(st, rec, o, loc, do_volume, do_tilt);
       }
+      for (int i = 0; i < P; ++i)
+        for (int k = 0; k < 3; ++k) {
+          const size_t o = (size_t(h.v_lo) + i) * 3 + size_t(k);
+          if (grad) grad[o] = acc[size_t(k) * st.A + i];
+          if (volgrad && do_volume) volgrad[o] = acc[size_t(3 + k) * st.A + i];
+          if (tilt_grad && do_tilt) tilt_grad[o] = k_tilt * tilts[o] * accAb[size_t(i)];
+        }
       for (int k = 0; k < PS_COUNT; ++k) total_b[k] += sums[k];
     }
     if (scalars_here)

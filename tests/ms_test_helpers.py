@@ -52,7 +52,7 @@ def build_emulator():
 
 def emulate(pos, tri, *, modules, flags=0, want_grad=True, is_boundary=None, body_mask=None,
             tilts=None, gamma=None, gamma_u=1.0, kappa=None, c0=None, kappa_u=0.0, c0_u=0.0,
-            k_tilt=0.0, threads=128, max_owned=512, max_local=896, n_owned=-1, phase=0, seeds=None):
+            k_tilt=0.0, threads=96, max_owned=512, max_local=896, n_owned=-1, phase=0, seeds=None):
     """Run the emulator; returns a dict of scalars and arrays."""
     global _EMUL
     if _EMUL is None:
@@ -89,7 +89,7 @@ def emulate(pos, tri, *, modules, flags=0, want_grad=True, is_boundary=None, bod
                seeds=(np.zeros((nv, 5)) if seeds is None else np.ascontiguousarray(seeds, dtype=np.float64).copy()),
                k_vecs=np.zeros((nv, 3)), a_vor=np.zeros(nv),
                a_eff=np.zeros(nv), e_vertex=np.zeros(nv))
-    stats = np.zeros(6, dtype=np.int64)
+    stats = np.zeros(8, dtype=np.int64)
     rc = _EMUL.emul_eval(
         ctypes.c_int32(nv), ctypes.c_int32(nf), tri.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
         bptr(u8(is_boundary)), bptr(u8(body_mask)), dptr(pos), dptr(f64(tilts)), dptr(f64(gamma)),
@@ -105,5 +105,5 @@ def emulate(pos, tri, *, modules, flags=0, want_grad=True, is_boundary=None, bod
     out.update(E_surface=scal[0], area=scal[1], volume=scal[2], E_bending=scal[3], E_tilt=scal[4],
                pack=dict(n_patches=int(stats[0]), n_slots=int(stats[1]), n_listed=int(stats[2]),
                          max_rounds=int(stats[3]), max_local=int(stats[4]),
-                         lane_conflicts=int(stats[5])))
+                         lane_conflicts=int(stats[5]), hw_groups=int(stats[6]), hw_excess=int(stats[7])))
     return out

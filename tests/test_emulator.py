@@ -59,7 +59,8 @@ def test_lane_placement_properties():
     pos, tri = icosphere(30)
     out = H.emulate(pos, tri, modules=H.MOD_SURFACE)
     p = out["pack"]
-    assert p["n_slots"] % 128 == 0 and p["n_slots"] >= p["n_listed"] >= tri.shape[0]
-    assert p["lane_conflicts"] <= 0.1 * 3 * p["n_listed"]
+    assert p["n_slots"] % 96 == 0 and p["n_slots"] >= p["n_listed"] >= tri.shape[0]
+    # bank-aware placement: few half-warp gather groups need an extra shared-memory wavefront
+    assert p["hw_excess"] <= 0.35 * p["hw_groups"]
     area = 0.5 * np.linalg.norm(np.cross(pos[tri[:, 1]] - pos[tri[:, 0]], pos[tri[:, 2]] - pos[tri[:, 0]]), axis=1).sum()
     assert abs(out["area"] - area) <= 1e-13 * area

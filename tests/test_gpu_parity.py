@@ -219,7 +219,7 @@ def test_minimizer_golden(L, minimizer_golden):
 
 # -------------------------------------------------------------- synthetic
 @pytest.mark.parametrize("n,pack", [(6, dict()), (40, dict()), (40, dict(threads=64, max_owned=200, max_local=420)),
-                                    (120, dict(threads=256, max_owned=1024, max_local=1600))])
+                                    (120, dict(threads=128, max_owned=384, max_local=700)), (120, dict(threads=160, max_owned=512, max_local=896))])
 def test_icosphere_fused_vs_oracle(L, n, pack):
     from membrane_solver_b200.synthetic import icosphere
     from oracle import ref_modules as ref
