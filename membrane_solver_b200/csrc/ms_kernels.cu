@@ -131,7 +131,7 @@ struct Plan {
   static constexpr size_t kAccBytes = size_t(kAccRows) * kACap * 8;
   static constexpr size_t oBars = oAcc + 2 * kAccBytes;
   static constexpr size_t oRed = oBars + 64;
-  static constexpr size_t oOpt = oRed + size_t(kMaxConsumerWarps) * PS_COUNT * 8;
+  static constexpr size_t oOpt = oRed + size_t(kMaxConsumerWarps + 1) * PS_COUNT * 8;
 };
 // optional arrays (after the fixed part): bfl[2][L] u8, t2[2][L] f64, accAb[2][ACap] f64
 __host__ __device__ inline size_t opt_bytes(bool boundary, bool tilt, bool tilt_acc) {
@@ -161,8 +161,10 @@ __device__ __forceinline__ FacetRec load_rec(const FacetRec* p) {
 // ---------------------------------------------------------------------------
 constexpr uint32_t kFastModules = MS_MOD_SURFACE | MS_MOD_BENDING | MS_MOD_VOLUME;
 
+// Warp roles inside the 512-thread CTA: warps [0, NC/32) are consumers, warp NC/32 runs the
+// patch epilogues, the last warp is the producer.
 template <int PASS, bool FAST, int NC>
-__global__ void __launch_bounds__(NC + 32, 1) k_patch(PatchLaunch a, bool bending_b, bool scalars_here_arg) {
+__global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bending_b, bool scalars_here_arg) {
   extern __shared__ __align__(128) unsigned char smem[];
   using P = Plan<PASS>;
   const DevStrides ST{};
@@ -171,6 +173,7 @@ __global__ void __launch_bounds__(NC + 32, 1) k_patch(PatchLaunch a, bool bendin
   int G = NC / T;
   if (G > kMaxGroups) G = kMaxGroups;
   const int n_active = G * T;  // consumer threads that take turns
+  const int n_epi_warps = (NC + 32 - n_active) / 32;  // every warp between consumers and producer
   const int n_my = a.patch_count > int(blockIdx.x) ? (a.patch_count - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x) : 0;
 
   const uint32_t modules = FAST ? kFastModules : a.modules;
@@ -180,8 +183,15 @@ __global__ void __launch_bounds__(NC + 32, 1) k_patch(PatchLaunch a, bool bendin
   const bool do_bending = FAST ? true : (PASS == 0 ? (modules & (MS_MOD_BENDING | MS_MOD_BENDING_TILT)) != 0 : bending_b);
   const bool do_volume = FAST ? true : (modules & MS_MOD_VOLUME) != 0;
   const bool scalars_here = FAST ? false : scalars_here_arg;
+  const bool want_epi = PASS == 1 || do_bending;  // pass A without bending accumulates nothing
 
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P::oBars);  // full[0], full[1], empty[0], empty[1]
+  // mbarriers: full[2] producer -> all; empty[2] consumers (+ epilogue in pass A) -> producer;
+  // acc_done[2] last round's group -> epilogue; acc_free[2] epilogue -> consumers
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P::oBars);
+  uint64_t* bar_full = bars;
+  uint64_t* bar_empty = bars + 2;
+  uint64_t* bar_done = bars + 4;
+  uint64_t* bar_free = bars + 6;
   double* red = reinterpret_cast<double*>(smem + P::oRed);
   unsigned char* opt = smem + P::oOpt;
   uint8_t* bfl_base = nullptr;
@@ -191,27 +201,30 @@ __global__ void __launch_bounds__(NC + 32, 1) k_patch(PatchLaunch a, bool bendin
   if (do_tilt) { t2_base = reinterpret_cast<double*>(opt); opt += 2 * size_t(kPatchLocalCap) * 8; }
   if (do_tilt && PASS == 1) { ab_base = reinterpret_cast<double*>(opt); }
 
+  const bool epi_holds_input = PASS == 0;  // the vertex stage may rescan the patch's records
   if (tid == 0) {
-    mbar_init(&bars[0], 32);
-    mbar_init(&bars[1], 32);
-    mbar_init(&bars[2], unsigned(n_active / 32));
-    mbar_init(&bars[3], unsigned(n_active / 32));
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bar_full[b], 32);
+      mbar_init(&bar_empty[b], unsigned(n_active / 32) + ((want_epi && epi_holds_input) ? unsigned(n_epi_warps) : 0u));
+      mbar_init(&bar_done[b], unsigned(T));
+      mbar_init(&bar_free[b], 32u * unsigned(n_epi_warps));
+    }
   }
   {  // zero both accumulator buffers (and the tilt area accumulators)
     double* acc0 = reinterpret_cast<double*>(smem + P::oAcc);
-    for (int j = tid; j < 2 * P::kAccRows * kACap; j += NC + 32) acc0[j] = 0.0;
+    for (int j = tid; j < 2 * P::kAccRows * kACap; j += NC + 64) acc0[j] = 0.0;
     if (ab_base)
-      for (int j = tid; j < 2 * kACap; j += NC + 32) ab_base[j] = 0.0;
+      for (int j = tid; j < 2 * kACap; j += NC + 64) ab_base[j] = 0.0;
   }
   __syncthreads();
 
-  if (tid >= NC) {
+  if (tid >= NC + 32) {
     // =========================== producer warp ===========================
-    const int lane = tid - NC;
+    const int lane = tid - (NC + 32);
     for (int j = 0; j < n_my; ++j) {
       const int b = j & 1;
       const int pid = a.patch_begin + int(blockIdx.x) + j * int(gridDim.x);
-      if (j >= 2) mbar_wait(&bars[2 + b], unsigned(((j >> 1) - 1) & 1));
+      if (j >= 2) mbar_wait(&bar_empty[b], unsigned(((j >> 1) - 1) & 1));
       const PatchHeader h = a.patches[pid];
       const int n_slots = int(a.patches[pid + 1].slot_off - h.slot_off);  // sentinel header at the end
       unsigned char* in = smem + size_t(b) * P::kInBytes;
@@ -272,36 +285,115 @@ __global__ void __launch_bounds__(NC + 32, 1) k_patch(PatchLaunch a, bool bendin
         }
       }
       cp_async_wait_all();
-      mbar_arrive(&bars[b]);
+      mbar_arrive(&bar_full[b]);
     }
     return;
   }
 
-  // ============================= consumers =============================
   double sums[PS_COUNT];
 #pragma unroll
   for (int k = 0; k < PS_COUNT; ++k) sums[k] = 0.0;
 
-  if (tid < n_active) {
-    const int grp = tid / T, lane = tid - grp * T;
-    const int bar_mine = 1 + grp, bar_next = 1 + (grp + 1 == G ? 0 : grp + 1);
-    const int ring = 2 * T;
-    const bool use_ring = G > 1;
+  if (tid >= n_active) {
+    // =========================== epilogue warps ===========================
+    // After the last round of a patch has been accumulated: vertex stage + seeds (pass A) or
+    // gradient rows + KKT dot products (pass B) of the owned vertices; the accumulator is zeroed
+    // on the way and handed back to the consumers.
+    const int lane = tid - n_active;   // 0 .. 32*n_epi_warps-1: one owned vertex per lane and sweep
+    const int epi_threads = 32 * n_epi_warps;
     const bool willmore = (flags & MS_FLAG_WILLMORE) != 0;
-    if (use_ring && grp == G - 1) named_arrive(1, ring);  // group 0 owns the first token
-    int t_rel = grp;   // my next turn, relative to the first turn of the current patch
-    int64_t turns_done = 0;
-    for (int j = 0; j < n_my; ++j) {
+    for (int j = 0; want_epi && j < n_my; ++j) {
       const int b = j & 1;
-      mbar_wait(&bars[b], unsigned((j >> 1) & 1));
+      mbar_wait(&bar_full[b], unsigned((j >> 1) & 1));   // header, records, positions
+      mbar_wait(&bar_done[b], unsigned((j >> 1) & 1));   // every round accumulated
       unsigned char* in = smem + size_t(b) * P::kInBytes;
       const PatchHdrS hs = *reinterpret_cast<const PatchHdrS*>(in + P::oHdr);
       const FacetRec* recs = reinterpret_cast<const FacetRec*>(in + P::oRecs);
       double* acc = reinterpret_cast<double*>(smem + P::oAcc + size_t(b) * P::kAccBytes);
       const int Pn = hs.n_owned;
-      const bool want_epi = PASS == 1 || do_bending;
-      const int n_epi = want_epi ? (Pn + T - 1) / T : 0;
-      const int n_turns = hs.n_rounds + n_epi;
+      LocalA la;
+      if (PASS == 0) {
+        la.pos = reinterpret_cast<const double*>(in + P::oPos);
+        la.bfl = has_boundary ? bfl_base + size_t(b) * kPatchLocalCap : nullptr;
+        la.t2 = nullptr;
+        la.acc = acc;
+        la.P = Pn;
+      }
+      double* accAb = ab_base ? ab_base + size_t(b) * kACap : nullptr;
+      for (int i = lane; i < Pn; i += epi_threads) {
+        const size_t row = size_t(hs.v_lo) + i;
+        if (PASS == 0) {
+          const double kap = (!FAST && a.kappa) ? a.kappa[row] : a.kappa_u;
+          const double c0 = (!FAST && a.c0) ? a.c0[row] : a.c0_u;
+          const VertexSeed sd = vertex_body_a(ST, i, la, recs, hs.n_slots, kap, c0, willmore);
+          sums[PS_E_BENDING] += sd.E;
+          if (a.seeds) {
+            double* o = a.seeds + row * kSeedStride;
+            o[0] = sd.fK.x; o[1] = sd.fK.y; o[2] = sd.fK.z; o[3] = sd.fAe; o[4] = sd.fAv;
+          }
+          if (!FAST) {
+            if (a.k_vecs) {
+              a.k_vecs[3 * row] = acc[i];
+              a.k_vecs[3 * row + 1] = acc[kACap + i];
+              a.k_vecs[3 * row + 2] = acc[2 * kACap + i];
+            }
+            if (a.a_vor) a.a_vor[row] = acc[3 * kACap + i];
+            if (a.a_eff) a.a_eff[row] = acc[4 * kACap + i];
+            if (a.e_vertex) a.e_vertex[row] = sd.E;
+          }
+#pragma unroll
+          for (int c = 0; c < 5; ++c) acc[c * kACap + i] = 0.0;
+        } else {
+          const double gx = acc[i], gy = acc[kACap + i], gz = acc[2 * kACap + i];
+          double* go = a.grad + 3 * row;
+          go[0] = gx; go[1] = gy; go[2] = gz;
+          sums[PS_G_G] += gx * gx + gy * gy + gz * gz;
+          acc[i] = 0.0; acc[kACap + i] = 0.0; acc[2 * kACap + i] = 0.0;
+          if (do_volume && a.volgrad) {
+            const double vx = acc[3 * kACap + i], vy = acc[4 * kACap + i], vz = acc[5 * kACap + i];
+            double* vo = a.volgrad + 3 * row;
+            vo[0] = vx; vo[1] = vy; vo[2] = vz;
+            sums[PS_G_GC] += gx * vx + gy * vy + gz * vz;
+            sums[PS_GC_GC] += vx * vx + vy * vy + vz * vz;
+            acc[3 * kACap + i] = 0.0; acc[4 * kACap + i] = 0.0; acc[5 * kACap + i] = 0.0;
+          }
+          if (do_tilt && accAb) {
+            if (a.tilt_grad) {  // tilt.py:163-170: dE/dt_v = k_t t_v A_bary(v)
+              const double ab = accAb[i];
+              a.tilt_grad[3 * row] = a.k_tilt * a.tilts[3 * row] * ab;
+              a.tilt_grad[3 * row + 1] = a.k_tilt * a.tilts[3 * row + 1] * ab;
+              a.tilt_grad[3 * row + 2] = a.k_tilt * a.tilts[3 * row + 2] * ab;
+            }
+            accAb[i] = 0.0;
+          }
+        }
+      }
+      mbar_arrive(&bar_free[b]);
+      if (epi_holds_input) {
+        __syncwarp();
+        if ((lane & 31) == 0) mbar_arrive(&bar_empty[b]);
+      }
+    }
+  } else {
+    // ============================= consumers =============================
+    const int grp = tid / T, lane = tid - grp * T;
+    const int bar_mine = 1 + grp, bar_next = 1 + (grp + 1 == G ? 0 : grp + 1);
+    const int ring = 2 * T;
+    const bool use_ring = G > 1;
+    if (use_ring && grp == G - 1) named_arrive(1, ring);  // group 0 owns the first token
+    int t_rel = grp;   // my next round, relative to the first round of the current patch
+    int64_t turns_done = 0;
+    for (int j = 0; j < n_my; ++j) {
+      const int b = j & 1;
+      mbar_wait(&bar_full[b], unsigned((j >> 1) & 1));
+      if (want_epi && j >= 2) mbar_wait(&bar_free[b], unsigned(((j >> 1) - 1) & 1));  // accumulator drained
+      unsigned char* in = smem + size_t(b) * P::kInBytes;
+      const PatchHdrS hs = *reinterpret_cast<const PatchHdrS*>(in + P::oHdr);
+      const FacetRec* recs = reinterpret_cast<const FacetRec*>(in + P::oRecs);
+      double* acc = reinterpret_cast<double*>(smem + P::oAcc + size_t(b) * P::kAccBytes);
+      const int Pn = hs.n_owned;
+      // a patch without facets still takes one (empty) round so that its epilogue is triggered
+      const int n_turns = hs.n_rounds > 0 ? hs.n_rounds : 1;
       const double* slot_gamma = (!FAST && a.slot_gamma) ? a.slot_gamma + hs.slot_off : nullptr;
 
       LocalA la;
@@ -323,98 +415,44 @@ __global__ void __launch_bounds__(NC + 32, 1) k_patch(PatchLaunch a, bool bendin
       }
 
       for (; t_rel < n_turns; t_rel += G) {
-        if (t_rel < hs.n_rounds) {
-          // ---------------- facet round ----------------
-          const int slot = t_rel * T + lane;
-          const FacetRec rec = load_rec(recs + slot);
-          const bool valid = (rec.flags & REC_VALID) != 0;
-          if (PASS == 0) {
-            CornerA ca;
-            if (valid) {
-              const double gam = slot_gamma ? slot_gamma[slot] : a.gamma_u;
-              ca = facet_compute_a(ST, rec, gam, la, modules, a.k_tilt, sums);
-            }
-            if (use_ring) named_sync(bar_mine, ring); else named_sync(1, T);
-            if (valid && do_bending) facet_accumulate_a(ST, rec, ca, la, modules);
-            if (use_ring) named_arrive(bar_next, ring);
-          } else {
-            FacetOutB out;
-            if (valid) {
-              const double gam = slot_gamma ? slot_gamma[slot] : a.gamma_u;
-              out = do_bending ? facet_compute_b<true>(ST, rec, gam, lb, modules, flags, a.k_tilt, scalars_here, sums)
-                               : facet_compute_b<false>(ST, rec, gam, lb, modules, flags, a.k_tilt, scalars_here, sums);
-            }
-            if (use_ring) named_sync(bar_mine, ring); else named_sync(1, T);
-            if (valid) facet_accumulate_b(ST, rec, out, lb, do_volume, do_tilt);
-            if (use_ring) named_arrive(bar_next, ring);
+        const int slot = t_rel * T + lane;
+        FacetRec rec;
+        rec.a = rec.b = rec.c = 0; rec.flags = 0;
+        if (slot < hs.n_slots) rec = load_rec(recs + slot);
+        const bool valid = (rec.flags & REC_VALID) != 0;
+        if (PASS == 0) {
+          CornerA ca;
+          if (valid) {
+            const double gam = slot_gamma ? slot_gamma[slot] : a.gamma_u;
+            ca = facet_compute_a(ST, rec, gam, la, modules, a.k_tilt, sums);
           }
+          if (use_ring) named_sync(bar_mine, ring); else named_sync(1, T);
+          if (valid && do_bending) facet_accumulate_a(ST, rec, ca, la, modules);
         } else {
-          // ---------------- epilogue turn: owned vertices [e*T, (e+1)*T) ----------------
-          // all earlier turns have accumulated once the token arrives; this slice of the
-          // accumulator belongs to this thread alone from here on, so the token moves on at once
-          if (use_ring) { named_sync(bar_mine, ring); named_arrive(bar_next, ring); } else named_sync(1, T);
-          const int i = (t_rel - hs.n_rounds) * T + lane;
-          if (i < Pn) {
-            const size_t row = size_t(hs.v_lo) + i;
-            if (PASS == 0) {
-              const double kap = (!FAST && a.kappa) ? a.kappa[row] : a.kappa_u;
-              const double c0 = (!FAST && a.c0) ? a.c0[row] : a.c0_u;
-              const VertexSeed sd = vertex_body_a(ST, i, la, recs, hs.n_slots, kap, c0, willmore);
-              sums[PS_E_BENDING] += sd.E;
-              if (a.seeds) {
-                double* o = a.seeds + row * kSeedStride;
-                o[0] = sd.fK.x; o[1] = sd.fK.y; o[2] = sd.fK.z; o[3] = sd.fAe; o[4] = sd.fAv;
-              }
-              if (!FAST) {
-                if (a.k_vecs) {
-                  a.k_vecs[3 * row] = acc[i];
-                  a.k_vecs[3 * row + 1] = acc[kACap + i];
-                  a.k_vecs[3 * row + 2] = acc[2 * kACap + i];
-                }
-                if (a.a_vor) a.a_vor[row] = acc[3 * kACap + i];
-                if (a.a_eff) a.a_eff[row] = acc[4 * kACap + i];
-                if (a.e_vertex) a.e_vertex[row] = sd.E;
-              }
-#pragma unroll
-              for (int c = 0; c < 5; ++c) acc[c * kACap + i] = 0.0;
-            } else {
-              const double gx = acc[i], gy = acc[kACap + i], gz = acc[2 * kACap + i];
-              double* go = a.grad + 3 * row;
-              go[0] = gx; go[1] = gy; go[2] = gz;
-              sums[PS_G_G] += gx * gx + gy * gy + gz * gz;
-              acc[i] = 0.0; acc[kACap + i] = 0.0; acc[2 * kACap + i] = 0.0;
-              if (do_volume && a.volgrad) {
-                const double vx = acc[3 * kACap + i], vy = acc[4 * kACap + i], vz = acc[5 * kACap + i];
-                double* vo = a.volgrad + 3 * row;
-                vo[0] = vx; vo[1] = vy; vo[2] = vz;
-                sums[PS_G_GC] += gx * vx + gy * vy + gz * vz;
-                sums[PS_GC_GC] += vx * vx + vy * vy + vz * vz;
-                acc[3 * kACap + i] = 0.0; acc[4 * kACap + i] = 0.0; acc[5 * kACap + i] = 0.0;
-              }
-              if (do_tilt && lb.accAb) {
-                if (a.tilt_grad) {  // tilt.py:163-170: dE/dt_v = k_t t_v A_bary(v)
-                  const double ab = lb.accAb[i];
-                  a.tilt_grad[3 * row] = a.k_tilt * a.tilts[3 * row] * ab;
-                  a.tilt_grad[3 * row + 1] = a.k_tilt * a.tilts[3 * row + 1] * ab;
-                  a.tilt_grad[3 * row + 2] = a.k_tilt * a.tilts[3 * row + 2] * ab;
-                }
-                lb.accAb[i] = 0.0;
-              }
-            }
+          FacetOutB out;
+          if (valid) {
+            const double gam = slot_gamma ? slot_gamma[slot] : a.gamma_u;
+            out = do_bending ? facet_compute_b<true>(ST, rec, gam, lb, modules, flags, a.k_tilt, scalars_here, sums)
+                             : facet_compute_b<false>(ST, rec, gam, lb, modules, flags, a.k_tilt, scalars_here, sums);
           }
+          if (use_ring) named_sync(bar_mine, ring); else named_sync(1, T);
+          if (valid) facet_accumulate_b(ST, rec, out, lb, do_volume, do_tilt);
         }
+        // the last round of the patch hands the accumulator to the epilogue warp
+        if (want_epi && t_rel == n_turns - 1) mbar_arrive(&bar_done[b]);
+        if (use_ring) named_arrive(bar_next, ring);
       }
       t_rel -= n_turns;
       turns_done += n_turns;
-      // leaving the patch: its input buffer and accumulator may be reused two patches on
+      // leaving the patch: its input buffer may be refilled
       __syncwarp();
-      if ((tid & 31) == 0) mbar_arrive(&bars[2 + b]);
+      if ((tid & 31) == 0) mbar_arrive(&bar_empty[b]);
     }
     // swallow the token left over by the last turn
     if (use_ring && int(turns_done % G) == grp) named_sync(bar_mine, ring);
   }
 
-  block_sum<PS_COUNT>(sums, red, NC, 15);
+  block_sum<PS_COUNT>(sums, red, NC + 32, 15);
   if (tid == 0) {
     double* p = a.partials + size_t(blockIdx.x) * kPartialStride;
 #pragma unroll
@@ -730,9 +768,9 @@ cudaError_t launch_pass_a(const PatchLaunch& a, cudaStream_t st) {
   const size_t smem = patch_smem_bytes<0>(a);
   const int grid = patch_grid(a);
   if (fast_config(a))
-    k_patch<0, true, kConsumerThreads><<<grid, kConsumerThreads + 32, smem, st>>>(a, true, false);
+    k_patch<0, true, kConsumerThreads><<<grid, kConsumerThreads + 64, smem, st>>>(a, true, false);
   else
-    k_patch<0, false, kConsumerThreads><<<grid, kConsumerThreads + 32, smem, st>>>(a, false, false);
+    k_patch<0, false, kConsumerThreads><<<grid, kConsumerThreads + 64, smem, st>>>(a, false, false);
   return cudaGetLastError();
 }
 
@@ -741,9 +779,9 @@ cudaError_t launch_pass_b(const PatchLaunch& a, bool bending, bool scalars_here,
   const size_t smem = patch_smem_bytes<1>(a);
   const int grid = patch_grid(a);
   if (fast_config(a) && bending && !scalars_here)
-    k_patch<1, true, kConsumerThreads><<<grid, kConsumerThreads + 32, smem, st>>>(a, true, false);
+    k_patch<1, true, kConsumerThreads><<<grid, kConsumerThreads + 64, smem, st>>>(a, true, false);
   else
-    k_patch<1, false, kConsumerThreads><<<grid, kConsumerThreads + 32, smem, st>>>(a, bending, scalars_here);
+    k_patch<1, false, kConsumerThreads><<<grid, kConsumerThreads + 64, smem, st>>>(a, bending, scalars_here);
   return cudaGetLastError();
 }
 

@@ -35,11 +35,11 @@ constexpr int kPatchOwnedCap = 512;   // owned vertices per patch
 constexpr int kPatchLocalCap = 896;   // owned + halo vertices per patch
 constexpr int kPatchSlotCap = 1536;   // record slots per patch (rounds x threads)
 #ifndef MS_CONSUMER_THREADS
-#define MS_CONSUMER_THREADS 480
+#define MS_CONSUMER_THREADS 448
 #endif
-constexpr int kConsumerThreads = MS_CONSUMER_THREADS;  // + one producer warp per CTA
+constexpr int kConsumerThreads = MS_CONSUMER_THREADS;  // + one epilogue warp + one producer warp per CTA
 constexpr int kMaxConsumerWarps = kConsumerThreads / 32;
-constexpr int kMaxGroups = 8;         // thread groups taking turns (named barriers 1..8)
+constexpr int kMaxGroups = 14;        // thread groups taking turns (named barriers 1..14)
 
 struct PatchLaunch {
   // packed topology (device)
