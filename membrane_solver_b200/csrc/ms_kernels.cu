@@ -83,16 +83,25 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ bool mbar_try(unsigned addr, unsigned parity) {
+  unsigned ok = 0;
+  asm volatile(
+      "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(addr), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
   const unsigned addr = smem_u32(bar);
-  unsigned ok = 0;
-  do {
-    asm volatile(
-        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity)
-        : "memory");
-  } while (!ok);
+  while (!mbar_try(addr, parity)) {
+  }
+}
+// for the service warps (producer, epilogue): back off between polls so that the spin does not
+// take issue slots from the consumers
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, unsigned parity) {
+  const unsigned addr = smem_u32(bar);
+  while (!mbar_try(addr, parity)) __nanosleep(200);
 }
 __device__ __forceinline__ void named_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
@@ -224,7 +233,7 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
     for (int j = 0; j < n_my; ++j) {
       const int b = j & 1;
       const int pid = a.patch_begin + int(blockIdx.x) + j * int(gridDim.x);
-      if (j >= 2) mbar_wait(&bar_empty[b], unsigned(((j >> 1) - 1) & 1));
+      if (j >= 2) mbar_wait_relaxed(&bar_empty[b], unsigned(((j >> 1) - 1) & 1));
       const PatchHeader h = a.patches[pid];
       const int n_slots = int(a.patches[pid + 1].slot_off - h.slot_off);  // sentinel header at the end
       unsigned char* in = smem + size_t(b) * P::kInBytes;
@@ -304,8 +313,8 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
     const bool willmore = (flags & MS_FLAG_WILLMORE) != 0;
     for (int j = 0; want_epi && j < n_my; ++j) {
       const int b = j & 1;
-      mbar_wait(&bar_full[b], unsigned((j >> 1) & 1));   // header, records, positions
-      mbar_wait(&bar_done[b], unsigned((j >> 1) & 1));   // every round accumulated
+      mbar_wait_relaxed(&bar_full[b], unsigned((j >> 1) & 1));   // header, records, positions
+      mbar_wait_relaxed(&bar_done[b], unsigned((j >> 1) & 1));   // every round accumulated
       unsigned char* in = smem + size_t(b) * P::kInBytes;
       const PatchHdrS hs = *reinterpret_cast<const PatchHdrS*>(in + P::oHdr);
       const FacetRec* recs = reinterpret_cast<const FacetRec*>(in + P::oRecs);

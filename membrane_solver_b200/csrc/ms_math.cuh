@@ -58,8 +58,17 @@ constexpr double kP1Clamp = 1.0e-20;       // tilt_operators.py:164: max(|n|^2, 
 // Geometry every per-facet routine starts from.
 struct FacetGeom {
   d3 e0, e1, e2, n;
-  double S;  // |n| = twice the facet area
+  double S;   // |n| = twice the facet area
+  double rS;  // 1/|n| (0 for a zero normal): ONE reciprocal square root serves sqrt and both divisions
 };
+
+MS_HD double recip_sqrt(double x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrt(x);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
 
 MS_HD FacetGeom facet_geom(d3 v0, d3 v1, d3 v2) {
   FacetGeom g;
@@ -67,9 +76,14 @@ MS_HD FacetGeom facet_geom(d3 v0, d3 v1, d3 v2) {
   g.e1 = v0 - v2;
   g.e2 = v1 - v0;
   g.n = cross(g.e1, g.e2);
-  g.S = sqrt(dot(g.n, g.n));
+  const double n2 = dot(g.n, g.n);
+  g.rS = n2 > 1.0e-300 ? recip_sqrt(n2) : 0.0;
+  g.S = n2 * g.rS;
   return g;
 }
+
+// 1 / max(S, 1e-12) without a division (curvature.py:271 clamps twice the area)
+MS_HD double inv_clamped_area2(const FacetGeom& g) { return g.S >= kAreaClamp ? g.rS : 1.0 / kAreaClamp; }
 
 // ---------------------------------------------------------------------------
 // Pass A: cotangents, curvature-vector and mixed-Voronoi corner contributions.
@@ -100,15 +114,17 @@ MS_HD void mixed_voronoi(double l0, double l1, double l2, double c0, double c1, 
 MS_HD CornerA facet_pass_a(const FacetGeom& g, bool b0, bool b1, bool b2) {
   CornerA r;
   const double D = fmax(g.S, kAreaClamp);
-  const double invD = 1.0 / D;
-  r.c0 = -dot(g.e1, g.e2) * invD;
-  r.c1 = -dot(g.e2, g.e0) * invD;
-  r.c2 = -dot(g.e0, g.e1) * invD;
-  // K[i0] += 1/2 (c1 (-e1) + c2 e2), cyclic
+  const double invD = inv_clamped_area2(g);
+  // e0 = -(e1 + e2): every edge product follows from l1 = e1.e1, l2 = e2.e2, C0 = -e1.e2
+  const double l1 = dot(g.e1, g.e1), l2 = dot(g.e2, g.e2), C0 = -dot(g.e1, g.e2);
+  const double C1 = l2 - C0, C2 = l1 - C0, l0 = (l1 + l2) - 2.0 * C0;
+  r.c0 = C0 * invD;
+  r.c1 = C1 * invD;
+  r.c2 = C2 * invD;
+  // K[i0] += 1/2 (c1 (-e1) + c2 e2), cyclic; the three contributions sum to zero
   r.K0 = 0.5 * (r.c2 * g.e2 - r.c1 * g.e1);
-  r.K1 = 0.5 * (r.c0 * g.e0 - r.c2 * g.e2);
-  r.K2 = 0.5 * (r.c1 * g.e1 - r.c0 * g.e0);
-  const double l0 = dot(g.e0, g.e0), l1 = dot(g.e1, g.e1), l2 = dot(g.e2, g.e2);
+  r.K1 = -0.5 * (r.c0 * g.e1 + (r.c0 + r.c2) * g.e2);
+  r.K2 = -(r.K0 + r.K1);
   mixed_voronoi(l0, l1, l2, r.c0, r.c1, r.c2, 0.5 * D, r.va0, r.va1, r.va2);
   // bending_utils.py:101-102 clamps the AREA (not twice the area) for A_eff
   const double Te = fmax(0.5 * g.S, kAreaClamp);
@@ -191,71 +207,78 @@ template <bool BENDING>
 MS_HD CornerG facet_pass_b(const FacetGeom& g, double gamma_eff, double area_coeff,
                            const BendIn& b, bool approx) {
   CornerG r;
-  const d3 q0 = cross(g.e0, g.n), q1 = cross(g.e1, g.n), q2 = cross(g.e2, g.n);
-  double Bq = 0.0;  // coefficient of q_m, identical for the three corners
-  // coefficients of e0,e1,e2 per corner
-  double k00 = 0, k01 = 0, k02 = 0, k10 = 0, k11 = 0, k12 = 0, k20 = 0, k21 = 0, k22 = 0;
-  r.g0 = make_d3(0, 0, 0); r.g1 = r.g0; r.g2 = r.g0;
-  const double invS = (g.S > kCotGradEps) ? 1.0 / g.S : 0.0;
+  double Bq = 0.0;  // coefficient of q_m = e_m x n, identical for the three corners
+  const double invS = (g.S > kCotGradEps) ? g.rS : 0.0;
   if (g.S >= kSurfaceSkip) Bq -= 0.5 * (gamma_eff + area_coeff) * invS;
 
-  if (BENDING) {
-    const double D = fmax(g.S, kAreaClamp);
-    const double invD = 1.0 / D;
-    const double C0 = -dot(g.e1, g.e2), C1 = -dot(g.e2, g.e0), C2 = -dot(g.e0, g.e1);
-    const double c0 = C0 * invD, c1 = C1 * invD, c2 = C2 * invD;
-    const d3 d12 = b.f1 - b.f2, d20 = b.f2 - b.f0, d01 = b.f0 - b.f1;
-    // term 1: g -= L fK  (bending_math.py:111-118)
-    r.g0 = 0.5 * (c1 * d20 - c2 * d01);
-    r.g1 = 0.5 * (c2 * d01 - c0 * d12);
-    r.g2 = 0.5 * (c0 * d12 - c1 * d20);
-    if (!approx) {
-      // term 2 weights: dE/dc_k = -1/2 (fK_i - fK_j).(v_i - v_j)
-      double a0 = 0.5 * dot(d12, g.e0);
-      double a1 = 0.5 * dot(d20, g.e1);
-      double a2 = 0.5 * dot(d01, g.e2);
-      // term 3: chi_k = (interior ? fA_eff : mean over interior corners) + fA_vor
-      const int ni = int(b.i0) + int(b.i1) + int(b.i2);
-      const double sum_i = (b.i0 ? b.fe0 : 0.0) + (b.i1 ? b.fe1 : 0.0) + (b.i2 ? b.fe2 : 0.0);
-      const double mean_i = ni > 0 ? sum_i / double(ni) : 0.0;
-      const double x0 = (b.i0 ? b.fe0 : mean_i) + b.fv0;
-      const double x1 = (b.i1 ? b.fe1 : mean_i) + b.fv1;
-      const double x2 = (b.i2 ? b.fe2 : mean_i) + b.fv2;
-      const bool o0 = c0 < 0.0, o1 = c1 < 0.0, o2 = c2 < 0.0;
-      double m0 = 0.0, m1 = 0.0, m2 = 0.0;
-      if (!(o0 || o1 || o2)) {
-        const double l0 = dot(g.e0, g.e0), l1 = dot(g.e1, g.e1), l2 = dot(g.e2, g.e2);
-        a0 += 0.125 * l0 * (x1 + x2);
-        a1 += 0.125 * l1 * (x0 + x2);
-        a2 += 0.125 * l2 * (x0 + x1);
-        m0 = 0.25 * c0 * (x1 + x2);
-        m1 = 0.25 * c1 * (x0 + x2);
-        m2 = 0.25 * c2 * (x0 + x1);
-      } else {
-        // each obtuse corner k adds (1/2 chi_k + 1/4 chi_a + 1/4 chi_b) dT/dx
-        double phi = 0.0;
-        if (o0) phi += 0.5 * x0 + 0.25 * x1 + 0.25 * x2;
-        if (o1) phi += 0.5 * x1 + 0.25 * x0 + 0.25 * x2;
-        if (o2) phi += 0.5 * x2 + 0.25 * x0 + 0.25 * x1;
-        Bq -= 0.5 * phi * invS;
-      }
-      // grad cot_k = 0 when S <= 1e-15 (invS == 0 then)
-      const double invS3 = invS * invS * invS;
-      Bq += (a0 * C0 + a1 * C1 + a2 * C2) * invS3;
-      const double aa0 = a0 * invS, aa1 = a1 * invS, aa2 = a2 * invS;
-      k00 = aa1 - aa2; k01 = aa0 + m1;  k02 = -aa0 - m2;
-      k11 = aa2 - aa0; k12 = aa1 + m2;  k10 = -aa1 - m0;
-      k22 = aa0 - aa1; k20 = aa2 + m0;  k21 = -aa2 - m1;
+  if (!BENDING) {
+    r.g0 = Bq * cross(g.e0, g.n);
+    r.g1 = Bq * cross(g.e1, g.n);
+    r.g2 = Bq * cross(g.e2, g.n);
+    return r;
+  }
+  // With e0 = -(e1 + e2) and n = e1 x e2 every contribution is a combination of FOUR vectors:
+  // e1, e2 and the seed differences u = fK1 - fK0, w = fK2 - fK0.
+  //   q_0 = -C1 e1 + C2 e2,  q_1 = -C0 e1 - l1 e2,  q_2 = l2 e1 + C0 e2   (a x (b x c) rule)
+  // and, the energy being translation invariant, g2 = -(g0 + g1).
+  const double invD = inv_clamped_area2(g);
+  const double l1 = dot(g.e1, g.e1), l2 = dot(g.e2, g.e2), C0 = -dot(g.e1, g.e2);
+  const double C1 = l2 - C0, C2 = l1 - C0;
+  const double c0 = C0 * invD, c1 = C1 * invD, c2 = C2 * invD;
+  const d3 u = b.f1 - b.f0, w = b.f2 - b.f0;
+  // term 1: g -= L fK  (bending_math.py:111-118): g0 = 1/2 (c1 d20 - c2 d01), d20 = w, d01 = -u
+  const double P0 = 0.5 * c2, Q0 = 0.5 * c1;
+  const double P1 = -0.5 * (c0 + c2), Q1 = 0.5 * c0;
+  double A0 = 0.0, B0 = 0.0, A1 = 0.0, B1 = 0.0;  // coefficients of e1, e2 for corners 0 and 1
+  if (!approx) {
+    // term 2 weights: dE/dc_k = -1/2 (fK_i - fK_j).(v_i - v_j)
+    const double ue1 = dot(u, g.e1), ue2 = dot(u, g.e2), we1 = dot(w, g.e1), we2 = dot(w, g.e2);
+    double a0 = -0.5 * ((ue1 + ue2) - (we1 + we2));  // 1/2 (f1 - f2).e0
+    double a1 = 0.5 * we1;                           // 1/2 (f2 - f0).e1
+    double a2 = -0.5 * ue2;                          // 1/2 (f0 - f1).e2
+    // term 3: chi_k = (interior ? fA_eff : mean over interior corners) + fA_vor
+    const int ni = int(b.i0) + int(b.i1) + int(b.i2);
+    const double sum_i = (b.i0 ? b.fe0 : 0.0) + (b.i1 ? b.fe1 : 0.0) + (b.i2 ? b.fe2 : 0.0);
+    const double mean_i = ni > 0 ? sum_i / double(ni) : 0.0;
+    const double x0 = (b.i0 ? b.fe0 : mean_i) + b.fv0;
+    const double x1 = (b.i1 ? b.fe1 : mean_i) + b.fv1;
+    const double x2 = (b.i2 ? b.fe2 : mean_i) + b.fv2;
+    const bool o0 = c0 < 0.0, o1 = c1 < 0.0, o2 = c2 < 0.0;
+    double m0 = 0.0, m1 = 0.0, m2 = 0.0;
+    if (!(o0 || o1 || o2)) {
+      const double l0 = (l1 + l2) - 2.0 * C0;
+      a0 += 0.125 * l0 * (x1 + x2);
+      a1 += 0.125 * l1 * (x0 + x2);
+      a2 += 0.125 * l2 * (x0 + x1);
+      m0 = 0.25 * c0 * (x1 + x2);
+      m1 = 0.25 * c1 * (x0 + x2);
+      m2 = 0.25 * c2 * (x0 + x1);
+    } else {
+      // each obtuse corner k adds (1/2 chi_k + 1/4 chi_a + 1/4 chi_b) dT/dx
+      double phi = 0.0;
+      if (o0) phi += 0.5 * x0 + 0.25 * x1 + 0.25 * x2;
+      if (o1) phi += 0.5 * x1 + 0.25 * x0 + 0.25 * x2;
+      if (o2) phi += 0.5 * x2 + 0.25 * x0 + 0.25 * x1;
+      Bq -= 0.5 * phi * invS;
     }
+    // grad cot_k = 0 when S <= 1e-15 (invS == 0 then)
+    const double invS3 = invS * invS * invS;
+    Bq += (a0 * C0 + a1 * C1 + a2 * C2) * invS3;
+    const double aa0 = a0 * invS, aa1 = a1 * invS, aa2 = a2 * invS;
+    // coefficients of (e0, e1, e2) per corner:  corner 0: (aa1-aa2, aa0+m1, -aa0-m2)
+    //                                           corner 1: (-aa1-m0, aa2-aa0, aa1+m2)
+    // folded onto (e1, e2) with e0 = -(e1 + e2)
+    const double k00 = aa1 - aa2, k10 = -aa1 - m0;
+    A0 = (aa0 + m1) - k00;
+    B0 = (-aa0 - m2) - k00;
+    A1 = (aa2 - aa0) - k10;
+    B1 = (aa1 + m2) - k10;
   }
-  r.g0 = axpy(Bq, q0, r.g0);
-  r.g1 = axpy(Bq, q1, r.g1);
-  r.g2 = axpy(Bq, q2, r.g2);
-  if (BENDING && !approx) {
-    r.g0 = axpy(k00, g.e0, axpy(k01, g.e1, axpy(k02, g.e2, r.g0)));
-    r.g1 = axpy(k10, g.e0, axpy(k11, g.e1, axpy(k12, g.e2, r.g1)));
-    r.g2 = axpy(k20, g.e0, axpy(k21, g.e1, axpy(k22, g.e2, r.g2)));
-  }
+  A0 -= Bq * C1; B0 += Bq * C2;
+  A1 -= Bq * C0; B1 -= Bq * l1;
+  r.g0 = axpy(A0, g.e1, axpy(B0, g.e2, axpy(P0, u, Q0 * w)));
+  r.g1 = axpy(A1, g.e1, axpy(B1, g.e2, axpy(P1, u, Q1 * w)));
+  r.g2 = -(r.g0 + r.g1);
   return r;
 }
 

@@ -89,15 +89,36 @@ MS_HD CornerA facet_compute_a(const S& st, FacetRec rec, double gam, const Local
   return c;
 }
 
+// Read-modify-write of the three corners' accumulator rows.  All loads are issued before the
+// first store: the three rows are distinct for owned corners, and a collision can only happen
+// between two halo corners sharing a dump row, whose content is never read -- so the loads of
+// one corner need not wait for the stores of another (shortest possible token hold time).
+template <int N>
+MS_HD void rmw3(double* base, int stride, int ia, int ib, int ic, const double (&ca)[N], const double (&cb)[N],
+                const double (&cc)[N]) {
+  double xa[N], xb[N], xc[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    xa[k] = base[k * stride + ia];
+    xb[k] = base[k * stride + ib];
+    xc[k] = base[k * stride + ic];
+  }
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    base[k * stride + ia] = xa[k] + ca[k];
+    base[k * stride + ib] = xb[k] + cb[k];
+    base[k * stride + ic] = xc[k] + cc[k];
+  }
+}
+
 template <class S>
 MS_HD void facet_accumulate_a(const S& st, FacetRec rec, const CornerA& c, const LocalA& s, uint32_t modules) {
   if (modules & (MS_MOD_BENDING | MS_MOD_BENDING_TILT)) {
     const int ia = acc_row(rec.a, s.P, st.A), ib = acc_row(rec.b, s.P, st.A), ic = acc_row(rec.c, s.P, st.A);
-    double* av = s.acc + 3 * st.A;
-    double* ae = s.acc + 4 * st.A;
-    add3s(s.acc, st.A, ia, c.K0); av[ia] += c.va0; ae[ia] += c.ve0;
-    add3s(s.acc, st.A, ib, c.K1); av[ib] += c.va1; ae[ib] += c.ve1;
-    add3s(s.acc, st.A, ic, c.K2); av[ic] += c.va2; ae[ic] += c.ve2;
+    const double ca[5] = {c.K0.x, c.K0.y, c.K0.z, c.va0, c.ve0};
+    const double cb[5] = {c.K1.x, c.K1.y, c.K1.z, c.va1, c.ve1};
+    const double cc[5] = {c.K2.x, c.K2.y, c.K2.z, c.va2, c.ve2};
+    rmw3<5>(s.acc, st.A, ia, ib, ic, ca, cb, cc);
   }
 }
 
@@ -198,14 +219,17 @@ template <class S>
 MS_HD void facet_accumulate_b(const S& st, FacetRec rec, const FacetOutB& o, const LocalB& s, bool do_volume,
                               bool do_tilt) {
   const int ia = acc_row(rec.a, s.P, st.A), ib = acc_row(rec.b, s.P, st.A), ic = acc_row(rec.c, s.P, st.A);
-  add3s(s.acc, st.A, ia, o.cg.g0);
-  add3s(s.acc, st.A, ib, o.cg.g1);
-  add3s(s.acc, st.A, ic, o.cg.g2);
+  {
+    const double ca[3] = {o.cg.g0.x, o.cg.g0.y, o.cg.g0.z};
+    const double cb[3] = {o.cg.g1.x, o.cg.g1.y, o.cg.g1.z};
+    const double cc[3] = {o.cg.g2.x, o.cg.g2.y, o.cg.g2.z};
+    rmw3<3>(s.acc, st.A, ia, ib, ic, ca, cb, cc);
+  }
   if (do_volume && o.in_body) {
-    double* v = s.acc + 3 * st.A;
-    add3s(v, st.A, ia, o.vg.g0);
-    add3s(v, st.A, ib, o.vg.g1);
-    add3s(v, st.A, ic, o.vg.g2);
+    const double ca[3] = {o.vg.g0.x, o.vg.g0.y, o.vg.g0.z};
+    const double cb[3] = {o.vg.g1.x, o.vg.g1.y, o.vg.g1.z};
+    const double cc[3] = {o.vg.g2.x, o.vg.g2.y, o.vg.g2.z};
+    rmw3<3>(s.acc + 3 * st.A, st.A, ia, ib, ic, ca, cb, cc);
   }
   if (do_tilt && o.third != 0.0) {
     s.accAb[ia] += o.third;
