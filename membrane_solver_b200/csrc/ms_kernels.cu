@@ -120,9 +120,30 @@ using DevStrides = StaticStrides<kPatchLocalCap, kACap>;
 
 struct PatchHdrS {  // header of the staged patch, written by the producer
   int32_t v_lo, n_owned, n_halo, n_rounds;
-  int32_t n_slots, pad;
+  int32_t n_slots, halo_off;
   int64_t slot_off;
 };
+
+// Area-weighted unit normal of owned vertex i of a patch, read from GLOBAL memory (the epilogue
+// warps never touch the staging buffers).  Same record order as vertex_normal_scan.
+__device__ d3 vertex_normal_global(const PatchLaunch& a, const PatchHdrS& hs, int i) {
+  const FacetRec* recs = a.recs + hs.slot_off;
+  const int32_t* ids = a.halo_ids + hs.halo_off;
+  d3 n = make_d3(0, 0, 0);
+  for (int k = 0; k < hs.n_slots; ++k) {
+    const FacetRec rec = recs[k];
+    if (!(rec.flags & REC_VALID)) continue;
+    if (rec.a != i && rec.b != i && rec.c != i) continue;
+    const int ra = rec.a < hs.n_owned ? hs.v_lo + rec.a : ids[rec.a - hs.n_owned];
+    const int rb = rec.b < hs.n_owned ? hs.v_lo + rec.b : ids[rec.b - hs.n_owned];
+    const int rc = rec.c < hs.n_owned ? hs.v_lo + rec.c : ids[rec.c - hs.n_owned];
+    const d3 v0 = ld3(a.pos, ra), v1 = ld3(a.pos, rb), v2 = ld3(a.pos, rc);
+    n = n + cross(v1 - v0, v2 - v0);
+  }
+  const double m = sqrt(dot(n, n));
+  if (m > 1.0e-15) n = (1.0 / m) * n;
+  return n;
+}
 
 template <int PASS>
 struct Plan {
@@ -139,7 +160,8 @@ struct Plan {
   static constexpr size_t oAcc = 2 * kInBytes;
   static constexpr size_t kAccBytes = size_t(kAccRows) * kACap * 8;
   static constexpr size_t oBars = oAcc + 2 * kAccBytes;
-  static constexpr size_t oRed = oBars + 64;
+  static constexpr size_t oMail = oBars + 64;   // PatchHdrS[2]: header handed to the epilogue warps
+  static constexpr size_t oRed = oMail + 64;
   static constexpr size_t oOpt = oRed + size_t(kMaxConsumerWarps + 1) * PS_COUNT * 8;
 };
 // optional arrays (after the fixed part): bfl[2][L] u8, t2[2][L] f64, accAb[2][ACap] f64
@@ -210,11 +232,11 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
   if (do_tilt) { t2_base = reinterpret_cast<double*>(opt); opt += 2 * size_t(kPatchLocalCap) * 8; }
   if (do_tilt && PASS == 1) { ab_base = reinterpret_cast<double*>(opt); }
 
-  const bool epi_holds_input = PASS == 0;  // the vertex stage may rescan the patch's records
+  PatchHdrS* mail = reinterpret_cast<PatchHdrS*>(smem + P::oMail);
   if (tid == 0) {
     for (int b = 0; b < 2; ++b) {
       mbar_init(&bar_full[b], 32);
-      mbar_init(&bar_empty[b], unsigned(n_active / 32) + ((want_epi && epi_holds_input) ? unsigned(n_epi_warps) : 0u));
+      mbar_init(&bar_empty[b], unsigned(n_active / 32));
       mbar_init(&bar_done[b], unsigned(T));
       mbar_init(&bar_free[b], 32u * unsigned(n_epi_warps));
     }
@@ -244,7 +266,7 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
       if (lane == 0) {
         PatchHdrS* hs = reinterpret_cast<PatchHdrS*>(in + P::oHdr);
         hs->v_lo = h.v_lo; hs->n_owned = h.n_owned; hs->n_halo = h.n_halo; hs->n_rounds = h.n_rounds;
-        hs->n_slots = n_slots; hs->pad = 0; hs->slot_off = h.slot_off;
+        hs->n_slots = n_slots; hs->halo_off = h.halo_off; hs->slot_off = h.slot_off;
       }
       const int Pn = h.n_owned;
       {  // level 1: records (16-byte copies: slot_off and n_slots are multiples of 32), halo ids, owned rows
@@ -313,17 +335,14 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
     const bool willmore = (flags & MS_FLAG_WILLMORE) != 0;
     for (int j = 0; want_epi && j < n_my; ++j) {
       const int b = j & 1;
-      mbar_wait_relaxed(&bar_full[b], unsigned((j >> 1) & 1));   // header, records, positions
-      mbar_wait_relaxed(&bar_done[b], unsigned((j >> 1) & 1));   // every round accumulated
-      unsigned char* in = smem + size_t(b) * P::kInBytes;
-      const PatchHdrS hs = *reinterpret_cast<const PatchHdrS*>(in + P::oHdr);
-      const FacetRec* recs = reinterpret_cast<const FacetRec*>(in + P::oRecs);
+      mbar_wait_relaxed(&bar_done[b], unsigned((j >> 1) & 1));   // every round accumulated, header mailed
+      const PatchHdrS hs = mail[b];
       double* acc = reinterpret_cast<double*>(smem + P::oAcc + size_t(b) * P::kAccBytes);
       const int Pn = hs.n_owned;
       LocalA la;
       if (PASS == 0) {
-        la.pos = reinterpret_cast<const double*>(in + P::oPos);
-        la.bfl = has_boundary ? bfl_base + size_t(b) * kPatchLocalCap : nullptr;
+        la.pos = nullptr;
+        la.bfl = nullptr;  // boundary flags of the owned rows come from global memory below
         la.t2 = nullptr;
         la.acc = acc;
         la.P = Pn;
@@ -334,7 +353,9 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
         if (PASS == 0) {
           const double kap = (!FAST && a.kappa) ? a.kappa[row] : a.kappa_u;
           const double c0 = (!FAST && a.c0) ? a.c0[row] : a.c0_u;
-          const VertexSeed sd = vertex_body_a(ST, i, la, recs, hs.n_slots, kap, c0, willmore);
+          auto normal_of = [&](int v) { return vertex_normal_global(a, hs, v); };
+          const bool on_boundary = has_boundary && a.is_boundary[row] != 0;
+          const VertexSeed sd = vertex_body_a(ST, i, la, on_boundary, normal_of, kap, c0, willmore);
           sums[PS_E_BENDING] += sd.E;
           if (a.seeds) {
             double* o = a.seeds + row * kSeedStride;
@@ -378,10 +399,6 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
         }
       }
       mbar_arrive(&bar_free[b]);
-      if (epi_holds_input) {
-        __syncwarp();
-        if ((lane & 31) == 0) mbar_arrive(&bar_empty[b]);
-      }
     }
   } else {
     // ============================= consumers =============================
@@ -447,8 +464,11 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
           if (use_ring) named_sync(bar_mine, ring); else named_sync(1, T);
           if (valid) facet_accumulate_b(ST, rec, out, lb, do_volume, do_tilt);
         }
-        // the last round of the patch hands the accumulator to the epilogue warp
-        if (want_epi && t_rel == n_turns - 1) mbar_arrive(&bar_done[b]);
+        // the last round of the patch hands the accumulator (and the header) to the epilogue warps
+        if (want_epi && t_rel == n_turns - 1) {
+          if (lane == 0) mail[b] = hs;
+          mbar_arrive(&bar_done[b]);
+        }
         if (use_ring) named_arrive(bar_next, ring);
       }
       t_rel -= n_turns;

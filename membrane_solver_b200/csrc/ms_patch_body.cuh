@@ -140,14 +140,14 @@ MS_HD d3 vertex_normal_scan(const S& st, const FacetRec* recs, int n_slots, cons
   return n;
 }
 
-// Vertex stage of owned vertex i (bending.py:112-158).
-template <class S>
-MS_HD VertexSeed vertex_body_a(const S& st, int i, const LocalA& s, const FacetRec* recs, int n_slots,
-                               double kappa, double c0, bool willmore) {
+// Vertex stage of owned vertex i (bending.py:112-158).  normal_of(i) supplies the unit
+// area-weighted vertex normal; it is only called for flat interior vertices.
+template <class S, class NormalFn>
+MS_HD VertexSeed vertex_body_a(const S& st, int i, const LocalA& s, bool boundary, NormalFn normal_of, double kappa,
+                               double c0, bool willmore) {
   const d3 K = ld3s(s.acc, st.A, i);
-  const bool boundary = s.bfl && s.bfl[i] != 0;
   d3 n = make_d3(0, 0, 0);
-  if (!(sqrt(dot(K, K)) > 1.0e-15) && !boundary) n = vertex_normal_scan(st, recs, n_slots, s.pos, i);
+  if (!(sqrt(dot(K, K)) > 1.0e-15) && !boundary) n = normal_of(i);
   return vertex_stage(K, s.acc[3 * st.A + i], s.acc[4 * st.A + i], kappa, willmore ? 0.0 : c0, boundary,
                       willmore, n, 0.0);
 }

@@ -89,7 +89,8 @@ int emul_eval(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* is_boun
       if (bending) {
         for (int i = 0; i < P; ++i) {
           const size_t row = size_t(h.v_lo) + i;
-          const VertexSeed sd = vertex_body_a(st, i, loc, recs, n_slots, kappa ? kappa[row] : kappa_u,
+          auto normal_of = [&](int v) { return vertex_normal_scan(st, recs, n_slots, lpos.data(), v); };
+          const VertexSeed sd = vertex_body_a(st, i, loc, bfl[size_t(i)] != 0, normal_of, kappa ? kappa[row] : kappa_u,
                                               c0 ? c0[row] : c0_u, willmore);
           sums[PS_E_BENDING] += sd.E;
           double* o = seed_store.data() + row * kSeedStrideBody;
