@@ -101,7 +101,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
 // take issue slots from the consumers
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, unsigned parity) {
   const unsigned addr = smem_u32(bar);
-  while (!mbar_try(addr, parity)) __nanosleep(200);
+  while (!mbar_try(addr, parity)) __nanosleep(500);
 }
 __device__ __forceinline__ void named_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
