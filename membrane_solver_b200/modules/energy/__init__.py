@@ -7,7 +7,9 @@ Each module keeps the reference contract (SURVEY.md section 8b)::
 
 accumulating (``+=``) into the caller-owned arrays, plus the optional
 ``compute_energy_array`` and the legacy dict API ``compute_energy_and_gradient``.  On top
-of that each module exposes ``B200_MODULE`` (its kernel bit) and ``b200_configure`` /
+of that each module exposes ``B200_MODULE`` (its kernel bit), ``b200_configure`` and
 ``b200_energy`` so that ``runtime.evaluation_manager.EvaluationManager`` can evaluate all
 loaded B200 modules in ONE fused device pass.
 """
+
+NAMES = ("surface", "volume", "bending", "tilt")

@@ -122,7 +122,7 @@ class DeviceState:
     # -- parameters (sent only when they change) ------------------------------
     def set_gamma(self, gamma) -> None:
         g = np.asarray(gamma, dtype=np.float64)
-        key = (g.shape, float(g.sum()), float(g[0]) if g.size else 0.0, float(g[-1]) if g.size else 0.0)
+        key = (g.shape, hash(g.tobytes()))
         if key != self._gamma_key:
             self.dm.set_surface_tension(g if g.ndim else float(g))
             self._gamma_key = key
@@ -130,8 +130,7 @@ class DeviceState:
     def set_bending(self, kappa, c0) -> None:
         k = np.asarray(kappa, dtype=np.float64)
         c = np.asarray(c0, dtype=np.float64)
-        key = (k.shape, float(k.sum()), float(np.abs(k).max(initial=0.0)), c.shape, float(c.sum()),
-               float(np.abs(c).max(initial=0.0)))
+        key = (k.shape, hash(k.tobytes()), c.shape, hash(c.tobytes()))
         if key != self._bend_key:
             self.dm.set_bending_params(k if k.ndim else float(k), c if c.ndim else float(c))
             self._bend_key = key

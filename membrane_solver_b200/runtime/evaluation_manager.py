@@ -1,0 +1,162 @@
+"""Energy / gradient evaluation orchestration on the B200 path.
+
+Twin of ``runtime/evaluation_manager.py`` (entry points ``:134-225``) with the same constructor
+and method names.  Modules that carry ``B200_MODULE`` are evaluated TOGETHER in one fused device
+pass (one upload of the positions, pass A + pass B, one download of the gradient); any other
+module in the list is called through the reference's array contract with the same
+signature-adapting dispatch (``evaluation_manager.py:45-124``).
+"""
+
+from __future__ import annotations
+
+import inspect
+from typing import Any, Callable
+
+import numpy as np
+
+from .. import _lib as L
+from .device_state import get_state, positions_array
+
+
+class EvaluationManager:
+    def __init__(self, *, mesh, global_params, param_resolver, energy_modules: list[Any],
+                 energy_module_names: list[str], energy_context_fn: Callable | None = None,
+                 experimental_energy_scale_fn: Callable[[str], float] | None = None):
+        self.mesh = mesh
+        self.global_params = global_params
+        self.param_resolver = param_resolver
+        self.energy_modules = energy_modules
+        self.energy_module_names = energy_module_names
+        self.energy_context_fn = energy_context_fn
+        self.experimental_energy_scale_fn = experimental_energy_scale_fn or (lambda name: 1.0)
+        self._specs: dict[int, dict] = {}
+
+    # -- reference-style dispatch for modules without a B200 twin -----------------
+    def _call_fn(self, fn: Callable, **kwargs) -> Any:
+        key = id(getattr(fn, "__func__", fn))
+        spec = self._specs.get(key)
+        if spec is None:
+            params = inspect.signature(fn).parameters
+            var_kw = any(p.kind is inspect.Parameter.VAR_KEYWORD for p in params.values())
+            spec = {"names": list(params), "var_kw": var_kw}
+            self._specs[key] = spec
+        names = spec["names"]
+        call = dict(kwargs)
+        if "resolver" in names:
+            call.setdefault("resolver", self.param_resolver)
+        elif "param_resolver" in names or spec["var_kw"]:
+            call.setdefault("param_resolver", self.param_resolver)
+        if ("ctx" in names or spec["var_kw"]) and self.energy_context_fn is not None:
+            call.setdefault("ctx", self.energy_context_fn())
+        if not spec["var_kw"]:
+            call = {k: v for k, v in call.items() if k in names}
+        args = []
+        if names and names[0] not in call:
+            args.append(self.mesh)
+        if len(names) > 1 and names[1] not in call:
+            args.append(self.global_params)
+        return fn(*args, **call)
+
+    @staticmethod
+    def _coerce(value) -> float:
+        arr = np.asarray(value, dtype=float)
+        return float(arr) if arr.ndim == 0 else float(np.sum(arr))
+
+    # -- the fused device pass -----------------------------------------------------
+    def _split(self):
+        fused, other = [], []
+        for name, mod in zip(self.energy_module_names, self.energy_modules):
+            (fused if hasattr(mod, "B200_MODULE") else other).append((name, mod))
+        return fused, other
+
+    def _fused_eval(self, positions, fused, *, want_grad: bool, grad=None, project: bool = False):
+        """Evaluate the B200 modules in one pass.  Returns ({name: energy}, EvalResult) or None when
+        the module set needs the sequential route (approx-mode boundary zeroing, several bodies)."""
+        pos = positions_array(positions)
+        st = get_state(self.mesh, pos)
+        mask, flags, extra = 0, 0, {}
+        for name, mod in fused:
+            if name == "volume" and L.MOD_VOLUME & mask:
+                continue
+            if name == "volume" and self.global_params.get("volume_constraint_mode", "lagrange") != "penalty":
+                continue  # lagrange mode: the volume enters through the constraint projection
+            if name == "tilt" and float(self.param_resolver.get(None, "tilt_rigidity") or 0.0) == 0.0:
+                continue
+            cfg = mod.b200_configure(st, self.mesh, self.global_params, self.param_resolver)
+            if cfg.get("unfused"):
+                return None
+            mask |= mod.B200_MODULE
+            flags |= cfg.pop("flags", 0)
+            extra.update(cfg)
+        if (flags & L.FLAG_APPROX) and st.boundary is not None:
+            return None
+        constraint_mode = extra.get("constraint_mode", -1)
+        if project and constraint_mode < 0 and st.body_rows is not None:
+            if self.global_params.get("volume_constraint_mode", "lagrange") == "lagrange":
+                mask |= L.MOD_VOLUME
+                constraint_mode = 0
+        opts = st.dm.options(mask, flags=flags, want_grad=want_grad, constraint_mode=constraint_mode,
+                             k_vol=extra.get("k_vol", 0.0), v_target=extra.get("v_target", 0.0),
+                             apply_fixed=project)
+        res = st.dm.eval_host(opts, pos, grad=grad)
+        energies = {}
+        for name, mod in fused:
+            if not (mod.B200_MODULE & mask) or (name == "volume" and constraint_mode != 1):
+                energies[name] = 0.0
+            elif name == "volume":
+                energies[name] = mod.b200_energy(res, extra.get("k_vol", 0.0), extra.get("v_target", 0.0))
+            else:
+                energies[name] = mod.b200_energy(res)
+        return energies, res
+
+    # -- entry points (same names as the reference) --------------------------------
+    def compute_energy_and_gradient_array(self, *, positions):
+        """Raw module energy and dense shape gradient (``evaluation_manager.py:134-151``)."""
+        index_map = self.mesh.vertex_index_to_row
+        fused, other = self._split()
+        grad = np.zeros_like(np.asarray(positions, dtype=np.float64))
+        total = 0.0
+        done = None
+        if fused:
+            done = self._fused_eval(positions, fused, want_grad=True, grad=grad)
+        if done is not None:
+            total += sum(done[0].values())
+        else:
+            other = fused + other
+        for _, mod in other:
+            total += self._call_fn(mod.compute_energy_and_gradient_array, positions=positions, index_map=index_map,
+                                   grad_arr=grad)
+        return float(total), grad
+
+    def compute_energy_and_projected_gradient(self, *, positions):
+        """Energy and the gradient after the single-constraint KKT projection and the fixed-vertex
+        mask, all on the device (``minimizer.py:941-992`` + ``constraint_manager.py:294-301``)."""
+        fused, other = self._split()
+        if other:
+            raise L.B200Error("compute_energy_and_projected_gradient needs every loaded module on the B200 path")
+        grad = np.zeros_like(np.asarray(positions, dtype=np.float64))
+        done = self._fused_eval(positions, fused, want_grad=True, grad=grad, project=True)
+        if done is None:
+            raise L.B200Error("this module set cannot be evaluated in one fused pass")
+        return float(sum(done[0].values())), grad, done[1]
+
+    def compute_energy_breakdown(self, *, positions) -> dict[str, float]:
+        """Per-module energies (``evaluation_manager.py:153-182``)."""
+        index_map = self.mesh.vertex_index_to_row
+        fused, other = self._split()
+        out: dict[str, float] = {}
+        done = self._fused_eval(positions, fused, want_grad=False) if fused else None
+        if done is None:
+            other = fused + other
+        else:
+            out.update(done[0])
+        for name, mod in other:
+            dummy = np.zeros_like(np.asarray(positions, dtype=np.float64))
+            out[name] = float(self._call_fn(mod.compute_energy_and_gradient_array, positions=positions,
+                                            index_map=index_map, grad_arr=dummy))
+        return {name: float(self.experimental_energy_scale_fn(str(name))) * out[name]
+                for name in self.energy_module_names}
+
+    def compute_energy_array_total(self, *, positions) -> float:
+        """Total energy for fixed positions (``evaluation_manager.py:184-225``)."""
+        return float(sum(self.compute_energy_breakdown(positions=positions).values()))
