@@ -176,6 +176,7 @@ def test_residency_follows_the_version_counters(backend):
     _close(e1, 1.21 * e0, 1e-12)
     assert st.uploads == 1
     mesh.bodies.clear()
+    mesh.facet_params["surface_tension"] = g["gamma"][:-2]
     mesh.set_triangles(g["tri"][:-2])   # what refine / equiangulate do: topology version bump
     surface.compute_energy_array(mesh, gp, positions=pos, index_map=idx)
     assert st.uploads == 2 and st.nf == g["tri"].shape[0] - 2
