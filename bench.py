@@ -296,7 +296,8 @@ def run_b200(args):
         except Exception:
             pass
 
-    cpu_val, cpu_nf = cpu_baseline(100, 2, 1) if not args.no_cpu else (None, 0)
+    cpu_reps = 3
+    cpu_val, cpu_nf = cpu_baseline(224, cpu_reps, 1) if not args.no_cpu else (None, 0)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
@@ -312,9 +313,11 @@ def run_b200(args):
             "step_frac_72": B_STRICT * nf / (ms_step * 1e-3) / 1e9 / peak,
         },
         "kernels_ms": {"pass_a": t_a, "pass_b": t_b, "reduce+kkt": t_f},
+        "fp64": {"peak_tflops_measured": 33.9, "note": "tools/fp64_peak.cu on this pool's B200; the path is "
+                 "co-limited by fp64 issue rate, see DESIGN.md section 3.4"},
         "cpu_baseline": None if cpu_val is None else {
             "value": cpu_val, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"2 evaluations of a {cpu_nf}-facet perturbed icosphere, same modules; NumPy oracle "
+            "sample": f"{cpu_reps} evaluations of a {cpu_nf}-facet perturbed icosphere, same modules; NumPy oracle "
                       "with the C restatement of fortran_kernels/*.f90 (gfortran absent), 1 process"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pos.nbytes),
                 "d2h_bytes_per_step": int(grad.nbytes + 8 * L.SC_COUNT), "ms_per_step": ms_e2e,

@@ -344,3 +344,30 @@ def test_trial_positions_energy_only(L):
     dm.accept_trial()
     assert rel_err(dm.download(L.ARR_POSITIONS), x) <= 1e-15
     dm.close()
+
+
+def test_repeatability_stress(L):
+    """The persistent kernels hand buffers between producer, consumer groups and epilogue warps
+    through barriers: 40 back-to-back evaluations at several pack geometries must be bitwise
+    identical (a race would show up as a last-bit or gross difference)."""
+    from membrane_solver_b200.synthetic import icosphere
+
+    pos, tri = icosphere(150)
+    nv, nf = pos.shape[0], tri.shape[0]
+    mods = L.MOD_SURFACE | L.MOD_BENDING | L.MOD_VOLUME
+    for pack in (dict(), dict(threads=32, max_owned=64, max_local=200), dict(threads=160, max_owned=512, max_local=896),
+                 dict(threads=64, max_owned=256, max_local=512)):
+        dm = _ctx(nv, tri, body_mask=np.ones(nf, np.uint8), **pack)
+        dm.set_bending_params(1.0, 0.1)
+        dm.set_positions(pos)
+        opts = dm.options(mods, constraint_mode=0)
+        first = dm.eval(opts)
+        g0, v0, s0 = dm.download(L.ARR_GRAD), dm.download(L.ARR_VOLGRAD), dm.download(L.ARR_SEEDS)
+        for _ in range(40):
+            dm.eval_async(opts)
+        again = dm.read_scalars()
+        assert np.array_equal(first.scalars, again.scalars), pack
+        assert np.array_equal(g0, dm.download(L.ARR_GRAD)), pack
+        assert np.array_equal(v0, dm.download(L.ARR_VOLGRAD)), pack
+        assert np.array_equal(s0, dm.download(L.ARR_SEEDS)), pack
+        dm.close()
