@@ -30,7 +30,7 @@ extern "C" {
 #define MS_MOD_VOLUME        (1u << 1) /* geometry/body.py:150-252: V and dV/dx of the body */
 #define MS_MOD_BENDING       (1u << 2) /* modules/energy/bending.py:90-181 */
 #define MS_MOD_TILT          (1u << 3) /* modules/energy/tilt.py:99-172 */
-#define MS_MOD_BENDING_TILT  (1u << 4) /* modules/energy/bending_tilt.py:151-482 */
+#define MS_MOD_BENDING_TILT  (1u << 4) /* modules/energy/bending_tilt.py:151-482 (single field; not with MS_MOD_BENDING) */
 
 #define MS_FLAG_WILLMORE     (1u << 0) /* bending_energy_model = willmore (bending_params.py:18-21) */
 #define MS_FLAG_APPROX       (1u << 1) /* bending_gradient_mode = approx (bending_params.py:24-31) */
@@ -78,7 +78,8 @@ typedef struct ms_eval_opts {
   int32_t patch_begin;     /* multi-GPU: range of patches this rank evaluates; */
   int32_t patch_count;     /*            patch_count < 0 means all patches */
   int32_t diagnostics;     /* also write K_VECS / A_VOR / A_EFF / E_VERTEX */
-  int32_t reserved;
+  int32_t want_tilt_grad;  /* with want_grad == 0: still produce MS_ARR_TILT_GRAD (tilt-only evaluation,
+                              evaluation_manager.py:693-698) */
 } ms_eval_opts;
 
 typedef struct ms_pack_info {

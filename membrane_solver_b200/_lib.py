@@ -47,7 +47,7 @@ class EvalOpts(ctypes.Structure):
         ("patch_begin", ctypes.c_int32),
         ("patch_count", ctypes.c_int32),
         ("diagnostics", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("want_tilt_grad", ctypes.c_int32),
     ]
 
 

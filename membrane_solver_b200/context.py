@@ -207,12 +207,12 @@ class DeviceMesh:
     def options(modules: int, *, flags: int = 0, want_grad: bool = True, constraint_mode: int = -1,
                 k_vol: float = 0.0, v_target: float = 0.0, apply_fixed: bool = False,
                 use_trial: bool = False, patch_begin: int = 0, patch_count: int = -1,
-                diagnostics: bool = False) -> L.EvalOpts:
+                diagnostics: bool = False, want_tilt_grad: bool = False) -> L.EvalOpts:
         return L.EvalOpts(modules=modules, flags=flags, want_grad=int(want_grad),
                           constraint_mode=constraint_mode, k_vol=k_vol, v_target=v_target,
                           apply_fixed=int(apply_fixed), use_trial=int(use_trial),
                           patch_begin=patch_begin, patch_count=patch_count,
-                          diagnostics=int(diagnostics), reserved=0)
+                          diagnostics=int(diagnostics), want_tilt_grad=int(want_tilt_grad))
 
     def eval(self, opts: L.EvalOpts) -> EvalResult:
         """Evaluate with everything resident; only the 16 scalars come back."""

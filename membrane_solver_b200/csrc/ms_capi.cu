@@ -81,6 +81,11 @@ struct ms_ctx {
   std::vector<cudaEvent_t> events;
   DevBuf<uint8_t> d_flush;
   DevBuf<int32_t> d_send_rows;  // rows other partitions read from this one (halo exchange)
+  // bending-tilt coupling: triangle rows + corner CSR on the device (built on first use)
+  std::vector<int32_t> h_tri;
+  bool bt_ready = false;
+  DevBuf<int32_t> d_tri, d_csr_ptr, d_csr_idx;
+  DevBuf<double> d_bt_corner, d_bt_base, d_bt_facet_e, d_bt_e;
   int64_t n_send_rows = 0;
 };
 
@@ -187,11 +192,59 @@ int fill_launch(ms_ctx* c, const ms_eval_opts* o, ms::PatchLaunch& a) {
     a.a_eff = c->d_aeff.p;
     a.e_vertex = c->d_evert.p;
   }
-  if (o->modules & MS_MOD_BENDING_TILT) return fail(-6, "bending_tilt is not available in the patch path yet");
+  if (o->modules & MS_MOD_BENDING_TILT) {
+    if (o->modules & MS_MOD_BENDING) return fail(-6, "bending and bending_tilt share the seed array; evaluate them separately");
+    if (c->n_owned != c->nv) return fail(-6, "bending_tilt is not available on partitioned (multi-GPU) contexts");
+    if (!c->d_tilts.p) return fail(-5, "bending_tilt requested but no tilts were uploaded");
+    // the patch kernels see it as bending: pass A delivers K, A_vor, A_eff, pass B back-propagates
+    // the seeds computed by the coupling stage (ms_bt.cuh)
+    a.modules = (o->modules & ~uint32_t(MS_MOD_BENDING_TILT)) | MS_MOD_BENDING;
+    for (int w : {MS_ARR_K_VECS, MS_ARR_A_VOR, MS_ARR_A_EFF})
+      if (int rc = ensure_array(c, w)) return rc;
+    a.k_vecs = c->d_kvecs.p;
+    a.a_vor = c->d_avor.p;
+    a.a_eff = c->d_aeff.p;
+    if (o->want_grad || o->want_tilt_grad)
+      if (int rc = ensure_array(c, MS_ARR_TILT_GRAD)) return rc;
+  }
   return 0;
 }
 
-bool needs_bending(const ms_eval_opts* o) { return (o->modules & MS_MOD_BENDING) != 0; }
+bool needs_bending(const ms_eval_opts* o) { return (o->modules & (MS_MOD_BENDING | MS_MOD_BENDING_TILT)) != 0; }
+bool has_bt(const ms_eval_opts* o) { return (o->modules & MS_MOD_BENDING_TILT) != 0; }
+bool wants_tilt_grad(const ms_eval_opts* o) { return o->want_grad || o->want_tilt_grad; }
+
+int bt_prepare(ms_ctx* c, ms::BtMesh& m) {
+  const size_t nv = size_t(c->nv), nf = size_t(c->nf);
+  if (!c->bt_ready) {
+    std::vector<int32_t> ptr, idx;
+    ms::build_corner_csr(c->nv, c->nf, c->h_tri.data(), ptr, idx);
+    if (int rc = c->d_tri.ensure(3 * nf + 1)) return rc;
+    if (int rc = c->d_csr_ptr.ensure(ptr.size())) return rc;
+    if (int rc = c->d_csr_idx.ensure(idx.size() + 1)) return rc;
+    if (nf) CU(cudaMemcpy(c->d_tri.p, c->h_tri.data(), 3 * nf * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_csr_ptr.p, ptr.data(), ptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    if (!idx.empty()) CU(cudaMemcpy(c->d_csr_idx.p, idx.data(), idx.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    if (int rc = c->d_bt_corner.ensure(12 * nf + 1)) return rc;
+    if (int rc = c->d_bt_base.ensure(nv + 1)) return rc;
+    if (int rc = c->d_bt_facet_e.ensure(nf + 1)) return rc;
+    if (int rc = c->d_bt_e.ensure(1)) return rc;
+    c->bt_ready = true;
+  }
+  m.nv = c->nv;
+  m.nf = c->nf;
+  m.tri = c->d_tri.p;
+  m.pos = nullptr;  // set by the caller (positions or trial)
+  m.tilts = c->d_tilts.p;
+  m.is_boundary = c->has_boundary ? c->d_boundary.p : nullptr;
+  m.kappa = c->has_kappa ? c->d_kappa.p : nullptr;
+  m.c0 = c->has_c0 ? c->d_c0.p : nullptr;
+  m.kappa_u = c->kappa_u;
+  m.c0_u = c->c0_u;
+  m.csr_ptr = c->d_csr_ptr.p;
+  m.csr_idx = c->d_csr_idx.p;
+  return 0;
+}
 
 }  // namespace
 
@@ -298,6 +351,8 @@ int ms_ctx_set_topology_partition(ms_ctx* c, int32_t nv, int32_t n_owned, int32_
   if (prc) return fail(-1, "pack_patches failed");
   c->nv = nv;
   c->nf = nf;
+  c->h_tri.assign(tri, tri + 3 * size_t(nf));
+  c->bt_ready = false;
   const ms::PackedMesh& pk = c->packed;
   const size_t np = pk.patches.size();
   c->v_lo.resize(np + 1);
@@ -518,17 +573,38 @@ int ms_ctx_eval_pass_a(ms_ctx* c, const ms_eval_opts* o) {
   a.partials = c->d_partials_a.p;
   c->ran_pass_a = needs_bending(o) || !o->want_grad;
   if (c->ran_pass_a) CU(ms::launch_pass_a(a, c->stream));
+  if (has_bt(o)) {
+    ms::BtMesh m;
+    if (int rc = bt_prepare(c, m)) return rc;
+    m.pos = a.pos;
+    CU(ms::launch_bt_stage(m, 1.0, c->d_kvecs.p, c->d_avor.p, c->d_aeff.p, c->d_bt_corner.p, c->d_seeds.p,
+                           c->d_bt_base.p, c->d_bt_facet_e.p, c->d_bt_e.p, wants_tilt_grad(o), c->stream));
+  }
   return 0;
 }
 
 int ms_ctx_eval_pass_b(ms_ctx* c, const ms_eval_opts* o) {
   if (int rc = check_ctx(c, true)) return rc;
   if (!o) return fail(-1, "null options");
-  if (!o->want_grad) return 0;
+  // a tilt-only evaluation (want_grad == 0, want_tilt_grad == 1) still needs pass B for the tilt
+  // magnitude module, whose tilt gradient comes from the barycentric areas accumulated there
+  const bool run_b = o->want_grad || (o->want_tilt_grad && (o->modules & MS_MOD_TILT));
   ms::PatchLaunch a;
   if (int rc = fill_launch(c, o, a)) return rc;
   a.partials = c->d_partials_b.p;
-  CU(ms::launch_pass_b(a, needs_bending(o), !needs_bending(o), c->stream));
+  if (run_b) {
+    if ((o->modules & MS_MOD_TILT) && !a.tilt_grad) {
+      if (int rc = ensure_array(c, MS_ARR_TILT_GRAD)) return rc;
+      a.tilt_grad = c->d_tilt_grad.p;
+    }
+    CU(ms::launch_pass_b(a, needs_bending(o), !needs_bending(o), c->stream));
+  }
+  if (has_bt(o) && wants_tilt_grad(o)) {
+    ms::BtMesh m;
+    if (int rc = bt_prepare(c, m)) return rc;
+    m.pos = a.pos;
+    CU(ms::launch_bt_tilt_gather(m, c->d_bt_corner.p, c->d_tilt_grad.p, run_b && (o->modules & MS_MOD_TILT), c->stream));
+  }
   return 0;
 }
 
@@ -553,6 +629,7 @@ int ms_ctx_eval_reduce(ms_ctx* c, const ms_eval_opts* o) {
   }
   CU(ms::launch_reduce_partials(c->d_partials_a.p, ran_a ? rows : 0, c->d_partials_b.p, o->want_grad ? rows : 0,
                                 b_mask, c->d_scalars.p, c->stream));
+  if (has_bt(o)) CU(ms::launch_bt_finalize(c->d_bt_e.p, c->d_scalars.p, c->stream));
   return 0;
 }
 
@@ -601,7 +678,7 @@ int ms_ctx_eval_host(ms_ctx* c, const ms_eval_opts* o, const double* pos_host, d
     CU(cudaMemcpyAsync(grad_host, c->d_grad.p, bytes, cudaMemcpyDeviceToHost, c->stream));
   if (o->want_grad && volgrad_host && n3 && (o->modules & MS_MOD_VOLUME))
     CU(cudaMemcpyAsync(volgrad_host, c->d_volgrad.p, bytes, cudaMemcpyDeviceToHost, c->stream));
-  if (o->want_grad && tilt_grad_host && n3 && c->d_tilt_grad.p)
+  if ((o->want_grad || o->want_tilt_grad) && tilt_grad_host && n3 && c->d_tilt_grad.p)
     CU(cudaMemcpyAsync(tilt_grad_host, c->d_tilt_grad.p, bytes, cudaMemcpyDeviceToHost, c->stream));
   return ms_ctx_read_scalars(c, scalars16);
 }

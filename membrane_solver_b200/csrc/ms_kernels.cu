@@ -23,6 +23,7 @@
 // Reference functions replaced: see the header of ms_math.cuh.
 #include "ms_kernels.cuh"
 
+#include "ms_bt.cuh"
 #include "ms_patch_body.cuh"
 
 namespace ms {
@@ -749,6 +750,32 @@ __global__ void __launch_bounds__(256) k_sum(const double* __restrict__ x, int64
   if (threadIdx.x == 0) *out = v[0] * scale;
 }
 
+// ---- bending-tilt coupling (ms_bt.cuh): per-facet / per-vertex passes on global arrays ----
+__global__ void __launch_bounds__(128) k_bt_facet_a(BtMesh m, double sign, double* corner4) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f < m.nf) bt_facet_a(m, f, sign, corner4);
+}
+
+__global__ void __launch_bounds__(128) k_bt_vertex(BtMesh m, const double* __restrict__ k_vecs,
+                                                   const double* __restrict__ a_vor,
+                                                   const double* __restrict__ a_eff,
+                                                   const double* __restrict__ corner4, double* seeds, double* base) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < m.nv) bt_vertex(m, v, k_vecs, a_vor, a_eff, corner4, seeds, base);
+}
+
+__global__ void __launch_bounds__(128) k_bt_facet_b(BtMesh m, const double* __restrict__ base, double sign,
+                                                    double* corner3, double* facet_e) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f < m.nf) facet_e[f] = bt_facet_b(m, f, base, sign, corner3);
+}
+
+// scalars[E_BENDING_TILT] <- *e_bt; the pass-A bending energy slot was only a by-product here
+__global__ void k_bt_finalize(const double* e_bt, double* scalars) {
+  scalars[SC_E_BENDING_TILT] = *e_bt;
+  scalars[SC_E_BENDING] = 0.0;
+}
+
 inline int blocks_for(int64_t n, int t) { return int((n + t - 1) / t); }
 
 }  // namespace
@@ -903,6 +930,30 @@ cudaError_t launch_p1_divergence(const SoupArgs& s, const double* tilts, double*
 
 cudaError_t launch_sum(const double* x, int64_t n, double scale, double* out, cudaStream_t st) {
   k_sum<<<1, 256, 0, st>>>(x, n, scale, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bt_stage(const BtMesh& m, double sign, const double* k_vecs, const double* a_vor,
+                            const double* a_eff, double* corner /* 12*nf doubles */, double* seeds, double* base,
+                            double* facet_e, double* e_out, bool tilt_grads, cudaStream_t st) {
+  if (m.nf > 0) k_bt_facet_a<<<blocks_for(m.nf, 128), 128, 0, st>>>(m, sign, corner);
+  if (m.nv > 0) k_bt_vertex<<<blocks_for(m.nv, 128), 128, 0, st>>>(m, k_vecs, a_vor, a_eff, corner, seeds, base);
+  // the corner buffer is free again: it now receives the tilt-gradient contributions (9 per facet)
+  if (m.nf > 0) k_bt_facet_b<<<blocks_for(m.nf, 128), 128, 0, st>>>(m, base, sign, tilt_grads ? corner : nullptr, facet_e);
+  k_sum<<<1, 256, 0, st>>>(facet_e, m.nf, 1.0, e_out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bt_tilt_gather(const BtMesh& m, const double* corner3, double* tilt_grad, bool accumulate,
+                                  cudaStream_t st) {
+  if (m.nv > 0)
+    k_gather<<<blocks_for(m.nv, 128), 128, 0, st>>>(m.nv, m.csr_ptr, m.csr_idx, corner3, 3, 0, 3, tilt_grad, 3,
+                                                     accumulate ? 1 : 0);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bt_finalize(const double* e_bt, double* scalars, cudaStream_t st) {
+  k_bt_finalize<<<1, 1, 0, st>>>(e_bt, scalars);
   return cudaGetLastError();
 }
 

@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include "../../include/ms_b200.h"
+#include "ms_bt.cuh"
 #include "ms_math.cuh"
 #include "ms_pack.h"
 
@@ -126,5 +127,15 @@ cudaError_t launch_grad_cotan(int32_t n, const double* u, const double* v, doubl
 cudaError_t launch_p1_divergence(const SoupArgs& s, const double* tilts, double* div, double* area,
                                  double* g0, double* g1, double* g2, cudaStream_t st);
 cudaError_t launch_sum(const double* x, int64_t n, double scale, double* out, cudaStream_t st);
+
+// --- bending-tilt coupling on the resident mesh (ms_bt.cuh); corner holds 12*nf doubles ---
+// stage: divergence / effective areas -> vertex seeds (into `seeds`, read by pass B) and base term ->
+// per-facet energy (sum into e_out) and, when tilt_grads, corner contributions of the tilt gradient
+cudaError_t launch_bt_stage(const BtMesh& m, double sign, const double* k_vecs, const double* a_vor,
+                            const double* a_eff, double* corner, double* seeds, double* base, double* facet_e,
+                            double* e_out, bool tilt_grads, cudaStream_t st);
+cudaError_t launch_bt_tilt_gather(const BtMesh& m, const double* corner3, double* tilt_grad, bool accumulate,
+                                  cudaStream_t st);
+cudaError_t launch_bt_finalize(const double* e_bt, double* scalars, cudaStream_t st);
 
 }  // namespace ms

@@ -12,4 +12,4 @@ of that each module exposes ``B200_MODULE`` (its kernel bit), ``b200_configure``
 loaded B200 modules in ONE fused device pass.
 """
 
-NAMES = ("surface", "volume", "bending", "tilt")
+NAMES = ("surface", "volume", "bending", "tilt", "bending_tilt")

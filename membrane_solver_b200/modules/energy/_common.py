@@ -134,5 +134,5 @@ def dict_api(array_fn):
     return compute_energy_and_gradient
 
 
-__all__ = ["L", "gp_get", "energy_model", "gradient_mode", "spontaneous_curvature", "per_vertex_bending_params",
+__all__ = ["L", "get_state", "positions_array", "gp_get", "energy_model", "gradient_mode", "spontaneous_curvature", "per_vertex_bending_params",
            "max_abs", "device_eval", "scratch_like", "accumulate", "dict_api"]

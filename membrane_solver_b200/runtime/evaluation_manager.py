@@ -75,6 +75,11 @@ class EvaluationManager:
         pos = positions_array(positions)
         st = get_state(self.mesh, pos)
         mask, flags, extra = 0, 0, {}
+        bits = 0
+        for _, mod in fused:
+            bits |= mod.B200_MODULE
+        if (bits & L.MOD_BENDING) and (bits & L.MOD_BENDING_TILT):
+            return None  # both write the seed array: evaluate them one after the other
         for name, mod in fused:
             if name == "volume" and L.MOD_VOLUME & mask:
                 continue
@@ -156,6 +161,41 @@ class EvaluationManager:
                                             index_map=index_map, grad_arr=dummy))
         return {name: float(self.experimental_energy_scale_fn(str(name))) * out[name]
                 for name in self.energy_module_names}
+
+    def compute_total_energy_array_with_tilts(self, *, positions, tilts) -> float:
+        """Total energy for fixed positions and a given tilt field (``evaluation_manager.py:227-301``)."""
+        index_map = self.mesh.vertex_index_to_row
+        total = 0.0
+        for name, mod in zip(self.energy_module_names, self.energy_modules):
+            scale = float(self.experimental_energy_scale_fn(str(name)))
+            kwargs = {"positions": positions, "index_map": index_map}
+            if getattr(mod, "USES_TILT", False):
+                kwargs["tilts"] = tilts
+            if hasattr(mod, "compute_energy_array"):
+                total += scale * self._coerce(self._call_fn(mod.compute_energy_array, **kwargs))
+            else:
+                dummy = np.zeros_like(np.asarray(positions, dtype=np.float64))
+                total += scale * self._coerce(self._call_fn(mod.compute_energy_and_gradient_array, grad_arr=dummy,
+                                                            **kwargs))
+        return float(total)
+
+    def compute_energy_and_tilt_gradient_array(self, *, positions, tilts, tilt_grad_arr) -> float:
+        """Tilt-dependent energy and dense tilt gradient (``evaluation_manager.py:386-462``): only the
+        modules with ``USES_TILT`` take part; ``tilt_grad_arr`` is overwritten."""
+        index_map = self.mesh.vertex_index_to_row
+        tilt_grad_arr.fill(0.0)
+        total = 0.0
+        for name, mod in zip(self.energy_module_names, self.energy_modules):
+            if not getattr(mod, "USES_TILT", False):
+                continue
+            scale = float(self.experimental_energy_scale_fn(str(name)))
+            part = np.zeros_like(tilt_grad_arr)
+            dummy = None if hasattr(mod, "B200_MODULE") else np.zeros_like(np.asarray(positions, dtype=np.float64))
+            e = self._call_fn(mod.compute_energy_and_gradient_array, positions=positions, index_map=index_map,
+                              grad_arr=dummy, tilts=tilts, tilt_grad_arr=part)
+            tilt_grad_arr += scale * part
+            total += scale * float(e)
+        return float(total)
 
     def compute_energy_array_total(self, *, positions) -> float:
         """Total energy for fixed positions (``evaluation_manager.py:184-225``)."""

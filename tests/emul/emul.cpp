@@ -8,6 +8,7 @@
 #include <cstring>
 #include <vector>
 
+#include "../../membrane_solver_b200/csrc/ms_bt.cuh"
 #include "../../membrane_solver_b200/csrc/ms_patch_body.cuh"
 
 using namespace ms;
@@ -47,7 +48,16 @@ int emul_eval(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* is_boun
     pack_stats[6] = pk.n_hw_groups;
     pack_stats[7] = pk.n_hw_excess;
   }
-  const bool bending = (modules & MS_MOD_BENDING) != 0;
+  const bool bt = (modules & MS_MOD_BENDING_TILT) != 0;
+  const bool bending = (modules & (MS_MOD_BENDING | MS_MOD_BENDING_TILT)) != 0;
+  // the coupling stage needs K, A_vor, A_eff of every vertex
+  std::vector<double> kv_store, av_store, ae_store;
+  if (bt) {
+    if (!k_vecs) { kv_store.assign(3 * size_t(nv), 0.0); k_vecs = kv_store.data(); }
+    if (!a_vor) { av_store.assign(size_t(nv), 0.0); a_vor = av_store.data(); }
+    if (!a_eff) { ae_store.assign(size_t(nv), 0.0); a_eff = ae_store.data(); }
+  }
+  if (bt) modules = (modules & ~uint32_t(MS_MOD_BENDING_TILT)) | MS_MOD_BENDING;
   const bool do_tilt = (modules & MS_MOD_TILT) && tilts;
   const bool willmore = (flags & MS_FLAG_WILLMORE) != 0;
   std::vector<double> seed_store(size_t(nv) * kSeedStrideBody, 0.0);
@@ -103,6 +113,22 @@ int emul_eval(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* is_boun
       }
       for (int k = 0; k < PS_COUNT; ++k) total[k] += sums[k];
     }
+  }
+  double e_bt = 0.0;
+  std::vector<double> bt_corner;
+  std::vector<int32_t> csr_ptr, csr_idx;
+  BtMesh bm;
+  if (bt) {
+    build_corner_csr(nv, nf, tri, csr_ptr, csr_idx);
+    bm.nv = nv; bm.nf = nf; bm.tri = tri; bm.pos = pos; bm.tilts = tilts; bm.is_boundary = is_boundary;
+    bm.kappa = kappa; bm.c0 = c0; bm.kappa_u = kappa_u; bm.c0_u = c0_u;
+    bm.csr_ptr = csr_ptr.data(); bm.csr_idx = csr_idx.data();
+    bt_corner.assign(12 * size_t(nf) + 1, 0.0);
+    std::vector<double> base(size_t(nv) + 1, 0.0);
+    for (int f = 0; f < nf; ++f) bt_facet_a(bm, f, 1.0, bt_corner.data());
+    for (int v = 0; v < nv; ++v) bt_vertex(bm, v, k_vecs, a_vor, a_eff, bt_corner.data(), seed_store.data(), base.data());
+    for (int f = 0; f < nf; ++f) e_bt += bt_facet_b(bm, f, base.data(), 1.0, tilt_grad ? bt_corner.data() : nullptr);
+    total[PS_E_BENDING] = 0.0;
   }
   if (seeds && phase != 2) std::memcpy(seeds, seed_store.data(), seed_store.size() * sizeof(double));
 
@@ -160,6 +186,16 @@ int emul_eval(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* is_boun
     else
       total[PS_E_TILT] = total_b[PS_E_TILT];
   }
+  if (bt && tilt_grad) {  // tilt gradient of the coupling term: fixed-order CSR gather, added to the tilt module's
+    for (int v = 0; v < nv; ++v)
+      for (int d = 0; d < 3; ++d) {
+        double acc = 0.0;
+        for (int j = csr_ptr[size_t(v)]; j < csr_ptr[size_t(v) + 1]; ++j) acc += bt_corner[3 * size_t(csr_idx[size_t(j)]) + d];
+        double& o = tilt_grad[3 * size_t(v) + d];
+        o = (do_tilt && want_grad) ? o + acc : acc;
+      }
+  }
+  total[PS_E_BENDING_TILT] = e_bt;
   total[PS_VOLUME6] /= 6.0;
   for (int k = 0; k < 8; ++k) scalars8[k] = total[k];
   return 0;

@@ -58,6 +58,7 @@ class FakeDeviceMesh:
         sc = np.zeros(L.SC_COUNT)
         sc[L.SC_E_SURFACE], sc[L.SC_AREA], sc[L.SC_VOLUME] = out["E_surface"], out["area"], out["volume"]
         sc[L.SC_E_BENDING], sc[L.SC_E_TILT] = out["E_bending"], out["E_tilt"]
+        sc[L.SC_E_BENDING_TILT] = out["E_bending_tilt"]
         g_out, gc = out["grad"], out["volgrad"]
         if opts.get("want_grad", True):
             # numpy restatement of k_dots / k_project (TEST ONLY)

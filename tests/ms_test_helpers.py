@@ -103,6 +103,7 @@ def emulate(pos, tri, *, modules, flags=0, want_grad=True, is_boundary=None, bod
     if rc:
         raise RuntimeError(f"emul_eval failed: {rc}")
     out.update(E_surface=scal[0], area=scal[1], volume=scal[2], E_bending=scal[3], E_tilt=scal[4],
+               E_bending_tilt=scal[5],
                pack=dict(n_patches=int(stats[0]), n_slots=int(stats[1]), n_listed=int(stats[2]),
                          max_rounds=int(stats[3]), max_local=int(stats[4]),
                          lane_conflicts=int(stats[5]), hw_groups=int(stats[6]), hw_excess=int(stats[7])))

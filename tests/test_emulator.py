@@ -64,3 +64,28 @@ def test_lane_placement_properties():
     assert p["hw_excess"] <= 0.6 * p["hw_groups"]  # unplaced (random) lanes give ~2.0
     area = 0.5 * np.linalg.norm(np.cross(pos[tri[:, 1]] - pos[tri[:, 0]], pos[tri[:, 2]] - pos[tri[:, 0]]), axis=1).sum()
     assert abs(out["area"] - area) <= 1e-13 * area
+
+
+@pytest.mark.parametrize("path", golden_module_files(), ids=golden_ids())
+def test_emulated_bending_tilt_vs_reference_golden(path):
+    """Single-field bending_tilt (bending_tilt.py:151-482): energy, shape gradient (div treated as
+    constant), exact tilt gradient, and the tilt-only evaluation."""
+    g = dict(np.load(path))
+    pos, tri = g["pos"], g["tri"]
+    for tag, (wil, apx) in BENDING_TAGS.items():
+        if wil:
+            continue
+        kappa, c0 = g[f"param_{tag}"]
+        out = H.emulate(pos, tri, modules=H.MOD_BENDING_TILT, flags=apx, is_boundary=g["is_boundary"],
+                        tilts=g["tilts"], kappa_u=float(kappa), c0_u=float(c0))
+        e = float(g[f"E_bending_tilt_{tag}"])
+        assert abs(out["E_bending_tilt"] - e) <= TOL * max(1.0, abs(e)), tag
+        grad = out["grad"]
+        if apx:
+            grad[g["is_boundary"]] = 0.0
+        assert rel_err(grad, g[f"g_bending_tilt_{tag}"]) <= 2e-12, tag
+        assert rel_err(out["tilt_grad"], g[f"tg_bending_tilt_{tag}"]) <= TOL, tag
+        only = H.emulate(pos, tri, modules=H.MOD_BENDING_TILT, flags=apx, want_grad=False, is_boundary=g["is_boundary"],
+                         tilts=g["tilts"], kappa_u=float(kappa), c0_u=float(c0))
+        assert abs(only["E_bending_tilt"] - e) <= TOL * max(1.0, abs(e)), tag
+        assert rel_err(only["tilt_grad"], g[f"tgonly_bending_tilt_{tag}"]) <= TOL, tag

@@ -371,3 +371,48 @@ def test_repeatability_stress(L):
         assert np.array_equal(v0, dm.download(L.ARR_VOLGRAD)), pack
         assert np.array_equal(s0, dm.download(L.ARR_SEEDS)), pack
         dm.close()
+
+
+@pytest.mark.parametrize("path", golden_module_files(), ids=golden_ids())
+def test_bending_tilt_vs_reference_golden(L, path):
+    """bending_tilt through the C ABI: coupling stage (divergence, seeds, energy, tilt gradient) +
+    pass B back-propagation, against the reference's vectors; tilt-only evaluation; combined with
+    the tilt-magnitude module."""
+    g = dict(np.load(path))
+    pos, tri = g["pos"], g["tri"]
+    nv = pos.shape[0]
+    is_b = g["is_boundary"].astype(np.uint8) if g["is_boundary"].any() else None
+    for pack in (dict(), dict(threads=32, max_owned=24, max_local=100)):
+        dm = _ctx(nv, tri, is_boundary=is_b, **pack)
+        dm.set_tilts(g["tilts"])
+        dm.set_tilt_rigidity(float(g["k_tilt"]))
+        for tag, (wil, apx) in BENDING_TAGS.items():
+            if wil:
+                continue
+            kappa, c0 = g[f"param_{tag}"]
+            dm.set_bending_params(float(kappa), float(c0))
+            grad, tg = np.empty_like(pos), np.empty_like(pos)
+            r = dm.eval_host(dm.options(L.MOD_BENDING_TILT, flags=apx), pos, grad=grad, tilt_grad=tg)
+            _scalar_close(float(r.scalars[L.SC_E_BENDING_TILT]), float(g[f"E_bending_tilt_{tag}"]))
+            assert r.e_bending == 0.0
+            if apx:
+                grad[g["is_boundary"]] = 0.0
+            assert rel_err(grad, g[f"g_bending_tilt_{tag}"]) <= 2e-12, tag
+            assert rel_err(tg, g[f"tg_bending_tilt_{tag}"]) <= TOL, tag
+            tg2 = np.empty_like(pos)
+            r = dm.eval_host(dm.options(L.MOD_BENDING_TILT, flags=apx, want_grad=False, want_tilt_grad=True), pos,
+                             tilt_grad=tg2)
+            _scalar_close(float(r.scalars[L.SC_E_BENDING_TILT]), float(g[f"E_bending_tilt_{tag}"]))
+            assert rel_err(tg2, g[f"tgonly_bending_tilt_{tag}"]) <= TOL, tag
+        # together with the tilt-magnitude module: energies separate, tilt gradients summed
+        kappa, c0 = g["param_helfrich_analytic"]
+        dm.set_bending_params(float(kappa), float(c0))
+        grad, tg = np.empty_like(pos), np.empty_like(pos)
+        r = dm.eval_host(dm.options(L.MOD_BENDING_TILT | L.MOD_TILT), pos, grad=grad, tilt_grad=tg)
+        _scalar_close(r.e_tilt, float(g["E_tilt"]))
+        _scalar_close(float(r.scalars[L.SC_E_BENDING_TILT]), float(g["E_bending_tilt_helfrich_analytic"]))
+        assert rel_err(grad, g["g_tilt"] + g["g_bending_tilt_helfrich_analytic"]) <= 2e-12
+        assert rel_err(tg, g["tg_tilt"] + g["tg_bending_tilt_helfrich_analytic"]) <= TOL
+        with pytest.raises(L.B200Error):
+            dm.eval(dm.options(L.MOD_BENDING_TILT | L.MOD_BENDING))
+        dm.close()

@@ -12,7 +12,7 @@ from ms_test_helpers import golden_ids, golden_module_files, rel_err
 from membrane_solver_b200 import _lib as L
 from membrane_solver_b200.geometry.array_mesh import ArrayBody, ArrayMesh, GlobalParams, ParamResolver
 from membrane_solver_b200.modules.constraints import volume as volume_constraint
-from membrane_solver_b200.modules.energy import bending, surface, tilt, volume
+from membrane_solver_b200.modules.energy import bending, bending_tilt, surface, tilt, volume
 from membrane_solver_b200.runtime import device_state
 from membrane_solver_b200.runtime.energy_manager import EnergyModuleManager
 from membrane_solver_b200.runtime.evaluation_manager import EvaluationManager
@@ -112,6 +112,38 @@ def test_plugin_modules_vs_reference_golden(backend, path):
     _close(tilt.compute_energy_array(mesh, gp, res, positions=pos, index_map=idx), float(g["E_tilt"]))
     with pytest.raises(ValueError):
         tilt.compute_energy_array(mesh, gp, res, positions=pos, index_map=idx, tilts=np.zeros((3, 3)))
+
+    # bending_tilt (single field): energy, shape gradient, exact tilt gradient, tilt-only evaluation
+    for tag, (model, mode) in BENDING_TAGS.items():
+        if model != "helfrich":
+            continue
+        kappa, c0 = (float(x) for x in g[f"param_{tag}"])
+        gp.update(bending_modulus=kappa, spontaneous_curvature=c0, bending_energy_model=model,
+                  bending_gradient_mode=mode)
+        grad, tg = np.zeros_like(pos), np.zeros_like(pos)
+        e = bending_tilt.compute_energy_and_gradient_array(mesh, gp, res, positions=pos, index_map=idx,
+                                                           grad_arr=grad, tilt_grad_arr=tg)
+        _close(e, float(g[f"E_bending_tilt_{tag}"]))
+        assert rel_err(grad, g[f"g_bending_tilt_{tag}"]) <= 2e-12, tag
+        assert rel_err(tg, g[f"tg_bending_tilt_{tag}"]) <= TOL, tag
+        tg = np.zeros_like(pos)
+        e = bending_tilt.compute_energy_and_gradient_array(mesh, gp, res, positions=pos, index_map=idx,
+                                                           grad_arr=None, tilts=g["tilts"], tilt_grad_arr=tg)
+        _close(e, float(g[f"E_bending_tilt_{tag}"]))
+        assert rel_err(tg, g[f"tgonly_bending_tilt_{tag}"]) <= TOL, tag
+    # the evaluation manager's tilt entry point: tilt + bending_tilt, tilt gradients summed
+    kappa, c0 = (float(x) for x in g["param_helfrich_analytic"])
+    gp.update(bending_modulus=kappa, spontaneous_curvature=c0, bending_energy_model="helfrich",
+              bending_gradient_mode="analytic")
+    mods = [tilt, bending_tilt, surface]
+    ev = EvaluationManager(mesh=mesh, global_params=gp, param_resolver=res, energy_modules=mods,
+                           energy_module_names=["tilt", "bending_tilt", "surface"])
+    tg = np.full_like(pos, 7.0)
+    e = ev.compute_energy_and_tilt_gradient_array(positions=pos, tilts=g["tilts"], tilt_grad_arr=tg)
+    _close(e, float(g["E_tilt"]) + float(g["E_bending_tilt_helfrich_analytic"]))
+    assert rel_err(tg, g["tg_tilt"] + g["tgonly_bending_tilt_helfrich_analytic"]) <= TOL
+    _close(ev.compute_total_energy_array_with_tilts(positions=pos, tilts=g["tilts"]),
+           float(g["E_tilt"]) + float(g["E_bending_tilt_helfrich_analytic"]) + float(g["E_surface"]))
 
 
 def test_bending_finite_difference_mode_is_refused(backend):
