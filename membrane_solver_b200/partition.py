@@ -204,6 +204,18 @@ class PartitionedMesh:
         self.eval_async(opts, **kw)
         return self.dm.read_scalars()
 
+    def eval_host(self, opts, pos_owned: np.ndarray, grad_owned: np.ndarray):
+        """End-to-end evaluation with HOST buffers: this rank uploads the positions of its OWNED rows,
+        the ghost rows arrive through the halo exchange, and the projected gradient of the owned rows
+        is copied back together with the (global) scalars."""
+        L, dm, n = self.L, self.dm, self.local.n_owned
+        lib = L.lib()
+        L.check(lib.ms_ctx_upload(dm._h, L.ARR_TRIAL if opts.use_trial else L.ARR_POSITIONS, L.dptr(pos_owned), 0,
+                                  3 * n))
+        self.eval_async(opts, exchange_positions=True)
+        L.check(lib.ms_ctx_get_array(dm._h, L.ARR_GRAD, L.dptr(grad_owned), 0, 3 * n))
+        return dm.read_scalars()
+
 
 def bench_multi_gpu(args, rank: int, world: int, local_rank: int, bench):
     """N>1 arm of bench.py: weak scaling, ``args.facets`` facets per GPU."""
@@ -243,7 +255,8 @@ def bench_multi_gpu(args, rank: int, world: int, local_rank: int, bench):
     dm = pm.dm
     dm.set_surface_tension(1.0)
     dm.set_bending_params(1.0, 0.0)
-    dm.set_positions(pos[local.global_rows()])
+    pos_local = pos[local.global_rows()]
+    dm.set_positions(pos_local)
     del pos
     opts = dm.options(L.MOD_SURFACE | L.MOD_BENDING | L.MOD_VOLUME, constraint_mode=0)
 
@@ -267,6 +280,31 @@ def bench_multi_gpu(args, rank: int, world: int, local_rank: int, bench):
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_step = float(ms.item()) / args.steps
     res = dm.read_scalars()
+    # ---- end to end: pinned host positions of the owned rows in, projected gradient out, every step ----
+    lib = L.lib()
+    pos_owned = np.ascontiguousarray(pos_local[:local.n_owned])
+    grad_owned = np.empty_like(pos_owned)
+    L.check(lib.ms_host_register(pos_owned.ctypes.data, pos_owned.nbytes))
+    L.check(lib.ms_host_register(grad_owned.ctypes.data, grad_owned.nbytes))
+    for _ in range(2):
+        pm.eval_host(opts, pos_owned, grad_owned)
+    e2e_steps = max(3, min(args.steps, 10))
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(e2e_steps):
+        pm.eval_host(opts, pos_owned, grad_owned)
+    ev1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms2 = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=pm.device)
+    dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    ms_e2e = float(ms2.item()) / e2e_steps
+    L.check(lib.ms_host_unregister(pos_owned.ctypes.data))
+    L.check(lib.ms_host_unregister(grad_owned.ctypes.data))
+    io = torch.tensor([pos_owned.nbytes, grad_owned.nbytes + 8 * L.SC_COUNT], dtype=torch.float64, device=pm.device)
+    dist.all_reduce(io, op=dist.ReduceOp.SUM)
     ghosts = torch.tensor([local.ghost_ids.size, pm.halo.send_rows.size], dtype=torch.float64, device=pm.device)
     dist.all_reduce(ghosts, op=dist.ReduceOp.MAX)
     sampler.close()
@@ -283,7 +321,10 @@ def bench_multi_gpu(args, rank: int, world: int, local_rank: int, bench):
                          "peak": peak * world, "unit": "GB/s", "frac": bench.B_STEP * value / (peak * world),
                          "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({peak_kind}) x {world} GPUs",
                          "bytes_per_facet": bench.B_STEP},
-            "e2e": None,
+            "e2e": {"value": nf / (ms_e2e * 1e-3) / 1e9, "unit": bench.UNIT, "h2d_bytes_per_step": int(io[0].item()),
+                    "d2h_bytes_per_step": int(io[1].item()), "ms_per_step": ms_e2e,
+                    "api": "PartitionedMesh.eval_host per rank (pinned owned positions in, halo exchange, "
+                           "projected gradient of the owned rows + scalars out)"},
             "collectives_per_step": {"halo_exchanges": 2, "all_reduce": 1,
                                      "halo_bytes_per_rank": int(ghosts[0].item()) * (24 + 40)},
             "gpu_launches": 6 * args.steps,  # pass A, pass B, reduce, project + 2 halo gathers
