@@ -116,6 +116,14 @@ MS_API int ms_ctx_set_pack_tuning(ms_ctx* ctx, int32_t fill_pct, int32_t repair_
 /* kept for ABI stability; the persistent kernels derive the thread-group count from the CTA
  * size (consumer threads / threads-per-round) */
 MS_API int ms_ctx_set_groups(ms_ctx* ctx, int32_t groups_a, int32_t groups_b);
+/* Optional: positions (nv,3) used ONLY to choose the internal vertex order of the next
+ * ms_ctx_set_topology (Morton curve), so that meshes in arbitrary vertex order -- e.g. the
+ * refinement order of runtime/refinement.py -- still pack into compact patches.  Transparent to
+ * the caller: every host-side upload / download of a per-vertex array is in the caller's order;
+ * only ms_ctx_device_ptr exposes internal rows (ms_ctx_get_permutation: internal row -> caller row).
+ * Not used for partitions (n_owned < nv), which arrive ordered. */
+MS_API int ms_ctx_set_vertex_order_hint(ms_ctx* ctx, int32_t nv, const double* pos);
+MS_API int ms_ctx_get_permutation(const ms_ctx* ctx, int32_t* perm_new_to_old);
 /* Re-called only after refine / equiangulate / vertex-average changed the topology
  * (commands/mesh_ops.py:21-78).  is_boundary, body_mask, fixed_mask may be NULL. */
 MS_API int ms_ctx_set_topology(ms_ctx* ctx, int32_t nv, int32_t nf, const int32_t* tri,

@@ -100,8 +100,9 @@ class DeviceMesh:
 
     # -- topology and parameters --------------------------------------------
     def set_topology(self, nv: int, tri: np.ndarray, *, is_boundary=None, body_mask=None,
-                     fixed_mask=None, n_owned: int | None = None) -> None:
-        """``n_owned`` < nv marks rows [n_owned, nv) as ghosts of other partitions (multi-GPU)."""
+                     fixed_mask=None, n_owned: int | None = None, order_hint=None) -> None:
+        """``n_owned`` < nv marks rows [n_owned, nv) as ghosts of other partitions (multi-GPU).
+        ``order_hint``: positions (nv,3) used only to pick the internal (Morton) vertex order."""
         tri = np.ascontiguousarray(tri, dtype=np.int32).reshape(-1, 3)
         keep = [tri]
 
@@ -118,10 +119,19 @@ class DeviceMesh:
         bm = mask(body_mask, tri.shape[0])
         fx = mask(fixed_mask, nv)
         self.n_owned = int(nv if n_owned is None else n_owned)
+        if order_hint is not None and self.n_owned == int(nv):
+            hint = L.as_f64(order_hint, (int(nv), 3))
+            L.check(self._lib.ms_ctx_set_vertex_order_hint(self._h, int(nv), L.dptr(hint)))
         L.check(self._lib.ms_ctx_set_topology_partition(self._h, int(nv), self.n_owned, int(tri.shape[0]),
                                                         L.iptr(tri), L.bptr(b), L.bptr(bm), L.bptr(fx)))
         self.nv = int(nv)
         self.nf = int(tri.shape[0])
+
+    def permutation(self) -> np.ndarray:
+        """Internal row -> caller's vertex row."""
+        out = np.empty(self.nv, dtype=np.int32)
+        L.check(self._lib.ms_ctx_get_permutation(self._h, L.iptr(out)))
+        return out
 
     def pack_info(self) -> dict:
         info = L.PackInfo()

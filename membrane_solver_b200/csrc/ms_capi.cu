@@ -3,7 +3,9 @@
 // fortran_kernels/loader.py for the energy+gradient path.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
+#include <numeric>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -81,6 +83,11 @@ struct ms_ctx {
   std::vector<cudaEvent_t> events;
   DevBuf<uint8_t> d_flush;
   DevBuf<int32_t> d_send_rows;  // rows other partitions read from this one (halo exchange)
+  // internal vertex order: row i of every device array holds the caller's vertex perm[i]
+  std::vector<double> order_hint;       // positions given by ms_ctx_set_vertex_order_hint (consumed by set_topology)
+  std::vector<int32_t> perm;            // new -> old; empty = identity
+  DevBuf<int32_t> d_perm;
+  DevBuf<double> d_stage;               // staging for permuted uploads / downloads (5*nv doubles)
   // bending-tilt coupling: triangle rows + corner CSR on the device (built on first use)
   std::vector<int32_t> h_tri;
   bool bt_ready = false;
@@ -246,6 +253,69 @@ int bt_prepare(ms_ctx* c, ms::BtMesh& m) {
   return 0;
 }
 
+// Asynchronous device -> host copy of a per-vertex array in the CALLER's vertex order.
+int download_rows(ms_ctx* c, const double* src_dev, double* host, int width) {
+  const size_t n = size_t(c->nv) * size_t(width);
+  if (!n) return 0;
+  if (c->perm.empty()) {
+    CU(cudaMemcpyAsync(host, src_dev, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    return 0;
+  }
+  CU(ms::launch_scatter_rows(src_dev, width, c->d_perm.p, c->nv, c->d_stage.p, c->stream));
+  CU(cudaMemcpyAsync(host, c->d_stage.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  return 0;
+}
+
+// Morton (Z-curve) order of the hint positions: contiguous row ranges become compact surface
+// patches, which is what keeps the ring-facet recomputation of the patch kernels small.
+void morton_permutation(const std::vector<double>& pos, int32_t nv, std::vector<int32_t>& perm) {
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  for (int32_t v = 0; v < nv; ++v)
+    for (int k = 0; k < 3; ++k) {
+      const double x = pos[3 * size_t(v) + k];
+      if (x < lo[k]) lo[k] = x;
+      if (x > hi[k]) hi[k] = x;
+    }
+  auto spread = [](uint64_t x) {
+    x &= 0x1FFFFFull;
+    x = (x | (x << 32)) & 0x1F00000000FFFFull;
+    x = (x | (x << 16)) & 0x1F0000FF0000FFull;
+    x = (x | (x << 8)) & 0x100F00F00F00F00Full;
+    x = (x | (x << 4)) & 0x10C30C30C30C30C3ull;
+    x = (x | (x << 2)) & 0x1249249249249249ull;
+    return x;
+  };
+  std::vector<uint64_t> key(size_t(nv), 0);
+  for (int32_t v = 0; v < nv; ++v) {
+    uint64_t q[3];
+    for (int k = 0; k < 3; ++k) {
+      const double span = hi[k] - lo[k];
+      double t = span > 0 ? (pos[3 * size_t(v) + k] - lo[k]) / span * 2097151.0 : 0.0;
+      if (!(t >= 0)) t = 0;  // also catches NaN
+      if (t > 2097151.0) t = 2097151.0;
+      q[k] = uint64_t(t);
+    }
+    key[size_t(v)] = spread(q[0]) | (spread(q[1]) << 1) | (spread(q[2]) << 2);
+  }
+  perm.resize(size_t(nv));
+  std::iota(perm.begin(), perm.end(), 0);
+  std::stable_sort(perm.begin(), perm.end(), [&](int32_t a, int32_t b) { return key[size_t(a)] < key[size_t(b)]; });
+  bool identity = true;
+  for (int32_t i = 0; i < nv && identity; ++i) identity = perm[size_t(i)] == i;
+  if (identity) perm.clear();
+}
+
+template <typename T>
+std::vector<T> permuted(const T* src, const std::vector<int32_t>& perm) {
+  std::vector<T> out(perm.size());
+  for (size_t i = 0; i < perm.size(); ++i) out[i] = src[size_t(perm[i])];
+  return out;
+}
+
+bool per_vertex_array(int which) {
+  return which != MS_ARR_SCALARS;
+}
+
 }  // namespace
 
 extern "C" {
@@ -331,6 +401,20 @@ int ms_ctx_set_groups(ms_ctx* c, int32_t groups_a, int32_t groups_b) {
   return 0;
 }
 
+int ms_ctx_set_vertex_order_hint(ms_ctx* c, int32_t nv, const double* pos) {
+  if (!c) return fail(-1, "null context");
+  c->order_hint.clear();
+  if (pos && nv > 0) c->order_hint.assign(pos, pos + 3 * size_t(nv));
+  return 0;
+}
+
+int ms_ctx_get_permutation(const ms_ctx* c, int32_t* perm_new_to_old) {
+  if (!c || !perm_new_to_old) return fail(-1, "null argument");
+  if (!c->have_topology) return fail(-2, "ms_ctx_set_topology has not been called");
+  for (int32_t i = 0; i < c->nv; ++i) perm_new_to_old[i] = c->perm.empty() ? i : c->perm[size_t(i)];
+  return 0;
+}
+
 int ms_ctx_set_topology(ms_ctx* c, int32_t nv, int32_t nf, const int32_t* tri,
                         const uint8_t* is_boundary, const uint8_t* body_mask,
                         const uint8_t* fixed_mask) {
@@ -345,6 +429,27 @@ int ms_ctx_set_topology_partition(ms_ctx* c, int32_t nv, int32_t n_owned, int32_
     return fail(-1, "bad topology arguments");
   c->have_topology = false;
   c->n_owned = n_owned;
+  // internal vertex order from the hint (single-context meshes only; partitions arrive ordered)
+  c->perm.clear();
+  if (c->order_hint.size() == 3 * size_t(nv) && n_owned == nv && nv > 1)
+    morton_permutation(c->order_hint, nv, c->perm);
+  c->order_hint.clear();
+  c->order_hint.shrink_to_fit();
+  std::vector<int32_t> tri_internal;
+  std::vector<uint8_t> boundary_internal, fixed_internal;
+  if (!c->perm.empty()) {
+    std::vector<int32_t> inv(size_t(nv), 0);
+    for (int32_t i = 0; i < nv; ++i) inv[size_t(c->perm[size_t(i)])] = i;
+    tri_internal.assign(tri, tri + 3 * size_t(nf));
+    for (auto& x : tri_internal)
+      if (x >= 0 && x < nv) x = inv[size_t(x)];  // out-of-range indices stay out of range (facet skipped)
+    tri = tri_internal.data();
+    if (is_boundary) { boundary_internal = permuted(is_boundary, c->perm); is_boundary = boundary_internal.data(); }
+    if (fixed_mask) { fixed_internal = permuted(fixed_mask, c->perm); fixed_mask = fixed_internal.data(); }
+    if (int rc = c->d_perm.ensure(size_t(nv))) return rc;
+    CU(cudaMemcpy(c->d_perm.p, c->perm.data(), size_t(nv) * sizeof(int32_t), cudaMemcpyHostToDevice));
+    if (int rc = c->d_stage.ensure(size_t(ms::kSeedStride) * size_t(nv))) return rc;
+  }
   const int prc = ms::pack_patches(nv, nf, tri, body_mask, c->pack_params, c->packed, n_owned);
   if (prc == -2) return fail(-8, "a vertex neighbourhood exceeds max_local; raise it with ms_ctx_set_pack_params");
   if (prc == -3) return fail(-8, "a vertex neighbourhood needs more record slots than a patch can hold");
@@ -499,11 +604,14 @@ int ms_ctx_set_bending_params(ms_ctx* c, const double* kappa, const double* c0, 
   c->has_kappa = kappa != nullptr;
   c->has_c0 = c0 != nullptr;
   const size_t nv = size_t(c->nv);
+  std::vector<double> tmp;
   if (kappa) {
+    if (!c->perm.empty()) { tmp = permuted(kappa, c->perm); kappa = tmp.data(); }
     if (int rc = c->d_kappa.ensure(nv)) return rc;
     if (nv) CU(cudaMemcpy(c->d_kappa.p, kappa, nv * sizeof(double), cudaMemcpyHostToDevice));
   }
   if (c0) {
+    if (!c->perm.empty()) { tmp = permuted(c0, c->perm); c0 = tmp.data(); }
     if (int rc = c->d_c0.ensure(nv)) return rc;
     if (nv) CU(cudaMemcpy(c->d_c0.p, c0, nv * sizeof(double), cudaMemcpyHostToDevice));
   }
@@ -524,6 +632,13 @@ int ms_ctx_upload(ms_ctx* c, int which, const double* host, int64_t offset, int6
   double* d = array_ptr(c, which, &len);
   if (!d && len > 0) return fail(-1, "array is not allocated");
   if (offset < 0 || count < 0 || offset + count > len) return fail(-1, "upload range out of bounds");
+  if (!c->perm.empty() && per_vertex_array(which) && count) {
+    // the caller's rows are in its own vertex order: land in the staging buffer, gather into internal order
+    if (offset != 0 || count != len) return fail(-1, "partial uploads are not available on an internally reordered mesh");
+    CU(cudaMemcpyAsync(c->d_stage.p, host, size_t(count) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(ms::launch_gather_rows(c->d_stage.p, int(len / c->nv), c->d_perm.p, c->nv, d, c->stream));
+    return 0;
+  }
   if (count) CU(cudaMemcpyAsync(d + offset, host, size_t(count) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   return 0;
 }
@@ -535,7 +650,12 @@ int ms_ctx_get_array(ms_ctx* c, int which, double* host, int64_t offset, int64_t
   double* d = array_ptr(c, which, &len);
   if (!d && len > 0) return fail(-1, "array has not been produced yet");
   if (offset < 0 || count < 0 || offset + count > len) return fail(-1, "download range out of bounds");
-  if (count) CU(cudaMemcpyAsync(host, d + offset, size_t(count) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (!c->perm.empty() && per_vertex_array(which) && count) {
+    if (offset != 0 || count != len) return fail(-1, "partial downloads are not available on an internally reordered mesh");
+    if (int rc = download_rows(c, d, host, int(len / c->nv))) return rc;
+  } else if (count) {
+    CU(cudaMemcpyAsync(host, d + offset, size_t(count) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  }
   CU(cudaStreamSynchronize(c->stream));
   return 0;
 }
@@ -673,13 +793,12 @@ int ms_ctx_eval_host(ms_ctx* c, const ms_eval_opts* o, const double* pos_host, d
   if (pos_host)
     if (int rc = ms_ctx_upload(c, o->use_trial ? MS_ARR_TRIAL : MS_ARR_POSITIONS, pos_host, 0, n3)) return rc;
   if (int rc = ms_ctx_eval_async(c, o)) return rc;
-  const size_t bytes = size_t(n3) * sizeof(double);
   if (o->want_grad && grad_host && n3)
-    CU(cudaMemcpyAsync(grad_host, c->d_grad.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (int rc = download_rows(c, c->d_grad.p, grad_host, 3)) return rc;
   if (o->want_grad && volgrad_host && n3 && (o->modules & MS_MOD_VOLUME))
-    CU(cudaMemcpyAsync(volgrad_host, c->d_volgrad.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (int rc = download_rows(c, c->d_volgrad.p, volgrad_host, 3)) return rc;
   if ((o->want_grad || o->want_tilt_grad) && tilt_grad_host && n3 && c->d_tilt_grad.p)
-    CU(cudaMemcpyAsync(tilt_grad_host, c->d_tilt_grad.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (int rc = download_rows(c, c->d_tilt_grad.p, tilt_grad_host, 3)) return rc;
   return ms_ctx_read_scalars(c, scalars16);
 }
 

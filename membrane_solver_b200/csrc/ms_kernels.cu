@@ -588,6 +588,17 @@ __global__ void __launch_bounds__(256) k_gather_rows(const double* __restrict__ 
   out[i] = src[size_t(rows[r]) * width + c];
 }
 
+// out[rows[r], :] = src[r, :]  (inverse of k_gather_rows: internal row order -> caller's order)
+__global__ void __launch_bounds__(256) k_scatter_rows(const double* __restrict__ src, int width,
+                                                      const int32_t* __restrict__ rows, int64_t n,
+                                                      double* out) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n * width) return;
+  const int64_t r = i / width;
+  const int c = int(i - r * width);
+  out[size_t(rows[r]) * width + c] = src[i];
+}
+
 __global__ void __launch_bounds__(256) k_axpy(const double* __restrict__ x,
                                               const double* __restrict__ d, double alpha,
                                               double* out, int64_t n) {
@@ -866,6 +877,13 @@ cudaError_t launch_gather_rows(const double* src, int width, const int32_t* rows
                                double* out, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   k_gather_rows<<<blocks_for(n * width, 256), 256, 0, st>>>(src, width, rows, n, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_scatter_rows(const double* src, int width, const int32_t* rows, int64_t n,
+                                double* out, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  k_scatter_rows<<<blocks_for(n * width, 256), 256, 0, st>>>(src, width, rows, n, out);
   return cudaGetLastError();
 }
 

@@ -98,6 +98,9 @@ cudaError_t launch_project(double* g, const double* gc, const uint8_t* fixed, in
 // out[i*width + c] = src[rows[i]*width + c]: packs the rows a neighbouring partition needs
 cudaError_t launch_gather_rows(const double* src, int width, const int32_t* rows, int64_t n,
                                double* out, cudaStream_t st);
+// out[rows[i]*width + c] = src[i*width + c]: internal vertex order -> caller's order
+cudaError_t launch_scatter_rows(const double* src, int width, const int32_t* rows, int64_t n,
+                                double* out, cudaStream_t st);
 // x_out = x + alpha * d  (trial positions of the line search, line_search.py:358-382)
 cudaError_t launch_axpy(const double* x, const double* d, double alpha, double* out, int64_t n,
                         cudaStream_t st);

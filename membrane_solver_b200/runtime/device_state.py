@@ -114,7 +114,8 @@ class DeviceState:
             self.body_rows = bodies[0][1]
         self.boundary = boundary_mask(mesh, nv)
         self.has_boundary = self.boundary is not None
-        self.dm.set_topology(nv, tri, is_boundary=self.boundary, body_mask=body, fixed_mask=fixed_mask(mesh, nv))
+        self.dm.set_topology(nv, tri, is_boundary=self.boundary, body_mask=body, fixed_mask=fixed_mask(mesh, nv),
+                             order_hint=positions)
         self.key, self.nv, self.nf = key, nv, int(tri.shape[0])
         self._gamma_key = self._bend_key = self._tilt_key = self._k_tilt = None
         self.uploads += 1

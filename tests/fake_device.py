@@ -25,7 +25,8 @@ class FakeDeviceMesh:
         FakeDeviceMesh.instances.append(self)
 
     # -- topology / parameters
-    def set_topology(self, nv, tri, *, is_boundary=None, body_mask=None, fixed_mask=None, n_owned=None):
+    def set_topology(self, nv, tri, *, is_boundary=None, body_mask=None, fixed_mask=None, n_owned=None,
+                     order_hint=None):
         self.nv, self.tri = int(nv), np.ascontiguousarray(tri, dtype=np.int32).reshape(-1, 3)
         self.nf = self.tri.shape[0]
         self.is_boundary, self.body_mask, self.fixed = is_boundary, body_mask, fixed_mask
