@@ -459,3 +459,55 @@ def test_internal_reordering_is_transparent(L):
             assert np.array_equal(perm, np.arange(nv))
         dm.close()
     assert listed[False] < 0.5 * listed[True], listed   # hint: ~1.2 x nf listings instead of ~3 x nf
+
+
+def test_full_size_invariants(L):
+    """BASELINE.json configs[4] at its full single-GPU size (10 M facets), where the oracle is too
+    slow: size-independent properties of the exact gradients.
+      * Euler's theorem: surface energy is homogeneous of degree 2 in x, volume of degree 3, the
+        Helfrich energy with c0 = 0 of degree 0  ->  <g_S, x> = 2 E_S, <dV/dx, x> = 3 V, <g_B, x> = 0;
+      * translation invariance: every gradient sums to zero over the closed surface;
+      * scaling x -> s x and a rigid rotation change the scalars exactly as the degrees predict;
+      * the KKT-projected gradient is orthogonal to dV/dx."""
+    from membrane_solver_b200.synthetic import frequency_for_facets, icosphere
+
+    n = frequency_for_facets(10_000_000)
+    pos, tri = icosphere(n)
+    nv, nf = pos.shape[0], tri.shape[0]
+    assert nf >= 10_000_000
+    dm = _ctx(nv, tri, body_mask=np.ones(nf, np.uint8))
+    dm.set_surface_tension(1.0)
+    dm.set_bending_params(1.0, 0.0)
+    dm.set_positions(pos)
+    x = pos.reshape(-1)
+
+    def run(mods, **kw):
+        r = dm.eval(dm.options(mods, **kw))
+        return r, dm.download(L.ARR_GRAD), dm.download(L.ARR_VOLGRAD)
+
+    rs, gs, gv = run(L.MOD_SURFACE | L.MOD_VOLUME)
+    assert abs(gs.reshape(-1) @ x - 2.0 * rs.e_surface) <= 1e-10 * rs.e_surface
+    assert abs(gv.reshape(-1) @ x - 3.0 * rs.volume) <= 1e-10 * rs.volume
+    assert np.abs(gs.sum(axis=0)).max() <= 1e-9 and np.abs(gv.sum(axis=0)).max() <= 1e-9
+    rb, gb, _ = run(L.MOD_BENDING)
+    gscale = np.abs(gb).max()
+    assert abs(gb.reshape(-1) @ x) <= 1e-9 * rb.e_bending            # scale invariance of the Willmore/Helfrich(c0=0) energy
+    assert np.abs(gb.sum(axis=0)).max() <= 1e-7 * gscale * np.sqrt(nv)
+    # fused evaluation = sum of the parts; projection removes the dV/dx component
+    rf, gf, gvf = run(L.MOD_SURFACE | L.MOD_BENDING | L.MOD_VOLUME)
+    assert rel_err(gf, gs + gb) <= 1e-12 and rel_err(gvf, gv) <= 1e-12  # other instantiation: rounding of (v1 x v2) only
+    rp, gp, _ = run(L.MOD_SURFACE | L.MOD_BENDING | L.MOD_VOLUME, constraint_mode=0)
+    lam = rp.kkt_lambda
+    assert rel_err(gp, gf - lam * gv) <= 1e-12
+    assert abs(gp.reshape(-1) @ gv.reshape(-1)) <= 1e-9 * np.linalg.norm(gp) * np.linalg.norm(gv)
+    # scaling and rotation
+    s = 1.37
+    c, sn = np.cos(0.7), np.sin(0.7)
+    rot = np.array([[c, -sn, 0.0], [sn, c, 0.0], [0.0, 0.0, 1.0]]) @ np.array([[1, 0, 0], [0, c, -sn], [0, sn, c]])
+    dm.set_positions(s * pos @ rot.T)
+    r2, g2, _ = run(L.MOD_SURFACE | L.MOD_BENDING | L.MOD_VOLUME)
+    assert abs(r2.e_surface - s * s * rf.e_surface) <= 1e-11 * r2.e_surface
+    assert abs(r2.volume - s**3 * rf.volume) <= 1e-11 * r2.volume
+    assert abs(r2.e_bending - rf.e_bending) <= 1e-10 * rf.e_bending
+    assert abs(r2.area - s * s * rf.area) <= 1e-11 * r2.area
+    dm.close()
