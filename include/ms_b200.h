@@ -110,8 +110,8 @@ MS_API int ms_ctx_destroy(ms_ctx* ctx);
  * also the compiled shared-memory capacities, so values may only be lowered) */
 MS_API int ms_ctx_set_pack_params(ms_ctx* ctx, int32_t threads, int32_t max_owned, int32_t max_local);
 /* packer tuning for the next ms_ctx_set_topology: target share (percent) of record slots that
- * hold a facet (default 90; lower = more free lanes = fewer shared-memory bank clashes) and
- * the number of lane-placement repair passes (default 0) */
+ * hold a facet (default 87; lower = more free lanes = fewer shared-memory bank clashes) and
+ * the number of lane-placement repair passes (default 1) */
 MS_API int ms_ctx_set_pack_tuning(ms_ctx* ctx, int32_t fill_pct, int32_t repair_sweeps);
 /* kept for ABI stability; the persistent kernels derive the thread-group count from the CTA
  * size (consumer threads / threads-per-round) */

@@ -83,8 +83,8 @@ class DeviceMesh:
         if groups is not None:
             L.check(self._lib.ms_ctx_set_groups(self._h, int(groups[0]), int(groups[1])))
         if fill_pct is not None or repair_sweeps is not None:
-            L.check(self._lib.ms_ctx_set_pack_tuning(self._h, int(90 if fill_pct is None else fill_pct),
-                                                     int(repair_sweeps or 0)))
+            L.check(self._lib.ms_ctx_set_pack_tuning(self._h, int(87 if fill_pct is None else fill_pct),
+                                                     int(1 if repair_sweeps is None else repair_sweeps)))
 
     # -- lifetime -----------------------------------------------------------
     def close(self) -> None:

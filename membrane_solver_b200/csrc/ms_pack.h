@@ -46,8 +46,8 @@ struct PackParams {
   int32_t max_owned = 512;   // owned vertices per patch
   int32_t max_local = 896;   // owned + halo vertices per patch (shared-memory budget)
   int32_t max_slots = 1536;  // record slots per patch (rounds x threads; shared-memory budget)
-  int32_t repair_sweeps = 0; // lane-placement repair passes (0 = greedy only)
-  int32_t fill_pct = 95;     // target share of valid slots: lower = more free lanes = fewer bank clashes
+  int32_t repair_sweeps = 1; // lane-placement repair passes (0 = greedy only)
+  int32_t fill_pct = 87;     // target share of valid slots: lower = more free lanes = fewer bank clashes
 };
 
 struct PackedMesh {
