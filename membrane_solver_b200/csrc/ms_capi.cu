@@ -72,6 +72,8 @@ struct ms_ctx {
   DevBuf<ms::FacetRec> d_recs;
   DevBuf<double> d_slot_gamma;
   DevBuf<uint8_t> d_boundary, d_fixed;
+  DevBuf<int32_t> d_boundary32;  // boundary flags as int32: staged into shared memory with 4-byte cp.async
+  DevBuf<double> d_tilt_sq;      // |t|^2 per vertex, refreshed before every evaluation that uses the tilts
   DevBuf<double> d_kappa, d_c0;
   DevBuf<double> d_pos, d_trial, d_dir, d_tilts, d_seeds, d_partials_a, d_partials_b, d_grad, d_volgrad,
       d_tilt_grad, d_scalars, d_dot_partials, d_kvecs, d_avor, d_aeff, d_evert;
@@ -172,6 +174,8 @@ int fill_launch(ms_ctx* c, const ms_eval_opts* o, ms::PatchLaunch& a) {
   }
   a.tilts = c->d_tilts.p;
   a.is_boundary = c->has_boundary ? c->d_boundary.p : nullptr;
+  a.boundary32 = c->has_boundary ? c->d_boundary32.p : nullptr;
+  a.tilt_sq = nullptr;
   a.kappa = c->has_kappa ? c->d_kappa.p : nullptr;
   a.c0 = c->has_c0 ? c->d_c0.p : nullptr;
   a.gamma_u = c->gamma_u;
@@ -186,6 +190,11 @@ int fill_launch(ms_ctx* c, const ms_eval_opts* o, ms::PatchLaunch& a) {
   a.volgrad = c->d_volgrad.p;
   if ((o->modules & MS_MOD_TILT)) {
     if (!c->d_tilts.p) return fail(-5, "tilt module requested but no tilts were uploaded");
+    // |t|^2 per vertex for the producer's asynchronous staging (the tilts may have been changed through
+    // ms_ctx_device_ptr, so it is refreshed per launch; 32 B per vertex of traffic)
+    if (int rc = c->d_tilt_sq.ensure(size_t(c->nv) + 1)) return rc;
+    CU(ms::launch_row_norm2(c->d_tilts.p, c->nv, c->d_tilt_sq.p, c->stream));
+    a.tilt_sq = c->d_tilt_sq.p;
     if (o->want_grad) {
       if (int rc = ensure_array(c, MS_ARR_TILT_GRAD)) return rc;
       a.tilt_grad = c->d_tilt_grad.p;
@@ -490,6 +499,10 @@ int ms_ctx_set_topology_partition(ms_ctx* c, int32_t nv, int32_t n_owned, int32_
   if (is_boundary) {
     if (int rc = c->d_boundary.ensure(size_t(nv))) return rc;
     if (nv) CU(cudaMemcpy(c->d_boundary.p, is_boundary, size_t(nv), cudaMemcpyHostToDevice));
+    std::vector<int32_t> b32(size_t(nv) + 1, 0);
+    for (int32_t v = 0; v < nv; ++v) b32[size_t(v)] = is_boundary[v] ? 1 : 0;
+    if (int rc = c->d_boundary32.ensure(size_t(nv) + 1)) return rc;
+    CU(cudaMemcpy(c->d_boundary32.p, b32.data(), b32.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   }
   if (fixed_mask) {
     if (int rc = c->d_fixed.ensure(size_t(nv))) return rc;
@@ -514,6 +527,7 @@ int ms_ctx_set_topology_partition(ms_ctx* c, int32_t nv, int32_t n_owned, int32_
   // per-entity parameter arrays belong to the previous topology
   c->has_gamma = c->has_kappa = c->has_c0 = false;
   c->d_tilts.release();
+  c->d_tilt_sq.release();
   c->d_tilt_grad.release();
   c->d_trial.release();
   c->d_dir.release();

@@ -165,10 +165,10 @@ struct Plan {
   static constexpr size_t oRed = oMail + 64;
   static constexpr size_t oOpt = oRed + size_t(kMaxConsumerWarps + 1) * PS_COUNT * 8;
 };
-// optional arrays (after the fixed part): bfl[2][L] u8, t2[2][L] f64, accAb[2][ACap] f64
+// optional arrays (after the fixed part): bfl[2][L] i32, t2[2][L] f64, accAb[2][ACap] f64
 __host__ __device__ inline size_t opt_bytes(bool boundary, bool tilt, bool tilt_acc) {
   size_t n = 0;
-  if (boundary) n += 2 * size_t(kPatchLocalCap);
+  if (boundary) n += 2 * size_t(kPatchLocalCap) * 4;
   if (tilt) n += 2 * size_t(kPatchLocalCap) * 8;
   if (tilt_acc) n += 2 * size_t(kACap) * 8;
   return n;
@@ -195,7 +195,7 @@ constexpr uint32_t kFastModules = MS_MOD_SURFACE | MS_MOD_BENDING | MS_MOD_VOLUM
 
 // Warp roles inside the 512-thread CTA: warps [0, NC/32) are consumers, warp NC/32 runs the
 // patch epilogues, the last warp is the producer.
-template <int PASS, bool FAST, int NC>
+template <int PASS, int KIND, int NC>
 __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bending_b, bool scalars_here_arg) {
   extern __shared__ __align__(128) unsigned char smem[];
   using P = Plan<PASS>;
@@ -208,13 +208,20 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
   const int n_epi_warps = (NC + 32 - n_active) / 32;  // every warp between consumers and producer
   const int n_my = a.patch_count > int(blockIdx.x) ? (a.patch_count - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x) : 0;
 
-  const uint32_t modules = FAST ? kFastModules : a.modules;
+  // KIND 0: everything decided at run time.  KIND 1 (headline): surface + Helfrich bending (analytic) +
+  // volume, closed mesh, uniform parameters.  KIND 2: surface and/or volume only, uniform gamma (boundary
+  // flags are irrelevant without bending).
+  constexpr bool FAST = KIND == 1 || KIND == 2;  // KIND 3: run-time parameters but no tilt module
+  const uint32_t modules = KIND == 1 ? kFastModules
+                           : KIND == 2 ? (a.modules & (MS_MOD_SURFACE | MS_MOD_VOLUME)) : a.modules;
   const uint32_t flags = FAST ? 0u : a.flags;
-  const bool do_tilt = !FAST && (modules & MS_MOD_TILT) && a.tilts != nullptr;
+  const bool do_tilt = KIND == 0 && (modules & MS_MOD_TILT) && a.tilts != nullptr;
   const bool has_boundary = !FAST && a.is_boundary != nullptr;
-  const bool do_bending = FAST ? true : (PASS == 0 ? (modules & (MS_MOD_BENDING | MS_MOD_BENDING_TILT)) != 0 : bending_b);
-  const bool do_volume = FAST ? true : (modules & MS_MOD_VOLUME) != 0;
-  const bool scalars_here = FAST ? false : scalars_here_arg;
+  const bool do_bending = (KIND == 1 || KIND == 3) ? true
+                          : KIND == 2 ? false
+                          : (PASS == 0 ? (modules & (MS_MOD_BENDING | MS_MOD_BENDING_TILT)) != 0 : bending_b);
+  const bool do_volume = KIND == 1 ? true : (modules & MS_MOD_VOLUME) != 0;
+  const bool scalars_here = (KIND == 1 || KIND == 3) ? false : scalars_here_arg;
   const bool want_epi = PASS == 1 || do_bending;  // pass A without bending accumulates nothing
 
   // mbarriers: full[2] producer -> all; empty[2] consumers (+ epilogue in pass A) -> producer;
@@ -226,10 +233,10 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
   uint64_t* bar_free = bars + 6;
   double* red = reinterpret_cast<double*>(smem + P::oRed);
   unsigned char* opt = smem + P::oOpt;
-  uint8_t* bfl_base = nullptr;
+  int32_t* bfl_base = nullptr;
   double* t2_base = nullptr;
   double* ab_base = nullptr;
-  if (has_boundary) { bfl_base = opt; opt += 2 * size_t(kPatchLocalCap); }
+  if (has_boundary) { bfl_base = reinterpret_cast<int32_t*>(opt); opt += 2 * size_t(kPatchLocalCap) * 4; }
   if (do_tilt) { t2_base = reinterpret_cast<double*>(opt); opt += 2 * size_t(kPatchLocalCap) * 8; }
   if (do_tilt && PASS == 1) { ab_base = reinterpret_cast<double*>(opt); }
 
@@ -305,15 +312,17 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
           for (int c = 0; c < kSeedStride; ++c) cp_async8(seed + c * kPatchLocalCap + i, srow + c);
         }
       }
-      if (has_boundary || do_tilt) {
-        const int L = Pn + h.n_halo;
-        for (int i = lane; i < L; i += 32) {
-          const size_t row = size_t(i < Pn ? h.v_lo + i : ids[i - Pn]);
-          if (has_boundary) bfl_base[size_t(b) * kPatchLocalCap + i] = a.is_boundary[row];
-          if (do_tilt) {
-            const double x = a.tilts[3 * row], y = a.tilts[3 * row + 1], z = a.tilts[3 * row + 2];
-            t2_base[size_t(b) * kPatchLocalCap + i] = x * x + y * y + z * z;
-          }
+      if (has_boundary || do_tilt) {  // flags (int32) and |t|^2 ride the same asynchronous copies
+        int32_t* bf = has_boundary ? bfl_base + size_t(b) * kPatchLocalCap : nullptr;
+        double* t2 = do_tilt ? t2_base + size_t(b) * kPatchLocalCap : nullptr;
+        for (int i = lane; i < Pn; i += 32) {
+          if (bf) cp_async4(bf + i, a.boundary32 + h.v_lo + i);
+          if (t2) cp_async8(t2 + i, a.tilt_sq + h.v_lo + i);
+        }
+        for (int k = lane; k < h.n_halo; k += 32) {
+          const size_t row = size_t(ids[k]);
+          if (bf) cp_async4(bf + Pn + k, a.boundary32 + row);
+          if (t2) cp_async8(t2 + Pn + k, a.tilt_sq + row);
         }
       }
       cp_async_wait_all();
@@ -787,6 +796,13 @@ __global__ void k_bt_finalize(const double* e_bt, double* scalars) {
   scalars[SC_E_BENDING] = 0.0;
 }
 
+__global__ void __launch_bounds__(256) k_row_norm2(const double* __restrict__ rows, int64_t n, double* out) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x = rows[3 * i], y = rows[3 * i + 1], z = rows[3 * i + 2];
+  out[i] = x * x + y * y + z * z;
+}
+
 inline int blocks_for(int64_t n, int t) { return int((n + t - 1) / t); }
 
 }  // namespace
@@ -794,16 +810,26 @@ inline int blocks_for(int64_t n, int t) { return int((n + t - 1) / t); }
 namespace {
 int g_num_sms = 0;
 
+// compile-time kernel kind of a launch (see k_patch)
+int kernel_kind(const PatchLaunch& a) {
+  const bool diag = a.k_vecs || a.a_vor || a.a_eff || a.e_vertex;
+  if (a.modules == kFastModules && a.flags == 0 && !a.is_boundary && !a.slot_gamma && !a.kappa && !a.c0 && !diag &&
+      a.seeds && a.volgrad)
+    return 1;
+  if ((a.modules & ~uint32_t(MS_MOD_SURFACE | MS_MOD_VOLUME)) == 0 && a.modules != 0 && !a.slot_gamma && !diag &&
+      a.volgrad)
+    return 2;
+  if (!(a.modules & MS_MOD_TILT) && (a.modules & MS_MOD_BENDING) && a.seeds) return 3;  // run-time parameters, no tilt
+  return 0;
+}
+
 template <int PASS>
 size_t patch_smem_bytes(const PatchLaunch& a) {
+  if (kernel_kind(a) == 1 || kernel_kind(a) == 2) return Plan<PASS>::oOpt;
   const bool tilt = (a.modules & MS_MOD_TILT) && a.tilts;
   return Plan<PASS>::oOpt + opt_bytes(a.is_boundary != nullptr, tilt, tilt && PASS == 1);
 }
 
-bool fast_config(const PatchLaunch& a) {
-  return a.modules == kFastModules && a.flags == 0 && !a.is_boundary && !a.slot_gamma && !a.kappa && !a.c0 &&
-         !a.k_vecs && !a.a_vor && !a.a_eff && !a.e_vertex && a.seeds && a.volgrad;
-}
 }  // namespace
 
 size_t pass_a_smem_bytes(const PatchLaunch& a) { return patch_smem_bytes<0>(a); }
@@ -816,8 +842,10 @@ cudaError_t configure_kernels() {
   e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   if (e != cudaSuccess) return e;
   const int max_dyn = 227 * 1024;
-  const void* fns[] = {(const void*)k_patch<0, false, kConsumerThreads>, (const void*)k_patch<0, true, kConsumerThreads>,
-                       (const void*)k_patch<1, false, kConsumerThreads>, (const void*)k_patch<1, true, kConsumerThreads>};
+  const void* fns[] = {(const void*)k_patch<0, 0, kConsumerThreads>, (const void*)k_patch<0, 1, kConsumerThreads>,
+                       (const void*)k_patch<0, 2, kConsumerThreads>, (const void*)k_patch<1, 0, kConsumerThreads>,
+                       (const void*)k_patch<1, 1, kConsumerThreads>, (const void*)k_patch<1, 2, kConsumerThreads>,
+                       (const void*)k_patch<0, 3, kConsumerThreads>, (const void*)k_patch<1, 3, kConsumerThreads>};
   for (const void* f : fns) {
     e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
     if (e != cudaSuccess) return e;
@@ -834,10 +862,12 @@ cudaError_t launch_pass_a(const PatchLaunch& a, cudaStream_t st) {
   if (a.patch_count <= 0) return cudaSuccess;
   const size_t smem = patch_smem_bytes<0>(a);
   const int grid = patch_grid(a);
-  if (fast_config(a))
-    k_patch<0, true, kConsumerThreads><<<grid, kConsumerThreads + 64, smem, st>>>(a, true, false);
-  else
-    k_patch<0, false, kConsumerThreads><<<grid, kConsumerThreads + 64, smem, st>>>(a, false, false);
+  switch (kernel_kind(a)) {
+    case 1: k_patch<0, 1, kConsumerThreads><<<grid, kConsumerThreads + 64, smem, st>>>(a, true, false); break;
+    case 2: k_patch<0, 2, kConsumerThreads><<<grid, kConsumerThreads + 64, smem, st>>>(a, false, false); break;
+    case 3: k_patch<0, 3, kConsumerThreads><<<grid, kConsumerThreads + 64, smem, st>>>(a, false, false); break;
+    default: k_patch<0, 0, kConsumerThreads><<<grid, kConsumerThreads + 64, smem, st>>>(a, false, false);
+  }
   return cudaGetLastError();
 }
 
@@ -845,10 +875,15 @@ cudaError_t launch_pass_b(const PatchLaunch& a, bool bending, bool scalars_here,
   if (a.patch_count <= 0) return cudaSuccess;
   const size_t smem = patch_smem_bytes<1>(a);
   const int grid = patch_grid(a);
-  if (fast_config(a) && bending && !scalars_here)
-    k_patch<1, true, kConsumerThreads><<<grid, kConsumerThreads + 64, smem, st>>>(a, true, false);
+  const int kind = kernel_kind(a);
+  if (kind == 1 && bending && !scalars_here)
+    k_patch<1, 1, kConsumerThreads><<<grid, kConsumerThreads + 64, smem, st>>>(a, true, false);
+  else if (kind == 2 && !bending)
+    k_patch<1, 2, kConsumerThreads><<<grid, kConsumerThreads + 64, smem, st>>>(a, false, scalars_here);
+  else if (kind == 3 && bending && !scalars_here)
+    k_patch<1, 3, kConsumerThreads><<<grid, kConsumerThreads + 64, smem, st>>>(a, bending, scalars_here);
   else
-    k_patch<1, false, kConsumerThreads><<<grid, kConsumerThreads + 64, smem, st>>>(a, bending, scalars_here);
+    k_patch<1, 0, kConsumerThreads><<<grid, kConsumerThreads + 64, smem, st>>>(a, bending, scalars_here);
   return cudaGetLastError();
 }
 
@@ -943,6 +978,11 @@ cudaError_t launch_grad_cotan(int32_t n, const double* u, const double* v, doubl
 cudaError_t launch_p1_divergence(const SoupArgs& s, const double* tilts, double* div, double* area,
                                  double* g0, double* g1, double* g2, cudaStream_t st) {
   if (s.nf > 0) k_p1_divergence<<<blocks_for(s.nf, 128), 128, 0, st>>>(s, tilts, div, area, g0, g1, g2);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_row_norm2(const double* rows, int64_t n, double* out, cudaStream_t st) {
+  if (n > 0) k_row_norm2<<<blocks_for(n, 256), 256, 0, st>>>(rows, n, out);
   return cudaGetLastError();
 }
 

@@ -56,6 +56,8 @@ struct PatchLaunch {
   const double* pos;          // (nv,3)
   const double* tilts;        // (nv,3) or nullptr
   const uint8_t* is_boundary; // nv or nullptr
+  const int32_t* boundary32;  // the same flags as int32 (cp.async staging), nullptr with is_boundary
+  const double* tilt_sq;      // nv: |t|^2 per vertex (tilt magnitude module), nullptr without tilts
   const double* kappa;        // nv or nullptr -> kappa_u
   const double* c0;           // nv or nullptr -> c0_u
   double gamma_u, kappa_u, c0_u, k_tilt;
@@ -130,6 +132,8 @@ cudaError_t launch_grad_cotan(int32_t n, const double* u, const double* v, doubl
 cudaError_t launch_p1_divergence(const SoupArgs& s, const double* tilts, double* div, double* area,
                                  double* g0, double* g1, double* g2, cudaStream_t st);
 cudaError_t launch_sum(const double* x, int64_t n, double scale, double* out, cudaStream_t st);
+// out[v] = |rows[v,:]|^2 of an (n,3) array (tilt magnitude staging)
+cudaError_t launch_row_norm2(const double* rows, int64_t n, double* out, cudaStream_t st);
 
 // --- bending-tilt coupling on the resident mesh (ms_bt.cuh); corner holds 12*nf doubles ---
 // stage: divergence / effective areas -> vertex seeds (into `seeds`, read by pass B) and base term ->

@@ -239,7 +239,8 @@ MS_HD CornerG facet_pass_b(const FacetGeom& g, double gamma_eff, double area_coe
     // term 3: chi_k = (interior ? fA_eff : mean over interior corners) + fA_vor
     const int ni = int(b.i0) + int(b.i1) + int(b.i2);
     const double sum_i = (b.i0 ? b.fe0 : 0.0) + (b.i1 ? b.fe1 : 0.0) + (b.i2 ? b.fe2 : 0.0);
-    const double mean_i = ni > 0 ? sum_i / double(ni) : 0.0;
+    // ni is 0..3: select the reciprocal instead of dividing (a double division is ~20 instructions)
+    const double mean_i = ni == 3 ? sum_i * (1.0 / 3.0) : (ni == 2 ? sum_i * 0.5 : (ni == 1 ? sum_i : 0.0));
     const double x0 = (b.i0 ? b.fe0 : mean_i) + b.fv0;
     const double x1 = (b.i1 ? b.fe1 : mean_i) + b.fv1;
     const double x2 = (b.i2 ? b.fe2 : mean_i) + b.fv2;

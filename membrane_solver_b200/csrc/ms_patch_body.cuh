@@ -60,7 +60,7 @@ MS_HD int acc_row(int local, int P, int A) { return local < P ? local : (A - kDu
 
 struct LocalA {
   const double* pos;   // 3 x L
-  const uint8_t* bfl;  // L  boundary flags; nullptr = closed mesh (no boundary vertex)
+  const int32_t* bfl;  // L  boundary flags; nullptr = closed mesh (no boundary vertex)
   const double* t2;    // L  |tilt|^2 (tilt module only)
   double* acc;         // 5 x A: K.x K.y K.z A_vor A_eff
   int P;               // owned vertices; local indices >= P are halo (read-only)
@@ -155,7 +155,7 @@ MS_HD VertexSeed vertex_body_a(const S& st, int i, const LocalA& s, bool boundar
 struct LocalB {
   const double* pos;   // 3 x L
   const double* seed;  // 5 x L   bending only: fK.x fK.y fK.z fA_eff fA_vor
-  const uint8_t* bfl;  // L       bending only; nullptr = closed mesh
+  const int32_t* bfl;  // L       bending only; nullptr = closed mesh
   const double* t2;    // L       tilt only
   double* acc;         // 6 x A: shape gradient (3), dV/dx (3)
   double* accAb;       // A       barycentric vertex area (tilt gradient)

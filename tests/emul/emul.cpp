@@ -75,7 +75,7 @@ int emul_eval(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* is_boun
       const int n_slots = h.n_rounds * T;
       const FacetRec* recs = pk.recs.data() + size_t(h.slot_off);
       std::vector<double> lpos(3 * size_t(L)), t2(size_t(L), 0.0), acc(5 * size_t(st.A), 0.0);
-      std::vector<uint8_t> bfl(size_t(L), 0);
+      std::vector<int32_t> bfl(size_t(L), 0);
       for (int j = 0; j < L; ++j) {
         const int row = local_row(pk, h, j);
         for (int k = 0; k < 3; ++k) lpos[size_t(k) * L + j] = pos[3 * size_t(row) + k];
@@ -146,7 +146,7 @@ int emul_eval(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* is_boun
       const FacetRec* recs = pk.recs.data() + size_t(h.slot_off);
       std::vector<double> lpos(3 * size_t(L)), lseed(size_t(kSeedStrideBody) * size_t(L), 0.0),
           t2(size_t(L), 0.0), acc(6 * size_t(st.A), 0.0), accAb(size_t(st.A), 0.0);
-      std::vector<uint8_t> bfl(size_t(L), 0);
+      std::vector<int32_t> bfl(size_t(L), 0);
       for (int j = 0; j < L; ++j) {
         const int row = local_row(pk, h, j);
         for (int k = 0; k < 3; ++k) lpos[size_t(k) * L + j] = pos[3 * size_t(row) + k];
