@@ -390,7 +390,8 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
           sums[PS_G_G] += gx * gx + gy * gy + gz * gz;
           acc[i] = 0.0; acc[kACap + i] = 0.0; acc[2 * kACap + i] = 0.0;
           if (do_volume && a.volgrad) {
-            const double vx = acc[3 * kACap + i], vy = acc[4 * kACap + i], vz = acc[5 * kACap + i];
+            const double sixth = 1.0 / 6.0;  // the facets accumulated 6 dV/dx
+            const double vx = sixth * acc[3 * kACap + i], vy = sixth * acc[4 * kACap + i], vz = sixth * acc[5 * kACap + i];
             double* vo = a.volgrad + 3 * row;
             vo[0] = vx; vo[1] = vy; vo[2] = vz;
             sums[PS_G_GC] += gx * vx + gy * vy + gz * vz;

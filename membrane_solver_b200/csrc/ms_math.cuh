@@ -95,13 +95,14 @@ struct CornerA {
   double c0, c1, c2;    // cotangents
 };
 
-MS_HD void mixed_voronoi(double l0, double l1, double l2, double c0, double c1, double c2,
+// h_k = c_k / 2 are the HALF cotangents (they save the 1/2 of every cotan-weight formula).
+MS_HD void mixed_voronoi(double l0, double l1, double l2, double h0, double h1, double h2,
                          double T, double& va0, double& va1, double& va2) {
-  const bool o0 = c0 < 0.0, o1 = c1 < 0.0, o2 = c2 < 0.0;
+  const bool o0 = h0 < 0.0, o1 = h1 < 0.0, o2 = h2 < 0.0;
   if (!(o0 || o1 || o2)) {
-    va0 = (l1 * c1 + l2 * c2) * 0.125;
-    va1 = (l2 * c2 + l0 * c0) * 0.125;
-    va2 = (l0 * c0 + l1 * c1) * 0.125;
+    va0 = (l1 * h1 + l2 * h2) * 0.25;
+    va1 = (l2 * h2 + l0 * h0) * 0.25;
+    va2 = (l0 * h0 + l1 * h1) * 0.25;
   } else {
     // own-angle T/2, then ANY other obtuse corner overrides with T/4 (curvature.py:308-315)
     va0 = (o1 || o2) ? 0.25 * T : (o0 ? 0.5 * T : 0.0);
@@ -118,20 +119,22 @@ MS_HD CornerA facet_pass_a(const FacetGeom& g, bool b0, bool b1, bool b2) {
   // e0 = -(e1 + e2): every edge product follows from l1 = e1.e1, l2 = e2.e2, C0 = -e1.e2
   const double l1 = dot(g.e1, g.e1), l2 = dot(g.e2, g.e2), C0 = -dot(g.e1, g.e2);
   const double C1 = l2 - C0, C2 = l1 - C0, l0 = (l1 + l2) - 2.0 * C0;
-  r.c0 = C0 * invD;
-  r.c1 = C1 * invD;
-  r.c2 = C2 * invD;
+  const double hD = 0.5 * invD;
+  const double h0 = C0 * hD, h1 = C1 * hD, h2 = C2 * hD;  // half cotangents
+  r.c0 = 2.0 * h0;  // cotangents: only the stateless curvature kernel stores them
+  r.c1 = 2.0 * h1;
+  r.c2 = 2.0 * h2;
   // K[i0] += 1/2 (c1 (-e1) + c2 e2), cyclic; the three contributions sum to zero
-  r.K0 = 0.5 * (r.c2 * g.e2 - r.c1 * g.e1);
-  r.K1 = -0.5 * (r.c0 * g.e1 + (r.c0 + r.c2) * g.e2);
+  r.K0 = h2 * g.e2 - h1 * g.e1;
+  r.K1 = -(h0 * g.e1 + (h0 + h2) * g.e2);
   r.K2 = -(r.K0 + r.K1);
-  mixed_voronoi(l0, l1, l2, r.c0, r.c1, r.c2, 0.5 * D, r.va0, r.va1, r.va2);
+  mixed_voronoi(l0, l1, l2, h0, h1, h2, 0.5 * D, r.va0, r.va1, r.va2);
   // bending_utils.py:101-102 clamps the AREA (not twice the area) for A_eff
   const double Te = fmax(0.5 * g.S, kAreaClamp);
   if (Te == 0.5 * D) {
     r.ve0 = r.va0; r.ve1 = r.va1; r.ve2 = r.va2;
   } else {
-    mixed_voronoi(l0, l1, l2, r.c0, r.c1, r.c2, Te, r.ve0, r.ve1, r.ve2);
+    mixed_voronoi(l0, l1, l2, h0, h1, h2, Te, r.ve0, r.ve1, r.ve2);
   }
   const int nb = int(b0) + int(b1) + int(b2);
   if (nb == 1 || nb == 2) {
@@ -221,21 +224,21 @@ MS_HD CornerG facet_pass_b(const FacetGeom& g, double gamma_eff, double area_coe
   // e1, e2 and the seed differences u = fK1 - fK0, w = fK2 - fK0.
   //   q_0 = -C1 e1 + C2 e2,  q_1 = -C0 e1 - l1 e2,  q_2 = l2 e1 + C0 e2   (a x (b x c) rule)
   // and, the energy being translation invariant, g2 = -(g0 + g1).
-  const double invD = inv_clamped_area2(g);
+  const double hD = 0.5 * inv_clamped_area2(g);
   const double l1 = dot(g.e1, g.e1), l2 = dot(g.e2, g.e2), C0 = -dot(g.e1, g.e2);
   const double C1 = l2 - C0, C2 = l1 - C0;
-  const double c0 = C0 * invD, c1 = C1 * invD, c2 = C2 * invD;
+  const double h0 = C0 * hD, h1 = C1 * hD, h2 = C2 * hD;  // half cotangents c_k / 2
   const d3 u = b.f1 - b.f0, w = b.f2 - b.f0;
   // term 1: g -= L fK  (bending_math.py:111-118): g0 = 1/2 (c1 d20 - c2 d01), d20 = w, d01 = -u
-  const double P0 = 0.5 * c2, Q0 = 0.5 * c1;
-  const double P1 = -0.5 * (c0 + c2), Q1 = 0.5 * c0;
+  const double P0 = h2, Q0 = h1;
+  const double P1 = -(h0 + h2), Q1 = h0;
   double A0 = 0.0, B0 = 0.0, A1 = 0.0, B1 = 0.0;  // coefficients of e1, e2 for corners 0 and 1
   if (!approx) {
-    // term 2 weights: dE/dc_k = -1/2 (fK_i - fK_j).(v_i - v_j)
+    // term 2 weights: dE/dc_k = -1/2 (fK_i - fK_j).(v_i - v_j); t_k = 2 a_k carries the factor
     const double ue1 = dot(u, g.e1), ue2 = dot(u, g.e2), we1 = dot(w, g.e1), we2 = dot(w, g.e2);
-    double a0 = -0.5 * ((ue1 + ue2) - (we1 + we2));  // 1/2 (f1 - f2).e0
-    double a1 = 0.5 * we1;                           // 1/2 (f2 - f0).e1
-    double a2 = -0.5 * ue2;                          // 1/2 (f0 - f1).e2
+    double t0 = (we1 + we2) - (ue1 + ue2);  // (f1 - f2).e0
+    double t1 = we1;                        // (f2 - f0).e1
+    double t2 = -ue2;                       // (f0 - f1).e2
     // term 3: chi_k = (interior ? fA_eff : mean over interior corners) + fA_vor
     const int ni = int(b.i0) + int(b.i1) + int(b.i2);
     const double sum_i = (b.i0 ? b.fe0 : 0.0) + (b.i1 ? b.fe1 : 0.0) + (b.i2 ? b.fe2 : 0.0);
@@ -244,16 +247,17 @@ MS_HD CornerG facet_pass_b(const FacetGeom& g, double gamma_eff, double area_coe
     const double x0 = (b.i0 ? b.fe0 : mean_i) + b.fv0;
     const double x1 = (b.i1 ? b.fe1 : mean_i) + b.fv1;
     const double x2 = (b.i2 ? b.fe2 : mean_i) + b.fv2;
-    const bool o0 = c0 < 0.0, o1 = c1 < 0.0, o2 = c2 < 0.0;
-    double m0 = 0.0, m1 = 0.0, m2 = 0.0;
+    const bool o0 = h0 < 0.0, o1 = h1 < 0.0, o2 = h2 < 0.0;
+    double n0 = 0.0, n1 = 0.0, n2 = 0.0;  // n_k = 2 m_k,  m_k = 1/4 c_k (chi_a + chi_b)
     if (!(o0 || o1 || o2)) {
       const double l0 = (l1 + l2) - 2.0 * C0;
-      a0 += 0.125 * l0 * (x1 + x2);
-      a1 += 0.125 * l1 * (x0 + x2);
-      a2 += 0.125 * l2 * (x0 + x1);
-      m0 = 0.25 * c0 * (x1 + x2);
-      m1 = 0.25 * c1 * (x0 + x2);
-      m2 = 0.25 * c2 * (x0 + x1);
+      const double s12 = x1 + x2, s02 = x0 + x2, s01 = x0 + x1;
+      t0 += 0.25 * l0 * s12;   // a_k += 1/8 l_k (chi_a + chi_b)
+      t1 += 0.25 * l1 * s02;
+      t2 += 0.25 * l2 * s01;
+      n0 = h0 * s12;
+      n1 = h1 * s02;
+      n2 = h2 * s01;
     } else {
       // each obtuse corner k adds (1/2 chi_k + 1/4 chi_a + 1/4 chi_b) dT/dx
       double phi = 0.0;
@@ -263,17 +267,17 @@ MS_HD CornerG facet_pass_b(const FacetGeom& g, double gamma_eff, double area_coe
       Bq -= 0.5 * phi * invS;
     }
     // grad cot_k = 0 when S <= 1e-15 (invS == 0 then)
-    const double invS3 = invS * invS * invS;
-    Bq += (a0 * C0 + a1 * C1 + a2 * C2) * invS3;
-    const double aa0 = a0 * invS, aa1 = a1 * invS, aa2 = a2 * invS;
+    const double invSh = 0.5 * invS;
+    Bq += (t0 * C0 + t1 * C1 + t2 * C2) * (invSh * invS * invS);
+    const double aa0 = t0 * invSh, aa1 = t1 * invSh, aa2 = t2 * invSh;  // a_k / S
     // coefficients of (e0, e1, e2) per corner:  corner 0: (aa1-aa2, aa0+m1, -aa0-m2)
     //                                           corner 1: (-aa1-m0, aa2-aa0, aa1+m2)
     // folded onto (e1, e2) with e0 = -(e1 + e2)
-    const double k00 = aa1 - aa2, k10 = -aa1 - m0;
-    A0 = (aa0 + m1) - k00;
-    B0 = (-aa0 - m2) - k00;
+    const double k00 = aa1 - aa2, k10 = -(aa1 + 0.5 * n0);
+    A0 = (aa0 + 0.5 * n1) - k00;
+    B0 = -(aa0 + 0.5 * n2) - k00;
     A1 = (aa2 - aa0) - k10;
-    B1 = (aa1 + m2) - k10;
+    B1 = (aa1 + 0.5 * n2) - k10;
   }
   A0 -= Bq * C1; B0 += Bq * C2;
   A1 -= Bq * C0; B1 -= Bq * l1;
@@ -292,6 +296,15 @@ MS_HD CornerG facet_volume_grad(d3 v0, d3 v1, d3 v2) {
   r.g0 = s * cross(v1, v2);
   r.g1 = s * cross(v2, v0);
   r.g2 = s * cross(v0, v1);
+  return r;
+}
+
+// Patch path: six times dV/dx per corner; the 1/6 is applied once per vertex in the epilogue.
+MS_HD CornerG facet_volume_grad6(d3 v0, d3 v1, d3 v2) {
+  CornerG r;
+  r.g0 = cross(v1, v2);
+  r.g1 = cross(v2, v0);
+  r.g2 = cross(v0, v1);
   return r;
 }
 

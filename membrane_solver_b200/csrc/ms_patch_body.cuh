@@ -157,7 +157,7 @@ struct LocalB {
   const double* seed;  // 5 x L   bending only: fK.x fK.y fK.z fA_eff fA_vor
   const int32_t* bfl;  // L       bending only; nullptr = closed mesh
   const double* t2;    // L       tilt only
-  double* acc;         // 6 x A: shape gradient (3), dV/dx (3)
+  double* acc;         // 6 x A: shape gradient (3), 6 dV/dx (3)
   double* accAb;       // A       barycentric vertex area (tilt gradient)
   int P;
 };
@@ -165,7 +165,7 @@ struct LocalB {
 // Results of one facet in pass B, held in registers between compute and accumulation.
 struct FacetOutB {
   CornerG cg;     // shape gradient contributions
-  CornerG vg;     // dV/dx contributions (valid when in_body)
+  CornerG vg;     // 6 dV/dx contributions (valid when in_body)
   double third;   // T/3 for the barycentric area (tilt), 0 when the facet is skipped
   bool in_body;
 };
@@ -211,7 +211,7 @@ MS_HD FacetOutB facet_compute_b(const S& st, FacetRec rec, double gam, const Loc
     b.i0 = b.i1 = b.i2 = true;
   }
   o.cg = facet_pass_b<BENDING>(g, gam, coeff, b, (flags & MS_FLAG_APPROX) != 0);
-  if (o.in_body) o.vg = facet_volume_grad(v0, v1, v2);
+  if (o.in_body) o.vg = facet_volume_grad6(v0, v1, v2);  // unscaled: the epilogue multiplies by 1/6
   return o;
 }
 

@@ -176,7 +176,7 @@ int emul_eval(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* is_boun
         for (int k = 0; k < 3; ++k) {
           const size_t o = (size_t(h.v_lo) + i) * 3 + size_t(k);
           if (grad) grad[o] = acc[size_t(k) * st.A + i];
-          if (volgrad && do_volume) volgrad[o] = acc[size_t(3 + k) * st.A + i];
+          if (volgrad && do_volume) volgrad[o] = (1.0 / 6.0) * acc[size_t(3 + k) * st.A + i];
           if (tilt_grad && do_tilt) tilt_grad[o] = k_tilt * tilts[o] * accAb[size_t(i)];
         }
       for (int k = 0; k < PS_COUNT; ++k) total_b[k] += sums[k];
