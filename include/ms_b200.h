@@ -63,6 +63,10 @@ extern "C" {
 #define MS_ARR_TRIAL         11 /* (nv,3) trial positions x + alpha d */
 #define MS_ARR_DIRECTION     12 /* (nv,3) search direction d */
 
+#define MS_PATCHES_ALL       (-1)
+#define MS_PATCHES_INTERIOR  (-2)
+#define MS_PATCHES_BOUNDARY  (-3)
+
 typedef struct ms_ctx ms_ctx;
 
 typedef struct ms_eval_opts {
@@ -75,8 +79,9 @@ typedef struct ms_eval_opts {
   double v_target;         /* body target volume */
   int32_t apply_fixed;     /* zero the gradient rows of fixed vertices (minimizer.py:988-990) */
   int32_t use_trial;       /* evaluate at MS_ARR_TRIAL instead of MS_ARR_POSITIONS */
-  int32_t patch_begin;     /* multi-GPU: range of patches this rank evaluates; */
-  int32_t patch_count;     /*            patch_count < 0 means all patches */
+  int32_t patch_begin;     /* range of patches to evaluate;  patch_count == -1: all patches */
+  int32_t patch_count;     /* MS_PATCHES_INTERIOR / MS_PATCHES_BOUNDARY: the two halves of a partitioned
+                              evaluation (patches without / with ghost rows in their halo) */
   int32_t diagnostics;     /* also write K_VECS / A_VOR / A_EFF / E_VERTEX */
   int32_t want_tilt_grad;  /* with want_grad == 0: still produce MS_ARR_TILT_GRAD (tilt-only evaluation,
                               evaluation_manager.py:693-698) */
@@ -113,6 +118,9 @@ MS_API int ms_ctx_set_pack_params(ms_ctx* ctx, int32_t threads, int32_t max_owne
  * hold a facet (default 87; lower = more free lanes = fewer shared-memory bank clashes) and
  * the number of lane-placement repair passes (default 1) */
 MS_API int ms_ctx_set_pack_tuning(ms_ctx* ctx, int32_t fill_pct, int32_t repair_sweeps);
+/* launch at most max_ctas persistent CTAs per pass (0 = one per SM): a partitioned evaluation leaves a
+ * few SMs to the NCCL kernels of the halo exchange that runs concurrently */
+MS_API int ms_ctx_set_max_ctas(ms_ctx* ctx, int32_t max_ctas);
 /* kept for ABI stability; the persistent kernels derive the thread-group count from the CTA
  * size (consumer threads / threads-per-round) */
 MS_API int ms_ctx_set_groups(ms_ctx* ctx, int32_t groups_a, int32_t groups_b);

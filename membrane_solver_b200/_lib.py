@@ -19,6 +19,7 @@ CSRC = os.path.join(_PKG, "csrc")
 
 MOD_SURFACE, MOD_VOLUME, MOD_BENDING, MOD_TILT, MOD_BENDING_TILT = 1, 2, 4, 8, 16
 FLAG_WILLMORE, FLAG_APPROX = 1, 2
+PATCHES_ALL, PATCHES_INTERIOR, PATCHES_BOUNDARY = -1, -2, -3
 
 SC_E_SURFACE, SC_AREA, SC_VOLUME, SC_E_BENDING, SC_E_TILT, SC_E_BENDING_TILT = 0, 1, 2, 3, 4, 5
 SC_G_G, SC_G_GC, SC_GC_GC, SC_LAMBDA, SC_COUNT = 8, 9, 10, 11, 16
@@ -79,6 +80,7 @@ SIGNATURES = {
     "ms_ctx_destroy": (ctypes.c_int, [_V]),
     "ms_ctx_set_pack_params": (ctypes.c_int, [_V, _i32, _i32, _i32]),
     "ms_ctx_set_pack_tuning": (ctypes.c_int, [_V, _i32, _i32]),
+    "ms_ctx_set_max_ctas": (ctypes.c_int, [_V, _i32]),
     "ms_ctx_set_groups": (ctypes.c_int, [_V, _i32, _i32]),
     "ms_ctx_set_vertex_order_hint": (ctypes.c_int, [_V, _i32, _D]),
     "ms_ctx_get_permutation": (ctypes.c_int, [_V, _I]),

@@ -85,6 +85,11 @@ struct ms_ctx {
   std::vector<cudaEvent_t> events;
   DevBuf<uint8_t> d_flush;
   DevBuf<int32_t> d_send_rows;  // rows other partitions read from this one (halo exchange)
+  // partitions: patches whose halo lies entirely in the owned rows (interior) first, then the patches that
+  // reference ghost rows (boundary) -- the interior ones can run while the halo exchange is in flight
+  DevBuf<int32_t> d_patch_order;
+  int32_t n_interior = 0;
+  int32_t max_ctas = 0;  // 0 = one persistent CTA per SM
   // internal vertex order: row i of every device array holds the caller's vertex perm[i]
   std::vector<double> order_hint;       // positions given by ms_ctx_set_vertex_order_hint (consumed by set_topology)
   std::vector<int32_t> perm;            // new -> old; empty = identity
@@ -155,12 +160,25 @@ int fill_launch(ms_ctx* c, const ms_eval_opts* o, ms::PatchLaunch& a) {
   int count = o->patch_count < 0 ? n_patches : o->patch_count;
   if (begin < 0 || count < 0 || begin + count > n_patches) return fail(-3, "patch range out of bounds");
   std::memset(&a, 0, sizeof(a));
+  if (o->patch_count == MS_PATCHES_INTERIOR || o->patch_count == MS_PATCHES_BOUNDARY) {
+    // the two halves of one evaluation: interior patches, then the patches that read ghost rows; their
+    // per-CTA sums occupy consecutive partial rows: [0, grid_i) and [grid_i, grid_i + grid_b)
+    a.patch_list = c->d_patch_order.p;
+    begin = o->patch_count == MS_PATCHES_INTERIOR ? 0 : c->n_interior;
+    count = o->patch_count == MS_PATCHES_INTERIOR ? c->n_interior : n_patches - c->n_interior;
+    ms::PatchLaunch inner;
+    std::memset(&inner, 0, sizeof(inner));
+    inner.patch_count = c->n_interior;
+    inner.max_ctas = c->max_ctas;
+    a.partial_row0 = o->patch_count == MS_PATCHES_INTERIOR ? 0 : ms::patch_grid(inner);
+  }
   a.patches = c->d_patches.p;
   a.halo_ids = c->d_halo.p;
   a.recs = c->d_recs.p;
   a.slot_gamma = c->has_gamma ? c->d_slot_gamma.p : nullptr;
   a.patch_begin = begin;
   a.patch_count = count;
+  a.max_ctas = c->max_ctas;
   a.threads = c->packed.params.threads;
   a.max_owned = c->packed.max_owned;
   a.max_local = c->packed.max_local;
@@ -403,6 +421,13 @@ int ms_ctx_set_pack_tuning(ms_ctx* c, int32_t fill_pct, int32_t repair_sweeps) {
   return 0;
 }
 
+int ms_ctx_set_max_ctas(ms_ctx* c, int32_t max_ctas) {
+  if (!c) return fail(-1, "null context");
+  if (max_ctas < 0) return fail(-1, "max_ctas must be >= 0");
+  c->max_ctas = max_ctas;
+  return 0;
+}
+
 int ms_ctx_set_groups(ms_ctx* c, int32_t groups_a, int32_t groups_b) {
   // kept for ABI stability: the persistent kernels derive the group count from the CTA size
   if (!c) return fail(-1, "null context");
@@ -472,6 +497,20 @@ int ms_ctx_set_topology_partition(ms_ctx* c, int32_t nv, int32_t n_owned, int32_
   c->v_lo.resize(np + 1);
   for (size_t p = 0; p < np; ++p) c->v_lo[p] = pk.patches[p].v_lo;
   c->v_lo[np] = n_owned;
+  {
+    std::vector<int32_t> order;
+    std::vector<int32_t> boundary;
+    for (size_t p = 0; p < np; ++p) {
+      const ms::PatchHeader& h = pk.patches[p];
+      bool ghost = false;
+      for (int32_t j = 0; j < h.n_halo && !ghost; ++j) ghost = pk.halo_ids[size_t(h.halo_off) + size_t(j)] >= n_owned;
+      (ghost ? boundary : order).push_back(int32_t(p));
+    }
+    c->n_interior = int32_t(order.size());
+    order.insert(order.end(), boundary.begin(), boundary.end());
+    if (int rc = c->d_patch_order.ensure(order.size() + 1)) return rc;
+    if (!order.empty()) CU(cudaMemcpy(c->d_patch_order.p, order.data(), order.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  }
 
   if (prc == 0 && (pk.max_owned > ms::kPatchOwnedCap || pk.max_local > ms::kPatchLocalCap || pk.max_slots > ms::kPatchSlotCap))
     return fail(-8, "a patch exceeds the compiled shared-memory capacities");
@@ -752,7 +791,14 @@ int ms_ctx_eval_reduce(ms_ctx* c, const ms_eval_opts* o) {
   if (!o) return fail(-1, "null options");
   ms::PatchLaunch a;
   if (int rc = fill_launch(c, o, a)) return rc;
-  const int rows = ms::patch_grid(a);
+  // a split evaluation (interior + boundary launches) leaves its sums in rows [0, grid_i + grid_b)
+  int rows = ms::patch_grid(a);
+  if (o->patch_count == MS_PATCHES_INTERIOR || o->patch_count == MS_PATCHES_BOUNDARY) {
+    ms::PatchLaunch inner = a, outer = a;
+    inner.patch_count = c->n_interior;
+    outer.patch_count = int(c->packed.patches.size()) - c->n_interior;
+    rows = ms::patch_grid(inner) + ms::patch_grid(outer);
+  }
   // energies, area, volume come from pass A when it ran, else from pass B; <g,g>, <g,gC>, <gC,gC>
   // and the tilt energy come from pass B when a gradient was requested -- one fixed-order sum
   const bool ran_a = needs_bending(o) || !o->want_grad;

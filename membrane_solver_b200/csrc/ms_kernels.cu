@@ -262,7 +262,8 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
     const int lane = tid - (NC + 32);
     for (int j = 0; j < n_my; ++j) {
       const int b = j & 1;
-      const int pid = a.patch_begin + int(blockIdx.x) + j * int(gridDim.x);
+      const int pidx = a.patch_begin + int(blockIdx.x) + j * int(gridDim.x);
+      const int pid = a.patch_list ? a.patch_list[pidx] : pidx;
       if (j >= 2) mbar_wait_relaxed(&bar_empty[b], unsigned(((j >> 1) - 1) & 1));
       const PatchHeader h = a.patches[pid];
       const int n_slots = int(a.patches[pid + 1].slot_off - h.slot_off);  // sentinel header at the end
@@ -494,7 +495,7 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
 
   block_sum<PS_COUNT>(sums, red, NC + 32, 15);
   if (tid == 0) {
-    double* p = a.partials + size_t(blockIdx.x) * kPartialStride;
+    double* p = a.partials + (size_t(a.partial_row0) + blockIdx.x) * kPartialStride;
 #pragma unroll
     for (int k = 0; k < PS_COUNT; ++k) p[k] = sums[k];
   }
@@ -855,7 +856,8 @@ cudaError_t configure_kernels() {
 }
 
 int patch_grid(const PatchLaunch& a) {
-  const int sms = g_num_sms > 0 ? g_num_sms : 148;
+  int sms = g_num_sms > 0 ? g_num_sms : 148;
+  if (a.max_ctas > 0 && a.max_ctas < sms) sms = a.max_ctas;
   return a.patch_count < sms ? a.patch_count : sms;
 }
 

@@ -49,6 +49,9 @@ struct PatchLaunch {
   const FacetRec* recs;
   const double* slot_gamma;   // per-slot surface tension, or nullptr -> gamma_u
   int32_t patch_begin, patch_count;
+  const int32_t* patch_list;  // optional indirection: the launch walks patch_list[patch_begin + i], i < patch_count
+  int32_t partial_row0;       // first row of `partials` this launch writes (one row per CTA)
+  int32_t max_ctas;           // > 0: launch at most this many persistent CTAs (leave SMs to NCCL kernels)
   int32_t threads;            // record slots per round = lanes of one consumer group
   int32_t max_owned, max_local;
   int32_t max_slots, max_rounds;  // largest record count / round count of any patch

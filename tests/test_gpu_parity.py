@@ -511,3 +511,52 @@ def test_full_size_invariants(L):
     assert abs(r2.e_bending - rf.e_bending) <= 1e-10 * rf.e_bending
     assert abs(r2.area - s * s * rf.area) <= 1e-11 * r2.area
     dm.close()
+
+
+def test_split_interior_boundary_evaluation(L):
+    """Partition context (owned + ghost rows): evaluating the interior patches and the patches that
+    read ghost rows as two launches gives the same gradients bit for bit, and the same scalars up to
+    the summation order of the per-CTA partial sums."""
+    from membrane_solver_b200.context import DeviceMesh
+    from membrane_solver_b200.partition import split_mesh
+    from membrane_solver_b200.synthetic import icosphere
+
+    pos, tri = icosphere(90)
+    lm = split_mesh(pos.shape[0], tri, 2, 0)
+    rows = lm.global_rows()
+    dm = DeviceMesh(0)
+    dm.set_topology(lm.nv_local, lm.tri, n_owned=lm.n_owned, body_mask=np.ones(lm.tri.shape[0], np.uint8))
+    dm.set_surface_tension(1.0)
+    dm.set_bending_params(1.0, 0.1)
+    dm.set_positions(pos[rows])
+    mods = L.MOD_SURFACE | L.MOD_BENDING | L.MOD_VOLUME
+    full = dm.options(mods)
+    # reference: the whole partition in one launch per pass (ghost seeds: take them from a full-mesh run)
+    whole = _ctx(pos.shape[0], tri, body_mask=np.ones(tri.shape[0], np.uint8))
+    whole.set_surface_tension(1.0)
+    whole.set_bending_params(1.0, 0.1)
+    whole.set_positions(pos)
+    whole.eval(whole.options(mods))
+    seeds_all = whole.download(L.ARR_SEEDS)
+
+    def run(parts):
+        for o in parts:
+            dm.eval_pass_a(o)
+        s = dm.download(L.ARR_SEEDS)
+        s[lm.n_owned:] = seeds_all[rows[lm.n_owned:]]          # what the seed halo exchange delivers
+        dm.upload(L.ARR_SEEDS, s)
+        for o in parts:
+            dm.eval_pass_b(o)
+        dm.eval_reduce(parts[-1])
+        sc = dm.read_scalars().scalars.copy()
+        return sc, dm.download(L.ARR_GRAD)[:lm.n_owned], dm.download(L.ARR_VOLGRAD)[:lm.n_owned]
+
+    sc1, g1, v1 = run([full])
+    inner, outer = dm.options(mods, patch_count=L.PATCHES_INTERIOR), dm.options(mods, patch_count=L.PATCHES_BOUNDARY)
+    sc2, g2, v2 = run([inner, outer])
+    assert np.array_equal(g1, g2) and np.array_equal(v1, v2)
+    assert np.allclose(sc1[:12], sc2[:12], rtol=1e-13, atol=0)
+    # and the owned rows agree with the single-context evaluation of the whole mesh
+    assert rel_err(g1, whole.download(L.ARR_GRAD)[rows[:lm.n_owned]]) <= 1e-13
+    dm.close()
+    whole.close()
