@@ -195,6 +195,15 @@ MS_API int ms_ctx_eval_host(ms_ctx* ctx, const ms_eval_opts* opts, const double*
 MS_API int ms_ctx_make_trial(ms_ctx* ctx, double alpha);
 /* positions <- trial (accept the step) */
 MS_API int ms_ctx_accept_trial(ms_ctx* ctx);
+/* --- device-resident line search (runtime/steppers/line_search.py:267-541, fast path) ---
+ * direction = scale * gradient (gradient descent: scale = -1) */
+MS_API int ms_ctx_direction_from_gradient(ms_ctx* ctx, double scale);
+/* out4 = { minimum edge length (runtime/topology.py:174-199), largest row norm of the direction,
+ *          <gradient, direction>, <gradient, gradient> } */
+MS_API int ms_ctx_line_search_stats(ms_ctx* ctx, double* out4);
+/* ok = 1 unless a facet normal turns by more than limit_radians between the positions and the trial
+ * positions or a facet collapses (runtime/topology.py:13-48) */
+MS_API int ms_ctx_normal_change_ok(ms_ctx* ctx, double limit_radians, int32_t* ok);
 /* deterministic <g,g>, <g,gC>, <gC,gC> into the scalar vector */
 MS_API int ms_ctx_dots(ms_ctx* ctx);
 

@@ -279,6 +279,20 @@ class DeviceMesh:
     def accept_trial(self) -> None:
         L.check(self._lib.ms_ctx_accept_trial(self._h))
 
+    def direction_from_gradient(self, scale: float = -1.0) -> None:
+        L.check(self._lib.ms_ctx_direction_from_gradient(self._h, float(scale)))
+
+    def line_search_stats(self) -> tuple[float, float, float, float]:
+        """(min edge length, max row norm of the direction, <g,d>, <g,g>) computed on the device."""
+        out = np.zeros(4)
+        L.check(self._lib.ms_ctx_line_search_stats(self._h, L.dptr(out)))
+        return float(out[0]), float(out[1]), float(out[2]), float(out[3])
+
+    def normal_change_ok(self, limit_radians: float = 0.5) -> bool:
+        ok = ctypes.c_int32(0)
+        L.check(self._lib.ms_ctx_normal_change_ok(self._h, float(limit_radians), ctypes.byref(ok)))
+        return bool(ok.value)
+
     def dots(self) -> None:
         L.check(self._lib.ms_ctx_dots(self._h))
 

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <numeric>
 #include <cstring>
@@ -97,7 +98,8 @@ struct ms_ctx {
   DevBuf<double> d_stage;               // staging for permuted uploads / downloads (5*nv doubles)
   // bending-tilt coupling: triangle rows + corner CSR on the device (built on first use)
   std::vector<int32_t> h_tri;
-  bool bt_ready = false;
+  bool bt_ready = false, tri_ready = false;
+  DevBuf<unsigned long long> d_ls_bits;  // line-search reductions: [min edge^2, max |d|^2] as bit patterns, [flag]
   DevBuf<int32_t> d_tri, d_csr_ptr, d_csr_idx;
   DevBuf<double> d_bt_corner, d_bt_base, d_bt_facet_e, d_bt_e;
   int64_t n_send_rows = 0;
@@ -248,15 +250,24 @@ bool needs_bending(const ms_eval_opts* o) { return (o->modules & (MS_MOD_BENDING
 bool has_bt(const ms_eval_opts* o) { return (o->modules & MS_MOD_BENDING_TILT) != 0; }
 bool wants_tilt_grad(const ms_eval_opts* o) { return o->want_grad || o->want_tilt_grad; }
 
+// triangle rows (internal vertex order) on the device, uploaded on first use
+int ensure_tri(ms_ctx* c) {
+  const size_t nf = size_t(c->nf);
+  if (c->tri_ready) return 0;
+  if (int rc = c->d_tri.ensure(3 * nf + 1)) return rc;
+  if (nf) CU(cudaMemcpy(c->d_tri.p, c->h_tri.data(), 3 * nf * sizeof(int32_t), cudaMemcpyHostToDevice));
+  c->tri_ready = true;
+  return 0;
+}
+
 int bt_prepare(ms_ctx* c, ms::BtMesh& m) {
   const size_t nv = size_t(c->nv), nf = size_t(c->nf);
   if (!c->bt_ready) {
     std::vector<int32_t> ptr, idx;
     ms::build_corner_csr(c->nv, c->nf, c->h_tri.data(), ptr, idx);
-    if (int rc = c->d_tri.ensure(3 * nf + 1)) return rc;
+    if (int rc = ensure_tri(c)) return rc;
     if (int rc = c->d_csr_ptr.ensure(ptr.size())) return rc;
     if (int rc = c->d_csr_idx.ensure(idx.size() + 1)) return rc;
-    if (nf) CU(cudaMemcpy(c->d_tri.p, c->h_tri.data(), 3 * nf * sizeof(int32_t), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->d_csr_ptr.p, ptr.data(), ptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     if (!idx.empty()) CU(cudaMemcpy(c->d_csr_idx.p, idx.data(), idx.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     if (int rc = c->d_bt_corner.ensure(12 * nf + 1)) return rc;
@@ -492,6 +503,7 @@ int ms_ctx_set_topology_partition(ms_ctx* c, int32_t nv, int32_t n_owned, int32_
   c->nf = nf;
   c->h_tri.assign(tri, tri + 3 * size_t(nf));
   c->bt_ready = false;
+  c->tri_ready = false;
   const ms::PackedMesh& pk = c->packed;
   const size_t np = pk.patches.size();
   c->v_lo.resize(np + 1);
@@ -903,6 +915,62 @@ int ms_ctx_dots(ms_ctx* c) {
   if (int rc = check_ctx(c, true)) return rc;
   CU(ms::launch_dots(c->d_grad.p, c->d_volgrad.p, 3 * int64_t(c->n_owned), c->d_dot_partials.p, kDotBlocks,
                      c->d_scalars.p, c->stream));
+  return 0;
+}
+
+int ms_ctx_direction_from_gradient(ms_ctx* c, double scale) {
+  if (int rc = check_ctx(c, true)) return rc;
+  if (int rc = ensure_array(c, MS_ARR_DIRECTION)) return rc;
+  CU(ms::launch_scale(c->d_grad.p, scale, c->d_dir.p, 3 * int64_t(c->nv), c->stream));
+  return 0;
+}
+
+int ms_ctx_line_search_stats(ms_ctx* c, double* out4) {
+  if (int rc = check_ctx(c, true)) return rc;
+  if (!out4) return fail(-1, "null argument");
+  if (!c->d_dir.p) return fail(-4, "no search direction exists (ms_ctx_direction_from_gradient / MS_ARR_DIRECTION)");
+  if (int rc = ensure_tri(c)) return rc;
+  if (int rc = c->d_ls_bits.ensure(4)) return rc;
+  const double big = 1.0e300, zero = 0.0;
+  unsigned long long init[4];
+  std::memcpy(&init[0], &big, 8);
+  std::memcpy(&init[1], &zero, 8);
+  init[2] = init[3] = 0;
+  CU(cudaMemcpyAsync(c->d_ls_bits.p, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+  CU(ms::launch_min_edge2(c->d_tri.p, c->nf, c->nv, c->d_pos.p, c->d_ls_bits.p, c->stream));
+  CU(ms::launch_max_row_norm2(c->d_dir.p, c->n_owned, c->d_ls_bits.p + 1, c->stream));
+  // <g,g>, <g,d>, <d,d> with the deterministic two-level sum; they land in the scalar vector
+  CU(ms::launch_dots(c->d_grad.p, c->d_dir.p, 3 * int64_t(c->n_owned), c->d_dot_partials.p, kDotBlocks,
+                     c->d_scalars.p, c->stream));
+  unsigned long long bits[4];
+  double sc[MS_SC_COUNT];
+  CU(cudaMemcpyAsync(bits, c->d_ls_bits.p, sizeof(bits), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(sc, c->d_scalars.p, sizeof(sc), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  double e2, d2;
+  std::memcpy(&e2, &bits[0], 8);
+  std::memcpy(&d2, &bits[1], 8);
+  out4[0] = (c->nf > 0 && e2 < 1.0e299) ? std::sqrt(e2) : 0.0;  // minimum edge length
+  out4[1] = std::sqrt(d2);                                       // largest row norm of the direction
+  out4[2] = sc[MS_SC_G_GC];                                      // <gradient, direction>
+  out4[3] = sc[MS_SC_G_G];                                       // <gradient, gradient>
+  return 0;
+}
+
+int ms_ctx_normal_change_ok(ms_ctx* c, double limit_radians, int32_t* ok) {
+  if (int rc = check_ctx(c, true)) return rc;
+  if (!ok) return fail(-1, "null argument");
+  if (!c->d_trial.p) return fail(-4, "no trial positions exist");
+  if (int rc = ensure_tri(c)) return rc;
+  if (int rc = c->d_ls_bits.ensure(4)) return rc;
+  int* flag = reinterpret_cast<int*>(c->d_ls_bits.p + 2);
+  CU(cudaMemsetAsync(flag, 0, sizeof(int), c->stream));
+  CU(ms::launch_normal_change(c->d_tri.p, c->nf, c->nv, c->d_pos.p, c->d_trial.p, std::cos(limit_radians), flag,
+                              c->stream));
+  int host_flag = 0;
+  CU(cudaMemcpyAsync(&host_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  *ok = host_flag ? 0 : 1;
   return 0;
 }
 

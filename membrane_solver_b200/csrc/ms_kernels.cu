@@ -805,6 +805,70 @@ __global__ void __launch_bounds__(256) k_row_norm2(const double* __restrict__ ro
   out[i] = x * x + y * y + z * z;
 }
 
+// ---- line-search helpers of the device-resident loop (runtime/steppers/line_search.py:267-541) ----
+// minimum edge length squared over the facets (runtime/topology.py:174-199) and maximum row norm
+// squared of the search direction; min / max are order independent, so atomics keep determinism.
+__global__ void __launch_bounds__(256) k_min_edge2(const int32_t* __restrict__ tri, int32_t nf, int32_t nv,
+                                                   const double* __restrict__ pos, unsigned long long* out) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  double m = 1.0e300;
+  if (f < nf) {
+    const int i0 = tri[3 * size_t(f)], i1 = tri[3 * size_t(f) + 1], i2 = tri[3 * size_t(f) + 2];
+    if (i0 >= 0 && i0 < nv && i1 >= 0 && i1 < nv && i2 >= 0 && i2 < nv) {
+      const d3 a = ld3(pos, i0), b = ld3(pos, i1), c = ld3(pos, i2);
+      const d3 e0 = c - b, e1 = a - c, e2 = b - a;
+      m = fmin(dot(e0, e0), fmin(dot(e1, e1), dot(e2, e2)));
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) m = fmin(m, __shfl_down_sync(0xffffffffu, m, off));
+  if ((threadIdx.x & 31) == 0) atomicMin(out, (unsigned long long)__double_as_longlong(m));
+}
+
+__global__ void __launch_bounds__(256) k_max_row_norm2(const double* __restrict__ rows, int64_t n,
+                                                       unsigned long long* out) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  double m = 0.0;
+  if (i < n) {
+    const double x = rows[3 * i], y = rows[3 * i + 1], z = rows[3 * i + 2];
+    m = x * x + y * y + z * z;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, off));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
+}
+
+// flag |= 1 when a facet normal turns by more than acos(cos_limit) between `old_pos` and `new_pos`, or
+// collapses (runtime/topology.py:13-48)
+__global__ void __launch_bounds__(256) k_normal_change(const int32_t* __restrict__ tri, int32_t nf, int32_t nv,
+                                                       const double* __restrict__ old_pos,
+                                                       const double* __restrict__ new_pos, double cos_limit,
+                                                       int* flag) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nf) return;
+  const int i0 = tri[3 * size_t(f)], i1 = tri[3 * size_t(f) + 1], i2 = tri[3 * size_t(f) + 2];
+  if (!(i0 >= 0 && i0 < nv && i1 >= 0 && i1 < nv && i2 >= 0 && i2 < nv)) return;
+  const d3 a = ld3(old_pos, i0), b = ld3(old_pos, i1), c = ld3(old_pos, i2);
+  const d3 n0 = cross(b - a, c - a);
+  const double m0 = sqrt(dot(n0, n0));
+  if (!(m0 > 1.0e-12)) return;  // facets that were degenerate before the step are not judged
+  const d3 a1 = ld3(new_pos, i0), b1 = ld3(new_pos, i1), c1 = ld3(new_pos, i2);
+  const d3 n1 = cross(b1 - a1, c1 - a1);
+  const double m1 = sqrt(dot(n1, n1));
+  bool bad = m1 < 1.0e-12;
+  if (!bad) {
+    double d = dot(n0, n1) / (m0 * m1);
+    d = fmin(1.0, fmax(-1.0, d));
+    bad = !(d >= cos_limit);
+  }
+  if (bad) atomicOr(flag, 1);
+}
+
+__global__ void __launch_bounds__(256) k_scale(const double* __restrict__ x, double scale, double* out, int64_t n) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = scale * x[i];
+}
+
 inline int blocks_for(int64_t n, int t) { return int((n + t - 1) / t); }
 
 }  // namespace
@@ -1015,6 +1079,28 @@ cudaError_t launch_bt_tilt_gather(const BtMesh& m, const double* corner3, double
 
 cudaError_t launch_bt_finalize(const double* e_bt, double* scalars, cudaStream_t st) {
   k_bt_finalize<<<1, 1, 0, st>>>(e_bt, scalars);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_min_edge2(const int32_t* tri, int32_t nf, int32_t nv, const double* pos,
+                             unsigned long long* out, cudaStream_t st) {
+  if (nf > 0) k_min_edge2<<<blocks_for(nf, 256), 256, 0, st>>>(tri, nf, nv, pos, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_max_row_norm2(const double* rows, int64_t n, unsigned long long* out, cudaStream_t st) {
+  if (n > 0) k_max_row_norm2<<<blocks_for(n, 256), 256, 0, st>>>(rows, n, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_normal_change(const int32_t* tri, int32_t nf, int32_t nv, const double* old_pos,
+                                 const double* new_pos, double cos_limit, int* flag, cudaStream_t st) {
+  if (nf > 0) k_normal_change<<<blocks_for(nf, 256), 256, 0, st>>>(tri, nf, nv, old_pos, new_pos, cos_limit, flag);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_scale(const double* x, double scale, double* out, int64_t n, cudaStream_t st) {
+  if (n > 0) k_scale<<<blocks_for(n, 256), 256, 0, st>>>(x, scale, out, n);
   return cudaGetLastError();
 }
 

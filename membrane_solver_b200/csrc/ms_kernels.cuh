@@ -138,6 +138,14 @@ cudaError_t launch_sum(const double* x, int64_t n, double scale, double* out, cu
 // out[v] = |rows[v,:]|^2 of an (n,3) array (tilt magnitude staging)
 cudaError_t launch_row_norm2(const double* rows, int64_t n, double* out, cudaStream_t st);
 
+// --- line-search helpers of the device-resident loop ---
+cudaError_t launch_min_edge2(const int32_t* tri, int32_t nf, int32_t nv, const double* pos,
+                             unsigned long long* out, cudaStream_t st);
+cudaError_t launch_max_row_norm2(const double* rows, int64_t n, unsigned long long* out, cudaStream_t st);
+cudaError_t launch_normal_change(const int32_t* tri, int32_t nf, int32_t nv, const double* old_pos,
+                                 const double* new_pos, double cos_limit, int* flag, cudaStream_t st);
+cudaError_t launch_scale(const double* x, double scale, double* out, int64_t n, cudaStream_t st);
+
 // --- bending-tilt coupling on the resident mesh (ms_bt.cuh); corner holds 12*nf doubles ---
 // stage: divergence / effective areas -> vertex seeds (into `seeds`, read by pass B) and base term ->
 // per-facet energy (sum into e_out) and, when tilt_grads, corner contributions of the tilt gradient

@@ -75,9 +75,11 @@ class FakeDeviceMesh:
                 sc[L.SC_LAMBDA] = coef
             if opts.get("apply_fixed") and self.fixed is not None:
                 g_out = np.where(np.asarray(self.fixed, bool)[:, None], 0.0, g_out)
-        self.arrays = {L.ARR_GRAD: g_out, L.ARR_VOLGRAD: gc, L.ARR_TILT_GRAD: out["tilt_grad"],
-                       L.ARR_E_VERTEX: out["e_vertex"], L.ARR_K_VECS: out["k_vecs"], L.ARR_A_VOR: out["a_vor"],
-                       L.ARR_A_EFF: out["a_eff"]}
+        new = {L.ARR_E_VERTEX: out["e_vertex"], L.ARR_K_VECS: out["k_vecs"], L.ARR_A_VOR: out["a_vor"],
+               L.ARR_A_EFF: out["a_eff"], L.ARR_TILT_GRAD: out["tilt_grad"]}
+        if opts.get("want_grad", True):  # an energy-only evaluation leaves the gradients alone, like the device
+            new.update({L.ARR_GRAD: g_out, L.ARR_VOLGRAD: gc})
+        self.arrays.update(new)
         if grad is not None:
             grad[:] = g_out
         if volgrad is not None:
@@ -87,7 +89,47 @@ class FakeDeviceMesh:
         return EvalResult(sc)
 
     def download(self, which):
+        if which == L.ARR_POSITIONS:
+            return np.array(self.pos)
         return np.array(self.arrays[which])
+
+    # -- device-resident loop (numpy restatement of the small kernels; TEST ONLY) --
+    def set_positions(self, pos):
+        self.pos = np.array(pos, dtype=np.float64)
+
+    def eval(self, opts):
+        p = self.trial if opts.get("use_trial") else self.pos
+        return self.eval_host(opts, p)
+
+    def direction_from_gradient(self, scale=-1.0):
+        self.dir = scale * self.arrays[L.ARR_GRAD]
+
+    def make_trial(self, alpha):
+        self.trial = self.pos + alpha * self.dir
+
+    def accept_trial(self):
+        self.pos = self.trial.copy()
+
+    def line_search_stats(self):
+        t, p = self.tri, self.pos
+        e = np.concatenate([p[t[:, 2]] - p[t[:, 1]], p[t[:, 0]] - p[t[:, 2]], p[t[:, 1]] - p[t[:, 0]]])
+        g = self.arrays[L.ARR_GRAD]
+        return (float(np.sqrt((e * e).sum(axis=1).min())), float(np.sqrt((self.dir**2).sum(axis=1).max())),
+                float((g * self.dir).sum()), float((g * g).sum()))
+
+    def normal_change_ok(self, limit=0.5):
+        t = self.tri
+        def normals(p):
+            return np.cross(p[t[:, 1]] - p[t[:, 0]], p[t[:, 2]] - p[t[:, 0]])
+        n0, n1 = normals(self.pos), normals(self.trial)
+        m0, m1 = np.linalg.norm(n0, axis=1), np.linalg.norm(n1, axis=1)
+        good = m0 > 1e-12
+        if not good.any():
+            return True
+        if (m1[good] < 1e-12).any():
+            return False
+        d = np.clip((n0[good] * n1[good]).sum(axis=1) / (m0[good] * m1[good]), -1.0, 1.0)
+        return bool(np.all(np.arccos(d) <= limit))
 
     def close(self):
         pass

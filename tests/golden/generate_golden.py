@@ -294,8 +294,53 @@ def minimizer_vectors():
     np.savez_compressed(os.path.join(HERE, "minimizer.npz"), **out)
 
 
+def trajectory_vectors():
+    """Gradient-descent trajectories of the reference Minimizer (GD + Armijo, trial-energy fast path:
+    no enforceable constraints) for the device-resident loop: initial dense state, per-step energies,
+    final positions."""
+    out = {}
+    for name, path, levels, steps, tweak in (
+        ("cube", os.path.join(REF, "meshes", "cube.json"), 2, 12, None),                 # surface + volume penalty
+        ("bcube", os.path.join(REF, "meshes", "bending_cube.yaml"), 1, 6, "no_constraints"),  # + Helfrich bending
+    ):
+        mesh = _refined(path, levels)
+        rng = np.random.default_rng(11)
+        for v in mesh.vertices.values():
+            v.position = np.asarray(v.position, dtype=float) + 0.01 * rng.normal(size=3)
+        mesh.increment_version()
+        gp = mesh.global_parameters
+        if tweak == "no_constraints":
+            # keep the trial-energy fast path: the volume enters as a penalty, not as a hard constraint
+            mesh.constraint_modules = []
+            gp.set("volume_constraint_mode", "penalty")
+            if "volume" not in mesh.energy_modules:
+                mesh.energy_modules = list(mesh.energy_modules) + ["volume"]
+        mini = Minimizer(mesh, gp, GradientDescent(), EnergyModuleManager(mesh.energy_modules),
+                         ConstraintModuleManager(mesh.constraint_modules), quiet=True)
+        assert not mini._has_enforceable_constraints
+        st = _dense_state(mesh)
+        for k, v in st.items():
+            out[f"{name}_{k}"] = v
+        energies = []
+        for i in range(steps):
+            res = mini.minimize(n_steps=1)
+            energies.append(res["energy"])
+        out[f"{name}_energies"] = np.array(energies)
+        out[f"{name}_final_pos"] = np.array(mesh.positions_view())
+        out[f"{name}_step_size"] = np.float64(mini.step_size)
+        out[f"{name}_modules"] = np.array(list(mesh.energy_modules))
+        out[f"{name}_mode"] = np.array(str(gp.get("volume_constraint_mode", "lagrange")))
+        out[f"{name}_kvol"] = np.float64(gp.get("volume_stiffness", 0.0) or 0.0)
+        out[f"{name}_kappa"] = np.float64(gp.get("bending_modulus", 0.0) or 0.0)
+        out[f"{name}_c0"] = np.float64(gp.get("spontaneous_curvature", 0.0) or 0.0)
+        out[f"{name}_steps"] = np.int64(steps)
+        print(name, list(mesh.energy_modules), energies[0], energies[-1], mini.step_size)
+    np.savez_compressed(os.path.join(HERE, "trajectory.npz"), **out)
+
+
 if __name__ == "__main__":
     _ = (volume_constraint, volume_energy)
     kernel_vectors()
     module_vectors()
     minimizer_vectors()
+    trajectory_vectors()
