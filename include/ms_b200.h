@@ -198,6 +198,11 @@ MS_API int ms_ctx_accept_trial(ms_ctx* ctx);
 /* --- device-resident line search (runtime/steppers/line_search.py:267-541, fast path) ---
  * direction = scale * gradient (gradient descent: scale = -1) */
 MS_API int ms_ctx_direction_from_gradient(ms_ctx* ctx, double scale);
+/* per-vertex Polak-Ribiere direction (runtime/steppers/conjugate_gradient.py:63-119); restart != 0 or no
+ * committed history: direction = -gradient.  ms_ctx_cg_commit stores gradient and direction of an
+ * accepted step as the history of the next one. */
+MS_API int ms_ctx_cg_direction(ms_ctx* ctx, int32_t restart);
+MS_API int ms_ctx_cg_commit(ms_ctx* ctx);
 /* out4 = { minimum edge length (runtime/topology.py:174-199), largest row norm of the direction,
  *          <gradient, direction>, <gradient, gradient> } */
 MS_API int ms_ctx_line_search_stats(ms_ctx* ctx, double* out4);

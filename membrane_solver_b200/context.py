@@ -282,6 +282,12 @@ class DeviceMesh:
     def direction_from_gradient(self, scale: float = -1.0) -> None:
         L.check(self._lib.ms_ctx_direction_from_gradient(self._h, float(scale)))
 
+    def cg_direction(self, restart: bool) -> None:
+        L.check(self._lib.ms_ctx_cg_direction(self._h, int(bool(restart))))
+
+    def cg_commit(self) -> None:
+        L.check(self._lib.ms_ctx_cg_commit(self._h))
+
     def line_search_stats(self) -> tuple[float, float, float, float]:
         """(min edge length, max row norm of the direction, <g,d>, <g,g>) computed on the device."""
         out = np.zeros(4)

@@ -99,6 +99,7 @@ struct ms_ctx {
   // bending-tilt coupling: triangle rows + corner CSR on the device (built on first use)
   std::vector<int32_t> h_tri;
   bool bt_ready = false, tri_ready = false;
+  DevBuf<double> d_cg_prev_g, d_cg_prev_d;  // conjugate-gradient memory (previous gradient / direction)
   DevBuf<unsigned long long> d_ls_bits;  // line-search reductions: [min edge^2, max |d|^2] as bit patterns, [flag]
   DevBuf<int32_t> d_tri, d_csr_ptr, d_csr_idx;
   DevBuf<double> d_bt_corner, d_bt_base, d_bt_facet_e, d_bt_e;
@@ -577,6 +578,8 @@ int ms_ctx_set_topology_partition(ms_ctx* c, int32_t nv, int32_t n_owned, int32_
   }
   // per-entity parameter arrays belong to the previous topology
   c->has_gamma = c->has_kappa = c->has_c0 = false;
+  c->d_cg_prev_g.release();
+  c->d_cg_prev_d.release();
   c->d_tilts.release();
   c->d_tilt_sq.release();
   c->d_tilt_grad.release();
@@ -922,6 +925,30 @@ int ms_ctx_direction_from_gradient(ms_ctx* c, double scale) {
   if (int rc = check_ctx(c, true)) return rc;
   if (int rc = ensure_array(c, MS_ARR_DIRECTION)) return rc;
   CU(ms::launch_scale(c->d_grad.p, scale, c->d_dir.p, 3 * int64_t(c->nv), c->stream));
+  return 0;
+}
+
+int ms_ctx_cg_direction(ms_ctx* c, int32_t restart) {
+  if (int rc = check_ctx(c, true)) return rc;
+  if (int rc = ensure_array(c, MS_ARR_DIRECTION)) return rc;
+  const int64_t nv = c->nv;
+  if (restart || !c->d_cg_prev_g.p || c->d_cg_prev_g.n < size_t(3 * nv)) {
+    CU(ms::launch_scale(c->d_grad.p, -1.0, c->d_dir.p, 3 * nv, c->stream));
+    return 0;
+  }
+  CU(ms::launch_cg_direction(c->d_grad.p, c->d_cg_prev_g.p, c->d_cg_prev_d.p, c->has_fixed ? c->d_fixed.p : nullptr,
+                             nv, c->d_dir.p, c->stream));
+  return 0;
+}
+
+int ms_ctx_cg_commit(ms_ctx* c) {
+  if (int rc = check_ctx(c, true)) return rc;
+  if (!c->d_dir.p) return fail(-4, "no search direction exists");
+  const size_t n3 = 3 * size_t(c->nv);
+  if (int rc = c->d_cg_prev_g.ensure(n3 + 1)) return rc;
+  if (int rc = c->d_cg_prev_d.ensure(n3 + 1)) return rc;
+  CU(cudaMemcpyAsync(c->d_cg_prev_g.p, c->d_grad.p, n3 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_cg_prev_d.p, c->d_dir.p, n3 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
   return 0;
 }
 

@@ -864,6 +864,27 @@ __global__ void __launch_bounds__(256) k_normal_change(const int32_t* __restrict
   if (bad) atomicOr(flag, 1);
 }
 
+// Per-vertex Polak-Ribiere direction (runtime/steppers/conjugate_gradient.py:84-104):
+//   beta_v = g_v.(g_v - g'_v) / (g'_v.g'_v + 1e-20);  d_v = -g_v + beta_v d'_v, or -g_v where beta_v < 0;
+// fixed rows get a zero direction.
+__global__ void __launch_bounds__(256) k_cg_direction(const double* __restrict__ g, const double* __restrict__ pg,
+                                                      const double* __restrict__ pd,
+                                                      const uint8_t* __restrict__ fixed, int64_t nv, double* d) {
+  const int64_t v = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (v >= nv) return;
+  const double gx = g[3 * v], gy = g[3 * v + 1], gz = g[3 * v + 2];
+  const double px = pg[3 * v], py = pg[3 * v + 1], pz = pg[3 * v + 2];
+  const double numer = gx * (gx - px) + gy * (gy - py) + gz * (gz - pz);
+  const double denom = (px * px + py * py + pz * pz) + 1.0e-20;
+  const double beta = numer / denom;
+  double dx = -gx, dy = -gy, dz = -gz;
+  if (!(beta < 0.0)) {
+    dx += beta * pd[3 * v]; dy += beta * pd[3 * v + 1]; dz += beta * pd[3 * v + 2];
+  }
+  if (fixed && fixed[v]) dx = dy = dz = 0.0;
+  d[3 * v] = dx; d[3 * v + 1] = dy; d[3 * v + 2] = dz;
+}
+
 __global__ void __launch_bounds__(256) k_scale(const double* __restrict__ x, double scale, double* out, int64_t n) {
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) out[i] = scale * x[i];
@@ -1096,6 +1117,12 @@ cudaError_t launch_max_row_norm2(const double* rows, int64_t n, unsigned long lo
 cudaError_t launch_normal_change(const int32_t* tri, int32_t nf, int32_t nv, const double* old_pos,
                                  const double* new_pos, double cos_limit, int* flag, cudaStream_t st) {
   if (nf > 0) k_normal_change<<<blocks_for(nf, 256), 256, 0, st>>>(tri, nf, nv, old_pos, new_pos, cos_limit, flag);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_cg_direction(const double* g, const double* pg, const double* pd, const uint8_t* fixed,
+                                int64_t nv, double* d, cudaStream_t st) {
+  if (nv > 0) k_cg_direction<<<blocks_for(nv, 256), 256, 0, st>>>(g, pg, pd, fixed, nv, d);
   return cudaGetLastError();
 }
 

@@ -8,7 +8,9 @@ constraints and without tilts --
 
 * ``Minimizer.minimize`` (``runtime/minimizer.py:1189-1535``): evaluate energy + projected gradient,
   stop on ``|g| < tol``, step, adapt the step size, count zero-steps;
-* ``GradientDescent.step`` (``runtime/steppers/gradient_descent.py:35-84``): direction ``-g``;
+* ``GradientDescent.step`` (``runtime/steppers/gradient_descent.py:35-84``): direction ``-g``, or
+  ``ConjugateGradient.step`` (``runtime/steppers/conjugate_gradient.py:63-119``): per-vertex
+  Polak-Ribiere direction with periodic restart;
 * the trial-energy fast path of ``backtracking_line_search_array``
   (``runtime/steppers/line_search.py:267-430``): Armijo rule ``E(x + a d) <= E0 + c a <g,d>``,
   backtracking factor ``beta``, growth ``gamma``, the normal-flip guard of
@@ -43,6 +45,10 @@ class DeviceMinimizer:
     gamma: float = 1.5
     alpha_max_factor: float = 10.0
     edge_fraction: float = 0.0     # global parameter shape_step_edge_fraction
+    stepper: str = "gd"            # "gd" | "cg" (per-vertex Polak-Ribiere, conjugate_gradient.py:63-119)
+    restart_interval: int = 10
+    _cg_iter: int = 0
+    _cg_have_history: bool = False
     history: list = field(default_factory=list)
 
     # -- energy of the loaded module set from the scalar vector ---------------------------------
@@ -111,7 +117,11 @@ class DeviceMinimizer:
         energy = float("nan")
         for i in range(n_steps):
             energy = self.energy_and_gradient()
-            self.dm.direction_from_gradient(-1.0)
+            if self.stepper == "cg":
+                restart = (not self._cg_have_history) or (self._cg_iter % self.restart_interval == 0)
+                self.dm.cg_direction(restart)
+            else:
+                self.dm.direction_from_gradient(-1.0)
             _, _, _, g_dot_g = self.dm.line_search_stats()
             grad_norm = g_dot_g ** 0.5
             if grad_norm < self.tol:
@@ -120,6 +130,14 @@ class DeviceMinimizer:
             step_in = self.step_size
             success, self.step_size, accepted = self._line_search(step_in)
             self.history.append((i, float(accepted), float(step_in), bool(success)))
+            if self.stepper == "cg":
+                if success:
+                    self.dm.cg_commit()
+                    self._cg_have_history = True
+                    self._cg_iter += 1
+                else:  # minimizer.py:1461-1463: a failed step resets the stepper
+                    self._cg_have_history = False
+                    self._cg_iter = 0
             if not success:
                 if self.step_size <= self.step_size_floor:
                     zero_steps += 1

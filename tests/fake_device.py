@@ -104,6 +104,21 @@ class FakeDeviceMesh:
     def direction_from_gradient(self, scale=-1.0):
         self.dir = scale * self.arrays[L.ARR_GRAD]
 
+    def cg_direction(self, restart):
+        g = self.arrays[L.ARR_GRAD]
+        if restart or getattr(self, "_pg", None) is None:
+            self.dir = -g
+            return
+        beta = np.einsum("ij,ij->i", g, g - self._pg) / (np.einsum("ij,ij->i", self._pg, self._pg) + 1e-20)
+        d = -g + beta[:, None] * self._pd
+        d[beta < 0] = -g[beta < 0]
+        if self.fixed is not None:
+            d[np.asarray(self.fixed, bool)] = 0.0
+        self.dir = d
+
+    def cg_commit(self):
+        self._pg, self._pd = self.arrays[L.ARR_GRAD].copy(), self.dir.copy()
+
     def make_trial(self, alpha):
         self.trial = self.pos + alpha * self.dir
 

@@ -302,6 +302,7 @@ def trajectory_vectors():
     for name, path, levels, steps, tweak in (
         ("cube", os.path.join(REF, "meshes", "cube.json"), 2, 12, None),                 # surface + volume penalty
         ("bcube", os.path.join(REF, "meshes", "bending_cube.yaml"), 1, 6, "no_constraints"),  # + Helfrich bending
+        ("cubecg", os.path.join(REF, "meshes", "cube.json"), 2, 14, "cg"),               # conjugate gradient stepper
     ):
         mesh = _refined(path, levels)
         rng = np.random.default_rng(11)
@@ -315,16 +316,27 @@ def trajectory_vectors():
             gp.set("volume_constraint_mode", "penalty")
             if "volume" not in mesh.energy_modules:
                 mesh.energy_modules = list(mesh.energy_modules) + ["volume"]
-        mini = Minimizer(mesh, gp, GradientDescent(), EnergyModuleManager(mesh.energy_modules),
+        if tweak == "cg":
+            from runtime.steppers.conjugate_gradient import ConjugateGradient
+
+            stepper = ConjugateGradient()
+        else:
+            stepper = GradientDescent()
+        mini = Minimizer(mesh, gp, stepper, EnergyModuleManager(mesh.energy_modules),
                          ConstraintModuleManager(mesh.constraint_modules), quiet=True)
         assert not mini._has_enforceable_constraints
         st = _dense_state(mesh)
         for k, v in st.items():
             out[f"{name}_{k}"] = v
         energies = []
-        for i in range(steps):
-            res = mini.minimize(n_steps=1)
-            energies.append(res["energy"])
+        if tweak == "cg":
+            # one call: the stepper keeps its history across the iterations of a single minimize()
+            res = mini.minimize(n_steps=steps)
+            energies = [res["energy"]] * steps
+        else:
+            for i in range(steps):
+                res = mini.minimize(n_steps=1)
+                energies.append(res["energy"])
         out[f"{name}_energies"] = np.array(energies)
         out[f"{name}_final_pos"] = np.array(mesh.positions_view())
         out[f"{name}_step_size"] = np.float64(mini.step_size)

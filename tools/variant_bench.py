@@ -34,3 +34,17 @@ run("surface only", mods=L.MOD_SURFACE)
 run("energy only S+B+V (line search)", want_grad=False)
 run("S+B+V+tilt", mods=L.MOD_SURFACE | L.MOD_BENDING | L.MOD_VOLUME | L.MOD_TILT)
 run("bending_tilt + tilt", mods=L.MOD_BENDING_TILT | L.MOD_TILT)
+
+# device-resident minimiser steps (only scalars cross PCIe): surface + bending + volume penalty
+from membrane_solver_b200.runtime.device_minimizer import DeviceMinimizer
+for stepper in ("gd", "cg"):
+    dm = DeviceMesh(0)
+    dm.set_topology(nv, tri, body_mask=np.ones(nf, np.uint8))
+    dm.set_surface_tension(1.0); dm.set_bending_params(1.0, 0.0); dm.set_positions(pos)
+    mini = DeviceMinimizer(dm, L.MOD_SURFACE | L.MOD_BENDING, volume_mode="penalty", k_vol=1000.0, v_target=4.18,
+                           step_size=1e-7, stepper=stepper)
+    mini.minimize(n_steps=3)
+    t0 = time.perf_counter(); r = mini.minimize(n_steps=20); dm.sync(); dt = time.perf_counter() - t0
+    evals = sum(1 for h in mini.history)
+    print(f"device-resident {stepper} step (10M facets)      {dt/20*1e3:.3f} ms/step  energy {r['energy']:.6f}  accepted {sum(h[3] for h in mini.history)}/{len(mini.history)}")
+    dm.close()
