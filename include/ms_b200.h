@@ -198,6 +198,9 @@ MS_API int ms_ctx_accept_trial(ms_ctx* ctx);
 /* --- device-resident line search (runtime/steppers/line_search.py:267-541, fast path) ---
  * direction = scale * gradient (gradient descent: scale = -1) */
 MS_API int ms_ctx_direction_from_gradient(ms_ctx* ctx, double scale);
+/* dst += alpha * src for two (nv,3) arrays, optionally leaving fixed rows untouched: the position update
+ * of the hard volume projection x -= lambda dV/dx (modules/constraints/volume.py:116-149) */
+MS_API int ms_ctx_axpy(ms_ctx* ctx, int dst, int src, double alpha, int32_t skip_fixed);
 /* per-vertex Polak-Ribiere direction (runtime/steppers/conjugate_gradient.py:63-119); restart != 0 or no
  * committed history: direction = -gradient.  ms_ctx_cg_commit stores gradient and direction of an
  * accepted step as the history of the next one. */

@@ -114,6 +114,7 @@ SIGNATURES = {
     "ms_ctx_accept_trial": (ctypes.c_int, [_V]),
     "ms_ctx_dots": (ctypes.c_int, [_V]),
     "ms_ctx_direction_from_gradient": (ctypes.c_int, [_V, _f64]),
+    "ms_ctx_axpy": (ctypes.c_int, [_V, ctypes.c_int, ctypes.c_int, _f64, _i32]),
     "ms_ctx_cg_direction": (ctypes.c_int, [_V, _i32]),
     "ms_ctx_cg_commit": (ctypes.c_int, [_V]),
     "ms_ctx_line_search_stats": (ctypes.c_int, [_V, _D]),

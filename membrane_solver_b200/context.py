@@ -282,6 +282,9 @@ class DeviceMesh:
     def direction_from_gradient(self, scale: float = -1.0) -> None:
         L.check(self._lib.ms_ctx_direction_from_gradient(self._h, float(scale)))
 
+    def axpy(self, dst: int, src: int, alpha: float, skip_fixed: bool = True) -> None:
+        L.check(self._lib.ms_ctx_axpy(self._h, int(dst), int(src), float(alpha), int(bool(skip_fixed))))
+
     def cg_direction(self, restart: bool) -> None:
         L.check(self._lib.ms_ctx_cg_direction(self._h, int(bool(restart))))
 

@@ -928,6 +928,16 @@ int ms_ctx_direction_from_gradient(ms_ctx* c, double scale) {
   return 0;
 }
 
+int ms_ctx_axpy(ms_ctx* c, int dst, int src, double alpha, int32_t skip_fixed) {
+  if (int rc = check_ctx(c, true)) return rc;
+  int64_t ld = 0, ls = 0;
+  double* d = array_ptr(c, dst, &ld);
+  double* s = array_ptr(c, src, &ls);
+  if (!d || !s || ld != ls || ld != 3 * int64_t(c->nv)) return fail(-1, "ms_ctx_axpy needs two allocated (nv,3) arrays");
+  CU(ms::launch_axpy_rows(s, alpha, (skip_fixed && c->has_fixed) ? c->d_fixed.p : nullptr, c->nv, d, c->stream));
+  return 0;
+}
+
 int ms_ctx_cg_direction(ms_ctx* c, int32_t restart) {
   if (int rc = check_ctx(c, true)) return rc;
   if (int rc = ensure_array(c, MS_ARR_DIRECTION)) return rc;

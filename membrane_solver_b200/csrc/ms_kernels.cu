@@ -885,6 +885,15 @@ __global__ void __launch_bounds__(256) k_cg_direction(const double* __restrict__
   d[3 * v] = dx; d[3 * v + 1] = dy; d[3 * v + 2] = dz;
 }
 
+// y[v,:] += alpha * x[v,:] on the rows that are not fixed (constraint projection of the positions)
+__global__ void __launch_bounds__(256) k_axpy_rows(const double* __restrict__ x, double alpha,
+                                                   const uint8_t* __restrict__ fixed, int64_t nv, double* y) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= 3 * nv) return;
+  if (fixed && fixed[i / 3]) return;
+  y[i] += alpha * x[i];
+}
+
 __global__ void __launch_bounds__(256) k_scale(const double* __restrict__ x, double scale, double* out, int64_t n) {
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) out[i] = scale * x[i];
@@ -1123,6 +1132,12 @@ cudaError_t launch_normal_change(const int32_t* tri, int32_t nf, int32_t nv, con
 cudaError_t launch_cg_direction(const double* g, const double* pg, const double* pd, const uint8_t* fixed,
                                 int64_t nv, double* d, cudaStream_t st) {
   if (nv > 0) k_cg_direction<<<blocks_for(nv, 256), 256, 0, st>>>(g, pg, pd, fixed, nv, d);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_axpy_rows(const double* x, double alpha, const uint8_t* fixed, int64_t nv, double* y,
+                             cudaStream_t st) {
+  if (nv > 0) k_axpy_rows<<<blocks_for(3 * nv, 256), 256, 0, st>>>(x, alpha, fixed, nv, y);
   return cudaGetLastError();
 }
 

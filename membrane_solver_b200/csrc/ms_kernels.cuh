@@ -145,6 +145,8 @@ cudaError_t launch_max_row_norm2(const double* rows, int64_t n, unsigned long lo
 cudaError_t launch_normal_change(const int32_t* tri, int32_t nf, int32_t nv, const double* old_pos,
                                  const double* new_pos, double cos_limit, int* flag, cudaStream_t st);
 cudaError_t launch_scale(const double* x, double scale, double* out, int64_t n, cudaStream_t st);
+cudaError_t launch_axpy_rows(const double* x, double alpha, const uint8_t* fixed, int64_t nv, double* y,
+                             cudaStream_t st);
 cudaError_t launch_cg_direction(const double* g, const double* pg, const double* pd, const uint8_t* fixed,
                                 int64_t nv, double* d, cudaStream_t st);
 

@@ -33,6 +33,10 @@ class DeviceMinimizer:
     modules: int                   # MS_MOD_* bits of the energy terms
     flags: int = 0
     volume_mode: str | None = None  # None | "lagrange" (KKT projection of the gradient) | "penalty"
+    projection_during_minimization: bool = True   # global parameter volume_projection_during_minimization
+    volume_tolerance: float = 1e-3                # global parameter volume_tolerance
+    enforce_volume: bool = False   # hard volume constraint: Newton projection of the positions inside the line
+                                   # search and around the loop (modules/constraints/volume.py:69-149)
     k_vol: float = 0.0
     v_target: float = 0.0
     step_size: float = 1e-3
@@ -81,6 +85,18 @@ class DeviceMinimizer:
         """Energy; the projected, fixed-masked gradient stays in MS_ARR_GRAD."""
         return self._total(self.dm.eval(self._opts(want_grad=True)))
 
+    # -- hard volume constraint (constraints/volume.py:116-149) -----------------------------------------
+    def _enforce(self, *, trial: bool, max_iter: int = 3, tol: float = 1e-12) -> None:
+        dm = self.dm
+        target = L.ARR_TRIAL if trial else L.ARR_POSITIONS
+        for _ in range(max_iter):
+            res = dm.eval(dm.options(L.MOD_VOLUME, want_grad=True, use_trial=trial))
+            delta = res.volume - self.v_target
+            if abs(delta) < tol:
+                break
+            lam = delta / (float(res.scalars[L.SC_GC_GC]) + 1e-12)
+            dm.axpy(target, L.ARR_VOLGRAD, -lam, skip_fixed=True)
+
     # -- one line search (line_search.py:267-430) --------------------------------------------------
     def _line_search(self, step_size: float):
         dm = self.dm
@@ -100,6 +116,10 @@ class DeviceMinimizer:
                 if alpha < 1e-8:
                     break
                 continue
+            if self.enforce_volume and self.projection_during_minimization:
+                # line_search.py:449-451: constraint_enforcer(mesh) before the trial energy; the volume module is
+                # skipped there when the projection is left to the drift check (constraint_manager.py:877-885)
+                self._enforce(trial=True)
             trial_energy = self.energy(trial=True)
             if trial_energy <= energy0 + self.c * alpha * g_dot_d:
                 dm.accept_trial()
@@ -115,6 +135,8 @@ class DeviceMinimizer:
         zero_steps = 0
         success = True
         energy = float("nan")
+        if self.enforce_volume and n_steps > 0:  # minimizer.py:1223-1226 (context mesh_operation: 12 iterations)
+            self._enforce(trial=False, max_iter=12)
         for i in range(n_steps):
             energy = self.energy_and_gradient()
             if self.stepper == "cg":
@@ -148,5 +170,14 @@ class DeviceMinimizer:
                     zero_steps = 0
             else:
                 zero_steps = 0
+                if self.enforce_volume and self.volume_mode == "lagrange" and not self.projection_during_minimization:
+                    # minimizer.py:1476-1510: geometric projection only when the volume drifted beyond tolerance
+                    vol = self.dm.eval(self.dm.options(L.MOD_VOLUME, want_grad=False)).volume
+                    if abs(vol - self.v_target) / max(abs(self.v_target), 1.0) > self.volume_tolerance:
+                        self._enforce(trial=False, max_iter=12)
+                        self._cg_have_history = False
+                        self._cg_iter = 0
+        if self.enforce_volume:  # minimizer.py:1518-1521: final projection (context finalize)
+            self._enforce(trial=False, max_iter=12)
         return {"energy": self.energy(), "iterations": n_steps, "terminated_early": False,
                 "step_success": success}

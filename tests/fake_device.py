@@ -104,6 +104,18 @@ class FakeDeviceMesh:
     def direction_from_gradient(self, scale=-1.0):
         self.dir = scale * self.arrays[L.ARR_GRAD]
 
+    def axpy(self, dst, src, alpha, skip_fixed=True):
+        x = self.arrays[src] if src != L.ARR_POSITIONS else self.pos
+        upd = alpha * x
+        if skip_fixed and self.fixed is not None:
+            upd[np.asarray(self.fixed, bool)] = 0.0
+        if dst == L.ARR_POSITIONS:
+            self.pos = self.pos + upd
+        elif dst == L.ARR_TRIAL:
+            self.trial = self.trial + upd
+        else:
+            self.arrays[dst] = self.arrays[dst] + upd
+
     def cg_direction(self, restart):
         g = self.arrays[L.ARR_GRAD]
         if restart or getattr(self, "_pg", None) is None:

@@ -303,6 +303,11 @@ def trajectory_vectors():
         ("cube", os.path.join(REF, "meshes", "cube.json"), 2, 12, None),                 # surface + volume penalty
         ("bcube", os.path.join(REF, "meshes", "bending_cube.yaml"), 1, 6, "no_constraints"),  # + Helfrich bending
         ("cubecg", os.path.join(REF, "meshes", "cube.json"), 2, 14, "cg"),               # conjugate gradient stepper
+        # hard volume constraint, projected in every trial.  (With volume_projection_during_minimization=False the
+        # reference's final projection starts from a STALE volume gradient -- Body.compute_volume refreshes the
+        # cached version but not the cached gradient, geometry/body.py:70-148 vs 401-410 -- so that trajectory is a
+        # property of the reference's host-side cache, kept by the drop-in path but not by the device loop.)
+        ("bcubep", os.path.join(REF, "meshes", "bending_cube.yaml"), 1, 5, "constrained_proj"),
     ):
         mesh = _refined(path, levels)
         rng = np.random.default_rng(11)
@@ -324,7 +329,9 @@ def trajectory_vectors():
             stepper = GradientDescent()
         mini = Minimizer(mesh, gp, stepper, EnergyModuleManager(mesh.energy_modules),
                          ConstraintModuleManager(mesh.constraint_modules), quiet=True)
-        assert not mini._has_enforceable_constraints
+        if tweak == "constrained_proj":
+            gp.set("volume_projection_during_minimization", True)
+        assert mini._has_enforceable_constraints == (tweak in ("constrained", "constrained_proj"))
         st = _dense_state(mesh)
         for k, v in st.items():
             out[f"{name}_{k}"] = v
@@ -346,6 +353,9 @@ def trajectory_vectors():
         out[f"{name}_kappa"] = np.float64(gp.get("bending_modulus", 0.0) or 0.0)
         out[f"{name}_c0"] = np.float64(gp.get("spontaneous_curvature", 0.0) or 0.0)
         out[f"{name}_steps"] = np.int64(steps)
+        out[f"{name}_enforce"] = np.bool_(mini._has_enforceable_constraints)
+        out[f"{name}_proj_flag"] = np.bool_(gp.get("volume_projection_during_minimization", True))
+        out[f"{name}_vol_tol"] = np.float64(gp.get("volume_tolerance", 1e-3))
         print(name, list(mesh.energy_modules), energies[0], energies[-1], mini.step_size)
     np.savez_compressed(os.path.join(HERE, "trajectory.npz"), **out)
 
