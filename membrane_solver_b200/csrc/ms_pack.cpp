@@ -2,7 +2,10 @@
 #include "ms_pack.h"
 
 #include <algorithm>
+#include <atomic>
+#include <cstdlib>
 #include <cstring>
+#include <thread>
 
 namespace ms {
 
@@ -68,38 +71,21 @@ int64_t collect(int32_t v_lo, int32_t n, int32_t stamp, const int32_t* tri,
 
 }  // namespace
 
-int pack_patches(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* body_mask,
-                 const PackParams& prm, PackedMesh& out, int32_t n_owned_vertices) {
-  if (n_owned_vertices < 0 || n_owned_vertices > nv) n_owned_vertices = nv;
-  if (nv < 0 || nf < 0 || (nf > 0 && !tri) || prm.threads <= 0 || prm.max_owned <= 0 ||
-      prm.max_local <= 0 || prm.max_local > 65535 || prm.max_slots < prm.threads || prm.fill_pct < 10 || prm.fill_pct > 100)
-    return -1;
-  out = PackedMesh();
-  out.nv = nv;
-  out.nf = nf;
-  out.params = prm;
-
-  std::vector<int64_t> vptr;
-  std::vector<int32_t> vfac;
-  build_vertex_facets(nv, nf, tri, vptr, vfac);
-  for (int32_t f = 0; f < nf; ++f) out.n_valid += facet_valid(tri + 3 * size_t(f), nv) ? 1 : 0;
-
-  Scratch s;
-  s.facet_stamp.assign(size_t(nf), -1);
-  s.vert_stamp.assign(size_t(nv), -1);
-  s.vert_local.assign(size_t(nv), 0);
+// Packs the patches owning the vertex rows [v_begin, v_end) into `part` (offsets relative to `part`).
+static int pack_range(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* body_mask, const PackParams& prm,
+                      const std::vector<int64_t>& vptr, const std::vector<int32_t>& vfac, int32_t v_begin,
+                      int32_t v_end, PackedMesh& part, Scratch& s, int32_t& stamp) {
+  (void)nv;
+  (void)nf;
 
   const int32_t T = prm.threads;
   std::vector<uint64_t> used;      // per owned vertex: bitmask words of occupied rounds
   std::vector<int32_t> round_fill; // facets already placed in each round
   std::vector<int32_t> round_of;   // per listed facet
-  int32_t stamp = 0;
-
-  out.n_owned_vertices = n_owned_vertices;
   bool too_many_slots = false;
   int32_t forced_n = 0;  // retry size after a patch exceeded the slot capacity
-  for (int32_t v_lo = 0; v_lo < n_owned_vertices;) {
-    int32_t n = std::min(forced_n > 0 ? forced_n : prm.max_owned, n_owned_vertices - v_lo);
+  for (int32_t v_lo = v_begin; v_lo < v_end;) {
+    int32_t n = std::min(forced_n > 0 ? forced_n : prm.max_owned, v_end - v_lo);
     int64_t n_local = collect(v_lo, n, stamp++, tri, vptr, vfac, s);
     while (n_local > prm.max_local && n > 1) {
       n = std::max(1, n / 2);
@@ -319,21 +305,21 @@ int pack_patches(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* body
       PatchHeader h;
       h.v_lo = v_lo;
       h.n_owned = n;
-      h.halo_off = int32_t(out.halo_ids.size());
+      h.halo_off = int32_t(part.halo_ids.size());
       h.n_halo = int32_t(s.halo.size());
-      h.slot_off = int64_t(out.recs.size());
+      h.slot_off = int64_t(part.recs.size());
       h.reserved = 0;
       h.n_rounds = n_rounds;
-      out.patches.push_back(h);
-      out.halo_ids.insert(out.halo_ids.end(), s.halo.begin(), s.halo.end());
+      part.patches.push_back(h);
+      part.halo_ids.insert(part.halo_ids.end(), s.halo.begin(), s.halo.end());
 
-      const size_t base = out.recs.size();
+      const size_t base = part.recs.size();
       const size_t n_slots = size_t(n_rounds) * size_t(T);
       FacetRec empty;
       empty.a = empty.b = empty.c = 0;
       empty.flags = 0;
-      out.recs.resize(base + n_slots, empty);
-      out.slot_facet.resize(base + n_slots, -1);
+      part.recs.resize(base + n_slots, empty);
+      part.slot_facet.resize(base + n_slots, -1);
       for (size_t i = 0; i < nfac; ++i) {
         const int32_t f = s.facets[i];
         const int32_t* t = tri + 3 * size_t(f);
@@ -352,8 +338,8 @@ int pack_patches(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* body
         rec.c = uint16_t(loc[(2 + pl.rot) % 3]);
         rec.flags = flags;
         const size_t slot = base + size_t(remap[pl.r]) * size_t(T) + size_t(pl.hw) * 16 + size_t(pl.lane);
-        out.recs[slot] = rec;
-        out.slot_facet[slot] = f;
+        part.recs[slot] = rec;
+        part.slot_facet[slot] = f;
       }
     }
     if (too_many_slots) {
@@ -362,16 +348,96 @@ int pack_patches(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* body
       continue;
     }
     forced_n = 0;
-    out.n_lane_conflicts += patch_clashes;
+    part.n_lane_conflicts += patch_clashes;
     const size_t n_slots = size_t(n_rounds) * size_t(T);
-    out.max_owned = std::max(out.max_owned, n);
-    out.max_local = std::max(out.max_local, int32_t(n_local));
-    out.max_rounds = std::max(out.max_rounds, n_rounds);
-    out.max_slots = std::max(out.max_slots, int32_t(n_slots));
-    out.n_round_slots += int64_t(n_rounds) * int64_t(T);
-    out.n_listed += int64_t(nfac);
+    part.max_owned = std::max(part.max_owned, n);
+    part.max_local = std::max(part.max_local, int32_t(n_local));
+    part.max_rounds = std::max(part.max_rounds, n_rounds);
+    part.max_slots = std::max(part.max_slots, int32_t(n_slots));
+    part.n_round_slots += int64_t(n_rounds) * int64_t(T);
+    part.n_listed += int64_t(nfac);
     v_lo += n;
   }
+  return 0;
+}
+
+int pack_patches(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* body_mask,
+                 const PackParams& prm, PackedMesh& out, int32_t n_owned_vertices) {
+  if (n_owned_vertices < 0 || n_owned_vertices > nv) n_owned_vertices = nv;
+  if (nv < 0 || nf < 0 || (nf > 0 && !tri) || prm.threads <= 0 || prm.max_owned <= 0 ||
+      prm.max_local <= 0 || prm.max_local > 65535 || prm.max_slots < prm.threads || prm.fill_pct < 10 || prm.fill_pct > 100)
+    return -1;
+  out = PackedMesh();
+  out.nv = nv;
+  out.nf = nf;
+  out.params = prm;
+
+  std::vector<int64_t> vptr;
+  std::vector<int32_t> vfac;
+  build_vertex_facets(nv, nf, tri, vptr, vfac);
+  for (int32_t f = 0; f < nf; ++f) out.n_valid += facet_valid(tri + 3 * size_t(f), nv) ? 1 : 0;
+
+  out.n_owned_vertices = n_owned_vertices;
+  // Chunks of 32 * max_owned vertex rows are packed independently (the chunk size, not the thread count,
+  // decides the patch boundaries, so the layout is the same on every host) and concatenated in order.
+  const int64_t chunk = int64_t(32) * int64_t(prm.max_owned);
+  const int64_t n_chunks = (int64_t(n_owned_vertices) + chunk - 1) / chunk;
+  std::vector<PackedMesh> parts(size_t(std::max<int64_t>(n_chunks, 0)));
+  std::vector<int> rcs(parts.size(), 0);
+  unsigned hw = std::thread::hardware_concurrency();
+  if (hw == 0) hw = 1;
+  if (const char* env = std::getenv("MS_PACK_THREADS")) {  // tuning / debugging knob
+    const int v = std::atoi(env);
+    if (v > 0) hw = unsigned(v);
+  }
+  // every worker owns stamp arrays of nf + 2 nv int32: keep their sum below ~6 GB
+  const double per_worker = 4.0 * (double(nf) + 2.0 * double(nv)) + 1.0;
+  const unsigned cap = unsigned(std::max(1.0, 6.0e9 / per_worker));
+  const unsigned n_workers = unsigned(std::max<int64_t>(1, std::min<int64_t>(std::min(hw, cap), n_chunks)));
+  std::atomic<int64_t> next(0);
+  auto work = [&]() {
+    Scratch s;  // stamp arrays live for the whole worker: the stamp counter keeps growing across chunks
+    s.facet_stamp.assign(size_t(nf), -1);
+    s.vert_stamp.assign(size_t(nv), -1);
+    s.vert_local.assign(size_t(nv), 0);
+    int32_t stamp = 0;
+    for (;;) {
+      const int64_t c = next.fetch_add(1);
+      if (c >= n_chunks) break;
+      const int32_t vb = int32_t(c * chunk), ve = int32_t(std::min<int64_t>((c + 1) * chunk, n_owned_vertices));
+      rcs[size_t(c)] = pack_range(nv, nf, tri, body_mask, prm, vptr, vfac, vb, ve, parts[size_t(c)], s, stamp);
+    }
+  };
+  if (n_workers <= 1) {
+    work();
+  } else {
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < n_workers; ++t) pool.emplace_back(work);
+    for (auto& th : pool) th.join();
+  }
+  for (int rc : rcs)
+    if (rc) return rc;
+  for (PackedMesh& part : parts) {
+    const int32_t halo_base = int32_t(out.halo_ids.size());
+    const int64_t slot_base = int64_t(out.recs.size());
+    for (PatchHeader h : part.patches) {
+      h.halo_off += halo_base;
+      h.slot_off += slot_base;
+      out.patches.push_back(h);
+    }
+    out.halo_ids.insert(out.halo_ids.end(), part.halo_ids.begin(), part.halo_ids.end());
+    out.recs.insert(out.recs.end(), part.recs.begin(), part.recs.end());
+    out.slot_facet.insert(out.slot_facet.end(), part.slot_facet.begin(), part.slot_facet.end());
+    out.max_owned = std::max(out.max_owned, part.max_owned);
+    out.max_local = std::max(out.max_local, part.max_local);
+    out.max_rounds = std::max(out.max_rounds, part.max_rounds);
+    out.max_slots = std::max(out.max_slots, part.max_slots);
+    out.n_round_slots += part.n_round_slots;
+    out.n_listed += part.n_listed;
+    out.n_lane_conflicts += part.n_lane_conflicts;
+    part = PackedMesh();  // release
+  }
+  const int32_t T = prm.threads;
   // exact statistic: extra shared-memory wavefronts per (round, half-warp, corner position) =
   // (largest number of DISTINCT local indices sharing one residue mod 16) - 1
   out.n_hw_groups = 0;

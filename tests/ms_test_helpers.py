@@ -45,7 +45,7 @@ def build_emulator():
     deps = [src] + [os.path.join(csrc, f) for f in ("ms_pack.cpp", "ms_pack.h", "ms_math.cuh", "ms_patch_body.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", out, src,
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-fPIC", "-shared", "-o", out, src,
                                os.path.join(csrc, "ms_pack.cpp")])
     return out
 
