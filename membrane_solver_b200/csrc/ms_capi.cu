@@ -496,9 +496,17 @@ int ms_ctx_set_topology_partition(ms_ctx* c, int32_t nv, int32_t n_owned, int32_
     CU(cudaMemcpy(c->d_perm.p, c->perm.data(), size_t(nv) * sizeof(int32_t), cudaMemcpyHostToDevice));
     if (int rc = c->d_stage.ensure(size_t(ms::kSeedStride) * size_t(nv))) return rc;
   }
-  const int prc = ms::pack_patches(nv, nf, tri, body_mask, c->pack_params, c->packed, n_owned);
+  // A vertex of valence V needs V rounds, i.e. V * threads record slots, and a patch holds at most
+  // kPatchSlotCap of them: meshes with high-valence vertices (a disk centre, a cone apex) are packed with
+  // narrower rounds (96 -> 64 -> 32 lanes: valence up to 16 / 24 / 48).
+  ms::PackParams used_params = c->pack_params;
+  int prc = ms::pack_patches(nv, nf, tri, body_mask, used_params, c->packed, n_owned);
+  while (prc == -3 && used_params.threads > 32) {
+    used_params.threads = used_params.threads > 64 ? 64 : 32;
+    prc = ms::pack_patches(nv, nf, tri, body_mask, used_params, c->packed, n_owned);
+  }
   if (prc == -2) return fail(-8, "a vertex neighbourhood exceeds max_local; raise it with ms_ctx_set_pack_params");
-  if (prc == -3) return fail(-8, "a vertex neighbourhood needs more record slots than a patch can hold");
+  if (prc == -3) return fail(-8, "a vertex has more than 48 incident facets: its rounds do not fit a patch");
   if (prc) return fail(-1, "pack_patches failed");
   c->nv = nv;
   c->nf = nf;

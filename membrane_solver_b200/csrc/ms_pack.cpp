@@ -331,6 +331,7 @@ static int pack_range(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t*
         uint16_t flags = REC_VALID;
         if (t[0] >= v_lo && t[0] < v_hi) flags |= REC_PRIMARY;
         if (body_mask && body_mask[f]) flags |= REC_BODY;
+        if (t[0] == t[1] || t[1] == t[2] || t[0] == t[2]) flags |= REC_REPEAT;
         const Place& pl = place[i];
         FacetRec rec;
         rec.a = uint16_t(loc[pl.rot % 3]);

@@ -32,14 +32,16 @@ static_assert(sizeof(PatchHeader) == 32, "PatchHeader layout");
 
 // One record slot.  flags bit0: valid (0 marks an empty slot); bit1: primary (this patch owns
 // the facet's first vertex, so per-facet scalars are summed here exactly once); bit2: facet
-// belongs to the body.  (a,b,c) may be a cyclic rotation of the facet's vertex order.
+// belongs to the body; bit3: repeated vertex.  (a,b,c) may be a cyclic rotation of the facet's vertex order.
 struct FacetRec {
   uint16_t a, b, c;  // patch-local vertex indices (owned first, then halo)
   uint16_t flags;
 };
 static_assert(sizeof(FacetRec) == 8, "FacetRec layout");
 
-enum : uint16_t { REC_VALID = 1, REC_PRIMARY = 2, REC_BODY = 4 };
+// REC_REPEAT: two corners of the facet are the same vertex (degenerate input): its read-modify-writes must
+// not be batched.
+enum : uint16_t { REC_VALID = 1, REC_PRIMARY = 2, REC_BODY = 4, REC_REPEAT = 8 };
 
 struct PackParams {
   int32_t threads = 96;      // record slots per round (= lanes of one consumer group)

@@ -560,3 +560,44 @@ def test_split_interior_boundary_evaluation(L):
     assert rel_err(g1, whole.download(L.ARR_GRAD)[rows[:lm.n_owned]]) <= 1e-13
     dm.close()
     whole.close()
+
+
+def test_random_soups_with_repeated_and_wild_indices(L):
+    """Random triangle soups through the PATCH path: repeated vertices inside a facet, facets listed
+    twice, out-of-range indices, isolated vertices, a very high valence vertex -- against the oracle."""
+    from oracle import ref_modules as ref
+
+    rng = np.random.default_rng(123)
+    for trial in range(6):
+        nv = int(rng.integers(40, 400))
+        nf = int(rng.integers(nv, 3 * nv))                             # mean valence 3..9, tails to ~25
+        pos = rng.normal(size=(nv, 3))
+        tri = rng.integers(0, nv - 5, size=(nf, 3)).astype(np.int32)   # the last 5 vertices stay isolated
+        tri[rng.integers(0, nf, 8), 1] = tri[rng.integers(0, nf, 8), 0]   # some facets name a vertex twice ...
+        rep = rng.integers(0, nf, 5)
+        tri[rep, 1] = tri[rep, 0]                                           # ... for sure
+        tri[rng.integers(0, nf, 4)] = tri[rng.integers(0, nf, 4)]           # duplicated facets
+        tri[:28, 0] = 3                                                     # a hub of valence ~30 (needs narrow rounds)
+        bad = tri.copy()
+        bad[1, 2] = nv + 7
+        bad[2, 0] = -3
+        gamma = 0.5 + rng.random(nf)
+        for t in (tri, bad):
+            ok = np.all((t >= 0) & (t < nv), axis=1)
+            tv, gv = np.ascontiguousarray(t[ok]), gamma[ok]
+            for is_b in (ref.boundary_mask_from_triangles(tv, nv), np.zeros(nv, bool)):
+                want_g = np.zeros_like(pos)
+                e_s = ref.surface_energy_and_gradient(pos, tv, gv, want_g)
+                e_b = ref.bending_energy_and_gradient(pos, tv, 1.3, 0.2, is_b, want_g)
+                dm = _ctx(nv, t, is_boundary=is_b.astype(np.uint8) if is_b.any() else None,
+                          body_mask=np.ones(nf, np.uint8), threads=32 * int(rng.integers(1, 4)), max_owned=64,
+                          max_local=600)
+                dm.set_surface_tension(gamma)
+                dm.set_bending_params(1.3, 0.2)
+                grad = np.empty_like(pos)
+                r = dm.eval_host(dm.options(L.MOD_SURFACE | L.MOD_BENDING | L.MOD_VOLUME), pos, grad=grad)
+                _scalar_close(r.e_surface, e_s, 1e-12)
+                _scalar_close(r.e_bending, e_b, 1e-11)
+                _scalar_close(r.volume, ref.body_volume(pos, tv), 1e-12)
+                assert rel_err(grad, want_g) <= 1e-11
+                dm.close()
