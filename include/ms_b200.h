@@ -121,9 +121,6 @@ MS_API int ms_ctx_set_pack_tuning(ms_ctx* ctx, int32_t fill_pct, int32_t repair_
 /* launch at most max_ctas persistent CTAs per pass (0 = one per SM): a partitioned evaluation leaves a
  * few SMs to the NCCL kernels of the halo exchange that runs concurrently */
 MS_API int ms_ctx_set_max_ctas(ms_ctx* ctx, int32_t max_ctas);
-/* kept for ABI stability; the persistent kernels derive the thread-group count from the CTA
- * size (consumer threads / threads-per-round) */
-MS_API int ms_ctx_set_groups(ms_ctx* ctx, int32_t groups_a, int32_t groups_b);
 /* Optional: positions (nv,3) used ONLY to choose the internal vertex order of the next
  * ms_ctx_set_topology (Morton curve), so that meshes in arbitrary vertex order -- e.g. the
  * refinement order of runtime/refinement.py -- still pack into compact patches.  Transparent to

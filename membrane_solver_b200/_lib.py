@@ -81,7 +81,6 @@ SIGNATURES = {
     "ms_ctx_set_pack_params": (ctypes.c_int, [_V, _i32, _i32, _i32]),
     "ms_ctx_set_pack_tuning": (ctypes.c_int, [_V, _i32, _i32]),
     "ms_ctx_set_max_ctas": (ctypes.c_int, [_V, _i32]),
-    "ms_ctx_set_groups": (ctypes.c_int, [_V, _i32, _i32]),
     "ms_ctx_set_vertex_order_hint": (ctypes.c_int, [_V, _i32, _D]),
     "ms_ctx_get_permutation": (ctypes.c_int, [_V, _I]),
     "ms_ctx_set_topology": (ctypes.c_int, [_V, _i32, _i32, _I, _B, _B, _B]),

@@ -67,7 +67,7 @@ class DeviceMesh:
     """One mesh resident on one GPU."""
 
     def __init__(self, device: int = 0, *, threads: int | None = None, max_owned: int | None = None,
-                 max_local: int | None = None, groups: tuple[int, int] | None = None,
+                 max_local: int | None = None,
                  fill_pct: int | None = None, repair_sweeps: int | None = None):
         self._lib = L.lib()
         handle = ctypes.c_void_p()
@@ -80,8 +80,6 @@ class DeviceMesh:
         if threads is not None or max_owned is not None or max_local is not None:
             L.check(self._lib.ms_ctx_set_pack_params(self._h, int(threads or 96), int(max_owned or 512),
                                                      int(max_local or 896)))
-        if groups is not None:
-            L.check(self._lib.ms_ctx_set_groups(self._h, int(groups[0]), int(groups[1])))
         if fill_pct is not None or repair_sweeps is not None:
             L.check(self._lib.ms_ctx_set_pack_tuning(self._h, int(87 if fill_pct is None else fill_pct),
                                                      int(1 if repair_sweeps is None else repair_sweeps)))

@@ -440,13 +440,6 @@ int ms_ctx_set_max_ctas(ms_ctx* c, int32_t max_ctas) {
   return 0;
 }
 
-int ms_ctx_set_groups(ms_ctx* c, int32_t groups_a, int32_t groups_b) {
-  // kept for ABI stability: the persistent kernels derive the group count from the CTA size
-  if (!c) return fail(-1, "null context");
-  if (groups_a < 1 || groups_a > 8 || groups_b < 1 || groups_b > 8) return fail(-1, "groups must be in [1,8]");
-  return 0;
-}
-
 int ms_ctx_set_vertex_order_hint(ms_ctx* c, int32_t nv, const double* pos) {
   if (!c) return fail(-1, "null context");
   c->order_hint.clear();
