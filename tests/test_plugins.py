@@ -212,3 +212,24 @@ def test_residency_follows_the_version_counters(backend):
     mesh.set_triangles(g["tri"][:-2])   # what refine / equiangulate do: topology version bump
     surface.compute_energy_array(mesh, gp, positions=pos, index_map=idx)
     assert st.uploads == 2 and st.nf == g["tri"].shape[0] - 2
+
+
+def test_array_refinement_matches_reference_hierarchy():
+    """1 -> 4 refinement on arrays: counts of the 24 * 4^k hierarchy, closedness,
+    orientation (volume stays +1), inherited fixed flags."""
+    from membrane_solver_b200.geometry.refine import cube_mesh, refine_triangles
+
+    pos, tri = cube_mesh()
+    assert pos.shape == (14, 3) and tri.shape == (24, 3)
+    fixed = np.zeros(14, bool)
+    fixed[[0, 1]] = True
+    for k in range(1, 4):
+        pos, tri, fixed, parent = refine_triangles(pos, tri, fixed)
+        assert tri.shape[0] == 24 * 4**k and pos.shape[0] == 12 * 4**k + 2
+        assert parent.shape == (tri.shape[0],) and parent.max() == 24 * 4 ** (k - 1) - 1
+        v = pos[tri]
+        vol = np.einsum("ij,ij->i", np.cross(v[:, 1], v[:, 2]), v[:, 0]).sum() / 6.0
+        area = 0.5 * np.linalg.norm(np.cross(v[:, 1] - v[:, 0], v[:, 2] - v[:, 0]), axis=1).sum()
+        assert abs(vol - 1.0) < 1e-14 and abs(area - 6.0) < 1e-13
+        assert not ArrayMesh(pos, tri).boundary_vertex_ids          # closed
+        assert fixed.sum() == 2 + (2**k - 1)                         # the refined edge 0-1 stays fixed
