@@ -14,7 +14,7 @@ import subprocess
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libms_b200.so")
+LIB_PATH = os.environ.get("MS_B200_LIB") or os.path.join(_PKG, "libms_b200.so")  # override: A/B builds
 CSRC = os.path.join(_PKG, "csrc")
 
 MOD_SURFACE, MOD_VOLUME, MOD_BENDING, MOD_TILT, MOD_BENDING_TILT = 1, 2, 4, 8, 16

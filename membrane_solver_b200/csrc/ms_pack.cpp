@@ -15,13 +15,18 @@ inline bool facet_valid(const int32_t* t, int32_t nv) {
   return t[0] >= 0 && t[0] < nv && t[1] >= 0 && t[1] < nv && t[2] >= 0 && t[2] < nv;
 }
 
+// listed by the patches: valid and naming three different vertices (see ms_pack.h)
+inline bool facet_listed(const int32_t* t, int32_t nv) {
+  return facet_valid(t, nv) && t[0] != t[1] && t[1] != t[2] && t[0] != t[2];
+}
+
 // vertex -> incident valid facets (a facet appears once per corner it has at the vertex)
 void build_vertex_facets(int32_t nv, int32_t nf, const int32_t* tri, std::vector<int64_t>& ptr,
                          std::vector<int32_t>& fac) {
   ptr.assign(size_t(nv) + 1, 0);
   for (int32_t f = 0; f < nf; ++f) {
     const int32_t* t = tri + 3 * size_t(f);
-    if (!facet_valid(t, nv)) continue;
+    if (!facet_listed(t, nv)) continue;
     for (int k = 0; k < 3; ++k) ++ptr[size_t(t[k]) + 1];
   }
   for (int32_t v = 0; v < nv; ++v) ptr[size_t(v) + 1] += ptr[v];
@@ -29,7 +34,7 @@ void build_vertex_facets(int32_t nv, int32_t nf, const int32_t* tri, std::vector
   std::vector<int64_t> cur(ptr.begin(), ptr.end() - 1);
   for (int32_t f = 0; f < nf; ++f) {
     const int32_t* t = tri + 3 * size_t(f);
-    if (!facet_valid(t, nv)) continue;
+    if (!facet_listed(t, nv)) continue;
     for (int k = 0; k < 3; ++k) fac[size_t(cur[t[k]]++)] = f;
   }
 }
@@ -331,7 +336,6 @@ static int pack_range(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t*
         uint16_t flags = REC_VALID;
         if (t[0] >= v_lo && t[0] < v_hi) flags |= REC_PRIMARY;
         if (body_mask && body_mask[f]) flags |= REC_BODY;
-        if (t[0] == t[1] || t[1] == t[2] || t[0] == t[2]) flags |= REC_REPEAT;
         const Place& pl = place[i];
         FacetRec rec;
         rec.a = uint16_t(loc[pl.rot % 3]);

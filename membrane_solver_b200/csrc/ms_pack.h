@@ -32,16 +32,14 @@ static_assert(sizeof(PatchHeader) == 32, "PatchHeader layout");
 
 // One record slot.  flags bit0: valid (0 marks an empty slot); bit1: primary (this patch owns
 // the facet's first vertex, so per-facet scalars are summed here exactly once); bit2: facet
-// belongs to the body; bit3: repeated vertex.  (a,b,c) may be a cyclic rotation of the facet's vertex order.
+// belongs to the body.  (a,b,c) may be a cyclic rotation of the facet's vertex order.
 struct FacetRec {
   uint16_t a, b, c;  // patch-local vertex indices (owned first, then halo)
   uint16_t flags;
 };
 static_assert(sizeof(FacetRec) == 8, "FacetRec layout");
 
-// REC_REPEAT: two corners of the facet are the same vertex (degenerate input): its read-modify-writes must
-// not be batched.
-enum : uint16_t { REC_VALID = 1, REC_PRIMARY = 2, REC_BODY = 4, REC_REPEAT = 8 };
+enum : uint16_t { REC_VALID = 1, REC_PRIMARY = 2, REC_BODY = 4 };
 
 struct PackParams {
   int32_t threads = 96;      // record slots per round (= lanes of one consumer group)
@@ -70,7 +68,9 @@ struct PackedMesh {
 };
 
 // body_mask: nf bytes (nonzero = facet in the body) or nullptr (no facet flagged).
-// Facets with an index outside [0,nv) are skipped, like surface_energy.f90:57-59.
+// Facets with an index outside [0,nv) are skipped, like surface_energy.f90:57-59; so are facets that name
+// one vertex twice: they have zero area and volume and their curvature / gradient contributions vanish
+// identically (every term carries a factor e_k = 0 or fK_i - fK_i = 0), in the reference as well.
 // Returns 0, or a negative error code (-1 bad arguments, -2 a single vertex needs
 // more than max_local local vertices, -3 a single vertex needs more than max_slots slots).
 // n_owned_vertices (multi-GPU partitions): only vertex rows [0, n_owned_vertices) are owned

@@ -90,20 +90,13 @@ MS_HD CornerA facet_compute_a(const S& st, FacetRec rec, double gam, const Local
 }
 
 // Read-modify-write of the three corners' accumulator rows.  All loads are issued before the
-// first store: the three rows are distinct for owned corners, and a collision can only happen
-// between two halo corners sharing a dump row, whose content is never read -- so the loads of
-// one corner need not wait for the stores of another (shortest possible token hold time).
+// first store: the three rows are distinct for owned corners (facets naming a vertex twice are
+// never listed, ms_pack.cpp), and a collision can only happen between two halo corners sharing a
+// dump row, whose content is never read -- so the loads of one corner need not wait for the stores
+// of another (shortest possible token hold time).
 template <int N>
 MS_HD void rmw3(double* base, int stride, int ia, int ib, int ic, const double (&ca)[N], const double (&cb)[N],
-                const double (&cc)[N], bool repeated) {
-  if (repeated) {  // a facet naming one vertex twice (degenerate input): plain sequential updates
-    for (int k = 0; k < N; ++k) {
-      base[k * stride + ia] += ca[k];
-      base[k * stride + ib] += cb[k];
-      base[k * stride + ic] += cc[k];
-    }
-    return;
-  }
+                const double (&cc)[N]) {
   double xa[N], xb[N], xc[N];
 #pragma unroll
   for (int k = 0; k < N; ++k) {
@@ -126,7 +119,7 @@ MS_HD void facet_accumulate_a(const S& st, FacetRec rec, const CornerA& c, const
     const double ca[5] = {c.K0.x, c.K0.y, c.K0.z, c.va0, c.ve0};
     const double cb[5] = {c.K1.x, c.K1.y, c.K1.z, c.va1, c.ve1};
     const double cc[5] = {c.K2.x, c.K2.y, c.K2.z, c.va2, c.ve2};
-    rmw3<5>(s.acc, st.A, ia, ib, ic, ca, cb, cc, (rec.flags & REC_REPEAT) != 0);
+    rmw3<5>(s.acc, st.A, ia, ib, ic, ca, cb, cc);
   }
 }
 
@@ -231,13 +224,13 @@ MS_HD void facet_accumulate_b(const S& st, FacetRec rec, const FacetOutB& o, con
     const double ca[3] = {o.cg.g0.x, o.cg.g0.y, o.cg.g0.z};
     const double cb[3] = {o.cg.g1.x, o.cg.g1.y, o.cg.g1.z};
     const double cc[3] = {o.cg.g2.x, o.cg.g2.y, o.cg.g2.z};
-    rmw3<3>(s.acc, st.A, ia, ib, ic, ca, cb, cc, (rec.flags & REC_REPEAT) != 0);
+    rmw3<3>(s.acc, st.A, ia, ib, ic, ca, cb, cc);
   }
   if (do_volume && o.in_body) {
     const double ca[3] = {o.vg.g0.x, o.vg.g0.y, o.vg.g0.z};
     const double cb[3] = {o.vg.g1.x, o.vg.g1.y, o.vg.g1.z};
     const double cc[3] = {o.vg.g2.x, o.vg.g2.y, o.vg.g2.z};
-    rmw3<3>(s.acc + 3 * st.A, st.A, ia, ib, ic, ca, cb, cc, (rec.flags & REC_REPEAT) != 0);
+    rmw3<3>(s.acc + 3 * st.A, st.A, ia, ib, ic, ca, cb, cc);
   }
   if (do_tilt && o.third != 0.0) {
     s.accAb[ia] += o.third;
