@@ -337,6 +337,32 @@ def bench_multi_gpu(args, rank: int, world: int, local_rank: int, bench):
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_step = float(ms.item()) / args.steps
     res = dm.read_scalars()
+    phases = None
+    if os.environ.get("MS_PHASES", "0") != "0":  # per-phase device times of this rank (diagnostic)
+        names = ["halo(pos)", "pass A", "halo(seeds)", "pass B", "reduce", "all-reduce", "project"]
+        acc = np.zeros(len(names))
+        reps = 10
+        for _ in range(reps):
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+            evs[0].record(); pm.exchange(L.ARR_POSITIONS)
+            evs[1].record(); dm.eval_pass_a(opts)
+            evs[2].record(); pm.exchange(L.ARR_SEEDS)
+            evs[3].record(); dm.eval_pass_b(opts)
+            evs[4].record(); dm.eval_reduce(opts)
+            evs[5].record(); dist.all_reduce(pm.view(L.ARR_SCALARS)[:12])
+            evs[6].record(); dm.eval_project(opts)
+            evs[7].record(); torch.cuda.synchronize()
+            acc += [evs[i].elapsed_time(evs[i + 1]) for i in range(len(names))]
+        mine = torch.tensor(acc / reps, dtype=torch.float64, device=pm.device)
+        allp = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allp, mine)
+        info = dm.pack_info()
+        stats = torch.tensor([info["n_listed"], info["n_patches"], local.tri.shape[0], local.nv_local],
+                             dtype=torch.float64, device=pm.device)
+        alls = [torch.zeros_like(stats) for _ in range(world)]
+        dist.all_gather(alls, stats)
+        phases = {"names": names, "ms_per_rank": [[round(float(x), 4) for x in t.tolist()] for t in allp],
+                  "listed_patches_facets_rows_per_rank": [[int(x) for x in t.tolist()] for t in alls]}
     # ---- end to end: pinned host positions of the owned rows in, projected gradient out, every step ----
     lib = L.lib()
     pos_owned = np.ascontiguousarray(pos_local[:local.n_owned])
@@ -389,6 +415,8 @@ def bench_multi_gpu(args, rank: int, world: int, local_rank: int, bench):
             "energies": {"surface": res.e_surface, "bending": res.e_bending, "volume": res.volume},
             "setup_seconds": t_gen,
         }
+        if phases is not None:
+            line["phases"] = phases
         print(json.dumps(line))
     dist.destroy_process_group()
     return 0
