@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <numeric>
 #include <cstring>
 #include <string>
@@ -91,6 +92,13 @@ struct ms_ctx {
   DevBuf<int32_t> d_patch_order;
   int32_t n_interior = 0;
   int32_t max_ctas = 0;  // 0 = one persistent CTA per SM
+  // pipelined host evaluation: chunks of the position upload overlap the patch kernels.  orderA lists the
+  // patches by the last vertex row they read; orderB by how many orderA patches must have run pass A first.
+  bool pipe_ready = false;
+  std::vector<int32_t> pipe_need_a, pipe_need_b;  // sorted keys of orderA / orderB
+  DevBuf<int32_t> d_order_a, d_order_b;
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> pipe_events;
   // internal vertex order: row i of every device array holds the caller's vertex perm[i]
   std::vector<double> order_hint;       // positions given by ms_ctx_set_vertex_order_hint (consumed by set_topology)
   std::vector<int32_t> perm;            // new -> old; empty = identity
@@ -403,6 +411,9 @@ int ms_ctx_destroy(ms_ctx* c) {
   if (c->ev1) cudaEventDestroy(c->ev1);
   for (cudaEvent_t e : c->events)
     if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->pipe_events)
+    if (e) cudaEventDestroy(e);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   delete c;
   return 0;
 }
@@ -506,6 +517,7 @@ int ms_ctx_set_topology_partition(ms_ctx* c, int32_t nv, int32_t n_owned, int32_
   c->h_tri.assign(tri, tri + 3 * size_t(nf));
   c->bt_ready = false;
   c->tri_ready = false;
+  c->pipe_ready = false;
   const ms::PackedMesh& pk = c->packed;
   const size_t np = pk.patches.size();
   c->v_lo.resize(np + 1);
@@ -566,8 +578,9 @@ int ms_ctx_set_topology_partition(ms_ctx* c, int32_t nv, int32_t n_owned, int32_
   if (int rc = c->d_grad.ensure(n3)) return rc;
   if (int rc = c->d_volgrad.ensure(n3)) return rc;
   if (int rc = c->d_seeds.ensure(size_t(ms::kSeedStride) * size_t(nv))) return rc;
-  {  // one row of running sums per persistent CTA and pass (at most one CTA per SM; 1024 is ample)
-    const size_t rows = 1024;
+  {  // one row of running sums per persistent CTA, pass and sub-launch (the pipelined host evaluation
+     // issues up to 2 x 9 sub-launches of <= 148 CTAs)
+    const size_t rows = 4096;
     if (int rc = c->d_partials_a.ensure(rows * ms::kPartialStride)) return rc;
     if (int rc = c->d_partials_b.ensure(rows * ms::kPartialStride)) return rc;
     CU(cudaMemset(c->d_partials_a.p, 0, rows * ms::kPartialStride * sizeof(double)));
@@ -802,6 +815,21 @@ int ms_ctx_eval_finish(ms_ctx* c, const ms_eval_opts* o) {
   return ms_ctx_eval_project(c, o);
 }
 
+static int reduce_rows(ms_ctx* c, const ms_eval_opts* o, int rows_a, int rows_b) {
+  // energies, area, volume come from pass A when it ran, else from pass B; <g,g>, <g,gC>, <gC,gC>
+  // and the tilt energy come from pass B when a gradient was requested -- one fixed-order sum
+  const bool ran_a = needs_bending(o) || !o->want_grad;
+  unsigned b_mask = 0;
+  if (o->want_grad) {
+    b_mask = (1u << MS_SC_G_G) | (1u << MS_SC_G_GC) | (1u << MS_SC_GC_GC);
+    if (!ran_a) b_mask = 0xfffu;
+  }
+  CU(ms::launch_reduce_partials(c->d_partials_a.p, ran_a ? rows_a : 0, c->d_partials_b.p, o->want_grad ? rows_b : 0,
+                                b_mask, c->d_scalars.p, c->stream));
+  if (has_bt(o)) CU(ms::launch_bt_finalize(c->d_bt_e.p, c->d_scalars.p, c->stream));
+  return 0;
+}
+
 int ms_ctx_eval_reduce(ms_ctx* c, const ms_eval_opts* o) {
   if (int rc = check_ctx(c, true)) return rc;
   if (!o) return fail(-1, "null options");
@@ -815,18 +843,7 @@ int ms_ctx_eval_reduce(ms_ctx* c, const ms_eval_opts* o) {
     outer.patch_count = int(c->packed.patches.size()) - c->n_interior;
     rows = ms::patch_grid(inner) + ms::patch_grid(outer);
   }
-  // energies, area, volume come from pass A when it ran, else from pass B; <g,g>, <g,gC>, <gC,gC>
-  // and the tilt energy come from pass B when a gradient was requested -- one fixed-order sum
-  const bool ran_a = needs_bending(o) || !o->want_grad;
-  unsigned b_mask = 0;
-  if (o->want_grad) {
-    b_mask = (1u << MS_SC_G_G) | (1u << MS_SC_G_GC) | (1u << MS_SC_GC_GC);
-    if (!ran_a) b_mask = 0xfffu;
-  }
-  CU(ms::launch_reduce_partials(c->d_partials_a.p, ran_a ? rows : 0, c->d_partials_b.p, o->want_grad ? rows : 0,
-                                b_mask, c->d_scalars.p, c->stream));
-  if (has_bt(o)) CU(ms::launch_bt_finalize(c->d_bt_e.p, c->d_scalars.p, c->stream));
-  return 0;
+  return reduce_rows(c, o, rows, rows);
 }
 
 int ms_ctx_eval_project(ms_ctx* c, const ms_eval_opts* o) {
@@ -861,14 +878,153 @@ int ms_ctx_eval(ms_ctx* c, const ms_eval_opts* o, double* scalars16) {
   return ms_ctx_read_scalars(c, scalars16);
 }
 
+// ---- pipelined host evaluation ---------------------------------------------------------------------
+// The positions travel in chunks of rows; a patch can run pass A as soon as every row it reads has
+// arrived, and pass B as soon as pass A has run for every patch that owns one of its local vertices.
+static int pipe_prepare(ms_ctx* c) {
+  if (c->pipe_ready) return 0;
+  const ms::PackedMesh& pk = c->packed;
+  const int32_t np = int32_t(pk.patches.size());
+  std::vector<int32_t> need_a(size_t(np), 0), pos_a(size_t(np), 0), order_a(size_t(np), 0), order_b(size_t(np), 0),
+      need_b(size_t(np), 0);
+  for (int32_t p = 0; p < np; ++p) {
+    const ms::PatchHeader& h = pk.patches[size_t(p)];
+    int32_t m = h.v_lo + h.n_owned;
+    for (int32_t j = 0; j < h.n_halo; ++j) m = std::max(m, pk.halo_ids[size_t(h.halo_off) + size_t(j)] + 1);
+    need_a[size_t(p)] = m;
+  }
+  std::iota(order_a.begin(), order_a.end(), 0);
+  std::stable_sort(order_a.begin(), order_a.end(), [&](int32_t x, int32_t y) { return need_a[size_t(x)] < need_a[size_t(y)]; });
+  for (int32_t i = 0; i < np; ++i) pos_a[size_t(order_a[size_t(i)])] = i;
+  for (int32_t p = 0; p < np; ++p) {
+    const ms::PatchHeader& h = pk.patches[size_t(p)];
+    int32_t m = pos_a[size_t(p)];
+    for (int32_t j = 0; j < h.n_halo; ++j) {
+      const int32_t v = pk.halo_ids[size_t(h.halo_off) + size_t(j)];
+      // the patch owning vertex v: last patch with v_lo <= v
+      const int32_t q = int32_t(std::upper_bound(c->v_lo.begin(), c->v_lo.begin() + np, v) - c->v_lo.begin()) - 1;
+      if (q >= 0) m = std::max(m, pos_a[size_t(q)]);
+    }
+    need_b[size_t(p)] = m + 1;  // number of orderA patches that must have been launched
+  }
+  std::iota(order_b.begin(), order_b.end(), 0);
+  std::stable_sort(order_b.begin(), order_b.end(), [&](int32_t x, int32_t y) { return need_b[size_t(x)] < need_b[size_t(y)]; });
+  c->pipe_need_a.resize(size_t(np));
+  c->pipe_need_b.resize(size_t(np));
+  for (int32_t i = 0; i < np; ++i) {
+    c->pipe_need_a[size_t(i)] = need_a[size_t(order_a[size_t(i)])];
+    c->pipe_need_b[size_t(i)] = need_b[size_t(order_b[size_t(i)])];
+  }
+  if (int rc = c->d_order_a.ensure(size_t(np) + 1)) return rc;
+  if (int rc = c->d_order_b.ensure(size_t(np) + 1)) return rc;
+  if (np) {
+    CU(cudaMemcpy(c->d_order_a.p, order_a.data(), size_t(np) * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_order_b.p, order_b.data(), size_t(np) * sizeof(int32_t), cudaMemcpyHostToDevice));
+  }
+  if (!c->copy_stream) CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  c->pipe_ready = true;
+  return 0;
+}
+
+constexpr int kPipeChunks = 8;
+
+static bool pipe_applicable(const ms_ctx* c, const ms_eval_opts* o, const double* pos_host) {
+  static const bool disabled = std::getenv("MS_NO_PIPELINE") != nullptr;
+  return !disabled && pos_host && c->perm.empty() && c->n_owned == c->nv && !has_bt(o) && !(o->modules & MS_MOD_TILT) && !o->want_tilt_grad &&
+         o->patch_count == -1 &&
+         c->nv >= 200000 && c->packed.patches.size() >= 64;
+}
+
+// upload + pass A + pass B, overlapped; leaves the per-CTA sums in rows [0, rows_a) / [0, rows_b)
+static int eval_pipelined(ms_ctx* c, const ms_eval_opts* o, const double* pos_host, int& rows_a, int& rows_b) {
+  if (int rc = pipe_prepare(c)) return rc;
+  if (o->use_trial)
+    if (int rc = ensure_array(c, MS_ARR_TRIAL)) return rc;
+  ms::PatchLaunch base;
+  if (int rc = fill_launch(c, o, base)) return rc;
+  const int32_t np = int32_t(c->packed.patches.size());
+  const bool ran_a = needs_bending(o) || !o->want_grad;
+  c->ran_pass_a = ran_a;
+  double* dst = o->use_trial ? c->d_trial.p : c->d_pos.p;
+  while (c->pipe_events.size() < size_t(kPipeChunks) + 1) {
+    cudaEvent_t e = nullptr;
+    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->pipe_events.push_back(e);
+  }
+  // the copies may start once everything queued so far (readers of the old positions) has finished
+  CU(cudaEventRecord(c->pipe_events[size_t(kPipeChunks)], c->stream));
+  CU(cudaStreamWaitEvent(c->copy_stream, c->pipe_events[size_t(kPipeChunks)], 0));
+  const int64_t nv = c->nv;
+  int64_t row_hi[kPipeChunks];
+  for (int k = 0; k < kPipeChunks; ++k) {
+    const int64_t r0 = nv * k / kPipeChunks, r1 = nv * (k + 1) / kPipeChunks;
+    row_hi[k] = r1;
+    if (r1 > r0)
+      CU(cudaMemcpyAsync(dst + 3 * r0, pos_host + 3 * r0, size_t(3 * (r1 - r0)) * sizeof(double), cudaMemcpyHostToDevice,
+                         c->copy_stream));
+    CU(cudaEventRecord(c->pipe_events[size_t(k)], c->copy_stream));
+  }
+  int32_t a_done = 0, b_done = 0;
+  rows_a = rows_b = 0;
+  for (int k = 0; k < kPipeChunks; ++k) {
+    CU(cudaStreamWaitEvent(c->stream, c->pipe_events[size_t(k)], 0));
+    const int32_t a_hi = int32_t(std::upper_bound(c->pipe_need_a.begin(), c->pipe_need_a.end(), int32_t(row_hi[k])) -
+                                 c->pipe_need_a.begin());
+    if (a_hi > a_done) {
+      ms::PatchLaunch a = base;
+      a.patch_list = c->d_order_a.p;
+      a.patch_begin = a_done;
+      a.patch_count = a_hi - a_done;
+      if (ran_a) {
+        a.partials = c->d_partials_a.p;
+        a.partial_row0 = rows_a;
+        CU(ms::launch_pass_a(a, c->stream));
+        rows_a += ms::patch_grid(a);
+      } else if (o->want_grad) {
+        // no pass A (surface / volume only): pass B reads positions alone and follows the same order
+        a.partials = c->d_partials_b.p;
+        a.partial_row0 = rows_b;
+        CU(ms::launch_pass_b(a, false, true, c->stream));
+        rows_b += ms::patch_grid(a);
+      }
+      a_done = a_hi;
+    }
+    if (ran_a && o->want_grad) {
+      const int32_t b_hi = int32_t(std::upper_bound(c->pipe_need_b.begin(), c->pipe_need_b.end(), a_done) -
+                                   c->pipe_need_b.begin());
+      if (b_hi > b_done) {
+        ms::PatchLaunch b = base;
+        b.patch_list = c->d_order_b.p;
+        b.patch_begin = b_done;
+        b.patch_count = b_hi - b_done;
+        b.partials = c->d_partials_b.p;
+        b.partial_row0 = rows_b;
+        CU(ms::launch_pass_b(b, true, false, c->stream));
+        rows_b += ms::patch_grid(b);
+        b_done = b_hi;
+      }
+    }
+  }
+  if (a_done != np || (ran_a && o->want_grad && b_done != np)) return fail(-9, "pipelined evaluation did not cover every patch");
+  return 0;
+}
+
 int ms_ctx_eval_host(ms_ctx* c, const ms_eval_opts* o, const double* pos_host, double* scalars16,
                      double* grad_host, double* volgrad_host, double* tilt_grad_host) {
   if (int rc = check_ctx(c, true)) return rc;
   if (!o || !scalars16) return fail(-1, "null argument");
   const int64_t n3 = 3 * int64_t(c->nv);
-  if (pos_host)
-    if (int rc = ms_ctx_upload(c, o->use_trial ? MS_ARR_TRIAL : MS_ARR_POSITIONS, pos_host, 0, n3)) return rc;
-  if (int rc = ms_ctx_eval_async(c, o)) return rc;
+  if (pipe_applicable(c, o, pos_host)) {
+    // large meshes: the upload is cut into row chunks and the patch kernels start as their rows arrive
+    int rows_a = 0, rows_b = 0;
+    if (int rc = eval_pipelined(c, o, pos_host, rows_a, rows_b)) return rc;
+    if (int rc = reduce_rows(c, o, rows_a, rows_b)) return rc;
+    if (int rc = ms_ctx_eval_project(c, o)) return rc;
+  } else {
+    if (pos_host)
+      if (int rc = ms_ctx_upload(c, o->use_trial ? MS_ARR_TRIAL : MS_ARR_POSITIONS, pos_host, 0, n3)) return rc;
+    if (int rc = ms_ctx_eval_async(c, o)) return rc;
+  }
   if (o->want_grad && grad_host && n3)
     if (int rc = download_rows(c, c->d_grad.p, grad_host, 3)) return rc;
   if (o->want_grad && volgrad_host && n3 && (o->modules & MS_MOD_VOLUME))
