@@ -62,6 +62,10 @@ extern "C" {
 #define MS_ARR_E_VERTEX      10 /* nv  per-vertex bending energy (bending.compute_energy_array) */
 #define MS_ARR_TRIAL         11 /* (nv,3) trial positions x + alpha d */
 #define MS_ARR_DIRECTION     12 /* (nv,3) search direction d */
+#define MS_ARR_TILTS_IN      13 /* (nv,3) inner-leaflet tilt field  (Mesh.tilts_in_view, geometry/mesh.py:425-460) */
+#define MS_ARR_TILTS_OUT     14 /* (nv,3) outer-leaflet tilt field  (Mesh.tilts_out_view, geometry/mesh.py:462-499) */
+#define MS_ARR_TILT_GRAD_IN  15 /* (nv,3) dE/dt_in  of the leaflet modules */
+#define MS_ARR_TILT_GRAD_OUT 16 /* (nv,3) dE/dt_out of the leaflet modules */
 
 #define MS_PATCHES_ALL       (-1)
 #define MS_PATCHES_INTERIOR  (-2)
@@ -166,6 +170,51 @@ MS_API int ms_ctx_get_array(ms_ctx* ctx, int which, double* host, int64_t offset
 MS_API void* ms_ctx_device_ptr(ms_ctx* ctx, int which);
 MS_API int64_t ms_ctx_array_len(const ms_ctx* ctx, int which);
 MS_API int ms_ctx_set_stream(ms_ctx* ctx, void* cuda_stream);
+
+/* ---- leaflet tilt modules: tilt_in / tilt_out, bending_tilt_in / bending_tilt_out ---------------
+ * Replaces modules/energy/tilt_leaflet.py:26-169 (through tilt_in.py:34-61, tilt_out.py) and
+ * modules/energy/bending_tilt_leaflet.py:231-758 (through bending_tilt_in.py, bending_tilt_out.py;
+ * bt_payload.py:40-298, bt_gradient.py:20-64,89-389, bt_divergence.py:49-93), default numerical path:
+ * ambient_v1 transport, analytic gradient mode.  The selections the reference derives from mesh options
+ * arrive as masks in the CALLER's vertex / facet order; NULL means "none":
+ *   facet_keep       nf   facets of the leaflet (leaflet_presence.py:34-170); NULL = all
+ *   interior         nv   rows carrying a base term (bt_selection.py:289-330); NULL = not is_boundary
+ *   base_zero        nv   rows whose base term is forced to 0 (assume-J0 presets, region rows)
+ *   kappa, c0        nv   per-vertex leaflet parameters (bt_params.py:233-318); NULL = the defaults
+ *   tilt_row_weight  nv   active-row weights of the tilt magnitude module (tilt_utils._active_row_weights)
+ *   facet_consistent nf   mass mode per facet (1 = consistent, 0 = lumped); NULL = consistent_default
+ * The geometric boundary mask is the one given to ms_ctx_set_topology.  Must be called again after
+ * ms_ctx_set_topology. */
+typedef struct ms_leaflet_desc {
+  const uint8_t* facet_keep;
+  const uint8_t* interior;
+  const uint8_t* base_zero;
+  const double* kappa;
+  const double* c0;
+  const double* tilt_row_weight;
+  const uint8_t* facet_consistent;
+  double kappa_default;     /* bending_modulus_in / _out */
+  double c0_default;        /* spontaneous_curvature_in / _out */
+  double k_tilt;            /* tilt_modulus_in / _out */
+  double div_sign;          /* -1 inner leaflet, +1 outer (bending_tilt_in.py:46, bending_tilt_out.py:46) */
+  int32_t consistent_default;
+  int32_t reserved;
+} ms_leaflet_desc;
+
+#define MS_LEAFLET_IN  0
+#define MS_LEAFLET_OUT 1
+#define MS_ACC_GRAD      1u  /* add the shape gradient to MS_ARR_GRAD instead of overwriting it */
+#define MS_ACC_TILT_GRAD 2u  /* add to MS_ARR_TILT_GRAD_IN / _OUT instead of overwriting */
+
+MS_API int ms_ctx_set_leaflet(ms_ctx* ctx, int32_t leaflet, const ms_leaflet_desc* desc);
+/* Evaluate the leaflet's modules (MS_MOD_TILT and / or MS_MOD_BENDING_TILT) at MS_ARR_POSITIONS (or
+ * MS_ARR_TRIAL) with the tilt field MS_ARR_TILTS_IN / _OUT.  want_grad: shape gradient into MS_ARR_GRAD;
+ * want_tilt_grad: tilt gradient into MS_ARR_TILT_GRAD_IN / _OUT (want_grad == 0 is the tilt-only
+ * evaluation of the inner relaxation loop, evaluation_manager.py:693-698).  energies2, when not NULL,
+ * receives {E_bending_tilt, E_tilt} (synchronises the stream). */
+MS_API int ms_ctx_eval_leaflet(ms_ctx* ctx, int32_t leaflet, uint32_t modules, int32_t want_grad,
+                               int32_t want_tilt_grad, uint32_t accumulate, int32_t use_trial,
+                               double* energies2);
 
 /* One evaluation with everything resident: pass A (+ pass B when want_grad), scalar
  * reduction, optional KKT/penalty/fixed post-processing.  Asynchronous on the context

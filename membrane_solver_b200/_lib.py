@@ -26,9 +26,13 @@ SC_G_G, SC_G_GC, SC_GC_GC, SC_LAMBDA, SC_COUNT = 8, 9, 10, 11, 16
 
 ARR_POSITIONS, ARR_GRAD, ARR_VOLGRAD, ARR_SEEDS, ARR_TILTS, ARR_TILT_GRAD = 0, 1, 2, 3, 4, 5
 ARR_SCALARS, ARR_K_VECS, ARR_A_VOR, ARR_A_EFF, ARR_E_VERTEX, ARR_TRIAL, ARR_DIRECTION = 6, 7, 8, 9, 10, 11, 12
+ARR_TILTS_IN, ARR_TILTS_OUT, ARR_TILT_GRAD_IN, ARR_TILT_GRAD_OUT = 13, 14, 15, 16
+LEAFLET_IN, LEAFLET_OUT = 0, 1
+ACC_GRAD, ACC_TILT_GRAD = 1, 2
 ARRAY_WIDTH = {ARR_POSITIONS: 3, ARR_GRAD: 3, ARR_VOLGRAD: 3, ARR_SEEDS: 5, ARR_TILTS: 3,
                ARR_TILT_GRAD: 3, ARR_SCALARS: 1, ARR_K_VECS: 3, ARR_A_VOR: 1, ARR_A_EFF: 1,
-               ARR_E_VERTEX: 1, ARR_TRIAL: 3, ARR_DIRECTION: 3}
+               ARR_E_VERTEX: 1, ARR_TRIAL: 3, ARR_DIRECTION: 3, ARR_TILTS_IN: 3, ARR_TILTS_OUT: 3,
+               ARR_TILT_GRAD_IN: 3, ARR_TILT_GRAD_OUT: 3}
 
 
 class B200Error(RuntimeError):
@@ -49,6 +53,25 @@ class EvalOpts(ctypes.Structure):
         ("patch_count", ctypes.c_int32),
         ("diagnostics", ctypes.c_int32),
         ("want_tilt_grad", ctypes.c_int32),
+    ]
+
+
+class LeafletDesc(ctypes.Structure):
+    """struct ms_leaflet_desc (include/ms_b200.h)."""
+    _fields_ = [
+        ("facet_keep", ctypes.POINTER(ctypes.c_uint8)),
+        ("interior", ctypes.POINTER(ctypes.c_uint8)),
+        ("base_zero", ctypes.POINTER(ctypes.c_uint8)),
+        ("kappa", ctypes.POINTER(ctypes.c_double)),
+        ("c0", ctypes.POINTER(ctypes.c_double)),
+        ("tilt_row_weight", ctypes.POINTER(ctypes.c_double)),
+        ("facet_consistent", ctypes.POINTER(ctypes.c_uint8)),
+        ("kappa_default", ctypes.c_double),
+        ("c0_default", ctypes.c_double),
+        ("k_tilt", ctypes.c_double),
+        ("div_sign", ctypes.c_double),
+        ("consistent_default", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
     ]
 
 
@@ -109,6 +132,8 @@ SIGNATURES = {
     "ms_ctx_read_scalars": (ctypes.c_int, [_V, _D]),
     "ms_ctx_eval": (ctypes.c_int, [_V, ctypes.POINTER(EvalOpts), _D]),
     "ms_ctx_eval_host": (ctypes.c_int, [_V, ctypes.POINTER(EvalOpts), _D, _D, _D, _D, _D]),
+    "ms_ctx_set_leaflet": (ctypes.c_int, [_V, _i32, ctypes.POINTER(LeafletDesc)]),
+    "ms_ctx_eval_leaflet": (ctypes.c_int, [_V, _i32, ctypes.c_uint32, _i32, _i32, ctypes.c_uint32, _i32, _D]),
     "ms_ctx_make_trial": (ctypes.c_int, [_V, _f64]),
     "ms_ctx_accept_trial": (ctypes.c_int, [_V]),
     "ms_ctx_dots": (ctypes.c_int, [_V]),

@@ -179,6 +179,49 @@ class DeviceMesh:
     def set_tilt_rigidity(self, k_tilt: float) -> None:
         L.check(self._lib.ms_ctx_set_tilt_rigidity(self._h, float(k_tilt)))
 
+    # -- leaflet tilt modules (tilt_in/out, bending_tilt_in/out) ------------
+    def set_leaflet(self, leaflet: int, *, div_sign: float, kappa=0.0, c0=0.0, k_tilt: float = 0.0,
+                    facet_keep=None, interior=None, base_zero=None, tilt_row_weight=None,
+                    facet_consistent=None, consistent: bool = False) -> None:
+        """Selections and parameters of one leaflet (``struct ms_leaflet_desc``).  ``kappa`` / ``c0``:
+        scalar or (nv,) array; masks in the caller's vertex / facet order, None = absent."""
+        hold = []
+
+        def mask(a, n):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dtype=np.uint8)
+            if a.shape != (n,):
+                raise ValueError(f"mask must have shape ({n},)")
+            hold.append(a)
+            return a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))
+
+        def vec(a):
+            if a is None or np.ndim(a) == 0:
+                return None
+            a = L.as_f64(a, (self.nv,))
+            hold.append(a)
+            return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+        d = L.LeafletDesc(
+            facet_keep=mask(facet_keep, self.nf), interior=mask(interior, self.nv), base_zero=mask(base_zero, self.nv),
+            kappa=vec(kappa), c0=vec(c0), tilt_row_weight=vec(tilt_row_weight),
+            facet_consistent=mask(facet_consistent, self.nf),
+            kappa_default=float(kappa) if np.ndim(kappa) == 0 else 0.0,
+            c0_default=float(c0) if np.ndim(c0) == 0 else 0.0,
+            k_tilt=float(k_tilt), div_sign=float(div_sign), consistent_default=int(bool(consistent)), reserved=0)
+        L.check(self._lib.ms_ctx_set_leaflet(self._h, int(leaflet), ctypes.byref(d)))
+
+    def eval_leaflet(self, leaflet: int, modules: int, *, want_grad: bool = True, want_tilt_grad: bool = True,
+                     accumulate: int = 0, use_trial: bool = False) -> tuple[float, float]:
+        """(E_bending_tilt, E_tilt) of the leaflet's modules; gradients stay on the device
+        (``ARR_GRAD``, ``ARR_TILT_GRAD_IN`` / ``_OUT``)."""
+        e = np.zeros(2)
+        L.check(self._lib.ms_ctx_eval_leaflet(self._h, int(leaflet), int(modules), int(bool(want_grad)),
+                                              int(bool(want_tilt_grad)), int(accumulate), int(bool(use_trial)),
+                                              L.dptr(e)))
+        return float(e[0]), float(e[1])
+
     # -- state --------------------------------------------------------------
     def upload(self, which: int, host: np.ndarray) -> None:
         a = L.as_f64(host)

@@ -112,6 +112,17 @@ struct ms_ctx {
   DevBuf<int32_t> d_tri, d_csr_ptr, d_csr_idx;
   DevBuf<double> d_bt_corner, d_bt_base, d_bt_facet_e, d_bt_e;
   int64_t n_send_rows = 0;
+  // leaflet tilt modules (ms_leaflet.cuh): per-leaflet selections, parameters and tilt fields
+  struct Leaflet {
+    bool set = false;
+    bool has_keep = false, has_interior = false, has_base_zero = false, has_kappa = false, has_c0 = false,
+         has_weight = false, has_consistent = false;
+    DevBuf<uint8_t> keep, interior, base_zero, consistent;
+    DevBuf<double> kappa, c0, weight, tilts, tilt_grad;
+    double kappa_u = 0.0, c0_u = 0.0, k_tilt = 0.0, sign = 1.0;
+    int32_t consistent_u = 0;
+  } leaflet[2];
+  DevBuf<double> d_lf_corner, d_lf_vbuf, d_lf_shape, d_lf_tilt, d_lf_facet_e, d_lf_e;
 };
 
 namespace {
@@ -145,6 +156,10 @@ double* array_ptr(ms_ctx* c, int which, int64_t* len) {
     case MS_ARR_E_VERTEX: *len = nv; return c->d_evert.p;
     case MS_ARR_TRIAL: *len = 3 * nv; return c->d_trial.p;
     case MS_ARR_DIRECTION: *len = 3 * nv; return c->d_dir.p;
+    case MS_ARR_TILTS_IN: *len = 3 * nv; return c->leaflet[0].tilts.p;
+    case MS_ARR_TILTS_OUT: *len = 3 * nv; return c->leaflet[1].tilts.p;
+    case MS_ARR_TILT_GRAD_IN: *len = 3 * nv; return c->leaflet[0].tilt_grad.p;
+    case MS_ARR_TILT_GRAD_OUT: *len = 3 * nv; return c->leaflet[1].tilt_grad.p;
     default: *len = 0; return nullptr;
   }
 }
@@ -161,6 +176,10 @@ int ensure_array(ms_ctx* c, int which) {
     case MS_ARR_E_VERTEX: return c->d_evert.ensure(nv);
     case MS_ARR_TRIAL: return c->d_trial.ensure(3 * nv);
     case MS_ARR_DIRECTION: return c->d_dir.ensure(3 * nv);
+    case MS_ARR_TILTS_IN: return c->leaflet[0].tilts.ensure(3 * nv);
+    case MS_ARR_TILTS_OUT: return c->leaflet[1].tilts.ensure(3 * nv);
+    case MS_ARR_TILT_GRAD_IN: return c->leaflet[0].tilt_grad.ensure(3 * nv);
+    case MS_ARR_TILT_GRAD_OUT: return c->leaflet[1].tilt_grad.ensure(3 * nv);
     default: return 0;
   }
 }
@@ -363,6 +382,20 @@ bool per_vertex_array(int which) {
   return which != MS_ARR_SCALARS;
 }
 
+template <typename T>
+int upload_optional(ms_ctx* c, const T* host, size_t n, bool per_vertex, DevBuf<T>& dst, bool& has) {
+  has = host != nullptr;
+  if (!host) return 0;
+  std::vector<T> tmp;
+  if (per_vertex && !c->perm.empty()) {
+    tmp = permuted(host, c->perm);
+    host = tmp.data();
+  }
+  if (int rc = dst.ensure(n + 1)) return rc;
+  if (n) CU(cudaMemcpy(dst.p, host, n * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -518,6 +551,7 @@ int ms_ctx_set_topology_partition(ms_ctx* c, int32_t nv, int32_t n_owned, int32_
   c->bt_ready = false;
   c->tri_ready = false;
   c->pipe_ready = false;
+  c->leaflet[0].set = c->leaflet[1].set = false;
   const ms::PackedMesh& pk = c->packed;
   const size_t np = pk.patches.size();
   c->v_lo.resize(np + 1);
@@ -876,6 +910,86 @@ int ms_ctx_read_scalars(ms_ctx* c, double* scalars16) {
 int ms_ctx_eval(ms_ctx* c, const ms_eval_opts* o, double* scalars16) {
   if (int rc = ms_ctx_eval_async(c, o)) return rc;
   return ms_ctx_read_scalars(c, scalars16);
+}
+
+// ---- leaflet tilt modules ------------------------------------------------------------------------------
+int ms_ctx_set_leaflet(ms_ctx* c, int32_t leaflet, const ms_leaflet_desc* d) {
+  if (int rc = check_ctx(c, true)) return rc;
+  if (!d || leaflet < 0 || leaflet > 1) return fail(-1, "bad leaflet arguments");
+  if (c->n_owned != c->nv) return fail(-5, "leaflet modules are not available on a partitioned context");
+  ms_ctx::Leaflet& L = c->leaflet[leaflet];
+  const size_t nv = size_t(c->nv), nf = size_t(c->nf);
+  L.set = false;
+  if (int rc = upload_optional(c, d->facet_keep, nf, false, L.keep, L.has_keep)) return rc;
+  if (int rc = upload_optional(c, d->interior, nv, true, L.interior, L.has_interior)) return rc;
+  if (int rc = upload_optional(c, d->base_zero, nv, true, L.base_zero, L.has_base_zero)) return rc;
+  if (int rc = upload_optional(c, d->kappa, nv, true, L.kappa, L.has_kappa)) return rc;
+  if (int rc = upload_optional(c, d->c0, nv, true, L.c0, L.has_c0)) return rc;
+  if (int rc = upload_optional(c, d->tilt_row_weight, nv, true, L.weight, L.has_weight)) return rc;
+  if (int rc = upload_optional(c, d->facet_consistent, nf, false, L.consistent, L.has_consistent)) return rc;
+  L.kappa_u = d->kappa_default;
+  L.c0_u = d->c0_default;
+  L.k_tilt = d->k_tilt;
+  L.sign = d->div_sign;
+  L.consistent_u = d->consistent_default;
+  L.set = true;
+  return 0;
+}
+
+int ms_ctx_eval_leaflet(ms_ctx* c, int32_t leaflet, uint32_t modules, int32_t want_grad, int32_t want_tilt_grad,
+                        uint32_t accumulate, int32_t use_trial, double* energies2) {
+  if (int rc = check_ctx(c, true)) return rc;
+  if (leaflet < 0 || leaflet > 1) return fail(-1, "bad leaflet index");
+  ms_ctx::Leaflet& L = c->leaflet[leaflet];
+  if (!L.set) return fail(-4, "ms_ctx_set_leaflet has not been called for this leaflet (or the topology changed)");
+  if (modules & ~uint32_t(MS_MOD_TILT | MS_MOD_BENDING_TILT))
+    return fail(-1, "leaflet modules are MS_MOD_TILT and MS_MOD_BENDING_TILT");
+  const int which_t = leaflet == 0 ? MS_ARR_TILTS_IN : MS_ARR_TILTS_OUT;
+  const int which_g = leaflet == 0 ? MS_ARR_TILT_GRAD_IN : MS_ARR_TILT_GRAD_OUT;
+  if (!L.tilts.p && c->nv > 0) return fail(-4, "the leaflet's tilt field has not been uploaded (MS_ARR_TILTS_IN / _OUT)");
+  if (use_trial && !c->d_trial.p) return fail(-4, "use_trial set but no trial positions exist (ms_ctx_make_trial)");
+  (void)which_t;
+  if (want_tilt_grad)
+    if (int rc = ensure_array(c, which_g)) return rc;
+  ms::BtMesh bm;  // triangle rows + corner CSR are shared with the single-field coupling stage
+  if (int rc = bt_prepare(c, bm)) return rc;
+  const size_t nv = size_t(c->nv), nf = size_t(c->nf);
+  if (int rc = c->d_lf_corner.ensure(3 * ms::kLfCornerA * nf + 1)) return rc;
+  if (int rc = c->d_lf_vbuf.ensure(ms::kLfVertex * nv + 1)) return rc;
+  if (int rc = c->d_lf_shape.ensure(9 * nf + 1)) return rc;
+  if (int rc = c->d_lf_tilt.ensure(9 * nf + 1)) return rc;
+  if (int rc = c->d_lf_facet_e.ensure(2 * nf + 1)) return rc;
+  if (int rc = c->d_lf_e.ensure(2)) return rc;
+  ms::LeafletMesh m;
+  m.nv = c->nv;
+  m.nf = c->nf;
+  m.tri = c->d_tri.p;
+  m.pos = use_trial ? c->d_trial.p : c->d_pos.p;
+  m.tilts = L.tilts.p;
+  m.keep = L.has_keep ? L.keep.p : nullptr;
+  m.is_boundary = c->has_boundary ? c->d_boundary.p : nullptr;
+  m.interior = L.has_interior ? L.interior.p : nullptr;
+  m.base_zero = L.has_base_zero ? L.base_zero.p : nullptr;
+  m.kappa = L.has_kappa ? L.kappa.p : nullptr;
+  m.c0 = L.has_c0 ? L.c0.p : nullptr;
+  m.kappa_u = L.kappa_u;
+  m.c0_u = L.c0_u;
+  m.row_weight = L.has_weight ? L.weight.p : nullptr;
+  m.consistent = L.has_consistent ? L.consistent.p : nullptr;
+  m.consistent_u = L.consistent_u;
+  m.k_tilt = L.k_tilt;
+  m.sign = L.sign;
+  m.csr_ptr = c->d_csr_ptr.p;
+  m.csr_idx = c->d_csr_idx.p;
+  CU(ms::launch_leaflet(m, (modules & MS_MOD_BENDING_TILT) != 0, (modules & MS_MOD_TILT) != 0, c->d_lf_corner.p,
+                        c->d_lf_vbuf.p, c->d_lf_shape.p, c->d_lf_tilt.p, c->d_lf_facet_e.p, c->d_lf_e.p,
+                        want_grad ? c->d_grad.p : nullptr, (accumulate & MS_ACC_GRAD) != 0,
+                        want_tilt_grad ? L.tilt_grad.p : nullptr, (accumulate & MS_ACC_TILT_GRAD) != 0, c->stream));
+  if (energies2) {
+    CU(cudaMemcpyAsync(energies2, c->d_lf_e.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  return 0;
 }
 
 // ---- pipelined host evaluation ---------------------------------------------------------------------

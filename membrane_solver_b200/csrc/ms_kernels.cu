@@ -798,6 +798,27 @@ __global__ void k_bt_finalize(const double* e_bt, double* scalars) {
   scalars[SC_E_BENDING] = 0.0;
 }
 
+// ---- leaflet tilt modules (ms_leaflet.cuh): three sweeps on global arrays + fixed-order gathers ----
+__global__ void __launch_bounds__(128) k_lf_facet_a(LeafletMesh m, double* corner) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f < m.nf) lf_facet_a(m, f, corner);
+}
+
+__global__ void __launch_bounds__(128) k_lf_vertex(LeafletMesh m, const double* __restrict__ corner, double* vbuf) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < m.nv) lf_vertex(m, v, corner, vbuf);
+}
+
+__global__ void __launch_bounds__(128) k_lf_facet_b(LeafletMesh m, const double* __restrict__ vbuf, int with_bt,
+                                                    int with_tilt, double* corner_shape, double* corner_tilt,
+                                                    double* facet_e /* [e_bt (nf) | e_tilt (nf)] */) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= m.nf) return;
+  const LfEnergies e = lf_facet_b(m, f, vbuf, with_bt != 0, with_tilt != 0, corner_shape, corner_tilt);
+  facet_e[f] = e.e_bt;
+  facet_e[size_t(m.nf) + f] = e.e_tilt;
+}
+
 __global__ void __launch_bounds__(256) k_row_norm2(const double* __restrict__ rows, int64_t n, double* out) {
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -1109,6 +1130,28 @@ cudaError_t launch_bt_tilt_gather(const BtMesh& m, const double* corner3, double
 
 cudaError_t launch_bt_finalize(const double* e_bt, double* scalars, cudaStream_t st) {
   k_bt_finalize<<<1, 1, 0, st>>>(e_bt, scalars);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_leaflet(const LeafletMesh& m, bool with_bt, bool with_tilt, double* corner, double* vbuf,
+                           double* corner_shape, double* corner_tilt, double* facet_e, double* e_out2, double* grad,
+                           bool accumulate_grad, double* tilt_grad, bool accumulate_tilt_grad, cudaStream_t st) {
+  if (with_bt) {
+    if (m.nf > 0) k_lf_facet_a<<<blocks_for(m.nf, 128), 128, 0, st>>>(m, corner);
+    if (m.nv > 0) k_lf_vertex<<<blocks_for(m.nv, 128), 128, 0, st>>>(m, corner, vbuf);
+  }
+  if (m.nf > 0)
+    k_lf_facet_b<<<blocks_for(m.nf, 128), 128, 0, st>>>(m, vbuf, with_bt ? 1 : 0, with_tilt ? 1 : 0,
+                                                        grad ? corner_shape : nullptr, tilt_grad ? corner_tilt : nullptr,
+                                                        facet_e);
+  k_sum<<<1, 256, 0, st>>>(facet_e, m.nf, 1.0, e_out2);
+  k_sum<<<1, 256, 0, st>>>(facet_e + size_t(m.nf), m.nf, 1.0, e_out2 + 1);
+  if (m.nv > 0 && grad)
+    k_gather<<<blocks_for(m.nv, 128), 128, 0, st>>>(m.nv, m.csr_ptr, m.csr_idx, corner_shape, 3, 0, 3, grad, 3,
+                                                     accumulate_grad ? 1 : 0);
+  if (m.nv > 0 && tilt_grad)
+    k_gather<<<blocks_for(m.nv, 128), 128, 0, st>>>(m.nv, m.csr_ptr, m.csr_idx, corner_tilt, 3, 0, 3, tilt_grad, 3,
+                                                     accumulate_tilt_grad ? 1 : 0);
   return cudaGetLastError();
 }
 

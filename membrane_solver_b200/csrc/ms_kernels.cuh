@@ -7,6 +7,7 @@
 
 #include "../../include/ms_b200.h"
 #include "ms_bt.cuh"
+#include "ms_leaflet.cuh"
 #include "ms_math.cuh"
 #include "ms_pack.h"
 
@@ -159,5 +160,11 @@ cudaError_t launch_bt_stage(const BtMesh& m, double sign, const double* k_vecs, 
 cudaError_t launch_bt_tilt_gather(const BtMesh& m, const double* corner3, double* tilt_grad, bool accumulate,
                                   cudaStream_t st);
 cudaError_t launch_bt_finalize(const double* e_bt, double* scalars, cudaStream_t st);
+
+// --- leaflet tilt modules (ms_leaflet.cuh).  corner: 27*nf doubles, vbuf: 5*nv, corner_shape / corner_tilt:
+// 9*nf each, facet_e: 2*nf, e_out2: {E_bending_tilt, E_tilt}.  grad / tilt_grad may be null. ---
+cudaError_t launch_leaflet(const LeafletMesh& m, bool with_bt, bool with_tilt, double* corner, double* vbuf,
+                           double* corner_shape, double* corner_tilt, double* facet_e, double* e_out2, double* grad,
+                           bool accumulate_grad, double* tilt_grad, bool accumulate_tilt_grad, cudaStream_t st);
 
 }  // namespace ms

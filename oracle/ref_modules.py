@@ -299,47 +299,45 @@ def _k_direction(k_vecs, k_mag, pos, tri):
     return d
 
 
-def bending_backprop(pos, tri, weights, interior, f_eff, f_vor, f_k, grad):
-    """bending_gradient.py:17-175: three-term analytic shape gradient."""
+def _angle_scatter(out, rows, coef0, coef1, coef2, s0u, s0p, s1u, s1p, s2u, s2p):
+    r0, r1, r2 = rows
+    k0, k1, k2 = coef0[:, None], coef1[:, None], coef2[:, None]
+    np.add.at(out, r1, k0 * s0u)
+    np.add.at(out, r2, k0 * s0p)
+    np.add.at(out, r0, k0 * -(s0u + s0p))
+    np.add.at(out, r2, k1 * s1u)
+    np.add.at(out, r0, k1 * s1p)
+    np.add.at(out, r1, k1 * -(s1u + s1p))
+    np.add.at(out, r0, k2 * s2u)
+    np.add.at(out, r1, k2 * s2p)
+    np.add.at(out, r2, k2 * -(s2u + s2p))
+
+
+def _corner_angle_gradients(pos, tri):
+    i0, i1, i2 = tri[:, 0], tri[:, 1], tri[:, 2]
+    v0, v1, v2 = pos[i0], pos[i1], pos[i2]
+    return grad_cotan(v1 - v0, v2 - v0) + grad_cotan(v2 - v1, v0 - v1) + grad_cotan(v0 - v2, v1 - v2)
+
+
+def backprop_operator_terms(pos, tri, weights, f_k):
+    """bending_gradient.py:17-80: -L fK (cotangents frozen) and the cotangent variation of L."""
+    i0, i1, i2 = tri[:, 0], tri[:, 1], tri[:, 2]
+    v0, v1, v2 = pos[i0], pos[i1], pos[i2]
+    g_lin = -beltrami_laplacian(weights, tri, f_k)
+    w0 = -0.5 * _dot(f_k[i1] - f_k[i2], v1 - v2)
+    w1 = -0.5 * _dot(f_k[i2] - f_k[i0], v2 - v0)
+    w2 = -0.5 * _dot(f_k[i0] - f_k[i1], v0 - v1)
+    g_cot = np.zeros_like(pos)
+    _angle_scatter(g_cot, (i0, i1, i2), w0, w1, w2, *_corner_angle_gradients(pos, tri))
+    return g_lin, g_cot
+
+
+def backprop_area_terms(pos, tri, weights, chi):
+    """bending_gradient.py:82-175: Voronoi / effective-area variation with corner weights chi (nf,3)."""
     i0, i1, i2 = tri[:, 0], tri[:, 1], tri[:, 2]
     v0, v1, v2 = pos[i0], pos[i1], pos[i2]
     e0, e1, e2 = v2 - v1, v0 - v2, v1 - v0
     c0, c1, c2 = weights[:, 0], weights[:, 1], weights[:, 2]
-
-    g_lin = -beltrami_laplacian(weights, tri, f_k)
-
-    w0 = -0.5 * _dot(f_k[i1] - f_k[i2], v1 - v2)
-    w1 = -0.5 * _dot(f_k[i2] - f_k[i0], v2 - v0)
-    w2 = -0.5 * _dot(f_k[i0] - f_k[i1], v0 - v1)
-    a0u, a0p = grad_cotan(v1 - v0, v2 - v0)
-    a1u, a1p = grad_cotan(v2 - v1, v0 - v1)
-    a2u, a2p = grad_cotan(v0 - v2, v1 - v2)
-
-    g_cot = np.zeros_like(pos)
-
-    def angle_scatter(out, rows, coef0, coef1, coef2, s0u, s0p, s1u, s1p, s2u, s2p):
-        r0, r1, r2 = rows
-        k0, k1, k2 = coef0[:, None], coef1[:, None], coef2[:, None]
-        np.add.at(out, r1, k0 * s0u)
-        np.add.at(out, r2, k0 * s0p)
-        np.add.at(out, r0, k0 * -(s0u + s0p))
-        np.add.at(out, r2, k1 * s1u)
-        np.add.at(out, r0, k1 * s1p)
-        np.add.at(out, r1, k1 * -(s1u + s1p))
-        np.add.at(out, r0, k2 * s2u)
-        np.add.at(out, r1, k2 * s2p)
-        np.add.at(out, r2, k2 * -(s2u + s2p))
-
-    angle_scatter(g_cot, (i0, i1, i2), w0, w1, w2, a0u, a0p, a1u, a1p, a2u, a2p)
-
-    corner_int = interior[tri]
-    n_int = corner_int.sum(axis=1)
-    fe = f_eff[tri]
-    mean_int = np.zeros(len(tri))
-    has = n_int > 0
-    mean_int[has] = (fe * corner_int).sum(axis=1)[has] / n_int[has]
-    chi = np.where(corner_int, fe, mean_int[:, None]) + f_vor[tri]
-
     g_area = np.zeros_like(pos)
     obtuse = (c0 < 0) | (c1 < 0) | (c2 < 0)
     std = ~obtuse
@@ -360,8 +358,8 @@ def bending_backprop(pos, tri, weights, interior, f_eff, f_vor, f_k, grad):
         q0 = 0.125 * _dot(e0[s], e0[s]) * (x1 + x2)
         q1 = 0.125 * _dot(e1[s], e1[s]) * (x0 + x2)
         q2 = 0.125 * _dot(e2[s], e2[s]) * (x0 + x1)
-        angle_scatter(g_area, (r0, r1, r2), q0, q1, q2,
-                      a0u[s], a0p[s], a1u[s], a1p[s], a2u[s], a2p[s])
+        sub = np.ascontiguousarray(tri[s])
+        _angle_scatter(g_area, (r0, r1, r2), q0, q1, q2, *_corner_angle_gradients(pos, sub))
     if np.any(obtuse):
         for k, at_k in enumerate((c0 < 0, c1 < 0, c2 < 0)):
             m = at_k & obtuse
@@ -373,7 +371,23 @@ def bending_backprop(pos, tri, weights, interior, f_eff, f_vor, f_k, grad):
             np.add.at(g_area, i1[m], phi * gu)
             np.add.at(g_area, i2[m], phi * gp)
             np.add.at(g_area, i0[m], phi * -(gu + gp))
+    return g_area
 
+
+def corner_weights(tri, interior, corner_f_eff, f_vor):
+    """chi_k = (interior corner ? fA_eff,k : mean of fA_eff over the facet's interior corners) + fA_vor."""
+    corner_int = interior[tri]
+    n_int = corner_int.sum(axis=1)
+    mean_int = np.zeros(len(tri))
+    has = n_int > 0
+    mean_int[has] = (corner_f_eff * corner_int).sum(axis=1)[has] / n_int[has]
+    return np.where(corner_int, corner_f_eff, mean_int[:, None]) + f_vor[tri]
+
+
+def bending_backprop(pos, tri, weights, interior, f_eff, f_vor, f_k, grad):
+    """bending_gradient.py:17-175: three-term analytic shape gradient."""
+    g_lin, g_cot = backprop_operator_terms(pos, tri, weights, f_k)
+    g_area = backprop_area_terms(pos, tri, weights, corner_weights(tri, interior, f_eff[tri], f_vor))
     grad += g_lin + g_cot + g_area
 
 

@@ -360,9 +360,85 @@ def trajectory_vectors():
     np.savez_compressed(os.path.join(HERE, "trajectory.npz"), **out)
 
 
+def leaflet_vectors():
+    """BASELINE config 4: the four leaflet modules of the reference's caveolin free-disk mesh
+    (bending_tilt_in/out, tilt_in/out) with the selections the reference derives from the mesh options
+    stored as plain masks.  One ``leaflet.npz``; keys ``<state>_<leaflet>_<what>``."""
+    from modules.energy import bending_tilt_in, bending_tilt_out, tilt_in, tilt_out
+    from modules.energy.bt_params import (_assume_J0_center_xy, _assume_J0_presets, _assume_J0_radius_max,
+                                          _per_vertex_params_leaflet)
+    from modules.energy.bt_selection import (_base_term_region_zero_rows, _collect_preset_rows,
+                                             _interior_mask_leaflet)
+    from modules.energy.leaflet_presence import leaflet_absent_vertex_mask, leaflet_present_triangle_mask
+    from modules.energy.tilt_params import _resolve_tilt_mass_mode, _resolve_tilt_modulus
+
+    path = os.path.join(REF, "meshes", "caveolin",
+                        "kozlov_1disk_3d_tensionless_single_leaflet_profile_hard_rim_R12_free_disk.yaml")
+    out = {}
+    for state, levels, jitter, mass in (("r0", 0, 0.02, None), ("r1", 1, 0.05, None), ("r1c", 1, 0.03, "consistent")):
+        mesh = _refined(path, levels)
+        gp = mesh.global_parameters
+        if mass:
+            gp.set("tilt_mass_mode", mass)
+        res = ParameterResolver(gp)
+        rng = np.random.default_rng(77 + levels)
+        pos = np.array(mesh.positions_view())
+        pos[:, 2] += jitter * rng.standard_normal(len(pos))
+        nv = len(pos)
+        idx = mesh.vertex_index_to_row
+        tri = np.ascontiguousarray(mesh.triangle_row_cache()[0], dtype=np.int32)
+        tilts = {"in": 0.1 * rng.standard_normal((nv, 3)), "out": 0.1 * rng.standard_normal((nv, 3))}
+        isb = np.zeros(nv, bool)
+        for vid in mesh.boundary_vertex_ids:
+            isb[idx[vid]] = True
+        out[f"{state}_pos"], out[f"{state}_tri"], out[f"{state}_is_boundary"] = pos, tri, isb
+        for leaf, sign, bt, tm in (("in", -1.0, bending_tilt_in, tilt_in), ("out", 1.0, bending_tilt_out, tilt_out)):
+            pre = f"{state}_{leaf}_"
+            am = leaflet_absent_vertex_mask(mesh, gp, leaflet=leaf)
+            keep = leaflet_present_triangle_mask(mesh, tri, absent_vertex_mask=am)
+            keep = np.ones(len(tri), bool) if keep.size == 0 else np.asarray(keep, bool)
+            inter = _interior_mask_leaflet(mesh, gp, cache_tag=leaf, index_map=idx)
+            kap, c0 = _per_vertex_params_leaflet(mesh, gp, model="helfrich", kappa_key=f"bending_modulus_{leaf}",
+                                                 cache_tag=leaf)
+            bz = np.zeros(nv, bool)
+            presets = _assume_J0_presets(gp, cache_tag=leaf)
+            if presets:
+                rows = _collect_preset_rows(mesh, presets=presets, cache_tag=leaf, index_map=idx,
+                                            radius_max=_assume_J0_radius_max(gp, cache_tag=leaf),
+                                            center_xy=_assume_J0_center_xy(gp))
+                bz[rows] = True
+            bz[_base_term_region_zero_rows(mesh, gp, cache_tag=leaf, index_map=idx)] = True
+            out[pre + "tilts"], out[pre + "keep"], out[pre + "interior"] = tilts[leaf], keep, np.asarray(inter, bool)
+            out[pre + "base_zero"], out[pre + "kappa"], out[pre + "c0"] = bz, np.array(kap), np.array(c0)
+            out[pre + "sign"] = np.float64(sign)
+            out[pre + "k_tilt"] = np.float64(_resolve_tilt_modulus(res, leaf))
+            out[pre + "consistent"] = np.bool_(_resolve_tilt_mass_mode(res, leaf) == "consistent")
+            for tag, mod in (("bt", bt), ("tilt", tm)):
+                g, tgi, tgo = np.zeros_like(pos), np.zeros_like(pos), np.zeros_like(pos)
+                e = mod.compute_energy_and_gradient_array(mesh, gp, res, positions=pos, index_map=idx, grad_arr=g,
+                                                          tilts_in=tilts["in"], tilts_out=tilts["out"],
+                                                          tilt_in_grad_arr=tgi, tilt_out_grad_arr=tgo)
+                out[pre + f"E_{tag}"], out[pre + f"g_{tag}"] = np.float64(e), g
+                out[pre + f"tg_{tag}"] = tgi if leaf == "in" else tgo
+                assert not np.any(tgo if leaf == "in" else tgi)
+                # tilt-only evaluation (grad_arr=None): the inner relaxation loop's call
+                tgi, tgo = np.zeros_like(pos), np.zeros_like(pos)
+                e2 = mod.compute_energy_and_gradient_array(mesh, gp, res, positions=pos, index_map=idx, grad_arr=None,
+                                                           tilts_in=tilts["in"], tilts_out=tilts["out"],
+                                                           tilt_in_grad_arr=tgi, tilt_out_grad_arr=tgo)
+                out[pre + f"E_{tag}_tiltonly"] = np.float64(e2)
+                out[pre + f"tg_{tag}_tiltonly"] = tgi if leaf == "in" else tgo
+                print(state, leaf, tag, e, e2, int(keep.sum()), int(inter.sum()), int(bz.sum()))
+    np.savez_compressed(os.path.join(HERE, "leaflet.npz"), **out)
+
+
 if __name__ == "__main__":
     _ = (volume_constraint, volume_energy)
+    if len(sys.argv) > 1 and sys.argv[1] == "leaflet":
+        leaflet_vectors()
+        sys.exit(0)
     kernel_vectors()
     module_vectors()
     minimizer_vectors()
     trajectory_vectors()
+    leaflet_vectors()

@@ -42,7 +42,8 @@ def build_emulator():
     src = os.path.join(ROOT, "tests", "emul", "emul.cpp")
     csrc = os.path.join(ROOT, "membrane_solver_b200", "csrc")
     out = os.path.join(ROOT, "tests", "emul", "_build", "libms_emul.so")
-    deps = [src] + [os.path.join(csrc, f) for f in ("ms_pack.cpp", "ms_pack.h", "ms_math.cuh", "ms_patch_body.cuh")]
+    deps = [src] + [os.path.join(csrc, f) for f in ("ms_pack.cpp", "ms_pack.h", "ms_math.cuh", "ms_patch_body.cuh", "ms_bt.cuh",
+                                                         "ms_leaflet.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-fPIC", "-shared", "-o", out, src,
@@ -108,3 +109,45 @@ def emulate(pos, tri, *, modules, flags=0, want_grad=True, is_boundary=None, bod
                          max_rounds=int(stats[3]), max_local=int(stats[4]),
                          lane_conflicts=int(stats[5]), hw_groups=int(stats[6]), hw_excess=int(stats[7])))
     return out
+
+
+def emulate_leaflet(pos, tri, tilts, *, sign, keep=None, is_boundary=None, interior=None, base_zero=None,
+                    kappa=None, c0=None, kappa_u=0.0, c0_u=0.0, row_weight=None, consistent=None,
+                    consistent_u=False, k_tilt=0.0, with_bt=True, with_tilt=False, want_grad=True,
+                    want_tilt_grad=True):
+    """Leaflet modules through the emulator (same ms_leaflet.cuh bodies as the device kernels)."""
+    global _EMUL
+    if _EMUL is None:
+        _EMUL = ctypes.CDLL(build_emulator())
+        _EMUL.emul_eval.restype = ctypes.c_int
+    pos = np.ascontiguousarray(pos, dtype=np.float64)
+    tri = np.ascontiguousarray(tri, dtype=np.int32)
+    tilts = np.ascontiguousarray(tilts, dtype=np.float64)
+    nv, nf = pos.shape[0], tri.shape[0]
+    keepalive = []
+
+    def conv(a, dt, ct):
+        if a is None:
+            return None
+        a = np.ascontiguousarray(a, dtype=dt)
+        keepalive.append(a)
+        return a.ctypes.data_as(ctypes.POINTER(ct))
+
+    grad = np.zeros((nv, 3)) if want_grad else None
+    tg = np.zeros((nv, 3)) if want_tilt_grad else None
+    e2 = np.zeros(2)
+    dp = ctypes.POINTER(ctypes.c_double)
+    rc = _EMUL.emul_leaflet(
+        ctypes.c_int32(nv), ctypes.c_int32(nf), tri.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+        pos.ctypes.data_as(dp), tilts.ctypes.data_as(dp), conv(keep, np.uint8, ctypes.c_uint8),
+        conv(is_boundary, np.uint8, ctypes.c_uint8), conv(interior, np.uint8, ctypes.c_uint8),
+        conv(base_zero, np.uint8, ctypes.c_uint8), conv(kappa, np.float64, ctypes.c_double),
+        conv(c0, np.float64, ctypes.c_double), ctypes.c_double(kappa_u), ctypes.c_double(c0_u),
+        conv(row_weight, np.float64, ctypes.c_double), conv(consistent, np.uint8, ctypes.c_uint8),
+        ctypes.c_int32(int(bool(consistent_u))), ctypes.c_double(k_tilt), ctypes.c_double(sign),
+        ctypes.c_int32(int(with_bt)), ctypes.c_int32(int(with_tilt)),
+        None if grad is None else grad.ctypes.data_as(dp), None if tg is None else tg.ctypes.data_as(dp),
+        e2.ctypes.data_as(dp))
+    if rc:
+        raise RuntimeError(f"emul_leaflet failed: {rc}")
+    return dict(E_bt=float(e2[0]), E_tilt=float(e2[1]), grad=grad, tilt_grad=tg)

@@ -1,0 +1,202 @@
+"""Leaflet tilt modules (BASELINE config 4: bending_tilt_in/out, tilt_in/out).
+
+Golden vectors: ``tests/golden/leaflet.npz`` -- outputs of the REAL reference on its caveolin free-disk mesh
+(``tests/golden/generate_golden.py leaflet``).  CPU tier: the oracle restatement and the host emulator of
+the device code against those vectors; GPU tier: the CUDA path through the C ABI.
+"""
+
+import os
+
+import numpy as np
+import pytest
+
+from ms_test_helpers import GOLDEN, emulate_leaflet, rel_err
+
+TOL = 1e-12
+STATES = ("r0", "r1", "r1c")
+LEAFLETS = ("in", "out")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(GOLDEN, "leaflet.npz"))
+
+
+def _inputs(gold, state, leaf):
+    pre = f"{state}_{leaf}_"
+    return dict(pos=gold[f"{state}_pos"], tri=gold[f"{state}_tri"], is_boundary=gold[f"{state}_is_boundary"],
+                tilts=gold[pre + "tilts"], keep=gold[pre + "keep"], interior=gold[pre + "interior"],
+                base_zero=gold[pre + "base_zero"], kappa=gold[pre + "kappa"], c0=gold[pre + "c0"],
+                sign=float(gold[pre + "sign"]), k_tilt=float(gold[pre + "k_tilt"]),
+                consistent=bool(gold[pre + "consistent"]))
+
+
+def _close(a, b):
+    assert abs(a - b) <= TOL * max(1.0, abs(b)), (a, b)
+
+
+@pytest.mark.parametrize("leaf", LEAFLETS)
+@pytest.mark.parametrize("state", STATES)
+def test_oracle_matches_reference(gold, state, leaf):
+    from oracle import ref_leaflet as rl
+
+    i = _inputs(gold, state, leaf)
+    pre = f"{state}_{leaf}_"
+    g, tg = np.zeros_like(i["pos"]), np.zeros_like(i["pos"])
+    e = rl.leaflet_bending_tilt_energy_and_gradient(i["pos"], i["tri"], i["tilts"], i["kappa"], i["c0"], sign=i["sign"],
+                                                    keep=i["keep"], interior=i["interior"], base_zero=i["base_zero"],
+                                                    is_boundary=i["is_boundary"], grad=g, tilt_grad=tg)
+    _close(e, float(gold[pre + "E_bt"]))
+    assert rel_err(g, gold[pre + "g_bt"]) <= TOL and rel_err(tg, gold[pre + "tg_bt"]) <= TOL
+    tg = np.zeros_like(i["pos"])
+    e = rl.leaflet_bending_tilt_energy_and_gradient(i["pos"], i["tri"], i["tilts"], i["kappa"], i["c0"], sign=i["sign"],
+                                                    keep=i["keep"], interior=i["interior"], base_zero=i["base_zero"],
+                                                    is_boundary=i["is_boundary"], grad=None, tilt_grad=tg)
+    _close(e, float(gold[pre + "E_bt_tiltonly"]))
+    assert rel_err(tg, gold[pre + "tg_bt_tiltonly"]) <= TOL
+    g, tg = np.zeros_like(i["pos"]), np.zeros_like(i["pos"])
+    e = rl.leaflet_tilt_energy_and_gradient(i["pos"], i["tri"], i["tilts"], i["k_tilt"], keep=i["keep"],
+                                            consistent=i["consistent"], grad=g, tilt_grad=tg)
+    _close(e, float(gold[pre + "E_tilt"]))
+    assert rel_err(g, gold[pre + "g_tilt"]) <= TOL and rel_err(tg, gold[pre + "tg_tilt"]) <= TOL
+
+
+@pytest.mark.parametrize("leaf", LEAFLETS)
+@pytest.mark.parametrize("state", STATES)
+def test_emulated_device_code_matches_reference(gold, state, leaf):
+    i = _inputs(gold, state, leaf)
+    pre = f"{state}_{leaf}_"
+    common = dict(sign=i["sign"], keep=i["keep"], is_boundary=i["is_boundary"], interior=i["interior"],
+                  base_zero=i["base_zero"], kappa=i["kappa"], c0=i["c0"], consistent_u=i["consistent"],
+                  k_tilt=i["k_tilt"])
+    r = emulate_leaflet(i["pos"], i["tri"], i["tilts"], with_bt=True, with_tilt=False, **common)
+    _close(r["E_bt"], float(gold[pre + "E_bt"]))
+    assert rel_err(r["grad"], gold[pre + "g_bt"]) <= TOL
+    assert rel_err(r["tilt_grad"], gold[pre + "tg_bt"]) <= TOL
+    r = emulate_leaflet(i["pos"], i["tri"], i["tilts"], with_bt=False, with_tilt=True, **common)
+    _close(r["E_tilt"], float(gold[pre + "E_tilt"]))
+    assert rel_err(r["grad"], gold[pre + "g_tilt"]) <= TOL
+    assert rel_err(r["tilt_grad"], gold[pre + "tg_tilt"]) <= TOL
+    # both modules of the leaflet in one sweep = the sum of the two
+    r = emulate_leaflet(i["pos"], i["tri"], i["tilts"], with_bt=True, with_tilt=True, **common)
+    assert rel_err(r["grad"], gold[pre + "g_bt"] + gold[pre + "g_tilt"]) <= TOL
+    assert rel_err(r["tilt_grad"], gold[pre + "tg_bt"] + gold[pre + "tg_tilt"]) <= TOL
+    # tilt-only evaluation (inner relaxation loop)
+    r = emulate_leaflet(i["pos"], i["tri"], i["tilts"], with_bt=True, with_tilt=True, want_grad=False, **common)
+    _close(r["E_bt"], float(gold[pre + "E_bt_tiltonly"]))
+    assert rel_err(r["tilt_grad"], gold[pre + "tg_bt_tiltonly"] + gold[pre + "tg_tilt_tiltonly"]) <= TOL
+
+
+def test_emulator_matches_oracle_with_row_weights_and_mixed_mass_modes(gold):
+    """Options the caveolin fixture does not exercise: active-row weights and a per-facet mass mode."""
+    from oracle import ref_leaflet as rl
+
+    i = _inputs(gold, "r1", "out")
+    rng = np.random.default_rng(5)
+    nv, nf = i["pos"].shape[0], i["tri"].shape[0]
+    w = rng.choice([0.0, 0.5, 1.0], size=nv)
+    cons = rng.random(nf) < 0.5
+    g, tg = np.zeros_like(i["pos"]), np.zeros_like(i["pos"])
+    e = rl.leaflet_tilt_energy_and_gradient(i["pos"], i["tri"], i["tilts"], i["k_tilt"], keep=i["keep"],
+                                            row_weights=w, consistent=cons, grad=g, tilt_grad=tg)
+    r = emulate_leaflet(i["pos"], i["tri"], i["tilts"], sign=1.0, keep=i["keep"], row_weight=w, consistent=cons,
+                        k_tilt=i["k_tilt"], with_bt=False, with_tilt=True)
+    _close(r["E_tilt"], e)
+    assert rel_err(r["grad"], g) <= TOL and rel_err(r["tilt_grad"], tg) <= TOL
+
+
+# ------------------------------------------------------------------ GPU tier (C ABI)
+def _device_leaflet(i, leaf, *, order_hint=None, **over):
+    from membrane_solver_b200 import _lib as L
+    from membrane_solver_b200.context import DeviceMesh
+
+    dm = DeviceMesh(0)
+    dm.set_topology(i["pos"].shape[0], i["tri"], is_boundary=i["is_boundary"].astype(np.uint8), order_hint=order_hint)
+    which = L.LEAFLET_IN if leaf == "in" else L.LEAFLET_OUT
+    args = dict(div_sign=i["sign"], kappa=i["kappa"], c0=i["c0"], k_tilt=i["k_tilt"], facet_keep=i["keep"],
+                interior=i["interior"], base_zero=i["base_zero"], consistent=i["consistent"])
+    args.update(over)
+    dm.set_leaflet(which, **args)
+    dm.set_positions(i["pos"])
+    dm.upload(L.ARR_TILTS_IN if leaf == "in" else L.ARR_TILTS_OUT, i["tilts"])
+    return dm, which, (L.ARR_TILT_GRAD_IN if leaf == "in" else L.ARR_TILT_GRAD_OUT)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("hint", [False, True], ids=["plain", "reordered"])
+@pytest.mark.parametrize("leaf", LEAFLETS)
+@pytest.mark.parametrize("state", STATES)
+def test_device_matches_reference(gold, state, leaf, hint):
+    from membrane_solver_b200 import _lib as L
+
+    i = _inputs(gold, state, leaf)
+    pre = f"{state}_{leaf}_"
+    dm, which, arr_tg = _device_leaflet(i, leaf, order_hint=i["pos"] if hint else None)
+    e_bt, e_t = dm.eval_leaflet(which, L.MOD_BENDING_TILT)
+    _close(e_bt, float(gold[pre + "E_bt"]))
+    assert e_t == 0.0
+    assert rel_err(dm.download(L.ARR_GRAD), gold[pre + "g_bt"]) <= TOL
+    assert rel_err(dm.download(arr_tg), gold[pre + "tg_bt"]) <= TOL
+    e_bt, e_t = dm.eval_leaflet(which, L.MOD_TILT)
+    _close(e_t, float(gold[pre + "E_tilt"]))
+    assert rel_err(dm.download(L.ARR_GRAD), gold[pre + "g_tilt"]) <= TOL
+    assert rel_err(dm.download(arr_tg), gold[pre + "tg_tilt"]) <= TOL
+    # both modules in one sweep, accumulated on top of the previous results
+    g_prev, tg_prev = dm.download(L.ARR_GRAD), dm.download(arr_tg)
+    e_bt, e_t = dm.eval_leaflet(which, L.MOD_TILT | L.MOD_BENDING_TILT, accumulate=L.ACC_GRAD | L.ACC_TILT_GRAD)
+    _close(e_bt, float(gold[pre + "E_bt"]))
+    _close(e_t, float(gold[pre + "E_tilt"]))
+    assert rel_err(dm.download(L.ARR_GRAD) - g_prev, gold[pre + "g_bt"] + gold[pre + "g_tilt"]) <= 4 * TOL
+    assert rel_err(dm.download(arr_tg) - tg_prev, gold[pre + "tg_bt"] + gold[pre + "tg_tilt"]) <= 4 * TOL
+    # tilt-only evaluation: the shape gradient array is left alone
+    g_before = dm.download(L.ARR_GRAD)
+    e_bt, e_t = dm.eval_leaflet(which, L.MOD_TILT | L.MOD_BENDING_TILT, want_grad=False)
+    _close(e_bt, float(gold[pre + "E_bt_tiltonly"]))
+    assert rel_err(dm.download(arr_tg), gold[pre + "tg_bt_tiltonly"] + gold[pre + "tg_tilt_tiltonly"]) <= TOL
+    assert np.array_equal(dm.download(L.ARR_GRAD), g_before)
+    # repeatable bit for bit (fixed-order gathers, no atomics)
+    dm.eval_leaflet(which, L.MOD_TILT | L.MOD_BENDING_TILT)
+    g1, t1 = dm.download(L.ARR_GRAD), dm.download(arr_tg)
+    dm.eval_leaflet(which, L.MOD_TILT | L.MOD_BENDING_TILT)
+    assert np.array_equal(dm.download(L.ARR_GRAD), g1) and np.array_equal(dm.download(arr_tg), t1)
+    dm.close()
+
+
+@pytest.mark.gpu
+def test_device_row_weights_mixed_mass_modes_and_errors(gold):
+    from membrane_solver_b200 import _lib as L
+    from membrane_solver_b200.context import DeviceMesh
+    from oracle import ref_leaflet as rl
+
+    i = _inputs(gold, "r1", "out")
+    rng = np.random.default_rng(5)
+    nv, nf = i["pos"].shape[0], i["tri"].shape[0]
+    w = rng.choice([0.0, 0.5, 1.0], size=nv)
+    cons = rng.random(nf) < 0.5
+    g, tg = np.zeros_like(i["pos"]), np.zeros_like(i["pos"])
+    e = rl.leaflet_tilt_energy_and_gradient(i["pos"], i["tri"], i["tilts"], i["k_tilt"], keep=i["keep"],
+                                            row_weights=w, consistent=cons, grad=g, tilt_grad=tg)
+    dm, which, arr_tg = _device_leaflet(i, "out", tilt_row_weight=w, facet_consistent=cons)
+    _, e_t = dm.eval_leaflet(which, L.MOD_TILT)
+    _close(e_t, e)
+    assert rel_err(dm.download(L.ARR_GRAD), g) <= TOL and rel_err(dm.download(arr_tg), tg) <= TOL
+    # uniform parameters as scalars = the same as arrays
+    dm.set_leaflet(which, div_sign=1.0, kappa=1.0, c0=0.0, k_tilt=i["k_tilt"], facet_keep=i["keep"],
+                   interior=i["interior"], base_zero=i["base_zero"])
+    e_bt, _ = dm.eval_leaflet(which, L.MOD_BENDING_TILT)
+    _close(e_bt, float(gold["r1_out_E_bt"]))
+    dm.close()
+    # loud failures: leaflet not configured, tilt field missing, foreign module bits
+    dm = DeviceMesh(0)
+    dm.set_topology(nv, i["tri"])
+    dm.set_positions(i["pos"])
+    with pytest.raises(L.B200Error):
+        dm.eval_leaflet(L.LEAFLET_IN, L.MOD_TILT)
+    dm.set_leaflet(L.LEAFLET_IN, div_sign=-1.0, kappa=1.0, k_tilt=1.0)
+    with pytest.raises(L.B200Error):
+        dm.eval_leaflet(L.LEAFLET_IN, L.MOD_TILT)
+    dm.upload(L.ARR_TILTS_IN, i["tilts"])
+    with pytest.raises(L.B200Error):
+        dm.eval_leaflet(L.LEAFLET_IN, L.MOD_SURFACE)
+    dm.eval_leaflet(L.LEAFLET_IN, L.MOD_TILT)
+    dm.close()
