@@ -72,7 +72,7 @@ class ParamResolver:
 
 class ArrayMesh:
     def __init__(self, positions, tri, *, global_params=None, facet_params=None, bodies=None, fixed=None,
-                 tilts=None, vertex_options=None):
+                 tilts=None, vertex_options=None, tilts_in=None, tilts_out=None, leaflets=None):
         self._positions = np.ascontiguousarray(positions, dtype=np.float64)
         self._tri = np.ascontiguousarray(tri, dtype=np.int32).reshape(-1, 3)
         nv = self._positions.shape[0]
@@ -88,6 +88,11 @@ class ArrayMesh:
             self.vertices[int(vid)] = type("V", (), {"options": dict(opts)})()
         self._fixed = np.zeros(nv, dtype=bool) if fixed is None else np.asarray(fixed, dtype=bool)
         self._tilts = np.zeros((nv, 3)) if tilts is None else np.asarray(tilts, dtype=np.float64)
+        self._tilts_in = np.zeros((nv, 3)) if tilts_in is None else np.asarray(tilts_in, dtype=np.float64)
+        self._tilts_out = np.zeros((nv, 3)) if tilts_out is None else np.asarray(tilts_out, dtype=np.float64)
+        # leaflet -> selections / parameters as plain arrays (keys of modules/energy/_leaflet.py: keep_bt, keep_tilt,
+        # interior, base_zero, kappa, c0, k_tilt, consistent, row_weight, facet_consistent)
+        self.leaflets = {k: dict(v) for k, v in (leaflets or {}).items()}
         self._version = 0
         self._facet_loops_version = 0
         self._vertex_ids_version = 0
@@ -103,6 +108,19 @@ class ArrayMesh:
 
     def tilts_view(self):
         return self._tilts
+
+    def tilts_in_view(self):
+        return self._tilts_in
+
+    def tilts_out_view(self):
+        return self._tilts_out
+
+    def leaflet_selection(self, leaflet: str) -> dict:
+        """What the reference derives from mesh options (leaflet presence, base-term rows, per-vertex
+        leaflet parameters), given here as arrays."""
+        if leaflet not in self.leaflets:
+            raise KeyError(f"ArrayMesh has no description of leaflet '{leaflet}' (leaflets={{...}})")
+        return self.leaflets[leaflet]
 
     def triangle_row_cache(self):
         return (self._tri if self._tri.shape[0] else None), None

@@ -1,0 +1,16 @@
+"""Outer-leaflet bending-tilt (splay) coupling on the B200 path.
+
+Twin of ``modules/energy/bending_tilt_out.py`` (which forwards to ``bending_tilt_leaflet.py:231-758, div_sign = +1``): same contract
+(``USES_TILT_LEAFLETS``, ``tilts_in`` / ``tilts_out`` / ``tilt_in_grad_arr`` / ``tilt_out_grad_arr`` keywords,
+``+=`` into caller-owned arrays, ``grad_arr=None`` = tilt-only evaluation).  See ``_leaflet.py``.
+"""
+
+from . import _common as C
+from . import _leaflet
+
+USES_TILT_LEAFLETS = True
+B200_LEAFLET = ("out", C.L.MOD_BENDING_TILT)
+
+compute_energy_and_gradient_array, compute_energy_array, compute_energy_and_gradient = _leaflet.make_module(*B200_LEAFLET)
+
+__all__ = ["compute_energy_and_gradient_array", "compute_energy_array", "compute_energy_and_gradient"]

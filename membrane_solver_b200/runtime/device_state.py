@@ -96,6 +96,7 @@ class DeviceState:
         self._bend_key = None
         self._tilt_key = None
         self._k_tilt = None
+        self._leaflet_key = {}     # leaflet -> hash of the description held by the device
         self.uploads = 0           # topology uploads (tests assert residency with this)
 
     # -- topology -------------------------------------------------------------
@@ -118,6 +119,7 @@ class DeviceState:
                              order_hint=positions)
         self.key, self.nv, self.nf = key, nv, int(tri.shape[0])
         self._gamma_key = self._bend_key = self._tilt_key = self._k_tilt = None
+        self._leaflet_key = {}
         self.uploads += 1
 
     # -- parameters (sent only when they change) ------------------------------
@@ -144,6 +146,45 @@ class DeviceState:
         if k_tilt != self._k_tilt:
             self.dm.set_tilt_rigidity(float(k_tilt))
             self._k_tilt = float(k_tilt)
+
+
+    def set_leaflet(self, leaflet: str, module_bits: int, spec: dict, div_sign: float) -> None:
+        """Send one leaflet's selections / parameters (``struct ms_leaflet_desc``) when they changed.
+        The coupling module may drop more facets than the tilt-magnitude module (transition triangles,
+        ``bt_payload.py:131-144``): the mask of the module about to run is the one held by the device."""
+        keep = spec.get("keep_bt") if (module_bits & L.MOD_BENDING_TILT) else spec.get("keep_tilt")
+        if (module_bits & L.MOD_BENDING_TILT) and (module_bits & L.MOD_TILT):
+            a, b = spec.get("keep_bt"), spec.get("keep_tilt")
+            if (a is None) != (b is None) or (a is not None and not np.array_equal(a, b)):
+                raise L.B200Error("the leaflet's two modules use different facet selections: evaluate them separately")
+        parts = []
+        for name, val in (("keep", keep), ("interior", spec.get("interior")), ("base_zero", spec.get("base_zero")),
+                          ("kappa", spec.get("kappa", 0.0)), ("c0", spec.get("c0", 0.0)),
+                          ("row_weight", spec.get("row_weight")), ("facet_consistent", spec.get("facet_consistent"))):
+            parts.append((name, None if val is None else (np.shape(val), hash(np.asarray(val).tobytes()))))
+        key = (tuple(parts), float(spec.get("k_tilt", 0.0)), bool(spec.get("consistent", False)), float(div_sign))
+        if self._leaflet_key.get(leaflet) == key:
+            return
+
+        def uniform(x):
+            a = np.asarray(x, dtype=np.float64)
+            return float(a.flat[0]) if a.ndim == 0 or (a.size and np.all(a == a.flat[0])) else a
+
+        def mask(x):
+            if x is None:
+                return None
+            m = np.asarray(x, dtype=bool)
+            return m.astype(np.uint8)
+
+        bz = mask(spec.get("base_zero"))
+        self.dm.set_leaflet(L.LEAFLET_IN if leaflet == "in" else L.LEAFLET_OUT, div_sign=div_sign,
+                            kappa=uniform(spec.get("kappa", 0.0)), c0=uniform(spec.get("c0", 0.0)),
+                            k_tilt=float(spec.get("k_tilt", 0.0)),
+                            facet_keep=None if keep is None or np.all(keep) else mask(keep),
+                            interior=mask(spec.get("interior")), base_zero=None if bz is None or not bz.any() else bz,
+                            tilt_row_weight=spec.get("row_weight"), facet_consistent=mask(spec.get("facet_consistent")),
+                            consistent=bool(spec.get("consistent", False)))
+        self._leaflet_key[leaflet] = key
 
 
 def get_state(mesh, positions: np.ndarray) -> DeviceState:

@@ -12,7 +12,9 @@ from __future__ import annotations
 import importlib
 import logging
 
-from ..modules.energy import NAMES
+from ..modules.energy import LEAFLET_NAMES, NAMES as _FUSED_NAMES
+
+NAMES = _FUSED_NAMES + LEAFLET_NAMES
 
 logger = logging.getLogger("membrane_solver")
 

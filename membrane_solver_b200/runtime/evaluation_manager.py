@@ -197,6 +197,130 @@ class EvaluationManager:
             total += scale * float(e)
         return float(total)
 
+    # -- leaflet tilt entry points (evaluation_manager.py:464-742) ---------------------------------
+    def _leaflet_pass(self, positions, tilts_in, tilts_out, *, tilt_in_grad_arr=None, tilt_out_grad_arr=None):
+        """Evaluate every loaded leaflet twin (``B200_LEAFLET``) on the device at frozen positions: ONE upload
+        of the positions and of each tilt field, ONE sweep per leaflet covering both of its modules, tilt
+        gradients only (the shape gradient is never needed by these entry points: the reference lets the
+        modules write it into a scratch array it discards).  Returns {module name: scaled energy}."""
+        from ..modules.energy import _leaflet as LF
+
+        pos = positions_array(positions)
+        st = get_state(self.mesh, pos)
+        groups: dict[str, list] = {}
+        for name, mod in zip(self.energy_module_names, self.energy_modules):
+            tag = getattr(mod, "B200_LEAFLET", None)
+            if tag is not None:
+                groups.setdefault(tag[0], []).append((name, tag[1], float(self.experimental_energy_scale_fn(str(name)))))
+        energies: dict[str, float] = {}
+        if not groups:
+            return energies
+        st.dm.set_positions(pos)
+        for leaflet, members in groups.items():
+            tilts = tilts_in if leaflet == "in" else tilts_out
+            out = tilt_in_grad_arr if leaflet == "in" else tilt_out_grad_arr
+            t = LF._leaflet_tilts(self.mesh, leaflet, tilts)
+            st.dm.upload(LF.ARR_TILTS[leaflet], t)
+            spec = LF.selection(self.mesh, self.global_params, self.param_resolver, leaflet)
+            a, b = spec.get("keep_bt"), spec.get("keep_tilt")
+            same_keep = (a is None and b is None) or (a is not None and b is not None and np.array_equal(a, b))
+            together = same_keep and len(members) > 1 and all(scale == 1.0 for _, _, scale in members)
+            batches = [members] if together else [[m] for m in members]
+            for batch in batches:
+                bits = 0
+                for name, bit, _ in batch:
+                    if LF.configure(st, self.mesh, self.global_params, self.param_resolver, leaflet, bit) is None:
+                        energies[name] = 0.0
+                    else:
+                        bits |= bit
+                if not bits:
+                    continue
+                if len(batch) > 1:
+                    st.set_leaflet(leaflet, bits, spec, LF.SIGN[leaflet])
+                e_bt, e_tilt = st.dm.eval_leaflet(LF.WHICH[leaflet], bits, want_grad=False, want_tilt_grad=out is not None)
+                scale = batch[0][2] if len(batch) == 1 else 1.0
+                for name, bit, sc in batch:
+                    if bit & bits:
+                        energies[name] = sc * (e_bt if bit == L.MOD_BENDING_TILT else e_tilt)
+                if out is not None:
+                    out += scale * st.dm.download(LF.ARR_TILT_GRAD[leaflet])
+        return energies
+
+    def _other_leaflet_energy(self, name, mod, *, positions, tilts_in, tilts_out, grad_arr, tilt_in_grad_arr=None,
+                              tilt_out_grad_arr=None) -> float:
+        """A module without a leaflet twin, through the reference's array contract (keywords the signature does
+        not list are dropped by ``_call_fn``, as ``evaluation_manager.py:88-124`` does)."""
+        index_map = self.mesh.vertex_index_to_row
+        scale = float(self.experimental_energy_scale_fn(str(name)))
+        before = None
+        if abs(scale - 1.0) > 1.0e-15 and tilt_in_grad_arr is not None:
+            before = (tilt_in_grad_arr.copy(), tilt_out_grad_arr.copy())
+        e = self._call_fn(mod.compute_energy_and_gradient_array, positions=positions, index_map=index_map,
+                          grad_arr=grad_arr, tilts_in=tilts_in, tilts_out=tilts_out,
+                          tilt_in_grad_arr=tilt_in_grad_arr, tilt_out_grad_arr=tilt_out_grad_arr)
+        if before is not None:
+            tilt_in_grad_arr[:] = before[0] + scale * (tilt_in_grad_arr - before[0])
+            tilt_out_grad_arr[:] = before[1] + scale * (tilt_out_grad_arr - before[1])
+        return scale * self._coerce(e)
+
+    def compute_energy_and_leaflet_tilt_gradients_array(self, *, positions, tilts_in, tilts_out, tilt_in_grad_arr,
+                                                        tilt_out_grad_arr, tilt_vertex_areas_in=None,
+                                                        tilt_vertex_areas_out=None, grad_dummy=None,
+                                                        tilt_only: bool = False) -> float:
+        """Total energy and leaflet tilt gradients at frozen positions (``evaluation_manager.py:630-742``).
+        ``tilt_vertex_areas_*`` (the reference's closed form for lumped ``tilt_in`` / ``tilt_out``) are accepted
+        and not needed: the device evaluates the modules themselves, which gives the same value."""
+        _ = (tilt_vertex_areas_in, tilt_vertex_areas_out)
+        if grad_dummy is None:
+            grad_dummy = np.zeros_like(np.asarray(positions, dtype=np.float64))
+        else:
+            grad_dummy.fill(0.0)
+        tilt_in_grad_arr.fill(0.0)
+        tilt_out_grad_arr.fill(0.0)
+        done = self._leaflet_pass(positions, tilts_in, tilts_out, tilt_in_grad_arr=tilt_in_grad_arr,
+                                  tilt_out_grad_arr=tilt_out_grad_arr)
+        total = float(sum(done.values()))
+        for name, mod in zip(self.energy_module_names, self.energy_modules):
+            if name in done:
+                continue
+            leafy = getattr(mod, "USES_TILT_LEAFLETS", False)
+            total += self._other_leaflet_energy(name, mod, positions=positions, tilts_in=tilts_in, tilts_out=tilts_out,
+                                                grad_arr=None if (tilt_only and leafy) else grad_dummy,
+                                                tilt_in_grad_arr=tilt_in_grad_arr, tilt_out_grad_arr=tilt_out_grad_arr)
+        return float(total)
+
+    def compute_tilt_dependent_energy_with_leaflet_tilts(self, *, positions, tilts_in, tilts_out, grad_dummy=None,
+                                                         tilt_vertex_areas_in=None, tilt_vertex_areas_out=None) -> float:
+        """Energy of the leaflet-tilt modules only (``evaluation_manager.py:537-628``)."""
+        _ = (grad_dummy, tilt_vertex_areas_in, tilt_vertex_areas_out)
+        done = self._leaflet_pass(positions, tilts_in, tilts_out)
+        total = float(sum(done.values()))
+        for name, mod in zip(self.energy_module_names, self.energy_modules):
+            if name in done or not getattr(mod, "USES_TILT_LEAFLETS", False):
+                continue
+            total += self._other_leaflet_energy(name, mod, positions=positions, tilts_in=tilts_in, tilts_out=tilts_out,
+                                                grad_arr=None)
+        return float(total)
+
+    def compute_energy_array_with_leaflet_tilts(self, *, positions, tilts_in, tilts_out, grad_dummy=None) -> float:
+        """Total energy for fixed positions and leaflet tilt arrays (``evaluation_manager.py:464-535``)."""
+        done = self._leaflet_pass(positions, tilts_in, tilts_out)
+        total = float(sum(done.values()))
+        fused = [(n, m) for n, m in zip(self.energy_module_names, self.energy_modules)
+                 if hasattr(m, "B200_MODULE")]
+        part = self._fused_eval(positions, fused, want_grad=False) if fused else None
+        if part is not None:
+            for name, e in part[0].items():
+                total += float(self.experimental_energy_scale_fn(str(name))) * e
+                done[name] = e
+        for name, mod in zip(self.energy_module_names, self.energy_modules):
+            if name in done:
+                continue
+            dummy = np.zeros_like(np.asarray(positions, dtype=np.float64))
+            total += self._other_leaflet_energy(name, mod, positions=positions, tilts_in=tilts_in, tilts_out=tilts_out,
+                                                grad_arr=dummy)
+        return float(total)
+
     def compute_energy_array_total(self, *, positions) -> float:
         """Total energy for fixed positions (``evaluation_manager.py:184-225``)."""
         return float(sum(self.compute_energy_breakdown(positions=positions).values()))

@@ -93,6 +93,36 @@ class FakeDeviceMesh:
             return np.array(self.pos)
         return np.array(self.arrays[which])
 
+    def upload(self, which, host):
+        self.arrays[which] = np.array(host, dtype=np.float64)
+
+    # -- leaflet modules (emulated ms_leaflet.cuh bodies) --
+    def set_leaflet(self, leaflet, **desc):
+        self.__dict__.setdefault("leaflets", {})[int(leaflet)] = desc
+        self.leaflet_uploads = getattr(self, "leaflet_uploads", 0) + 1
+
+    def eval_leaflet(self, leaflet, modules, *, want_grad=True, want_tilt_grad=True, accumulate=0, use_trial=False):
+        if int(leaflet) not in getattr(self, "leaflets", {}):
+            raise L.B200Error("ms_ctx_set_leaflet has not been called for this leaflet")
+        d = self.leaflets[int(leaflet)]
+        arr_t = L.ARR_TILTS_IN if leaflet == L.LEAFLET_IN else L.ARR_TILTS_OUT
+        arr_g = L.ARR_TILT_GRAD_IN if leaflet == L.LEAFLET_IN else L.ARR_TILT_GRAD_OUT
+        k, c = d.get("kappa", 0.0), d.get("c0", 0.0)
+        r = H.emulate_leaflet(self.trial if use_trial else self.pos, self.tri, self.arrays[arr_t], sign=d["div_sign"],
+                              keep=d.get("facet_keep"), is_boundary=self.is_boundary, interior=d.get("interior"),
+                              base_zero=d.get("base_zero"), kappa=k if np.ndim(k) else None,
+                              kappa_u=0.0 if np.ndim(k) else float(k), c0=c if np.ndim(c) else None,
+                              c0_u=0.0 if np.ndim(c) else float(c), row_weight=d.get("tilt_row_weight"),
+                              consistent=d.get("facet_consistent"), consistent_u=d.get("consistent", False),
+                              k_tilt=d.get("k_tilt", 0.0), with_bt=bool(modules & L.MOD_BENDING_TILT),
+                              with_tilt=bool(modules & L.MOD_TILT), want_grad=want_grad, want_tilt_grad=want_tilt_grad)
+        self.evals += 1
+        if want_grad:
+            self.arrays[L.ARR_GRAD] = r["grad"] + (self.arrays[L.ARR_GRAD] if accumulate & L.ACC_GRAD else 0.0)
+        if want_tilt_grad:
+            self.arrays[arr_g] = r["tilt_grad"] + (self.arrays[arr_g] if accumulate & L.ACC_TILT_GRAD else 0.0)
+        return r["E_bt"], r["E_tilt"]
+
     # -- device-resident loop (numpy restatement of the small kernels; TEST ONLY) --
     def set_positions(self, pos):
         self.pos = np.array(pos, dtype=np.float64)

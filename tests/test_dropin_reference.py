@@ -63,7 +63,7 @@ def b200_installed(monkeypatch):
     saved_cv = (ref_cv.constraint_gradients_array, ref_cv.constraint_gradients)
     monkeypatch.setattr(device_state, "DEVICE_MESH_FACTORY", FakeDeviceMesh)
     yield energy_manager.install
-    for name in ("surface", "volume", "bending", "tilt"):
+    for name in energy_manager.NAMES:
         key = f"modules.energy.{name}"
         if saved.get(key) is not None:
             sys.modules[key] = saved[key]
@@ -107,3 +107,74 @@ def test_reference_minimizer_runs_on_b200_plugins(b200_installed, path, levels, 
     p = np.array([mesh.vertices[v].position for v in sorted(mesh.vertices)])
     assert np.max(np.abs(p - p_ref)) <= 1e-9
     _ = (res, res_ref)
+
+
+CAVEOLIN = "meshes/caveolin/kozlov_1disk_3d_tensionless_single_leaflet_profile_hard_rim_R12_free_disk.yaml"
+
+
+def _build_caveolin(seed=3):
+    load_data, parse_geometry, CMM, EMM, Minimizer, refine, GD = _ref_imports()
+    mesh = refine(parse_geometry(load_data(os.path.join(REF, CAVEOLIN))))
+    rng = np.random.default_rng(seed)
+    nv = len(mesh.vertex_ids)
+    pos = np.array(mesh.positions_view())
+    pos[:, 2] += 0.03 * rng.standard_normal(nv)
+    tilts_in, tilts_out = 0.1 * rng.standard_normal((nv, 3)), 0.1 * rng.standard_normal((nv, 3))
+    gp = mesh.global_parameters
+    mini = Minimizer(mesh, gp, GD(), EMM(mesh.energy_modules), CMM(mesh.constraint_modules), quiet=True)
+    return mesh, mini, pos, tilts_in, tilts_out
+
+
+def test_reference_leaflet_entry_points_run_on_b200_plugins(b200_installed):
+    """BASELINE config 4 (caveolin free disk: bending_tilt_in/out, tilt_in/out + a contact module that stays the
+    reference's): the reference's own EvaluationManager drives the B200 leaflet twins; selections come from the
+    reference's helpers (leaflet presence, base-term rows, per-vertex parameters)."""
+
+    def run(mini, pos, ti, to):
+        ev = mini._evaluation_manager if hasattr(mini, "_evaluation_manager") else mini.evaluation_manager
+        gi, go = np.zeros_like(pos), np.zeros_like(pos)
+        e_t = ev.compute_energy_and_leaflet_tilt_gradients_array(positions=pos, tilts_in=ti, tilts_out=to,
+                                                                 tilt_in_grad_arr=gi, tilt_out_grad_arr=go)
+        gi2, go2 = np.zeros_like(pos), np.zeros_like(pos)
+        e_only = ev.compute_energy_and_leaflet_tilt_gradients_array(positions=pos, tilts_in=ti, tilts_out=to,
+                                                                    tilt_in_grad_arr=gi2, tilt_out_grad_arr=go2,
+                                                                    tilt_only=True)
+        e_dep = ev.compute_tilt_dependent_energy_with_leaflet_tilts(positions=pos, tilts_in=ti, tilts_out=to)
+        e_tot = ev.compute_energy_array_with_leaflet_tilts(positions=pos, tilts_in=ti, tilts_out=to)
+        return e_t, gi, go, e_only, gi2, go2, e_dep, e_tot
+
+    mesh_ref, mini_ref, pos, ti, to = _build_caveolin()
+    want = run(mini_ref, pos, ti, to)
+    mods_ref = {n: m for n, m in zip(mesh_ref.energy_modules, mini_ref.energy_modules)}
+    shape_ref = {}
+    for name in ("bending_tilt_in", "bending_tilt_out", "tilt_in", "tilt_out"):
+        g = np.zeros_like(pos)
+        e = mods_ref[name].compute_energy_and_gradient_array(
+            mesh_ref, mesh_ref.global_parameters, mini_ref.param_resolver, positions=pos,
+            index_map=mesh_ref.vertex_index_to_row, grad_arr=g, tilts_in=ti, tilts_out=to,
+            tilt_in_grad_arr=np.zeros_like(pos), tilt_out_grad_arr=np.zeros_like(pos))
+        shape_ref[name] = (e, g)
+
+    bound = b200_installed()
+    assert "modules.energy.bending_tilt_in" in bound and "modules.energy.tilt_out" in bound
+    mesh, mini, pos2, ti2, to2 = _build_caveolin()
+    assert np.array_equal(pos, pos2)
+    mods = {n: m for n, m in zip(mesh.energy_modules, mini.energy_modules)}
+    for name in ("bending_tilt_in", "bending_tilt_out", "tilt_in", "tilt_out"):
+        assert mods[name].__name__.startswith("membrane_solver_b200."), mods[name].__name__
+    assert not mods["tilt_thetaB_contact_in"].__name__.startswith("membrane_solver_b200.")
+    got = run(mini, pos, ti, to)
+    for a, b in zip(got, want):
+        if np.ndim(b) == 0:
+            assert abs(a - b) <= 1e-12 * max(1.0, abs(b)), (a, b)
+        else:
+            assert np.max(np.abs(a - b)) <= 1e-12 * max(1.0, np.max(np.abs(b)))
+    for name, (e_ref, g_ref) in shape_ref.items():
+        g = np.zeros_like(pos)
+        e = mods[name].compute_energy_and_gradient_array(
+            mesh, mesh.global_parameters, mini.param_resolver, positions=pos, index_map=mesh.vertex_index_to_row,
+            grad_arr=g, tilts_in=ti, tilts_out=to, tilt_in_grad_arr=np.zeros_like(pos),
+            tilt_out_grad_arr=np.zeros_like(pos))
+        assert abs(e - e_ref) <= 1e-12 * max(1.0, abs(e_ref)), name
+        assert np.max(np.abs(g - g_ref)) <= 1e-12 * max(1.0, np.max(np.abs(g_ref))), name
+    assert mesh._b200_state.uploads == 1

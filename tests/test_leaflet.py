@@ -200,3 +200,136 @@ def test_device_row_weights_mixed_mass_modes_and_errors(gold):
         dm.eval_leaflet(L.LEAFLET_IN, L.MOD_SURFACE)
     dm.eval_leaflet(L.LEAFLET_IN, L.MOD_TILT)
     dm.close()
+
+
+# ------------------------------------------------------------------ plugin level
+def _array_mesh(gold, state):
+    from membrane_solver_b200.geometry.array_mesh import ArrayMesh
+
+    leaflets, tilts = {}, {}
+    for leaf in LEAFLETS:
+        i = _inputs(gold, state, leaf)
+        leaflets[leaf] = dict(keep_bt=i["keep"], keep_tilt=i["keep"], interior=i["interior"], base_zero=i["base_zero"],
+                              kappa=i["kappa"], c0=i["c0"], k_tilt=i["k_tilt"], consistent=i["consistent"])
+        tilts[leaf] = i["tilts"]
+    return ArrayMesh(gold[f"{state}_pos"], gold[f"{state}_tri"], tilts_in=tilts["in"], tilts_out=tilts["out"],
+                     leaflets=leaflets)
+
+
+def _plugin_checks(gold, state):
+    import importlib
+
+    mesh = _array_mesh(gold, state)
+    pos = mesh.positions_view()
+    idx = mesh.vertex_index_to_row
+    for leaf in LEAFLETS:
+        for name, tag in ((f"bending_tilt_{leaf}", "bt"), (f"tilt_{leaf}", "tilt")):
+            mod = importlib.import_module(f"membrane_solver_b200.modules.energy.{name}")
+            assert mod.USES_TILT_LEAFLETS
+            pre = f"{state}_{leaf}_"
+            g = np.full_like(pos, 0.25)                       # plugins ADD into caller-owned arrays
+            tg = {"in": np.full_like(pos, -0.5), "out": np.full_like(pos, 0.75)}
+            e = mod.compute_energy_and_gradient_array(mesh, mesh.global_params, None, positions=pos, index_map=idx,
+                                                      grad_arr=g, tilts_in=mesh.tilts_in_view(),
+                                                      tilts_out=mesh.tilts_out_view(), tilt_in_grad_arr=tg["in"],
+                                                      tilt_out_grad_arr=tg["out"])
+            _close(e, float(gold[pre + f"E_{tag}"]))
+            assert rel_err(g - 0.25, gold[pre + f"g_{tag}"]) <= 4 * TOL
+            other = "out" if leaf == "in" else "in"
+            assert rel_err(tg[leaf] - (-0.5 if leaf == "in" else 0.75), gold[pre + f"tg_{tag}"]) <= 4 * TOL
+            assert np.all(tg[other] == (-0.5 if other == "in" else 0.75))     # the other leaflet is untouched
+            # tilt-only evaluation and the energy-only entry point (tilts default to the mesh's own)
+            t2 = np.zeros_like(pos)
+            kw = {f"tilt_{leaf}_grad_arr": t2}
+            e2 = mod.compute_energy_and_gradient_array(mesh, mesh.global_params, None, positions=pos, index_map=idx,
+                                                       grad_arr=None, **kw)
+            _close(e2, float(gold[pre + f"E_{tag}_tiltonly"]))
+            assert rel_err(t2, gold[pre + f"tg_{tag}_tiltonly"]) <= TOL
+            _close(mod.compute_energy_array(mesh, mesh.global_params, None, positions=pos, index_map=idx),
+                   float(gold[pre + f"E_{tag}"]))
+            ed, gd, tgd = mod.compute_energy_and_gradient(mesh, mesh.global_params, None)
+            _close(ed, float(gold[pre + f"E_{tag}"]))
+            assert rel_err(np.array([gd[v] for v in range(len(pos))]), gold[pre + f"g_{tag}"]) <= TOL
+    st = mesh._b200_state
+    assert st.uploads == 1                                    # one topology upload for all of the above
+    with pytest.raises(ValueError):
+        importlib.import_module("membrane_solver_b200.modules.energy.tilt_in").compute_energy_and_gradient_array(
+            mesh, mesh.global_params, None, positions=pos, index_map=idx, grad_arr=None, tilts_in=np.zeros((3, 3)))
+    from membrane_solver_b200 import _lib as L
+    from membrane_solver_b200.geometry.array_mesh import GlobalParams
+
+    for key, val in (("theory_parity_lane", "stage_a_emergent"), ("tilt_transport_model", "connection_v1"),
+                     ("bending_gradient_mode", "approx"), ("bending_tilt_in_update_mode", "radial_cross_term_off_v1")):
+        gp = GlobalParams({key: val})
+        with pytest.raises(L.B200Error):
+            importlib.import_module("membrane_solver_b200.modules.energy.bending_tilt_in").compute_energy_array(
+                mesh, gp, None, positions=pos, index_map=idx)
+
+
+@pytest.mark.parametrize("state", ["r0", "r1c"])
+def test_plugins_on_emulated_device(gold, state, monkeypatch):
+    from fake_device import FakeDeviceMesh
+
+    from membrane_solver_b200.runtime import device_state
+
+    monkeypatch.setattr(device_state, "DEVICE_MESH_FACTORY", FakeDeviceMesh)
+    _plugin_checks(gold, state)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("state", ["r0", "r1", "r1c"])
+def test_plugins_on_device(gold, state):
+    _plugin_checks(gold, state)
+
+
+def _manager_checks(gold, state):
+    """The B200 EvaluationManager's leaflet entry points: all four twins in one device pass."""
+    import importlib
+
+    from membrane_solver_b200.runtime.evaluation_manager import EvaluationManager
+
+    mesh = _array_mesh(gold, state)
+    names = ["bending_tilt_in", "bending_tilt_out", "tilt_in", "tilt_out"]
+    mods = [importlib.import_module(f"membrane_solver_b200.modules.energy.{n}") for n in names]
+    ev = EvaluationManager(mesh=mesh, global_params=mesh.global_params, param_resolver=None, energy_modules=mods,
+                           energy_module_names=names)
+    pos = mesh.positions_view()
+    ti, to = mesh.tilts_in_view(), mesh.tilts_out_view()
+    gi, go = np.ones_like(pos), np.ones_like(pos)            # overwritten, not accumulated (":651-652")
+    e = ev.compute_energy_and_leaflet_tilt_gradients_array(positions=pos, tilts_in=ti, tilts_out=to,
+                                                           tilt_in_grad_arr=gi, tilt_out_grad_arr=go, tilt_only=True)
+    want_e = sum(float(gold[f"{state}_{leaf}_E_{tag}"]) for leaf in LEAFLETS for tag in ("bt", "tilt"))
+    _close(e, want_e)
+    for leaf, got in (("in", gi), ("out", go)):
+        want = gold[f"{state}_{leaf}_tg_bt_tiltonly"] + gold[f"{state}_{leaf}_tg_tilt_tiltonly"]
+        assert rel_err(got, want) <= TOL
+    _close(ev.compute_tilt_dependent_energy_with_leaflet_tilts(positions=pos, tilts_in=ti, tilts_out=to), want_e)
+    _close(ev.compute_energy_array_with_leaflet_tilts(positions=pos, tilts_in=ti, tilts_out=to), want_e)
+    # a per-module experimental scale splits the sweep and scales energy and gradient alike
+    ev2 = EvaluationManager(mesh=mesh, global_params=mesh.global_params, param_resolver=None, energy_modules=mods,
+                            energy_module_names=names,
+                            experimental_energy_scale_fn=lambda n: 0.5 if n == "tilt_in" else 1.0)
+    gi2, go2 = np.zeros_like(pos), np.zeros_like(pos)
+    e2 = ev2.compute_energy_and_leaflet_tilt_gradients_array(positions=pos, tilts_in=ti, tilts_out=to,
+                                                             tilt_in_grad_arr=gi2, tilt_out_grad_arr=go2)
+    _close(e2, want_e - 0.5 * float(gold[f"{state}_in_E_tilt"]))
+    assert rel_err(gi2, gold[f"{state}_in_tg_bt"] + 0.5 * gold[f"{state}_in_tg_tilt"]) <= TOL
+    assert rel_err(go2, go) <= TOL
+    return mesh
+
+
+def test_manager_leaflet_entry_points_on_emulated_device(gold, monkeypatch):
+    from fake_device import FakeDeviceMesh
+
+    from membrane_solver_b200.runtime import device_state
+
+    monkeypatch.setattr(device_state, "DEVICE_MESH_FACTORY", FakeDeviceMesh)
+    mesh = _manager_checks(gold, "r1")
+    fake = mesh._b200_state.dm
+    assert fake.topology_uploads == 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("state", ["r1", "r1c"])
+def test_manager_leaflet_entry_points_on_device(gold, state):
+    _manager_checks(gold, state)
