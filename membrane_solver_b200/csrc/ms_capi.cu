@@ -301,7 +301,7 @@ int bt_prepare(ms_ctx* c, ms::BtMesh& m) {
     if (int rc = c->d_bt_corner.ensure(12 * nf + 1)) return rc;
     if (int rc = c->d_bt_base.ensure(nv + 1)) return rc;
     if (int rc = c->d_bt_facet_e.ensure(nf + 1)) return rc;
-    if (int rc = c->d_bt_e.ensure(1)) return rc;
+    if (int rc = c->d_bt_e.ensure(1 + ms::kSumBlocks)) return rc;
     c->bt_ready = true;
   }
   m.nv = c->nv;
@@ -959,7 +959,7 @@ int ms_ctx_eval_leaflet(ms_ctx* c, int32_t leaflet, uint32_t modules, int32_t wa
   if (int rc = c->d_lf_shape.ensure(9 * nf + 1)) return rc;
   if (int rc = c->d_lf_tilt.ensure(9 * nf + 1)) return rc;
   if (int rc = c->d_lf_facet_e.ensure(2 * nf + 1)) return rc;
-  if (int rc = c->d_lf_e.ensure(2)) return rc;
+  if (int rc = c->d_lf_e.ensure(2 + 2 * ms::kSumBlocks)) return rc;
   ms::LeafletMesh m;
   m.nv = c->nv;
   m.nf = c->nf;

@@ -725,6 +725,20 @@ __global__ void k_gather(int nv, const int32_t* __restrict__ ptr, const int32_t*
                          double* out, int out_stride, int accumulate) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= nv) return;
+  if (dim == 3) {  // the common case: one pass over the corner list, three running sums (same order per component)
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    for (int j = ptr[v]; j < ptr[v + 1]; ++j) {
+      const double* q = corner + size_t(idx[j]) * in_stride + in_off;
+      a0 += q[0];
+      a1 += q[1];
+      a2 += q[2];
+    }
+    double* o = out + size_t(v) * out_stride;
+    o[0] = accumulate ? o[0] + a0 : a0;
+    o[1] = accumulate ? o[1] + a1 : a1;
+    o[2] = accumulate ? o[2] + a2 : a2;
+    return;
+  }
   for (int d = 0; d < dim; ++d) {
     double acc = 0.0;
     for (int j = ptr[v]; j < ptr[v + 1]; ++j) acc += corner[size_t(idx[j]) * in_stride + in_off + d];
@@ -770,6 +784,18 @@ __global__ void __launch_bounds__(256) k_sum(const double* __restrict__ x, int64
   for (int64_t i = threadIdx.x; i < n; i += blockDim.x) v[0] += x[i];
   block_sum<1>(v, red, 256, 0);
   if (threadIdx.x == 0) *out = v[0] * scale;
+}
+
+// Two-stage fixed-order sum for long arrays: block b sums the contiguous chunk b (threads strided inside
+// it) into partial[b]; k_sum then adds the partials in index order.  Same result on every run.
+__global__ void __launch_bounds__(256) k_sum_partial(const double* __restrict__ x, int64_t n, double* partial) {
+  __shared__ double red[32];
+  const int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = chunk * blockIdx.x, hi = lo + chunk < n ? lo + chunk : n;
+  double v[1] = {0.0};
+  for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) v[0] += x[i];
+  block_sum<1>(v, red, 256, 0);
+  if (threadIdx.x == 0) partial[blockIdx.x] = v[0];
 }
 
 // ---- bending-tilt coupling (ms_bt.cuh): per-facet / per-vertex passes on global arrays ----
@@ -1109,6 +1135,16 @@ cudaError_t launch_sum(const double* x, int64_t n, double scale, double* out, cu
   return cudaGetLastError();
 }
 
+// sum of x[0..n) * scale -> *out; scratch holds kSumBlocks doubles (used for long arrays only)
+static void sum_fixed_order(const double* x, int64_t n, double scale, double* out, double* scratch, cudaStream_t st) {
+  if (n < (int64_t(1) << 16)) {
+    k_sum<<<1, 256, 0, st>>>(x, n, scale, out);
+  } else {
+    k_sum_partial<<<kSumBlocks, 256, 0, st>>>(x, n, scratch);
+    k_sum<<<1, 256, 0, st>>>(scratch, kSumBlocks, scale, out);
+  }
+}
+
 cudaError_t launch_bt_stage(const BtMesh& m, double sign, const double* k_vecs, const double* a_vor,
                             const double* a_eff, double* corner /* 12*nf doubles */, double* seeds, double* base,
                             double* facet_e, double* e_out, bool tilt_grads, cudaStream_t st) {
@@ -1116,7 +1152,7 @@ cudaError_t launch_bt_stage(const BtMesh& m, double sign, const double* k_vecs, 
   if (m.nv > 0) k_bt_vertex<<<blocks_for(m.nv, 128), 128, 0, st>>>(m, k_vecs, a_vor, a_eff, corner, seeds, base);
   // the corner buffer is free again: it now receives the tilt-gradient contributions (9 per facet)
   if (m.nf > 0) k_bt_facet_b<<<blocks_for(m.nf, 128), 128, 0, st>>>(m, base, sign, tilt_grads ? corner : nullptr, facet_e);
-  k_sum<<<1, 256, 0, st>>>(facet_e, m.nf, 1.0, e_out);
+  sum_fixed_order(facet_e, m.nf, 1.0, e_out, e_out + 1, st);
   return cudaGetLastError();
 }
 
@@ -1144,8 +1180,8 @@ cudaError_t launch_leaflet(const LeafletMesh& m, bool with_bt, bool with_tilt, d
     k_lf_facet_b<<<blocks_for(m.nf, 128), 128, 0, st>>>(m, vbuf, with_bt ? 1 : 0, with_tilt ? 1 : 0,
                                                         grad ? corner_shape : nullptr, tilt_grad ? corner_tilt : nullptr,
                                                         facet_e);
-  k_sum<<<1, 256, 0, st>>>(facet_e, m.nf, 1.0, e_out2);
-  k_sum<<<1, 256, 0, st>>>(facet_e + size_t(m.nf), m.nf, 1.0, e_out2 + 1);
+  sum_fixed_order(facet_e, m.nf, 1.0, e_out2, e_out2 + 2, st);
+  sum_fixed_order(facet_e + size_t(m.nf), m.nf, 1.0, e_out2 + 1, e_out2 + 2 + kSumBlocks, st);
   if (m.nv > 0 && grad)
     k_gather<<<blocks_for(m.nv, 128), 128, 0, st>>>(m.nv, m.csr_ptr, m.csr_idx, corner_shape, 3, 0, 3, grad, 3,
                                                      accumulate_grad ? 1 : 0);

@@ -151,7 +151,8 @@ cudaError_t launch_axpy_rows(const double* x, double alpha, const uint8_t* fixed
 cudaError_t launch_cg_direction(const double* g, const double* pg, const double* pd, const uint8_t* fixed,
                                 int64_t nv, double* d, cudaStream_t st);
 
-// --- bending-tilt coupling on the resident mesh (ms_bt.cuh); corner holds 12*nf doubles ---
+constexpr int kSumBlocks = 592;  // partial sums of the two-stage fixed-order reductions (4 CTAs per SM)
+// --- bending-tilt coupling on the resident mesh (ms_bt.cuh); corner holds 12*nf doubles, e_out 1 + kSumBlocks ---
 // stage: divergence / effective areas -> vertex seeds (into `seeds`, read by pass B) and base term ->
 // per-facet energy (sum into e_out) and, when tilt_grads, corner contributions of the tilt gradient
 cudaError_t launch_bt_stage(const BtMesh& m, double sign, const double* k_vecs, const double* a_vor,
@@ -162,7 +163,7 @@ cudaError_t launch_bt_tilt_gather(const BtMesh& m, const double* corner3, double
 cudaError_t launch_bt_finalize(const double* e_bt, double* scalars, cudaStream_t st);
 
 // --- leaflet tilt modules (ms_leaflet.cuh).  corner: 27*nf doubles, vbuf: 5*nv, corner_shape / corner_tilt:
-// 9*nf each, facet_e: 2*nf, e_out2: {E_bending_tilt, E_tilt}.  grad / tilt_grad may be null. ---
+// 9*nf each, facet_e: 2*nf, e_out2: {E_bending_tilt, E_tilt} followed by 2*kSumBlocks doubles of scratch.  grad / tilt_grad may be null. ---
 cudaError_t launch_leaflet(const LeafletMesh& m, bool with_bt, bool with_tilt, double* corner, double* vbuf,
                            double* corner_shape, double* corner_tilt, double* facet_e, double* e_out2, double* grad,
                            bool accumulate_grad, double* tilt_grad, bool accumulate_tilt_grad, cudaStream_t st);

@@ -178,3 +178,29 @@ def test_reference_leaflet_entry_points_run_on_b200_plugins(b200_installed):
         assert abs(e - e_ref) <= 1e-12 * max(1.0, abs(e_ref)), name
         assert np.max(np.abs(g - g_ref)) <= 1e-12 * max(1.0, np.max(np.abs(g_ref))), name
     assert mesh._b200_state.uploads == 1
+
+
+def test_reference_minimizer_config4_trajectory_on_b200_leaflet_plugins(b200_installed):
+    """BASELINE configs[3]: the reference's full step on the caveolin free-disk mesh -- leaflet tilt relaxation
+    (``TiltRelaxationManager.relax_leaflet_tilts``, coupled mode), shape step, rigid-disk / pin / rim constraints --
+    unmodified, with the four leaflet energy modules replaced by the B200 twins: same energies, positions and
+    tilt fields step by step (north_star: trajectories within 1e-9)."""
+    load_data, parse_geometry, CMM, EMM, Minimizer, refine, GD = _ref_imports()
+
+    def run(steps=3):
+        mesh = parse_geometry(load_data(os.path.join(REF, CAVEOLIN)))
+        mini = Minimizer(mesh, mesh.global_parameters, GD(), EMM(mesh.energy_modules), CMM(mesh.constraint_modules),
+                         quiet=True)
+        energies = [mini.minimize(n_steps=1)["energy"] for _ in range(steps)]
+        return (mini, np.array(energies), np.array(mesh.positions_view()), np.array(mesh.tilts_in_view()),
+                np.array(mesh.tilts_out_view()))
+
+    _, e_ref, p_ref, ti_ref, to_ref = run()
+    b200_installed()
+    mini, e, p, ti, to = run()
+    names = [m.__name__ for m in mini.energy_modules]
+    assert sum(n.startswith("membrane_solver_b200.") for n in names) == 4, names
+    assert np.max(np.abs(e - e_ref)) <= 1e-9 * max(1.0, np.max(np.abs(e_ref))), (e, e_ref)
+    assert np.max(np.abs(p - p_ref)) <= 1e-9
+    assert np.max(np.abs(ti - ti_ref)) <= 1e-9 and np.max(np.abs(to - to_ref)) <= 1e-9
+    assert e[-1] < e[0]
