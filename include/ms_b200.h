@@ -273,6 +273,11 @@ MS_API int ms_ctx_flush_l2(ms_ctx* ctx, int64_t bytes);
 MS_API int ms_host_register(void* ptr, int64_t bytes);
 MS_API int ms_host_unregister(void* ptr);
 
+/* geometry/tilt_operators.py:414-465 p1_vertex_divergence (ambient_v1): triangle divergences averaged onto the
+ * vertices with barycentric area weights; area_v receives the accumulated weights. */
+MS_API int ms_p1_vertex_divergence(int32_t nv, int32_t nf, const double* pos, const double* tilts,
+                                   const int32_t* tri, double* div_v, double* area_v, int32_t zero_based);
+
 /* ---- stateless shims: one per reference kernel, host pointers in and out ------ */
 /* fortran_kernels/surface_energy.f90:27-99 -- grad is accumulated (+=), E returned */
 MS_API int ms_surface_energy_and_gradient(int32_t nv, int32_t nf, const double* pos,

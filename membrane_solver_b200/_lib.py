@@ -155,6 +155,7 @@ SIGNATURES = {
     "ms_grad_cotan_batch": (ctypes.c_int, [_i32, _D, _D, _D, _D]),
     "ms_apply_beltrami_laplacian": (ctypes.c_int, [_i32, _i32, _i32, _D, _I, _D, _D, _i32]),
     "ms_p1_triangle_divergence": (ctypes.c_int, [_i32, _i32, _D, _D, _I, _D, _D, _D, _D, _D, _i32]),
+    "ms_p1_vertex_divergence": (ctypes.c_int, [_i32, _i32, _D, _D, _I, _D, _D, _i32]),
     "ms_compute_curvature_data": (ctypes.c_int, [_i32, _i32, _D, _I, _D, _D, _D, _i32, _D, _D, _D]),
     "ms_volume_and_gradient": (ctypes.c_int, [_i32, _i32, _D, _I, _f64, _D, _D]),
 }

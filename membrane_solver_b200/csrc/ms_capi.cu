@@ -1495,6 +1495,27 @@ int ms_p1_triangle_divergence(int32_t nv, int32_t nf, const double* pos, const d
   return to_host(g2, d_g2, 3 * size_t(nf));
 }
 
+int ms_p1_vertex_divergence(int32_t nv, int32_t nf, const double* pos, const double* tilts, const int32_t* tri,
+                            double* div_v, double* area_v, int32_t zero_based) {
+  if ((nv > 0 && (!tilts || !div_v || !area_v))) return fail(-1, "null argument");
+  SoupDev d;
+  if (int rc = soup_setup(nv, nf, pos, tri, zero_based, true, d)) return rc;
+  DevBuf<double> d_t, d_div, d_area, d_g0, d_g1, d_g2, d_dv, d_av;
+  if (int rc = to_dev(d_t, tilts, 3 * size_t(nv))) return rc;
+  if (int rc = d_div.ensure(size_t(nf) + 1)) return rc;
+  if (int rc = d_area.ensure(size_t(nf) + 1)) return rc;
+  if (int rc = d_g0.ensure(3 * size_t(nf) + 1)) return rc;
+  if (int rc = d_g1.ensure(3 * size_t(nf) + 1)) return rc;
+  if (int rc = d_g2.ensure(3 * size_t(nf) + 1)) return rc;
+  if (int rc = d_dv.ensure(size_t(nv) + 1)) return rc;
+  if (int rc = d_av.ensure(size_t(nv) + 1)) return rc;
+  CU(ms::launch_p1_divergence(d.args, d_t.p, d_div.p, d_area.p, d_g0.p, d_g1.p, d_g2.p, nullptr));
+  CU(ms::launch_p1_vertex_divergence(d.args, d_div.p, d_area.p, d_dv.p, d_av.p, nullptr));
+  CU(cudaDeviceSynchronize());
+  if (int rc = to_host(div_v, d_dv, size_t(nv))) return rc;
+  return to_host(area_v, d_av, size_t(nv));
+}
+
 int ms_compute_curvature_data(int32_t nv, int32_t nf, const double* pos, const int32_t* tri,
                               double* k_vecs, double* vertex_areas, double* weights,
                               int32_t zero_based, double* va0, double* va1, double* va2) {

@@ -776,6 +776,22 @@ __global__ void k_p1_divergence(SoupArgs s, const double* __restrict__ tilts, do
   st3(g2, f, p.g2);
 }
 
+// barycentric-area-averaged vertex divergence (geometry/tilt_operators.py:414-465): fixed-order gather
+__global__ void k_p1_vertex_divergence(SoupArgs s, const double* __restrict__ div, const double* __restrict__ area,
+                                       double* div_v, double* area_v) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= s.nv) return;
+  double num = 0.0, den = 0.0;
+  for (int j = s.csr_ptr[v]; j < s.csr_ptr[v + 1]; ++j) {
+    const int f = s.csr_idx[j] / 3;
+    const double w = area[f] / 3.0;
+    num += w * div[f];
+    den += w;
+  }
+  div_v[v] = den > 1.0e-20 ? num / den : 0.0;
+  area_v[v] = den;
+}
+
 // single-CTA fixed-order sum (stateless shims only; sizes are modest there)
 __global__ void __launch_bounds__(256) k_sum(const double* __restrict__ x, int64_t n, double scale,
                                              double* out) {
@@ -1122,6 +1138,12 @@ cudaError_t launch_grad_cotan(int32_t n, const double* u, const double* v, doubl
 cudaError_t launch_p1_divergence(const SoupArgs& s, const double* tilts, double* div, double* area,
                                  double* g0, double* g1, double* g2, cudaStream_t st) {
   if (s.nf > 0) k_p1_divergence<<<blocks_for(s.nf, 128), 128, 0, st>>>(s, tilts, div, area, g0, g1, g2);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_p1_vertex_divergence(const SoupArgs& s, const double* div, const double* area, double* div_v,
+                                       double* area_v, cudaStream_t st) {
+  if (s.nv > 0) k_p1_vertex_divergence<<<blocks_for(s.nv, 128), 128, 0, st>>>(s, div, area, div_v, area_v);
   return cudaGetLastError();
 }
 

@@ -135,6 +135,8 @@ cudaError_t launch_grad_cotan(int32_t n, const double* u, const double* v, doubl
                               cudaStream_t st);
 cudaError_t launch_p1_divergence(const SoupArgs& s, const double* tilts, double* div, double* area,
                                  double* g0, double* g1, double* g2, cudaStream_t st);
+cudaError_t launch_p1_vertex_divergence(const SoupArgs& s, const double* div, const double* area, double* div_v,
+                                       double* area_v, cudaStream_t st);
 cudaError_t launch_sum(const double* x, int64_t n, double scale, double* out, cudaStream_t st);
 // out[v] = |rows[v,:]|^2 of an (n,3) array (tilt magnitude staging)
 cudaError_t launch_row_norm2(const double* rows, int64_t n, double* out, cudaStream_t st);

@@ -571,3 +571,19 @@ def fused_surface_bending_volume(pos, tri, gamma, kappa, c0, is_boundary,
     accumulate_volume_gradient(pos, tri, vol_grad, 1.0)
     return dict(E_surface=e_s, E_bending=e_b, volume=body_volume(pos, tri),
                 area=float(triangle_areas(pos, tri).sum()), grad=grad, vol_grad=vol_grad)
+
+
+def p1_vertex_divergence(pos, tilts, tri):
+    """geometry/tilt_operators.py:414-465: (div_v, area_bary), barycentric-area average of div_f."""
+    nv = pos.shape[0]
+    if len(tri) == 0:
+        return np.zeros(nv), np.zeros(nv)
+    div, area, _, _, _ = p1_triangle_divergence(pos, tilts, tri)
+    w = area / 3.0
+    num, den = np.zeros(nv), np.zeros(nv)
+    _scatter_vec(num, tri, w * div, w * div, w * div)
+    _scatter_vec(den, tri, w, w, w)
+    out = np.zeros(nv)
+    ok = den > 1e-20
+    out[ok] = num[ok] / den[ok]
+    return out, den

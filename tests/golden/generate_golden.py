@@ -432,13 +432,31 @@ def leaflet_vectors():
     np.savez_compressed(os.path.join(HERE, "leaflet.npz"), **out)
 
 
+def p1_vertex_vectors():
+    """geometry/tilt_operators.py:414-465 on a jittered catenoid (open mesh) with a random tilt field."""
+    from geometry.tilt_operators import p1_vertex_divergence
+
+    mesh = _refined(os.path.join(REF, "meshes", "catenoid.json"), 2)
+    rng = np.random.default_rng(11)
+    pos = np.array(mesh.positions_view()) + 0.01 * rng.standard_normal((len(mesh.vertex_ids), 3))
+    tri = np.ascontiguousarray(mesh.triangle_row_cache()[0], dtype=np.int32)
+    tilts = 0.2 * rng.standard_normal(pos.shape)
+    div_v, area_v = p1_vertex_divergence(n_vertices=len(pos), positions=pos, tilts=tilts, tri_rows=tri)
+    np.savez_compressed(os.path.join(HERE, "p1_vertex.npz"), pos=pos, tri=tri, tilts=tilts, div_v=div_v, area_v=area_v)
+    print("p1_vertex", len(pos), len(tri), float(np.abs(div_v).max()))
+
+
 if __name__ == "__main__":
     _ = (volume_constraint, volume_energy)
     if len(sys.argv) > 1 and sys.argv[1] == "leaflet":
         leaflet_vectors()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "p1vertex":
+        p1_vertex_vectors()
         sys.exit(0)
     kernel_vectors()
     module_vectors()
     minimizer_vectors()
     trajectory_vectors()
     leaflet_vectors()
+    p1_vertex_vectors()

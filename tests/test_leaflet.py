@@ -333,3 +333,36 @@ def test_manager_leaflet_entry_points_on_emulated_device(gold, monkeypatch):
 @pytest.mark.parametrize("state", ["r1", "r1c"])
 def test_manager_leaflet_entry_points_on_device(gold, state):
     _manager_checks(gold, state)
+
+
+# ------------------------------------------------------------------ P1 operators (row a17)
+def test_oracle_p1_vertex_divergence_matches_reference():
+    from oracle import ref_modules as rm
+
+    g = np.load(os.path.join(GOLDEN, "p1_vertex.npz"))
+    div_v, area_v = rm.p1_vertex_divergence(g["pos"], g["tilts"], g["tri"])
+    assert rel_err(div_v, g["div_v"]) <= TOL and rel_err(area_v, g["area_v"]) <= TOL
+
+
+@pytest.mark.gpu
+def test_device_p1_operators_match_reference():
+    from membrane_solver_b200 import _lib as L
+    from membrane_solver_b200.geometry import tilt_operators as ops
+    from oracle import ref_modules as rm
+
+    g = np.load(os.path.join(GOLDEN, "p1_vertex.npz"))
+    pos, tri, tilts = g["pos"], g["tri"], g["tilts"]
+    div_v, area_v = ops.p1_vertex_divergence(n_vertices=len(pos), positions=pos, tilts=tilts, tri_rows=tri)
+    assert rel_err(div_v, g["div_v"]) <= TOL and rel_err(area_v, g["area_v"]) <= TOL
+    div, area, g0, g1, g2 = ops.p1_triangle_divergence(positions=pos, tilts=tilts, tri_rows=tri)
+    want = rm.p1_triangle_divergence(pos, tilts, tri)
+    for a, b in zip((div, area, g0, g1, g2), want):
+        assert rel_err(a, b) <= TOL
+    area2, h0, _, _ = ops.p1_triangle_shape_gradients(positions=pos, tri_rows=tri)
+    assert np.array_equal(area2, area) and np.array_equal(h0, g0)
+    assert ops.p1_vertex_divergence(n_vertices=0, positions=pos, tilts=tilts, tri_rows=tri)[0].size == 0
+    e_div, e_area = ops.p1_vertex_divergence(n_vertices=len(pos), positions=pos, tilts=tilts,
+                                             tri_rows=np.zeros((0, 3), np.int32))
+    assert not e_div.any() and not e_area.any()
+    with pytest.raises(L.B200Error):
+        ops.p1_triangle_divergence(positions=pos, tilts=tilts, tri_rows=tri, transport_model="connection_v1")
