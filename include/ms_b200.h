@@ -216,6 +216,22 @@ MS_API int ms_ctx_eval_leaflet(ms_ctx* ctx, int32_t leaflet, uint32_t modules, i
                                int32_t want_tilt_grad, uint32_t accumulate, int32_t use_trial,
                                double* energies2);
 
+/* --- leaflet tilt relaxation at frozen geometry (runtime/steppers/tilt_relaxation.py:426-1057, gradient-descent
+ * solver; the host keeps the loop control, only scalars cross PCIe) ---
+ * rows whose tilt is fixed (vertex flags tilt_fixed_in / tilt_fixed_out); NULL = none */
+MS_API int ms_ctx_set_leaflet_fixed(ms_ctx* ctx, int32_t leaflet, const uint8_t* fixed_rows);
+/* unit area-weighted vertex normals of MS_ARR_POSITIONS (Mesh.vertex_normals, geometry/triangle_ops.py:55-72),
+ * kept on the device for the projections below */
+MS_API int ms_ctx_update_vertex_normals(ms_ctx* ctx);
+/* t -= (t.n) n on the leaflet's tilt field (runtime/projections/tilt.py:8-14) */
+MS_API int ms_ctx_leaflet_project_tilts(ms_ctx* ctx, int32_t leaflet);
+/* zero the fixed rows of MS_ARR_TILT_GRAD_IN / _OUT and return the sum of squares of the rest (:856-871) */
+MS_API int ms_ctx_leaflet_gradient_norm2(ms_ctx* ctx, int32_t leaflet, double* norm2);
+/* trial = P(t - step * tilt gradient), fixed rows keep t (build_leaflet_trial_tilts, projections/tilt.py:99-138) */
+MS_API int ms_ctx_leaflet_make_trial(ms_ctx* ctx, int32_t leaflet, double step);
+/* exchange the tilt field and the trial field: evaluate at the trial, swap back to reject */
+MS_API int ms_ctx_leaflet_swap_trial(ms_ctx* ctx, int32_t leaflet);
+
 /* One evaluation with everything resident: pass A (+ pass B when want_grad), scalar
  * reduction, optional KKT/penalty/fixed post-processing.  Asynchronous on the context
  * stream; results stay on the device. */

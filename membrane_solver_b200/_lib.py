@@ -134,6 +134,12 @@ SIGNATURES = {
     "ms_ctx_eval_host": (ctypes.c_int, [_V, ctypes.POINTER(EvalOpts), _D, _D, _D, _D, _D]),
     "ms_ctx_set_leaflet": (ctypes.c_int, [_V, _i32, ctypes.POINTER(LeafletDesc)]),
     "ms_ctx_eval_leaflet": (ctypes.c_int, [_V, _i32, ctypes.c_uint32, _i32, _i32, ctypes.c_uint32, _i32, _D]),
+    "ms_ctx_set_leaflet_fixed": (ctypes.c_int, [_V, _i32, _B]),
+    "ms_ctx_update_vertex_normals": (ctypes.c_int, [_V]),
+    "ms_ctx_leaflet_project_tilts": (ctypes.c_int, [_V, _i32]),
+    "ms_ctx_leaflet_gradient_norm2": (ctypes.c_int, [_V, _i32, _D]),
+    "ms_ctx_leaflet_make_trial": (ctypes.c_int, [_V, _i32, _f64]),
+    "ms_ctx_leaflet_swap_trial": (ctypes.c_int, [_V, _i32]),
     "ms_ctx_make_trial": (ctypes.c_int, [_V, _f64]),
     "ms_ctx_accept_trial": (ctypes.c_int, [_V]),
     "ms_ctx_dots": (ctypes.c_int, [_V]),

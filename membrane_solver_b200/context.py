@@ -212,6 +212,32 @@ class DeviceMesh:
             k_tilt=float(k_tilt), div_sign=float(div_sign), consistent_default=int(bool(consistent)), reserved=0)
         L.check(self._lib.ms_ctx_set_leaflet(self._h, int(leaflet), ctypes.byref(d)))
 
+    # -- leaflet tilt relaxation primitives (tilt_relaxation.py:426-1057, GD solver) --
+    def set_leaflet_fixed(self, leaflet: int, fixed_rows) -> None:
+        m = None
+        if fixed_rows is not None:
+            m = np.ascontiguousarray(fixed_rows, dtype=np.uint8)
+            if m.shape != (self.nv,):
+                raise ValueError(f"mask must have shape ({self.nv},)")
+        L.check(self._lib.ms_ctx_set_leaflet_fixed(self._h, int(leaflet), L.bptr(m)))
+
+    def update_vertex_normals(self) -> None:
+        L.check(self._lib.ms_ctx_update_vertex_normals(self._h))
+
+    def leaflet_project_tilts(self, leaflet: int) -> None:
+        L.check(self._lib.ms_ctx_leaflet_project_tilts(self._h, int(leaflet)))
+
+    def leaflet_gradient_norm2(self, leaflet: int) -> float:
+        out = np.zeros(1)
+        L.check(self._lib.ms_ctx_leaflet_gradient_norm2(self._h, int(leaflet), L.dptr(out)))
+        return float(out[0])
+
+    def leaflet_make_trial(self, leaflet: int, step: float) -> None:
+        L.check(self._lib.ms_ctx_leaflet_make_trial(self._h, int(leaflet), float(step)))
+
+    def leaflet_swap_trial(self, leaflet: int) -> None:
+        L.check(self._lib.ms_ctx_leaflet_swap_trial(self._h, int(leaflet)))
+
     def eval_leaflet(self, leaflet: int, modules: int, *, want_grad: bool = True, want_tilt_grad: bool = True,
                      accumulate: int = 0, use_trial: bool = False) -> tuple[float, float]:
         """(E_bending_tilt, E_tilt) of the leaflet's modules; gradients stay on the device

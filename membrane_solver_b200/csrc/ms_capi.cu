@@ -118,11 +118,15 @@ struct ms_ctx {
     bool has_keep = false, has_interior = false, has_base_zero = false, has_kappa = false, has_c0 = false,
          has_weight = false, has_consistent = false;
     DevBuf<uint8_t> keep, interior, base_zero, consistent;
-    DevBuf<double> kappa, c0, weight, tilts, tilt_grad;
+    DevBuf<double> kappa, c0, weight, tilts, tilt_grad, trial;
+    DevBuf<uint8_t> fixed;
+    bool has_fixed = false;
     double kappa_u = 0.0, c0_u = 0.0, k_tilt = 0.0, sign = 1.0;
     int32_t consistent_u = 0;
   } leaflet[2];
   DevBuf<double> d_lf_corner, d_lf_vbuf, d_lf_shape, d_lf_tilt, d_lf_facet_e, d_lf_e;
+  DevBuf<double> d_vnormals, d_rowsq, d_norm_out;
+  bool vnormals_ready = false;
 };
 
 namespace {
@@ -552,6 +556,8 @@ int ms_ctx_set_topology_partition(ms_ctx* c, int32_t nv, int32_t n_owned, int32_
   c->tri_ready = false;
   c->pipe_ready = false;
   c->leaflet[0].set = c->leaflet[1].set = false;
+  c->leaflet[0].has_fixed = c->leaflet[1].has_fixed = false;
+  c->vnormals_ready = false;
   const ms::PackedMesh& pk = c->packed;
   const size_t np = pk.patches.size();
   c->v_lo.resize(np + 1);
@@ -989,6 +995,71 @@ int ms_ctx_eval_leaflet(ms_ctx* c, int32_t leaflet, uint32_t modules, int32_t wa
     CU(cudaMemcpyAsync(energies2, c->d_lf_e.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
   }
+  return 0;
+}
+
+int ms_ctx_set_leaflet_fixed(ms_ctx* c, int32_t leaflet, const uint8_t* fixed_rows) {
+  if (int rc = check_ctx(c, true)) return rc;
+  if (leaflet < 0 || leaflet > 1) return fail(-1, "bad leaflet index");
+  ms_ctx::Leaflet& L = c->leaflet[leaflet];
+  return upload_optional(c, fixed_rows, size_t(c->nv), true, L.fixed, L.has_fixed);
+}
+
+int ms_ctx_update_vertex_normals(ms_ctx* c) {
+  if (int rc = check_ctx(c, true)) return rc;
+  if (c->n_owned != c->nv) return fail(-5, "not available on a partitioned context");
+  ms::BtMesh bm;
+  if (int rc = bt_prepare(c, bm)) return rc;
+  if (int rc = c->d_vnormals.ensure(3 * size_t(c->nv) + 1)) return rc;
+  CU(ms::launch_vertex_normals(c->nv, c->d_tri.p, c->d_csr_ptr.p, c->d_csr_idx.p, c->d_pos.p, c->d_vnormals.p, c->stream));
+  c->vnormals_ready = true;
+  return 0;
+}
+
+static int leaflet_ready(ms_ctx* c, int32_t leaflet, bool need_normals) {
+  if (int rc = check_ctx(c, true)) return rc;
+  if (leaflet < 0 || leaflet > 1) return fail(-1, "bad leaflet index");
+  if (!c->leaflet[leaflet].tilts.p && c->nv > 0) return fail(-4, "the leaflet's tilt field has not been uploaded");
+  if (need_normals && !c->vnormals_ready) return fail(-4, "ms_ctx_update_vertex_normals has not been called for this topology");
+  return 0;
+}
+
+int ms_ctx_leaflet_project_tilts(ms_ctx* c, int32_t leaflet) {
+  if (int rc = leaflet_ready(c, leaflet, true)) return rc;
+  CU(ms::launch_project_tangent(c->nv, c->d_vnormals.p, c->leaflet[leaflet].tilts.p, c->stream));
+  return 0;
+}
+
+int ms_ctx_leaflet_gradient_norm2(ms_ctx* c, int32_t leaflet, double* norm2) {
+  if (int rc = leaflet_ready(c, leaflet, false)) return rc;
+  if (!norm2) return fail(-1, "null argument");
+  ms_ctx::Leaflet& L = c->leaflet[leaflet];
+  if (!L.tilt_grad.p && c->nv > 0) return fail(-4, "no tilt gradient exists for this leaflet (ms_ctx_eval_leaflet)");
+  if (int rc = c->d_rowsq.ensure(size_t(c->nv) + 1)) return rc;
+  if (int rc = c->d_norm_out.ensure(1 + ms::kSumBlocks)) return rc;
+  CU(ms::launch_masked_norm2(c->nv, L.tilt_grad.p, L.has_fixed ? L.fixed.p : nullptr, c->d_rowsq.p, c->d_norm_out.p,
+                             c->stream));
+  CU(cudaMemcpyAsync(norm2, c->d_norm_out.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int ms_ctx_leaflet_make_trial(ms_ctx* c, int32_t leaflet, double step) {
+  if (int rc = leaflet_ready(c, leaflet, true)) return rc;
+  ms_ctx::Leaflet& L = c->leaflet[leaflet];
+  if (!L.tilt_grad.p && c->nv > 0) return fail(-4, "no tilt gradient exists for this leaflet (ms_ctx_eval_leaflet)");
+  if (int rc = L.trial.ensure(3 * size_t(c->nv) + 1)) return rc;
+  CU(ms::launch_tilt_trial(c->nv, L.tilts.p, L.tilt_grad.p, c->d_vnormals.p, L.has_fixed ? L.fixed.p : nullptr, step,
+                           L.trial.p, c->stream));
+  return 0;
+}
+
+int ms_ctx_leaflet_swap_trial(ms_ctx* c, int32_t leaflet) {
+  if (int rc = leaflet_ready(c, leaflet, false)) return rc;
+  ms_ctx::Leaflet& L = c->leaflet[leaflet];
+  if (!L.trial.p && c->nv > 0) return fail(-4, "no trial tilt field exists (ms_ctx_leaflet_make_trial)");
+  std::swap(L.tilts.p, L.trial.p);  // DevBuf owns its pointer: exchange the fields, not the objects
+  std::swap(L.tilts.n, L.trial.n);
   return 0;
 }
 

@@ -861,6 +861,62 @@ __global__ void __launch_bounds__(128) k_lf_facet_b(LeafletMesh m, const double*
   facet_e[size_t(m.nf) + f] = e.e_tilt;
 }
 
+// ---- leaflet tilt relaxation helpers (runtime/steppers/tilt_relaxation.py:630-668,894-955) ----
+// unit area-weighted vertex normals (Mesh.vertex_normals, geometry/triangle_ops.py:55-72): fixed-order gather
+__global__ void __launch_bounds__(128) k_vertex_normals(int32_t nv, const int32_t* __restrict__ tri,
+                                                        const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                                                        const double* __restrict__ pos, double* normals) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nv) return;
+  d3 n = make_d3(0, 0, 0);
+  for (int j = ptr[v]; j < ptr[v + 1]; ++j) {
+    const int f = idx[j] / 3;
+    const d3 a = ld3(pos, tri[3 * size_t(f)]), b = ld3(pos, tri[3 * size_t(f) + 1]), c = ld3(pos, tri[3 * size_t(f) + 2]);
+    n = n + cross(b - a, c - a);
+  }
+  const double len = sqrt(dot(n, n));
+  if (len >= 1.0e-12) n = (1.0 / len) * n;
+  st3(normals, v, n);
+}
+
+// t -= (t.n) n  (runtime/projections/tilt.py:8-14)
+__global__ void __launch_bounds__(256) k_project_tangent(int64_t nv, const double* __restrict__ normals, double* t) {
+  const int64_t v = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (v >= nv) return;
+  const d3 n = ld3(normals, v), x = ld3(t, v);
+  st3(t, v, axpy(-dot(x, n), n, x));
+}
+
+// trial = P(t - step g); rows with fixed tilts keep their value (projections/tilt.py:99-138)
+__global__ void __launch_bounds__(256) k_tilt_trial(int64_t nv, const double* __restrict__ t, const double* __restrict__ g,
+                                                    const double* __restrict__ normals, const uint8_t* __restrict__ fixed,
+                                                    double step, double* trial) {
+  const int64_t v = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (v >= nv) return;
+  const d3 x = ld3(t, v);
+  if (fixed && fixed[v]) {
+    st3(trial, v, x);
+    return;
+  }
+  const d3 n = ld3(normals, v);
+  const d3 y = axpy(-step, ld3(g, v), x);
+  st3(trial, v, axpy(-dot(y, n), n, y));
+}
+
+// zero the gradient rows of fixed tilts; rowsq[v] = |g_v|^2 of the free rows (tilt_relaxation.py:856-871)
+__global__ void __launch_bounds__(256) k_masked_row_norm2(int64_t nv, double* g, const uint8_t* __restrict__ fixed,
+                                                          double* rowsq) {
+  const int64_t v = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (v >= nv) return;
+  if (fixed && fixed[v]) {
+    st3(g, v, make_d3(0, 0, 0));
+    rowsq[v] = 0.0;
+    return;
+  }
+  const d3 x = ld3(g, v);
+  rowsq[v] = dot(x, x);
+}
+
 __global__ void __launch_bounds__(256) k_row_norm2(const double* __restrict__ rows, int64_t n, double* out) {
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -1210,6 +1266,30 @@ cudaError_t launch_leaflet(const LeafletMesh& m, bool with_bt, bool with_tilt, d
   if (m.nv > 0 && tilt_grad)
     k_gather<<<blocks_for(m.nv, 128), 128, 0, st>>>(m.nv, m.csr_ptr, m.csr_idx, corner_tilt, 3, 0, 3, tilt_grad, 3,
                                                      accumulate_tilt_grad ? 1 : 0);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_vertex_normals(int32_t nv, const int32_t* tri, const int32_t* csr_ptr, const int32_t* csr_idx,
+                                  const double* pos, double* normals, cudaStream_t st) {
+  if (nv > 0) k_vertex_normals<<<blocks_for(nv, 128), 128, 0, st>>>(nv, tri, csr_ptr, csr_idx, pos, normals);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_project_tangent(int64_t nv, const double* normals, double* t, cudaStream_t st) {
+  if (nv > 0) k_project_tangent<<<blocks_for(nv, 256), 256, 0, st>>>(nv, normals, t);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tilt_trial(int64_t nv, const double* t, const double* g, const double* normals, const uint8_t* fixed,
+                              double step, double* trial, cudaStream_t st) {
+  if (nv > 0) k_tilt_trial<<<blocks_for(nv, 256), 256, 0, st>>>(nv, t, g, normals, fixed, step, trial);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_masked_norm2(int64_t nv, double* g, const uint8_t* fixed, double* rowsq, double* out /*1 + kSumBlocks*/,
+                                cudaStream_t st) {
+  if (nv > 0) k_masked_row_norm2<<<blocks_for(nv, 256), 256, 0, st>>>(nv, g, fixed, rowsq);
+  sum_fixed_order(rowsq, nv, 1.0, out, out + 1, st);
   return cudaGetLastError();
 }
 

@@ -170,4 +170,12 @@ cudaError_t launch_leaflet(const LeafletMesh& m, bool with_bt, bool with_tilt, d
                            double* corner_shape, double* corner_tilt, double* facet_e, double* e_out2, double* grad,
                            bool accumulate_grad, double* tilt_grad, bool accumulate_tilt_grad, cudaStream_t st);
 
+// --- leaflet tilt relaxation helpers ---
+cudaError_t launch_vertex_normals(int32_t nv, const int32_t* tri, const int32_t* csr_ptr, const int32_t* csr_idx,
+                                  const double* pos, double* normals, cudaStream_t st);
+cudaError_t launch_project_tangent(int64_t nv, const double* normals, double* t, cudaStream_t st);
+cudaError_t launch_tilt_trial(int64_t nv, const double* t, const double* g, const double* normals, const uint8_t* fixed,
+                              double step, double* trial, cudaStream_t st);
+cudaError_t launch_masked_norm2(int64_t nv, double* g, const uint8_t* fixed, double* rowsq, double* out, cudaStream_t st);
+
 }  // namespace ms

@@ -1,0 +1,91 @@
+"""Device-resident leaflet tilt relaxation at frozen geometry.
+
+Twin of the gradient-descent solver of ``TiltRelaxationManager.relax_leaflet_tilts``
+(``runtime/steppers/tilt_relaxation.py:426-1057``: setup ``:630-668``, gradients ``:825-872``, loop ``:894-1055``)
+for a mesh whose tilt fields are constrained only by fixed rows (no tilt constraint modules, no axisymmetric
+projection).  Positions, both tilt fields, their gradients and the trial fields stay on the device; per
+iteration the host sees three scalars (energy, gradient norm, trial energy) and keeps the loop control:
+
+    E0, g = tilt-only evaluation of the leaflet modules;  g[fixed] = 0;  stop on |g| == 0 or |g| < tol
+    step = tilt_step_size;  up to 12 trials:  t' = P(t - step g), fixed rows kept;  accept if E(t') <= E0 else halve
+    after an accepted step the fields pass through the tangent projection once more (the reference's per-step
+    refresh writes them to the mesh and reads them back projected, ``:803-823``)
+"""
+
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+from .. import _lib as L
+
+_WHICH = {"in": L.LEAFLET_IN, "out": L.LEAFLET_OUT}
+
+
+@dataclass
+class DeviceTiltRelaxer:
+    """``dm``: a DeviceMesh with positions uploaded, both leaflets described (``set_leaflet``), their fixed rows
+    (``set_leaflet_fixed``) and tilt fields (``ARR_TILTS_IN`` / ``_OUT``) in place."""
+
+    dm: object
+    leaflets: tuple = ("in", "out")
+    modules: int = L.MOD_TILT | L.MOD_BENDING_TILT
+    stats: dict = field(default_factory=dict)
+
+    def _energy(self, want_tilt_grad: bool) -> float:
+        total = 0.0
+        for name in self.leaflets:
+            e_bt, e_tilt = self.dm.eval_leaflet(_WHICH[name], self.modules, want_grad=False,
+                                                want_tilt_grad=want_tilt_grad)
+            total += e_bt + e_tilt
+        return total
+
+    def relax(self, *, max_iters: int, step_size: float, tol: float = 0.0) -> dict:
+        dm = self.dm
+        st = dict(accepted_steps=0, rejected_steps=0, backtracking_steps=0, stop_reason="completed_max_iters",
+                  initial_energy=0.0, final_energy=0.0, initial_gradient_norm=0.0, final_gradient_norm=0.0)
+        self.stats = st
+        if step_size <= 0.0:
+            st["stop_reason"] = "step_size_zero"
+            return st
+        dm.update_vertex_normals()
+        for name in self.leaflets:
+            dm.leaflet_project_tilts(_WHICH[name])
+        for _ in range(int(max_iters)):
+            e0 = self._energy(True)
+            gnorm = math.sqrt(sum(dm.leaflet_gradient_norm2(_WHICH[n]) for n in self.leaflets))
+            if st["accepted_steps"] == 0 and st["rejected_steps"] == 0:
+                st["initial_energy"], st["initial_gradient_norm"] = e0, gnorm
+            st["final_energy"], st["final_gradient_norm"] = e0, gnorm
+            if gnorm == 0.0:
+                st["stop_reason"] = "zero_gradient"
+                break
+            if tol > 0.0 and gnorm < tol:
+                st["stop_reason"] = "converged"
+                break
+            step, accepted, e1 = float(step_size), False, e0
+            for attempt in range(12):
+                if attempt:
+                    st["backtracking_steps"] += 1
+                for name in self.leaflets:
+                    dm.leaflet_make_trial(_WHICH[name], step)
+                    dm.leaflet_swap_trial(_WHICH[name])        # evaluate at the trial fields
+                e1 = self._energy(False)
+                if e1 <= e0:
+                    accepted = True
+                    break
+                for name in self.leaflets:
+                    dm.leaflet_swap_trial(_WHICH[name])        # rejected: back to the base fields
+                step *= 0.5
+                if step < 1e-16:
+                    break
+            if not accepted:
+                st["rejected_steps"] += 1
+                st["stop_reason"] = "line_search_rejected"
+                break
+            st["accepted_steps"] += 1
+            st["step_size_last_accepted"] = step
+            for name in self.leaflets:
+                dm.leaflet_project_tilts(_WHICH[name])
+            st["final_energy"] = e1
+        return st

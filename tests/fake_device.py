@@ -101,6 +101,53 @@ class FakeDeviceMesh:
         self.__dict__.setdefault("leaflets", {})[int(leaflet)] = desc
         self.leaflet_uploads = getattr(self, "leaflet_uploads", 0) + 1
 
+    # -- tilt relaxation primitives: numpy restatements of the small kernels (TEST ONLY) --
+    def set_leaflet_fixed(self, leaflet, fixed_rows):
+        self.__dict__.setdefault("leaflet_fixed", {})[int(leaflet)] = (
+            None if fixed_rows is None else np.asarray(fixed_rows, bool))
+
+    def update_vertex_normals(self):
+        p, t = self.pos, self.tri
+        n = np.cross(p[t[:, 1]] - p[t[:, 0]], p[t[:, 2]] - p[t[:, 0]])
+        out = np.zeros_like(p)
+        for k in range(3):
+            np.add.at(out, t[:, k], n)
+        mag = np.linalg.norm(out, axis=1)
+        ok = mag >= 1e-12
+        out[ok] /= mag[ok][:, None]
+        self.vnormals = out
+
+    def _lf_arrays(self, leaflet):
+        if leaflet == L.LEAFLET_IN:
+            return L.ARR_TILTS_IN, L.ARR_TILT_GRAD_IN
+        return L.ARR_TILTS_OUT, L.ARR_TILT_GRAD_OUT
+
+    def leaflet_project_tilts(self, leaflet):
+        a, _ = self._lf_arrays(leaflet)
+        t = self.arrays[a]
+        self.arrays[a] = t - (t * self.vnormals).sum(axis=1)[:, None] * self.vnormals
+
+    def leaflet_gradient_norm2(self, leaflet):
+        _, g = self._lf_arrays(leaflet)
+        fx = getattr(self, "leaflet_fixed", {}).get(int(leaflet))
+        if fx is not None:
+            self.arrays[g][fx] = 0.0
+        return float((self.arrays[g] ** 2).sum())
+
+    def leaflet_make_trial(self, leaflet, step):
+        a, g = self._lf_arrays(leaflet)
+        t = self.arrays[a]
+        y = t - step * self.arrays[g]
+        y = y - (y * self.vnormals).sum(axis=1)[:, None] * self.vnormals
+        fx = getattr(self, "leaflet_fixed", {}).get(int(leaflet))
+        if fx is not None:
+            y[fx] = t[fx]
+        self.__dict__.setdefault("leaflet_trial", {})[int(leaflet)] = y
+
+    def leaflet_swap_trial(self, leaflet):
+        a, _ = self._lf_arrays(leaflet)
+        self.arrays[a], self.leaflet_trial[int(leaflet)] = self.leaflet_trial[int(leaflet)], self.arrays[a]
+
     def eval_leaflet(self, leaflet, modules, *, want_grad=True, want_tilt_grad=True, accumulate=0, use_trial=False):
         if int(leaflet) not in getattr(self, "leaflets", {}):
             raise L.B200Error("ms_ctx_set_leaflet has not been called for this leaflet")

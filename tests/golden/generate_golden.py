@@ -446,10 +446,87 @@ def p1_vertex_vectors():
     print("p1_vertex", len(pos), len(tri), float(np.abs(div_v).max()))
 
 
+def tilt_relaxation_vectors():
+    """Row f3: the reference's leaflet tilt relaxation (``TiltRelaxationManager.relax_leaflet_tilts``, gradient-
+    descent solver, frozen geometry) on the caveolin free-disk mesh with its four leaflet energy modules and NO
+    tilt constraint modules.  Stores the initial state, the selections as masks and the relaxed tilt fields."""
+    from modules.energy.bt_params import (_assume_J0_center_xy, _assume_J0_presets, _assume_J0_radius_max,
+                                          _per_vertex_params_leaflet)
+    from modules.energy.bt_selection import _collect_preset_rows, _interior_mask_leaflet
+    from modules.energy.leaflet_presence import leaflet_absent_vertex_mask, leaflet_present_triangle_mask
+
+    path = os.path.join(REF, "meshes", "caveolin",
+                        "kozlov_1disk_3d_tensionless_single_leaflet_profile_hard_rim_R12_free_disk.yaml")
+    out = {}
+    for case, steps, step_size in (("gd5", 5, 0.15), ("gd4small", 4, 0.003), ("gdreject", 3, 40.0)):
+        mesh = _refined(path, 1)
+        gp = mesh.global_parameters
+        gp.set("tilt_solver", "gd")
+        gp.set("tilt_solve_mode", "nested")
+        gp.set("tilt_inner_steps", steps)
+        gp.set("tilt_step_size", step_size)
+        gp.set("tilt_tol", 0.0)
+        rng = np.random.default_rng(31)
+        nv = len(mesh.vertex_ids)
+        for row, vid in enumerate(mesh.vertex_ids):
+            v = mesh.vertices[int(vid)]
+            v.position = np.asarray(v.position, dtype=float) + np.array([0.0, 0.0, 0.05 * rng.standard_normal()])
+            if not getattr(v, "tilt_fixed_in", False):
+                v.tilt_in = 0.05 * rng.standard_normal(3)
+            if not getattr(v, "tilt_fixed_out", False):
+                v.tilt_out = 0.05 * rng.standard_normal(3)
+        mesh.increment_version()
+        if hasattr(mesh, "touch_tilts_in"):
+            mesh.touch_tilts_in()
+            mesh.touch_tilts_out()
+        names = ["bending_tilt_in", "bending_tilt_out", "tilt_in", "tilt_out"]
+        mesh.energy_modules = list(names)
+        mesh.constraint_modules = []
+        mini = Minimizer(mesh, gp, GradientDescent(), EnergyModuleManager(names), ConstraintModuleManager([]), quiet=True)
+        pos = np.array(mesh.positions_view())
+        idx = mesh.vertex_index_to_row
+        tri = np.ascontiguousarray(mesh.triangle_row_cache()[0], dtype=np.int32)
+        isb = np.zeros(nv, bool)
+        for vid in mesh.boundary_vertex_ids:
+            isb[idx[vid]] = True
+        pre = case + "_"
+        out[pre + "pos"], out[pre + "tri"], out[pre + "is_boundary"] = pos, tri, isb
+        out[pre + "tilts_in0"], out[pre + "tilts_out0"] = np.array(mesh.tilts_in_view()), np.array(mesh.tilts_out_view())
+        out[pre + "fixed_in"], out[pre + "fixed_out"] = np.array(mini._tilt_fixed_mask_in()), np.array(mini._tilt_fixed_mask_out())
+        for leaf in ("in", "out"):
+            am = leaflet_absent_vertex_mask(mesh, gp, leaflet=leaf)
+            keep = leaflet_present_triangle_mask(mesh, tri, absent_vertex_mask=am)
+            out[pre + f"{leaf}_keep"] = np.ones(len(tri), bool) if keep.size == 0 else np.asarray(keep, bool)
+            out[pre + f"{leaf}_interior"] = np.asarray(_interior_mask_leaflet(mesh, gp, cache_tag=leaf, index_map=idx), bool)
+            bz = np.zeros(nv, bool)
+            presets = _assume_J0_presets(gp, cache_tag=leaf)
+            if presets:
+                bz[_collect_preset_rows(mesh, presets=presets, cache_tag=leaf, index_map=idx,
+                                        radius_max=_assume_J0_radius_max(gp, cache_tag=leaf),
+                                        center_xy=_assume_J0_center_xy(gp))] = True
+            out[pre + f"{leaf}_base_zero"] = bz
+            kap, c0 = _per_vertex_params_leaflet(mesh, gp, model="helfrich", kappa_key=f"bending_modulus_{leaf}",
+                                                 cache_tag=leaf)
+            out[pre + f"{leaf}_kappa"], out[pre + f"{leaf}_c0"] = np.array(kap), np.array(c0)
+            out[pre + f"{leaf}_k_tilt"] = np.float64(gp.get(f"tilt_modulus_{leaf}"))
+        stats = mini._relax_leaflet_tilts(positions=mesh.positions_view(), mode="nested")
+        out[pre + "tilts_in1"], out[pre + "tilts_out1"] = np.array(mesh.tilts_in_view()), np.array(mesh.tilts_out_view())
+        for k in ("accepted_steps", "backtracking_steps", "initial_energy", "final_energy", "initial_gradient_norm",
+                  "final_gradient_norm"):
+            out[pre + k] = np.float64(stats[k])
+        out[pre + "steps"], out[pre + "step_size"] = np.int64(steps), np.float64(step_size)
+        print(case, {k: stats[k] for k in ("accepted_steps", "backtracking_steps", "stop_reason", "initial_energy",
+                                           "final_energy", "initial_gradient_norm", "final_gradient_norm")})
+    np.savez_compressed(os.path.join(HERE, "tilt_relaxation.npz"), **out)
+
+
 if __name__ == "__main__":
     _ = (volume_constraint, volume_energy)
     if len(sys.argv) > 1 and sys.argv[1] == "leaflet":
         leaflet_vectors()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "tiltrelax":
+        tilt_relaxation_vectors()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "p1vertex":
         p1_vertex_vectors()
@@ -460,3 +537,4 @@ if __name__ == "__main__":
     trajectory_vectors()
     leaflet_vectors()
     p1_vertex_vectors()
+    tilt_relaxation_vectors()

@@ -366,3 +366,84 @@ def test_device_p1_operators_match_reference():
     assert not e_div.any() and not e_area.any()
     with pytest.raises(L.B200Error):
         ops.p1_triangle_divergence(positions=pos, tilts=tilts, tri_rows=tri, transport_model="connection_v1")
+
+
+# ------------------------------------------------------------------ leaflet tilt relaxation (row f3)
+RELAX_CASES = ("gd5", "gd4small", "gdreject")
+
+
+@pytest.fixture(scope="module")
+def relax_gold():
+    return np.load(os.path.join(GOLDEN, "tilt_relaxation.npz"))
+
+
+def _relax_leaflets(g, case):
+    p = case + "_"
+    return {k: dict(keep=g[p + f"{k}_keep"], interior=g[p + f"{k}_interior"], base_zero=g[p + f"{k}_base_zero"],
+                    kappa=g[p + f"{k}_kappa"], c0=g[p + f"{k}_c0"], k_tilt=float(g[p + f"{k}_k_tilt"]))
+            for k in LEAFLETS}
+
+
+def _relax_stats_match(st, g, case):
+    p = case + "_"
+    assert st["accepted_steps"] == int(g[p + "accepted_steps"])
+    assert st["backtracking_steps"] == int(g[p + "backtracking_steps"])
+    for k in ("initial_energy", "final_energy", "initial_gradient_norm", "final_gradient_norm"):
+        assert abs(st[k] - float(g[p + k])) <= 1e-11 * max(1.0, abs(float(g[p + k]))), k
+
+
+@pytest.mark.parametrize("case", RELAX_CASES)
+def test_oracle_tilt_relaxation_matches_reference(relax_gold, case):
+    from oracle import ref_leaflet as rl
+
+    g, p = relax_gold, case + "_"
+    t, st = rl.relax_leaflet_tilts_gd(g[p + "pos"], g[p + "tri"], {"in": g[p + "tilts_in0"], "out": g[p + "tilts_out0"]},
+                                      _relax_leaflets(g, case), is_boundary=g[p + "is_boundary"],
+                                      fixed={"in": g[p + "fixed_in"], "out": g[p + "fixed_out"]},
+                                      max_iters=int(g[p + "steps"]), step_size=float(g[p + "step_size"]))
+    _relax_stats_match(st, g, case)
+    assert np.max(np.abs(t["in"] - g[p + "tilts_in1"])) <= 1e-12
+    assert np.max(np.abs(t["out"] - g[p + "tilts_out1"])) <= 1e-12
+
+
+def _device_relaxation(g, case, factory):
+    from membrane_solver_b200 import _lib as L
+    from membrane_solver_b200.runtime.device_tilt_relaxer import DeviceTiltRelaxer
+
+    p = case + "_"
+    pos, tri = g[p + "pos"], g[p + "tri"]
+    dm = factory(0)
+    dm.set_topology(pos.shape[0], tri, is_boundary=g[p + "is_boundary"].astype(np.uint8))
+    dm.set_positions(pos)
+    for leaf, d in _relax_leaflets(g, case).items():
+        which = L.LEAFLET_IN if leaf == "in" else L.LEAFLET_OUT
+        dm.set_leaflet(which, div_sign=-1.0 if leaf == "in" else 1.0, kappa=d["kappa"], c0=d["c0"], k_tilt=d["k_tilt"],
+                       facet_keep=d["keep"].astype(np.uint8), interior=d["interior"].astype(np.uint8),
+                       base_zero=d["base_zero"].astype(np.uint8))
+        dm.set_leaflet_fixed(which, g[p + f"fixed_{leaf}"].astype(np.uint8))
+        dm.upload(L.ARR_TILTS_IN if leaf == "in" else L.ARR_TILTS_OUT, g[p + f"tilts_{leaf}0"])
+    st = DeviceTiltRelaxer(dm).relax(max_iters=int(g[p + "steps"]), step_size=float(g[p + "step_size"]))
+    _relax_stats_match(st, g, case)
+    # north_star: trajectories within 1e-9
+    assert np.max(np.abs(dm.download(L.ARR_TILTS_IN) - g[p + "tilts_in1"])) <= 1e-10
+    assert np.max(np.abs(dm.download(L.ARR_TILTS_OUT) - g[p + "tilts_out1"])) <= 1e-10
+    fixed = g[p + "fixed_in"]
+    if case != "gdreject":
+        moved = np.abs(dm.download(L.ARR_TILTS_IN) - g[p + "tilts_in0"]).max(axis=1)
+        assert moved[~fixed].max() > 1e-4
+    dm.close()
+
+
+@pytest.mark.parametrize("case", RELAX_CASES)
+def test_tilt_relaxer_on_emulated_device(relax_gold, case):
+    from fake_device import FakeDeviceMesh
+
+    _device_relaxation(relax_gold, case, FakeDeviceMesh)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", RELAX_CASES)
+def test_tilt_relaxer_on_device(relax_gold, case):
+    from membrane_solver_b200.context import DeviceMesh
+
+    _device_relaxation(relax_gold, case, DeviceMesh)
