@@ -227,8 +227,18 @@ MS_API int ms_ctx_update_vertex_normals(ms_ctx* ctx);
 MS_API int ms_ctx_leaflet_project_tilts(ms_ctx* ctx, int32_t leaflet);
 /* zero the fixed rows of MS_ARR_TILT_GRAD_IN / _OUT and return the sum of squares of the rest (:856-871) */
 MS_API int ms_ctx_leaflet_gradient_norm2(ms_ctx* ctx, int32_t leaflet, double* norm2);
-/* trial = P(t - step * tilt gradient), fixed rows keep t (build_leaflet_trial_tilts, projections/tilt.py:99-138) */
-MS_API int ms_ctx_leaflet_make_trial(ms_ctx* ctx, int32_t leaflet, double step);
+/* trial = P(t - step * tilt gradient) or, with along_direction, P(t + step * CG direction); fixed rows keep t
+ * (build_leaflet_trial_tilts, projections/tilt.py:99-138) */
+MS_API int ms_ctx_leaflet_make_trial(ms_ctx* ctx, int32_t leaflet, double step, int32_t along_direction);
+/* preconditioned CG solver of the same loop (tilt_relaxation.py:1057-1440, runtime/preconditioners.py:64-146):
+ * Jacobi inverse diagonal 1 / (k_tilt * barycentric area + k_smooth/2 * opposite cotangents); the area runs over the
+ * leaflet's facets when kept_facets_only, else over every facet */
+MS_API int ms_ctx_leaflet_build_preconditioner(ms_ctx* ctx, int32_t leaflet, double k_smooth, int32_t kept_facets_only);
+/* rz = sum_v g_v . (M^-1 g_v) over the leaflet's tilt gradient (fixed rows were zeroed by ..._gradient_norm2) */
+MS_API int ms_ctx_leaflet_rz(ms_ctx* ctx, int32_t leaflet, int32_t preconditioned, double* rz);
+/* direction = -M^-1 g + beta * direction  (restart != 0: direction = -M^-1 g) */
+MS_API int ms_ctx_leaflet_cg_direction(ms_ctx* ctx, int32_t leaflet, double beta, int32_t restart,
+                                       int32_t preconditioned);
 /* exchange the tilt field and the trial field: evaluate at the trial, swap back to reject */
 MS_API int ms_ctx_leaflet_swap_trial(ms_ctx* ctx, int32_t leaflet);
 

@@ -232,8 +232,21 @@ class DeviceMesh:
         L.check(self._lib.ms_ctx_leaflet_gradient_norm2(self._h, int(leaflet), L.dptr(out)))
         return float(out[0])
 
-    def leaflet_make_trial(self, leaflet: int, step: float) -> None:
-        L.check(self._lib.ms_ctx_leaflet_make_trial(self._h, int(leaflet), float(step)))
+    def leaflet_make_trial(self, leaflet: int, step: float, along_direction: bool = False) -> None:
+        L.check(self._lib.ms_ctx_leaflet_make_trial(self._h, int(leaflet), float(step), int(bool(along_direction))))
+
+    def leaflet_build_preconditioner(self, leaflet: int, k_smooth: float, kept_facets_only: bool) -> None:
+        L.check(self._lib.ms_ctx_leaflet_build_preconditioner(self._h, int(leaflet), float(k_smooth),
+                                                              int(bool(kept_facets_only))))
+
+    def leaflet_rz(self, leaflet: int, preconditioned: bool) -> float:
+        out = np.zeros(1)
+        L.check(self._lib.ms_ctx_leaflet_rz(self._h, int(leaflet), int(bool(preconditioned)), L.dptr(out)))
+        return float(out[0])
+
+    def leaflet_cg_direction(self, leaflet: int, beta: float, restart: bool, preconditioned: bool) -> None:
+        L.check(self._lib.ms_ctx_leaflet_cg_direction(self._h, int(leaflet), float(beta), int(bool(restart)),
+                                                      int(bool(preconditioned))))
 
     def leaflet_swap_trial(self, leaflet: int) -> None:
         L.check(self._lib.ms_ctx_leaflet_swap_trial(self._h, int(leaflet)))

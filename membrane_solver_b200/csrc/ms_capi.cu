@@ -118,7 +118,8 @@ struct ms_ctx {
     bool has_keep = false, has_interior = false, has_base_zero = false, has_kappa = false, has_c0 = false,
          has_weight = false, has_consistent = false;
     DevBuf<uint8_t> keep, interior, base_zero, consistent;
-    DevBuf<double> kappa, c0, weight, tilts, tilt_grad, trial;
+    DevBuf<double> kappa, c0, weight, tilts, tilt_grad, trial, dir, minv;
+    bool has_minv = false;
     DevBuf<uint8_t> fixed;
     bool has_fixed = false;
     double kappa_u = 0.0, c0_u = 0.0, k_tilt = 0.0, sign = 1.0;
@@ -557,6 +558,7 @@ int ms_ctx_set_topology_partition(ms_ctx* c, int32_t nv, int32_t n_owned, int32_
   c->pipe_ready = false;
   c->leaflet[0].set = c->leaflet[1].set = false;
   c->leaflet[0].has_fixed = c->leaflet[1].has_fixed = false;
+  c->leaflet[0].has_minv = c->leaflet[1].has_minv = false;
   c->vnormals_ready = false;
   const ms::PackedMesh& pk = c->packed;
   const size_t np = pk.patches.size();
@@ -942,6 +944,29 @@ int ms_ctx_set_leaflet(ms_ctx* c, int32_t leaflet, const ms_leaflet_desc* d) {
   return 0;
 }
 
+static void fill_leaflet_mesh(ms_ctx* c, ms_ctx::Leaflet& L, bool use_trial, ms::LeafletMesh& m) {
+  m.nv = c->nv;
+  m.nf = c->nf;
+  m.tri = c->d_tri.p;
+  m.pos = use_trial ? c->d_trial.p : c->d_pos.p;
+  m.tilts = L.tilts.p;
+  m.keep = L.has_keep ? L.keep.p : nullptr;
+  m.is_boundary = c->has_boundary ? c->d_boundary.p : nullptr;
+  m.interior = L.has_interior ? L.interior.p : nullptr;
+  m.base_zero = L.has_base_zero ? L.base_zero.p : nullptr;
+  m.kappa = L.has_kappa ? L.kappa.p : nullptr;
+  m.c0 = L.has_c0 ? L.c0.p : nullptr;
+  m.kappa_u = L.kappa_u;
+  m.c0_u = L.c0_u;
+  m.row_weight = L.has_weight ? L.weight.p : nullptr;
+  m.consistent = L.has_consistent ? L.consistent.p : nullptr;
+  m.consistent_u = L.consistent_u;
+  m.k_tilt = L.k_tilt;
+  m.sign = L.sign;
+  m.csr_ptr = c->d_csr_ptr.p;
+  m.csr_idx = c->d_csr_idx.p;
+}
+
 int ms_ctx_eval_leaflet(ms_ctx* c, int32_t leaflet, uint32_t modules, int32_t want_grad, int32_t want_tilt_grad,
                         uint32_t accumulate, int32_t use_trial, double* energies2) {
   if (int rc = check_ctx(c, true)) return rc;
@@ -967,26 +992,7 @@ int ms_ctx_eval_leaflet(ms_ctx* c, int32_t leaflet, uint32_t modules, int32_t wa
   if (int rc = c->d_lf_facet_e.ensure(2 * nf + 1)) return rc;
   if (int rc = c->d_lf_e.ensure(2 + 2 * ms::kSumBlocks)) return rc;
   ms::LeafletMesh m;
-  m.nv = c->nv;
-  m.nf = c->nf;
-  m.tri = c->d_tri.p;
-  m.pos = use_trial ? c->d_trial.p : c->d_pos.p;
-  m.tilts = L.tilts.p;
-  m.keep = L.has_keep ? L.keep.p : nullptr;
-  m.is_boundary = c->has_boundary ? c->d_boundary.p : nullptr;
-  m.interior = L.has_interior ? L.interior.p : nullptr;
-  m.base_zero = L.has_base_zero ? L.base_zero.p : nullptr;
-  m.kappa = L.has_kappa ? L.kappa.p : nullptr;
-  m.c0 = L.has_c0 ? L.c0.p : nullptr;
-  m.kappa_u = L.kappa_u;
-  m.c0_u = L.c0_u;
-  m.row_weight = L.has_weight ? L.weight.p : nullptr;
-  m.consistent = L.has_consistent ? L.consistent.p : nullptr;
-  m.consistent_u = L.consistent_u;
-  m.k_tilt = L.k_tilt;
-  m.sign = L.sign;
-  m.csr_ptr = c->d_csr_ptr.p;
-  m.csr_idx = c->d_csr_idx.p;
+  fill_leaflet_mesh(c, L, use_trial != 0, m);
   CU(ms::launch_leaflet(m, (modules & MS_MOD_BENDING_TILT) != 0, (modules & MS_MOD_TILT) != 0, c->d_lf_corner.p,
                         c->d_lf_vbuf.p, c->d_lf_shape.p, c->d_lf_tilt.p, c->d_lf_facet_e.p, c->d_lf_e.p,
                         want_grad ? c->d_grad.p : nullptr, (accumulate & MS_ACC_GRAD) != 0,
@@ -1044,13 +1050,59 @@ int ms_ctx_leaflet_gradient_norm2(ms_ctx* c, int32_t leaflet, double* norm2) {
   return 0;
 }
 
-int ms_ctx_leaflet_make_trial(ms_ctx* c, int32_t leaflet, double step) {
+int ms_ctx_leaflet_make_trial(ms_ctx* c, int32_t leaflet, double step, int32_t along_direction) {
   if (int rc = leaflet_ready(c, leaflet, true)) return rc;
   ms_ctx::Leaflet& L = c->leaflet[leaflet];
   if (!L.tilt_grad.p && c->nv > 0) return fail(-4, "no tilt gradient exists for this leaflet (ms_ctx_eval_leaflet)");
+  if (along_direction && !L.dir.p && c->nv > 0) return fail(-4, "no CG direction exists (ms_ctx_leaflet_cg_direction)");
   if (int rc = L.trial.ensure(3 * size_t(c->nv) + 1)) return rc;
-  CU(ms::launch_tilt_trial(c->nv, L.tilts.p, L.tilt_grad.p, c->d_vnormals.p, L.has_fixed ? L.fixed.p : nullptr, step,
-                           L.trial.p, c->stream));
+  // t - step * g  or  t + step * d
+  CU(ms::launch_tilt_trial(c->nv, L.tilts.p, along_direction ? L.dir.p : L.tilt_grad.p, c->d_vnormals.p,
+                           L.has_fixed ? L.fixed.p : nullptr, along_direction ? -step : step, L.trial.p, c->stream));
+  return 0;
+}
+
+int ms_ctx_leaflet_build_preconditioner(ms_ctx* c, int32_t leaflet, double k_smooth, int32_t kept_facets_only) {
+  if (int rc = leaflet_ready(c, leaflet, false)) return rc;
+  ms_ctx::Leaflet& L = c->leaflet[leaflet];
+  if (!L.set) return fail(-4, "ms_ctx_set_leaflet has not been called for this leaflet");
+  ms::BtMesh bm;
+  if (int rc = bt_prepare(c, bm)) return rc;
+  if (int rc = L.minv.ensure(size_t(c->nv) + 1)) return rc;
+  ms::LeafletMesh m;
+  fill_leaflet_mesh(c, L, false, m);
+  CU(ms::launch_leaflet_jacobi(m, kept_facets_only != 0, k_smooth, L.has_fixed ? L.fixed.p : nullptr, L.minv.p, c->stream));
+  L.has_minv = true;
+  return 0;
+}
+
+static int cg_ready(ms_ctx* c, int32_t leaflet, int32_t preconditioned) {
+  if (int rc = leaflet_ready(c, leaflet, false)) return rc;
+  ms_ctx::Leaflet& L = c->leaflet[leaflet];
+  if (!L.tilt_grad.p && c->nv > 0) return fail(-4, "no tilt gradient exists for this leaflet (ms_ctx_eval_leaflet)");
+  if (preconditioned && !L.has_minv) return fail(-4, "no preconditioner exists (ms_ctx_leaflet_build_preconditioner)");
+  return 0;
+}
+
+int ms_ctx_leaflet_rz(ms_ctx* c, int32_t leaflet, int32_t preconditioned, double* rz) {
+  if (int rc = cg_ready(c, leaflet, preconditioned)) return rc;
+  if (!rz) return fail(-1, "null argument");
+  ms_ctx::Leaflet& L = c->leaflet[leaflet];
+  if (int rc = c->d_rowsq.ensure(size_t(c->nv) + 1)) return rc;
+  if (int rc = c->d_norm_out.ensure(1 + ms::kSumBlocks)) return rc;
+  CU(ms::launch_rz(c->nv, L.tilt_grad.p, preconditioned ? L.minv.p : nullptr, c->d_rowsq.p, c->d_norm_out.p, c->stream));
+  CU(cudaMemcpyAsync(rz, c->d_norm_out.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int ms_ctx_leaflet_cg_direction(ms_ctx* c, int32_t leaflet, double beta, int32_t restart, int32_t preconditioned) {
+  if (int rc = cg_ready(c, leaflet, preconditioned)) return rc;
+  ms_ctx::Leaflet& L = c->leaflet[leaflet];
+  if (!restart && !L.dir.p && c->nv > 0) return fail(-4, "no previous CG direction: restart first");
+  if (int rc = L.dir.ensure(3 * size_t(c->nv) + 1)) return rc;
+  CU(ms::launch_tilt_cg_direction(c->nv, L.tilt_grad.p, preconditioned ? L.minv.p : nullptr, beta, restart != 0, L.dir.p,
+                                  c->stream));
   return 0;
 }
 

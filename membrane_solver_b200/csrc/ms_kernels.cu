@@ -917,6 +917,48 @@ __global__ void __launch_bounds__(256) k_masked_row_norm2(int64_t nv, double* g,
   rowsq[v] = dot(x, x);
 }
 
+// Jacobi preconditioner of the leaflet tilt CG (runtime/preconditioners.py:64-146): diag_v = k_tilt * barycentric
+// area (facets of the leaflet when use_keep, else every facet) + 1/2 k_smooth * sum of the two opposite cotangents
+// over every facet; diag <= 1e-12 and fixed rows -> 1; the inverse is stored.
+__global__ void __launch_bounds__(128) k_leaflet_jacobi(LeafletMesh m, int use_keep, double k_smooth,
+                                                        const uint8_t* __restrict__ fixed, double* minv) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= m.nv) return;
+  double area = 0.0, cot = 0.0;
+  for (int j = m.csr_ptr[v]; j < m.csr_ptr[v + 1]; ++j) {
+    const int f = m.csr_idx[j] / 3, k = m.csr_idx[j] - 3 * f;
+    int idx[3];
+    if (!lf_facet_ok(m, f, idx)) continue;
+    const FacetGeom g = facet_geom(lf_row(m.pos, idx[0]), lf_row(m.pos, idx[1]), lf_row(m.pos, idx[2]));
+    if ((!use_keep || lf_kept(m, f)) && g.S >= kSurfaceSkip) area += 0.5 * g.S / 3.0;
+    const CornerA c = facet_pass_a(g, false, false, false);
+    cot += k == 0 ? c.c1 + c.c2 : (k == 1 ? c.c2 + c.c0 : c.c0 + c.c1);
+  }
+  double diag = m.k_tilt * area + 0.5 * k_smooth * cot;
+  if (!(diag > 1.0e-12)) diag = 1.0;
+  if (fixed && fixed[v]) diag = 1.0;
+  minv[v] = 1.0 / diag;
+}
+
+// rows[v] = g_v . (minv_v g_v)  (the r.z of the preconditioned CG; minv == nullptr -> identity)
+__global__ void __launch_bounds__(256) k_rz_rows(int64_t nv, const double* __restrict__ g, const double* __restrict__ minv,
+                                                 double* rows) {
+  const int64_t v = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (v >= nv) return;
+  const d3 x = ld3(g, v);
+  rows[v] = dot(x, x) * (minv ? minv[v] : 1.0);
+}
+
+// dir = -minv g + beta dir   (restart: beta == 0 and the old direction is not read)
+__global__ void __launch_bounds__(256) k_tilt_cg_direction(int64_t nv, const double* __restrict__ g,
+                                                           const double* __restrict__ minv, double beta, int restart,
+                                                           double* dir) {
+  const int64_t v = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (v >= nv) return;
+  const d3 z = (minv ? -minv[v] : -1.0) * ld3(g, v);
+  st3(dir, v, restart ? z : axpy(beta, ld3(dir, v), z));
+}
+
 __global__ void __launch_bounds__(256) k_row_norm2(const double* __restrict__ rows, int64_t n, double* out) {
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -1290,6 +1332,25 @@ cudaError_t launch_masked_norm2(int64_t nv, double* g, const uint8_t* fixed, dou
                                 cudaStream_t st) {
   if (nv > 0) k_masked_row_norm2<<<blocks_for(nv, 256), 256, 0, st>>>(nv, g, fixed, rowsq);
   sum_fixed_order(rowsq, nv, 1.0, out, out + 1, st);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_leaflet_jacobi(const LeafletMesh& m, bool use_keep, double k_smooth, const uint8_t* fixed, double* minv,
+                                  cudaStream_t st) {
+  if (m.nv > 0) k_leaflet_jacobi<<<blocks_for(m.nv, 128), 128, 0, st>>>(m, use_keep ? 1 : 0, k_smooth, fixed, minv);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rz(int64_t nv, const double* g, const double* minv, double* rows, double* out /*1 + kSumBlocks*/,
+                      cudaStream_t st) {
+  if (nv > 0) k_rz_rows<<<blocks_for(nv, 256), 256, 0, st>>>(nv, g, minv, rows);
+  sum_fixed_order(rows, nv, 1.0, out, out + 1, st);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tilt_cg_direction(int64_t nv, const double* g, const double* minv, double beta, bool restart, double* dir,
+                                     cudaStream_t st) {
+  if (nv > 0) k_tilt_cg_direction<<<blocks_for(nv, 256), 256, 0, st>>>(nv, g, minv, beta, restart ? 1 : 0, dir);
   return cudaGetLastError();
 }
 

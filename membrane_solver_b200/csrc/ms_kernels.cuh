@@ -176,6 +176,11 @@ cudaError_t launch_vertex_normals(int32_t nv, const int32_t* tri, const int32_t*
 cudaError_t launch_project_tangent(int64_t nv, const double* normals, double* t, cudaStream_t st);
 cudaError_t launch_tilt_trial(int64_t nv, const double* t, const double* g, const double* normals, const uint8_t* fixed,
                               double step, double* trial, cudaStream_t st);
+cudaError_t launch_leaflet_jacobi(const LeafletMesh& m, bool use_keep, double k_smooth, const uint8_t* fixed, double* minv,
+                                  cudaStream_t st);
+cudaError_t launch_rz(int64_t nv, const double* g, const double* minv, double* rows, double* out, cudaStream_t st);
+cudaError_t launch_tilt_cg_direction(int64_t nv, const double* g, const double* minv, double beta, bool restart, double* dir,
+                                     cudaStream_t st);
 cudaError_t launch_masked_norm2(int64_t nv, double* g, const uint8_t* fixed, double* rowsq, double* out, cudaStream_t st);
 
 }  // namespace ms

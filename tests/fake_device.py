@@ -134,10 +134,34 @@ class FakeDeviceMesh:
             self.arrays[g][fx] = 0.0
         return float((self.arrays[g] ** 2).sum())
 
-    def leaflet_make_trial(self, leaflet, step):
+    def leaflet_build_preconditioner(self, leaflet, k_smooth, kept_facets_only):
+        from oracle import ref_leaflet as rl
+
+        d = self.leaflets[int(leaflet)]
+        keep = d.get("facet_keep")
+        fx = getattr(self, "leaflet_fixed", {}).get(int(leaflet))
+        fx = np.zeros(self.nv, bool) if fx is None else fx
+        self.__dict__.setdefault("leaflet_minv", {})[int(leaflet)] = rl.leaflet_jacobi_inverse(
+            self.pos, self.tri, area_facets=(np.asarray(keep, bool) if (kept_facets_only and keep is not None) else None),
+            k_tilt=d.get("k_tilt", 0.0), k_smooth=k_smooth, fixed=fx)
+
+    def _minv(self, leaflet, preconditioned):
+        return self.leaflet_minv[int(leaflet)][:, None] if preconditioned else 1.0
+
+    def leaflet_rz(self, leaflet, preconditioned):
+        _, g = self._lf_arrays(leaflet)
+        return float((self.arrays[g] ** 2 * self._minv(leaflet, preconditioned)).sum())
+
+    def leaflet_cg_direction(self, leaflet, beta, restart, preconditioned):
+        _, g = self._lf_arrays(leaflet)
+        z = -self.arrays[g] * self._minv(leaflet, preconditioned)
+        dirs = self.__dict__.setdefault("leaflet_dir", {})
+        dirs[int(leaflet)] = z if restart else z + beta * dirs[int(leaflet)]
+
+    def leaflet_make_trial(self, leaflet, step, along_direction=False):
         a, g = self._lf_arrays(leaflet)
         t = self.arrays[a]
-        y = t - step * self.arrays[g]
+        y = t + step * self.leaflet_dir[int(leaflet)] if along_direction else t - step * self.arrays[g]
         y = y - (y * self.vnormals).sum(axis=1)[:, None] * self.vnormals
         fx = getattr(self, "leaflet_fixed", {}).get(int(leaflet))
         if fx is not None:

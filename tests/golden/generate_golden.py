@@ -458,10 +458,15 @@ def tilt_relaxation_vectors():
     path = os.path.join(REF, "meshes", "caveolin",
                         "kozlov_1disk_3d_tensionless_single_leaflet_profile_hard_rim_R12_free_disk.yaml")
     out = {}
-    for case, steps, step_size in (("gd5", 5, 0.15), ("gd4small", 4, 0.003), ("gdreject", 3, 40.0)):
+    for case, steps, step_size, solver, extra in (("gd5", 5, 0.15, "gd", {}), ("gd4small", 4, 0.003, "gd", {}),
+                                                  ("gdreject", 3, 40.0, "gd", {}), ("cg6", 6, 0.15, "cg", {}),
+                                                  ("cg5plain", 5, 0.15, "cg", {"tilt_cg_preconditioner": "none"}),
+                                                  ("cg6big", 6, 1.0, "cg", {"tilt_cg_rejection_fallback": "gd"})):
         mesh = _refined(path, 1)
         gp = mesh.global_parameters
-        gp.set("tilt_solver", "gd")
+        gp.set("tilt_solver", solver)
+        for k_extra, v_extra in extra.items():
+            gp.set(k_extra, v_extra)
         gp.set("tilt_solve_mode", "nested")
         gp.set("tilt_inner_steps", steps)
         gp.set("tilt_step_size", step_size)
@@ -515,6 +520,13 @@ def tilt_relaxation_vectors():
                   "final_gradient_norm"):
             out[pre + k] = np.float64(stats[k])
         out[pre + "steps"], out[pre + "step_size"] = np.int64(steps), np.float64(step_size)
+        out[pre + "solver"] = np.array(solver)
+        out[pre + "preconditioner"] = np.bool_(extra.get("tilt_cg_preconditioner", "jacobi") == "jacobi")
+        out[pre + "gd_fallback"] = np.bool_(extra.get("tilt_cg_rejection_fallback", "off") == "gd")
+        out[pre + "k_smooth_in"] = np.float64(gp.get("bending_modulus_in") or gp.get("bending_modulus") or 0.0)
+        out[pre + "k_smooth_out"] = np.float64(gp.get("bending_modulus_out") or gp.get("bending_modulus") or 0.0)
+        out[pre + "rejected_steps"] = np.float64(stats["rejected_steps"])
+        out[pre + "stop_reason"] = np.array(str(stats["stop_reason"]))
         print(case, {k: stats[k] for k in ("accepted_steps", "backtracking_steps", "stop_reason", "initial_energy",
                                            "final_energy", "initial_gradient_norm", "final_gradient_norm")})
     np.savez_compressed(os.path.join(HERE, "tilt_relaxation.npz"), **out)

@@ -369,7 +369,7 @@ def test_device_p1_operators_match_reference():
 
 
 # ------------------------------------------------------------------ leaflet tilt relaxation (row f3)
-RELAX_CASES = ("gd5", "gd4small", "gdreject")
+RELAX_CASES = ("gd5", "gd4small", "gdreject", "cg6", "cg5plain", "cg6big")
 
 
 @pytest.fixture(scope="module")
@@ -397,10 +397,17 @@ def test_oracle_tilt_relaxation_matches_reference(relax_gold, case):
     from oracle import ref_leaflet as rl
 
     g, p = relax_gold, case + "_"
-    t, st = rl.relax_leaflet_tilts_gd(g[p + "pos"], g[p + "tri"], {"in": g[p + "tilts_in0"], "out": g[p + "tilts_out0"]},
-                                      _relax_leaflets(g, case), is_boundary=g[p + "is_boundary"],
-                                      fixed={"in": g[p + "fixed_in"], "out": g[p + "fixed_out"]},
-                                      max_iters=int(g[p + "steps"]), step_size=float(g[p + "step_size"]))
+    common = dict(is_boundary=g[p + "is_boundary"], fixed={"in": g[p + "fixed_in"], "out": g[p + "fixed_out"]},
+                  max_iters=int(g[p + "steps"]), step_size=float(g[p + "step_size"]))
+    start = {"in": g[p + "tilts_in0"], "out": g[p + "tilts_out0"]}
+    if str(g[p + "solver"]) == "cg":
+        t, st = rl.relax_leaflet_tilts_cg(g[p + "pos"], g[p + "tri"], start, _relax_leaflets(g, case),
+                                          preconditioner=bool(g[p + "preconditioner"]),
+                                          gd_fallback=bool(g[p + "gd_fallback"]),
+                                          k_smooth={"in": float(g[p + "k_smooth_in"]), "out": float(g[p + "k_smooth_out"])},
+                                          **common)
+    else:
+        t, st = rl.relax_leaflet_tilts_gd(g[p + "pos"], g[p + "tri"], start, _relax_leaflets(g, case), **common)
     _relax_stats_match(st, g, case)
     assert np.max(np.abs(t["in"] - g[p + "tilts_in1"])) <= 1e-12
     assert np.max(np.abs(t["out"] - g[p + "tilts_out1"])) <= 1e-12
@@ -422,8 +429,13 @@ def _device_relaxation(g, case, factory):
                        base_zero=d["base_zero"].astype(np.uint8))
         dm.set_leaflet_fixed(which, g[p + f"fixed_{leaf}"].astype(np.uint8))
         dm.upload(L.ARR_TILTS_IN if leaf == "in" else L.ARR_TILTS_OUT, g[p + f"tilts_{leaf}0"])
-    st = DeviceTiltRelaxer(dm).relax(max_iters=int(g[p + "steps"]), step_size=float(g[p + "step_size"]))
+    st = DeviceTiltRelaxer(dm).relax(
+        max_iters=int(g[p + "steps"]), step_size=float(g[p + "step_size"]), solver=str(g[p + "solver"]),
+        preconditioner=bool(g[p + "preconditioner"]), gd_fallback=bool(g[p + "gd_fallback"]),
+        k_smooth={"in": float(g[p + "k_smooth_in"]), "out": float(g[p + "k_smooth_out"])},
+        area_kept_only={"out": not bool(np.all(g[p + "out_keep"]))})
     _relax_stats_match(st, g, case)
+    assert st["stop_reason"] == str(g[p + "stop_reason"])
     # north_star: trajectories within 1e-9
     assert np.max(np.abs(dm.download(L.ARR_TILTS_IN) - g[p + "tilts_in1"])) <= 1e-10
     assert np.max(np.abs(dm.download(L.ARR_TILTS_OUT) - g[p + "tilts_out1"])) <= 1e-10

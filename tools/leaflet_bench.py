@@ -98,44 +98,52 @@ def large():
 
 
 def relax():
-    """Row f3: the GD tilt relaxation of tests/golden/tilt_relaxation.npz (case gd5: 5 accepted steps, 25 halvings)
-    resident on the device vs. the CPU port of the same loop."""
+    """Row f3: the tilt relaxations of tests/golden/tilt_relaxation.npz (gd5: 5 accepted GD steps, 25 halvings; cg6: 6
+    Jacobi-preconditioned CG steps) resident on the device vs. the CPU port of the same loops."""
     from membrane_solver_b200.runtime.device_tilt_relaxer import DeviceTiltRelaxer
     from oracle import ref_leaflet as rl
 
     g = np.load(os.path.join(ROOT, "tests", "golden", "tilt_relaxation.npz"))
-    p = "gd5_"
-    pos, tri = g[p + "pos"], g[p + "tri"]
-    leaflets = {k: dict(keep=g[p + f"{k}_keep"], interior=g[p + f"{k}_interior"], base_zero=g[p + f"{k}_base_zero"],
-                        kappa=g[p + f"{k}_kappa"], c0=g[p + f"{k}_c0"], k_tilt=float(g[p + f"{k}_k_tilt"]))
-                for k in ("in", "out")}
-    dm = DeviceMesh(0)
-    dm.set_topology(pos.shape[0], tri, is_boundary=g[p + "is_boundary"].astype(np.uint8))
-    dm.set_positions(pos)
-    for leaf, d in leaflets.items():
-        which = L.LEAFLET_IN if leaf == "in" else L.LEAFLET_OUT
-        dm.set_leaflet(which, div_sign=-1.0 if leaf == "in" else 1.0, kappa=1.0, c0=0.0, k_tilt=d["k_tilt"],
-                       facet_keep=d["keep"].astype(np.uint8), interior=d["interior"].astype(np.uint8),
-                       base_zero=d["base_zero"].astype(np.uint8))
-        dm.set_leaflet_fixed(which, g[p + f"fixed_{leaf}"].astype(np.uint8))
-    times = []
-    for rep in range(6):
-        dm.upload(L.ARR_TILTS_IN, g[p + "tilts_in0"])
-        dm.upload(L.ARR_TILTS_OUT, g[p + "tilts_out0"])
+    for case in ("gd5", "cg6"):
+        p = case + "_"
+        pos, tri = g[p + "pos"], g[p + "tri"]
+        leaflets = {k: dict(keep=g[p + f"{k}_keep"], interior=g[p + f"{k}_interior"], base_zero=g[p + f"{k}_base_zero"],
+                            kappa=g[p + f"{k}_kappa"], c0=g[p + f"{k}_c0"], k_tilt=float(g[p + f"{k}_k_tilt"]))
+                    for k in ("in", "out")}
+        dm = DeviceMesh(0)
+        dm.set_topology(pos.shape[0], tri, is_boundary=g[p + "is_boundary"].astype(np.uint8))
+        dm.set_positions(pos)
+        for leaf, d in leaflets.items():
+            which = L.LEAFLET_IN if leaf == "in" else L.LEAFLET_OUT
+            dm.set_leaflet(which, div_sign=-1.0 if leaf == "in" else 1.0, kappa=1.0, c0=0.0, k_tilt=d["k_tilt"],
+                           facet_keep=d["keep"].astype(np.uint8), interior=d["interior"].astype(np.uint8),
+                           base_zero=d["base_zero"].astype(np.uint8))
+            dm.set_leaflet_fixed(which, g[p + f"fixed_{leaf}"].astype(np.uint8))
+        solver = str(g[p + "solver"])
+        ks = {"in": float(g[p + "k_smooth_in"]), "out": float(g[p + "k_smooth_out"])}
+        kw = dict(max_iters=int(g[p + "steps"]), step_size=float(g[p + "step_size"]))
+        times = []
+        for rep in range(6):
+            dm.upload(L.ARR_TILTS_IN, g[p + "tilts_in0"])
+            dm.upload(L.ARR_TILTS_OUT, g[p + "tilts_out0"])
+            t0 = time.perf_counter()
+            st = DeviceTiltRelaxer(dm).relax(solver=solver, k_smooth=ks, area_kept_only={"out": True}, **kw)
+            times.append(time.perf_counter() - t0)
+        dev = min(times[1:])
+        start = {"in": g[p + "tilts_in0"], "out": g[p + "tilts_out0"]}
+        fixed = {"in": g[p + "fixed_in"], "out": g[p + "fixed_out"]}
         t0 = time.perf_counter()
-        st = DeviceTiltRelaxer(dm).relax(max_iters=5, step_size=0.15)
-        times.append(time.perf_counter() - t0)
-    dev = min(times[1:])
-    t0 = time.perf_counter()
-    _, st_cpu = rl.relax_leaflet_tilts_gd(pos, tri, {"in": g[p + "tilts_in0"], "out": g[p + "tilts_out0"]}, leaflets,
-                                          is_boundary=g[p + "is_boundary"],
-                                          fixed={"in": g[p + "fixed_in"], "out": g[p + "fixed_out"]}, max_iters=5,
-                                          step_size=0.15)
-    cpu = time.perf_counter() - t0
-    out(case="caveolin_r1 tilt relaxation gd5", facets=int(tri.shape[0]), accepted=st["accepted_steps"],
-        backtracking=st["backtracking_steps"], final_energy=st["final_energy"], device_ms=dev * 1e3, cpu_port_ms=cpu * 1e3,
-        cpu_final_energy=st_cpu["final_energy"])
-    dm.close()
+        if solver == "cg":
+            _, st_cpu = rl.relax_leaflet_tilts_cg(pos, tri, start, leaflets, is_boundary=g[p + "is_boundary"], fixed=fixed,
+                                                  k_smooth=ks, **kw)
+        else:
+            _, st_cpu = rl.relax_leaflet_tilts_gd(pos, tri, start, leaflets, is_boundary=g[p + "is_boundary"], fixed=fixed,
+                                                  **kw)
+        cpu = time.perf_counter() - t0
+        out(case=f"caveolin_r1 tilt relaxation {case}", facets=int(tri.shape[0]), accepted=st["accepted_steps"],
+            backtracking=st["backtracking_steps"], final_energy=st["final_energy"], device_ms=dev * 1e3,
+            cpu_port_ms=cpu * 1e3, cpu_final_energy=st_cpu["final_energy"])
+        dm.close()
 
 
 if __name__ == "__main__":
