@@ -5,8 +5,8 @@ Twin of ``modules/energy/bending_tilt.py:151-482``:
 ``geometry/tilt_operators.py:158-175``.  The shape gradient treats ``div t`` as constant
 (``bending_tilt.py:14-19``) -- the bending back-propagation with ``term = base + div_eff`` -- and
 the tilt gradient is exact.  ``grad_arr=None`` requests the tilt-only evaluation of the inner tilt
-solve (``evaluation_manager.py:693-698``).  The leaflet variants (``bending_tilt_leaflet.py``) are
-not part of this path yet.
+solve (``evaluation_manager.py:693-698``).  The leaflet variants (``bending_tilt_leaflet.py``) live in
+``bending_tilt_in.py`` / ``bending_tilt_out.py``.
 """
 
 from __future__ import annotations
