@@ -242,6 +242,26 @@ MS_API int ms_ctx_leaflet_cg_direction(ms_ctx* ctx, int32_t leaflet, double beta
 /* exchange the tilt field and the trial field: evaluate at the trial, swap back to reject */
 MS_API int ms_ctx_leaflet_swap_trial(ms_ctx* ctx, int32_t leaflet);
 
+/* ---- halo exchange over NVLink peer memory (multi-GPU, one process per GPU) --------------------------
+ * Each rank exports CUDA IPC handles of its position / trial / seed arrays and of its flag words; the ranks that
+ * hold ghosts of it open them.  ms_ctx_halo_signal publishes "my owned rows of the arrays guarded by this flag are
+ * written" (stream-ordered); ms_ctx_halo_pull waits inside ONE kernel until every owner has published the same
+ * epoch and copies the ghost rows straight out of the owners' memory (no staging buffer, no host round trip).
+ * Every rank must call signal / pull in the same sequence.  The next overwrite of an exported array must be
+ * ordered after a collective that all ranks enter after their pulls (the scalar all-reduce of an evaluation is). */
+#define MS_IPC_FLAGS        100   /* pseudo array id: the flag words */
+#define MS_IPC_HANDLE_BYTES 64
+#define MS_FLAG_POSITIONS   0     /* guards MS_ARR_POSITIONS and MS_ARR_TRIAL */
+#define MS_FLAG_SEEDS       1     /* guards MS_ARR_SEEDS */
+MS_API int ms_ctx_ipc_export(ms_ctx* ctx, int32_t which, uint8_t* handle64);
+MS_API int ms_ctx_peer_open(ms_ctx* ctx, int32_t slot, int32_t which, const uint8_t* handle64);
+/* owner slot and owner-local row of every ghost row [n_owned, nv), in ghost order */
+MS_API int ms_ctx_set_ghost_sources(ms_ctx* ctx, int32_t n_slots, const int32_t* owner_slot, const int32_t* owner_row);
+MS_API int ms_ctx_halo_signal(ms_ctx* ctx, int32_t flag_index);
+MS_API int ms_ctx_halo_pull(ms_ctx* ctx, int32_t which, int32_t flag_index);
+/* 0 while every pull found its flags in time; 1 after a pull gave up waiting (~2 s) */
+MS_API int ms_ctx_halo_error(ms_ctx* ctx, int32_t* error);
+
 /* One evaluation with everything resident: pass A (+ pass B when want_grad), scalar
  * reduction, optional KKT/penalty/fixed post-processing.  Asynchronous on the context
  * stream; results stay on the device. */

@@ -28,6 +28,7 @@ ARR_POSITIONS, ARR_GRAD, ARR_VOLGRAD, ARR_SEEDS, ARR_TILTS, ARR_TILT_GRAD = 0, 1
 ARR_SCALARS, ARR_K_VECS, ARR_A_VOR, ARR_A_EFF, ARR_E_VERTEX, ARR_TRIAL, ARR_DIRECTION = 6, 7, 8, 9, 10, 11, 12
 ARR_TILTS_IN, ARR_TILTS_OUT, ARR_TILT_GRAD_IN, ARR_TILT_GRAD_OUT = 13, 14, 15, 16
 LEAFLET_IN, LEAFLET_OUT = 0, 1
+IPC_FLAGS, IPC_HANDLE_BYTES, FLAG_POSITIONS, FLAG_SEEDS = 100, 64, 0, 1
 ACC_GRAD, ACC_TILT_GRAD = 1, 2
 ARRAY_WIDTH = {ARR_POSITIONS: 3, ARR_GRAD: 3, ARR_VOLGRAD: 3, ARR_SEEDS: 5, ARR_TILTS: 3,
                ARR_TILT_GRAD: 3, ARR_SCALARS: 1, ARR_K_VECS: 3, ARR_A_VOR: 1, ARR_A_EFF: 1,
@@ -143,6 +144,12 @@ SIGNATURES = {
     "ms_ctx_leaflet_rz": (ctypes.c_int, [_V, _i32, _i32, _D]),
     "ms_ctx_leaflet_cg_direction": (ctypes.c_int, [_V, _i32, _f64, _i32, _i32]),
     "ms_ctx_leaflet_swap_trial": (ctypes.c_int, [_V, _i32]),
+    "ms_ctx_ipc_export": (ctypes.c_int, [_V, _i32, _B]),
+    "ms_ctx_peer_open": (ctypes.c_int, [_V, _i32, _i32, _B]),
+    "ms_ctx_set_ghost_sources": (ctypes.c_int, [_V, _i32, _I, _I]),
+    "ms_ctx_halo_signal": (ctypes.c_int, [_V, _i32]),
+    "ms_ctx_halo_pull": (ctypes.c_int, [_V, _i32, _i32]),
+    "ms_ctx_halo_error": (ctypes.c_int, [_V, _I]),
     "ms_ctx_make_trial": (ctypes.c_int, [_V, _f64]),
     "ms_ctx_accept_trial": (ctypes.c_int, [_V]),
     "ms_ctx_dots": (ctypes.c_int, [_V]),

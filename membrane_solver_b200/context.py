@@ -333,6 +333,36 @@ class DeviceMesh:
         rows = np.ascontiguousarray(rows, dtype=np.int32)
         L.check(self._lib.ms_ctx_set_send_rows(self._h, L.iptr(rows), int(rows.size)))
 
+    # -- halo exchange over NVLink peer memory (multi-GPU) -------------------
+    def ipc_export(self, which: int) -> bytes:
+        buf = (ctypes.c_uint8 * L.IPC_HANDLE_BYTES)()
+        L.check(self._lib.ms_ctx_ipc_export(self._h, int(which), buf))
+        return bytes(buf)
+
+    def peer_open(self, slot: int, which: int, handle: bytes) -> None:
+        if len(handle) != L.IPC_HANDLE_BYTES:
+            raise ValueError("IPC handles are 64 bytes")
+        buf = (ctypes.c_uint8 * L.IPC_HANDLE_BYTES).from_buffer_copy(handle)
+        L.check(self._lib.ms_ctx_peer_open(self._h, int(slot), int(which), buf))
+
+    def set_ghost_sources(self, n_slots: int, owner_slot: np.ndarray, owner_row: np.ndarray) -> None:
+        o = np.ascontiguousarray(owner_slot, dtype=np.int32)
+        r = np.ascontiguousarray(owner_row, dtype=np.int32)
+        if o.shape != (self.nv - self.n_owned,) or r.shape != o.shape:
+            raise ValueError("one owner slot and one owner row per ghost row")
+        L.check(self._lib.ms_ctx_set_ghost_sources(self._h, int(n_slots), L.iptr(o), L.iptr(r)))
+
+    def halo_signal(self, flag: int) -> None:
+        L.check(self._lib.ms_ctx_halo_signal(self._h, int(flag)))
+
+    def halo_pull(self, which: int, flag: int) -> None:
+        L.check(self._lib.ms_ctx_halo_pull(self._h, int(which), int(flag)))
+
+    def halo_error(self) -> bool:
+        e = ctypes.c_int32(0)
+        L.check(self._lib.ms_ctx_halo_error(self._h, ctypes.byref(e)))
+        return bool(e.value)
+
     def pack_send(self, which: int, out_device_ptr: int) -> None:
         L.check(self._lib.ms_ctx_pack_send(self._h, int(which), ctypes.c_void_p(int(out_device_ptr))))
 

@@ -127,6 +127,20 @@ struct ms_ctx {
   } leaflet[2];
   DevBuf<double> d_lf_corner, d_lf_vbuf, d_lf_shape, d_lf_tilt, d_lf_facet_e, d_lf_e;
   DevBuf<double> d_vnormals, d_rowsq, d_norm_out;
+  // halo exchange over peer memory: opened peer arrays, flag words, ghost source table
+  struct PeerTable {
+    std::vector<void*> opened;                       // every pointer returned by cudaIpcOpenMemHandle
+    std::vector<const double*> pos, trial, seeds;    // per owner slot
+    std::vector<unsigned long long*> flags;
+    DevBuf<const double*> d_pos, d_trial, d_seeds;
+    DevBuf<unsigned long long*> d_flags;
+    DevBuf<int32_t> d_owner, d_row;
+    int32_t n_slots = 0;
+    bool tables_current = false;
+  } peers;
+  DevBuf<unsigned long long> d_flag_words;           // this rank's flag words (exported)
+  DevBuf<int> d_halo_error;
+  unsigned long long flag_epoch[4] = {0, 0, 0, 0};
   bool vnormals_ready = false;
 };
 
@@ -452,6 +466,8 @@ int ms_ctx_destroy(ms_ctx* c) {
   for (cudaEvent_t e : c->pipe_events)
     if (e) cudaEventDestroy(e);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  for (void* p : c->peers.opened)
+    if (p) cudaIpcCloseMemHandle(p);
   delete c;
   return 0;
 }
@@ -1112,6 +1128,153 @@ int ms_ctx_leaflet_swap_trial(ms_ctx* c, int32_t leaflet) {
   if (!L.trial.p && c->nv > 0) return fail(-4, "no trial tilt field exists (ms_ctx_leaflet_make_trial)");
   std::swap(L.tilts.p, L.trial.p);  // DevBuf owns its pointer: exchange the fields, not the objects
   std::swap(L.tilts.n, L.trial.n);
+  return 0;
+}
+
+// ---- halo exchange over NVLink peer memory ---------------------------------------------------------------
+static int ensure_flag_words(ms_ctx* c) {
+  if (c->d_flag_words.p) return 0;
+  if (int rc = c->d_flag_words.ensure(4)) return rc;
+  CU(cudaMemset(c->d_flag_words.p, 0, 4 * sizeof(unsigned long long)));
+  if (int rc = c->d_halo_error.ensure(1)) return rc;
+  CU(cudaMemset(c->d_halo_error.p, 0, sizeof(int)));
+  return 0;
+}
+
+int ms_ctx_ipc_export(ms_ctx* c, int32_t which, uint8_t* handle64) {
+  if (int rc = check_ctx(c, true)) return rc;
+  if (!handle64) return fail(-1, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == MS_IPC_HANDLE_BYTES, "IPC handle size");
+  void* p = nullptr;
+  if (which == MS_IPC_FLAGS) {
+    if (int rc = ensure_flag_words(c)) return rc;
+    p = c->d_flag_words.p;
+  } else if (which == MS_ARR_POSITIONS || which == MS_ARR_TRIAL || which == MS_ARR_SEEDS) {
+    if (int rc = ensure_array(c, which)) return rc;
+    int64_t len = 0;
+    p = array_ptr(c, which, &len);
+  } else {
+    return fail(-1, "only positions, trial positions, seeds and the flag words are exported");
+  }
+  if (!p) return fail(-1, "array is not allocated");
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, p));
+  std::memcpy(handle64, &h, sizeof(h));
+  return 0;
+}
+
+int ms_ctx_peer_open(ms_ctx* c, int32_t slot, int32_t which, const uint8_t* handle64) {
+  if (int rc = check_ctx(c, true)) return rc;
+  if (!handle64 || slot < 0 || slot >= 4096) return fail(-1, "bad peer arguments");
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle64, sizeof(h));
+  void* p = nullptr;
+  CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  ms_ctx::PeerTable& t = c->peers;
+  t.opened.push_back(p);
+  const size_t need = size_t(slot) + 1;
+  if (t.pos.size() < need) {
+    t.pos.resize(need, nullptr);
+    t.trial.resize(need, nullptr);
+    t.seeds.resize(need, nullptr);
+    t.flags.resize(need, nullptr);
+  }
+  switch (which) {
+    case MS_ARR_POSITIONS: t.pos[size_t(slot)] = static_cast<const double*>(p); break;
+    case MS_ARR_TRIAL: t.trial[size_t(slot)] = static_cast<const double*>(p); break;
+    case MS_ARR_SEEDS: t.seeds[size_t(slot)] = static_cast<const double*>(p); break;
+    case MS_IPC_FLAGS: t.flags[size_t(slot)] = static_cast<unsigned long long*>(p); break;
+    default: return fail(-1, "unknown peer array");
+  }
+  t.tables_current = false;
+  return 0;
+}
+
+int ms_ctx_set_ghost_sources(ms_ctx* c, int32_t n_slots, const int32_t* owner_slot, const int32_t* owner_row) {
+  if (int rc = check_ctx(c, true)) return rc;
+  const int64_t n_ghost = int64_t(c->nv) - c->n_owned;
+  if (n_slots <= 0 || (n_ghost > 0 && (!owner_slot || !owner_row))) return fail(-1, "bad ghost source arguments");
+  for (int64_t g = 0; g < n_ghost; ++g)
+    if (owner_slot[g] < 0 || owner_slot[g] >= n_slots || owner_row[g] < 0) return fail(-1, "ghost source out of range");
+  ms_ctx::PeerTable& t = c->peers;
+  if (int rc = t.d_owner.ensure(size_t(n_ghost) + 1)) return rc;
+  if (int rc = t.d_row.ensure(size_t(n_ghost) + 1)) return rc;
+  if (n_ghost) {
+    CU(cudaMemcpy(t.d_owner.p, owner_slot, size_t(n_ghost) * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(t.d_row.p, owner_row, size_t(n_ghost) * sizeof(int32_t), cudaMemcpyHostToDevice));
+  }
+  t.n_slots = n_slots;
+  t.tables_current = false;
+  return 0;
+}
+
+static int peer_tables(ms_ctx* c) {
+  ms_ctx::PeerTable& t = c->peers;
+  if (t.tables_current) return 0;
+  const size_t n = size_t(t.n_slots);
+  if (n == 0) return fail(-4, "ms_ctx_set_ghost_sources has not been called");
+  t.pos.resize(n, nullptr);
+  t.trial.resize(n, nullptr);
+  t.seeds.resize(n, nullptr);
+  t.flags.resize(n, nullptr);
+  if (int rc = t.d_pos.ensure(n)) return rc;
+  if (int rc = t.d_trial.ensure(n)) return rc;
+  if (int rc = t.d_seeds.ensure(n)) return rc;
+  if (int rc = t.d_flags.ensure(n)) return rc;
+  CU(cudaMemcpy(t.d_pos.p, t.pos.data(), n * sizeof(void*), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(t.d_trial.p, t.trial.data(), n * sizeof(void*), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(t.d_seeds.p, t.seeds.data(), n * sizeof(void*), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(t.d_flags.p, t.flags.data(), n * sizeof(void*), cudaMemcpyHostToDevice));
+  t.tables_current = true;
+  return 0;
+}
+
+int ms_ctx_halo_signal(ms_ctx* c, int32_t flag_index) {
+  if (int rc = check_ctx(c, true)) return rc;
+  if (flag_index < 0 || flag_index >= 4) return fail(-1, "bad flag index");
+  if (int rc = ensure_flag_words(c)) return rc;
+  CU(ms::launch_halo_signal(c->d_flag_words.p + flag_index, ++c->flag_epoch[flag_index], c->stream));
+  return 0;
+}
+
+int ms_ctx_halo_pull(ms_ctx* c, int32_t which, int32_t flag_index) {
+  if (int rc = check_ctx(c, true)) return rc;
+  if (flag_index < 0 || flag_index >= 4) return fail(-1, "bad flag index");
+  if (int rc = ensure_flag_words(c)) return rc;
+  const int64_t n_ghost = int64_t(c->nv) - c->n_owned;
+  if (n_ghost <= 0) return 0;
+  if (int rc = peer_tables(c)) return rc;
+  ms_ctx::PeerTable& t = c->peers;
+  const double* const* table = nullptr;
+  const std::vector<const double*>* host = nullptr;
+  int width = 3;
+  switch (which) {
+    case MS_ARR_POSITIONS: table = t.d_pos.p; host = &t.pos; break;
+    case MS_ARR_TRIAL: table = t.d_trial.p; host = &t.trial; break;
+    case MS_ARR_SEEDS: table = t.d_seeds.p; host = &t.seeds; width = ms::kSeedStride; break;
+    default: return fail(-1, "only positions, trial positions and seeds travel through the halo");
+  }
+  bool any = false;
+  for (const double* p : *host) any = any || p != nullptr;
+  if (!any) return fail(-4, "no peer array has been opened for this exchange (ms_ctx_peer_open)");
+  int64_t len = 0;
+  double* dst = array_ptr(c, which, &len);
+  if (!dst) return fail(-4, "the local array does not exist");
+  // the epoch this rank has published is the epoch every owner must have reached (lock-step sequence)
+  CU(ms::launch_halo_pull(int(n_ghost), width, table, t.d_flags.p, t.n_slots, flag_index, c->flag_epoch[flag_index],
+                          t.d_owner.p, t.d_row.p, dst + size_t(c->n_owned) * width, c->d_halo_error.p, c->stream));
+  return 0;
+}
+
+int ms_ctx_halo_error(ms_ctx* c, int32_t* error) {
+  if (int rc = check_ctx(c, true)) return rc;
+  if (!error) return fail(-1, "null argument");
+  *error = 0;
+  if (!c->d_halo_error.p) return 0;
+  int e = 0;
+  CU(cudaMemcpyAsync(&e, c->d_halo_error.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  *error = e;
   return 0;
 }
 

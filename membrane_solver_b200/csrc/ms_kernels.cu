@@ -959,6 +959,49 @@ __global__ void __launch_bounds__(256) k_tilt_cg_direction(int64_t nv, const dou
   st3(dir, v, restart ? z : axpy(beta, ld3(dir, v), z));
 }
 
+// ---- halo exchange over NVLink peer memory ------------------------------------------------------------
+// Every rank publishes "my owned rows of this array are written" by storing an epoch number into its flag
+// word (k_halo_signal, stream-ordered after the producing kernel).  A consumer waits until every owner's flag
+// has reached the epoch it expects and then copies its ghost rows straight out of the owners' arrays with
+// peer loads (k_halo_pull): one kernel, no staging buffer, no host round trip.  The wait is bounded: after
+// ~2 s without the flag the kernel records an error instead of spinning forever.
+__global__ void k_halo_signal(unsigned long long* flag, unsigned long long epoch) {
+  __threadfence_system();
+  *reinterpret_cast<volatile unsigned long long*>(flag) = epoch;
+  __threadfence_system();
+}
+
+__global__ void __launch_bounds__(256) k_halo_pull(int n_ghost, int width, const double* const* __restrict__ peer_base,
+                                                   unsigned long long* const* __restrict__ peer_flag, int n_slots,
+                                                   int flag_index, unsigned long long epoch,
+                                                   const int32_t* __restrict__ owner, const int32_t* __restrict__ row,
+                                                   double* dst, int* error) {
+  __shared__ int ok;
+  if (threadIdx.x == 0) ok = 1;
+  __syncthreads();
+  for (int s = threadIdx.x; s < n_slots; s += blockDim.x) {
+    if (!peer_flag[s]) continue;
+    const volatile unsigned long long* f = peer_flag[s] + flag_index;
+    const long long t0 = clock64();
+    while (*f < epoch) {
+      if (clock64() - t0 > 4000000000LL) {
+        atomicExch(error, 1);
+        ok = 0;
+        break;
+      }
+      __nanosleep(200);
+    }
+  }
+  __syncthreads();
+  if (!ok) return;
+  __threadfence_system();
+  const int total = n_ghost * width;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int g = i / width, k = i - g * width;
+    dst[i] = __ldcv(peer_base[owner[g]] + size_t(row[g]) * width + k);
+  }
+}
+
 __global__ void __launch_bounds__(256) k_row_norm2(const double* __restrict__ rows, int64_t n, double* out) {
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -1351,6 +1394,21 @@ cudaError_t launch_rz(int64_t nv, const double* g, const double* minv, double* r
 cudaError_t launch_tilt_cg_direction(int64_t nv, const double* g, const double* minv, double beta, bool restart, double* dir,
                                      cudaStream_t st) {
   if (nv > 0) k_tilt_cg_direction<<<blocks_for(nv, 256), 256, 0, st>>>(nv, g, minv, beta, restart ? 1 : 0, dir);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_halo_signal(unsigned long long* flag, unsigned long long epoch, cudaStream_t st) {
+  k_halo_signal<<<1, 1, 0, st>>>(flag, epoch);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_halo_pull(int n_ghost, int width, const double* const* peer_base, unsigned long long* const* peer_flag,
+                             int n_slots, int flag_index, unsigned long long epoch, const int32_t* owner,
+                             const int32_t* row, double* dst, int* error, cudaStream_t st) {
+  if (n_ghost <= 0) return cudaSuccess;
+  const int blocks = (n_ghost * width + 255) / 256;
+  k_halo_pull<<<blocks < 64 ? blocks : 64, 256, 0, st>>>(n_ghost, width, peer_base, peer_flag, n_slots, flag_index, epoch,
+                                                          owner, row, dst, error);
   return cudaGetLastError();
 }
 

@@ -170,6 +170,11 @@ cudaError_t launch_leaflet(const LeafletMesh& m, bool with_bt, bool with_tilt, d
                            double* corner_shape, double* corner_tilt, double* facet_e, double* e_out2, double* grad,
                            bool accumulate_grad, double* tilt_grad, bool accumulate_tilt_grad, cudaStream_t st);
 
+// --- halo exchange over NVLink peer memory (flag wait + peer loads in one kernel) ---
+cudaError_t launch_halo_signal(unsigned long long* flag, unsigned long long epoch, cudaStream_t st);
+cudaError_t launch_halo_pull(int n_ghost, int width, const double* const* peer_base, unsigned long long* const* peer_flag,
+                             int n_slots, int flag_index, unsigned long long epoch, const int32_t* owner,
+                             const int32_t* row, double* dst, int* error, cudaStream_t st);
 // --- leaflet tilt relaxation helpers ---
 cudaError_t launch_vertex_normals(int32_t nv, const int32_t* tri, const int32_t* csr_ptr, const int32_t* csr_idx,
                                   const double* pos, double* normals, cudaStream_t st);

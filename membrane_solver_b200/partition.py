@@ -14,9 +14,16 @@ One evaluation on every rank::
                      ->  all-reduce(12 scalars)  ->  project (KKT with the global lambda)
 
 The two halo exchanges move ``24`` and ``40`` bytes per ghost vertex (O(sqrt(nv/P))
-ghosts per rank); the all-reduce moves 96 bytes.  ``torch.distributed`` (NCCL over
-NVLink on the GPU box, gloo in the CPU tests) is the transport; the gather of the rows
-a neighbour needs is a kernel of this library (``ms_ctx_pack_send``).
+ghosts per rank); the all-reduce moves 96 bytes.  Two transports for the halo:
+
+* ``peer`` (default on GPUs): each rank opens the owners' arrays through CUDA IPC and ONE kernel of this
+  library waits for the owners' epoch flags and copies the ghost rows with NVLink peer loads
+  (``ms_ctx_halo_signal`` / ``ms_ctx_halo_pull``) -- no staging buffer, no send/recv launches;
+* ``nccl``: ``torch.distributed`` send/recv of rows gathered by ``ms_ctx_pack_send`` (also gloo in the
+  CPU tests).
+
+The scalar all-reduce is ``torch.distributed`` in both; it also orders the next overwrite of the exported
+arrays after every rank's pulls.
 
 Only numpy is needed to build the partition (``split_mesh``), so the plan is unit
 tested on the CPU; ``PartitionedMesh`` needs a GPU per rank.
@@ -152,7 +159,7 @@ class PartitionedMesh:
     """One rank's share of a mesh on its GPU plus the exchange plumbing."""
 
     def __init__(self, local: LocalMesh, device_index: int, *, body_mask=None, is_boundary=None,
-                 fixed_mask=None, pack=None, reserve_sms: int = 0):
+                 fixed_mask=None, pack=None, reserve_sms: int = 0, transport: str | None = None):
         import torch
         import torch.distributed as dist
 
@@ -172,6 +179,12 @@ class PartitionedMesh:
         sends = send_lists(local, gathered)
         self.halo = HaloExchange(local, sends, dist, torch, self.device)
         self.dm.set_send_rows(self.halo.send_rows)
+        import os as _os
+
+        want = (transport or _os.environ.get("MS_HALO", "peer")).strip().lower()
+        self.transport = "nccl"
+        if want == "peer" and local.world > 1:
+            self.transport = "peer" if self._open_peers(gathered) else "nccl"
         # the context launches on the legacy default stream; torch's current stream is the
         # same stream unless the caller changed it, so kernels and NCCL calls stay ordered
         if reserve_sms > 0:
@@ -190,7 +203,45 @@ class PartitionedMesh:
             self._views[which] = t
         return t
 
+    def _open_peers(self, all_ghost_ids) -> bool:
+        """Exchange the IPC handles of the position / trial / seed arrays and of the flag words and open the
+        owners of this rank's ghosts.  All ranks agree on the outcome (a failure anywhere -> NCCL for all)."""
+        L, dm, dist, local = self.L, self.dm, self.dist, self.local
+        whiches = (L.ARR_POSITIONS, L.ARR_TRIAL, L.ARR_SEEDS, L.IPC_FLAGS)
+        ok, mine, err = 1, None, ""
+        try:
+            mine = [dm.ipc_export(w) for w in whiches]
+        except L.B200Error as exc:
+            ok, err = 0, str(exc)
+        table = [None] * local.world
+        dist.all_gather_object(table, mine)
+        if ok and all(t is not None for t in table):
+            owners = np.searchsorted(local.cuts, local.ghost_ids, side="right") - 1
+            rows = local.ghost_ids - local.cuts[owners]
+            try:
+                for o in np.unique(owners):
+                    for w, handle in zip(whiches, table[int(o)]):
+                        dm.peer_open(int(o), w, handle)
+                dm.set_ghost_sources(local.world, owners.astype(np.int32), rows.astype(np.int32))
+            except L.B200Error as exc:
+                ok, err = 0, str(exc)
+        else:
+            ok = 0
+        flag = self.torch.tensor([ok], dtype=self.torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0 and err:
+            import sys
+
+            print(f"[ms_b200] rank {local.rank}: peer-memory halo unavailable ({err}); using NCCL send/recv",
+                  file=sys.stderr)
+        return int(flag.item()) == 1
+
     def exchange(self, which: int) -> None:
+        if self.transport == "peer":
+            flag = self.L.FLAG_SEEDS if which == self.L.ARR_SEEDS else self.L.FLAG_POSITIONS
+            self.dm.halo_signal(flag)
+            self.dm.halo_pull(which, flag)
+            return
         self.halo.exchange(self.view(which), lambda buf: self.dm.pack_send(which, buf.data_ptr()))
 
     def _with_patches(self, opts, which: int):
@@ -257,7 +308,10 @@ class PartitionedMesh:
 
     def eval(self, opts, **kw):
         self.eval_async(opts, **kw)
-        return self.dm.read_scalars()
+        res = self.dm.read_scalars()
+        if self.transport == "peer" and self.dm.halo_error():
+            raise self.L.B200Error("a halo pull gave up waiting for a peer's flag (a rank left the lock-step sequence)")
+        return res
 
     def eval_host(self, opts, pos_owned: np.ndarray, grad_owned: np.ndarray):
         """End-to-end evaluation with HOST buffers: this rank uploads the positions of its OWNED rows,
@@ -408,9 +462,10 @@ def bench_multi_gpu(args, rank: int, world: int, local_rank: int, bench):
                     "d2h_bytes_per_step": int(io[1].item()), "ms_per_step": ms_e2e,
                     "api": "PartitionedMesh.eval_host per rank (pinned owned positions in, halo exchange, "
                            "projected gradient of the owned rows + scalars out)"},
-            "collectives_per_step": {"halo_exchanges": 2, "all_reduce": 1,
+            "collectives_per_step": {"halo_exchanges": 2, "all_reduce": 1, "halo_transport": pm.transport,
                                      "halo_bytes_per_rank": int(ghosts[0].item()) * (24 + 40)},
-            "gpu_launches": 6 * args.steps,  # pass A, pass B, reduce, project + 2 halo gathers
+            # pass A, pass B, reduce, project + per halo exchange: flag signal + pull (peer) or the row gather (nccl)
+            "gpu_launches": (4 + (4 if pm.transport == "peer" else 2)) * args.steps,
             "clocks": sampler.summary(),
             "energies": {"surface": res.e_surface, "bending": res.e_bending, "volume": res.volume},
             "setup_seconds": t_gen,

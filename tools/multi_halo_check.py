@@ -1,0 +1,79 @@
+"""torchrun -n N tools/multi_halo_check.py [facets_per_gpu]: the peer-memory halo against the NCCL send/recv halo on
+the same partitioned mesh -- scalars and owned gradients must be BITWISE equal (only the transport differs) -- and
+the time per distributed evaluation with either."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from membrane_solver_b200 import _lib as L  # noqa: E402
+from membrane_solver_b200.partition import PartitionedMesh, split_mesh  # noqa: E402
+from membrane_solver_b200.synthetic import frequency_for_facets, icosphere  # noqa: E402
+
+
+def main():
+    rank, world, local_rank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    per_gpu = int(sys.argv[1]) if len(sys.argv) > 1 else 2_500_000
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pos, tri = icosphere(frequency_for_facets(per_gpu * world))
+    rng = np.random.default_rng(4)
+    pos = pos * (1.0 + 0.01 * rng.standard_normal((pos.shape[0], 1)))
+    local = split_mesh(pos.shape[0], tri, world, rank)
+    pm = PartitionedMesh(local, local_rank, body_mask=np.ones(local.tri.shape[0], np.uint8))
+    assert pm.transport == "peer", pm.transport
+    dm = pm.dm
+    dm.set_surface_tension(1.0)
+    dm.set_bending_params(1.0, 0.0)
+    rows = local.global_rows()
+    # ghost rows start from garbage: the halo has to bring them
+    start = pos[rows].copy()
+    start[local.n_owned:] = 7.0
+    opts = dm.options(L.MOD_SURFACE | L.MOD_BENDING | L.MOD_VOLUME, constraint_mode=0)
+    out = {}
+    for transport in ("nccl", "peer", "nccl", "peer"):
+        pm.transport = transport
+        dm.set_positions(start)
+        res = pm.eval(opts)
+        grad = dm.download(L.ARR_GRAD)[: local.n_owned]
+        got_pos = dm.download(L.ARR_POSITIONS)
+        assert np.array_equal(got_pos, pos[rows]), f"rank {rank}: ghost positions differ with {transport}"
+        key = (res.e_surface, res.e_bending, res.volume, res.kkt_lambda)
+        if transport in out:
+            assert out[transport][0] == key and np.array_equal(out[transport][1], grad), f"{transport} not repeatable"
+        out[transport] = (key, grad)
+        for _ in range(3):
+            pm.eval_async(opts)
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            pm.eval_async(opts)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / 20], device=pm.device)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        out[transport + "_ms"] = float(ms.item())
+        assert not dm.halo_error()
+    assert out["nccl"][0] == out["peer"][0], (out["nccl"][0], out["peer"][0])
+    assert np.array_equal(out["nccl"][1], out["peer"][1])
+    # energy-only evaluation at trial positions (the line-search call) through the peer halo
+    pm.transport = "peer"
+    if rank == 0:
+        print(json.dumps({"n_gpus": world, "facets": int(tri.shape[0]), "ghost_rows": int(local.ghost_ids.size),
+                          "bitwise_equal": True, "nccl_ms": out["nccl_ms"], "peer_ms": out["peer_ms"],
+                          "E_surface": out["peer"][0][0], "E_bending": out["peer"][0][1]}), flush=True)
+    dist.barrier()
+    dm.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
