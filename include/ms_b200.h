@@ -259,6 +259,12 @@ MS_API int ms_ctx_peer_open(ms_ctx* ctx, int32_t slot, int32_t which, const uint
 MS_API int ms_ctx_set_ghost_sources(ms_ctx* ctx, int32_t n_slots, const int32_t* owner_slot, const int32_t* owner_row);
 MS_API int ms_ctx_halo_signal(ms_ctx* ctx, int32_t flag_index);
 MS_API int ms_ctx_halo_pull(ms_ctx* ctx, int32_t which, int32_t flag_index);
+/* this rank's slot among n_slots ranks (its own flag block takes part in the all-reduce) */
+MS_API int ms_ctx_set_rank_slot(ms_ctx* ctx, int32_t slot, int32_t n_slots);
+/* sum of MS_ARR_SCALARS[0..count) over all ranks through peer memory, in rank order (bitwise the same on every
+ * rank); needs the flag words of EVERY rank opened.  Replaces the NCCL all-reduce of an evaluation and, like it,
+ * is entered by every rank after its pulls. */
+MS_API int ms_ctx_allreduce_scalars(ms_ctx* ctx, int32_t count);
 /* 0 while every pull found its flags in time; 1 after a pull gave up waiting (~2 s) */
 MS_API int ms_ctx_halo_error(ms_ctx* ctx, int32_t* error);
 

@@ -358,6 +358,12 @@ class DeviceMesh:
     def halo_pull(self, which: int, flag: int) -> None:
         L.check(self._lib.ms_ctx_halo_pull(self._h, int(which), int(flag)))
 
+    def set_rank_slot(self, slot: int, n_slots: int) -> None:
+        L.check(self._lib.ms_ctx_set_rank_slot(self._h, int(slot), int(n_slots)))
+
+    def allreduce_scalars(self, count: int = 12) -> None:
+        L.check(self._lib.ms_ctx_allreduce_scalars(self._h, int(count)))
+
     def halo_error(self) -> bool:
         e = ctypes.c_int32(0)
         L.check(self._lib.ms_ctx_halo_error(self._h, ctypes.byref(e)))

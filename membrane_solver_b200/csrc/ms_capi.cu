@@ -1134,8 +1134,8 @@ int ms_ctx_leaflet_swap_trial(ms_ctx* c, int32_t leaflet) {
 // ---- halo exchange over NVLink peer memory ---------------------------------------------------------------
 static int ensure_flag_words(ms_ctx* c) {
   if (c->d_flag_words.p) return 0;
-  if (int rc = c->d_flag_words.ensure(4)) return rc;
-  CU(cudaMemset(c->d_flag_words.p, 0, 4 * sizeof(unsigned long long)));
+  if (int rc = c->d_flag_words.ensure(ms::kFlagWords)) return rc;
+  CU(cudaMemset(c->d_flag_words.p, 0, ms::kFlagWords * sizeof(unsigned long long)));
   if (int rc = c->d_halo_error.ensure(1)) return rc;
   CU(cudaMemset(c->d_halo_error.p, 0, sizeof(int)));
   return 0;
@@ -1263,6 +1263,37 @@ int ms_ctx_halo_pull(ms_ctx* c, int32_t which, int32_t flag_index) {
   // the epoch this rank has published is the epoch every owner must have reached (lock-step sequence)
   CU(ms::launch_halo_pull(int(n_ghost), width, table, t.d_flags.p, t.n_slots, flag_index, c->flag_epoch[flag_index],
                           t.d_owner.p, t.d_row.p, dst + size_t(c->n_owned) * width, c->d_halo_error.p, c->stream));
+  return 0;
+}
+
+int ms_ctx_set_rank_slot(ms_ctx* c, int32_t slot, int32_t n_slots) {
+  if (int rc = check_ctx(c, true)) return rc;
+  if (n_slots <= 0 || slot < 0 || slot >= n_slots) return fail(-1, "bad rank slot");
+  if (int rc = ensure_flag_words(c)) return rc;
+  ms_ctx::PeerTable& t = c->peers;
+  const size_t need = size_t(n_slots);
+  if (t.pos.size() < need) {
+    t.pos.resize(need, nullptr);
+    t.trial.resize(need, nullptr);
+    t.seeds.resize(need, nullptr);
+    t.flags.resize(need, nullptr);
+  }
+  t.flags[size_t(slot)] = c->d_flag_words.p;  // this rank's own block takes part in the all-reduce
+  t.n_slots = n_slots;
+  t.tables_current = false;
+  return 0;
+}
+
+int ms_ctx_allreduce_scalars(ms_ctx* c, int32_t count) {
+  if (int rc = check_ctx(c, true)) return rc;
+  if (count <= 0 || count > 16) return fail(-1, "between 1 and 16 scalars");
+  if (int rc = ensure_flag_words(c)) return rc;
+  if (int rc = peer_tables(c)) return rc;
+  ms_ctx::PeerTable& t = c->peers;
+  for (int32_t s = 0; s < t.n_slots; ++s)
+    if (!t.flags[size_t(s)]) return fail(-4, "the flag words of every rank must be opened (ms_ctx_peer_open, ms_ctx_set_rank_slot)");
+  CU(ms::launch_allreduce_peer(c->d_scalars.p, count, c->d_flag_words.p, t.d_flags.p, t.n_slots, ++c->flag_epoch[2],
+                               c->d_halo_error.p, c->stream));
   return 0;
 }
 

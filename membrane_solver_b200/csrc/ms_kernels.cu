@@ -980,7 +980,7 @@ __global__ void __launch_bounds__(256) k_halo_pull(int n_ghost, int width, const
   if (threadIdx.x == 0) ok = 1;
   __syncthreads();
   for (int s = threadIdx.x; s < n_slots; s += blockDim.x) {
-    if (!peer_flag[s]) continue;
+    if (!peer_flag[s] || !peer_base[s]) continue;  // only the owners of this rank's ghosts
     const volatile unsigned long long* f = peer_flag[s] + flag_index;
     const long long t0 = clock64();
     while (*f < epoch) {
@@ -999,6 +999,52 @@ __global__ void __launch_bounds__(256) k_halo_pull(int n_ghost, int width, const
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int g = i / width, k = i - g * width;
     dst[i] = __ldcv(peer_base[owner[g]] + size_t(row[g]) * width + k);
+  }
+}
+
+// All-reduce (sum) of n <= 16 scalars over peer memory.  Word layout of every rank's exported block:
+// [0..3] epoch flags, [8 + 16 p .. 8 + 16 p + 15] scalar slot of parity p.  Publish: copy this rank's scalars into
+// the slot of the epoch's parity, then raise flag 2.  Gather: wait for every rank's flag, add the slots in RANK
+// ORDER (the same order on every rank, so all ranks hold bitwise the same sums) and store them.  Two slots: a
+// rank can publish epoch e+1 only after it has seen every flag of epoch e, and a peer can only lag behind reading
+// epoch e, never e-1.
+__global__ void k_allreduce_publish(const double* __restrict__ scalars, int n, unsigned long long* words,
+                                    unsigned long long epoch) {
+  double* slot = reinterpret_cast<double*>(words + 8 + 16 * (epoch & 1ull));
+  if (int(threadIdx.x) < n) slot[threadIdx.x] = scalars[threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(words + 2) = epoch;
+    __threadfence_system();
+  }
+}
+
+__global__ void k_allreduce_gather(unsigned long long* const* __restrict__ peer_words, int n_slots, int n,
+                                   unsigned long long epoch, double* scalars, int* error) {
+  __shared__ int ok;
+  if (threadIdx.x == 0) ok = 1;
+  __syncthreads();
+  for (int s = threadIdx.x; s < n_slots; s += blockDim.x) {
+    const volatile unsigned long long* f = peer_words[s] + 2;
+    const long long t0 = clock64();
+    while (*f < epoch) {
+      if (clock64() - t0 > 4000000000LL) {
+        atomicExch(error, 1);
+        ok = 0;
+        break;
+      }
+      __nanosleep(200);
+    }
+  }
+  __syncthreads();
+  if (!ok) return;
+  __threadfence_system();
+  if (int(threadIdx.x) < n) {
+    double acc = 0.0;
+    for (int s = 0; s < n_slots; ++s)
+      acc += __ldcv(reinterpret_cast<const double*>(peer_words[s] + 8 + 16 * (epoch & 1ull)) + threadIdx.x);
+    scalars[threadIdx.x] = acc;
   }
 }
 
@@ -1409,6 +1455,13 @@ cudaError_t launch_halo_pull(int n_ghost, int width, const double* const* peer_b
   const int blocks = (n_ghost * width + 255) / 256;
   k_halo_pull<<<blocks < 64 ? blocks : 64, 256, 0, st>>>(n_ghost, width, peer_base, peer_flag, n_slots, flag_index, epoch,
                                                           owner, row, dst, error);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_allreduce_peer(double* scalars, int n, unsigned long long* own_words, unsigned long long* const* peer_words,
+                                  int n_slots, unsigned long long epoch, int* error, cudaStream_t st) {
+  k_allreduce_publish<<<1, 32, 0, st>>>(scalars, n, own_words, epoch);
+  k_allreduce_gather<<<1, 64, 0, st>>>(peer_words, n_slots, n, epoch, scalars, error);
   return cudaGetLastError();
 }
 

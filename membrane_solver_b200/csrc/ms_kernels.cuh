@@ -175,6 +175,10 @@ cudaError_t launch_halo_signal(unsigned long long* flag, unsigned long long epoc
 cudaError_t launch_halo_pull(int n_ghost, int width, const double* const* peer_base, unsigned long long* const* peer_flag,
                              int n_slots, int flag_index, unsigned long long epoch, const int32_t* owner,
                              const int32_t* row, double* dst, int* error, cudaStream_t st);
+cudaError_t launch_allreduce_peer(double* scalars, int n, unsigned long long* own_words, unsigned long long* const* peer_words,
+                                  int n_slots, unsigned long long epoch, int* error, cudaStream_t st);
+constexpr int kFlagWords = 64;  // exported block: 4 epoch flags, 2 x 16 scalar slots (see k_allreduce_publish)
+
 // --- leaflet tilt relaxation helpers ---
 cudaError_t launch_vertex_normals(int32_t nv, const int32_t* tri, const int32_t* csr_ptr, const int32_t* csr_idx,
                                   const double* pos, double* normals, cudaStream_t st);

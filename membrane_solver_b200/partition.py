@@ -220,8 +220,12 @@ class PartitionedMesh:
             rows = local.ghost_ids - local.cuts[owners]
             try:
                 for o in np.unique(owners):
-                    for w, handle in zip(whiches, table[int(o)]):
+                    for w, handle in zip(whiches[:3], table[int(o)][:3]):
                         dm.peer_open(int(o), w, handle)
+                for r in range(local.world):      # the flag / scalar words of every rank: all-reduce over peer memory
+                    if r != local.rank:
+                        dm.peer_open(r, L.IPC_FLAGS, table[r][3])
+                dm.set_rank_slot(local.rank, local.world)
                 dm.set_ghost_sources(local.world, owners.astype(np.int32), rows.astype(np.int32))
             except L.B200Error as exc:
                 ok, err = 0, str(exc)
@@ -280,8 +284,7 @@ class PartitionedMesh:
                 self.exchange(L.ARR_SEEDS)
             dm.eval_pass_b(opts)
             dm.eval_reduce(opts)
-            sc = self.view(L.ARR_SCALARS)
-            self.dist.all_reduce(sc[:12], op=self.dist.ReduceOp.SUM)
+            self._allreduce_scalars()
             dm.eval_project(opts)
             return
         main = torch.cuda.current_stream(self.device)
@@ -302,9 +305,17 @@ class PartitionedMesh:
             main.wait_stream(side)
         dm.eval_pass_b(outer)
         dm.eval_reduce(outer)
-        sc = self.view(L.ARR_SCALARS)
-        self.dist.all_reduce(sc[:12], op=self.dist.ReduceOp.SUM)
+        self._allreduce_scalars()
         dm.eval_project(opts)
+
+    def _allreduce_scalars(self) -> None:
+        """Global sums of the 12 evaluation scalars: one kernel pair over peer memory (rank-order sum, bitwise the
+        same on every rank) with the peer transport, ``torch.distributed`` otherwise."""
+        if self.transport == "peer":
+            self.dm.allreduce_scalars(12)
+            return
+        sc = self.view(self.L.ARR_SCALARS)
+        self.dist.all_reduce(sc[:12], op=self.dist.ReduceOp.SUM)
 
     def eval(self, opts, **kw):
         self.eval_async(opts, **kw)
@@ -403,7 +414,7 @@ def bench_multi_gpu(args, rank: int, world: int, local_rank: int, bench):
             evs[2].record(); pm.exchange(L.ARR_SEEDS)
             evs[3].record(); dm.eval_pass_b(opts)
             evs[4].record(); dm.eval_reduce(opts)
-            evs[5].record(); dist.all_reduce(pm.view(L.ARR_SCALARS)[:12])
+            evs[5].record(); pm._allreduce_scalars()
             evs[6].record(); dm.eval_project(opts)
             evs[7].record(); torch.cuda.synchronize()
             acc += [evs[i].elapsed_time(evs[i + 1]) for i in range(len(names))]
@@ -463,9 +474,11 @@ def bench_multi_gpu(args, rank: int, world: int, local_rank: int, bench):
                     "api": "PartitionedMesh.eval_host per rank (pinned owned positions in, halo exchange, "
                            "projected gradient of the owned rows + scalars out)"},
             "collectives_per_step": {"halo_exchanges": 2, "all_reduce": 1, "halo_transport": pm.transport,
+                                     "all_reduce_transport": "peer memory" if pm.transport == "peer" else "nccl",
                                      "halo_bytes_per_rank": int(ghosts[0].item()) * (24 + 40)},
             # pass A, pass B, reduce, project + per halo exchange: flag signal + pull (peer) or the row gather (nccl)
-            "gpu_launches": (4 + (4 if pm.transport == "peer" else 2)) * args.steps,
+            # + the peer all-reduce's publish and gather kernels
+            "gpu_launches": (4 + (6 if pm.transport == "peer" else 2)) * args.steps,
             "clocks": sampler.summary(),
             "energies": {"surface": res.e_surface, "bending": res.e_bending, "volume": res.volume},
             "setup_seconds": t_gen,

@@ -62,13 +62,18 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         out[transport + "_ms"] = float(ms.item())
         assert not dm.halo_error()
-    assert out["nccl"][0] == out["peer"][0], (out["nccl"][0], out["peer"][0])
-    assert np.array_equal(out["nccl"][1], out["peer"][1])
+    # the peer all-reduce adds in rank order; NCCL's order is its own: identical for two ranks, rounding beyond
+    a, b = np.array(out["nccl"][0]), np.array(out["peer"][0])
+    bitwise = bool(np.array_equal(a, b) and np.array_equal(out["nccl"][1], out["peer"][1]))
+    assert np.all(np.abs(a - b) <= 1e-13 * np.maximum(1.0, np.abs(a))), (a, b)
+    scale = np.abs(out["nccl"][1]).max()
+    assert np.abs(out["nccl"][1] - out["peer"][1]).max() <= 1e-12 * scale
+    assert bitwise or world > 2
     # energy-only evaluation at trial positions (the line-search call) through the peer halo
     pm.transport = "peer"
     if rank == 0:
         print(json.dumps({"n_gpus": world, "facets": int(tri.shape[0]), "ghost_rows": int(local.ghost_ids.size),
-                          "bitwise_equal": True, "nccl_ms": out["nccl_ms"], "peer_ms": out["peer_ms"],
+                          "bitwise_equal": bitwise, "nccl_ms": out["nccl_ms"], "peer_ms": out["peer_ms"],
                           "E_surface": out["peer"][0][0], "E_bending": out["peer"][0][1]}), flush=True)
     dist.barrier()
     dm.close()
