@@ -446,6 +446,8 @@ def bench_multi_gpu(args, rank: int, world: int, local_rank: int, bench):
     ev1.record()
     torch.cuda.synchronize()
     dist.barrier()
+    if pm.transport == "peer" and dm.halo_error():
+        raise L.B200Error(f"rank {rank}: a peer-memory pull gave up waiting; the numbers of this run are void")
     ms2 = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=pm.device)
     dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     ms_e2e = float(ms2.item()) / e2e_steps
