@@ -255,6 +255,10 @@ MS_API int ms_ctx_leaflet_swap_trial(ms_ctx* ctx, int32_t leaflet);
 #define MS_FLAG_SEEDS       1     /* guards MS_ARR_SEEDS */
 MS_API int ms_ctx_ipc_export(ms_ctx* ctx, int32_t which, uint8_t* handle64);
 MS_API int ms_ctx_peer_open(ms_ctx* ctx, int32_t slot, int32_t which, const uint8_t* handle64);
+/* peers living in THIS process (several contexts driven by one host thread or several threads): register the
+ * owner's device pointers directly (ms_ctx_device_ptr / ms_ctx_flag_words_ptr) instead of IPC handles */
+MS_API int ms_ctx_peer_set_pointer(ms_ctx* ctx, int32_t slot, int32_t which, void* device_ptr);
+MS_API void* ms_ctx_flag_words_ptr(ms_ctx* ctx);
 /* owner slot and owner-local row of every ghost row [n_owned, nv), in ghost order */
 MS_API int ms_ctx_set_ghost_sources(ms_ctx* ctx, int32_t n_slots, const int32_t* owner_slot, const int32_t* owner_row);
 MS_API int ms_ctx_halo_signal(ms_ctx* ctx, int32_t flag_index);

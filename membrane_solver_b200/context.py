@@ -345,6 +345,21 @@ class DeviceMesh:
         buf = (ctypes.c_uint8 * L.IPC_HANDLE_BYTES).from_buffer_copy(handle)
         L.check(self._lib.ms_ctx_peer_open(self._h, int(slot), int(which), buf))
 
+    def peer_set_pointer(self, slot: int, which: int, device_ptr: int) -> None:
+        L.check(self._lib.ms_ctx_peer_set_pointer(self._h, int(slot), int(which), ctypes.c_void_p(int(device_ptr))))
+
+    def flag_words_ptr(self) -> int:
+        p = self._lib.ms_ctx_flag_words_ptr(self._h)
+        if not p:
+            raise L.B200Error("flag words are not available")
+        return int(p)
+
+    def device_ptr(self, which: int) -> int:
+        p = self._lib.ms_ctx_device_ptr(self._h, int(which))
+        if not p:
+            raise L.B200Error(f"array {which} is not available")
+        return int(p)
+
     def set_ghost_sources(self, n_slots: int, owner_slot: np.ndarray, owner_row: np.ndarray) -> None:
         o = np.ascontiguousarray(owner_slot, dtype=np.int32)
         r = np.ascontiguousarray(owner_row, dtype=np.int32)

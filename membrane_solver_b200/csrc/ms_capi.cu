@@ -1163,6 +1163,8 @@ int ms_ctx_ipc_export(ms_ctx* c, int32_t which, uint8_t* handle64) {
   return 0;
 }
 
+static int peer_register(ms_ctx* c, int32_t slot, int32_t which, void* p);
+
 int ms_ctx_peer_open(ms_ctx* c, int32_t slot, int32_t which, const uint8_t* handle64) {
   if (int rc = check_ctx(c, true)) return rc;
   if (!handle64 || slot < 0 || slot >= 4096) return fail(-1, "bad peer arguments");
@@ -1170,8 +1172,12 @@ int ms_ctx_peer_open(ms_ctx* c, int32_t slot, int32_t which, const uint8_t* hand
   std::memcpy(&h, handle64, sizeof(h));
   void* p = nullptr;
   CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  c->peers.opened.push_back(p);
+  return peer_register(c, slot, which, p);
+}
+
+static int peer_register(ms_ctx* c, int32_t slot, int32_t which, void* p) {
   ms_ctx::PeerTable& t = c->peers;
-  t.opened.push_back(p);
   const size_t need = size_t(slot) + 1;
   if (t.pos.size() < need) {
     t.pos.resize(need, nullptr);
@@ -1188,6 +1194,18 @@ int ms_ctx_peer_open(ms_ctx* c, int32_t slot, int32_t which, const uint8_t* hand
   }
   t.tables_current = false;
   return 0;
+}
+
+int ms_ctx_peer_set_pointer(ms_ctx* c, int32_t slot, int32_t which, void* device_ptr) {
+  if (int rc = check_ctx(c, true)) return rc;
+  if (!device_ptr || slot < 0 || slot >= 4096) return fail(-1, "bad peer arguments");
+  return peer_register(c, slot, which, device_ptr);
+}
+
+void* ms_ctx_flag_words_ptr(ms_ctx* c) {
+  if (!c || !c->have_topology || use_device(c)) return nullptr;
+  if (ensure_flag_words(c)) return nullptr;
+  return c->d_flag_words.p;
 }
 
 int ms_ctx_set_ghost_sources(ms_ctx* c, int32_t n_slots, const int32_t* owner_slot, const int32_t* owner_row) {

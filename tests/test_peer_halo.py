@@ -1,0 +1,99 @@
+"""The peer-memory transport of the multi-GPU path on ONE GPU: three partitions of a mesh as
+three contexts of this process, each on its own stream, wired to each other with device pointers
+(``ms_ctx_peer_set_pointer``) instead of CUDA IPC handles.  The kernels are the ones the multi-process path runs:
+epoch flags, wait + pull of the ghost rows, rank-order all-reduce of the scalars."""
+
+import numpy as np
+import pytest
+
+from ms_test_helpers import rel_err
+
+
+@pytest.mark.gpu
+def test_three_partitions_exchange_over_peer_pointers():
+    import torch
+
+    from membrane_solver_b200 import _lib as L
+    from membrane_solver_b200.context import DeviceMesh
+    from membrane_solver_b200.partition import split_mesh
+    from membrane_solver_b200.synthetic import icosphere
+
+    pos, tri = icosphere(40)
+    rng = np.random.default_rng(9)
+    pos = pos * (1.0 + 0.02 * rng.standard_normal((pos.shape[0], 1)))
+    nv, nf = pos.shape[0], tri.shape[0]
+    mods = L.MOD_SURFACE | L.MOD_BENDING | L.MOD_VOLUME
+
+    whole = DeviceMesh(0)
+    whole.set_topology(nv, tri, body_mask=np.ones(nf, np.uint8))
+    whole.set_surface_tension(1.0)
+    whole.set_bending_params(1.2, 0.05)
+    whole.set_positions(pos)
+    want = whole.eval(whole.options(mods, constraint_mode=0))
+    want_g = whole.download(L.ARR_GRAD)
+    want_e = whole.eval(whole.options(mods, want_grad=False))
+    whole.close()
+
+    world = 3
+    lib = L.lib()
+    parts = [split_mesh(nv, tri, world, r) for r in range(world)]
+    dms, streams = [], []
+    for loc in parts:
+        dm = DeviceMesh(0)
+        dm.set_topology(loc.nv_local, loc.tri, n_owned=loc.n_owned, body_mask=np.ones(loc.tri.shape[0], np.uint8))
+        dm.set_surface_tension(1.0)
+        dm.set_bending_params(1.2, 0.05)
+        start = pos[loc.global_rows()].copy()
+        start[loc.n_owned:] = 7.0                     # ghost rows must come through the halo
+        dm.set_positions(start)
+        stream = torch.cuda.Stream()
+        L.check(lib.ms_ctx_set_stream(dm._h, stream.cuda_stream))
+        dms.append(dm)
+        streams.append(stream)
+    torch.cuda.synchronize()
+    for r, (loc, dm) in enumerate(zip(parts, dms)):
+        owners = np.searchsorted(loc.cuts, loc.ghost_ids, side="right") - 1
+        rows = loc.ghost_ids - loc.cuts[owners]
+        for o in np.unique(owners):
+            for which in (L.ARR_POSITIONS, L.ARR_TRIAL, L.ARR_SEEDS):
+                dm.peer_set_pointer(int(o), which, dms[int(o)].device_ptr(which))
+        for o in range(world):
+            if o != r:
+                dm.peer_set_pointer(o, L.IPC_FLAGS, dms[o].flag_words_ptr())
+        dm.set_rank_slot(r, world)
+        dm.set_ghost_sources(world, owners.astype(np.int32), rows.astype(np.int32))
+
+    def evaluate(opts):
+        # every context issues the same sequence; the waits resolve on the device across the three streams
+        for dm in dms:
+            dm.halo_signal(L.FLAG_POSITIONS)
+            dm.halo_pull(L.ARR_POSITIONS, L.FLAG_POSITIONS)
+            dm.eval_pass_a(opts)
+            if opts.want_grad:
+                dm.halo_signal(L.FLAG_SEEDS)
+                dm.halo_pull(L.ARR_SEEDS, L.FLAG_SEEDS)
+            dm.eval_pass_b(opts)
+            dm.eval_reduce(opts)
+            dm.allreduce_scalars(12)
+            dm.eval_project(opts)
+        out = [dm.read_scalars() for dm in dms]
+        assert not any(dm.halo_error() for dm in dms)
+        return out
+
+    opts = dms[0].options(mods, constraint_mode=0)
+    for step in range(3):                              # repeated: epochs advance, slots alternate
+        res = evaluate(opts)
+        for r in res:
+            assert r.scalars.tobytes() == res[0].scalars.tobytes()       # rank-order sum: bitwise the same everywhere
+        for name in ("e_surface", "e_bending", "volume", "area", "kkt_lambda"):
+            a, b = getattr(res[0], name), getattr(want, name)
+            assert abs(a - b) <= 1e-12 * max(1.0, abs(b)), (name, a, b)
+        grad = np.concatenate([dm.download(L.ARR_GRAD)[: loc.n_owned] for dm, loc in zip(dms, parts)])
+        assert rel_err(grad, want_g) <= 2e-12
+        for dm, loc in zip(dms, parts):
+            assert np.array_equal(dm.download(L.ARR_POSITIONS), pos[loc.global_rows()])
+    res = evaluate(dms[0].options(mods, want_grad=False))      # energy-only: positions halo + all-reduce alone
+    assert abs(res[0].e_bending - want_e.e_bending) <= 1e-12 * abs(want_e.e_bending)
+    for dm in dms:
+        L.check(lib.ms_ctx_set_stream(dm._h, None))
+        dm.close()
