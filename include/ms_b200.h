@@ -261,6 +261,9 @@ MS_API int ms_ctx_peer_set_pointer(ms_ctx* ctx, int32_t slot, int32_t which, voi
 MS_API void* ms_ctx_flag_words_ptr(ms_ctx* ctx);
 /* owner slot and owner-local row of every ghost row [n_owned, nv), in ghost order */
 MS_API int ms_ctx_set_ghost_sources(ms_ctx* ctx, int32_t n_slots, const int32_t* owner_slot, const int32_t* owner_row);
+/* upload the pointer tables now (allocations and NULL-stream copies serialise streams of one process: keep them
+ * out of the exchange sequence when several contexts of one process wait for each other) */
+MS_API int ms_ctx_halo_prepare(ms_ctx* ctx);
 MS_API int ms_ctx_halo_signal(ms_ctx* ctx, int32_t flag_index);
 MS_API int ms_ctx_halo_pull(ms_ctx* ctx, int32_t which, int32_t flag_index);
 /* this rank's slot among n_slots ranks (its own flag block takes part in the all-reduce) */

@@ -149,6 +149,7 @@ SIGNATURES = {
     "ms_ctx_peer_set_pointer": (ctypes.c_int, [_V, _i32, _i32, _V]),
     "ms_ctx_flag_words_ptr": (_V, [_V]),
     "ms_ctx_set_ghost_sources": (ctypes.c_int, [_V, _i32, _I, _I]),
+    "ms_ctx_halo_prepare": (ctypes.c_int, [_V]),
     "ms_ctx_halo_signal": (ctypes.c_int, [_V, _i32]),
     "ms_ctx_halo_pull": (ctypes.c_int, [_V, _i32, _i32]),
     "ms_ctx_set_rank_slot": (ctypes.c_int, [_V, _i32, _i32]),

@@ -367,6 +367,9 @@ class DeviceMesh:
             raise ValueError("one owner slot and one owner row per ghost row")
         L.check(self._lib.ms_ctx_set_ghost_sources(self._h, int(n_slots), L.iptr(o), L.iptr(r)))
 
+    def halo_prepare(self) -> None:
+        L.check(self._lib.ms_ctx_halo_prepare(self._h))
+
     def halo_signal(self, flag: int) -> None:
         L.check(self._lib.ms_ctx_halo_signal(self._h, int(flag)))
 

@@ -1247,6 +1247,15 @@ static int peer_tables(ms_ctx* c) {
   return 0;
 }
 
+int ms_ctx_halo_prepare(ms_ctx* c) {
+  if (int rc = check_ctx(c, true)) return rc;
+  if (int rc = ensure_flag_words(c)) return rc;
+  if (int rc = peer_tables(c)) return rc;
+  CU(ms::launch_halo_warmup(c->d_flag_words.p, c->d_scalars.p, c->d_halo_error.p, c->stream));
+  CU(cudaDeviceSynchronize());
+  return 0;
+}
+
 int ms_ctx_halo_signal(ms_ctx* c, int32_t flag_index) {
   if (int rc = check_ctx(c, true)) return rc;
   if (flag_index < 0 || flag_index >= 4) return fail(-1, "bad flag index");

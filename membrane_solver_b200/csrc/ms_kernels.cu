@@ -1465,6 +1465,16 @@ cudaError_t launch_allreduce_peer(double* scalars, int n, unsigned long long* ow
   return cudaGetLastError();
 }
 
+// First launches load the kernels' code (lazy module loading), which may synchronise the device: do them once,
+// with no work, before contexts start waiting for each other.
+cudaError_t launch_halo_warmup(unsigned long long* words, double* scalars, int* error, cudaStream_t st) {
+  k_halo_signal<<<1, 1, 0, st>>>(words + 3, 0ull);
+  k_halo_pull<<<1, 256, 0, st>>>(0, 3, nullptr, nullptr, 0, 0, 0ull, nullptr, nullptr, nullptr, error);
+  k_allreduce_publish<<<1, 32, 0, st>>>(scalars, 0, words, 0ull);
+  k_allreduce_gather<<<1, 64, 0, st>>>(nullptr, 0, 0, 0ull, scalars, error);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_min_edge2(const int32_t* tri, int32_t nf, int32_t nv, const double* pos,
                              unsigned long long* out, cudaStream_t st) {
   if (nf > 0) k_min_edge2<<<blocks_for(nf, 256), 256, 0, st>>>(tri, nf, nv, pos, out);

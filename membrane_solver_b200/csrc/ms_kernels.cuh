@@ -177,6 +177,7 @@ cudaError_t launch_halo_pull(int n_ghost, int width, const double* const* peer_b
                              const int32_t* row, double* dst, int* error, cudaStream_t st);
 cudaError_t launch_allreduce_peer(double* scalars, int n, unsigned long long* own_words, unsigned long long* const* peer_words,
                                   int n_slots, unsigned long long epoch, int* error, cudaStream_t st);
+cudaError_t launch_halo_warmup(unsigned long long* words, double* scalars, int* error, cudaStream_t st);
 constexpr int kFlagWords = 64;  // exported block: 4 epoch flags, 2 x 16 scalar slots (see k_allreduce_publish)
 
 // --- leaflet tilt relaxation helpers ---

@@ -227,6 +227,7 @@ class PartitionedMesh:
                         dm.peer_open(r, L.IPC_FLAGS, table[r][3])
                 dm.set_rank_slot(local.rank, local.world)
                 dm.set_ghost_sources(local.world, owners.astype(np.int32), rows.astype(np.int32))
+                dm.halo_prepare()
             except L.B200Error as exc:
                 ok, err = 0, str(exc)
         else:

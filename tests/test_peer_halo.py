@@ -62,6 +62,9 @@ def test_three_partitions_exchange_over_peer_pointers():
                 dm.peer_set_pointer(o, L.IPC_FLAGS, dms[o].flag_words_ptr())
         dm.set_rank_slot(r, world)
         dm.set_ghost_sources(world, owners.astype(np.int32), rows.astype(np.int32))
+    for dm in dms:
+        dm.halo_prepare()      # allocations / NULL-stream copies would serialise the three streams of this process
+    torch.cuda.synchronize()
 
     def evaluate(opts):
         # every context issues the same sequence; the waits resolve on the device across the three streams
