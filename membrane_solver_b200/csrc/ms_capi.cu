@@ -637,8 +637,8 @@ int ms_ctx_set_topology_partition(ms_ctx* c, int32_t nv, int32_t n_owned, int32_
   if (int rc = c->d_volgrad.ensure(n3)) return rc;
   if (int rc = c->d_seeds.ensure(size_t(ms::kSeedStride) * size_t(nv))) return rc;
   {  // one row of running sums per persistent CTA, pass and sub-launch (the pipelined host evaluation
-     // issues up to 2 x 9 sub-launches of <= 148 CTAs)
-    const size_t rows = 4096;
+     // issues up to 32 sub-launches of <= 148 CTAs per pass)
+    const size_t rows = 5120;  // >= 148 CTAs x (32 + 1) sub-launches
     if (int rc = c->d_partials_a.ensure(rows * ms::kPartialStride)) return rc;
     if (int rc = c->d_partials_b.ensure(rows * ms::kPartialStride)) return rc;
     CU(cudaMemset(c->d_partials_a.p, 0, rows * ms::kPartialStride * sizeof(double)));
@@ -1384,7 +1384,16 @@ static int pipe_prepare(ms_ctx* c) {
   return 0;
 }
 
-constexpr int kPipeChunks = 8;
+constexpr int kPipeChunksMax = 32;
+
+static int pipe_chunks() {
+  static const int n = [] {
+    const char* e = std::getenv("MS_PIPE_CHUNKS");
+    const int v = e ? std::atoi(e) : 8;
+    return v < 2 ? 2 : (v > kPipeChunksMax ? kPipeChunksMax : v);
+  }();
+  return n;
+}
 
 static bool pipe_applicable(const ms_ctx* c, const ms_eval_opts* o, const double* pos_host) {
   static const bool disabled = std::getenv("MS_NO_PIPELINE") != nullptr;
@@ -1404,6 +1413,7 @@ static int eval_pipelined(ms_ctx* c, const ms_eval_opts* o, const double* pos_ho
   const bool ran_a = needs_bending(o) || !o->want_grad;
   c->ran_pass_a = ran_a;
   double* dst = o->use_trial ? c->d_trial.p : c->d_pos.p;
+  const int kPipeChunks = pipe_chunks();
   while (c->pipe_events.size() < size_t(kPipeChunks) + 1) {
     cudaEvent_t e = nullptr;
     CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1413,7 +1423,7 @@ static int eval_pipelined(ms_ctx* c, const ms_eval_opts* o, const double* pos_ho
   CU(cudaEventRecord(c->pipe_events[size_t(kPipeChunks)], c->stream));
   CU(cudaStreamWaitEvent(c->copy_stream, c->pipe_events[size_t(kPipeChunks)], 0));
   const int64_t nv = c->nv;
-  int64_t row_hi[kPipeChunks];
+  int64_t row_hi[kPipeChunksMax];
   for (int k = 0; k < kPipeChunks; ++k) {
     const int64_t r0 = nv * k / kPipeChunks, r1 = nv * (k + 1) / kPipeChunks;
     row_hi[k] = r1;
