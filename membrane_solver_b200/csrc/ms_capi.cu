@@ -126,7 +126,10 @@ struct ms_ctx {
     int32_t consistent_u = 0;
   } leaflet[2];
   DevBuf<double> d_lf_corner, d_lf_vbuf, d_lf_shape, d_lf_tilt, d_lf_facet_e, d_lf_e;
-  DevBuf<double> d_vnormals, d_rowsq, d_norm_out;
+  DevBuf<double> d_vnormals, d_rowsq, d_norm_out, d_lf_block_e;
+  DevBuf<unsigned long long> d_lf_ticket;
+  unsigned long long lf_ticket_base = 0;
+  bool lf_fused_ok = true;
   // halo exchange over peer memory: opened peer arrays, flag words, ghost source table
   struct PeerTable {
     std::vector<void*> opened;                       // every pointer returned by cudaIpcOpenMemHandle
@@ -1009,6 +1012,30 @@ int ms_ctx_eval_leaflet(ms_ctx* c, int32_t leaflet, uint32_t modules, int32_t wa
   if (int rc = c->d_lf_e.ensure(2 + 2 * ms::kSumBlocks)) return rc;
   ms::LeafletMesh m;
   fill_leaflet_mesh(c, L, use_trial != 0, m);
+  static const bool fused_off = std::getenv("MS_LEAFLET_NO_FUSE") != nullptr;
+  if (!fused_off && c->lf_fused_ok && c->nf <= ms::kLfFusedMaxItems && c->nv <= ms::kLfFusedMaxItems && c->nf > 0) {
+    // a mesh this small is launch-latency bound: all phases in one cooperative launch
+    if (!c->d_lf_ticket.p) {
+      if (int rc = c->d_lf_ticket.ensure(1)) return rc;
+      CU(cudaMemset(c->d_lf_ticket.p, 0, sizeof(unsigned long long)));
+      c->lf_ticket_base = 0;
+      if (int rc = c->d_lf_block_e.ensure(2 * ms::kLfFusedMaxBlocks)) return rc;
+    }
+    cudaError_t e = ms::launch_leaflet_fused(
+        m, (modules & MS_MOD_BENDING_TILT) != 0, (modules & MS_MOD_TILT) != 0, c->d_lf_corner.p, c->d_lf_vbuf.p,
+        c->d_lf_shape.p, c->d_lf_tilt.p, c->d_lf_block_e.p, ms::kLfFusedMaxBlocks, c->d_lf_e.p,
+        want_grad ? c->d_grad.p : nullptr, (accumulate & MS_ACC_GRAD) != 0, want_tilt_grad ? L.tilt_grad.p : nullptr,
+        (accumulate & MS_ACC_TILT_GRAD) != 0, c->d_lf_ticket.p, &c->lf_ticket_base, c->stream);
+    if (e == cudaSuccess) {
+      if (energies2) {
+        CU(cudaMemcpyAsync(energies2, c->d_lf_e.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+      }
+      return 0;
+    }
+    cudaGetLastError();       // not launchable cooperatively here: the sweeps as separate launches from now on
+    c->lf_fused_ok = false;
+  }
   CU(ms::launch_leaflet(m, (modules & MS_MOD_BENDING_TILT) != 0, (modules & MS_MOD_TILT) != 0, c->d_lf_corner.p,
                         c->d_lf_vbuf.p, c->d_lf_shape.p, c->d_lf_tilt.p, c->d_lf_facet_e.p, c->d_lf_e.p,
                         want_grad ? c->d_grad.p : nullptr, (accumulate & MS_ACC_GRAD) != 0,

@@ -861,6 +861,76 @@ __global__ void __launch_bounds__(128) k_lf_facet_b(LeafletMesh m, const double*
   facet_e[size_t(m.nf) + f] = e.e_tilt;
 }
 
+// ---- small meshes: the whole leaflet evaluation in ONE cooperative launch ----
+// The three sweeps, the energy sums and the gathers of a mesh of a few thousand facets take a few microseconds
+// each; as separate launches they cost ~50 us of launch latency and pipeline drain.  Here they are phases of one
+// grid (all CTAs resident: cudaLaunchCooperativeKernel) separated by a grid barrier on a 64-bit ticket counter
+// that only ever grows (no reset between launches: barrier k of this launch waits for base + k * gridDim.x).
+__device__ __forceinline__ void lf_grid_barrier(unsigned long long* ticket, unsigned long long target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ticket, 1ull);
+    while (*reinterpret_cast<volatile unsigned long long*>(ticket) < target) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(128) k_lf_fused(LeafletMesh m, int with_bt, int with_tilt, double* corner,
+                                                  double* vbuf, double* corner_shape, double* corner_tilt,
+                                                  double* block_e /* 2 * gridDim.x */, double* e_out2, double* grad,
+                                                  int accumulate_grad, double* tilt_grad, int accumulate_tilt_grad,
+                                                  unsigned long long* ticket, unsigned long long base) {
+  __shared__ double red[32 * 2];
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  unsigned long long target = base;
+  if (with_bt) {
+    for (int f = tid; f < m.nf; f += stride) lf_facet_a(m, f, corner);
+    lf_grid_barrier(ticket, target += gridDim.x);
+    for (int v = tid; v < m.nv; v += stride) lf_vertex(m, v, corner, vbuf);
+    lf_grid_barrier(ticket, target += gridDim.x);
+  }
+  double e[2] = {0.0, 0.0};
+  for (int f = tid; f < m.nf; f += stride) {
+    const LfEnergies r = lf_facet_b(m, f, vbuf, with_bt != 0, with_tilt != 0, grad ? corner_shape : nullptr,
+                                    tilt_grad ? corner_tilt : nullptr);
+    e[0] += r.e_bt;
+    e[1] += r.e_tilt;
+  }
+  block_sum<2>(e, red, 128, 0);
+  if (threadIdx.x == 0) {
+    block_e[2 * blockIdx.x] = e[0];
+    block_e[2 * blockIdx.x + 1] = e[1];
+  }
+  lf_grid_barrier(ticket, target += gridDim.x);
+  if (blockIdx.x == 0 && threadIdx.x < 2) {  // fixed order: block 0, 1, 2, ...
+    double acc = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) acc += block_e[2 * b + threadIdx.x];
+    e_out2[threadIdx.x] = acc;
+  }
+  for (int v = tid; v < m.nv; v += stride) {
+    for (int which = 0; which < 2; ++which) {
+      double* out = which == 0 ? grad : tilt_grad;
+      if (!out) continue;
+      const double* src = which == 0 ? corner_shape : corner_tilt;
+      const bool acc = which == 0 ? accumulate_grad != 0 : accumulate_tilt_grad != 0;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+      for (int j = m.csr_ptr[v]; j < m.csr_ptr[v + 1]; ++j) {
+        const double* q = src + 3 * size_t(m.csr_idx[j]);
+        a0 += q[0];
+        a1 += q[1];
+        a2 += q[2];
+      }
+      double* o = out + 3 * size_t(v);
+      o[0] = acc ? o[0] + a0 : a0;
+      o[1] = acc ? o[1] + a1 : a1;
+      o[2] = acc ? o[2] + a2 : a2;
+    }
+  }
+}
+
 // ---- leaflet tilt relaxation helpers (runtime/steppers/tilt_relaxation.py:630-668,894-955) ----
 // unit area-weighted vertex normals (Mesh.vertex_normals, geometry/triangle_ops.py:55-72): fixed-order gather
 __global__ void __launch_bounds__(128) k_vertex_normals(int32_t nv, const int32_t* __restrict__ tri,
@@ -1398,6 +1468,37 @@ cudaError_t launch_leaflet(const LeafletMesh& m, bool with_bt, bool with_tilt, d
     k_gather<<<blocks_for(m.nv, 128), 128, 0, st>>>(m.nv, m.csr_ptr, m.csr_idx, corner_tilt, 3, 0, 3, tilt_grad, 3,
                                                      accumulate_tilt_grad ? 1 : 0);
   return cudaGetLastError();
+}
+
+// Cooperative single-launch variant for small meshes.  Returns cudaErrorNotSupported when the device cannot launch
+// cooperatively or the grid would not be resident; the caller then uses launch_leaflet.  *ticket_base is the
+// host-side mirror of the ticket counter (advanced by the barriers this launch performs).
+cudaError_t launch_leaflet_fused(const LeafletMesh& m, bool with_bt, bool with_tilt, double* corner, double* vbuf,
+                                 double* corner_shape, double* corner_tilt, double* block_e, int max_blocks,
+                                 double* e_out2, double* grad, bool accumulate_grad, double* tilt_grad,
+                                 bool accumulate_tilt_grad, unsigned long long* ticket, unsigned long long* ticket_base,
+                                 cudaStream_t st) {
+  static int resident = -1;
+  if (resident < 0) {
+    int dev = 0, coop = 0, per_sm = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lf_fused, 128, 0);
+    resident = coop ? per_sm * sms : 0;
+  }
+  int blocks = blocks_for(m.nf > m.nv ? m.nf : m.nv, 128);
+  if (blocks > max_blocks) blocks = max_blocks;
+  if (blocks > resident) blocks = resident;
+  if (blocks <= 0) return cudaErrorNotSupported;
+  LeafletMesh mm = m;
+  int bt = with_bt ? 1 : 0, tl = with_tilt ? 1 : 0, ag = accumulate_grad ? 1 : 0, at = accumulate_tilt_grad ? 1 : 0;
+  unsigned long long base = *ticket_base;
+  void* args[] = {&mm, &bt, &tl, &corner, &vbuf, &corner_shape, &corner_tilt, &block_e, &e_out2, &grad, &ag,
+                  &tilt_grad, &at, &ticket, &base};
+  cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_lf_fused), dim3(blocks), dim3(128), args, 0, st);
+  if (e == cudaSuccess) *ticket_base = base + (unsigned long long)(blocks) * (with_bt ? 3ull : 1ull);
+  return e;
 }
 
 cudaError_t launch_vertex_normals(int32_t nv, const int32_t* tri, const int32_t* csr_ptr, const int32_t* csr_idx,

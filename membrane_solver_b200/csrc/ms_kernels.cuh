@@ -170,6 +170,16 @@ cudaError_t launch_leaflet(const LeafletMesh& m, bool with_bt, bool with_tilt, d
                            double* corner_shape, double* corner_tilt, double* facet_e, double* e_out2, double* grad,
                            bool accumulate_grad, double* tilt_grad, bool accumulate_tilt_grad, cudaStream_t st);
 
+// small meshes: the same evaluation as ONE cooperative launch (block_e: 2 * max_blocks doubles; ticket: one zeroed
+// 64-bit word that is never reset; *ticket_base mirrors it on the host)
+cudaError_t launch_leaflet_fused(const LeafletMesh& m, bool with_bt, bool with_tilt, double* corner, double* vbuf,
+                                 double* corner_shape, double* corner_tilt, double* block_e, int max_blocks,
+                                 double* e_out2, double* grad, bool accumulate_grad, double* tilt_grad,
+                                 bool accumulate_tilt_grad, unsigned long long* ticket, unsigned long long* ticket_base,
+                                 cudaStream_t st);
+constexpr int kLfFusedMaxBlocks = 512;
+constexpr int kLfFusedMaxItems = 1 << 16;  // facets / vertices up to which the single-launch variant is used
+
 // --- halo exchange over NVLink peer memory (flag wait + peer loads in one kernel) ---
 cudaError_t launch_halo_signal(unsigned long long* flag, unsigned long long epoch, cudaStream_t st);
 cudaError_t launch_halo_pull(int n_ghost, int width, const double* const* peer_base, unsigned long long* const* peer_flag,

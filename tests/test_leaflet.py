@@ -459,3 +459,41 @@ def test_tilt_relaxer_on_device(relax_gold, case):
     from membrane_solver_b200.context import DeviceMesh
 
     _device_relaxation(relax_gold, case, DeviceMesh)
+
+
+@pytest.mark.gpu
+def test_device_leaflet_on_a_mesh_above_the_single_launch_threshold():
+    """Meshes up to 65 536 facets are evaluated in one cooperative launch, larger ones by separate sweeps with
+    two-stage energy sums: the larger path against the oracle (72 000 facets, random leaflet selections)."""
+    from membrane_solver_b200 import _lib as L
+    from membrane_solver_b200.context import DeviceMesh
+    from membrane_solver_b200.synthetic import icosphere
+    from oracle import ref_leaflet as rl
+
+    pos, tri = icosphere(60)
+    nv, nf = pos.shape[0], tri.shape[0]
+    assert nf > 65536
+    rng = np.random.default_rng(21)
+    pos = pos * (1.0 + 0.02 * rng.standard_normal((nv, 1)))
+    tilts = 0.1 * rng.standard_normal((nv, 3))
+    keep = rng.random(nf) > 0.1
+    interior = rng.random(nv) > 0.05
+    base_zero = rng.random(nv) < 0.03
+    kappa = 1.0 + 0.2 * rng.random(nv)
+    c0 = 0.05 * rng.standard_normal(nv)
+    dm = DeviceMesh(0)
+    dm.set_topology(nv, tri)
+    dm.set_positions(pos)
+    dm.set_leaflet(L.LEAFLET_OUT, div_sign=1.0, kappa=kappa, c0=c0, k_tilt=3.0, facet_keep=keep.astype(np.uint8),
+                   interior=interior.astype(np.uint8), base_zero=base_zero.astype(np.uint8), consistent=True)
+    dm.upload(L.ARR_TILTS_OUT, tilts)
+    g, tg = np.zeros_like(pos), np.zeros_like(pos)
+    e_bt = rl.leaflet_bending_tilt_energy_and_gradient(pos, tri, tilts, kappa, c0, sign=1.0, keep=keep, interior=interior,
+                                                       base_zero=base_zero, is_boundary=None, grad=g, tilt_grad=tg)
+    e_t = rl.leaflet_tilt_energy_and_gradient(pos, tri, tilts, 3.0, keep=keep, consistent=True, grad=g, tilt_grad=tg)
+    got_bt, got_t = dm.eval_leaflet(L.LEAFLET_OUT, L.MOD_TILT | L.MOD_BENDING_TILT)
+    _close(got_bt, e_bt)
+    _close(got_t, e_t)
+    assert rel_err(dm.download(L.ARR_GRAD), g) <= 2e-12
+    assert rel_err(dm.download(L.ARR_TILT_GRAD_OUT), tg) <= TOL
+    dm.close()
