@@ -31,6 +31,7 @@ extern "C" {
 #define MS_MOD_BENDING       (1u << 2) /* modules/energy/bending.py:90-181 */
 #define MS_MOD_TILT          (1u << 3) /* modules/energy/tilt.py:99-172 */
 #define MS_MOD_BENDING_TILT  (1u << 4) /* modules/energy/bending_tilt.py:151-482 (single field; not with MS_MOD_BENDING) */
+#define MS_MOD_TILT_SMOOTHNESS (1u << 5) /* modules/energy/tilt_smoothness*.py (leaflet evaluation only: ms_ctx_eval_leaflet) */
 
 #define MS_FLAG_WILLMORE     (1u << 0) /* bending_energy_model = willmore (bending_params.py:18-21) */
 #define MS_FLAG_APPROX       (1u << 1) /* bending_gradient_mode = approx (bending_params.py:24-31) */
@@ -196,6 +197,7 @@ typedef struct ms_leaflet_desc {
   double kappa_default;     /* bending_modulus_in / _out */
   double c0_default;        /* spontaneous_curvature_in / _out */
   double k_tilt;            /* tilt_modulus_in / _out */
+  double k_smooth;          /* tilt smoothness rigidity: bending_modulus_in / _out (tilt_smoothness_utils.py:77-84) */
   double div_sign;          /* -1 inner leaflet, +1 outer (bending_tilt_in.py:46, bending_tilt_out.py:46) */
   int32_t consistent_default;
   int32_t reserved;
@@ -207,14 +209,16 @@ typedef struct ms_leaflet_desc {
 #define MS_ACC_TILT_GRAD 2u  /* add to MS_ARR_TILT_GRAD_IN / _OUT instead of overwriting */
 
 MS_API int ms_ctx_set_leaflet(ms_ctx* ctx, int32_t leaflet, const ms_leaflet_desc* desc);
-/* Evaluate the leaflet's modules (MS_MOD_TILT and / or MS_MOD_BENDING_TILT) at MS_ARR_POSITIONS (or
+/* Evaluate the leaflet's modules (any of MS_MOD_TILT, MS_MOD_BENDING_TILT, MS_MOD_TILT_SMOOTHNESS) at MS_ARR_POSITIONS (or
  * MS_ARR_TRIAL) with the tilt field MS_ARR_TILTS_IN / _OUT.  want_grad: shape gradient into MS_ARR_GRAD;
  * want_tilt_grad: tilt gradient into MS_ARR_TILT_GRAD_IN / _OUT (want_grad == 0 is the tilt-only
- * evaluation of the inner relaxation loop, evaluation_manager.py:693-698).  energies2, when not NULL,
- * receives {E_bending_tilt, E_tilt} (synchronises the stream). */
+ * evaluation of the inner relaxation loop, evaluation_manager.py:693-698).  MS_MOD_TILT_SMOOTHNESS
+ * (modules/energy/tilt_smoothness_leaflet.py:17-79, cotangent Dirichlet energy of the tilt field) has a tilt
+ * gradient only.  energies3, when not NULL,
+ * receives {E_bending_tilt, E_tilt, E_tilt_smoothness} (synchronises the stream). */
 MS_API int ms_ctx_eval_leaflet(ms_ctx* ctx, int32_t leaflet, uint32_t modules, int32_t want_grad,
                                int32_t want_tilt_grad, uint32_t accumulate, int32_t use_trial,
-                               double* energies2);
+                               double* energies3);
 
 /* --- leaflet tilt relaxation at frozen geometry (runtime/steppers/tilt_relaxation.py:426-1057, gradient-descent
  * solver; the host keeps the loop control, only scalars cross PCIe) ---

@@ -18,6 +18,7 @@ LIB_PATH = os.environ.get("MS_B200_LIB") or os.path.join(_PKG, "libms_b200.so") 
 CSRC = os.path.join(_PKG, "csrc")
 
 MOD_SURFACE, MOD_VOLUME, MOD_BENDING, MOD_TILT, MOD_BENDING_TILT = 1, 2, 4, 8, 16
+MOD_TILT_SMOOTHNESS = 32
 FLAG_WILLMORE, FLAG_APPROX = 1, 2
 PATCHES_ALL, PATCHES_INTERIOR, PATCHES_BOUNDARY = -1, -2, -3
 
@@ -70,6 +71,7 @@ class LeafletDesc(ctypes.Structure):
         ("kappa_default", ctypes.c_double),
         ("c0_default", ctypes.c_double),
         ("k_tilt", ctypes.c_double),
+        ("k_smooth", ctypes.c_double),
         ("div_sign", ctypes.c_double),
         ("consistent_default", ctypes.c_int32),
         ("reserved", ctypes.c_int32),

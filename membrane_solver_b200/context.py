@@ -180,7 +180,7 @@ class DeviceMesh:
         L.check(self._lib.ms_ctx_set_tilt_rigidity(self._h, float(k_tilt)))
 
     # -- leaflet tilt modules (tilt_in/out, bending_tilt_in/out) ------------
-    def set_leaflet(self, leaflet: int, *, div_sign: float, kappa=0.0, c0=0.0, k_tilt: float = 0.0,
+    def set_leaflet(self, leaflet: int, *, div_sign: float, kappa=0.0, c0=0.0, k_tilt: float = 0.0, k_smooth: float = 0.0,
                     facet_keep=None, interior=None, base_zero=None, tilt_row_weight=None,
                     facet_consistent=None, consistent: bool = False) -> None:
         """Selections and parameters of one leaflet (``struct ms_leaflet_desc``).  ``kappa`` / ``c0``:
@@ -209,7 +209,7 @@ class DeviceMesh:
             facet_consistent=mask(facet_consistent, self.nf),
             kappa_default=float(kappa) if np.ndim(kappa) == 0 else 0.0,
             c0_default=float(c0) if np.ndim(c0) == 0 else 0.0,
-            k_tilt=float(k_tilt), div_sign=float(div_sign), consistent_default=int(bool(consistent)), reserved=0)
+            k_tilt=float(k_tilt), k_smooth=float(k_smooth), div_sign=float(div_sign), consistent_default=int(bool(consistent)), reserved=0)
         L.check(self._lib.ms_ctx_set_leaflet(self._h, int(leaflet), ctypes.byref(d)))
 
     # -- leaflet tilt relaxation primitives (tilt_relaxation.py:426-1057, GD solver) --
@@ -252,14 +252,14 @@ class DeviceMesh:
         L.check(self._lib.ms_ctx_leaflet_swap_trial(self._h, int(leaflet)))
 
     def eval_leaflet(self, leaflet: int, modules: int, *, want_grad: bool = True, want_tilt_grad: bool = True,
-                     accumulate: int = 0, use_trial: bool = False) -> tuple[float, float]:
-        """(E_bending_tilt, E_tilt) of the leaflet's modules; gradients stay on the device
+                     accumulate: int = 0, use_trial: bool = False) -> tuple[float, float, float]:
+        """(E_bending_tilt, E_tilt, E_tilt_smoothness) of the leaflet's modules; gradients stay on the device
         (``ARR_GRAD``, ``ARR_TILT_GRAD_IN`` / ``_OUT``)."""
-        e = np.zeros(2)
+        e = np.zeros(3)
         L.check(self._lib.ms_ctx_eval_leaflet(self._h, int(leaflet), int(modules), int(bool(want_grad)),
                                               int(bool(want_tilt_grad)), int(accumulate), int(bool(use_trial)),
                                               L.dptr(e)))
-        return float(e[0]), float(e[1])
+        return float(e[0]), float(e[1]), float(e[2])
 
     # -- state --------------------------------------------------------------
     def upload(self, which: int, host: np.ndarray) -> None:

@@ -122,7 +122,7 @@ struct ms_ctx {
     bool has_minv = false;
     DevBuf<uint8_t> fixed;
     bool has_fixed = false;
-    double kappa_u = 0.0, c0_u = 0.0, k_tilt = 0.0, sign = 1.0;
+    double kappa_u = 0.0, c0_u = 0.0, k_tilt = 0.0, k_smooth = 0.0, sign = 1.0;
     int32_t consistent_u = 0;
   } leaflet[2];
   DevBuf<double> d_lf_corner, d_lf_vbuf, d_lf_shape, d_lf_tilt, d_lf_facet_e, d_lf_e;
@@ -957,6 +957,7 @@ int ms_ctx_set_leaflet(ms_ctx* c, int32_t leaflet, const ms_leaflet_desc* d) {
   L.kappa_u = d->kappa_default;
   L.c0_u = d->c0_default;
   L.k_tilt = d->k_tilt;
+  L.k_smooth = d->k_smooth;
   L.sign = d->div_sign;
   L.consistent_u = d->consistent_default;
   L.set = true;
@@ -981,19 +982,20 @@ static void fill_leaflet_mesh(ms_ctx* c, ms_ctx::Leaflet& L, bool use_trial, ms:
   m.consistent = L.has_consistent ? L.consistent.p : nullptr;
   m.consistent_u = L.consistent_u;
   m.k_tilt = L.k_tilt;
+  m.k_smooth = L.k_smooth;
   m.sign = L.sign;
   m.csr_ptr = c->d_csr_ptr.p;
   m.csr_idx = c->d_csr_idx.p;
 }
 
 int ms_ctx_eval_leaflet(ms_ctx* c, int32_t leaflet, uint32_t modules, int32_t want_grad, int32_t want_tilt_grad,
-                        uint32_t accumulate, int32_t use_trial, double* energies2) {
+                        uint32_t accumulate, int32_t use_trial, double* energies3) {
   if (int rc = check_ctx(c, true)) return rc;
   if (leaflet < 0 || leaflet > 1) return fail(-1, "bad leaflet index");
   ms_ctx::Leaflet& L = c->leaflet[leaflet];
   if (!L.set) return fail(-4, "ms_ctx_set_leaflet has not been called for this leaflet (or the topology changed)");
-  if (modules & ~uint32_t(MS_MOD_TILT | MS_MOD_BENDING_TILT))
-    return fail(-1, "leaflet modules are MS_MOD_TILT and MS_MOD_BENDING_TILT");
+  if (modules & ~uint32_t(MS_MOD_TILT | MS_MOD_BENDING_TILT | MS_MOD_TILT_SMOOTHNESS))
+    return fail(-1, "leaflet modules are MS_MOD_TILT, MS_MOD_BENDING_TILT and MS_MOD_TILT_SMOOTHNESS");
   const int which_t = leaflet == 0 ? MS_ARR_TILTS_IN : MS_ARR_TILTS_OUT;
   const int which_g = leaflet == 0 ? MS_ARR_TILT_GRAD_IN : MS_ARR_TILT_GRAD_OUT;
   if (!L.tilts.p && c->nv > 0) return fail(-4, "the leaflet's tilt field has not been uploaded (MS_ARR_TILTS_IN / _OUT)");
@@ -1008,8 +1010,8 @@ int ms_ctx_eval_leaflet(ms_ctx* c, int32_t leaflet, uint32_t modules, int32_t wa
   if (int rc = c->d_lf_vbuf.ensure(ms::kLfVertex * nv + 1)) return rc;
   if (int rc = c->d_lf_shape.ensure(9 * nf + 1)) return rc;
   if (int rc = c->d_lf_tilt.ensure(9 * nf + 1)) return rc;
-  if (int rc = c->d_lf_facet_e.ensure(2 * nf + 1)) return rc;
-  if (int rc = c->d_lf_e.ensure(2 + 2 * ms::kSumBlocks)) return rc;
+  if (int rc = c->d_lf_facet_e.ensure(3 * nf + 1)) return rc;
+  if (int rc = c->d_lf_e.ensure(3 + 3 * ms::kSumBlocks)) return rc;
   ms::LeafletMesh m;
   fill_leaflet_mesh(c, L, use_trial != 0, m);
   static const bool fused_off = std::getenv("MS_LEAFLET_NO_FUSE") != nullptr;
@@ -1019,16 +1021,16 @@ int ms_ctx_eval_leaflet(ms_ctx* c, int32_t leaflet, uint32_t modules, int32_t wa
       if (int rc = c->d_lf_ticket.ensure(1)) return rc;
       CU(cudaMemset(c->d_lf_ticket.p, 0, sizeof(unsigned long long)));
       c->lf_ticket_base = 0;
-      if (int rc = c->d_lf_block_e.ensure(2 * ms::kLfFusedMaxBlocks)) return rc;
+      if (int rc = c->d_lf_block_e.ensure(3 * ms::kLfFusedMaxBlocks)) return rc;
     }
     cudaError_t e = ms::launch_leaflet_fused(
-        m, (modules & MS_MOD_BENDING_TILT) != 0, (modules & MS_MOD_TILT) != 0, c->d_lf_corner.p, c->d_lf_vbuf.p,
-        c->d_lf_shape.p, c->d_lf_tilt.p, c->d_lf_block_e.p, ms::kLfFusedMaxBlocks, c->d_lf_e.p,
+        m, (modules & MS_MOD_BENDING_TILT) != 0, (modules & MS_MOD_TILT) != 0, (modules & MS_MOD_TILT_SMOOTHNESS) != 0,
+        c->d_lf_corner.p, c->d_lf_vbuf.p, c->d_lf_shape.p, c->d_lf_tilt.p, c->d_lf_block_e.p, ms::kLfFusedMaxBlocks, c->d_lf_e.p,
         want_grad ? c->d_grad.p : nullptr, (accumulate & MS_ACC_GRAD) != 0, want_tilt_grad ? L.tilt_grad.p : nullptr,
         (accumulate & MS_ACC_TILT_GRAD) != 0, c->d_lf_ticket.p, &c->lf_ticket_base, c->stream);
     if (e == cudaSuccess) {
-      if (energies2) {
-        CU(cudaMemcpyAsync(energies2, c->d_lf_e.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      if (energies3) {
+        CU(cudaMemcpyAsync(energies3, c->d_lf_e.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
       }
       return 0;
@@ -1036,12 +1038,13 @@ int ms_ctx_eval_leaflet(ms_ctx* c, int32_t leaflet, uint32_t modules, int32_t wa
     cudaGetLastError();       // not launchable cooperatively here: the sweeps as separate launches from now on
     c->lf_fused_ok = false;
   }
-  CU(ms::launch_leaflet(m, (modules & MS_MOD_BENDING_TILT) != 0, (modules & MS_MOD_TILT) != 0, c->d_lf_corner.p,
+  CU(ms::launch_leaflet(m, (modules & MS_MOD_BENDING_TILT) != 0, (modules & MS_MOD_TILT) != 0,
+                        (modules & MS_MOD_TILT_SMOOTHNESS) != 0, c->d_lf_corner.p,
                         c->d_lf_vbuf.p, c->d_lf_shape.p, c->d_lf_tilt.p, c->d_lf_facet_e.p, c->d_lf_e.p,
                         want_grad ? c->d_grad.p : nullptr, (accumulate & MS_ACC_GRAD) != 0,
                         want_tilt_grad ? L.tilt_grad.p : nullptr, (accumulate & MS_ACC_TILT_GRAD) != 0, c->stream));
-  if (energies2) {
-    CU(cudaMemcpyAsync(energies2, c->d_lf_e.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (energies3) {
+    CU(cudaMemcpyAsync(energies3, c->d_lf_e.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
   }
   return 0;

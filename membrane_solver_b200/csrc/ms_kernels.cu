@@ -852,13 +852,15 @@ __global__ void __launch_bounds__(128) k_lf_vertex(LeafletMesh m, const double* 
 }
 
 __global__ void __launch_bounds__(128) k_lf_facet_b(LeafletMesh m, const double* __restrict__ vbuf, int with_bt,
-                                                    int with_tilt, double* corner_shape, double* corner_tilt,
-                                                    double* facet_e /* [e_bt (nf) | e_tilt (nf)] */) {
+                                                    int with_tilt, int with_smooth, double* corner_shape,
+                                                    double* corner_tilt,
+                                                    double* facet_e /* [e_bt (nf) | e_tilt (nf) | e_smooth (nf)] */) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= m.nf) return;
-  const LfEnergies e = lf_facet_b(m, f, vbuf, with_bt != 0, with_tilt != 0, corner_shape, corner_tilt);
+  const LfEnergies e = lf_facet_b(m, f, vbuf, with_bt != 0, with_tilt != 0, with_smooth != 0, corner_shape, corner_tilt);
   facet_e[f] = e.e_bt;
   facet_e[size_t(m.nf) + f] = e.e_tilt;
+  facet_e[2 * size_t(m.nf) + f] = e.e_smooth;
 }
 
 // ---- small meshes: the whole leaflet evaluation in ONE cooperative launch ----
@@ -878,12 +880,12 @@ __device__ __forceinline__ void lf_grid_barrier(unsigned long long* ticket, unsi
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(128) k_lf_fused(LeafletMesh m, int with_bt, int with_tilt, double* corner,
+__global__ void __launch_bounds__(128) k_lf_fused(LeafletMesh m, int with_bt, int with_tilt, int with_smooth, double* corner,
                                                   double* vbuf, double* corner_shape, double* corner_tilt,
-                                                  double* block_e /* 2 * gridDim.x */, double* e_out2, double* grad,
+                                                  double* block_e /* 3 * gridDim.x */, double* e_out3, double* grad,
                                                   int accumulate_grad, double* tilt_grad, int accumulate_tilt_grad,
                                                   unsigned long long* ticket, unsigned long long base) {
-  __shared__ double red[32 * 2];
+  __shared__ double red[32 * 3];
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
   unsigned long long target = base;
   if (with_bt) {
@@ -892,23 +894,25 @@ __global__ void __launch_bounds__(128) k_lf_fused(LeafletMesh m, int with_bt, in
     for (int v = tid; v < m.nv; v += stride) lf_vertex(m, v, corner, vbuf);
     lf_grid_barrier(ticket, target += gridDim.x);
   }
-  double e[2] = {0.0, 0.0};
+  double e[3] = {0.0, 0.0, 0.0};
   for (int f = tid; f < m.nf; f += stride) {
-    const LfEnergies r = lf_facet_b(m, f, vbuf, with_bt != 0, with_tilt != 0, grad ? corner_shape : nullptr,
-                                    tilt_grad ? corner_tilt : nullptr);
+    const LfEnergies r = lf_facet_b(m, f, vbuf, with_bt != 0, with_tilt != 0, with_smooth != 0,
+                                    grad ? corner_shape : nullptr, tilt_grad ? corner_tilt : nullptr);
     e[0] += r.e_bt;
     e[1] += r.e_tilt;
+    e[2] += r.e_smooth;
   }
-  block_sum<2>(e, red, 128, 0);
+  block_sum<3>(e, red, 128, 0);
   if (threadIdx.x == 0) {
-    block_e[2 * blockIdx.x] = e[0];
-    block_e[2 * blockIdx.x + 1] = e[1];
+    block_e[3 * blockIdx.x] = e[0];
+    block_e[3 * blockIdx.x + 1] = e[1];
+    block_e[3 * blockIdx.x + 2] = e[2];
   }
   lf_grid_barrier(ticket, target += gridDim.x);
-  if (blockIdx.x == 0 && threadIdx.x < 2) {  // fixed order: block 0, 1, 2, ...
+  if (blockIdx.x == 0 && threadIdx.x < 3) {  // fixed order: block 0, 1, 2, ...
     double acc = 0.0;
-    for (unsigned b = 0; b < gridDim.x; ++b) acc += block_e[2 * b + threadIdx.x];
-    e_out2[threadIdx.x] = acc;
+    for (unsigned b = 0; b < gridDim.x; ++b) acc += block_e[3 * b + threadIdx.x];
+    e_out3[threadIdx.x] = acc;
   }
   for (int v = tid; v < m.nv; v += stride) {
     for (int which = 0; which < 2; ++which) {
@@ -1448,19 +1452,20 @@ cudaError_t launch_bt_finalize(const double* e_bt, double* scalars, cudaStream_t
   return cudaGetLastError();
 }
 
-cudaError_t launch_leaflet(const LeafletMesh& m, bool with_bt, bool with_tilt, double* corner, double* vbuf,
-                           double* corner_shape, double* corner_tilt, double* facet_e, double* e_out2, double* grad,
+cudaError_t launch_leaflet(const LeafletMesh& m, bool with_bt, bool with_tilt, bool with_smooth, double* corner,
+                           double* vbuf, double* corner_shape, double* corner_tilt, double* facet_e, double* e_out3,
+                           double* grad,
                            bool accumulate_grad, double* tilt_grad, bool accumulate_tilt_grad, cudaStream_t st) {
   if (with_bt) {
     if (m.nf > 0) k_lf_facet_a<<<blocks_for(m.nf, 128), 128, 0, st>>>(m, corner);
     if (m.nv > 0) k_lf_vertex<<<blocks_for(m.nv, 128), 128, 0, st>>>(m, corner, vbuf);
   }
   if (m.nf > 0)
-    k_lf_facet_b<<<blocks_for(m.nf, 128), 128, 0, st>>>(m, vbuf, with_bt ? 1 : 0, with_tilt ? 1 : 0,
+    k_lf_facet_b<<<blocks_for(m.nf, 128), 128, 0, st>>>(m, vbuf, with_bt ? 1 : 0, with_tilt ? 1 : 0, with_smooth ? 1 : 0,
                                                         grad ? corner_shape : nullptr, tilt_grad ? corner_tilt : nullptr,
                                                         facet_e);
-  sum_fixed_order(facet_e, m.nf, 1.0, e_out2, e_out2 + 2, st);
-  sum_fixed_order(facet_e + size_t(m.nf), m.nf, 1.0, e_out2 + 1, e_out2 + 2 + kSumBlocks, st);
+  for (int k = 0; k < 3; ++k)
+    sum_fixed_order(facet_e + k * size_t(m.nf), m.nf, 1.0, e_out3 + k, e_out3 + 3 + k * kSumBlocks, st);
   if (m.nv > 0 && grad)
     k_gather<<<blocks_for(m.nv, 128), 128, 0, st>>>(m.nv, m.csr_ptr, m.csr_idx, corner_shape, 3, 0, 3, grad, 3,
                                                      accumulate_grad ? 1 : 0);
@@ -1473,9 +1478,9 @@ cudaError_t launch_leaflet(const LeafletMesh& m, bool with_bt, bool with_tilt, d
 // Cooperative single-launch variant for small meshes.  Returns cudaErrorNotSupported when the device cannot launch
 // cooperatively or the grid would not be resident; the caller then uses launch_leaflet.  *ticket_base is the
 // host-side mirror of the ticket counter (advanced by the barriers this launch performs).
-cudaError_t launch_leaflet_fused(const LeafletMesh& m, bool with_bt, bool with_tilt, double* corner, double* vbuf,
-                                 double* corner_shape, double* corner_tilt, double* block_e, int max_blocks,
-                                 double* e_out2, double* grad, bool accumulate_grad, double* tilt_grad,
+cudaError_t launch_leaflet_fused(const LeafletMesh& m, bool with_bt, bool with_tilt, bool with_smooth, double* corner,
+                                 double* vbuf, double* corner_shape, double* corner_tilt, double* block_e, int max_blocks,
+                                 double* e_out3, double* grad, bool accumulate_grad, double* tilt_grad,
                                  bool accumulate_tilt_grad, unsigned long long* ticket, unsigned long long* ticket_base,
                                  cudaStream_t st) {
   static int resident = -1;
@@ -1492,9 +1497,10 @@ cudaError_t launch_leaflet_fused(const LeafletMesh& m, bool with_bt, bool with_t
   if (blocks > resident) blocks = resident;
   if (blocks <= 0) return cudaErrorNotSupported;
   LeafletMesh mm = m;
-  int bt = with_bt ? 1 : 0, tl = with_tilt ? 1 : 0, ag = accumulate_grad ? 1 : 0, at = accumulate_tilt_grad ? 1 : 0;
+  int bt = with_bt ? 1 : 0, tl = with_tilt ? 1 : 0, sm = with_smooth ? 1 : 0, ag = accumulate_grad ? 1 : 0,
+      at = accumulate_tilt_grad ? 1 : 0;
   unsigned long long base = *ticket_base;
-  void* args[] = {&mm, &bt, &tl, &corner, &vbuf, &corner_shape, &corner_tilt, &block_e, &e_out2, &grad, &ag,
+  void* args[] = {&mm, &bt, &tl, &sm, &corner, &vbuf, &corner_shape, &corner_tilt, &block_e, &e_out3, &grad, &ag,
                   &tilt_grad, &at, &ticket, &base};
   cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_lf_fused), dim3(blocks), dim3(128), args, 0, st);
   if (e == cudaSuccess) *ticket_base = base + (unsigned long long)(blocks) * (with_bt ? 3ull : 1ull);

@@ -165,16 +165,17 @@ cudaError_t launch_bt_tilt_gather(const BtMesh& m, const double* corner3, double
 cudaError_t launch_bt_finalize(const double* e_bt, double* scalars, cudaStream_t st);
 
 // --- leaflet tilt modules (ms_leaflet.cuh).  corner: 27*nf doubles, vbuf: 5*nv, corner_shape / corner_tilt:
-// 9*nf each, facet_e: 2*nf, e_out2: {E_bending_tilt, E_tilt} followed by 2*kSumBlocks doubles of scratch.  grad / tilt_grad may be null. ---
-cudaError_t launch_leaflet(const LeafletMesh& m, bool with_bt, bool with_tilt, double* corner, double* vbuf,
-                           double* corner_shape, double* corner_tilt, double* facet_e, double* e_out2, double* grad,
+// 9*nf each, facet_e: 3*nf, e_out3: {E_bending_tilt, E_tilt, E_tilt_smoothness} followed by 3*kSumBlocks doubles of scratch.  grad / tilt_grad may be null. ---
+cudaError_t launch_leaflet(const LeafletMesh& m, bool with_bt, bool with_tilt, bool with_smooth, double* corner,
+                           double* vbuf, double* corner_shape, double* corner_tilt, double* facet_e, double* e_out3,
+                           double* grad,
                            bool accumulate_grad, double* tilt_grad, bool accumulate_tilt_grad, cudaStream_t st);
 
-// small meshes: the same evaluation as ONE cooperative launch (block_e: 2 * max_blocks doubles; ticket: one zeroed
+// small meshes: the same evaluation as ONE cooperative launch (block_e: 3 * max_blocks doubles; ticket: one zeroed
 // 64-bit word that is never reset; *ticket_base mirrors it on the host)
-cudaError_t launch_leaflet_fused(const LeafletMesh& m, bool with_bt, bool with_tilt, double* corner, double* vbuf,
-                                 double* corner_shape, double* corner_tilt, double* block_e, int max_blocks,
-                                 double* e_out2, double* grad, bool accumulate_grad, double* tilt_grad,
+cudaError_t launch_leaflet_fused(const LeafletMesh& m, bool with_bt, bool with_tilt, bool with_smooth, double* corner,
+                                 double* vbuf, double* corner_shape, double* corner_tilt, double* block_e, int max_blocks,
+                                 double* e_out3, double* grad, bool accumulate_grad, double* tilt_grad,
                                  bool accumulate_tilt_grad, unsigned long long* ticket, unsigned long long* ticket_base,
                                  cudaStream_t st);
 constexpr int kLfFusedMaxBlocks = 512;

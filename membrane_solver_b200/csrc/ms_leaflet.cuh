@@ -3,10 +3,12 @@
 // (Kozlov-Hamm splay coupling per leaflet).
 //
 //   E_tilt = sum_{kept f} q_f T_f,   q_f = k/6 sum|t_k|^2 (lumped) | k/12 (sum|t_k|^2 + t0.t1 + t1.t2 + t2.t0)
+//   E_smooth = k_s/4 sum_{kept f} (c0 |t1-t2|^2 + c1 |t2-t0|^2 + c2 |t0-t1|^2)   (tilt gradient only)
 //   E_bt   = 1/2 sum_{kept f} sum_k kappa_k (base_k + s div_f)^2 va_eff,k
 //            base_v = 2 (K_v . n_v) / (2 A_vor,v) - c0_v   on interior rows, else 0   (s = -1 in, +1 out)
 //
-// Reference: modules/energy/tilt_leaflet.py:26-169; modules/energy/bending_tilt_leaflet.py:231-758 with
+// Reference: modules/energy/tilt_leaflet.py:26-169; modules/energy/tilt_smoothness_leaflet.py:17-79 with
+// tilt_smoothness.py:81-187 (cotangent Dirichlet energy, ambient_v1); modules/energy/bending_tilt_leaflet.py:231-758 with
 // bt_payload.py:40-298 (curvature on the COMPLETE mesh, energy on the leaflet's facets),
 // bt_gradient.py:89-389 (operator terms over all facets, area terms over kept facets with PER-CORNER
 // dE/dA_eff), bt_gradient.py:20-64 (d div/dx for ambient tilts), bt_divergence.py:49-93.
@@ -34,6 +36,7 @@ struct LeafletMesh {
   const uint8_t* consistent;   // nf or nullptr -> consistent_u: mass mode per facet
   int32_t consistent_u;
   double k_tilt;
+  double k_smooth;             // tilt smoothness rigidity (bending_modulus_in / _out)
   double sign;                 // s
   const int32_t* csr_ptr;      // vertex -> corners (corner id = 3 f + k), facet-major order
   const int32_t* csr_idx;
@@ -128,14 +131,14 @@ MS_HD void lf_div_shape_gradient(const FacetGeom& g, d3 t0, d3 t1, d3 t2, double
 }
 
 struct LfEnergies {
-  double e_bt, e_tilt;
+  double e_bt, e_tilt, e_smooth;
 };
 
 // Sweep 3 (per facet): energies; corner payloads of the shape gradient (9 doubles per facet, may be null)
 // and of the tilt gradient (9 per facet, may be null).  with_bt / with_tilt select the modules.
 MS_HD LfEnergies lf_facet_b(const LeafletMesh& m, int f, const double* vbuf, bool with_bt, bool with_tilt,
-                            double* corner_shape, double* corner_tilt) {
-  LfEnergies r = {0.0, 0.0};
+                            bool with_smooth, double* corner_shape, double* corner_tilt) {
+  LfEnergies r = {0.0, 0.0, 0.0};
   double* os = corner_shape ? corner_shape + 9 * size_t(f) : nullptr;
   double* ot = corner_tilt ? corner_tilt + 9 * size_t(f) : nullptr;
   if (os) for (int k = 0; k < 9; ++k) os[k] = 0.0;
@@ -172,6 +175,17 @@ MS_HD LfEnergies lf_facet_b(const LeafletMesh& m, int f, const double* vbuf, boo
       tg[2] = (w[2] * fa) * s2;
     }
     r.e_tilt = q_tilt * area;
+  }
+
+  // tilt smoothness (tilt_smoothness.py:103-187): cotangent Dirichlet energy of the ambient field; no shape gradient
+  if (with_smooth && kept && m.k_smooth != 0.0) {
+    const CornerA c = facet_pass_a(g, false, false, false);
+    const d3 d12 = t[1] - t[2], d20 = t[2] - t[0], d01 = t[0] - t[1];
+    r.e_smooth = 0.25 * m.k_smooth * (c.c0 * dot(d12, d12) + c.c1 * dot(d20, d20) + c.c2 * dot(d01, d01));
+    const double hk = 0.5 * m.k_smooth;
+    tg[0] = tg[0] + hk * (c.c2 * d01 - c.c1 * d20);
+    tg[1] = tg[1] + hk * (c.c0 * d12 - c.c2 * d01);
+    tg[2] = tg[2] + hk * (c.c1 * d20 - c.c0 * d12);
   }
 
   CornerG cg;

@@ -32,6 +32,7 @@ SIGN = {"in": -1.0, "out": 1.0}        # bending_tilt_in.py:46, bending_tilt_out
 WHICH = {"in": L.LEAFLET_IN, "out": L.LEAFLET_OUT}
 ARR_TILTS = {"in": L.ARR_TILTS_IN, "out": L.ARR_TILTS_OUT}
 ARR_TILT_GRAD = {"in": L.ARR_TILT_GRAD_IN, "out": L.ARR_TILT_GRAD_OUT}
+ENERGY_SLOT = {L.MOD_BENDING_TILT: 0, L.MOD_TILT: 1, L.MOD_TILT_SMOOTHNESS: 2}   # ms_ctx_eval_leaflet energies3
 
 
 def _txt(global_params, key, default=""):
@@ -106,6 +107,10 @@ def _selection_from_reference(mesh, global_params, param_resolver, leaflet: str)
     out = dict(keep_bt=keep, keep_tilt=keep_tilt, interior=interior, base_zero=base_zero,
                kappa=np.asarray(kappa, float), c0=np.asarray(c0, float))
     if param_resolver is not None:
+        k_s = param_resolver.get(None, f"bending_modulus_{leaflet}")        # tilt_smoothness_utils.py:77-84
+        if k_s is None:
+            k_s = param_resolver.get(None, "bending_modulus")
+        out["k_smooth"] = float(k_s or 0.0)
         out["k_tilt"] = float(tpar._resolve_tilt_modulus(param_resolver, leaflet))
         mode = tpar._resolve_tilt_mass_mode(param_resolver, leaflet)
         out["consistent"] = mode == "consistent"
@@ -140,9 +145,13 @@ def _leaflet_tilts(mesh, leaflet: str, tilts) -> np.ndarray:
 def configure(state, mesh, global_params, param_resolver, leaflet: str, module_bit: int) -> dict | None:
     """Bring the device's description of the leaflet up to date; None = the module contributes nothing."""
     refuse_unsupported(global_params, leaflet, bending_tilt=bool(module_bit & L.MOD_BENDING_TILT))
+    if (module_bit & L.MOD_TILT_SMOOTHNESS) and _txt(global_params, "tilt_transport_model", "ambient_v1") != "ambient_v1":
+        raise L.B200Error("tilt_transport_model=connection_v1 is not available on the B200 path")
     spec = selection(mesh, global_params, param_resolver, leaflet)
     if (module_bit & L.MOD_TILT) and float(spec.get("k_tilt", 0.0)) == 0.0:
         return None                                   # tilt_leaflet.py:41-43
+    if (module_bit & L.MOD_TILT_SMOOTHNESS) and float(spec.get("k_smooth", 0.0)) == 0.0:
+        return None                                   # tilt_smoothness_leaflet.py:33-35
     state.set_leaflet(leaflet, module_bit, spec, SIGN[leaflet])
     return spec
 
@@ -164,13 +173,13 @@ def evaluate(mesh, global_params, param_resolver, *, leaflet: str, module_bit: i
     t = _leaflet_tilts(mesh, leaflet, tilts)
     st.dm.set_positions(pos)
     st.dm.upload(ARR_TILTS[leaflet], t)
-    e_bt, e_tilt = st.dm.eval_leaflet(WHICH[leaflet], module_bit, want_grad=grad_arr is not None,
-                                      want_tilt_grad=tilt_grad_arr is not None)
-    if grad_arr is not None:
+    energies = st.dm.eval_leaflet(WHICH[leaflet], module_bit, want_grad=grad_arr is not None and module_bit != L.MOD_TILT_SMOOTHNESS,
+                                  want_tilt_grad=tilt_grad_arr is not None)
+    if grad_arr is not None and module_bit != L.MOD_TILT_SMOOTHNESS:     # the smoothness term has no shape gradient
         C.accumulate(grad_arr, st.dm.download(L.ARR_GRAD))
     if tilt_grad_arr is not None:
         C.accumulate(tilt_grad_arr, st.dm.download(ARR_TILT_GRAD[leaflet]))
-    return float(e_bt if module_bit == L.MOD_BENDING_TILT else e_tilt)
+    return float(energies[ENERGY_SLOT[module_bit]])
 
 
 def make_module(leaflet: str, module_bit: int):

@@ -153,7 +153,7 @@ class DeviceState:
         The coupling module may drop more facets than the tilt-magnitude module (transition triangles,
         ``bt_payload.py:131-144``): the mask of the module about to run is the one held by the device."""
         keep = spec.get("keep_bt") if (module_bits & L.MOD_BENDING_TILT) else spec.get("keep_tilt")
-        if (module_bits & L.MOD_BENDING_TILT) and (module_bits & L.MOD_TILT):
+        if (module_bits & L.MOD_BENDING_TILT) and (module_bits & (L.MOD_TILT | L.MOD_TILT_SMOOTHNESS)):
             a, b = spec.get("keep_bt"), spec.get("keep_tilt")
             if (a is None) != (b is None) or (a is not None and not np.array_equal(a, b)):
                 raise L.B200Error("the leaflet's two modules use different facet selections: evaluate them separately")
@@ -162,7 +162,8 @@ class DeviceState:
                           ("kappa", spec.get("kappa", 0.0)), ("c0", spec.get("c0", 0.0)),
                           ("row_weight", spec.get("row_weight")), ("facet_consistent", spec.get("facet_consistent"))):
             parts.append((name, None if val is None else (np.shape(val), hash(np.asarray(val).tobytes()))))
-        key = (tuple(parts), float(spec.get("k_tilt", 0.0)), bool(spec.get("consistent", False)), float(div_sign))
+        key = (tuple(parts), float(spec.get("k_tilt", 0.0)), float(spec.get("k_smooth", 0.0)),
+               bool(spec.get("consistent", False)), float(div_sign))
         if self._leaflet_key.get(leaflet) == key:
             return
 
@@ -179,7 +180,7 @@ class DeviceState:
         bz = mask(spec.get("base_zero"))
         self.dm.set_leaflet(L.LEAFLET_IN if leaflet == "in" else L.LEAFLET_OUT, div_sign=div_sign,
                             kappa=uniform(spec.get("kappa", 0.0)), c0=uniform(spec.get("c0", 0.0)),
-                            k_tilt=float(spec.get("k_tilt", 0.0)),
+                            k_tilt=float(spec.get("k_tilt", 0.0)), k_smooth=float(spec.get("k_smooth", 0.0)),
                             facet_keep=None if keep is None or np.all(keep) else mask(keep),
                             interior=mask(spec.get("interior")), base_zero=None if bz is None or not bz.any() else bz,
                             tilt_row_weight=spec.get("row_weight"), facet_consistent=mask(spec.get("facet_consistent")),

@@ -36,9 +36,8 @@ class DeviceTiltRelaxer:
     def _energy(self, want_tilt_grad: bool) -> float:
         total = 0.0
         for name in self.leaflets:
-            e_bt, e_tilt = self.dm.eval_leaflet(_WHICH[name], self.modules, want_grad=False,
-                                                want_tilt_grad=want_tilt_grad)
-            total += e_bt + e_tilt
+            total += sum(self.dm.eval_leaflet(_WHICH[name], self.modules, want_grad=False,
+                                              want_tilt_grad=want_tilt_grad))
         return total
 
     def relax(self, *, max_iters: int, step_size: float, tol: float = 0.0, solver: str = "gd",

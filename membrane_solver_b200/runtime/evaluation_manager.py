@@ -237,11 +237,11 @@ class EvaluationManager:
                     continue
                 if len(batch) > 1:
                     st.set_leaflet(leaflet, bits, spec, LF.SIGN[leaflet])
-                e_bt, e_tilt = st.dm.eval_leaflet(LF.WHICH[leaflet], bits, want_grad=False, want_tilt_grad=out is not None)
+                got = st.dm.eval_leaflet(LF.WHICH[leaflet], bits, want_grad=False, want_tilt_grad=out is not None)
                 scale = batch[0][2] if len(batch) == 1 else 1.0
                 for name, bit, sc in batch:
                     if bit & bits:
-                        energies[name] = sc * (e_bt if bit == L.MOD_BENDING_TILT else e_tilt)
+                        energies[name] = sc * got[LF.ENERGY_SLOT[bit]]
                 if out is not None:
                     out += scale * st.dm.download(LF.ARR_TILT_GRAD[leaflet])
         return energies

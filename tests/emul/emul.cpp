@@ -203,28 +203,30 @@ int emul_eval(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* is_boun
 }
 
 // Leaflet modules (ms_leaflet.cuh): the three sweeps and the gathers in the device path's order.
-// grad / tilt_grad (may be null) are ACCUMULATED into.  energies2 = {E_bending_tilt, E_tilt}.
+// grad / tilt_grad (may be null) are ACCUMULATED into.  energies3 = {E_bending_tilt, E_tilt, E_tilt_smoothness}.
 int emul_leaflet(int32_t nv, int32_t nf, const int32_t* tri, const double* pos, const double* tilts,
                  const uint8_t* keep, const uint8_t* is_boundary, const uint8_t* interior, const uint8_t* base_zero,
                  const double* kappa, const double* c0, double kappa_u, double c0_u, const double* row_weight,
-                 const uint8_t* consistent, int32_t consistent_u, double k_tilt, double sign, int32_t with_bt,
-                 int32_t with_tilt, double* grad, double* tilt_grad, double* energies2) {
+                 const uint8_t* consistent, int32_t consistent_u, double k_tilt, double k_smooth, double sign,
+                 int32_t with_bt, int32_t with_tilt, int32_t with_smooth, double* grad, double* tilt_grad,
+                 double* energies3) {
   std::vector<int32_t> csr_ptr, csr_idx;
   build_corner_csr(nv, nf, tri, csr_ptr, csr_idx);
   LeafletMesh m{nv, nf, tri, pos, tilts, keep, is_boundary, interior, base_zero, kappa, c0, kappa_u, c0_u,
-                row_weight, consistent, consistent_u, k_tilt, sign, csr_ptr.data(), csr_idx.data()};
+                row_weight, consistent, consistent_u, k_tilt, k_smooth, sign, csr_ptr.data(), csr_idx.data()};
   std::vector<double> corner(size_t(3 * kLfCornerA) * size_t(nf) + 1, 0.0), vbuf(size_t(kLfVertex) * size_t(nv) + 1, 0.0);
   std::vector<double> cs(9 * size_t(nf) + 1, 0.0), ct(9 * size_t(nf) + 1, 0.0);
   if (with_bt) {
     for (int f = 0; f < nf; ++f) lf_facet_a(m, f, corner.data());
     for (int v = 0; v < nv; ++v) lf_vertex(m, v, corner.data(), vbuf.data());
   }
-  double e_bt = 0.0, e_tilt = 0.0;
+  double e_bt = 0.0, e_tilt = 0.0, e_smooth = 0.0;
   for (int f = 0; f < nf; ++f) {
-    const LfEnergies e = lf_facet_b(m, f, vbuf.data(), with_bt != 0, with_tilt != 0, grad ? cs.data() : nullptr,
-                                    tilt_grad ? ct.data() : nullptr);
+    const LfEnergies e = lf_facet_b(m, f, vbuf.data(), with_bt != 0, with_tilt != 0, with_smooth != 0,
+                                    grad ? cs.data() : nullptr, tilt_grad ? ct.data() : nullptr);
     e_bt += e.e_bt;
     e_tilt += e.e_tilt;
+    e_smooth += e.e_smooth;
   }
   for (int v = 0; v < nv; ++v)
     for (int d = 0; d < 3; ++d) {
@@ -236,8 +238,9 @@ int emul_leaflet(int32_t nv, int32_t nf, const int32_t* tri, const double* pos, 
       if (grad) grad[3 * size_t(v) + d] += a;
       if (tilt_grad) tilt_grad[3 * size_t(v) + d] += b;
     }
-  energies2[0] = e_bt;
-  energies2[1] = e_tilt;
+  energies3[0] = e_bt;
+  energies3[1] = e_tilt;
+  energies3[2] = e_smooth;
   return 0;
 }
 

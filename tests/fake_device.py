@@ -185,14 +185,16 @@ class FakeDeviceMesh:
                               kappa_u=0.0 if np.ndim(k) else float(k), c0=c if np.ndim(c) else None,
                               c0_u=0.0 if np.ndim(c) else float(c), row_weight=d.get("tilt_row_weight"),
                               consistent=d.get("facet_consistent"), consistent_u=d.get("consistent", False),
-                              k_tilt=d.get("k_tilt", 0.0), with_bt=bool(modules & L.MOD_BENDING_TILT),
-                              with_tilt=bool(modules & L.MOD_TILT), want_grad=want_grad, want_tilt_grad=want_tilt_grad)
+                              k_tilt=d.get("k_tilt", 0.0), k_smooth=d.get("k_smooth", 0.0),
+                              with_bt=bool(modules & L.MOD_BENDING_TILT), with_tilt=bool(modules & L.MOD_TILT),
+                              with_smooth=bool(modules & L.MOD_TILT_SMOOTHNESS), want_grad=want_grad,
+                              want_tilt_grad=want_tilt_grad)
         self.evals += 1
         if want_grad:
             self.arrays[L.ARR_GRAD] = r["grad"] + (self.arrays[L.ARR_GRAD] if accumulate & L.ACC_GRAD else 0.0)
         if want_tilt_grad:
             self.arrays[arr_g] = r["tilt_grad"] + (self.arrays[arr_g] if accumulate & L.ACC_TILT_GRAD else 0.0)
-        return r["E_bt"], r["E_tilt"]
+        return r["E_bt"], r["E_tilt"], r["E_smooth"]
 
     # -- device-resident loop (numpy restatement of the small kernels; TEST ONLY) --
     def set_positions(self, pos):

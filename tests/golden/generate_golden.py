@@ -364,7 +364,9 @@ def leaflet_vectors():
     """BASELINE config 4: the four leaflet modules of the reference's caveolin free-disk mesh
     (bending_tilt_in/out, tilt_in/out) with the selections the reference derives from the mesh options
     stored as plain masks.  One ``leaflet.npz``; keys ``<state>_<leaflet>_<what>``."""
-    from modules.energy import bending_tilt_in, bending_tilt_out, tilt_in, tilt_out
+    from modules.energy import (bending_tilt_in, bending_tilt_out, tilt_in, tilt_out, tilt_smoothness_in,
+                                tilt_smoothness_out)
+    from modules.energy.tilt_smoothness_utils import _resolve_smoothness_rigidity
     from modules.energy.bt_params import (_assume_J0_center_xy, _assume_J0_presets, _assume_J0_radius_max,
                                           _per_vertex_params_leaflet)
     from modules.energy.bt_selection import (_base_term_region_zero_rows, _collect_preset_rows,
@@ -392,7 +394,8 @@ def leaflet_vectors():
         for vid in mesh.boundary_vertex_ids:
             isb[idx[vid]] = True
         out[f"{state}_pos"], out[f"{state}_tri"], out[f"{state}_is_boundary"] = pos, tri, isb
-        for leaf, sign, bt, tm in (("in", -1.0, bending_tilt_in, tilt_in), ("out", 1.0, bending_tilt_out, tilt_out)):
+        for leaf, sign, bt, tm, sm in (("in", -1.0, bending_tilt_in, tilt_in, tilt_smoothness_in),
+                                       ("out", 1.0, bending_tilt_out, tilt_out, tilt_smoothness_out)):
             pre = f"{state}_{leaf}_"
             am = leaflet_absent_vertex_mask(mesh, gp, leaflet=leaf)
             keep = leaflet_present_triangle_mask(mesh, tri, absent_vertex_mask=am)
@@ -413,7 +416,8 @@ def leaflet_vectors():
             out[pre + "sign"] = np.float64(sign)
             out[pre + "k_tilt"] = np.float64(_resolve_tilt_modulus(res, leaf))
             out[pre + "consistent"] = np.bool_(_resolve_tilt_mass_mode(res, leaf) == "consistent")
-            for tag, mod in (("bt", bt), ("tilt", tm)):
+            out[pre + "k_smooth"] = np.float64(_resolve_smoothness_rigidity(res, leaf))
+            for tag, mod in (("bt", bt), ("tilt", tm), ("smooth", sm)):
                 g, tgi, tgo = np.zeros_like(pos), np.zeros_like(pos), np.zeros_like(pos)
                 e = mod.compute_energy_and_gradient_array(mesh, gp, res, positions=pos, index_map=idx, grad_arr=g,
                                                           tilts_in=tilts["in"], tilts_out=tilts["out"],

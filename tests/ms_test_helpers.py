@@ -113,8 +113,8 @@ def emulate(pos, tri, *, modules, flags=0, want_grad=True, is_boundary=None, bod
 
 def emulate_leaflet(pos, tri, tilts, *, sign, keep=None, is_boundary=None, interior=None, base_zero=None,
                     kappa=None, c0=None, kappa_u=0.0, c0_u=0.0, row_weight=None, consistent=None,
-                    consistent_u=False, k_tilt=0.0, with_bt=True, with_tilt=False, want_grad=True,
-                    want_tilt_grad=True):
+                    consistent_u=False, k_tilt=0.0, k_smooth=0.0, with_bt=True, with_tilt=False, with_smooth=False,
+                    want_grad=True, want_tilt_grad=True):
     """Leaflet modules through the emulator (same ms_leaflet.cuh bodies as the device kernels)."""
     global _EMUL
     if _EMUL is None:
@@ -135,7 +135,7 @@ def emulate_leaflet(pos, tri, tilts, *, sign, keep=None, is_boundary=None, inter
 
     grad = np.zeros((nv, 3)) if want_grad else None
     tg = np.zeros((nv, 3)) if want_tilt_grad else None
-    e2 = np.zeros(2)
+    e2 = np.zeros(3)
     dp = ctypes.POINTER(ctypes.c_double)
     rc = _EMUL.emul_leaflet(
         ctypes.c_int32(nv), ctypes.c_int32(nf), tri.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
@@ -144,10 +144,10 @@ def emulate_leaflet(pos, tri, tilts, *, sign, keep=None, is_boundary=None, inter
         conv(base_zero, np.uint8, ctypes.c_uint8), conv(kappa, np.float64, ctypes.c_double),
         conv(c0, np.float64, ctypes.c_double), ctypes.c_double(kappa_u), ctypes.c_double(c0_u),
         conv(row_weight, np.float64, ctypes.c_double), conv(consistent, np.uint8, ctypes.c_uint8),
-        ctypes.c_int32(int(bool(consistent_u))), ctypes.c_double(k_tilt), ctypes.c_double(sign),
-        ctypes.c_int32(int(with_bt)), ctypes.c_int32(int(with_tilt)),
+        ctypes.c_int32(int(bool(consistent_u))), ctypes.c_double(k_tilt), ctypes.c_double(k_smooth), ctypes.c_double(sign),
+        ctypes.c_int32(int(with_bt)), ctypes.c_int32(int(with_tilt)), ctypes.c_int32(int(with_smooth)),
         None if grad is None else grad.ctypes.data_as(dp), None if tg is None else tg.ctypes.data_as(dp),
         e2.ctypes.data_as(dp))
     if rc:
         raise RuntimeError(f"emul_leaflet failed: {rc}")
-    return dict(E_bt=float(e2[0]), E_tilt=float(e2[1]), grad=grad, tilt_grad=tg)
+    return dict(E_bt=float(e2[0]), E_tilt=float(e2[1]), E_smooth=float(e2[2]), grad=grad, tilt_grad=tg)

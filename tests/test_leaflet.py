@@ -28,7 +28,7 @@ def _inputs(gold, state, leaf):
                 tilts=gold[pre + "tilts"], keep=gold[pre + "keep"], interior=gold[pre + "interior"],
                 base_zero=gold[pre + "base_zero"], kappa=gold[pre + "kappa"], c0=gold[pre + "c0"],
                 sign=float(gold[pre + "sign"]), k_tilt=float(gold[pre + "k_tilt"]),
-                consistent=bool(gold[pre + "consistent"]))
+                k_smooth=float(gold[pre + "k_smooth"]), consistent=bool(gold[pre + "consistent"]))
 
 
 def _close(a, b):
@@ -59,6 +59,12 @@ def test_oracle_matches_reference(gold, state, leaf):
                                             consistent=i["consistent"], grad=g, tilt_grad=tg)
     _close(e, float(gold[pre + "E_tilt"]))
     assert rel_err(g, gold[pre + "g_tilt"]) <= TOL and rel_err(tg, gold[pre + "tg_tilt"]) <= TOL
+    tg = np.zeros_like(i["pos"])
+    e = rl.leaflet_tilt_smoothness_energy_and_gradient(i["pos"], i["tri"], i["tilts"], i["k_smooth"], keep=i["keep"],
+                                                       tilt_grad=tg)
+    _close(e, float(gold[pre + "E_smooth"]))
+    assert rel_err(tg, gold[pre + "tg_smooth"]) <= TOL
+    assert not np.any(gold[pre + "g_smooth"])          # the reference's smoothness term has no shape gradient
 
 
 @pytest.mark.parametrize("leaf", LEAFLETS)
@@ -68,7 +74,10 @@ def test_emulated_device_code_matches_reference(gold, state, leaf):
     pre = f"{state}_{leaf}_"
     common = dict(sign=i["sign"], keep=i["keep"], is_boundary=i["is_boundary"], interior=i["interior"],
                   base_zero=i["base_zero"], kappa=i["kappa"], c0=i["c0"], consistent_u=i["consistent"],
-                  k_tilt=i["k_tilt"])
+                  k_tilt=i["k_tilt"], k_smooth=i["k_smooth"])
+    r = emulate_leaflet(i["pos"], i["tri"], i["tilts"], with_bt=False, with_smooth=True, **common)
+    _close(r["E_smooth"], float(gold[pre + "E_smooth"]))
+    assert rel_err(r["tilt_grad"], gold[pre + "tg_smooth"]) <= TOL and not np.any(r["grad"])
     r = emulate_leaflet(i["pos"], i["tri"], i["tilts"], with_bt=True, with_tilt=False, **common)
     _close(r["E_bt"], float(gold[pre + "E_bt"]))
     assert rel_err(r["grad"], gold[pre + "g_bt"]) <= TOL
@@ -113,7 +122,7 @@ def _device_leaflet(i, leaf, *, order_hint=None, **over):
     dm = DeviceMesh(0)
     dm.set_topology(i["pos"].shape[0], i["tri"], is_boundary=i["is_boundary"].astype(np.uint8), order_hint=order_hint)
     which = L.LEAFLET_IN if leaf == "in" else L.LEAFLET_OUT
-    args = dict(div_sign=i["sign"], kappa=i["kappa"], c0=i["c0"], k_tilt=i["k_tilt"], facet_keep=i["keep"],
+    args = dict(div_sign=i["sign"], kappa=i["kappa"], c0=i["c0"], k_tilt=i["k_tilt"], k_smooth=i["k_smooth"], facet_keep=i["keep"],
                 interior=i["interior"], base_zero=i["base_zero"], consistent=i["consistent"])
     args.update(over)
     dm.set_leaflet(which, **args)
@@ -132,27 +141,32 @@ def test_device_matches_reference(gold, state, leaf, hint):
     i = _inputs(gold, state, leaf)
     pre = f"{state}_{leaf}_"
     dm, which, arr_tg = _device_leaflet(i, leaf, order_hint=i["pos"] if hint else None)
-    e_bt, e_t = dm.eval_leaflet(which, L.MOD_BENDING_TILT)
+    _, _, e_s = dm.eval_leaflet(which, L.MOD_TILT_SMOOTHNESS)
+    _close(e_s, float(gold[pre + "E_smooth"]))
+    assert rel_err(dm.download(arr_tg), gold[pre + "tg_smooth"]) <= TOL and not np.any(dm.download(L.ARR_GRAD))
+    e_bt, e_t, _ = dm.eval_leaflet(which, L.MOD_BENDING_TILT)
     _close(e_bt, float(gold[pre + "E_bt"]))
     assert e_t == 0.0
     assert rel_err(dm.download(L.ARR_GRAD), gold[pre + "g_bt"]) <= TOL
     assert rel_err(dm.download(arr_tg), gold[pre + "tg_bt"]) <= TOL
-    e_bt, e_t = dm.eval_leaflet(which, L.MOD_TILT)
+    e_bt, e_t, _ = dm.eval_leaflet(which, L.MOD_TILT)
     _close(e_t, float(gold[pre + "E_tilt"]))
     assert rel_err(dm.download(L.ARR_GRAD), gold[pre + "g_tilt"]) <= TOL
     assert rel_err(dm.download(arr_tg), gold[pre + "tg_tilt"]) <= TOL
     # both modules in one sweep, accumulated on top of the previous results
     g_prev, tg_prev = dm.download(L.ARR_GRAD), dm.download(arr_tg)
-    e_bt, e_t = dm.eval_leaflet(which, L.MOD_TILT | L.MOD_BENDING_TILT, accumulate=L.ACC_GRAD | L.ACC_TILT_GRAD)
+    e_bt, e_t, _ = dm.eval_leaflet(which, L.MOD_TILT | L.MOD_BENDING_TILT, accumulate=L.ACC_GRAD | L.ACC_TILT_GRAD)
     _close(e_bt, float(gold[pre + "E_bt"]))
     _close(e_t, float(gold[pre + "E_tilt"]))
     assert rel_err(dm.download(L.ARR_GRAD) - g_prev, gold[pre + "g_bt"] + gold[pre + "g_tilt"]) <= 4 * TOL
     assert rel_err(dm.download(arr_tg) - tg_prev, gold[pre + "tg_bt"] + gold[pre + "tg_tilt"]) <= 4 * TOL
     # tilt-only evaluation: the shape gradient array is left alone
     g_before = dm.download(L.ARR_GRAD)
-    e_bt, e_t = dm.eval_leaflet(which, L.MOD_TILT | L.MOD_BENDING_TILT, want_grad=False)
+    e_bt, e_t, e_s = dm.eval_leaflet(which, L.MOD_TILT | L.MOD_BENDING_TILT | L.MOD_TILT_SMOOTHNESS, want_grad=False)
     _close(e_bt, float(gold[pre + "E_bt_tiltonly"]))
-    assert rel_err(dm.download(arr_tg), gold[pre + "tg_bt_tiltonly"] + gold[pre + "tg_tilt_tiltonly"]) <= TOL
+    _close(e_s, float(gold[pre + "E_smooth_tiltonly"]))
+    assert rel_err(dm.download(arr_tg), gold[pre + "tg_bt_tiltonly"] + gold[pre + "tg_tilt_tiltonly"]
+                   + gold[pre + "tg_smooth_tiltonly"]) <= TOL
     assert np.array_equal(dm.download(L.ARR_GRAD), g_before)
     # repeatable bit for bit (fixed-order gathers, no atomics)
     dm.eval_leaflet(which, L.MOD_TILT | L.MOD_BENDING_TILT)
@@ -177,13 +191,13 @@ def test_device_row_weights_mixed_mass_modes_and_errors(gold):
     e = rl.leaflet_tilt_energy_and_gradient(i["pos"], i["tri"], i["tilts"], i["k_tilt"], keep=i["keep"],
                                             row_weights=w, consistent=cons, grad=g, tilt_grad=tg)
     dm, which, arr_tg = _device_leaflet(i, "out", tilt_row_weight=w, facet_consistent=cons)
-    _, e_t = dm.eval_leaflet(which, L.MOD_TILT)
+    _, e_t, _ = dm.eval_leaflet(which, L.MOD_TILT)
     _close(e_t, e)
     assert rel_err(dm.download(L.ARR_GRAD), g) <= TOL and rel_err(dm.download(arr_tg), tg) <= TOL
     # uniform parameters as scalars = the same as arrays
     dm.set_leaflet(which, div_sign=1.0, kappa=1.0, c0=0.0, k_tilt=i["k_tilt"], facet_keep=i["keep"],
                    interior=i["interior"], base_zero=i["base_zero"])
-    e_bt, _ = dm.eval_leaflet(which, L.MOD_BENDING_TILT)
+    e_bt, _, _ = dm.eval_leaflet(which, L.MOD_BENDING_TILT)
     _close(e_bt, float(gold["r1_out_E_bt"]))
     dm.close()
     # loud failures: leaflet not configured, tilt field missing, foreign module bits
@@ -210,7 +224,8 @@ def _array_mesh(gold, state):
     for leaf in LEAFLETS:
         i = _inputs(gold, state, leaf)
         leaflets[leaf] = dict(keep_bt=i["keep"], keep_tilt=i["keep"], interior=i["interior"], base_zero=i["base_zero"],
-                              kappa=i["kappa"], c0=i["c0"], k_tilt=i["k_tilt"], consistent=i["consistent"])
+                              kappa=i["kappa"], c0=i["c0"], k_tilt=i["k_tilt"], k_smooth=i["k_smooth"],
+                              consistent=i["consistent"])
         tilts[leaf] = i["tilts"]
     return ArrayMesh(gold[f"{state}_pos"], gold[f"{state}_tri"], tilts_in=tilts["in"], tilts_out=tilts["out"],
                      leaflets=leaflets)
@@ -223,7 +238,7 @@ def _plugin_checks(gold, state):
     pos = mesh.positions_view()
     idx = mesh.vertex_index_to_row
     for leaf in LEAFLETS:
-        for name, tag in ((f"bending_tilt_{leaf}", "bt"), (f"tilt_{leaf}", "tilt")):
+        for name, tag in ((f"bending_tilt_{leaf}", "bt"), (f"tilt_{leaf}", "tilt"), (f"tilt_smoothness_{leaf}", "smooth")):
             mod = importlib.import_module(f"membrane_solver_b200.modules.energy.{name}")
             assert mod.USES_TILT_LEAFLETS
             pre = f"{state}_{leaf}_"
@@ -491,7 +506,7 @@ def test_device_leaflet_on_a_mesh_above_the_single_launch_threshold():
     e_bt = rl.leaflet_bending_tilt_energy_and_gradient(pos, tri, tilts, kappa, c0, sign=1.0, keep=keep, interior=interior,
                                                        base_zero=base_zero, is_boundary=None, grad=g, tilt_grad=tg)
     e_t = rl.leaflet_tilt_energy_and_gradient(pos, tri, tilts, 3.0, keep=keep, consistent=True, grad=g, tilt_grad=tg)
-    got_bt, got_t = dm.eval_leaflet(L.LEAFLET_OUT, L.MOD_TILT | L.MOD_BENDING_TILT)
+    got_bt, got_t, _ = dm.eval_leaflet(L.LEAFLET_OUT, L.MOD_TILT | L.MOD_BENDING_TILT)
     _close(got_bt, e_bt)
     _close(got_t, e_t)
     assert rel_err(dm.download(L.ARR_GRAD), g) <= 2e-12
