@@ -67,6 +67,8 @@ extern "C" {
 #define MS_ARR_TILTS_OUT     14 /* (nv,3) outer-leaflet tilt field  (Mesh.tilts_out_view, geometry/mesh.py:462-499) */
 #define MS_ARR_TILT_GRAD_IN  15 /* (nv,3) dE/dt_in  of the leaflet modules */
 #define MS_ARR_TILT_GRAD_OUT 16 /* (nv,3) dE/dt_out of the leaflet modules */
+#define MS_ARR_TILTS_FIELD   17 /* (nv,3) single tilt field evaluated through the leaflet sweeps (MS_LEAFLET_FIELD) */
+#define MS_ARR_TILT_GRAD_FIELD 18 /* (nv,3) its tilt gradient */
 
 #define MS_PATCHES_ALL       (-1)
 #define MS_PATCHES_INTERIOR  (-2)
@@ -205,6 +207,7 @@ typedef struct ms_leaflet_desc {
 
 #define MS_LEAFLET_IN  0
 #define MS_LEAFLET_OUT 1
+#define MS_LEAFLET_FIELD 2  /* the single tilt field (modules/energy/tilt_smoothness.py:219-262): same sweeps, own arrays */
 #define MS_ACC_GRAD      1u  /* add the shape gradient to MS_ARR_GRAD instead of overwriting it */
 #define MS_ACC_TILT_GRAD 2u  /* add to MS_ARR_TILT_GRAD_IN / _OUT instead of overwriting */
 

@@ -28,13 +28,14 @@ SC_G_G, SC_G_GC, SC_GC_GC, SC_LAMBDA, SC_COUNT = 8, 9, 10, 11, 16
 ARR_POSITIONS, ARR_GRAD, ARR_VOLGRAD, ARR_SEEDS, ARR_TILTS, ARR_TILT_GRAD = 0, 1, 2, 3, 4, 5
 ARR_SCALARS, ARR_K_VECS, ARR_A_VOR, ARR_A_EFF, ARR_E_VERTEX, ARR_TRIAL, ARR_DIRECTION = 6, 7, 8, 9, 10, 11, 12
 ARR_TILTS_IN, ARR_TILTS_OUT, ARR_TILT_GRAD_IN, ARR_TILT_GRAD_OUT = 13, 14, 15, 16
-LEAFLET_IN, LEAFLET_OUT = 0, 1
+ARR_TILTS_FIELD, ARR_TILT_GRAD_FIELD = 17, 18
+LEAFLET_IN, LEAFLET_OUT, LEAFLET_FIELD = 0, 1, 2
 IPC_FLAGS, IPC_HANDLE_BYTES, FLAG_POSITIONS, FLAG_SEEDS = 100, 64, 0, 1
 ACC_GRAD, ACC_TILT_GRAD = 1, 2
 ARRAY_WIDTH = {ARR_POSITIONS: 3, ARR_GRAD: 3, ARR_VOLGRAD: 3, ARR_SEEDS: 5, ARR_TILTS: 3,
                ARR_TILT_GRAD: 3, ARR_SCALARS: 1, ARR_K_VECS: 3, ARR_A_VOR: 1, ARR_A_EFF: 1,
                ARR_E_VERTEX: 1, ARR_TRIAL: 3, ARR_DIRECTION: 3, ARR_TILTS_IN: 3, ARR_TILTS_OUT: 3,
-               ARR_TILT_GRAD_IN: 3, ARR_TILT_GRAD_OUT: 3}
+               ARR_TILT_GRAD_IN: 3, ARR_TILT_GRAD_OUT: 3, ARR_TILTS_FIELD: 3, ARR_TILT_GRAD_FIELD: 3}
 
 
 class B200Error(RuntimeError):

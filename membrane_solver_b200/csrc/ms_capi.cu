@@ -124,7 +124,7 @@ struct ms_ctx {
     bool has_fixed = false;
     double kappa_u = 0.0, c0_u = 0.0, k_tilt = 0.0, k_smooth = 0.0, sign = 1.0;
     int32_t consistent_u = 0;
-  } leaflet[2];
+  } leaflet[3];  // inner leaflet, outer leaflet, single tilt field
   DevBuf<double> d_lf_corner, d_lf_vbuf, d_lf_shape, d_lf_tilt, d_lf_facet_e, d_lf_e;
   DevBuf<double> d_vnormals, d_rowsq, d_norm_out, d_lf_block_e;
   DevBuf<unsigned long long> d_lf_ticket;
@@ -182,6 +182,8 @@ double* array_ptr(ms_ctx* c, int which, int64_t* len) {
     case MS_ARR_TILTS_OUT: *len = 3 * nv; return c->leaflet[1].tilts.p;
     case MS_ARR_TILT_GRAD_IN: *len = 3 * nv; return c->leaflet[0].tilt_grad.p;
     case MS_ARR_TILT_GRAD_OUT: *len = 3 * nv; return c->leaflet[1].tilt_grad.p;
+    case MS_ARR_TILTS_FIELD: *len = 3 * nv; return c->leaflet[2].tilts.p;
+    case MS_ARR_TILT_GRAD_FIELD: *len = 3 * nv; return c->leaflet[2].tilt_grad.p;
     default: *len = 0; return nullptr;
   }
 }
@@ -202,6 +204,8 @@ int ensure_array(ms_ctx* c, int which) {
     case MS_ARR_TILTS_OUT: return c->leaflet[1].tilts.ensure(3 * nv);
     case MS_ARR_TILT_GRAD_IN: return c->leaflet[0].tilt_grad.ensure(3 * nv);
     case MS_ARR_TILT_GRAD_OUT: return c->leaflet[1].tilt_grad.ensure(3 * nv);
+    case MS_ARR_TILTS_FIELD: return c->leaflet[2].tilts.ensure(3 * nv);
+    case MS_ARR_TILT_GRAD_FIELD: return c->leaflet[2].tilt_grad.ensure(3 * nv);
     default: return 0;
   }
 }
@@ -575,9 +579,7 @@ int ms_ctx_set_topology_partition(ms_ctx* c, int32_t nv, int32_t n_owned, int32_
   c->bt_ready = false;
   c->tri_ready = false;
   c->pipe_ready = false;
-  c->leaflet[0].set = c->leaflet[1].set = false;
-  c->leaflet[0].has_fixed = c->leaflet[1].has_fixed = false;
-  c->leaflet[0].has_minv = c->leaflet[1].has_minv = false;
+  for (auto& lf : c->leaflet) lf.set = lf.has_fixed = lf.has_minv = false;
   c->vnormals_ready = false;
   const ms::PackedMesh& pk = c->packed;
   const size_t np = pk.patches.size();
@@ -942,7 +944,7 @@ int ms_ctx_eval(ms_ctx* c, const ms_eval_opts* o, double* scalars16) {
 // ---- leaflet tilt modules ------------------------------------------------------------------------------
 int ms_ctx_set_leaflet(ms_ctx* c, int32_t leaflet, const ms_leaflet_desc* d) {
   if (int rc = check_ctx(c, true)) return rc;
-  if (!d || leaflet < 0 || leaflet > 1) return fail(-1, "bad leaflet arguments");
+  if (!d || leaflet < 0 || leaflet > 2) return fail(-1, "bad leaflet arguments");
   if (c->n_owned != c->nv) return fail(-5, "leaflet modules are not available on a partitioned context");
   ms_ctx::Leaflet& L = c->leaflet[leaflet];
   const size_t nv = size_t(c->nv), nf = size_t(c->nf);
@@ -991,13 +993,13 @@ static void fill_leaflet_mesh(ms_ctx* c, ms_ctx::Leaflet& L, bool use_trial, ms:
 int ms_ctx_eval_leaflet(ms_ctx* c, int32_t leaflet, uint32_t modules, int32_t want_grad, int32_t want_tilt_grad,
                         uint32_t accumulate, int32_t use_trial, double* energies3) {
   if (int rc = check_ctx(c, true)) return rc;
-  if (leaflet < 0 || leaflet > 1) return fail(-1, "bad leaflet index");
+  if (leaflet < 0 || leaflet > 2) return fail(-1, "bad leaflet index");
   ms_ctx::Leaflet& L = c->leaflet[leaflet];
   if (!L.set) return fail(-4, "ms_ctx_set_leaflet has not been called for this leaflet (or the topology changed)");
   if (modules & ~uint32_t(MS_MOD_TILT | MS_MOD_BENDING_TILT | MS_MOD_TILT_SMOOTHNESS))
     return fail(-1, "leaflet modules are MS_MOD_TILT, MS_MOD_BENDING_TILT and MS_MOD_TILT_SMOOTHNESS");
-  const int which_t = leaflet == 0 ? MS_ARR_TILTS_IN : MS_ARR_TILTS_OUT;
-  const int which_g = leaflet == 0 ? MS_ARR_TILT_GRAD_IN : MS_ARR_TILT_GRAD_OUT;
+  const int which_t = leaflet == 0 ? MS_ARR_TILTS_IN : (leaflet == 1 ? MS_ARR_TILTS_OUT : MS_ARR_TILTS_FIELD);
+  const int which_g = leaflet == 0 ? MS_ARR_TILT_GRAD_IN : (leaflet == 1 ? MS_ARR_TILT_GRAD_OUT : MS_ARR_TILT_GRAD_FIELD);
   if (!L.tilts.p && c->nv > 0) return fail(-4, "the leaflet's tilt field has not been uploaded (MS_ARR_TILTS_IN / _OUT)");
   if (use_trial && !c->d_trial.p) return fail(-4, "use_trial set but no trial positions exist (ms_ctx_make_trial)");
   (void)which_t;
@@ -1052,7 +1054,7 @@ int ms_ctx_eval_leaflet(ms_ctx* c, int32_t leaflet, uint32_t modules, int32_t wa
 
 int ms_ctx_set_leaflet_fixed(ms_ctx* c, int32_t leaflet, const uint8_t* fixed_rows) {
   if (int rc = check_ctx(c, true)) return rc;
-  if (leaflet < 0 || leaflet > 1) return fail(-1, "bad leaflet index");
+  if (leaflet < 0 || leaflet > 2) return fail(-1, "bad leaflet index");
   ms_ctx::Leaflet& L = c->leaflet[leaflet];
   return upload_optional(c, fixed_rows, size_t(c->nv), true, L.fixed, L.has_fixed);
 }
@@ -1070,7 +1072,7 @@ int ms_ctx_update_vertex_normals(ms_ctx* c) {
 
 static int leaflet_ready(ms_ctx* c, int32_t leaflet, bool need_normals) {
   if (int rc = check_ctx(c, true)) return rc;
-  if (leaflet < 0 || leaflet > 1) return fail(-1, "bad leaflet index");
+  if (leaflet < 0 || leaflet > 2) return fail(-1, "bad leaflet index");
   if (!c->leaflet[leaflet].tilts.p && c->nv > 0) return fail(-4, "the leaflet's tilt field has not been uploaded");
   if (need_normals && !c->vnormals_ready) return fail(-4, "ms_ctx_update_vertex_normals has not been called for this topology");
   return 0;

@@ -15,4 +15,4 @@ loaded B200 modules in ONE fused device pass.
 NAMES = ("surface", "volume", "bending", "tilt", "bending_tilt")
 # leaflet plugins: evaluated by their own device sweeps (csrc/ms_leaflet.cuh), not by the fused patch pass
 LEAFLET_NAMES = ("tilt_in", "tilt_out", "bending_tilt_in", "bending_tilt_out", "tilt_smoothness_in",
-                 "tilt_smoothness_out")
+                 "tilt_smoothness_out", "tilt_smoothness")

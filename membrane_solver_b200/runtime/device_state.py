@@ -178,7 +178,8 @@ class DeviceState:
             return m.astype(np.uint8)
 
         bz = mask(spec.get("base_zero"))
-        self.dm.set_leaflet(L.LEAFLET_IN if leaflet == "in" else L.LEAFLET_OUT, div_sign=div_sign,
+        slot = {"in": L.LEAFLET_IN, "out": L.LEAFLET_OUT, "field": L.LEAFLET_FIELD}[leaflet]
+        self.dm.set_leaflet(slot, div_sign=div_sign,
                             kappa=uniform(spec.get("kappa", 0.0)), c0=uniform(spec.get("c0", 0.0)),
                             k_tilt=float(spec.get("k_tilt", 0.0)), k_smooth=float(spec.get("k_smooth", 0.0)),
                             facet_keep=None if keep is None or np.all(keep) else mask(keep),

@@ -176,8 +176,9 @@ class FakeDeviceMesh:
         if int(leaflet) not in getattr(self, "leaflets", {}):
             raise L.B200Error("ms_ctx_set_leaflet has not been called for this leaflet")
         d = self.leaflets[int(leaflet)]
-        arr_t = L.ARR_TILTS_IN if leaflet == L.LEAFLET_IN else L.ARR_TILTS_OUT
-        arr_g = L.ARR_TILT_GRAD_IN if leaflet == L.LEAFLET_IN else L.ARR_TILT_GRAD_OUT
+        arr_t = {L.LEAFLET_IN: L.ARR_TILTS_IN, L.LEAFLET_OUT: L.ARR_TILTS_OUT, L.LEAFLET_FIELD: L.ARR_TILTS_FIELD}[leaflet]
+        arr_g = {L.LEAFLET_IN: L.ARR_TILT_GRAD_IN, L.LEAFLET_OUT: L.ARR_TILT_GRAD_OUT,
+                 L.LEAFLET_FIELD: L.ARR_TILT_GRAD_FIELD}[leaflet]
         k, c = d.get("kappa", 0.0), d.get("c0", 0.0)
         r = H.emulate_leaflet(self.trial if use_trial else self.pos, self.tri, self.arrays[arr_t], sign=d["div_sign"],
                               keep=d.get("facet_keep"), is_boundary=self.is_boundary, interior=d.get("interior"),

@@ -446,7 +446,18 @@ def p1_vertex_vectors():
     tri = np.ascontiguousarray(mesh.triangle_row_cache()[0], dtype=np.int32)
     tilts = 0.2 * rng.standard_normal(pos.shape)
     div_v, area_v = p1_vertex_divergence(n_vertices=len(pos), positions=pos, tilts=tilts, tri_rows=tri)
-    np.savez_compressed(os.path.join(HERE, "p1_vertex.npz"), pos=pos, tri=tri, tilts=tilts, div_v=div_v, area_v=area_v)
+    # single-field tilt smoothness (modules/energy/tilt_smoothness.py) on the same state
+    from modules.energy import tilt_smoothness
+
+    gp = mesh.global_parameters
+    gp.set("tilt_smoothness_rigidity", 0.7)
+    tg, g = np.zeros_like(pos), np.zeros_like(pos)
+    e_s = tilt_smoothness.compute_energy_and_gradient_array(mesh, gp, ParameterResolver(gp), positions=pos,
+                                                            index_map=mesh.vertex_index_to_row, grad_arr=g, tilts=tilts,
+                                                            tilt_grad_arr=tg)
+    assert not g.any()
+    np.savez_compressed(os.path.join(HERE, "p1_vertex.npz"), pos=pos, tri=tri, tilts=tilts, div_v=div_v, area_v=area_v,
+                        smooth_k=np.float64(0.7), smooth_E=np.float64(e_s), smooth_tg=tg)
     print("p1_vertex", len(pos), len(tri), float(np.abs(div_v).max()))
 
 

@@ -512,3 +512,43 @@ def test_device_leaflet_on_a_mesh_above_the_single_launch_threshold():
     assert rel_err(dm.download(L.ARR_GRAD), g) <= 2e-12
     assert rel_err(dm.download(L.ARR_TILT_GRAD_OUT), tg) <= TOL
     dm.close()
+
+
+def _single_field_smoothness(factory_patch=None):
+    from membrane_solver_b200.geometry.array_mesh import ArrayMesh, GlobalParams
+    from membrane_solver_b200.modules.energy import tilt_smoothness as mod
+
+    g = np.load(os.path.join(GOLDEN, "p1_vertex.npz"))
+    gp = GlobalParams({"tilt_smoothness_rigidity": float(g["smooth_k"])})
+    mesh = ArrayMesh(g["pos"], g["tri"], global_params=gp, tilts=g["tilts"])
+    pos = mesh.positions_view()
+    tg = np.full_like(pos, 0.5)
+    grad = np.full_like(pos, -1.0)
+    e = mod.compute_energy_and_gradient_array(mesh, gp, None, positions=pos, index_map=mesh.vertex_index_to_row,
+                                              grad_arr=grad, tilts=g["tilts"], tilt_grad_arr=tg)
+    _close(e, float(g["smooth_E"]))
+    assert rel_err(tg - 0.5, g["smooth_tg"]) <= 4 * TOL
+    assert np.all(grad == -1.0)                          # no shape gradient
+    _close(mod.compute_energy_array(mesh, gp, None, positions=pos, index_map=mesh.vertex_index_to_row),
+           float(g["smooth_E"]))
+    assert mod.compute_energy_array(mesh, GlobalParams({}), None, positions=pos, index_map=None) == 0.0
+
+
+def test_single_field_tilt_smoothness_on_emulated_device(monkeypatch):
+    from fake_device import FakeDeviceMesh
+
+    from membrane_solver_b200.runtime import device_state
+    from oracle import ref_leaflet as rl
+
+    g = np.load(os.path.join(GOLDEN, "p1_vertex.npz"))
+    tg = np.zeros_like(g["pos"])
+    e = rl.leaflet_tilt_smoothness_energy_and_gradient(g["pos"], g["tri"], g["tilts"], float(g["smooth_k"]), tilt_grad=tg)
+    _close(e, float(g["smooth_E"]))
+    assert rel_err(tg, g["smooth_tg"]) <= TOL
+    monkeypatch.setattr(device_state, "DEVICE_MESH_FACTORY", FakeDeviceMesh)
+    _single_field_smoothness()
+
+
+@pytest.mark.gpu
+def test_single_field_tilt_smoothness_on_device():
+    _single_field_smoothness()
