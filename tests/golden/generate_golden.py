@@ -547,6 +547,28 @@ def tilt_relaxation_vectors():
     np.savez_compressed(os.path.join(HERE, "tilt_relaxation.npz"), **out)
 
 
+def vertex_average_vectors():
+    """runtime/vertex_average.py on a jittered refined cube (closed) and on the catenoid (fixed rims)."""
+    from runtime.vertex_average import vertex_average
+
+    out = {}
+    for name, path, levels in (("cube", os.path.join(REF, "meshes", "cube.json"), 2),
+                               ("catenoid", os.path.join(REF, "meshes", "catenoid.json"), 2)):
+        mesh = _refined(path, levels)
+        rng = np.random.default_rng(13)
+        for v in mesh.vertices.values():
+            if not getattr(v, "fixed", False):
+                v.position = np.asarray(v.position, dtype=float) + 0.03 * rng.normal(size=3)
+        mesh.increment_version()
+        out[f"{name}_pos0"] = np.array(mesh.positions_view())
+        out[f"{name}_tri"] = np.ascontiguousarray(mesh.triangle_row_cache()[0], dtype=np.int32)
+        out[f"{name}_fixed"] = np.array([bool(mesh.vertices[int(v)].fixed) for v in mesh.vertex_ids])
+        vertex_average(mesh)
+        out[f"{name}_pos1"] = np.array(mesh.positions_view())
+        print("vertex_average", name, len(mesh.vertex_ids), float(np.abs(out[f"{name}_pos1"] - out[f"{name}_pos0"]).max()))
+    np.savez_compressed(os.path.join(HERE, "vertex_average.npz"), **out)
+
+
 if __name__ == "__main__":
     _ = (volume_constraint, volume_energy)
     if len(sys.argv) > 1 and sys.argv[1] == "leaflet":
@@ -554,6 +576,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "tiltrelax":
         tilt_relaxation_vectors()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "vertexaverage":
+        vertex_average_vectors()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "p1vertex":
         p1_vertex_vectors()
@@ -565,3 +590,4 @@ if __name__ == "__main__":
     leaflet_vectors()
     p1_vertex_vectors()
     tilt_relaxation_vectors()
+    vertex_average_vectors()

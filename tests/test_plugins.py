@@ -233,3 +233,28 @@ def test_array_refinement_matches_reference_hierarchy():
         assert abs(vol - 1.0) < 1e-14 and abs(area - 6.0) < 1e-13
         assert not ArrayMesh(pos, tri).boundary_vertex_ids          # closed
         assert fixed.sum() == 2 + (2**k - 1)                         # the refined edge 0-1 stays fixed
+
+
+def test_array_vertex_averaging_matches_reference():
+    """Mesh maintenance next to the refinement: ``geometry.vertex_average`` against the
+    reference's ``runtime/vertex_average.py`` on a jittered cube (closed) and catenoid (fixed rims)."""
+    import os
+
+    from membrane_solver_b200.geometry.vertex_average import vertex_average_arrays
+    from ms_test_helpers import GOLDEN
+
+    g = np.load(os.path.join(GOLDEN, "vertex_average.npz"))
+    for name in ("cube", "catenoid"):
+        pos0, tri, fixed = g[name + "_pos0"], g[name + "_tri"], g[name + "_fixed"]
+        out = vertex_average_arrays(pos0, tri, movable=~fixed)
+        assert np.max(np.abs(out - g[name + "_pos1"])) <= 1e-13
+        assert np.array_equal(out[fixed], pos0[fixed])
+        assert np.max(np.abs(out - pos0)) > 1e-3
+    # pin groups: a grouped vertex only averages over neighbours of its own group
+    pos0, tri = g["cube_pos0"], g["cube_tri"]
+    group = np.full(len(pos0), -1)
+    group[:5] = 0
+    out = vertex_average_arrays(pos0, tri, group=group)
+    assert np.max(np.abs(out[5:] - g["cube_pos1"][5:])) <= 1e-13     # ungrouped vertices are unaffected
+    assert not np.allclose(out[:5], g["cube_pos1"][:5])
+    assert vertex_average_arrays(pos0, np.zeros((0, 3), np.int32)).tolist() == pos0.tolist()
