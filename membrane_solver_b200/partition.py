@@ -110,6 +110,14 @@ def send_lists(local: LocalMesh, all_ghost_ids: list[np.ndarray]) -> list[tuple[
     return out
 
 
+def ghost_sources(local: LocalMesh) -> tuple[np.ndarray, np.ndarray]:
+    """For every ghost row of ``local`` (in ghost order): the rank that owns it and its row in the owner's local
+    numbering (owned rows come first there, so it is the global id minus the owner's cut)."""
+    owners = np.searchsorted(local.cuts, local.ghost_ids, side="right") - 1
+    rows = local.ghost_ids - local.cuts[owners]
+    return owners.astype(np.int32), rows.astype(np.int32)
+
+
 class HaloExchange:
     """Exchanges the ghost rows of per-vertex arrays between ranks (torch.distributed).
 
@@ -216,8 +224,7 @@ class PartitionedMesh:
         table = [None] * local.world
         dist.all_gather_object(table, mine)
         if ok and all(t is not None for t in table):
-            owners = np.searchsorted(local.cuts, local.ghost_ids, side="right") - 1
-            rows = local.ghost_ids - local.cuts[owners]
+            owners, rows = ghost_sources(local)
             try:
                 for o in np.unique(owners):
                     for w, handle in zip(whiches[:3], table[int(o)][:3]):
@@ -226,7 +233,7 @@ class PartitionedMesh:
                     if r != local.rank:
                         dm.peer_open(r, L.IPC_FLAGS, table[r][3])
                 dm.set_rank_slot(local.rank, local.world)
-                dm.set_ghost_sources(local.world, owners.astype(np.int32), rows.astype(np.int32))
+                dm.set_ghost_sources(local.world, owners, rows)
                 dm.halo_prepare()
             except L.B200Error as exc:
                 ok, err = 0, str(exc)

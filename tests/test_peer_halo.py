@@ -15,7 +15,7 @@ def test_three_partitions_exchange_over_peer_pointers():
 
     from membrane_solver_b200 import _lib as L
     from membrane_solver_b200.context import DeviceMesh
-    from membrane_solver_b200.partition import split_mesh
+    from membrane_solver_b200.partition import ghost_sources, split_mesh
     from membrane_solver_b200.synthetic import icosphere
 
     pos, tri = icosphere(40)
@@ -52,8 +52,7 @@ def test_three_partitions_exchange_over_peer_pointers():
         streams.append(stream)
     torch.cuda.synchronize()
     for r, (loc, dm) in enumerate(zip(parts, dms)):
-        owners = np.searchsorted(loc.cuts, loc.ghost_ids, side="right") - 1
-        rows = loc.ghost_ids - loc.cuts[owners]
+        owners, rows = ghost_sources(loc)
         for o in np.unique(owners):
             for which in (L.ARR_POSITIONS, L.ARR_TRIAL, L.ARR_SEEDS):
                 dm.peer_set_pointer(int(o), which, dms[int(o)].device_ptr(which))
@@ -61,7 +60,7 @@ def test_three_partitions_exchange_over_peer_pointers():
             if o != r:
                 dm.peer_set_pointer(o, L.IPC_FLAGS, dms[o].flag_words_ptr())
         dm.set_rank_slot(r, world)
-        dm.set_ghost_sources(world, owners.astype(np.int32), rows.astype(np.int32))
+        dm.set_ghost_sources(world, owners, rows)
     for dm in dms:
         dm.halo_prepare()      # allocations / NULL-stream copies would serialise the three streams of this process
     torch.cuda.synchronize()
@@ -100,3 +99,23 @@ def test_three_partitions_exchange_over_peer_pointers():
     for dm in dms:
         L.check(lib.ms_ctx_set_stream(dm._h, None))
         dm.close()
+
+
+def test_ghost_sources_point_at_the_owners_rows():
+    """CPU tier: the (owner rank, owner-local row) table the peer pulls read through."""
+    from membrane_solver_b200.partition import ghost_sources, split_mesh
+    from membrane_solver_b200.synthetic import icosphere
+
+    pos, tri = icosphere(12)
+    nv = pos.shape[0]
+    for world in (2, 3, 5):
+        parts = [split_mesh(nv, tri, world, r) for r in range(world)]
+        for loc in parts:
+            owners, rows = ghost_sources(loc)
+            assert owners.shape == rows.shape == loc.ghost_ids.shape
+            assert not np.any(owners == loc.rank)
+            for o in np.unique(owners):
+                sel = owners == o
+                owner = parts[int(o)]
+                assert np.all(rows[sel] < owner.n_owned)
+                assert np.array_equal(owner.global_rows()[rows[sel]], loc.ghost_ids[sel])
