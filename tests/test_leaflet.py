@@ -552,3 +552,44 @@ def test_single_field_tilt_smoothness_on_emulated_device(monkeypatch):
 @pytest.mark.gpu
 def test_single_field_tilt_smoothness_on_device():
     _single_field_smoothness()
+
+
+@pytest.mark.parametrize("solver", ["gd", "cg"])
+def test_tilt_relaxer_stop_conditions_on_emulated_device(relax_gold, solver):
+    """Loop control of the relaxer: tolerance reached before the first step, every row fixed, zero step size."""
+    from fake_device import FakeDeviceMesh
+
+    from membrane_solver_b200 import _lib as L
+    from membrane_solver_b200.runtime.device_tilt_relaxer import DeviceTiltRelaxer
+
+    g, p = relax_gold, "gd5_"
+    pos, tri = g[p + "pos"], g[p + "tri"]
+
+    def build(fixed_all=False):
+        dm = FakeDeviceMesh(0)
+        dm.set_topology(pos.shape[0], tri, is_boundary=g[p + "is_boundary"].astype(np.uint8))
+        dm.set_positions(pos)
+        for leaf, d in _relax_leaflets(g, "gd5").items():
+            which = L.LEAFLET_IN if leaf == "in" else L.LEAFLET_OUT
+            dm.set_leaflet(which, div_sign=-1.0 if leaf == "in" else 1.0, kappa=d["kappa"], c0=d["c0"], k_tilt=d["k_tilt"],
+                           facet_keep=d["keep"].astype(np.uint8), interior=d["interior"].astype(np.uint8),
+                           base_zero=d["base_zero"].astype(np.uint8))
+            fx = np.ones(pos.shape[0], np.uint8) if fixed_all else g[p + f"fixed_{leaf}"].astype(np.uint8)
+            dm.set_leaflet_fixed(which, fx)
+            dm.upload(L.ARR_TILTS_IN if leaf == "in" else L.ARR_TILTS_OUT, g[p + f"tilts_{leaf}0"])
+        return dm
+
+    kw = dict(solver=solver, k_smooth={"in": 1.0, "out": 1.0}, area_kept_only={"out": True})
+    dm = build()
+    st = DeviceTiltRelaxer(dm).relax(max_iters=5, step_size=0.15, tol=1e9, **kw)
+    assert st["stop_reason"] == "converged" and st["accepted_steps"] == 0
+    assert abs(st["initial_gradient_norm"] - float(g[p + "initial_gradient_norm"])) <= 1e-9
+    st = DeviceTiltRelaxer(dm).relax(max_iters=5, step_size=0.0, **kw)
+    assert st["stop_reason"] == "step_size_zero"
+    dm = build(fixed_all=True)
+    before = dm.download(L.ARR_TILTS_IN)
+    st = DeviceTiltRelaxer(dm).relax(max_iters=5, step_size=0.15, **kw)
+    assert st["stop_reason"] == "zero_gradient" and st["accepted_steps"] == 0
+    # only the tangent projection touched the fields
+    n = dm.vnormals
+    assert np.allclose(dm.download(L.ARR_TILTS_IN), before - (before * n).sum(axis=1)[:, None] * n, atol=1e-15)
