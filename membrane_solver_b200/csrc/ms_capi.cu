@@ -1456,8 +1456,19 @@ static int eval_pipelined(ms_ctx* c, const ms_eval_opts* o, const double* pos_ho
   CU(cudaStreamWaitEvent(c->copy_stream, c->pipe_events[size_t(kPipeChunks)], 0));
   const int64_t nv = c->nv;
   int64_t row_hi[kPipeChunksMax];
+  // chunk boundaries: quadratic spacing (large chunks first, small ones last) keeps the kernels busy early and
+  // leaves little work behind the last copy; MS_PIPE_SPACING=uniform for equal chunks
+  static const bool uniform = [] {
+    const char* e = std::getenv("MS_PIPE_SPACING");
+    return e && std::string(e) == "uniform";
+  }();
+  auto boundary = [&](int k) -> int64_t {
+    if (k >= kPipeChunks) return nv;
+    const double x = double(k) / kPipeChunks;
+    return int64_t(double(nv) * (uniform ? x : 1.0 - (1.0 - x) * (1.0 - x)));
+  };
   for (int k = 0; k < kPipeChunks; ++k) {
-    const int64_t r0 = nv * k / kPipeChunks, r1 = nv * (k + 1) / kPipeChunks;
+    const int64_t r0 = boundary(k), r1 = boundary(k + 1);
     row_hi[k] = r1;
     if (r1 > r0)
       CU(cudaMemcpyAsync(dst + 3 * r0, pos_host + 3 * r0, size_t(3 * (r1 - r0)) * sizeof(double), cudaMemcpyHostToDevice,
