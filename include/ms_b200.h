@@ -232,8 +232,14 @@ MS_API int ms_ctx_set_leaflet_fixed(ms_ctx* ctx, int32_t leaflet, const uint8_t*
 MS_API int ms_ctx_update_vertex_normals(ms_ctx* ctx);
 /* t -= (t.n) n on the leaflet's tilt field (runtime/projections/tilt.py:8-14) */
 MS_API int ms_ctx_leaflet_project_tilts(ms_ctx* ctx, int32_t leaflet);
-/* zero the fixed rows of MS_ARR_TILT_GRAD_IN / _OUT and return the sum of squares of the rest (:856-871) */
+/* zero the fixed rows of MS_ARR_TILT_GRAD_IN / _OUT and return the sum of squares of the rest (:856-871);
+ * norm2 may be NULL (result read later through ms_ctx_leaflet_results) */
 MS_API int ms_ctx_leaflet_gradient_norm2(ms_ctx* ctx, int32_t leaflet, double* norm2);
+/* Batched read-back for loops that evaluate several leaflets per iteration: ms_ctx_eval_leaflet (energies3 ==
+ * NULL), ms_ctx_leaflet_gradient_norm2 (norm2 == NULL) and ms_ctx_leaflet_rz (rz == NULL) leave their results on the
+ * device; this call synchronises ONCE and returns, per leaflet slot l = 0..2, out15[5 l + {0,1,2}] = the three
+ * energies of the last evaluation, [5 l + 3] = |g|^2, [5 l + 4] = r.z */
+MS_API int ms_ctx_leaflet_results(ms_ctx* ctx, double* out15);
 /* trial = P(t - step * tilt gradient) or, with along_direction, P(t + step * CG direction); fixed rows keep t
  * (build_leaflet_trial_tilts, projections/tilt.py:99-138) */
 MS_API int ms_ctx_leaflet_make_trial(ms_ctx* ctx, int32_t leaflet, double step, int32_t along_direction);

@@ -227,10 +227,20 @@ class DeviceMesh:
     def leaflet_project_tilts(self, leaflet: int) -> None:
         L.check(self._lib.ms_ctx_leaflet_project_tilts(self._h, int(leaflet)))
 
-    def leaflet_gradient_norm2(self, leaflet: int) -> float:
+    def leaflet_gradient_norm2(self, leaflet: int, read: bool = True) -> float | None:
+        if not read:                                   # result stays on the device: leaflet_results()
+            L.check(self._lib.ms_ctx_leaflet_gradient_norm2(self._h, int(leaflet), None))
+            return None
         out = np.zeros(1)
         L.check(self._lib.ms_ctx_leaflet_gradient_norm2(self._h, int(leaflet), L.dptr(out)))
         return float(out[0])
+
+    def leaflet_results(self) -> np.ndarray:
+        """One synchronisation for everything the leaflet calls left on the device: rows = leaflet slots,
+        columns = E_bending_tilt, E_tilt, E_tilt_smoothness, |g|^2, r.z."""
+        out = np.zeros(15)
+        L.check(self._lib.ms_ctx_leaflet_results(self._h, L.dptr(out)))
+        return out.reshape(3, 5)
 
     def leaflet_make_trial(self, leaflet: int, step: float, along_direction: bool = False) -> None:
         L.check(self._lib.ms_ctx_leaflet_make_trial(self._h, int(leaflet), float(step), int(bool(along_direction))))
@@ -239,7 +249,10 @@ class DeviceMesh:
         L.check(self._lib.ms_ctx_leaflet_build_preconditioner(self._h, int(leaflet), float(k_smooth),
                                                               int(bool(kept_facets_only))))
 
-    def leaflet_rz(self, leaflet: int, preconditioned: bool) -> float:
+    def leaflet_rz(self, leaflet: int, preconditioned: bool, read: bool = True) -> float | None:
+        if not read:
+            L.check(self._lib.ms_ctx_leaflet_rz(self._h, int(leaflet), int(bool(preconditioned)), None))
+            return None
         out = np.zeros(1)
         L.check(self._lib.ms_ctx_leaflet_rz(self._h, int(leaflet), int(bool(preconditioned)), L.dptr(out)))
         return float(out[0])
@@ -252,9 +265,14 @@ class DeviceMesh:
         L.check(self._lib.ms_ctx_leaflet_swap_trial(self._h, int(leaflet)))
 
     def eval_leaflet(self, leaflet: int, modules: int, *, want_grad: bool = True, want_tilt_grad: bool = True,
-                     accumulate: int = 0, use_trial: bool = False) -> tuple[float, float, float]:
+                     accumulate: int = 0, use_trial: bool = False, read: bool = True):
         """(E_bending_tilt, E_tilt, E_tilt_smoothness) of the leaflet's modules; gradients stay on the device
         (``ARR_GRAD``, ``ARR_TILT_GRAD_IN`` / ``_OUT``)."""
+        if not read:                                   # energies stay on the device: leaflet_results()
+            L.check(self._lib.ms_ctx_eval_leaflet(self._h, int(leaflet), int(modules), int(bool(want_grad)),
+                                                  int(bool(want_tilt_grad)), int(accumulate), int(bool(use_trial)),
+                                                  None))
+            return None
         e = np.zeros(3)
         L.check(self._lib.ms_ctx_eval_leaflet(self._h, int(leaflet), int(modules), int(bool(want_grad)),
                                               int(bool(want_tilt_grad)), int(accumulate), int(bool(use_trial)),

@@ -1013,7 +1013,12 @@ int ms_ctx_eval_leaflet(ms_ctx* c, int32_t leaflet, uint32_t modules, int32_t wa
   if (int rc = c->d_lf_shape.ensure(9 * nf + 1)) return rc;
   if (int rc = c->d_lf_tilt.ensure(9 * nf + 1)) return rc;
   if (int rc = c->d_lf_facet_e.ensure(3 * nf + 1)) return rc;
-  if (int rc = c->d_lf_e.ensure(3 + 3 * ms::kSumBlocks)) return rc;
+  constexpr size_t kLfResult = 3 + 3 * ms::kSumBlocks;  // per leaflet: three energies + reduction scratch
+  if (!c->d_lf_e.p) {
+    if (int rc = c->d_lf_e.ensure(3 * kLfResult)) return rc;
+    CU(cudaMemset(c->d_lf_e.p, 0, 3 * kLfResult * sizeof(double)));
+  }
+  double* lf_e = c->d_lf_e.p + size_t(leaflet) * kLfResult;
   ms::LeafletMesh m;
   fill_leaflet_mesh(c, L, use_trial != 0, m);
   static const bool fused_off = std::getenv("MS_LEAFLET_NO_FUSE") != nullptr;
@@ -1027,12 +1032,12 @@ int ms_ctx_eval_leaflet(ms_ctx* c, int32_t leaflet, uint32_t modules, int32_t wa
     }
     cudaError_t e = ms::launch_leaflet_fused(
         m, (modules & MS_MOD_BENDING_TILT) != 0, (modules & MS_MOD_TILT) != 0, (modules & MS_MOD_TILT_SMOOTHNESS) != 0,
-        c->d_lf_corner.p, c->d_lf_vbuf.p, c->d_lf_shape.p, c->d_lf_tilt.p, c->d_lf_block_e.p, ms::kLfFusedMaxBlocks, c->d_lf_e.p,
+        c->d_lf_corner.p, c->d_lf_vbuf.p, c->d_lf_shape.p, c->d_lf_tilt.p, c->d_lf_block_e.p, ms::kLfFusedMaxBlocks, lf_e,
         want_grad ? c->d_grad.p : nullptr, (accumulate & MS_ACC_GRAD) != 0, want_tilt_grad ? L.tilt_grad.p : nullptr,
         (accumulate & MS_ACC_TILT_GRAD) != 0, c->d_lf_ticket.p, &c->lf_ticket_base, c->stream);
     if (e == cudaSuccess) {
       if (energies3) {
-        CU(cudaMemcpyAsync(energies3, c->d_lf_e.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(energies3, lf_e, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
       }
       return 0;
@@ -1042,11 +1047,11 @@ int ms_ctx_eval_leaflet(ms_ctx* c, int32_t leaflet, uint32_t modules, int32_t wa
   }
   CU(ms::launch_leaflet(m, (modules & MS_MOD_BENDING_TILT) != 0, (modules & MS_MOD_TILT) != 0,
                         (modules & MS_MOD_TILT_SMOOTHNESS) != 0, c->d_lf_corner.p,
-                        c->d_lf_vbuf.p, c->d_lf_shape.p, c->d_lf_tilt.p, c->d_lf_facet_e.p, c->d_lf_e.p,
+                        c->d_lf_vbuf.p, c->d_lf_shape.p, c->d_lf_tilt.p, c->d_lf_facet_e.p, lf_e,
                         want_grad ? c->d_grad.p : nullptr, (accumulate & MS_ACC_GRAD) != 0,
                         want_tilt_grad ? L.tilt_grad.p : nullptr, (accumulate & MS_ACC_TILT_GRAD) != 0, c->stream));
   if (energies3) {
-    CU(cudaMemcpyAsync(energies3, c->d_lf_e.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(energies3, lf_e, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
   }
   return 0;
@@ -1086,14 +1091,34 @@ int ms_ctx_leaflet_project_tilts(ms_ctx* c, int32_t leaflet) {
 
 int ms_ctx_leaflet_gradient_norm2(ms_ctx* c, int32_t leaflet, double* norm2) {
   if (int rc = leaflet_ready(c, leaflet, false)) return rc;
-  if (!norm2) return fail(-1, "null argument");
   ms_ctx::Leaflet& L = c->leaflet[leaflet];
   if (!L.tilt_grad.p && c->nv > 0) return fail(-4, "no tilt gradient exists for this leaflet (ms_ctx_eval_leaflet)");
   if (int rc = c->d_rowsq.ensure(size_t(c->nv) + 1)) return rc;
-  if (int rc = c->d_norm_out.ensure(1 + ms::kSumBlocks)) return rc;
-  CU(ms::launch_masked_norm2(c->nv, L.tilt_grad.p, L.has_fixed ? L.fixed.p : nullptr, c->d_rowsq.p, c->d_norm_out.p,
-                             c->stream));
-  CU(cudaMemcpyAsync(norm2, c->d_norm_out.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  constexpr size_t kBlock = 1 + ms::kSumBlocks;  // per leaflet and kind (0 = |g|^2, 1 = r.z): result + scratch
+  if (int rc = c->d_norm_out.ensure(6 * kBlock)) return rc;
+  double* out = c->d_norm_out.p + size_t(2 * leaflet) * kBlock;
+  CU(ms::launch_masked_norm2(c->nv, L.tilt_grad.p, L.has_fixed ? L.fixed.p : nullptr, c->d_rowsq.p, out, c->stream));
+  if (norm2) {
+    CU(cudaMemcpyAsync(norm2, out, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  return 0;
+}
+
+int ms_ctx_leaflet_results(ms_ctx* c, double* out15) {
+  if (int rc = check_ctx(c, true)) return rc;
+  if (!out15) return fail(-1, "null argument");
+  for (int k = 0; k < 15; ++k) out15[k] = 0.0;
+  constexpr size_t kLfResult = 3 + 3 * ms::kSumBlocks, kBlock = 1 + ms::kSumBlocks;
+  for (int l = 0; l < 3; ++l) {
+    if (c->d_lf_e.p)
+      CU(cudaMemcpyAsync(out15 + 5 * l, c->d_lf_e.p + size_t(l) * kLfResult, 3 * sizeof(double), cudaMemcpyDeviceToHost,
+                         c->stream));
+    if (c->d_norm_out.p)
+      for (int k = 0; k < 2; ++k)
+        CU(cudaMemcpyAsync(out15 + 5 * l + 3 + k, c->d_norm_out.p + size_t(2 * l + k) * kBlock, sizeof(double),
+                           cudaMemcpyDeviceToHost, c->stream));
+  }
   CU(cudaStreamSynchronize(c->stream));
   return 0;
 }
@@ -1134,13 +1159,16 @@ static int cg_ready(ms_ctx* c, int32_t leaflet, int32_t preconditioned) {
 
 int ms_ctx_leaflet_rz(ms_ctx* c, int32_t leaflet, int32_t preconditioned, double* rz) {
   if (int rc = cg_ready(c, leaflet, preconditioned)) return rc;
-  if (!rz) return fail(-1, "null argument");
   ms_ctx::Leaflet& L = c->leaflet[leaflet];
   if (int rc = c->d_rowsq.ensure(size_t(c->nv) + 1)) return rc;
-  if (int rc = c->d_norm_out.ensure(1 + ms::kSumBlocks)) return rc;
-  CU(ms::launch_rz(c->nv, L.tilt_grad.p, preconditioned ? L.minv.p : nullptr, c->d_rowsq.p, c->d_norm_out.p, c->stream));
-  CU(cudaMemcpyAsync(rz, c->d_norm_out.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  constexpr size_t kBlock = 1 + ms::kSumBlocks;
+  if (int rc = c->d_norm_out.ensure(6 * kBlock)) return rc;
+  double* out = c->d_norm_out.p + size_t(2 * leaflet + 1) * kBlock;
+  CU(ms::launch_rz(c->nv, L.tilt_grad.p, preconditioned ? L.minv.p : nullptr, c->d_rowsq.p, out, c->stream));
+  if (rz) {
+    CU(cudaMemcpyAsync(rz, out, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
   return 0;
 }
 

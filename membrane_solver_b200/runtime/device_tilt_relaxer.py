@@ -34,11 +34,19 @@ class DeviceTiltRelaxer:
     stats: dict = field(default_factory=dict)
 
     def _energy(self, want_tilt_grad: bool) -> float:
-        total = 0.0
+        """Both leaflets are launched back to back; ONE synchronisation brings their energies."""
         for name in self.leaflets:
-            total += sum(self.dm.eval_leaflet(_WHICH[name], self.modules, want_grad=False,
-                                              want_tilt_grad=want_tilt_grad))
-        return total
+            self.dm.eval_leaflet(_WHICH[name], self.modules, want_grad=False, want_tilt_grad=want_tilt_grad, read=False)
+        res = self.dm.leaflet_results()
+        return float(sum(res[_WHICH[name], :3].sum() for name in self.leaflets))
+
+    def _energy_and_gradient_norm(self) -> tuple[float, float]:
+        for name in self.leaflets:
+            self.dm.eval_leaflet(_WHICH[name], self.modules, want_grad=False, want_tilt_grad=True, read=False)
+            self.dm.leaflet_gradient_norm2(_WHICH[name], read=False)
+        res = self.dm.leaflet_results()
+        e = float(sum(res[_WHICH[name], :3].sum() for name in self.leaflets))
+        return e, math.sqrt(float(sum(res[_WHICH[name], 3] for name in self.leaflets)))
 
     def relax(self, *, max_iters: int, step_size: float, tol: float = 0.0, solver: str = "gd",
               preconditioner: bool = True, k_smooth: dict | None = None, area_kept_only: dict | None = None,
@@ -61,8 +69,7 @@ class DeviceTiltRelaxer:
         for name in self.leaflets:
             dm.leaflet_project_tilts(_WHICH[name])
         for _ in range(int(max_iters)):
-            e0 = self._energy(True)
-            gnorm = math.sqrt(sum(dm.leaflet_gradient_norm2(_WHICH[n]) for n in self.leaflets))
+            e0, gnorm = self._energy_and_gradient_norm()
             if st["accepted_steps"] == 0 and st["rejected_steps"] == 0:
                 st["initial_energy"], st["initial_gradient_norm"] = e0, gnorm
             st["final_energy"], st["final_gradient_norm"] = e0, gnorm
@@ -101,8 +108,7 @@ class DeviceTiltRelaxer:
 
     # -- preconditioned conjugate gradients (tilt_relaxation.py:1057-1440) ------------------------------
     def _gradients(self) -> tuple[float, float]:
-        e = self._energy(True)
-        return e, math.sqrt(sum(self.dm.leaflet_gradient_norm2(_WHICH[n]) for n in self.leaflets))
+        return self._energy_and_gradient_norm()
 
     def _line_search(self, e0: float, step_size: float, along_direction: bool, st: dict):
         step = float(step_size)
@@ -146,7 +152,10 @@ class DeviceTiltRelaxer:
                                                 bool(area_kept_only.get(name, False)))
 
         def rz() -> float:
-            return sum(dm.leaflet_rz(_WHICH[n], preconditioner) for n in self.leaflets)
+            for n in self.leaflets:
+                dm.leaflet_rz(_WHICH[n], preconditioner, read=False)
+            res = dm.leaflet_results()
+            return float(sum(res[_WHICH[n], 4] for n in self.leaflets))
 
         rz_old = rz()
         for name in self.leaflets:

@@ -127,12 +127,14 @@ class FakeDeviceMesh:
         t = self.arrays[a]
         self.arrays[a] = t - (t * self.vnormals).sum(axis=1)[:, None] * self.vnormals
 
-    def leaflet_gradient_norm2(self, leaflet):
+    def leaflet_gradient_norm2(self, leaflet, read=True):
         _, g = self._lf_arrays(leaflet)
         fx = getattr(self, "leaflet_fixed", {}).get(int(leaflet))
         if fx is not None:
             self.arrays[g][fx] = 0.0
-        return float((self.arrays[g] ** 2).sum())
+        val = float((self.arrays[g] ** 2).sum())
+        self.__dict__.setdefault("lf_results", np.zeros((3, 5)))[int(leaflet), 3] = val
+        return val if read else None
 
     def leaflet_build_preconditioner(self, leaflet, k_smooth, kept_facets_only):
         from oracle import ref_leaflet as rl
@@ -148,9 +150,11 @@ class FakeDeviceMesh:
     def _minv(self, leaflet, preconditioned):
         return self.leaflet_minv[int(leaflet)][:, None] if preconditioned else 1.0
 
-    def leaflet_rz(self, leaflet, preconditioned):
+    def leaflet_rz(self, leaflet, preconditioned, read=True):
         _, g = self._lf_arrays(leaflet)
-        return float((self.arrays[g] ** 2 * self._minv(leaflet, preconditioned)).sum())
+        val = float((self.arrays[g] ** 2 * self._minv(leaflet, preconditioned)).sum())
+        self.__dict__.setdefault("lf_results", np.zeros((3, 5)))[int(leaflet), 4] = val
+        return val if read else None
 
     def leaflet_cg_direction(self, leaflet, beta, restart, preconditioned):
         _, g = self._lf_arrays(leaflet)
@@ -172,7 +176,11 @@ class FakeDeviceMesh:
         a, _ = self._lf_arrays(leaflet)
         self.arrays[a], self.leaflet_trial[int(leaflet)] = self.leaflet_trial[int(leaflet)], self.arrays[a]
 
-    def eval_leaflet(self, leaflet, modules, *, want_grad=True, want_tilt_grad=True, accumulate=0, use_trial=False):
+    def leaflet_results(self):
+        return np.array(self.__dict__.setdefault("lf_results", np.zeros((3, 5))))
+
+    def eval_leaflet(self, leaflet, modules, *, want_grad=True, want_tilt_grad=True, accumulate=0, use_trial=False,
+                     read=True):
         if int(leaflet) not in getattr(self, "leaflets", {}):
             raise L.B200Error("ms_ctx_set_leaflet has not been called for this leaflet")
         d = self.leaflets[int(leaflet)]
@@ -195,7 +203,8 @@ class FakeDeviceMesh:
             self.arrays[L.ARR_GRAD] = r["grad"] + (self.arrays[L.ARR_GRAD] if accumulate & L.ACC_GRAD else 0.0)
         if want_tilt_grad:
             self.arrays[arr_g] = r["tilt_grad"] + (self.arrays[arr_g] if accumulate & L.ACC_TILT_GRAD else 0.0)
-        return r["E_bt"], r["E_tilt"], r["E_smooth"]
+        self.__dict__.setdefault("lf_results", np.zeros((3, 5)))[int(leaflet), :3] = (r["E_bt"], r["E_tilt"], r["E_smooth"])
+        return (r["E_bt"], r["E_tilt"], r["E_smooth"]) if read else None
 
     # -- device-resident loop (numpy restatement of the small kernels; TEST ONLY) --
     def set_positions(self, pos):
