@@ -966,6 +966,16 @@ int ms_ctx_set_leaflet(ms_ctx* c, int32_t leaflet, const ms_leaflet_desc* d) {
   return 0;
 }
 
+// 15 result doubles (3 leaflet slots x {E_bending_tilt, E_tilt, E_tilt_smoothness, |g|^2, r.z}) in one block, so
+// that one copy brings everything back, followed by the scratch of the two-stage sums
+static int ensure_leaflet_results(ms_ctx* c) {
+  if (c->d_lf_e.p) return 0;
+  const size_t n = 16 + 3 * size_t(ms::kSumBlocks);
+  if (int rc = c->d_lf_e.ensure(n)) return rc;
+  CU(cudaMemset(c->d_lf_e.p, 0, n * sizeof(double)));
+  return 0;
+}
+
 static void fill_leaflet_mesh(ms_ctx* c, ms_ctx::Leaflet& L, bool use_trial, ms::LeafletMesh& m) {
   m.nv = c->nv;
   m.nf = c->nf;
@@ -1013,12 +1023,9 @@ int ms_ctx_eval_leaflet(ms_ctx* c, int32_t leaflet, uint32_t modules, int32_t wa
   if (int rc = c->d_lf_shape.ensure(9 * nf + 1)) return rc;
   if (int rc = c->d_lf_tilt.ensure(9 * nf + 1)) return rc;
   if (int rc = c->d_lf_facet_e.ensure(3 * nf + 1)) return rc;
-  constexpr size_t kLfResult = 3 + 3 * ms::kSumBlocks;  // per leaflet: three energies + reduction scratch
-  if (!c->d_lf_e.p) {
-    if (int rc = c->d_lf_e.ensure(3 * kLfResult)) return rc;
-    CU(cudaMemset(c->d_lf_e.p, 0, 3 * kLfResult * sizeof(double)));
-  }
-  double* lf_e = c->d_lf_e.p + size_t(leaflet) * kLfResult;
+  if (int rc = ensure_leaflet_results(c)) return rc;
+  double* lf_e = c->d_lf_e.p + 5 * size_t(leaflet);         // result row of this leaflet: 3 energies, |g|^2, r.z
+  double* lf_scratch = c->d_lf_e.p + 16;                     // reduction scratch behind the 15 results
   ms::LeafletMesh m;
   fill_leaflet_mesh(c, L, use_trial != 0, m);
   static const bool fused_off = std::getenv("MS_LEAFLET_NO_FUSE") != nullptr;
@@ -1047,7 +1054,7 @@ int ms_ctx_eval_leaflet(ms_ctx* c, int32_t leaflet, uint32_t modules, int32_t wa
   }
   CU(ms::launch_leaflet(m, (modules & MS_MOD_BENDING_TILT) != 0, (modules & MS_MOD_TILT) != 0,
                         (modules & MS_MOD_TILT_SMOOTHNESS) != 0, c->d_lf_corner.p,
-                        c->d_lf_vbuf.p, c->d_lf_shape.p, c->d_lf_tilt.p, c->d_lf_facet_e.p, lf_e,
+                        c->d_lf_vbuf.p, c->d_lf_shape.p, c->d_lf_tilt.p, c->d_lf_facet_e.p, lf_e, lf_scratch,
                         want_grad ? c->d_grad.p : nullptr, (accumulate & MS_ACC_GRAD) != 0,
                         want_tilt_grad ? L.tilt_grad.p : nullptr, (accumulate & MS_ACC_TILT_GRAD) != 0, c->stream));
   if (energies3) {
@@ -1094,10 +1101,10 @@ int ms_ctx_leaflet_gradient_norm2(ms_ctx* c, int32_t leaflet, double* norm2) {
   ms_ctx::Leaflet& L = c->leaflet[leaflet];
   if (!L.tilt_grad.p && c->nv > 0) return fail(-4, "no tilt gradient exists for this leaflet (ms_ctx_eval_leaflet)");
   if (int rc = c->d_rowsq.ensure(size_t(c->nv) + 1)) return rc;
-  constexpr size_t kBlock = 1 + ms::kSumBlocks;  // per leaflet and kind (0 = |g|^2, 1 = r.z): result + scratch
-  if (int rc = c->d_norm_out.ensure(6 * kBlock)) return rc;
-  double* out = c->d_norm_out.p + size_t(2 * leaflet) * kBlock;
-  CU(ms::launch_masked_norm2(c->nv, L.tilt_grad.p, L.has_fixed ? L.fixed.p : nullptr, c->d_rowsq.p, out, c->stream));
+  if (int rc = ensure_leaflet_results(c)) return rc;
+  double* out = c->d_lf_e.p + 5 * size_t(leaflet) + 3;
+  CU(ms::launch_masked_norm2(c->nv, L.tilt_grad.p, L.has_fixed ? L.fixed.p : nullptr, c->d_rowsq.p, out,
+                             c->d_lf_e.p + 16, c->stream));
   if (norm2) {
     CU(cudaMemcpyAsync(norm2, out, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -1108,17 +1115,8 @@ int ms_ctx_leaflet_gradient_norm2(ms_ctx* c, int32_t leaflet, double* norm2) {
 int ms_ctx_leaflet_results(ms_ctx* c, double* out15) {
   if (int rc = check_ctx(c, true)) return rc;
   if (!out15) return fail(-1, "null argument");
-  for (int k = 0; k < 15; ++k) out15[k] = 0.0;
-  constexpr size_t kLfResult = 3 + 3 * ms::kSumBlocks, kBlock = 1 + ms::kSumBlocks;
-  for (int l = 0; l < 3; ++l) {
-    if (c->d_lf_e.p)
-      CU(cudaMemcpyAsync(out15 + 5 * l, c->d_lf_e.p + size_t(l) * kLfResult, 3 * sizeof(double), cudaMemcpyDeviceToHost,
-                         c->stream));
-    if (c->d_norm_out.p)
-      for (int k = 0; k < 2; ++k)
-        CU(cudaMemcpyAsync(out15 + 5 * l + 3 + k, c->d_norm_out.p + size_t(2 * l + k) * kBlock, sizeof(double),
-                           cudaMemcpyDeviceToHost, c->stream));
-  }
+  if (int rc = ensure_leaflet_results(c)) return rc;
+  CU(cudaMemcpyAsync(out15, c->d_lf_e.p, 15 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return 0;
 }
@@ -1161,10 +1159,10 @@ int ms_ctx_leaflet_rz(ms_ctx* c, int32_t leaflet, int32_t preconditioned, double
   if (int rc = cg_ready(c, leaflet, preconditioned)) return rc;
   ms_ctx::Leaflet& L = c->leaflet[leaflet];
   if (int rc = c->d_rowsq.ensure(size_t(c->nv) + 1)) return rc;
-  constexpr size_t kBlock = 1 + ms::kSumBlocks;
-  if (int rc = c->d_norm_out.ensure(6 * kBlock)) return rc;
-  double* out = c->d_norm_out.p + size_t(2 * leaflet + 1) * kBlock;
-  CU(ms::launch_rz(c->nv, L.tilt_grad.p, preconditioned ? L.minv.p : nullptr, c->d_rowsq.p, out, c->stream));
+  if (int rc = ensure_leaflet_results(c)) return rc;
+  double* out = c->d_lf_e.p + 5 * size_t(leaflet) + 4;
+  CU(ms::launch_rz(c->nv, L.tilt_grad.p, preconditioned ? L.minv.p : nullptr, c->d_rowsq.p, out, c->d_lf_e.p + 16,
+                   c->stream));
   if (rz) {
     CU(cudaMemcpyAsync(rz, out, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));

@@ -1454,7 +1454,7 @@ cudaError_t launch_bt_finalize(const double* e_bt, double* scalars, cudaStream_t
 
 cudaError_t launch_leaflet(const LeafletMesh& m, bool with_bt, bool with_tilt, bool with_smooth, double* corner,
                            double* vbuf, double* corner_shape, double* corner_tilt, double* facet_e, double* e_out3,
-                           double* grad,
+                           double* sum_scratch, double* grad,
                            bool accumulate_grad, double* tilt_grad, bool accumulate_tilt_grad, cudaStream_t st) {
   if (with_bt) {
     if (m.nf > 0) k_lf_facet_a<<<blocks_for(m.nf, 128), 128, 0, st>>>(m, corner);
@@ -1465,7 +1465,7 @@ cudaError_t launch_leaflet(const LeafletMesh& m, bool with_bt, bool with_tilt, b
                                                         grad ? corner_shape : nullptr, tilt_grad ? corner_tilt : nullptr,
                                                         facet_e);
   for (int k = 0; k < 3; ++k)
-    sum_fixed_order(facet_e + k * size_t(m.nf), m.nf, 1.0, e_out3 + k, e_out3 + 3 + k * kSumBlocks, st);
+    sum_fixed_order(facet_e + k * size_t(m.nf), m.nf, 1.0, e_out3 + k, sum_scratch + k * kSumBlocks, st);
   if (m.nv > 0 && grad)
     k_gather<<<blocks_for(m.nv, 128), 128, 0, st>>>(m.nv, m.csr_ptr, m.csr_idx, corner_shape, 3, 0, 3, grad, 3,
                                                      accumulate_grad ? 1 : 0);
@@ -1524,10 +1524,10 @@ cudaError_t launch_tilt_trial(int64_t nv, const double* t, const double* g, cons
   return cudaGetLastError();
 }
 
-cudaError_t launch_masked_norm2(int64_t nv, double* g, const uint8_t* fixed, double* rowsq, double* out /*1 + kSumBlocks*/,
-                                cudaStream_t st) {
+cudaError_t launch_masked_norm2(int64_t nv, double* g, const uint8_t* fixed, double* rowsq, double* out,
+                                double* sum_scratch /* kSumBlocks */, cudaStream_t st) {
   if (nv > 0) k_masked_row_norm2<<<blocks_for(nv, 256), 256, 0, st>>>(nv, g, fixed, rowsq);
-  sum_fixed_order(rowsq, nv, 1.0, out, out + 1, st);
+  sum_fixed_order(rowsq, nv, 1.0, out, sum_scratch, st);
   return cudaGetLastError();
 }
 
@@ -1537,10 +1537,10 @@ cudaError_t launch_leaflet_jacobi(const LeafletMesh& m, bool use_keep, double k_
   return cudaGetLastError();
 }
 
-cudaError_t launch_rz(int64_t nv, const double* g, const double* minv, double* rows, double* out /*1 + kSumBlocks*/,
-                      cudaStream_t st) {
+cudaError_t launch_rz(int64_t nv, const double* g, const double* minv, double* rows, double* out,
+                      double* sum_scratch /* kSumBlocks */, cudaStream_t st) {
   if (nv > 0) k_rz_rows<<<blocks_for(nv, 256), 256, 0, st>>>(nv, g, minv, rows);
-  sum_fixed_order(rows, nv, 1.0, out, out + 1, st);
+  sum_fixed_order(rows, nv, 1.0, out, sum_scratch, st);
   return cudaGetLastError();
 }
 

@@ -165,10 +165,10 @@ cudaError_t launch_bt_tilt_gather(const BtMesh& m, const double* corner3, double
 cudaError_t launch_bt_finalize(const double* e_bt, double* scalars, cudaStream_t st);
 
 // --- leaflet tilt modules (ms_leaflet.cuh).  corner: 27*nf doubles, vbuf: 5*nv, corner_shape / corner_tilt:
-// 9*nf each, facet_e: 3*nf, e_out3: {E_bending_tilt, E_tilt, E_tilt_smoothness} followed by 3*kSumBlocks doubles of scratch.  grad / tilt_grad may be null. ---
+// 9*nf each, facet_e: 3*nf, e_out3: {E_bending_tilt, E_tilt, E_tilt_smoothness}, sum_scratch: 3*kSumBlocks doubles.  grad / tilt_grad may be null. ---
 cudaError_t launch_leaflet(const LeafletMesh& m, bool with_bt, bool with_tilt, bool with_smooth, double* corner,
                            double* vbuf, double* corner_shape, double* corner_tilt, double* facet_e, double* e_out3,
-                           double* grad,
+                           double* sum_scratch, double* grad,
                            bool accumulate_grad, double* tilt_grad, bool accumulate_tilt_grad, cudaStream_t st);
 
 // small meshes: the same evaluation as ONE cooperative launch (block_e: 3 * max_blocks doubles; ticket: one zeroed
@@ -199,9 +199,11 @@ cudaError_t launch_tilt_trial(int64_t nv, const double* t, const double* g, cons
                               double step, double* trial, cudaStream_t st);
 cudaError_t launch_leaflet_jacobi(const LeafletMesh& m, bool use_keep, double k_smooth, const uint8_t* fixed, double* minv,
                                   cudaStream_t st);
-cudaError_t launch_rz(int64_t nv, const double* g, const double* minv, double* rows, double* out, cudaStream_t st);
+cudaError_t launch_rz(int64_t nv, const double* g, const double* minv, double* rows, double* out, double* sum_scratch,
+                      cudaStream_t st);
 cudaError_t launch_tilt_cg_direction(int64_t nv, const double* g, const double* minv, double beta, bool restart, double* dir,
                                      cudaStream_t st);
-cudaError_t launch_masked_norm2(int64_t nv, double* g, const uint8_t* fixed, double* rowsq, double* out, cudaStream_t st);
+cudaError_t launch_masked_norm2(int64_t nv, double* g, const uint8_t* fixed, double* rowsq, double* out,
+                                double* sum_scratch, cudaStream_t st);
 
 }  // namespace ms
