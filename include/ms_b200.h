@@ -235,6 +235,11 @@ MS_API int ms_ctx_leaflet_project_tilts(ms_ctx* ctx, int32_t leaflet);
 /* zero the fixed rows of MS_ARR_TILT_GRAD_IN / _OUT and return the sum of squares of the rest (:856-871);
  * norm2 may be NULL (result read later through ms_ctx_leaflet_results) */
 MS_API int ms_ctx_leaflet_gradient_norm2(ms_ctx* ctx, int32_t leaflet, double* norm2);
+/* Inner AND outer leaflet in one call (on meshes up to 32 768 facets: one cooperative launch for both); results
+ * stay on the device (ms_ctx_leaflet_results).  The shape gradient is the inner leaflet's plus the outer one's,
+ * bitwise what two ms_ctx_eval_leaflet calls (the second with MS_ACC_GRAD) leave. */
+MS_API int ms_ctx_eval_leaflet_pair(ms_ctx* ctx, uint32_t modules, int32_t want_grad, int32_t want_tilt_grad,
+                                    uint32_t accumulate, int32_t use_trial);
 /* Batched read-back for loops that evaluate several leaflets per iteration: ms_ctx_eval_leaflet (energies3 ==
  * NULL), ms_ctx_leaflet_gradient_norm2 (norm2 == NULL) and ms_ctx_leaflet_rz (rz == NULL) leave their results on the
  * device; this call synchronises ONCE and returns, per leaflet slot l = 0..2, out15[5 l + {0,1,2}] = the three

@@ -142,6 +142,7 @@ SIGNATURES = {
     "ms_ctx_update_vertex_normals": (ctypes.c_int, [_V]),
     "ms_ctx_leaflet_project_tilts": (ctypes.c_int, [_V, _i32]),
     "ms_ctx_leaflet_gradient_norm2": (ctypes.c_int, [_V, _i32, _D]),
+    "ms_ctx_eval_leaflet_pair": (ctypes.c_int, [_V, ctypes.c_uint32, _i32, _i32, ctypes.c_uint32, _i32]),
     "ms_ctx_leaflet_results": (ctypes.c_int, [_V, _D]),
     "ms_ctx_leaflet_make_trial": (ctypes.c_int, [_V, _i32, _f64, _i32]),
     "ms_ctx_leaflet_build_preconditioner": (ctypes.c_int, [_V, _i32, _f64, _i32]),

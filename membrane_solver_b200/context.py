@@ -235,6 +235,12 @@ class DeviceMesh:
         L.check(self._lib.ms_ctx_leaflet_gradient_norm2(self._h, int(leaflet), L.dptr(out)))
         return float(out[0])
 
+    def eval_leaflet_pair(self, modules: int, *, want_grad: bool = False, want_tilt_grad: bool = True,
+                          accumulate: int = 0, use_trial: bool = False) -> None:
+        """Inner and outer leaflet together (one launch on small meshes); read with ``leaflet_results()``."""
+        L.check(self._lib.ms_ctx_eval_leaflet_pair(self._h, int(modules), int(bool(want_grad)), int(bool(want_tilt_grad)),
+                                                   int(accumulate), int(bool(use_trial))))
+
     def leaflet_results(self) -> np.ndarray:
         """One synchronisation for everything the leaflet calls left on the device: rows = leaflet slots,
         columns = E_bending_tilt, E_tilt, E_tilt_smoothness, |g|^2, r.z."""

@@ -126,6 +126,7 @@ struct ms_ctx {
     int32_t consistent_u = 0;
   } leaflet[3];  // inner leaflet, outer leaflet, single tilt field
   DevBuf<double> d_lf_corner, d_lf_vbuf, d_lf_shape, d_lf_tilt, d_lf_facet_e, d_lf_e;
+  DevBuf<double> d_lf_corner2, d_lf_vbuf2, d_lf_shape2, d_lf_tilt2;  // second leaflet of a paired evaluation
   DevBuf<double> d_vnormals, d_rowsq, d_norm_out, d_lf_block_e;
   DevBuf<unsigned long long> d_lf_ticket;
   unsigned long long lf_ticket_base = 0;
@@ -1035,7 +1036,7 @@ int ms_ctx_eval_leaflet(ms_ctx* c, int32_t leaflet, uint32_t modules, int32_t wa
       if (int rc = c->d_lf_ticket.ensure(1)) return rc;
       CU(cudaMemset(c->d_lf_ticket.p, 0, sizeof(unsigned long long)));
       c->lf_ticket_base = 0;
-      if (int rc = c->d_lf_block_e.ensure(3 * ms::kLfFusedMaxBlocks)) return rc;
+      if (int rc = c->d_lf_block_e.ensure(6 * ms::kLfFusedMaxBlocks)) return rc;
     }
     cudaError_t e = ms::launch_leaflet_fused(
         m, (modules & MS_MOD_BENDING_TILT) != 0, (modules & MS_MOD_TILT) != 0, (modules & MS_MOD_TILT_SMOOTHNESS) != 0,
@@ -1110,6 +1111,63 @@ int ms_ctx_leaflet_gradient_norm2(ms_ctx* c, int32_t leaflet, double* norm2) {
     CU(cudaStreamSynchronize(c->stream));
   }
   return 0;
+}
+
+int ms_ctx_eval_leaflet_pair(ms_ctx* c, uint32_t modules, int32_t want_grad, int32_t want_tilt_grad, uint32_t accumulate,
+                             int32_t use_trial) {
+  if (int rc = check_ctx(c, true)) return rc;
+  ms_ctx::Leaflet& A = c->leaflet[0];
+  ms_ctx::Leaflet& B = c->leaflet[1];
+  static const bool fused_off = std::getenv("MS_LEAFLET_NO_FUSE") != nullptr;
+  const bool small = c->nf <= ms::kLfFusedMaxItems / 2 && c->nv <= ms::kLfFusedMaxItems / 2 && c->nf > 0;
+  if (!fused_off && c->lf_fused_ok && small && A.set && B.set && A.tilts.p && B.tilts.p &&
+      !(modules & ~uint32_t(MS_MOD_TILT | MS_MOD_BENDING_TILT | MS_MOD_TILT_SMOOTHNESS)) &&
+      !(use_trial && !c->d_trial.p)) {
+    if (want_tilt_grad) {
+      if (int rc = ensure_array(c, MS_ARR_TILT_GRAD_IN)) return rc;
+      if (int rc = ensure_array(c, MS_ARR_TILT_GRAD_OUT)) return rc;
+    }
+    ms::BtMesh bm;
+    if (int rc = bt_prepare(c, bm)) return rc;
+    const size_t nv = size_t(c->nv), nf = size_t(c->nf);
+    if (int rc = c->d_lf_corner.ensure(3 * ms::kLfCornerA * nf + 1)) return rc;
+    if (int rc = c->d_lf_vbuf.ensure(ms::kLfVertex * nv + 1)) return rc;
+    if (int rc = c->d_lf_shape.ensure(9 * nf + 1)) return rc;
+    if (int rc = c->d_lf_tilt.ensure(9 * nf + 1)) return rc;
+    if (int rc = c->d_lf_corner2.ensure(3 * ms::kLfCornerA * nf + 1)) return rc;
+    if (int rc = c->d_lf_vbuf2.ensure(ms::kLfVertex * nv + 1)) return rc;
+    if (int rc = c->d_lf_shape2.ensure(9 * nf + 1)) return rc;
+    if (int rc = c->d_lf_tilt2.ensure(9 * nf + 1)) return rc;
+    if (int rc = ensure_leaflet_results(c)) return rc;
+    if (!c->d_lf_ticket.p) {
+      if (int rc = c->d_lf_ticket.ensure(1)) return rc;
+      CU(cudaMemset(c->d_lf_ticket.p, 0, sizeof(unsigned long long)));
+      c->lf_ticket_base = 0;
+    }
+    if (int rc = c->d_lf_block_e.ensure(6 * ms::kLfFusedMaxBlocks)) return rc;
+    ms::LeafletMesh m0, m1;
+    fill_leaflet_mesh(c, A, use_trial != 0, m0);
+    fill_leaflet_mesh(c, B, use_trial != 0, m1);
+    double* const corner[2] = {c->d_lf_corner.p, c->d_lf_corner2.p};
+    double* const vbuf[2] = {c->d_lf_vbuf.p, c->d_lf_vbuf2.p};
+    double* const shape[2] = {c->d_lf_shape.p, c->d_lf_shape2.p};
+    double* const tilt[2] = {c->d_lf_tilt.p, c->d_lf_tilt2.p};
+    double* const e_out[2] = {c->d_lf_e.p, c->d_lf_e.p + 5};
+    double* const tg[2] = {want_tilt_grad ? A.tilt_grad.p : nullptr, want_tilt_grad ? B.tilt_grad.p : nullptr};
+    cudaError_t e = ms::launch_leaflet_fused_pair(
+        m0, m1, (modules & MS_MOD_BENDING_TILT) != 0, (modules & MS_MOD_TILT) != 0, (modules & MS_MOD_TILT_SMOOTHNESS) != 0,
+        corner, vbuf, shape, tilt, e_out, tg, c->d_lf_block_e.p, ms::kLfFusedMaxBlocks, want_grad ? c->d_grad.p : nullptr,
+        (accumulate & MS_ACC_GRAD) != 0, (accumulate & MS_ACC_TILT_GRAD) != 0, c->d_lf_ticket.p, &c->lf_ticket_base,
+        c->stream);
+    if (e == cudaSuccess) return 0;
+    cudaGetLastError();
+    c->lf_fused_ok = false;
+  }
+  // one leaflet after the other: the inner leaflet's shape gradient first, the outer one's added to it
+  if (int rc = ms_ctx_eval_leaflet(c, MS_LEAFLET_IN, modules, want_grad, want_tilt_grad, accumulate, use_trial, nullptr))
+    return rc;
+  return ms_ctx_eval_leaflet(c, MS_LEAFLET_OUT, modules, want_grad, want_tilt_grad,
+                             accumulate | (want_grad ? MS_ACC_GRAD : 0u), use_trial, nullptr);
 }
 
 int ms_ctx_leaflet_results(ms_ctx* c, double* out15) {

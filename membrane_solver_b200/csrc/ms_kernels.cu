@@ -935,6 +935,95 @@ __global__ void __launch_bounds__(128) k_lf_fused(LeafletMesh m, int with_bt, in
   }
 }
 
+// Both leaflets of a small mesh in ONE cooperative launch: the work items of the two leaflets share every phase
+// (item i < n belongs to the inner leaflet, i >= n to the outer one), so a tilt relaxation iteration costs one
+// launch instead of two.  Same per-item code and the same gather order as k_lf_fused: the gradients are bitwise
+// those of two separate evaluations (inner first, outer accumulated on top).
+struct LfPairBuffers {
+  double* corner[2];
+  double* vbuf[2];
+  double* shape[2];
+  double* tilt[2];
+  double* e_out3[2];
+  double* tilt_grad[2];
+};
+
+__global__ void __launch_bounds__(128) k_lf_fused_pair(LeafletMesh m0, LeafletMesh m1, LfPairBuffers b, int with_bt,
+                                                       int with_tilt, int with_smooth, double* block_e /* 6 * gridDim.x */,
+                                                       double* grad, int accumulate_grad, int accumulate_tilt_grad,
+                                                       unsigned long long* ticket, unsigned long long base) {
+  __shared__ double red[32 * 6];
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  const int nf = m0.nf, nv = m0.nv;
+  unsigned long long target = base;
+  if (with_bt) {
+    for (int i = tid; i < 2 * nf; i += stride) {
+      const int l = i >= nf;
+      lf_facet_a(l ? m1 : m0, i - l * nf, b.corner[l]);
+    }
+    lf_grid_barrier(ticket, target += gridDim.x);
+    for (int i = tid; i < 2 * nv; i += stride) {
+      const int l = i >= nv;
+      lf_vertex(l ? m1 : m0, i - l * nv, b.corner[l], b.vbuf[l]);
+    }
+    lf_grid_barrier(ticket, target += gridDim.x);
+  }
+  double e[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  for (int i = tid; i < 2 * nf; i += stride) {
+    const int l = i >= nf;
+    const LfEnergies r = lf_facet_b(l ? m1 : m0, i - l * nf, b.vbuf[l], with_bt != 0, with_tilt != 0, with_smooth != 0,
+                                    grad ? b.shape[l] : nullptr, b.tilt_grad[l] ? b.tilt[l] : nullptr);
+    e[3 * l] += r.e_bt;
+    e[3 * l + 1] += r.e_tilt;
+    e[3 * l + 2] += r.e_smooth;
+  }
+  block_sum<6>(e, red, 128, 0);
+  if (threadIdx.x == 0)
+    for (int k = 0; k < 6; ++k) block_e[6 * blockIdx.x + k] = e[k];
+  lf_grid_barrier(ticket, target += gridDim.x);
+  if (blockIdx.x == 0 && threadIdx.x < 6) {  // fixed order: block 0, 1, 2, ...
+    double acc = 0.0;
+    for (unsigned blk = 0; blk < gridDim.x; ++blk) acc += block_e[6 * blk + threadIdx.x];
+    b.e_out3[threadIdx.x / 3][threadIdx.x % 3] = acc;
+  }
+  for (int i = tid; i < 2 * nv; i += stride) {  // tilt gradients: one array per leaflet
+    const int l = i >= nv, v = i - l * nv;
+    double* out = b.tilt_grad[l];
+    if (!out) continue;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    for (int j = m0.csr_ptr[v]; j < m0.csr_ptr[v + 1]; ++j) {
+      const double* q = b.tilt[l] + 3 * size_t(m0.csr_idx[j]);
+      a0 += q[0];
+      a1 += q[1];
+      a2 += q[2];
+    }
+    double* o = out + 3 * size_t(v);
+    o[0] = accumulate_tilt_grad ? o[0] + a0 : a0;
+    o[1] = accumulate_tilt_grad ? o[1] + a1 : a1;
+    o[2] = accumulate_tilt_grad ? o[2] + a2 : a2;
+  }
+  if (grad)
+    for (int v = tid; v < nv; v += stride) {  // shape gradient: one array, inner leaflet first, outer on top
+      double* o = grad + 3 * size_t(v);
+      double g0 = accumulate_grad ? o[0] : 0.0, g1 = accumulate_grad ? o[1] : 0.0, g2 = accumulate_grad ? o[2] : 0.0;
+      for (int l = 0; l < 2; ++l) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        for (int j = m0.csr_ptr[v]; j < m0.csr_ptr[v + 1]; ++j) {
+          const double* q = b.shape[l] + 3 * size_t(m0.csr_idx[j]);
+          a0 += q[0];
+          a1 += q[1];
+          a2 += q[2];
+        }
+        g0 = (l == 0 && !accumulate_grad) ? a0 : g0 + a0;
+        g1 = (l == 0 && !accumulate_grad) ? a1 : g1 + a1;
+        g2 = (l == 0 && !accumulate_grad) ? a2 : g2 + a2;
+      }
+      o[0] = g0;
+      o[1] = g1;
+      o[2] = g2;
+    }
+}
+
 // ---- leaflet tilt relaxation helpers (runtime/steppers/tilt_relaxation.py:630-668,894-955) ----
 // unit area-weighted vertex normals (Mesh.vertex_normals, geometry/triangle_ops.py:55-72): fixed-order gather
 __global__ void __launch_bounds__(128) k_vertex_normals(int32_t nv, const int32_t* __restrict__ tri,
@@ -1503,6 +1592,46 @@ cudaError_t launch_leaflet_fused(const LeafletMesh& m, bool with_bt, bool with_t
   void* args[] = {&mm, &bt, &tl, &sm, &corner, &vbuf, &corner_shape, &corner_tilt, &block_e, &e_out3, &grad, &ag,
                   &tilt_grad, &at, &ticket, &base};
   cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_lf_fused), dim3(blocks), dim3(128), args, 0, st);
+  if (e == cudaSuccess) *ticket_base = base + (unsigned long long)(blocks) * (with_bt ? 3ull : 1ull);
+  return e;
+}
+
+// Inner and outer leaflet of a small mesh in one cooperative launch (see k_lf_fused_pair); the arrays of index 0
+// belong to m0, of index 1 to m1.  cudaErrorNotSupported -> evaluate the leaflets one after the other.
+cudaError_t launch_leaflet_fused_pair(const LeafletMesh& m0, const LeafletMesh& m1, bool with_bt, bool with_tilt,
+                                      bool with_smooth, double* const corner[2], double* const vbuf[2],
+                                      double* const shape[2], double* const tilt[2], double* const e_out3[2],
+                                      double* const tilt_grad[2], double* block_e, int max_blocks, double* grad,
+                                      bool accumulate_grad, bool accumulate_tilt_grad, unsigned long long* ticket,
+                                      unsigned long long* ticket_base, cudaStream_t st) {
+  static int resident = -1;
+  if (resident < 0) {
+    int dev = 0, coop = 0, per_sm = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lf_fused_pair, 128, 0);
+    resident = coop ? per_sm * sms : 0;
+  }
+  int blocks = blocks_for(2 * int64_t(m0.nf > m0.nv ? m0.nf : m0.nv), 128);
+  if (blocks > max_blocks) blocks = max_blocks;
+  if (blocks > resident) blocks = resident;
+  if (blocks <= 0) return cudaErrorNotSupported;
+  LeafletMesh a = m0, b = m1;
+  LfPairBuffers buf;
+  for (int l = 0; l < 2; ++l) {
+    buf.corner[l] = corner[l];
+    buf.vbuf[l] = vbuf[l];
+    buf.shape[l] = shape[l];
+    buf.tilt[l] = tilt[l];
+    buf.e_out3[l] = e_out3[l];
+    buf.tilt_grad[l] = tilt_grad[l];
+  }
+  int bt = with_bt ? 1 : 0, tl = with_tilt ? 1 : 0, sm = with_smooth ? 1 : 0, ag = accumulate_grad ? 1 : 0,
+      at = accumulate_tilt_grad ? 1 : 0;
+  unsigned long long base = *ticket_base;
+  void* args[] = {&a, &b, &buf, &bt, &tl, &sm, &block_e, &grad, &ag, &at, &ticket, &base};
+  cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_lf_fused_pair), dim3(blocks), dim3(128), args, 0, st);
   if (e == cudaSuccess) *ticket_base = base + (unsigned long long)(blocks) * (with_bt ? 3ull : 1ull);
   return e;
 }

@@ -178,6 +178,12 @@ cudaError_t launch_leaflet_fused(const LeafletMesh& m, bool with_bt, bool with_t
                                  double* e_out3, double* grad, bool accumulate_grad, double* tilt_grad,
                                  bool accumulate_tilt_grad, unsigned long long* ticket, unsigned long long* ticket_base,
                                  cudaStream_t st);
+cudaError_t launch_leaflet_fused_pair(const LeafletMesh& m0, const LeafletMesh& m1, bool with_bt, bool with_tilt,
+                                      bool with_smooth, double* const corner[2], double* const vbuf[2],
+                                      double* const shape[2], double* const tilt[2], double* const e_out3[2],
+                                      double* const tilt_grad[2], double* block_e /* 6 * max_blocks */, int max_blocks,
+                                      double* grad, bool accumulate_grad, bool accumulate_tilt_grad,
+                                      unsigned long long* ticket, unsigned long long* ticket_base, cudaStream_t st);
 constexpr int kLfFusedMaxBlocks = 512;
 constexpr int kLfFusedMaxItems = 1 << 16;  // facets / vertices up to which the single-launch variant is used
 

@@ -35,14 +35,20 @@ class DeviceTiltRelaxer:
 
     def _energy(self, want_tilt_grad: bool) -> float:
         """Both leaflets are launched back to back; ONE synchronisation brings their energies."""
-        for name in self.leaflets:
-            self.dm.eval_leaflet(_WHICH[name], self.modules, want_grad=False, want_tilt_grad=want_tilt_grad, read=False)
+        self._launch(want_tilt_grad)
         res = self.dm.leaflet_results()
         return float(sum(res[_WHICH[name], :3].sum() for name in self.leaflets))
 
-    def _energy_and_gradient_norm(self) -> tuple[float, float]:
+    def _launch(self, want_tilt_grad: bool) -> None:
+        if tuple(self.leaflets) == ("in", "out"):       # both leaflets: one call (one launch on small meshes)
+            self.dm.eval_leaflet_pair(self.modules, want_grad=False, want_tilt_grad=want_tilt_grad)
+            return
         for name in self.leaflets:
-            self.dm.eval_leaflet(_WHICH[name], self.modules, want_grad=False, want_tilt_grad=True, read=False)
+            self.dm.eval_leaflet(_WHICH[name], self.modules, want_grad=False, want_tilt_grad=want_tilt_grad, read=False)
+
+    def _energy_and_gradient_norm(self) -> tuple[float, float]:
+        self._launch(True)
+        for name in self.leaflets:
             self.dm.leaflet_gradient_norm2(_WHICH[name], read=False)
         res = self.dm.leaflet_results()
         e = float(sum(res[_WHICH[name], :3].sum() for name in self.leaflets))

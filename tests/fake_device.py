@@ -176,6 +176,12 @@ class FakeDeviceMesh:
         a, _ = self._lf_arrays(leaflet)
         self.arrays[a], self.leaflet_trial[int(leaflet)] = self.leaflet_trial[int(leaflet)], self.arrays[a]
 
+    def eval_leaflet_pair(self, modules, *, want_grad=False, want_tilt_grad=True, accumulate=0, use_trial=False):
+        self.eval_leaflet(L.LEAFLET_IN, modules, want_grad=want_grad, want_tilt_grad=want_tilt_grad, accumulate=accumulate,
+                          use_trial=use_trial, read=False)
+        self.eval_leaflet(L.LEAFLET_OUT, modules, want_grad=want_grad, want_tilt_grad=want_tilt_grad,
+                          accumulate=accumulate | (L.ACC_GRAD if want_grad else 0), use_trial=use_trial, read=False)
+
     def leaflet_results(self):
         return np.array(self.__dict__.setdefault("lf_results", np.zeros((3, 5))))
 

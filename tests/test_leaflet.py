@@ -593,3 +593,46 @@ def test_tilt_relaxer_stop_conditions_on_emulated_device(relax_gold, solver):
     # only the tangent projection touched the fields
     n = dm.vnormals
     assert np.allclose(dm.download(L.ARR_TILTS_IN), before - (before * n).sum(axis=1)[:, None] * n, atol=1e-15)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("state", ["r1", "r1c"])
+def test_device_leaflet_pair_equals_two_evaluations(gold, state):
+    """Both leaflets in one call (one cooperative launch on this mesh): gradients bitwise those of two evaluations,
+    energies equal to rounding (different grouping of the block sums), results read back with one copy."""
+    from membrane_solver_b200 import _lib as L
+    from membrane_solver_b200.context import DeviceMesh
+
+    ins = {leaf: _inputs(gold, state, leaf) for leaf in LEAFLETS}
+    i = ins["in"]
+    dm = DeviceMesh(0)
+    dm.set_topology(i["pos"].shape[0], i["tri"], is_boundary=i["is_boundary"].astype(np.uint8))
+    dm.set_positions(i["pos"])
+    for leaf, which, arr in (("in", L.LEAFLET_IN, L.ARR_TILTS_IN), ("out", L.LEAFLET_OUT, L.ARR_TILTS_OUT)):
+        d = ins[leaf]
+        dm.set_leaflet(which, div_sign=d["sign"], kappa=d["kappa"], c0=d["c0"], k_tilt=d["k_tilt"], k_smooth=d["k_smooth"],
+                       facet_keep=d["keep"], interior=d["interior"], base_zero=d["base_zero"], consistent=d["consistent"])
+        dm.upload(arr, d["tilts"])
+    mods = L.MOD_TILT | L.MOD_BENDING_TILT | L.MOD_TILT_SMOOTHNESS
+    e_in = dm.eval_leaflet(L.LEAFLET_IN, mods)
+    e_out = dm.eval_leaflet(L.LEAFLET_OUT, mods, accumulate=L.ACC_GRAD)
+    want = (dm.download(L.ARR_GRAD), dm.download(L.ARR_TILT_GRAD_IN), dm.download(L.ARR_TILT_GRAD_OUT))
+    dm.upload(L.ARR_GRAD, np.full_like(i["pos"], 3.0))
+    dm.eval_leaflet_pair(mods, want_grad=True, want_tilt_grad=True)
+    res = dm.leaflet_results()
+    for k in range(3):
+        _close(res[L.LEAFLET_IN, k], e_in[k])
+        _close(res[L.LEAFLET_OUT, k], e_out[k])
+    got = (dm.download(L.ARR_GRAD), dm.download(L.ARR_TILT_GRAD_IN), dm.download(L.ARR_TILT_GRAD_OUT))
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+    # tilt-only: the shape gradient array is left alone; gradient norms join the same read-back
+    dm.eval_leaflet_pair(mods, want_grad=False, want_tilt_grad=True)
+    dm.leaflet_gradient_norm2(L.LEAFLET_IN, read=False)
+    dm.leaflet_gradient_norm2(L.LEAFLET_OUT, read=False)
+    res = dm.leaflet_results()
+    assert np.array_equal(dm.download(L.ARR_GRAD), want[0])
+    tgi = gold[f"{state}_in_tg_bt_tiltonly"] + gold[f"{state}_in_tg_tilt_tiltonly"] + gold[f"{state}_in_tg_smooth_tiltonly"]
+    assert rel_err(dm.download(L.ARR_TILT_GRAD_IN), tgi) <= TOL
+    assert abs(res[L.LEAFLET_IN, 3] - float((dm.download(L.ARR_TILT_GRAD_IN) ** 2).sum())) <= 1e-10 * res[L.LEAFLET_IN, 3]
+    dm.close()
