@@ -216,6 +216,8 @@ class EvaluationManager:
         if not groups:
             return energies
         st.dm.set_positions(pos)
+        if self._leaflet_pair_pass(st, LF, groups, tilts_in, tilts_out, tilt_in_grad_arr, tilt_out_grad_arr, energies):
+            return energies
         for leaflet, members in groups.items():
             tilts = tilts_in if leaflet == "in" else tilts_out
             out = tilt_in_grad_arr if leaflet == "in" else tilt_out_grad_arr
@@ -245,6 +247,45 @@ class EvaluationManager:
                 if out is not None:
                     out += scale * st.dm.download(LF.ARR_TILT_GRAD[leaflet])
         return energies
+
+    def _leaflet_pair_pass(self, st, LF, groups, tilts_in, tilts_out, grad_in, grad_out, energies) -> bool:
+        """Both leaflets carry the same modules with unit scales and one facet selection each: evaluate them with
+        ONE call (one cooperative launch on small meshes) and read all energies back with one copy."""
+        if set(groups) != {"in", "out"}:
+            return False
+        bits = {}
+        specs = {}
+        for leaflet, members in groups.items():
+            if any(scale != 1.0 for _, _, scale in members):
+                return False
+            spec = LF.selection(self.mesh, self.global_params, self.param_resolver, leaflet)
+            a, b = spec.get("keep_bt"), spec.get("keep_tilt")
+            if not ((a is None and b is None) or (a is not None and b is not None and np.array_equal(a, b))):
+                return False
+            specs[leaflet] = spec
+            bits[leaflet] = 0
+            for _, bit, _ in members:
+                bits[leaflet] |= bit
+        if bits["in"] != bits["out"]:
+            return False
+        for leaflet, members in groups.items():
+            for name, bit, _ in members:          # a module that contributes nothing (zero modulus) breaks the symmetry
+                if LF.configure(st, self.mesh, self.global_params, self.param_resolver, leaflet, bit) is None:
+                    return False
+            st.set_leaflet(leaflet, bits[leaflet], specs[leaflet], LF.SIGN[leaflet])
+            tilts = tilts_in if leaflet == "in" else tilts_out
+            st.dm.upload(LF.ARR_TILTS[leaflet], LF._leaflet_tilts(self.mesh, leaflet, tilts))
+        want_tg = grad_in is not None or grad_out is not None
+        st.dm.eval_leaflet_pair(bits["in"], want_grad=False, want_tilt_grad=want_tg)
+        res = st.dm.leaflet_results()
+        for leaflet, members in groups.items():
+            for name, bit, _ in members:
+                energies[name] = float(res[LF.WHICH[leaflet], LF.ENERGY_SLOT[bit]])
+        if grad_in is not None:
+            grad_in += st.dm.download(LF.ARR_TILT_GRAD["in"])
+        if grad_out is not None:
+            grad_out += st.dm.download(LF.ARR_TILT_GRAD["out"])
+        return True
 
     def _other_leaflet_energy(self, name, mod, *, positions, tilts_in, tilts_out, grad_arr, tilt_in_grad_arr=None,
                               tilt_out_grad_arr=None) -> float:
