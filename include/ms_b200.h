@@ -100,7 +100,7 @@ typedef struct ms_pack_info {
   int32_t max_owned, max_local, max_steps;
   int32_t max_events;  /* largest event-row count of a patch */
   int32_t teams;       /* teams of consumer warps per CTA the kernels run with on this mesh */
-  int32_t reserved;
+  int32_t max_words;   /* largest step-word count of a patch (steps + tail rows + restart rows) */
   int64_t n_lane_steps;    /* sum over patches of lanes x steps: step words streamed per pass */
   int64_t n_listed;        /* facet listings over all patches (ring facets counted per patch) */
   int64_t n_valid;         /* facets with all indices in range */

@@ -85,7 +85,7 @@ class PackInfo(ctypes.Structure):
         ("n_patches", ctypes.c_int32), ("threads", ctypes.c_int32),
         ("max_owned", ctypes.c_int32), ("max_local", ctypes.c_int32),
         ("max_steps", ctypes.c_int32), ("max_events", ctypes.c_int32),
-        ("teams", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("teams", ctypes.c_int32), ("max_words", ctypes.c_int32),
         ("n_lane_steps", ctypes.c_int64), ("n_listed", ctypes.c_int64),
         ("n_valid", ctypes.c_int64), ("n_halo", ctypes.c_int64),
         ("n_strips", ctypes.c_int64), ("n_pieces", ctypes.c_int64),

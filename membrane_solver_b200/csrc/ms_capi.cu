@@ -247,6 +247,7 @@ int fill_launch(ms_ctx* c, const ms_eval_opts* o, ms::PatchLaunch& a) {
   a.max_local = c->packed.max_local;
   a.max_events = c->packed.max_events;
   a.max_steps = c->packed.max_steps;
+  a.max_words = c->packed.max_words;
   // pass A also produces dV/dx when a gradient evaluation with bending follows
   a.volgrad_in_a = (o->want_grad && (o->modules & MS_MOD_VOLUME) && (o->modules & (MS_MOD_BENDING | MS_MOD_BENDING_TILT))) ? 1 : 0;
   if (o->use_trial) {
@@ -610,6 +611,7 @@ int ms_ctx_set_topology_partition(ms_ctx* c, int32_t nv, int32_t n_owned, int32_
     probe.max_owned = pk.max_owned;
     probe.max_local = pk.max_local;
     probe.max_events = pk.max_events;
+    probe.max_words = pk.max_words;
     probe.modules = MS_MOD_SURFACE | MS_MOD_BENDING | MS_MOD_VOLUME | MS_MOD_TILT;
     probe.volgrad = reinterpret_cast<double*>(1);  // worst case of the plans: every optional array present
     probe.seeds = reinterpret_cast<double*>(1);
@@ -629,7 +631,18 @@ int ms_ctx_set_topology_partition(ms_ctx* c, int32_t nv, int32_t n_owned, int32_
   const size_t step_pad = 4 * size_t(pk.params.threads);  // the lanes prefetch one restart pair past their last
   if (int rc = c->d_steps.ensure(pk.steps.size() + step_pad)) return rc;
   if (int rc = c->d_evt_ptr.ensure(pk.evt_ptr.size() + 8)) return rc;
-  CU(cudaMemcpy(c->d_patches.p, pk.patches.data(), np * sizeof(ms::PatchHeader), cudaMemcpyHostToDevice));
+  {  // sentinel header: closes the step-word range of the last patch
+    std::vector<ms::PatchHeader> hdr(pk.patches);
+    ms::PatchHeader end;
+    std::memset(&end, 0, sizeof(end));
+    end.v_lo = n_owned;
+    end.halo_off = int32_t(pk.halo_ids.size());
+    end.step_off = int64_t(pk.steps.size());
+    end.fac_off = int64_t(pk.recs.size());
+    end.evt_off = int32_t(pk.evt_ptr.size());
+    hdr.push_back(end);
+    CU(cudaMemcpy(c->d_patches.p, hdr.data(), hdr.size() * sizeof(ms::PatchHeader), cudaMemcpyHostToDevice));
+  }
   if (!pk.halo_ids.empty())
     CU(cudaMemcpy(c->d_halo.p, pk.halo_ids.data(), pk.halo_ids.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   if (!pk.recs.empty())
@@ -702,7 +715,7 @@ int ms_ctx_pack_info(const ms_ctx* c, ms_pack_info* info) {
   info->max_steps = pk.max_steps;
   info->max_events = pk.max_events;
   info->teams = c->teams;
-  info->reserved = 0;
+  info->max_words = pk.max_words;
   info->n_lane_steps = pk.n_lane_steps;
   info->n_listed = pk.n_listed;
   info->n_valid = pk.n_valid;

@@ -99,11 +99,6 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, unsigned parity
 __device__ __forceinline__ void named_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
-__device__ __forceinline__ uint32_t ldg_stream(const uint32_t* p) {  // step words: read once, keep them out of L1
-  uint32_t v;
-  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
-  return v;
-}
 
 // ---------------------------------------------------------------------------
 // Shared-memory plan (run-time sizes: the largest patch of the packed mesh).  A CTA holds
@@ -124,7 +119,7 @@ struct PlanFlags {
 
 struct Plan {
   // offsets inside one staging buffer
-  unsigned oPos, oSeed, oPtr, oBfl, oT2, oHdr, in_bytes;
+  unsigned oPos, oSeed, oPtr, oWords, oBfl, oT2, oHdr, in_bytes;
   // offsets inside one event buffer
   unsigned oEvA, oEvV, oEvG, oEvT, ev_bytes;
   // whole window
@@ -133,14 +128,15 @@ struct Plan {
 
 __host__ __device__ inline unsigned up16(unsigned x) { return (x + 15u) & ~15u; }
 
-__host__ __device__ inline Plan make_plan(const PlanFlags& f, int max_local, int max_owned, int max_events, int n_buf,
-                                          int n_teams, int n_warps) {
+__host__ __device__ inline Plan make_plan(const PlanFlags& f, int max_local, int max_owned, int max_events, int max_words,
+                                          int n_buf, int n_teams, int n_warps) {
   Plan p;
   const unsigned L = unsigned(max_local + 2), E = unsigned(max_events + 2);
   unsigned o = 0;
   p.oPos = o; o += up16(L * 24u);
   p.oSeed = o; if (f.seed) o += up16(L * 40u);
   p.oPtr = o; o += up16(unsigned(max_owned + 9) * 2u);
+  p.oWords = o; o += up16(unsigned(max_words) * 4u);
   p.oBfl = o; if (f.bfl) o += up16(L * 4u);
   p.oT2 = o; if (f.t2) o += up16(L * 8u);
   p.oHdr = o; o += 64u;
@@ -162,7 +158,8 @@ constexpr int kMaxBuffers = 6;
 
 // Area-weighted unit normal of owned vertex i of a patch, read from GLOBAL memory (rare path: flat interior
 // vertices only).  Same facet order as vertex_normal_scan.
-__device__ d3 vertex_normal_global(const PatchLaunch& a, const PatchHdrS& hs, const int32_t* ids, int i) {
+__device__ d3 vertex_normal_global(const PatchLaunch& a, const PatchHdrS& hs, int i) {
+  const int32_t* ids = a.halo_ids + hs.halo_off;
   const FacetRec* recs = a.recs + hs.fac_off;
   d3 n = make_d3(0, 0, 0);
   for (int k = 0; k < hs.n_fac; ++k) {
@@ -192,57 +189,55 @@ struct StepCtx {
   bool scalars_here;
 };
 
-// ---- pass A: one step on slot K ----
+// ---- pass A: one step on slot K.  `aux` walks the lane's restart rows. ----
 template <int K, bool BEND, bool VG>
-__device__ __forceinline__ void step_a(uint32_t w, const uint32_t*& aux, uint32_t& ax0, uint32_t& ax1, int lanes,
-                                       SlotA& s0, SlotA& s1, SlotA& s2, const LocalA& loc, const StepCtx& cx,
-                                       const double* gam_p, double* sums) {
+__device__ __forceinline__ void step_a(uint32_t w, const uint32_t*& aux, int lanes, SlotA& s0, SlotA& s1, SlotA& s2,
+                                       const LocalA& loc, const StepCtx& cx, const double* gam_p, double* sums) {
   if (w & STEP_RESTART) {
+    const uint32_t ax0 = aux[0], ax1 = aux[lanes];
+    aux += 2 * lanes;
     SlotA& n1 = pick<(K + 1) % 3>(s0, s1, s2);
     SlotA& n2 = pick<(K + 2) % 3>(s0, s1, s2);
     if (step_event(ax0) >= 0) slot_flush_a<BEND, VG>(n1, loc, step_event(ax0));
     slot_load_a(n1, loc, step_index(ax0));
     if (step_event(ax1) >= 0) slot_flush_a<BEND, VG>(n2, loc, step_event(ax1));
     slot_load_a(n2, loc, step_index(ax1));
-    aux += 2 * lanes;
-    ax0 = ldg_stream(aux);
-    ax1 = ldg_stream(aux + lanes);
   }
   SlotA& me = pick<K>(s0, s1, s2);
   if (step_event(w) >= 0) slot_flush_a<BEND, VG>(me, loc, step_event(w));
-  if (w & STEP_LOAD) slot_load_a(me, loc, step_index(w));
-  if (w & STEP_COMPUTE) {
+  if (w & STEP_COMPUTE) {  // every step that evaluates a facet also loads its slot (ms_pack.cpp); others are no-ops
+    slot_load_a<false>(me, loc, step_index(w));
     const double gam = gam_p ? *gam_p : cx.gamma_u;
-    step_compute_a<BEND, VG>(s0, s1, s2, w, gam, cx.modules, cx.k_tilt, sums);
+    step_compute_a<BEND, VG, K>(s0, s1, s2, w, gam, cx.modules, cx.k_tilt, sums);
   }
 }
 
 template <int K, bool BEND, bool VG, bool TILT>
-__device__ __forceinline__ void step_b(uint32_t w, const uint32_t*& aux, uint32_t& ax0, uint32_t& ax1, int lanes,
-                                       SlotB& s0, SlotB& s1, SlotB& s2, const LocalB& loc, const StepCtx& cx,
-                                       const double* gam_p, double* sums) {
+__device__ __forceinline__ void step_b(uint32_t w, const uint32_t*& aux, int lanes, SlotB& s0, SlotB& s1, SlotB& s2,
+                                       const LocalB& loc, const StepCtx& cx, const double* gam_p, double* sums) {
   if (w & STEP_RESTART) {
+    const uint32_t ax0 = aux[0], ax1 = aux[lanes];
+    aux += 2 * lanes;
     SlotB& n1 = pick<(K + 1) % 3>(s0, s1, s2);
     SlotB& n2 = pick<(K + 2) % 3>(s0, s1, s2);
     if (step_event(ax0) >= 0) slot_flush_b<VG, TILT>(n1, loc, step_event(ax0));
     slot_load_b<BEND>(n1, loc, step_index(ax0));
     if (step_event(ax1) >= 0) slot_flush_b<VG, TILT>(n2, loc, step_event(ax1));
     slot_load_b<BEND>(n2, loc, step_index(ax1));
-    aux += 2 * lanes;
-    ax0 = ldg_stream(aux);
-    ax1 = ldg_stream(aux + lanes);
   }
   SlotB& me = pick<K>(s0, s1, s2);
   if (step_event(w) >= 0) slot_flush_b<VG, TILT>(me, loc, step_event(w));
-  if (w & STEP_LOAD) slot_load_b<BEND>(me, loc, step_index(w));
-  if (w & STEP_COMPUTE) {
+  if (w & STEP_COMPUTE) {  // every step that evaluates a facet also loads its slot (ms_pack.cpp); others are no-ops
+    slot_load_b<BEND, false>(me, loc, step_index(w));
     const double gam = gam_p ? *gam_p : cx.gamma_u;
-    step_compute_b<BEND, VG, TILT>(s0, s1, s2, w, gam, cx.modules, cx.flags, cx.k_tilt, cx.scalars_here, sums);
+    step_compute_b<BEND, VG, TILT, K>(s0, s1, s2, w, gam, cx.modules, cx.flags, cx.k_tilt, cx.scalars_here, sums);
   }
 }
 
-// The strip walk of one lane over one patch (device form of walk_lane, ms_patch_body.cuh): the step word of
-// the next step and the lane's next restart pair are always in flight while the current facet is evaluated.
+// The strip walk of one lane over one patch (device form of walk_lane, ms_patch_body.cuh).  `words` points at
+// the lane's column of the patch's step words in SHARED memory (staged by the producer with the rest of the
+// patch: the consumers never wait for global memory); n_steps is a multiple of 3 (ms_pack.cpp pads with no-op
+// rows).  The word of step s + 1 is read while step s is evaluated.
 template <bool BEND, bool VG>
 __device__ __forceinline__ void walk_a(const uint32_t* words, int lanes, int n_steps, const LocalA& loc, const StepCtx& cx,
                                        const double* gam, double* sums) {
@@ -251,27 +246,21 @@ __device__ __forceinline__ void walk_a(const uint32_t* words, int lanes, int n_s
   s0.bnd = s1.bnd = s2.bnd = 0;
   s0.t2 = s1.t2 = s2.t2 = 0.0;
   slot_clear_a(s0); slot_clear_a(s1); slot_clear_a(s2);
-  const uint32_t* aux = words + size_t(n_steps + 3) * size_t(lanes);
-  uint32_t ax0 = ldg_stream(aux), ax1 = ldg_stream(aux + lanes);
-  uint32_t w = ldg_stream(words);
+  const uint32_t* aux = words + (n_steps + 3) * lanes;
+  uint32_t w0 = words[0];
   for (int s = 0; s < n_steps; s += 3) {
-    uint32_t wn = ldg_stream(words + size_t(s + 1) * lanes);
-    step_a<0, BEND, VG>(w, aux, ax0, ax1, lanes, s0, s1, s2, loc, cx, gam ? gam + size_t(s) * lanes : nullptr, sums);
-    w = wn;
-    if (s + 1 < n_steps) {
-      wn = ldg_stream(words + size_t(s + 2) * lanes);
-      step_a<1, BEND, VG>(w, aux, ax0, ax1, lanes, s0, s1, s2, loc, cx, gam ? gam + size_t(s + 1) * lanes : nullptr, sums);
-      w = wn;
-    }
-    if (s + 2 < n_steps) {
-      wn = ldg_stream(words + size_t(s + 3) * lanes);
-      step_a<2, BEND, VG>(w, aux, ax0, ax1, lanes, s0, s1, s2, loc, cx, gam ? gam + size_t(s + 2) * lanes : nullptr, sums);
-      w = wn;
-    }
+    const uint32_t* row = words + s * lanes;
+    const double* g = gam ? gam + size_t(s) * lanes : nullptr;
+    const uint32_t w1 = row[lanes];
+    step_a<0, BEND, VG>(w0, aux, lanes, s0, s1, s2, loc, cx, g, sums);
+    const uint32_t w2 = row[2 * lanes];
+    step_a<1, BEND, VG>(w1, aux, lanes, s0, s1, s2, loc, cx, g ? g + lanes : nullptr, sums);
+    w0 = row[3 * lanes];
+    step_a<2, BEND, VG>(w2, aux, lanes, s0, s1, s2, loc, cx, g ? g + 2 * lanes : nullptr, sums);
   }
-  // tail rows: w holds row n_steps
-  const uint32_t t1 = ldg_stream(words + size_t(n_steps + 1) * lanes), t2 = ldg_stream(words + size_t(n_steps + 2) * lanes);
-  if (step_event(w) >= 0) slot_flush_a<BEND, VG>(s0, loc, step_event(w));
+  // tail rows: w0 holds row n_steps
+  const uint32_t t1 = words[(n_steps + 1) * lanes], t2 = words[(n_steps + 2) * lanes];
+  if (step_event(w0) >= 0) slot_flush_a<BEND, VG>(s0, loc, step_event(w0));
   if (step_event(t1) >= 0) slot_flush_a<BEND, VG>(s1, loc, step_event(t1));
   if (step_event(t2) >= 0) slot_flush_a<BEND, VG>(s2, loc, step_event(t2));
 }
@@ -286,26 +275,20 @@ __device__ __forceinline__ void walk_b(const uint32_t* words, int lanes, int n_s
   s0.bnd = s1.bnd = s2.bnd = 0;
   s0.t2 = s1.t2 = s2.t2 = 0.0;
   slot_clear_b(s0); slot_clear_b(s1); slot_clear_b(s2);
-  const uint32_t* aux = words + size_t(n_steps + 3) * size_t(lanes);
-  uint32_t ax0 = ldg_stream(aux), ax1 = ldg_stream(aux + lanes);
-  uint32_t w = ldg_stream(words);
+  const uint32_t* aux = words + (n_steps + 3) * lanes;
+  uint32_t w0 = words[0];
   for (int s = 0; s < n_steps; s += 3) {
-    uint32_t wn = ldg_stream(words + size_t(s + 1) * lanes);
-    step_b<0, BEND, VG, TILT>(w, aux, ax0, ax1, lanes, s0, s1, s2, loc, cx, gam ? gam + size_t(s) * lanes : nullptr, sums);
-    w = wn;
-    if (s + 1 < n_steps) {
-      wn = ldg_stream(words + size_t(s + 2) * lanes);
-      step_b<1, BEND, VG, TILT>(w, aux, ax0, ax1, lanes, s0, s1, s2, loc, cx, gam ? gam + size_t(s + 1) * lanes : nullptr, sums);
-      w = wn;
-    }
-    if (s + 2 < n_steps) {
-      wn = ldg_stream(words + size_t(s + 3) * lanes);
-      step_b<2, BEND, VG, TILT>(w, aux, ax0, ax1, lanes, s0, s1, s2, loc, cx, gam ? gam + size_t(s + 2) * lanes : nullptr, sums);
-      w = wn;
-    }
+    const uint32_t* row = words + s * lanes;
+    const double* g = gam ? gam + size_t(s) * lanes : nullptr;
+    const uint32_t w1 = row[lanes];
+    step_b<0, BEND, VG, TILT>(w0, aux, lanes, s0, s1, s2, loc, cx, g, sums);
+    const uint32_t w2 = row[2 * lanes];
+    step_b<1, BEND, VG, TILT>(w1, aux, lanes, s0, s1, s2, loc, cx, g ? g + lanes : nullptr, sums);
+    w0 = row[3 * lanes];
+    step_b<2, BEND, VG, TILT>(w2, aux, lanes, s0, s1, s2, loc, cx, g ? g + 2 * lanes : nullptr, sums);
   }
-  const uint32_t t1 = ldg_stream(words + size_t(n_steps + 1) * lanes), t2 = ldg_stream(words + size_t(n_steps + 2) * lanes);
-  if (step_event(w) >= 0) slot_flush_b<VG, TILT>(s0, loc, step_event(w));
+  const uint32_t t1 = words[(n_steps + 1) * lanes], t2 = words[(n_steps + 2) * lanes];
+  if (step_event(w0) >= 0) slot_flush_b<VG, TILT>(s0, loc, step_event(w0));
   if (step_event(t1) >= 0) slot_flush_b<VG, TILT>(s1, loc, step_event(t1));
   if (step_event(t2) >= 0) slot_flush_b<VG, TILT>(s2, loc, step_event(t2));
 }
@@ -332,7 +315,8 @@ __device__ __forceinline__ void walk_b(const uint32_t* words, int lanes, int n_s
 constexpr uint32_t kFastModules = MS_MOD_SURFACE | MS_MOD_BENDING | MS_MOD_VOLUME;
 
 template <int PASS, int KIND>
-__global__ void __launch_bounds__(kPatchThreads, 1) k_patch(PatchLaunch a, bool bending_b, bool scalars_here_arg) {
+__global__ void __launch_bounds__(kPatchThreads, 1) k_patch(const PatchLaunch a, const PlanFlags pf, const Plan pl, bool bending_b,
+                                                            bool scalars_here_arg) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x;
   const int lanes = a.threads;                 // lanes of one team
@@ -357,16 +341,7 @@ __global__ void __launch_bounds__(kPatchThreads, 1) k_patch(PatchLaunch a, bool 
                                  : (!do_bending && do_volume && a.volgrad != nullptr);
   const bool want_epi = PASS == 1 || do_bending;  // pass A without bending accumulates nothing
 
-  PlanFlags pf;
-  pf.seed = PASS == 1 && do_bending;
-  pf.bfl = has_boundary;
-  pf.t2 = do_tilt;
-  pf.evA = PASS == 0 && do_bending;
-  pf.evV = vg_here;
-  pf.evG = PASS == 1;
-  pf.evT = PASS == 1 && do_tilt;
-  const Plan pl = make_plan(pf, a.max_local, a.max_owned, a.max_events, n_buf, n_teams, n_cons / 32 + 1);
-
+  // pf / pl: the staging and event arrays of this launch and their offsets (computed by the host: plan_flags, make_plan)
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + pl.oBars);
   uint64_t* bar_empty = bar_full + n_buf;
   double* red = reinterpret_cast<double*>(smem + pl.oRed);
@@ -385,41 +360,60 @@ __global__ void __launch_bounds__(kPatchThreads, 1) k_patch(PatchLaunch a, bool 
 
   if (tid >= n_cons) {
     // =========================== producer warp ===========================
+    // Software pipelined by one patch: while the copies of patch j are in flight, the header and the halo
+    // ids of patch j + 1 are fetched into registers, so that a freed staging buffer is refilled after ONE
+    // memory latency (no header -> ids -> rows chain in front of the copies).
     const int lane = tid - n_cons;
+    constexpr int kIds = 10;  // halo ids per lane held in registers (320 per patch); more are read in place
+    auto patch_of = [&](int j) {
+      const int pidx = a.patch_begin + int(blockIdx.x) + j * int(gridDim.x);
+      return a.patch_list ? a.patch_list[pidx] : pidx;
+    };
+    PatchHeader h;
+    int64_t words_end = 0;
+    int32_t ids[kIds];
+    auto fetch = [&](int j) {
+      const int pid = patch_of(j);
+      h = a.patches[pid];
+      words_end = a.patches[pid + 1].step_off;  // a sentinel header closes the last patch
+      const int32_t* hsrc = a.halo_ids + h.halo_off;
+#pragma unroll
+      for (int q = 0; q < kIds; ++q) {
+        const int k = lane + 32 * q;
+        ids[q] = k < h.n_halo ? hsrc[k] : 0;
+      }
+    };
+    if (n_my > 0) fetch(0);
     for (int j = 0; j < n_my; ++j) {
       const int b = j % n_buf;
-      const int pidx = a.patch_begin + int(blockIdx.x) + j * int(gridDim.x);
-      const int pid = a.patch_list ? a.patch_list[pidx] : pidx;
       if (j >= n_buf) mbar_wait_relaxed(&bar_empty[b], unsigned((j / n_buf - 1) & 1));
-      const PatchHeader h = a.patches[pid];
       unsigned char* in = smem + size_t(b) * pl.in_bytes;
       double* pos = reinterpret_cast<double*>(in + pl.oPos);
       double* seed = reinterpret_cast<double*>(in + pl.oSeed);
-      const int Pn = h.n_owned;
+      const int Pn = h.n_owned, Hn = h.n_halo, v_lo = h.v_lo;
+      const int32_t* hsrc = a.halo_ids + h.halo_off;
       // rows [0, Pb) of the owned range move as bulk copies (16-byte aligned start, even row count)
-      const int Pb = (h.v_lo & 1) ? 0 : (Pn & ~1);
+      const int Pb = (v_lo & 1) ? 0 : (Pn & ~1);
       if (lane == 0) {
         PatchHdrS* hs = reinterpret_cast<PatchHdrS*>(in + pl.oHdr);
         hs->v_lo = h.v_lo; hs->n_owned = h.n_owned; hs->n_halo = h.n_halo; hs->n_steps = h.n_steps;
         hs->n_events = h.n_events; hs->n_fac = h.n_fac; hs->halo_off = h.halo_off; hs->reserved = 0;
         hs->step_off = h.step_off; hs->fac_off = h.fac_off;
         const unsigned ptr_bytes = up16(unsigned(Pn + 1) * 2u);
-        unsigned tx = ptr_bytes + unsigned(Pb) * 24u;
+        const unsigned word_bytes = unsigned(words_end - h.step_off) * 4u;
+        unsigned tx = ptr_bytes + word_bytes + unsigned(Pb) * 24u;
         if (pf.seed) tx += unsigned(Pb) * 40u;
         mbar_expect_tx(&bar_full[b], tx);
         bulk_copy(in + pl.oPtr, a.evt_ptr + h.evt_off, ptr_bytes, &bar_full[b]);
+        if (word_bytes) bulk_copy(in + pl.oWords, a.steps + h.step_off, word_bytes, &bar_full[b]);
         if (Pb) {
-          bulk_copy(pos, a.pos + size_t(h.v_lo) * 3, unsigned(Pb) * 24u, &bar_full[b]);
-          if (pf.seed) bulk_copy(seed, a.seeds + size_t(h.v_lo) * kSeedStride, unsigned(Pb) * 40u, &bar_full[b]);
+          bulk_copy(pos, a.pos + size_t(v_lo) * 3, unsigned(Pb) * 24u, &bar_full[b]);
+          if (pf.seed) bulk_copy(seed, a.seeds + size_t(v_lo) * kSeedStride, unsigned(Pb) * 40u, &bar_full[b]);
         }
       }
-      const int32_t* hsrc = a.halo_ids + h.halo_off;
-      const int n_rest = (Pn - Pb) + h.n_halo;   // rows staged with 8-byte copies
       int32_t* bf = pf.bfl ? reinterpret_cast<int32_t*>(in + pl.oBfl) : nullptr;
       double* t2 = pf.t2 ? reinterpret_cast<double*>(in + pl.oT2) : nullptr;
-      for (int k = lane; k < n_rest; k += 32) {
-        const int i = Pb + k;
-        const size_t row = i < Pn ? size_t(h.v_lo) + i : size_t(hsrc[i - Pn]);
+      auto stage_row = [&](int i, size_t row) {  // one vertex row with 8-byte asynchronous copies
         const double* prow = a.pos + row * 3;
         cp_async8(pos + 3 * i, prow);
         cp_async8(pos + 3 * i + 1, prow + 1);
@@ -431,13 +425,21 @@ __global__ void __launch_bounds__(kPatchThreads, 1) k_patch(PatchLaunch a, bool 
         }
         if (bf) cp_async4(bf + i, a.boundary32 + row);
         if (t2) cp_async8(t2 + i, a.tilt_sq + row);
+      };
+#pragma unroll
+      for (int q = 0; q < kIds; ++q) {  // halo rows whose ids are already in registers
+        const int k = lane + 32 * q;
+        if (k < Hn) stage_row(Pn + k, size_t(ids[q]));
       }
+      for (int k = lane + 32 * kIds; k < Hn; k += 32) stage_row(Pn + k, size_t(hsrc[k]));
+      for (int i = Pb + lane; i < Pn; i += 32) stage_row(i, size_t(v_lo) + i);  // owned rows outside the bulk copy
       if (bf || t2) {  // flags (int32) and |t|^2 of the bulk-copied rows
         for (int i = lane; i < Pb; i += 32) {
-          if (bf) cp_async4(bf + i, a.boundary32 + h.v_lo + i);
-          if (t2) cp_async8(t2 + i, a.tilt_sq + h.v_lo + i);
+          if (bf) cp_async4(bf + i, a.boundary32 + v_lo + i);
+          if (t2) cp_async8(t2 + i, a.tilt_sq + v_lo + i);
         }
       }
+      if (j + 1 < n_my) fetch(j + 1);  // in flight while the copies land
       cp_async_wait_all();
       mbar_arrive(&bar_full[b]);
     }
@@ -458,9 +460,9 @@ __global__ void __launch_bounds__(kPatchThreads, 1) k_patch(PatchLaunch a, bool 
       const int b = j % n_buf;
       mbar_wait(&bar_full[b], unsigned((j / n_buf) & 1));
       unsigned char* in = smem + size_t(b) * pl.in_bytes;
-      const PatchHdrS hs = *reinterpret_cast<const PatchHdrS*>(in + pl.oHdr);
+      const PatchHdrS& hs = *reinterpret_cast<const PatchHdrS*>(in + pl.oHdr);  // fields are read where they are needed
       const uint16_t* ptr = reinterpret_cast<const uint16_t*>(in + pl.oPtr);
-      const uint32_t* words = a.steps + hs.step_off + lt;
+      const uint32_t* words = reinterpret_cast<const uint32_t*>(in + pl.oWords) + lt;
       const double* gam = cx.step_gamma ? cx.step_gamma + hs.step_off + lt : nullptr;
       const int Pn = hs.n_owned;
       if (PASS == 0) {
@@ -486,7 +488,7 @@ __global__ void __launch_bounds__(kPatchThreads, 1) k_patch(PatchLaunch a, bool 
             const double kap = (!FAST && a.kappa) ? a.kappa[row] : a.kappa_u;
             const double c0 = (!FAST && a.c0) ? a.c0[row] : a.c0_u;
             const bool on_boundary = has_boundary && a.is_boundary[row] != 0;
-            auto normal_fn = [&]() { return vertex_normal_global(a, hs, a.halo_ids + hs.halo_off, i); };
+            auto normal_fn = [&]() { return vertex_normal_global(a, hs, i); };
             const VertexSeed sd = vertex_body_a(vs, on_boundary, normal_fn, kap, c0, willmore);
             sums[PS_E_BENDING] += sd.E;
             if (a.seeds) {
@@ -530,22 +532,30 @@ __global__ void __launch_bounds__(kPatchThreads, 1) k_patch(PatchLaunch a, bool 
           walk_b<true, false, false>(words, lanes, hs.n_steps, lb, cx, gam, sums);
         }
         named_sync(bar_id, lanes);
+        // dV/dx rows written by pass A (bending evaluations): issued ahead of the event sums that hide their latency
+        // (not ahead of the barrier: a register reload in front of it would wait for these loads)
+        constexpr int kPre = 3;
+        d3 vg_pre[kPre];
+        const bool vg_from_a = !vg_here && do_volume && a.volgrad != nullptr;
+        if (vg_from_a) {
+#pragma unroll
+          for (int q = 0; q < kPre; ++q) {
+            const int i = lt + q * lanes;
+            vg_pre[q] = i < Pn ? ld3(a.volgrad + 3 * size_t(hs.v_lo), i) : make_d3(0, 0, 0);
+          }
+        }
         // gradient (+ dV/dx) rows of the owned vertices and the three KKT dot products
-        for (int i = lt; i < Pn; i += lanes) {
+        auto vertex_b = [&](int i, d3& g_out) {
           const size_t row = size_t(hs.v_lo) + i;
           VertexSumsB vs;
           if (vg_here) vs = do_tilt ? vertex_sums_b<true, true>(lb, ptr[i], ptr[i + 1]) : vertex_sums_b<true, false>(lb, ptr[i], ptr[i + 1]);
           else vs = do_tilt ? vertex_sums_b<false, true>(lb, ptr[i], ptr[i + 1]) : vertex_sums_b<false, false>(lb, ptr[i], ptr[i + 1]);
           st3(a.grad, row, vs.g);
           sums[PS_G_G] += dot(vs.g, vs.g);
-          if (do_volume && a.volgrad) {
-            d3 vg;
-            if (vg_here) {
-              vg = (1.0 / 6.0) * vs.vg;
-              st3(a.volgrad, row, vg);
-            } else {
-              vg = ld3(a.volgrad, int(row));  // written by pass A of this evaluation
-            }
+          g_out = vs.g;
+          if (vg_here) {
+            const d3 vg = (1.0 / 6.0) * vs.vg;
+            st3(a.volgrad, row, vg);
             sums[PS_G_GC] += dot(vs.g, vg);
             sums[PS_GC_GC] += dot(vg, vg);
           }
@@ -553,6 +563,29 @@ __global__ void __launch_bounds__(kPatchThreads, 1) k_patch(PatchLaunch a, bool 
             a.tilt_grad[3 * row] = a.k_tilt * a.tilts[3 * row] * vs.ab;
             a.tilt_grad[3 * row + 1] = a.k_tilt * a.tilts[3 * row + 1] * vs.ab;
             a.tilt_grad[3 * row + 2] = a.k_tilt * a.tilts[3 * row + 2] * vs.ab;
+          }
+        };
+        d3 g_pre[kPre];
+#pragma unroll
+        for (int q = 0; q < kPre; ++q) {
+          const int i = lt + q * lanes;
+          g_pre[q] = make_d3(0, 0, 0);
+          if (i < Pn) vertex_b(i, g_pre[q]);
+        }
+        if (vg_from_a) {
+#pragma unroll
+          for (int q = 0; q < kPre; ++q) {  // rows beyond the patch carry zeros on both sides
+            sums[PS_G_GC] += dot(g_pre[q], vg_pre[q]);
+            sums[PS_GC_GC] += dot(vg_pre[q], vg_pre[q]);
+          }
+        }
+        for (int i = lt + kPre * lanes; i < Pn; i += lanes) {  // patches with more than kPre vertices per lane
+          d3 g;
+          vertex_b(i, g);
+          if (vg_from_a) {
+            const d3 vg = ld3(a.volgrad + 3 * size_t(hs.v_lo), i);
+            sums[PS_G_GC] += dot(g, vg);
+            sums[PS_GC_GC] += dot(vg, vg);
           }
         }
         named_sync(bar_id, lanes);
@@ -1435,7 +1468,7 @@ PlanFlags plan_flags(int pass, int kind, const PatchLaunch& a, bool bending_b) {
 size_t patch_smem_bytes(int pass, const PatchLaunch& a, bool bending_b, int teams) {
   const int warps = teams * (a.threads / 32);
   const int kind = launched_kind(pass, a, bending_b, !bending_b);  // the callers sum the scalars in pass B iff pass A does not run
-  return make_plan(plan_flags(pass, kind, a, bending_b), a.max_local, a.max_owned, a.max_events, teams + 1, teams, warps + 1).total;
+  return make_plan(plan_flags(pass, kind, a, bending_b), a.max_local, a.max_owned, a.max_events, a.max_words, teams + 1, teams, warps + 1).total;
 }
 
 // Largest number of teams (of a.threads lanes) a pass can run with: bounded by the warps of a CTA and by the
@@ -1489,11 +1522,14 @@ cudaError_t launch_pass_a(const PatchLaunch& a_in, cudaStream_t st) {
   const size_t smem = patch_smem_bytes(0, a, false, a.teams);
   const int grid = patch_grid(a);
   const int block = a.teams * a.threads + 32;
-  switch (kernel_kind(a)) {
-    case 1: k_patch<0, 1><<<grid, block, smem, st>>>(a, true, false); break;
-    case 2: k_patch<0, 2><<<grid, block, smem, st>>>(a, false, false); break;
-    case 3: k_patch<0, 3><<<grid, block, smem, st>>>(a, false, false); break;
-    default: k_patch<0, 0><<<grid, block, smem, st>>>(a, false, false);
+  const int kind = kernel_kind(a);
+  const PlanFlags pf = plan_flags(0, kind, a, false);
+  const Plan pl = make_plan(pf, a.max_local, a.max_owned, a.max_events, a.max_words, a.teams + 1, a.teams, a.teams * (a.threads / 32) + 1);
+  switch (kind) {
+    case 1: k_patch<0, 1><<<grid, block, smem, st>>>(a, pf, pl, true, false); break;
+    case 2: k_patch<0, 2><<<grid, block, smem, st>>>(a, pf, pl, false, false); break;
+    case 3: k_patch<0, 3><<<grid, block, smem, st>>>(a, pf, pl, false, false); break;
+    default: k_patch<0, 0><<<grid, block, smem, st>>>(a, pf, pl, false, false);
   }
   return cudaGetLastError();
 }
@@ -1506,11 +1542,14 @@ cudaError_t launch_pass_b(const PatchLaunch& a_in, bool bending, bool scalars_he
   const size_t smem = patch_smem_bytes(1, a, bending, a.teams);
   const int grid = patch_grid(a);
   const int block = a.teams * a.threads + 32;
-  switch (launched_kind(1, a, bending, scalars_here)) {
-    case 1: k_patch<1, 1><<<grid, block, smem, st>>>(a, true, false); break;
-    case 2: k_patch<1, 2><<<grid, block, smem, st>>>(a, false, scalars_here); break;
-    case 3: k_patch<1, 3><<<grid, block, smem, st>>>(a, bending, scalars_here); break;
-    default: k_patch<1, 0><<<grid, block, smem, st>>>(a, bending, scalars_here);
+  const int kind = launched_kind(1, a, bending, scalars_here);
+  const PlanFlags pf = plan_flags(1, kind, a, bending);
+  const Plan pl = make_plan(pf, a.max_local, a.max_owned, a.max_events, a.max_words, a.teams + 1, a.teams, a.teams * (a.threads / 32) + 1);
+  switch (kind) {
+    case 1: k_patch<1, 1><<<grid, block, smem, st>>>(a, pf, pl, true, false); break;
+    case 2: k_patch<1, 2><<<grid, block, smem, st>>>(a, pf, pl, false, scalars_here); break;
+    case 3: k_patch<1, 3><<<grid, block, smem, st>>>(a, pf, pl, bending, scalars_here); break;
+    default: k_patch<1, 0><<<grid, block, smem, st>>>(a, pf, pl, bending, scalars_here);
   }
   return cudaGetLastError();
 }

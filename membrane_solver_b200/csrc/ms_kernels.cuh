@@ -43,7 +43,7 @@ constexpr int kPatchSmemBytes = 227 * 1024;
 
 struct PatchLaunch {
   // packed topology (device)
-  const PatchHeader* patches;
+  const PatchHeader* patches;  // n_patches + 1 entries: a sentinel closes the step-word range of the last patch
   const int32_t* halo_ids;
   const uint32_t* steps;      // step words (ms_pack.h), padded behind the last patch
   const uint16_t* evt_ptr;    // per patch n_owned + 1 event offsets
@@ -55,7 +55,7 @@ struct PatchLaunch {
   int32_t max_ctas;           // > 0: launch at most this many persistent CTAs (leave SMs to NCCL kernels)
   int32_t threads;            // lanes of one team = lanes the mesh was packed for
   int32_t teams;              // teams of consumer warps per CTA (set by the launch functions)
-  int32_t max_owned, max_local, max_events, max_steps;  // largest patch of the packed mesh
+  int32_t max_owned, max_local, max_events, max_steps, max_words;  // largest patch of the packed mesh
   int32_t volgrad_in_a;       // pass A also produces dV/dx (a gradient evaluation with bending follows)
   // mesh state (device)
   const double* pos;          // (nv,3)

@@ -100,7 +100,7 @@ struct StripWork {
   std::vector<Event> events;
   std::vector<int32_t> evt_count;
   std::vector<uint16_t> evt_ptr;
-  int32_t n_steps = 0, n_events = 0, n_pieces = 0;
+  int32_t n_steps = 0, n_steps_used = 0, n_events = 0, n_pieces = 0;
   int64_t warp_compute = 0, gather_groups = 0, gather_excess = 0;
 };
 
@@ -203,8 +203,10 @@ void build_strips(StripWork& w, int32_t nfac) {
 void emit_steps(StripWork& w, int32_t lanes, int32_t n_owned, const int32_t* patch_facets, const int32_t* tri,
                 const uint8_t* body_mask, int32_t v_lo) {
   const int32_t nfac = int32_t(w.seq_f.size());
-  const int32_t S = (nfac + lanes - 1) / lanes;
+  const int32_t S_used = (nfac + lanes - 1) / lanes;
+  const int32_t S = (S_used + 2) / 3 * 3;  // whole triples of steps (the kernels rotate three word registers); padded rows are no-ops
   w.n_steps = S;
+  w.n_steps_used = S_used;
   // restarts per lane -> number of restart rows
   const size_t ns = w.strip_begin.size() - 1;
   int32_t max_restarts = 0;
@@ -213,8 +215,8 @@ void emit_steps(StripWork& w, int32_t lanes, int32_t n_owned, const int32_t* pat
     for (size_t i = 0; i < ns; ++i) {
       int32_t rem = w.strip_begin[i + 1] - w.strip_begin[i];
       while (rem > 0) {
-        if (s == S) { ++lane; s = 0; r = 0; }
-        const int32_t m = std::min(rem, S - s);
+        if (s == S_used) { ++lane; s = 0; r = 0; }
+        const int32_t m = std::min(rem, S_used - s);
         max_restarts = std::max(max_restarts, ++r);
         s += m;
         rem -= m;
@@ -249,13 +251,13 @@ void emit_steps(StripWork& w, int32_t lanes, int32_t n_owned, const int32_t* pat
     const int32_t j_end = w.strip_begin[i + 1];
     const int32_t voff = 2 * int32_t(i);  // vertex sequence of strip i starts at strip_begin[i] + 2 i
     while (j < j_end) {
-      if (s == S) {
+      if (s == S_used) {
         close_lane();
         ++lane;
         s = 0;
         r = 0;
       }
-      const int32_t m = std::min(j_end - j, S - s);
+      const int32_t m = std::min(j_end - j, S_used - s);
       ++w.n_pieces;
       for (int32_t t = 0; t < m; ++t, ++s) {
         const int k = s % 3;
@@ -428,11 +430,12 @@ static int pack_range(const int32_t* tri, const uint8_t* body_mask, const PackPa
     part.max_local = std::max(part.max_local, int32_t(n_local));
     part.max_steps = std::max(part.max_steps, w.n_steps);
     part.max_events = std::max(part.max_events, w.n_events);
+    part.max_words = std::max(part.max_words, int32_t(w.words.size()));
     part.n_listed += int64_t(s.facets.size());
     part.n_strips += int64_t(w.strip_begin.size()) - 1;
     part.n_pieces += w.n_pieces;
     part.n_events += w.n_events;
-    part.n_lane_steps += int64_t(lanes) * int64_t(w.n_steps);
+    part.n_lane_steps += int64_t(lanes) * int64_t(w.n_steps_used);
     part.n_warp_compute += w.warp_compute;
     part.n_gather_groups += w.gather_groups;
     part.n_gather_excess += w.gather_excess;
@@ -519,6 +522,7 @@ int pack_patches(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* body
     out.max_local = std::max(out.max_local, part.max_local);
     out.max_steps = std::max(out.max_steps, part.max_steps);
     out.max_events = std::max(out.max_events, part.max_events);
+    out.max_words = std::max(out.max_words, part.max_words);
     out.n_listed += part.n_listed;
     out.n_strips += part.n_strips;
     out.n_pieces += part.n_pieces;

@@ -32,7 +32,7 @@ struct PatchHeader {  // 48 bytes
   int32_t n_halo;     // local index n_owned + j  ->  vertex row halo_ids[halo_off + j]
   int64_t step_off;   // first step word of this patch: word (s, lane) at step_off + s*lanes + lane,
                       // followed by the tail rows and the restart rows
-  int32_t n_steps;    // steps per lane
+  int32_t n_steps;    // steps per lane: a multiple of 3 (padded with no-op rows)
   int32_t n_events;   // event rows of this patch
   int64_t fac_off;    // first compact facet record (flat-vertex normal fallback only)
   int32_t n_fac;      // facets listed by this patch
@@ -94,12 +94,13 @@ struct PackedMesh {
   std::vector<uint16_t> evt_ptr;    // per patch n_owned + 1 offsets: events of owned vertex i are rows [ptr[i], ptr[i+1])
   std::vector<FacetRec> recs;       // compact facet records, patch after patch
   int32_t max_owned = 0, max_local = 0, max_steps = 0, max_events = 0;
+  int32_t max_words = 0;       // largest step-word count of a patch (steps + tail rows + restart rows)
   int64_t n_listed = 0;        // facet listings over all patches (>= valid facets)
   int64_t n_valid = 0;         // facets with all indices in range
   int64_t n_strips = 0;        // strips before cutting
   int64_t n_pieces = 0;        // strip pieces after cutting (each begins with a restart step)
   int64_t n_events = 0;        // event rows over all patches
-  int64_t n_lane_steps = 0;    // sum over patches of lanes * n_steps
+  int64_t n_lane_steps = 0;    // sum over patches of lanes * steps in use (without the no-op padding rows)
   int64_t n_warp_compute = 0;  // (patch, warp, step) triples in which at least one lane evaluates a facet
   int64_t n_gather_groups = 0; // (patch, half-warp, step) groups that load at least one vertex
   int64_t n_gather_excess = 0; // extra shared-memory wavefronts of those gathers (bank conflicts)

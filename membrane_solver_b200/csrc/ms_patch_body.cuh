@@ -76,11 +76,13 @@ MS_HD void slot_clear_a(SlotA& s) {
   s.vg = make_d3(0, 0, 0);
 }
 
+// ZERO = false: the step that loads the slot assigns its partial sums (step_compute_a<.., K>)
+template <bool ZERO = true>
 MS_HD void slot_load_a(SlotA& s, const LocalA& l, int i) {
   s.p = ld3(l.pos, i);
   s.bnd = l.bfl ? l.bfl[i] : 0;
   s.t2 = l.t2 ? l.t2[i] : 0.0;
-  slot_clear_a(s);
+  if (ZERO) slot_clear_a(s);
 }
 
 template <bool BENDING, bool VG>
@@ -92,35 +94,44 @@ MS_HD void slot_flush_a(const SlotA& s, const LocalA& l, int e) {
   if (VG) st3(l.evV, e, s.vg);
 }
 
+// r = fresh ? c : r + c.  FRESH is a compile-time property of the slot a step has just loaded: its first
+// contribution is assigned, so loading a vertex does not have to zero its partial sums.
+template <bool FRESH>
+MS_HD void acc1(double& r, double c) { r = FRESH ? c : r + c; }
+template <bool FRESH>
+MS_HD void acc3(d3& r, d3 c) { r = FRESH ? c : r + c; }
+
 // Evaluate the facet held by the three slots: per-facet scalars (primary listing only) and the corner
-// contributions of pass A, added to the slots' partial sums.
-template <bool BENDING, bool VG>
+// contributions of pass A, added to the slots' partial sums.  K (0..2) names the slot this step loaded (its sums
+// start here); K = -1: no slot is fresh (host emulator, restart-loaded slots are zeroed when they are loaded).
+template <bool BENDING, bool VG, int K = -1>
 MS_HD void step_compute_a(SlotA& s0, SlotA& s1, SlotA& s2, uint32_t word, double gam, uint32_t modules, double k_tilt,
                           double* sums) {
   const FacetGeom g = facet_geom(s0.p, s1.p, s2.p);
   const bool body = (modules & MS_MOD_VOLUME) && (word & STEP_BODY);
+  const bool primary = (word & STEP_PRIMARY) != 0;
   const double sgn = (word & STEP_NEG) ? -1.0 : 1.0;
   d3 c12 = make_d3(0, 0, 0);
-  if (body && (VG || (word & STEP_PRIMARY))) c12 = sgn * cross(s1.p, s2.p);
-  if (word & STEP_PRIMARY) {
-    const double T = 0.5 * g.S;
+  if (modules & MS_MOD_VOLUME) c12 = (body ? sgn : 0.0) * cross(s1.p, s2.p);
+  {  // scalars of the primary listing (branch-free: other listings add zeros)
+    const double T = primary ? 0.5 * g.S : 0.0;
     sums[PS_AREA] += T;
-    if (g.S >= kSurfaceSkip) {
-      if (modules & MS_MOD_SURFACE) sums[PS_E_SURFACE] += gam * T;
-      if (modules & MS_MOD_TILT) sums[PS_E_TILT] += 0.5 * k_tilt * ((s0.t2 + s1.t2 + s2.t2) / 3.0) * T;
-    }
-    if (body) sums[PS_VOLUME6] += dot(c12, s0.p);
+    const double Ts = g.S >= kSurfaceSkip ? T : 0.0;
+    if (modules & MS_MOD_SURFACE) sums[PS_E_SURFACE] += gam * Ts;
+    if (modules & MS_MOD_TILT) sums[PS_E_TILT] += 0.5 * k_tilt * ((s0.t2 + s1.t2 + s2.t2) / 3.0) * Ts;
+    if (modules & MS_MOD_VOLUME) sums[PS_VOLUME6] += primary ? dot(c12, s0.p) : 0.0;
   }
   if (BENDING) {
     const CornerA c = facet_pass_a(g, s0.bnd != 0, s1.bnd != 0, s2.bnd != 0);
-    s0.K = s0.K + c.K0; s0.va += c.va0; s0.ve += c.ve0;
-    s1.K = s1.K + c.K1; s1.va += c.va1; s1.ve += c.ve1;
-    s2.K = s2.K + c.K2; s2.va += c.va2; s2.ve += c.ve2;
+    acc3<K == 0>(s0.K, c.K0); acc1<K == 0>(s0.va, c.va0); acc1<K == 0>(s0.ve, c.ve0);
+    acc3<K == 1>(s1.K, c.K1); acc1<K == 1>(s1.va, c.va1); acc1<K == 1>(s1.ve, c.ve1);
+    acc3<K == 2>(s2.K, c.K2); acc1<K == 2>(s2.va, c.va2); acc1<K == 2>(s2.ve, c.ve2);
   }
-  if (VG && body) {
-    s0.vg = s0.vg + c12;
-    s1.vg = s1.vg + sgn * cross(s2.p, s0.p);
-    s2.vg = s2.vg + sgn * cross(s0.p, s1.p);
+  if (VG) {  // facets outside the body contribute zeros (c12 and sgn0 vanish)
+    const double sg = body ? sgn : 0.0;
+    acc3<K == 0>(s0.vg, c12);
+    acc3<K == 1>(s1.vg, sg * cross(s2.p, s0.p));
+    acc3<K == 2>(s2.vg, sg * cross(s0.p, s1.p));
   }
 }
 
@@ -205,7 +216,7 @@ MS_HD void slot_clear_b(SlotB& s) {
   s.ab = 0.0;
 }
 
-template <bool BENDING>
+template <bool BENDING, bool ZERO = true>
 MS_HD void slot_load_b(SlotB& s, const LocalB& l, int i) {
   s.p = ld3(l.pos, i);
   if (BENDING) {
@@ -220,7 +231,7 @@ MS_HD void slot_load_b(SlotB& s, const LocalB& l, int i) {
     s.bnd = 0;
   }
   s.t2 = l.t2 ? l.t2[i] : 0.0;
-  slot_clear_b(s);
+  if (ZERO) slot_clear_b(s);
 }
 
 template <bool VG, bool TILT>
@@ -231,30 +242,31 @@ MS_HD void slot_flush_b(const SlotB& s, const LocalB& l, int e) {
 }
 
 // scalars_here: pass A did not run (no bending), so the per-facet scalars are summed here.
-template <bool BENDING, bool VG, bool TILT>
+// K: the slot this step loaded (see step_compute_a).
+template <bool BENDING, bool VG, bool TILT, int K = -1>
 MS_HD void step_compute_b(SlotB& s0, SlotB& s1, SlotB& s2, uint32_t word, double gam, uint32_t modules, uint32_t flags,
                           double k_tilt, bool scalars_here, double* sums) {
   const FacetGeom g = facet_geom(s0.p, s1.p, s2.p);
-  const double T = 0.5 * g.S;
   const bool primary = (word & STEP_PRIMARY) != 0;
   const bool body = (modules & MS_MOD_VOLUME) && (word & STEP_BODY);
   const double sgn = (word & STEP_NEG) ? -1.0 : 1.0;
+  const double T = 0.5 * g.S;
   if (!(modules & MS_MOD_SURFACE)) gam = 0.0;
   double coeff = 0.0;
   if (TILT) {
     coeff = 0.5 * k_tilt * ((s0.t2 + s1.t2 + s2.t2) / 3.0);
-    if (g.S >= kSurfaceSkip) {
-      if (primary) sums[PS_E_TILT] += coeff * T;
-      const double third = T / 3.0;
-      s0.ab += third; s1.ab += third; s2.ab += third;
-    }
+    const double Ts = g.S >= kSurfaceSkip ? T : 0.0;
+    sums[PS_E_TILT] += primary ? coeff * Ts : 0.0;
+    const double third = Ts / 3.0;
+    acc1<K == 0>(s0.ab, third); acc1<K == 1>(s1.ab, third); acc1<K == 2>(s2.ab, third);
   }
   d3 c12 = make_d3(0, 0, 0);
-  if (body && (VG || (scalars_here && primary))) c12 = sgn * cross(s1.p, s2.p);
-  if (scalars_here && primary) {
-    sums[PS_AREA] += T;
-    if ((modules & MS_MOD_SURFACE) && g.S >= kSurfaceSkip) sums[PS_E_SURFACE] += gam * T;
-    if (body) sums[PS_VOLUME6] += dot(c12, s0.p);
+  if ((modules & MS_MOD_VOLUME) && (VG || scalars_here)) c12 = (body ? sgn : 0.0) * cross(s1.p, s2.p);
+  if (scalars_here) {
+    const double Tp = primary ? T : 0.0;
+    sums[PS_AREA] += Tp;
+    if (modules & MS_MOD_SURFACE) sums[PS_E_SURFACE] += g.S >= kSurfaceSkip ? gam * Tp : 0.0;
+    if (modules & MS_MOD_VOLUME) sums[PS_VOLUME6] += primary ? dot(c12, s0.p) : 0.0;
   }
   BendIn b;
   if (BENDING) {
@@ -268,13 +280,14 @@ MS_HD void step_compute_b(SlotB& s0, SlotB& s1, SlotB& s2, uint32_t word, double
     b.i0 = b.i1 = b.i2 = true;
   }
   const CornerG cg = facet_pass_b<BENDING>(g, gam, coeff, b, (flags & MS_FLAG_APPROX) != 0);
-  s0.g = s0.g + cg.g0;
-  s1.g = s1.g + cg.g1;
-  s2.g = s2.g + cg.g2;
-  if (VG && body) {  // unscaled: the vertex sums multiply by 1/6
-    s0.vg = s0.vg + c12;
-    s1.vg = s1.vg + sgn * cross(s2.p, s0.p);
-    s2.vg = s2.vg + sgn * cross(s0.p, s1.p);
+  acc3<K == 0>(s0.g, cg.g0);
+  acc3<K == 1>(s1.g, cg.g1);
+  acc3<K == 2>(s2.g, cg.g2);
+  if (VG) {  // unscaled: the vertex sums multiply by 1/6; facets outside the body contribute zeros
+    const double sg = body ? sgn : 0.0;
+    acc3<K == 0>(s0.vg, c12);
+    acc3<K == 1>(s1.vg, sg * cross(s2.p, s0.p));
+    acc3<K == 2>(s2.vg, sg * cross(s0.p, s1.p));
   }
 }
 
