@@ -216,7 +216,8 @@ def run_b200(args):
     nv, nf = pos.shape[0], tri.shape[0]
     t_gen = time.perf_counter() - t_setup
     dm = DeviceMesh(local, threads=args.threads, max_owned=args.max_owned, max_local=args.max_local,
-                    max_events=args.max_events, trim=args.trim)
+                    fill_pct=args.fill,
+                    repair_sweeps=args.repair)
     t0 = time.perf_counter()
     dm.set_topology(nv, tri, body_mask=np.ones(nf, np.uint8))
     t_pack = time.perf_counter() - t0
@@ -341,8 +342,8 @@ def main():
     ap.add_argument("--threads", type=int, default=None)
     ap.add_argument("--max-owned", type=int, default=None)
     ap.add_argument("--max-local", type=int, default=None)
-    ap.add_argument("--max-events", type=int, default=None, help="packer: event rows per patch")
-    ap.add_argument("--trim", type=int, default=None, help="packer: trim patches to whole lane steps (default 1)")
+    ap.add_argument("--fill", type=int, default=None, help="packer: target percent of record slots holding a facet")
+    ap.add_argument("--repair", type=int, default=None, help="packer: lane-placement repair passes")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -96,21 +96,17 @@ typedef struct ms_eval_opts {
 
 typedef struct ms_pack_info {
   int32_t nv, nf;
-  int32_t n_patches, threads; /* threads: lanes of the team of warps that walks one patch */
-  int32_t max_owned, max_local, max_steps;
-  int32_t max_events;  /* largest event-row count of a patch */
-  int32_t teams;       /* teams of consumer warps per CTA the kernels run with on this mesh */
-  int32_t max_words;   /* largest step-word count of a patch (steps + tail rows + restart rows) */
-  int64_t n_lane_steps;    /* sum over patches of lanes x steps: step words streamed per pass */
-  int64_t n_listed;        /* facet listings over all patches (ring facets counted per patch) */
-  int64_t n_valid;         /* facets with all indices in range */
-  int64_t n_halo;          /* halo vertex references over all patches */
-  int64_t n_strips;        /* triangle strips before they are cut into lane pieces */
-  int64_t n_pieces;        /* strip pieces (each starts with a restart step) */
-  int64_t n_events;        /* event rows: partial sums leaving a lane's registers */
-  int64_t n_warp_compute;  /* (patch, warp, step) triples in which at least one lane evaluates a facet */
-  int64_t n_gather_groups; /* (patch, half-warp, step) gather groups */
-  int64_t n_gather_excess; /* extra shared-memory wavefronts over those groups (0 = conflict free) */
+  int32_t n_patches, threads;
+  int32_t max_owned, max_local, max_rounds;
+  int32_t max_slots; /* largest record count of a patch */
+  int64_t n_slots;   /* record slots streamed per pass */
+  int64_t n_listed;  /* facet listings over all patches (ring facets counted per patch) */
+  int64_t n_valid;   /* facets with all indices in range */
+  int64_t n_halo;    /* halo vertex references over all patches */
+  int64_t n_round_slots; /* sum over patches of rounds x threads (= n_slots) */
+  int64_t n_lane_conflicts; /* facets sharing a bank residue with another facet of their half-warp */
+  int64_t n_hw_groups;      /* (round, half-warp, corner) gather groups holding at least one facet */
+  int64_t n_hw_excess;      /* extra shared-memory wavefronts over those groups (0 = conflict free) */
 } ms_pack_info;
 
 /* ---- library ------------------------------------------------------------------ */
@@ -122,13 +118,13 @@ MS_API int ms_device_count(int* count);
  *      runtime/energy_context.py:63-276 and Mesh.positions_view/triangle_row_cache) - */
 MS_API int ms_ctx_create(int device, ms_ctx** out);
 MS_API int ms_ctx_destroy(ms_ctx* ctx);
-/* patch geometry used by the next ms_ctx_set_topology: lanes of the team of warps that walks one patch
- * (a multiple of 32, at most 480), owned vertices per patch, owned + halo vertices per patch (<= 2047).
- * Defaults 192 / 448 / 768; the shared-memory need is checked when the topology is set. */
+/* patch geometry used by the next ms_ctx_set_topology (defaults 128 / 512 / 896; these are
+ * also the compiled shared-memory capacities, so values may only be lowered) */
 MS_API int ms_ctx_set_pack_params(ms_ctx* ctx, int32_t threads, int32_t max_owned, int32_t max_local);
-/* packer tuning for the next ms_ctx_set_topology: largest event-row count of a patch (0 = default, twice
- * max_local) and whether patches are trimmed so that their facets fill the lanes' steps evenly (default 1) */
-MS_API int ms_ctx_set_pack_tuning(ms_ctx* ctx, int32_t max_events, int32_t trim);
+/* packer tuning for the next ms_ctx_set_topology: target share (percent) of record slots that
+ * hold a facet (default 87; lower = more free lanes = fewer shared-memory bank clashes) and
+ * the number of lane-placement repair passes (default 1) */
+MS_API int ms_ctx_set_pack_tuning(ms_ctx* ctx, int32_t fill_pct, int32_t repair_sweeps);
 /* launch at most max_ctas persistent CTAs per pass (0 = one per SM): a partitioned evaluation leaves a
  * few SMs to the NCCL kernels of the halo exchange that runs concurrently */
 MS_API int ms_ctx_set_max_ctas(ms_ctx* ctx, int32_t max_ctas);

@@ -84,13 +84,11 @@ class PackInfo(ctypes.Structure):
         ("nv", ctypes.c_int32), ("nf", ctypes.c_int32),
         ("n_patches", ctypes.c_int32), ("threads", ctypes.c_int32),
         ("max_owned", ctypes.c_int32), ("max_local", ctypes.c_int32),
-        ("max_steps", ctypes.c_int32), ("max_events", ctypes.c_int32),
-        ("teams", ctypes.c_int32), ("max_words", ctypes.c_int32),
-        ("n_lane_steps", ctypes.c_int64), ("n_listed", ctypes.c_int64),
+        ("max_rounds", ctypes.c_int32), ("max_slots", ctypes.c_int32),
+        ("n_slots", ctypes.c_int64), ("n_listed", ctypes.c_int64),
         ("n_valid", ctypes.c_int64), ("n_halo", ctypes.c_int64),
-        ("n_strips", ctypes.c_int64), ("n_pieces", ctypes.c_int64),
-        ("n_events", ctypes.c_int64), ("n_warp_compute", ctypes.c_int64),
-        ("n_gather_groups", ctypes.c_int64), ("n_gather_excess", ctypes.c_int64),
+        ("n_round_slots", ctypes.c_int64), ("n_lane_conflicts", ctypes.c_int64),
+        ("n_hw_groups", ctypes.c_int64), ("n_hw_excess", ctypes.c_int64),
     ]
 
 

@@ -68,7 +68,7 @@ class DeviceMesh:
 
     def __init__(self, device: int = 0, *, threads: int | None = None, max_owned: int | None = None,
                  max_local: int | None = None,
-                 max_events: int | None = None, trim: int | None = None):
+                 fill_pct: int | None = None, repair_sweeps: int | None = None):
         self._lib = L.lib()
         handle = ctypes.c_void_p()
         L.check(self._lib.ms_ctx_create(int(device), ctypes.byref(handle)))
@@ -78,10 +78,11 @@ class DeviceMesh:
         self.nf = 0
         self.n_owned = 0
         if threads is not None or max_owned is not None or max_local is not None:
-            L.check(self._lib.ms_ctx_set_pack_params(self._h, int(threads or 192), int(max_owned or 448),
-                                                     int(max_local or 768)))
-        if max_events is not None or trim is not None:
-            L.check(self._lib.ms_ctx_set_pack_tuning(self._h, int(max_events or 0), int(1 if trim is None else trim)))
+            L.check(self._lib.ms_ctx_set_pack_params(self._h, int(threads or 96), int(max_owned or 512),
+                                                     int(max_local or 896)))
+        if fill_pct is not None or repair_sweeps is not None:
+            L.check(self._lib.ms_ctx_set_pack_tuning(self._h, int(87 if fill_pct is None else fill_pct),
+                                                     int(1 if repair_sweeps is None else repair_sweeps)))
 
     # -- lifetime -----------------------------------------------------------
     def close(self) -> None:

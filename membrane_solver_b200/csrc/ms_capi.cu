@@ -66,16 +66,13 @@ struct ms_ctx {
   int32_t nv = 0, nf = 0;
   int32_t n_owned = 0;  // vertex rows owned by this context's patches (== nv unless partitioned)
   ms::PackParams pack_params;
-  ms::PackedMesh packed;  // step_facet kept on the host for gamma repacking
-  int32_t teams = 0;      // teams of consumer warps per CTA on this mesh
+  ms::PackedMesh packed;  // recs / slot_facet kept on the host for gamma repacking
   std::vector<int32_t> v_lo;
 
   DevBuf<ms::PatchHeader> d_patches;
   DevBuf<int32_t> d_halo;
   DevBuf<ms::FacetRec> d_recs;
-  DevBuf<uint32_t> d_steps;
-  DevBuf<uint16_t> d_evt_ptr;
-  DevBuf<double> d_step_gamma;
+  DevBuf<double> d_slot_gamma;
   DevBuf<uint8_t> d_boundary, d_fixed;
   DevBuf<int32_t> d_boundary32;  // boundary flags as int32: staged into shared memory with 4-byte cp.async
   DevBuf<double> d_tilt_sq;      // |t|^2 per vertex, refreshed before every evaluation that uses the tilts
@@ -235,21 +232,15 @@ int fill_launch(ms_ctx* c, const ms_eval_opts* o, ms::PatchLaunch& a) {
   a.patches = c->d_patches.p;
   a.halo_ids = c->d_halo.p;
   a.recs = c->d_recs.p;
-  a.steps = c->d_steps.p;
-  a.evt_ptr = c->d_evt_ptr.p;
-  a.step_gamma = c->has_gamma ? c->d_step_gamma.p : nullptr;
+  a.slot_gamma = c->has_gamma ? c->d_slot_gamma.p : nullptr;
   a.patch_begin = begin;
   a.patch_count = count;
   a.max_ctas = c->max_ctas;
   a.threads = c->packed.params.threads;
-  a.teams = 0;  // chosen per launch
   a.max_owned = c->packed.max_owned;
   a.max_local = c->packed.max_local;
-  a.max_events = c->packed.max_events;
-  a.max_steps = c->packed.max_steps;
-  a.max_words = c->packed.max_words;
-  // pass A also produces dV/dx when a gradient evaluation with bending follows
-  a.volgrad_in_a = (o->want_grad && (o->modules & MS_MOD_VOLUME) && (o->modules & (MS_MOD_BENDING | MS_MOD_BENDING_TILT))) ? 1 : 0;
+  a.max_slots = c->packed.max_slots;
+  a.max_rounds = c->packed.max_rounds;
   if (o->use_trial) {
     if (!c->d_trial.p) return fail(-4, "use_trial set but no trial positions exist (ms_ctx_make_trial)");
     a.pos = c->d_trial.p;
@@ -497,22 +488,21 @@ int ms_ctx_set_stream(ms_ctx* c, void* s) {
 
 int ms_ctx_set_pack_params(ms_ctx* c, int32_t threads, int32_t max_owned, int32_t max_local) {
   if (!c) return fail(-1, "null context");
-  if (threads < 32 || threads > ms::kPatchThreads - 32 || threads % 32)
-    return fail(-1, "threads must be a multiple of 32 in [32,480]");
+  if (threads < 32 || threads > 256 || threads % 32) return fail(-1, "threads must be a multiple of 32 in [32,256]");
   if (max_owned < 1 || max_local < max_owned) return fail(-1, "bad patch sizes");
-  if (max_local > int32_t(ms::STEP_INDEX_MASK)) return fail(-1, "max_local exceeds the 11-bit local vertex index of a step word (2047)");
+  if (max_owned > ms::kPatchOwnedCap || max_local > ms::kPatchLocalCap)
+    return fail(-1, "patch sizes exceed the compiled shared-memory capacities (512 owned / 896 local)");
   c->pack_params.threads = threads;
   c->pack_params.max_owned = max_owned;
   c->pack_params.max_local = max_local;
-  c->pack_params.max_events = 2 * max_local;
   return 0;
 }
 
-int ms_ctx_set_pack_tuning(ms_ctx* c, int32_t max_events, int32_t trim) {
+int ms_ctx_set_pack_tuning(ms_ctx* c, int32_t fill_pct, int32_t repair_sweeps) {
   if (!c) return fail(-1, "null context");
-  if (max_events < 0 || max_events > ms::kMaxPatchEvents || trim < 0 || trim > 1) return fail(-1, "bad tuning values");
-  if (max_events > 0) c->pack_params.max_events = max_events;
-  c->pack_params.trim = trim;
+  if (fill_pct < 10 || fill_pct > 100 || repair_sweeps < 0 || repair_sweeps > 8) return fail(-1, "bad tuning values");
+  c->pack_params.fill_pct = fill_pct;
+  c->pack_params.repair_sweeps = repair_sweeps;
   return 0;
 }
 
@@ -572,9 +562,17 @@ int ms_ctx_set_topology_partition(ms_ctx* c, int32_t nv, int32_t n_owned, int32_
     CU(cudaMemcpy(c->d_perm.p, c->perm.data(), size_t(nv) * sizeof(int32_t), cudaMemcpyHostToDevice));
     if (int rc = c->d_stage.ensure(size_t(ms::kSeedStride) * size_t(nv))) return rc;
   }
-  int prc = ms::pack_patches(nv, nf, tri, body_mask, c->pack_params, c->packed, n_owned);
+  // A vertex of valence V needs V rounds, i.e. V * threads record slots, and a patch holds at most
+  // kPatchSlotCap of them: meshes with high-valence vertices (a disk centre, a cone apex) are packed with
+  // narrower rounds (96 -> 64 -> 32 lanes: valence up to 16 / 24 / 48).
+  ms::PackParams used_params = c->pack_params;
+  int prc = ms::pack_patches(nv, nf, tri, body_mask, used_params, c->packed, n_owned);
+  while (prc == -3 && used_params.threads > 32) {
+    used_params.threads = used_params.threads > 64 ? 64 : 32;
+    prc = ms::pack_patches(nv, nf, tri, body_mask, used_params, c->packed, n_owned);
+  }
   if (prc == -2) return fail(-8, "a vertex neighbourhood exceeds max_local; raise it with ms_ctx_set_pack_params");
-  if (prc == -3) return fail(-8, "a vertex neighbourhood needs more event rows than max_events; raise it with ms_ctx_set_pack_tuning");
+  if (prc == -3) return fail(-8, "a vertex has more than 48 incident facets: its rounds do not fit a patch");
   if (prc) return fail(-1, "pack_patches failed");
   c->nv = nv;
   c->nf = nf;
@@ -604,42 +602,18 @@ int ms_ctx_set_topology_partition(ms_ctx* c, int32_t nv, int32_t n_owned, int32_
     if (!order.empty()) CU(cudaMemcpy(c->d_patch_order.p, order.data(), order.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   }
 
-  {  // the headline configuration must fit the shared memory of an SM with at least one team
-    ms::PatchLaunch probe;
-    std::memset(&probe, 0, sizeof(probe));
-    probe.threads = pk.params.threads;
-    probe.max_owned = pk.max_owned;
-    probe.max_local = pk.max_local;
-    probe.max_events = pk.max_events;
-    probe.max_words = pk.max_words;
-    probe.modules = MS_MOD_SURFACE | MS_MOD_BENDING | MS_MOD_VOLUME | MS_MOD_TILT;
-    probe.volgrad = reinterpret_cast<double*>(1);  // worst case of the plans: every optional array present
-    probe.seeds = reinterpret_cast<double*>(1);
-    probe.tilts = reinterpret_cast<const double*>(1);
-    probe.is_boundary = reinterpret_cast<const uint8_t*>(1);
-    probe.volgrad_in_a = 1;
-    if (ms::patch_teams(0, probe, true) <= 0 || ms::patch_teams(1, probe, true) <= 0)
-      return fail(-8, "the largest patch does not fit the shared memory of an SM; lower max_owned / max_local");
-    probe.modules = MS_MOD_SURFACE | MS_MOD_BENDING | MS_MOD_VOLUME;
-    probe.tilts = nullptr;
-    probe.is_boundary = nullptr;
-    c->teams = std::min(ms::patch_teams(0, probe, true), ms::patch_teams(1, probe, true));
-  }
+  if (prc == 0 && (pk.max_owned > ms::kPatchOwnedCap || pk.max_local > ms::kPatchLocalCap || pk.max_slots > ms::kPatchSlotCap))
+    return fail(-8, "a patch exceeds the compiled shared-memory capacities");
   if (int rc = c->d_patches.ensure(np + 1)) return rc;
-  if (int rc = c->d_halo.ensure(pk.halo_ids.size() + 1)) return rc;
-  if (int rc = c->d_recs.ensure(pk.recs.size() + 1)) return rc;
-  const size_t step_pad = 4 * size_t(pk.params.threads);  // the lanes prefetch one restart pair past their last
-  if (int rc = c->d_steps.ensure(pk.steps.size() + step_pad)) return rc;
-  if (int rc = c->d_evt_ptr.ensure(pk.evt_ptr.size() + 8)) return rc;
-  {  // sentinel header: closes the step-word range of the last patch
+  if (int rc = c->d_halo.ensure(pk.halo_ids.size())) return rc;
+  if (int rc = c->d_recs.ensure(pk.recs.size())) return rc;
+  {  // sentinel header: closes the record range of the last patch
     std::vector<ms::PatchHeader> hdr(pk.patches);
     ms::PatchHeader end;
     std::memset(&end, 0, sizeof(end));
     end.v_lo = n_owned;
     end.halo_off = int32_t(pk.halo_ids.size());
-    end.step_off = int64_t(pk.steps.size());
-    end.fac_off = int64_t(pk.recs.size());
-    end.evt_off = int32_t(pk.evt_ptr.size());
+    end.slot_off = int64_t(pk.recs.size());
     hdr.push_back(end);
     CU(cudaMemcpy(c->d_patches.p, hdr.data(), hdr.size() * sizeof(ms::PatchHeader), cudaMemcpyHostToDevice));
   }
@@ -647,11 +621,6 @@ int ms_ctx_set_topology_partition(ms_ctx* c, int32_t nv, int32_t n_owned, int32_
     CU(cudaMemcpy(c->d_halo.p, pk.halo_ids.data(), pk.halo_ids.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   if (!pk.recs.empty())
     CU(cudaMemcpy(c->d_recs.p, pk.recs.data(), pk.recs.size() * sizeof(ms::FacetRec), cudaMemcpyHostToDevice));
-  CU(cudaMemset(c->d_steps.p, 0, (pk.steps.size() + step_pad) * sizeof(uint32_t)));
-  if (!pk.steps.empty())
-    CU(cudaMemcpy(c->d_steps.p, pk.steps.data(), pk.steps.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-  if (!pk.evt_ptr.empty())
-    CU(cudaMemcpy(c->d_evt_ptr.p, pk.evt_ptr.data(), pk.evt_ptr.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
 
   c->has_boundary = is_boundary != nullptr;
   c->has_fixed = fixed_mask != nullptr;
@@ -712,20 +681,16 @@ int ms_ctx_pack_info(const ms_ctx* c, ms_pack_info* info) {
   info->threads = pk.params.threads;
   info->max_owned = pk.max_owned;
   info->max_local = pk.max_local;
-  info->max_steps = pk.max_steps;
-  info->max_events = pk.max_events;
-  info->teams = c->teams;
-  info->max_words = pk.max_words;
-  info->n_lane_steps = pk.n_lane_steps;
+  info->max_rounds = pk.max_rounds;
+  info->max_slots = pk.max_slots;
+  info->n_slots = int64_t(pk.recs.size());
   info->n_listed = pk.n_listed;
   info->n_valid = pk.n_valid;
   info->n_halo = int64_t(pk.halo_ids.size());
-  info->n_strips = pk.n_strips;
-  info->n_pieces = pk.n_pieces;
-  info->n_events = pk.n_events;
-  info->n_warp_compute = pk.n_warp_compute;
-  info->n_gather_groups = pk.n_gather_groups;
-  info->n_gather_excess = pk.n_gather_excess;
+  info->n_round_slots = pk.n_round_slots;
+  info->n_lane_conflicts = pk.n_lane_conflicts;
+  info->n_hw_groups = pk.n_hw_groups;
+  info->n_hw_excess = pk.n_hw_excess;
   return 0;
 }
 
@@ -767,12 +732,12 @@ int ms_ctx_set_surface_tension(ms_ctx* c, const double* gamma, double gamma_unif
   c->has_gamma = false;
   if (!gamma) return 0;
   const ms::PackedMesh& pk = c->packed;
-  std::vector<double> step_gamma(pk.step_facet.size(), 0.0);
-  for (size_t s = 0; s < step_gamma.size(); ++s)
-    if (pk.step_facet[s] >= 0) step_gamma[s] = gamma[pk.step_facet[s]];
-  if (int rc = c->d_step_gamma.ensure(step_gamma.size() + 1)) return rc;
-  if (!step_gamma.empty())
-    CU(cudaMemcpy(c->d_step_gamma.p, step_gamma.data(), step_gamma.size() * sizeof(double), cudaMemcpyHostToDevice));
+  std::vector<double> slot_gamma(pk.slot_facet.size(), 0.0);
+  for (size_t s = 0; s < slot_gamma.size(); ++s)
+    if (pk.slot_facet[s] >= 0) slot_gamma[s] = gamma[pk.slot_facet[s]];
+  if (int rc = c->d_slot_gamma.ensure(slot_gamma.size())) return rc;
+  if (!slot_gamma.empty())
+    CU(cudaMemcpy(c->d_slot_gamma.p, slot_gamma.data(), slot_gamma.size() * sizeof(double), cudaMemcpyHostToDevice));
   c->has_gamma = true;
   return 0;
 }

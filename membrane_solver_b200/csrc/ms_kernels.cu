@@ -1,13 +1,27 @@
 // sm_100a kernels of the energy+gradient path.
 //
-// Patch kernels (pass A / pass B): PERSISTENT CTAs, one per SM, each walking its share of the
-// vertex patches; the facets of a patch are walked as lane-local triangle strips (ms_pack.h,
-// ms_patch_body.cuh) -- see k_patch below.
+// Patch kernels (pass A / pass B): PERSISTENT CTAs, one per SM, each walking its share of
+// the vertex patches.  A CTA is warp-specialised:
+//
+//   * one PRODUCER warp stages patch j+1 into the second shared-memory buffer with
+//     asynchronous copies (cp.async / LDGSTS) while patch j is being computed: records,
+//     halo ids and owned rows first, the halo rows (which need the ids) second.  Global rows
+//     are (nv,3) / (nv,5) arrays-of-structures; they land in shared memory as structure of
+//     arrays, so every component of a local vertex is one address register + an immediate.
+//   * the CONSUMER threads form G groups of `threads` lanes.  The patch's facet records are
+//     scheduled in ROUNDS (ms_pack.cpp): within a round no two facets write the same owned
+//     vertex and the lanes of a half-warp gather from distinct bank pairs.  Group g takes
+//     every G-th round: it computes its facets entirely in registers, then waits for a
+//     token (named barrier), adds the corner contributions to the shared accumulators with
+//     plain read-modify-writes, and passes the token on.  Accumulation therefore happens in
+//     round order -- fixed at pack time, no atomics, run-to-run reproducible -- while the
+//     other groups are computing.  After the last round come the patch's EPILOGUE turns
+//     (vertex stage + seeds in pass A; gradient rows + KKT dot products in pass B), taken by
+//     the groups in the same rotation; accumulators are double buffered so that the next
+//     patch's rounds overlap them.
 //
 // Reference functions replaced: see the header of ms_math.cuh.
 #include "ms_kernels.cuh"
-
-#include <cstdlib>
 
 #include "ms_bt.cuh"
 #include "ms_patch_body.cuh"
@@ -48,7 +62,7 @@ __device__ __forceinline__ void block_sum(double (&v)[N], double* red, int n_thr
   }
 }
 
-// ---- asynchronous copies: LDGSTS (cp.async) for scattered rows, bulk copies for contiguous ranges ----
+// ---- asynchronous copies (LDGSTS): global -> shared without a register round trip ----
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return unsigned(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src));
@@ -56,26 +70,19 @@ __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
 __device__ __forceinline__ void cp_async8(void* dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src));
 }
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src));
+}
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
-// One contiguous global range -> shared memory (16-byte aligned on both sides, size a multiple of 16);
-// completion is counted in bytes on the mbarrier.
-__device__ __forceinline__ void bulk_copy(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
 
-// ---- mbarriers (producer <-> consumers) and named barriers (one per team) ----
+// ---- mbarriers (producer <-> consumers) and named barriers (token ring) ----
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
-  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ bool mbar_try(unsigned addr, unsigned parity) {
   unsigned ok = 0;
@@ -91,79 +98,42 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
   while (!mbar_try(addr, parity)) {
   }
 }
-// for the producer warp: back off between polls so that the spin does not take issue slots from the consumers
+// for the service warps (producer, epilogue): back off between polls so that the spin does not
+// take issue slots from the consumers
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, unsigned parity) {
   const unsigned addr = smem_u32(bar);
-  while (!mbar_try(addr, parity)) __nanosleep(200);
+  while (!mbar_try(addr, parity)) __nanosleep(500);
 }
 __device__ __forceinline__ void named_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
-
-// ---------------------------------------------------------------------------
-// Shared-memory plan (run-time sizes: the largest patch of the packed mesh).  A CTA holds
-//   n_buf staging buffers   positions (+ seeds) of the patch-local vertices, event offsets, header
-//   n_teams event buffers   one per team of consumer warps
-// Every section starts on a 16-byte boundary.
-// ---------------------------------------------------------------------------
-struct PatchHdrS {  // header of the staged patch, written by the producer
-  int32_t v_lo, n_owned, n_halo, n_steps;
-  int32_t n_events, n_fac, halo_off, reserved;
-  int64_t step_off, fac_off;
-};
-
-struct PlanFlags {
-  bool seed, bfl, t2;       // staging arrays besides the positions
-  bool evA, evV, evG, evT;  // event arrays
-};
-
-struct Plan {
-  // offsets inside one staging buffer
-  unsigned oPos, oSeed, oPtr, oWords, oBfl, oT2, oHdr, in_bytes;
-  // offsets inside one event buffer
-  unsigned oEvA, oEvV, oEvG, oEvT, ev_bytes;
-  // whole window
-  unsigned oEv, oBars, oRed, total;
-};
-
-__host__ __device__ inline unsigned up16(unsigned x) { return (x + 15u) & ~15u; }
-
-__host__ __device__ inline Plan make_plan(const PlanFlags& f, int max_local, int max_owned, int max_events, int max_words,
-                                          int n_buf, int n_teams, int n_warps) {
-  Plan p;
-  const unsigned L = unsigned(max_local + 2), E = unsigned(max_events + 2);
-  unsigned o = 0;
-  p.oPos = o; o += up16(L * 24u);
-  p.oSeed = o; if (f.seed) o += up16(L * 40u);
-  p.oPtr = o; o += up16(unsigned(max_owned + 9) * 2u);
-  p.oWords = o; o += up16(unsigned(max_words) * 4u);
-  p.oBfl = o; if (f.bfl) o += up16(L * 4u);
-  p.oT2 = o; if (f.t2) o += up16(L * 8u);
-  p.oHdr = o; o += 64u;
-  p.in_bytes = o;
-  o = 0;
-  p.oEvA = o; if (f.evA) o += up16(E * 40u);
-  p.oEvV = o; if (f.evV) o += up16(E * 24u);
-  p.oEvG = o; if (f.evG) o += up16(E * 24u);
-  p.oEvT = o; if (f.evT) o += up16(E * 8u);
-  p.ev_bytes = o;
-  p.oEv = unsigned(n_buf) * p.in_bytes;
-  p.oBars = p.oEv + unsigned(n_teams) * p.ev_bytes;
-  p.oRed = p.oBars + 16u * unsigned(n_buf);
-  p.total = p.oRed + unsigned(n_warps + 1) * PS_COUNT * 8u;
-  return p;
+__device__ __forceinline__ void named_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
-constexpr int kMaxBuffers = 6;
+// ---------------------------------------------------------------------------
+// Shared-memory plan.  Capacities are compile-time so that strides fold into immediates;
+// the run-time pack parameters must stay within them (checked by the C-ABI layer).
+// ---------------------------------------------------------------------------
+constexpr int kACap = kPatchOwnedCap + kDumpRows;  // accumulator stride (owned rows + dump rows)
+static_assert(kPatchOwnedCap % 16 == 0 && kPatchLocalCap % 16 == 0 && kPatchSlotCap % 32 == 0, "capacities");
+using DevStrides = StaticStrides<kPatchLocalCap, kACap>;
 
-// Area-weighted unit normal of owned vertex i of a patch, read from GLOBAL memory (rare path: flat interior
-// vertices only).  Same facet order as vertex_normal_scan.
+struct PatchHdrS {  // header of the staged patch, written by the producer
+  int32_t v_lo, n_owned, n_halo, n_rounds;
+  int32_t n_slots, halo_off;
+  int64_t slot_off;
+};
+
+// Area-weighted unit normal of owned vertex i of a patch, read from GLOBAL memory (the epilogue
+// warps never touch the staging buffers).  Same record order as vertex_normal_scan.
 __device__ d3 vertex_normal_global(const PatchLaunch& a, const PatchHdrS& hs, int i) {
+  const FacetRec* recs = a.recs + hs.slot_off;
   const int32_t* ids = a.halo_ids + hs.halo_off;
-  const FacetRec* recs = a.recs + hs.fac_off;
   d3 n = make_d3(0, 0, 0);
-  for (int k = 0; k < hs.n_fac; ++k) {
+  for (int k = 0; k < hs.n_slots; ++k) {
     const FacetRec rec = recs[k];
+    if (!(rec.flags & REC_VALID)) continue;
     if (rec.a != i && rec.b != i && rec.c != i) continue;
     const int ra = rec.a < hs.n_owned ? hs.v_lo + rec.a : ids[rec.a - hs.n_owned];
     const int rb = rec.b < hs.n_owned ? hs.v_lo + rec.b : ids[rec.b - hs.n_owned];
@@ -176,156 +146,72 @@ __device__ d3 vertex_normal_global(const PatchLaunch& a, const PatchHdrS& hs, in
   return n;
 }
 
-template <int K, class S>
-__device__ __forceinline__ S& pick(S& s0, S& s1, S& s2) {
-  return K == 0 ? s0 : (K == 1 ? s1 : s2);
-}
-
-// Per-launch constants of the consumer loops.
-struct StepCtx {
-  uint32_t modules, flags;
-  double gamma_u, k_tilt;
-  const double* step_gamma;  // per step word, or nullptr
-  bool scalars_here;
+template <int PASS>
+struct Plan {
+  static constexpr int kInDoubles = (PASS == 0 ? 3 : 3 + kSeedStride) * kPatchLocalCap;  // pos (+ seeds)
+  static constexpr int kAccRows = PASS == 0 ? 5 : 6;
+  // byte offsets inside one input buffer
+  static constexpr size_t oPos = 0;
+  static constexpr size_t oSeed = size_t(3) * kPatchLocalCap * 8;
+  static constexpr size_t oRecs = size_t(kInDoubles) * 8;
+  static constexpr size_t oIds = oRecs + size_t(kPatchSlotCap) * sizeof(FacetRec);
+  static constexpr size_t oHdr = oIds + size_t(kPatchLocalCap) * 4;
+  static constexpr size_t kInBytes = oHdr + 32;
+  // whole window: in[2] | acc[2] | mbarriers | reduction scratch | optional arrays
+  static constexpr size_t oAcc = 2 * kInBytes;
+  static constexpr size_t kAccBytes = size_t(kAccRows) * kACap * 8;
+  static constexpr size_t oBars = oAcc + 2 * kAccBytes;
+  static constexpr size_t oMail = oBars + 64;   // PatchHdrS[2]: header handed to the epilogue warps
+  static constexpr size_t oRed = oMail + 64;
+  static constexpr size_t oOpt = oRed + size_t(kMaxConsumerWarps + 1) * PS_COUNT * 8;
 };
-
-// ---- pass A: one step on slot K.  `aux` walks the lane's restart rows. ----
-template <int K, bool BEND, bool VG>
-__device__ __forceinline__ void step_a(uint32_t w, const uint32_t*& aux, int lanes, SlotA& s0, SlotA& s1, SlotA& s2,
-                                       const LocalA& loc, const StepCtx& cx, const double* gam_p, double* sums) {
-  if (w & STEP_RESTART) {
-    const uint32_t ax0 = aux[0], ax1 = aux[lanes];
-    aux += 2 * lanes;
-    SlotA& n1 = pick<(K + 1) % 3>(s0, s1, s2);
-    SlotA& n2 = pick<(K + 2) % 3>(s0, s1, s2);
-    if (step_event(ax0) >= 0) slot_flush_a<BEND, VG>(n1, loc, step_event(ax0));
-    slot_load_a(n1, loc, step_index(ax0));
-    if (step_event(ax1) >= 0) slot_flush_a<BEND, VG>(n2, loc, step_event(ax1));
-    slot_load_a(n2, loc, step_index(ax1));
-  }
-  SlotA& me = pick<K>(s0, s1, s2);
-  if (step_event(w) >= 0) slot_flush_a<BEND, VG>(me, loc, step_event(w));
-  if (w & STEP_COMPUTE) {  // every step that evaluates a facet also loads its slot (ms_pack.cpp); others are no-ops
-    slot_load_a<false>(me, loc, step_index(w));
-    const double gam = gam_p ? *gam_p : cx.gamma_u;
-    step_compute_a<BEND, VG, K>(s0, s1, s2, w, gam, cx.modules, cx.k_tilt, sums);
-  }
+// optional arrays (after the fixed part): bfl[2][L] i32, t2[2][L] f64, accAb[2][ACap] f64
+__host__ __device__ inline size_t opt_bytes(bool boundary, bool tilt, bool tilt_acc) {
+  size_t n = 0;
+  if (boundary) n += 2 * size_t(kPatchLocalCap) * 4;
+  if (tilt) n += 2 * size_t(kPatchLocalCap) * 8;
+  if (tilt_acc) n += 2 * size_t(kACap) * 8;
+  return n;
 }
 
-template <int K, bool BEND, bool VG, bool TILT>
-__device__ __forceinline__ void step_b(uint32_t w, const uint32_t*& aux, int lanes, SlotB& s0, SlotB& s1, SlotB& s2,
-                                       const LocalB& loc, const StepCtx& cx, const double* gam_p, double* sums) {
-  if (w & STEP_RESTART) {
-    const uint32_t ax0 = aux[0], ax1 = aux[lanes];
-    aux += 2 * lanes;
-    SlotB& n1 = pick<(K + 1) % 3>(s0, s1, s2);
-    SlotB& n2 = pick<(K + 2) % 3>(s0, s1, s2);
-    if (step_event(ax0) >= 0) slot_flush_b<VG, TILT>(n1, loc, step_event(ax0));
-    slot_load_b<BEND>(n1, loc, step_index(ax0));
-    if (step_event(ax1) >= 0) slot_flush_b<VG, TILT>(n2, loc, step_event(ax1));
-    slot_load_b<BEND>(n2, loc, step_index(ax1));
-  }
-  SlotB& me = pick<K>(s0, s1, s2);
-  if (step_event(w) >= 0) slot_flush_b<VG, TILT>(me, loc, step_event(w));
-  if (w & STEP_COMPUTE) {  // every step that evaluates a facet also loads its slot (ms_pack.cpp); others are no-ops
-    slot_load_b<BEND, false>(me, loc, step_index(w));
-    const double gam = gam_p ? *gam_p : cx.gamma_u;
-    step_compute_b<BEND, VG, TILT, K>(s0, s1, s2, w, gam, cx.modules, cx.flags, cx.k_tilt, cx.scalars_here, sums);
-  }
-}
-
-// The strip walk of one lane over one patch (device form of walk_lane, ms_patch_body.cuh).  `words` points at
-// the lane's column of the patch's step words in SHARED memory (staged by the producer with the rest of the
-// patch: the consumers never wait for global memory); n_steps is a multiple of 3 (ms_pack.cpp pads with no-op
-// rows).  The word of step s + 1 is read while step s is evaluated.
-template <bool BEND, bool VG>
-__device__ __forceinline__ void walk_a(const uint32_t* words, int lanes, int n_steps, const LocalA& loc, const StepCtx& cx,
-                                       const double* gam, double* sums) {
-  SlotA s0, s1, s2;
-  s0.p = s1.p = s2.p = make_d3(0, 0, 0);
-  s0.bnd = s1.bnd = s2.bnd = 0;
-  s0.t2 = s1.t2 = s2.t2 = 0.0;
-  slot_clear_a(s0); slot_clear_a(s1); slot_clear_a(s2);
-  const uint32_t* aux = words + (n_steps + 3) * lanes;
-  uint32_t w0 = words[0];
-  for (int s = 0; s < n_steps; s += 3) {
-    const uint32_t* row = words + s * lanes;
-    const double* g = gam ? gam + size_t(s) * lanes : nullptr;
-    const uint32_t w1 = row[lanes];
-    step_a<0, BEND, VG>(w0, aux, lanes, s0, s1, s2, loc, cx, g, sums);
-    const uint32_t w2 = row[2 * lanes];
-    step_a<1, BEND, VG>(w1, aux, lanes, s0, s1, s2, loc, cx, g ? g + lanes : nullptr, sums);
-    w0 = row[3 * lanes];
-    step_a<2, BEND, VG>(w2, aux, lanes, s0, s1, s2, loc, cx, g ? g + 2 * lanes : nullptr, sums);
-  }
-  // tail rows: w0 holds row n_steps
-  const uint32_t t1 = words[(n_steps + 1) * lanes], t2 = words[(n_steps + 2) * lanes];
-  if (step_event(w0) >= 0) slot_flush_a<BEND, VG>(s0, loc, step_event(w0));
-  if (step_event(t1) >= 0) slot_flush_a<BEND, VG>(s1, loc, step_event(t1));
-  if (step_event(t2) >= 0) slot_flush_a<BEND, VG>(s2, loc, step_event(t2));
-}
-
-template <bool BEND, bool VG, bool TILT>
-__device__ __forceinline__ void walk_b(const uint32_t* words, int lanes, int n_steps, const LocalB& loc, const StepCtx& cx,
-                                       const double* gam, double* sums) {
-  SlotB s0, s1, s2;
-  s0.p = s1.p = s2.p = make_d3(0, 0, 0);
-  s0.f = s1.f = s2.f = make_d3(0, 0, 0);
-  s0.fe = s1.fe = s2.fe = s0.fv = s1.fv = s2.fv = 0.0;
-  s0.bnd = s1.bnd = s2.bnd = 0;
-  s0.t2 = s1.t2 = s2.t2 = 0.0;
-  slot_clear_b(s0); slot_clear_b(s1); slot_clear_b(s2);
-  const uint32_t* aux = words + (n_steps + 3) * lanes;
-  uint32_t w0 = words[0];
-  for (int s = 0; s < n_steps; s += 3) {
-    const uint32_t* row = words + s * lanes;
-    const double* g = gam ? gam + size_t(s) * lanes : nullptr;
-    const uint32_t w1 = row[lanes];
-    step_b<0, BEND, VG, TILT>(w0, aux, lanes, s0, s1, s2, loc, cx, g, sums);
-    const uint32_t w2 = row[2 * lanes];
-    step_b<1, BEND, VG, TILT>(w1, aux, lanes, s0, s1, s2, loc, cx, g ? g + lanes : nullptr, sums);
-    w0 = row[3 * lanes];
-    step_b<2, BEND, VG, TILT>(w2, aux, lanes, s0, s1, s2, loc, cx, g ? g + 2 * lanes : nullptr, sums);
-  }
-  const uint32_t t1 = words[(n_steps + 1) * lanes], t2 = words[(n_steps + 2) * lanes];
-  if (step_event(w0) >= 0) slot_flush_b<VG, TILT>(s0, loc, step_event(w0));
-  if (step_event(t1) >= 0) slot_flush_b<VG, TILT>(s1, loc, step_event(t1));
-  if (step_event(t2) >= 0) slot_flush_b<VG, TILT>(s2, loc, step_event(t2));
+__device__ __forceinline__ FacetRec load_rec(const FacetRec* p) {
+  const uint2 w = *reinterpret_cast<const uint2*>(p);
+  FacetRec r;
+  r.a = uint16_t(w.x & 0xffffu);
+  r.b = uint16_t(w.x >> 16);
+  r.c = uint16_t(w.y & 0xffffu);
+  r.flags = uint16_t(w.y >> 16);
+  return r;
 }
 
 // ---------------------------------------------------------------------------
 // The persistent patch kernel.  PASS 0 = pass A (curvature accumulation, per-facet scalars,
-// vertex stage -> seeds, and dV/dx when a gradient evaluation with bending follows; alone it is the
-// energy-only evaluation of the line search); PASS 1 = pass B (shape gradient of surface + bending
-// (+ tilt magnitude); dV/dx when pass A did not run).
-//
-// One CTA per SM walks patches blockIdx.x, +gridDim.x, ...  Warp roles: the last warp is the PRODUCER:
-// it stages patch j into staging buffer j % n_buf -- one bulk copy per contiguous array (owned
-// position rows, owned seed rows, event offsets), 8-byte asynchronous copies for the halo rows -- and
-// hands it over through a full/empty mbarrier pair.  The other warps form n_teams TEAMS; team t takes
-// the CTA's patches t, t + n_teams, ...: its lanes walk their strip pieces (registers only, event rows
-// are plain stores), meet at the team's named barrier, then each lane sums the event rows of its
-// owned vertices in row order and writes their output rows; a second barrier frees the team's event
-// buffer.  While one team is in its epilogue or waits for a patch, the others keep the fp64 pipe busy.
-//
-// KIND fixes parts of the configuration at compile time: 1 = headline (closed mesh, uniform
-// gamma / kappa / c0, surface + Helfrich analytic + volume), 2 = surface and/or volume only,
-// 3 = bending with run-time parameters but no tilt, 0 = everything at run time.
+// vertex stage -> seeds; alone it is the energy-only evaluation of the line search);
+// PASS 1 = pass B (shape gradient of surface + bending (+ tilt magnitude) and dV/dx).
+// FAST fixes the configuration of the headline workload at compile time: closed mesh,
+// uniform gamma / kappa / c0, surface + Helfrich bending (analytic) + volume, no tilt.
 // ---------------------------------------------------------------------------
 constexpr uint32_t kFastModules = MS_MOD_SURFACE | MS_MOD_BENDING | MS_MOD_VOLUME;
 
-template <int PASS, int KIND>
-__global__ void __launch_bounds__(kPatchThreads, 1) k_patch(const PatchLaunch a, const PlanFlags pf, const Plan pl, bool bending_b,
-                                                            bool scalars_here_arg) {
+// Warp roles inside the 512-thread CTA: warps [0, NC/32) are consumers, warp NC/32 runs the
+// patch epilogues, the last warp is the producer.
+template <int PASS, int KIND, int NC>
+__global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bending_b, bool scalars_here_arg) {
   extern __shared__ __align__(128) unsigned char smem[];
+  using P = Plan<PASS>;
+  const DevStrides ST{};
   const int tid = threadIdx.x;
-  const int lanes = a.threads;                 // lanes of one team
-  const int n_teams = a.teams;
-  const int n_buf = n_teams + 1;
-  const int n_cons = lanes * n_teams;          // consumer threads; the producer warp follows
+  const int T = a.threads;
+  int G = NC / T;
+  if (G > kMaxGroups) G = kMaxGroups;
+  const int n_active = G * T;  // consumer threads that take turns
+  const int n_epi_warps = (NC + 32 - n_active) / 32;  // every warp between consumers and producer
   const int n_my = a.patch_count > int(blockIdx.x) ? (a.patch_count - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x) : 0;
 
-  constexpr bool FAST = KIND == 1 || KIND == 2;
+  // KIND 0: everything decided at run time.  KIND 1 (headline): surface + Helfrich bending (analytic) +
+  // volume, closed mesh, uniform parameters.  KIND 2: surface and/or volume only, uniform gamma (boundary
+  // flags are irrelevant without bending).
+  constexpr bool FAST = KIND == 1 || KIND == 2;  // KIND 3: run-time parameters but no tilt module
   const uint32_t modules = KIND == 1 ? kFastModules
                            : KIND == 2 ? (a.modules & (MS_MOD_SURFACE | MS_MOD_VOLUME)) : a.modules;
   const uint32_t flags = FAST ? 0u : a.flags;
@@ -336,267 +222,278 @@ __global__ void __launch_bounds__(kPatchThreads, 1) k_patch(const PatchLaunch a,
                           : (PASS == 0 ? (modules & (MS_MOD_BENDING | MS_MOD_BENDING_TILT)) != 0 : bending_b);
   const bool do_volume = KIND == 1 ? true : (modules & MS_MOD_VOLUME) != 0;
   const bool scalars_here = (KIND == 1 || KIND == 3) ? false : scalars_here_arg;
-  // dV/dx: produced by pass A when it runs ahead of a gradient evaluation, else by pass B
-  const bool vg_here = PASS == 0 ? (do_bending && do_volume && a.volgrad_in_a != 0 && a.volgrad != nullptr)
-                                 : (!do_bending && do_volume && a.volgrad != nullptr);
   const bool want_epi = PASS == 1 || do_bending;  // pass A without bending accumulates nothing
 
-  // pf / pl: the staging and event arrays of this launch and their offsets (computed by the host: plan_flags, make_plan)
-  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + pl.oBars);
-  uint64_t* bar_empty = bar_full + n_buf;
-  double* red = reinterpret_cast<double*>(smem + pl.oRed);
+  // mbarriers: full[2] producer -> all; empty[2] consumers (+ epilogue in pass A) -> producer;
+  // acc_done[2] last round's group -> epilogue; acc_free[2] epilogue -> consumers
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P::oBars);
+  uint64_t* bar_full = bars;
+  uint64_t* bar_empty = bars + 2;
+  uint64_t* bar_done = bars + 4;
+  uint64_t* bar_free = bars + 6;
+  double* red = reinterpret_cast<double*>(smem + P::oRed);
+  unsigned char* opt = smem + P::oOpt;
+  int32_t* bfl_base = nullptr;
+  double* t2_base = nullptr;
+  double* ab_base = nullptr;
+  if (has_boundary) { bfl_base = reinterpret_cast<int32_t*>(opt); opt += 2 * size_t(kPatchLocalCap) * 4; }
+  if (do_tilt) { t2_base = reinterpret_cast<double*>(opt); opt += 2 * size_t(kPatchLocalCap) * 8; }
+  if (do_tilt && PASS == 1) { ab_base = reinterpret_cast<double*>(opt); }
+
+  PatchHdrS* mail = reinterpret_cast<PatchHdrS*>(smem + P::oMail);
   if (tid == 0) {
-    for (int b = 0; b < n_buf; ++b) {
+    for (int b = 0; b < 2; ++b) {
       mbar_init(&bar_full[b], 32);
-      mbar_init(&bar_empty[b], unsigned(lanes / 32));
+      mbar_init(&bar_empty[b], unsigned(n_active / 32));
+      mbar_init(&bar_done[b], unsigned(T));
+      mbar_init(&bar_free[b], 32u * unsigned(n_epi_warps));
     }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  {  // zero both accumulator buffers (and the tilt area accumulators)
+    double* acc0 = reinterpret_cast<double*>(smem + P::oAcc);
+    for (int j = tid; j < 2 * P::kAccRows * kACap; j += NC + 64) acc0[j] = 0.0;
+    if (ab_base)
+      for (int j = tid; j < 2 * kACap; j += NC + 64) ab_base[j] = 0.0;
   }
   __syncthreads();
+
+  if (tid >= NC + 32) {
+    // =========================== producer warp ===========================
+    const int lane = tid - (NC + 32);
+    for (int j = 0; j < n_my; ++j) {
+      const int b = j & 1;
+      const int pidx = a.patch_begin + int(blockIdx.x) + j * int(gridDim.x);
+      const int pid = a.patch_list ? a.patch_list[pidx] : pidx;
+      if (j >= 2) mbar_wait_relaxed(&bar_empty[b], unsigned(((j >> 1) - 1) & 1));
+      const PatchHeader h = a.patches[pid];
+      const int n_slots = int(a.patches[pid + 1].slot_off - h.slot_off);  // sentinel header at the end
+      unsigned char* in = smem + size_t(b) * P::kInBytes;
+      double* pos = reinterpret_cast<double*>(in + P::oPos);
+      double* seed = reinterpret_cast<double*>(in + P::oSeed);
+      FacetRec* recs = reinterpret_cast<FacetRec*>(in + P::oRecs);
+      int32_t* ids = reinterpret_cast<int32_t*>(in + P::oIds);
+      if (lane == 0) {
+        PatchHdrS* hs = reinterpret_cast<PatchHdrS*>(in + P::oHdr);
+        hs->v_lo = h.v_lo; hs->n_owned = h.n_owned; hs->n_halo = h.n_halo; hs->n_rounds = h.n_rounds;
+        hs->n_slots = n_slots; hs->halo_off = h.halo_off; hs->slot_off = h.slot_off;
+      }
+      const int Pn = h.n_owned;
+      {  // level 1: records (16-byte copies: slot_off and n_slots are multiples of 32), halo ids, owned rows
+        const FacetRec* src = a.recs + h.slot_off;
+        for (int k = lane; k < (n_slots >> 1); k += 32) cp_async16(recs + 2 * k, src + 2 * k);
+        const int32_t* hsrc = a.halo_ids + h.halo_off;
+        for (int k = lane; k < h.n_halo; k += 32) cp_async4(ids + k, hsrc + k);
+        const double* prow = a.pos + size_t(h.v_lo) * 3;
+        for (int i = lane; i < Pn; i += 32) {
+          cp_async8(pos + i, prow + 3 * i);
+          cp_async8(pos + kPatchLocalCap + i, prow + 3 * i + 1);
+          cp_async8(pos + 2 * kPatchLocalCap + i, prow + 3 * i + 2);
+        }
+        if (PASS == 1 && do_bending) {
+          const double* srow = a.seeds + size_t(h.v_lo) * kSeedStride;
+          for (int i = lane; i < Pn; i += 32) {
+#pragma unroll
+            for (int c = 0; c < kSeedStride; ++c) cp_async8(seed + c * kPatchLocalCap + i, srow + kSeedStride * i + c);
+          }
+        }
+      }
+      cp_async_wait_all();
+      __syncwarp();
+      // level 2: halo rows
+      for (int k = lane; k < h.n_halo; k += 32) {
+        const size_t row = size_t(ids[k]);
+        const int i = Pn + k;
+        const double* prow = a.pos + row * 3;
+        cp_async8(pos + i, prow);
+        cp_async8(pos + kPatchLocalCap + i, prow + 1);
+        cp_async8(pos + 2 * kPatchLocalCap + i, prow + 2);
+        if (PASS == 1 && do_bending) {
+          const double* srow = a.seeds + row * kSeedStride;
+#pragma unroll
+          for (int c = 0; c < kSeedStride; ++c) cp_async8(seed + c * kPatchLocalCap + i, srow + c);
+        }
+      }
+      if (has_boundary || do_tilt) {  // flags (int32) and |t|^2 ride the same asynchronous copies
+        int32_t* bf = has_boundary ? bfl_base + size_t(b) * kPatchLocalCap : nullptr;
+        double* t2 = do_tilt ? t2_base + size_t(b) * kPatchLocalCap : nullptr;
+        for (int i = lane; i < Pn; i += 32) {
+          if (bf) cp_async4(bf + i, a.boundary32 + h.v_lo + i);
+          if (t2) cp_async8(t2 + i, a.tilt_sq + h.v_lo + i);
+        }
+        for (int k = lane; k < h.n_halo; k += 32) {
+          const size_t row = size_t(ids[k]);
+          if (bf) cp_async4(bf + Pn + k, a.boundary32 + row);
+          if (t2) cp_async8(t2 + Pn + k, a.tilt_sq + row);
+        }
+      }
+      cp_async_wait_all();
+      mbar_arrive(&bar_full[b]);
+    }
+    return;
+  }
 
   double sums[PS_COUNT];
 #pragma unroll
   for (int k = 0; k < PS_COUNT; ++k) sums[k] = 0.0;
 
-  if (tid >= n_cons) {
-    // =========================== producer warp ===========================
-    // Software pipelined by one patch: while the copies of patch j are in flight, the header and the halo
-    // ids of patch j + 1 are fetched into registers, so that a freed staging buffer is refilled after ONE
-    // memory latency (no header -> ids -> rows chain in front of the copies).
-    const int lane = tid - n_cons;
-    constexpr int kIds = 10;  // halo ids per lane held in registers (320 per patch); more are read in place
-    auto patch_of = [&](int j) {
-      const int pidx = a.patch_begin + int(blockIdx.x) + j * int(gridDim.x);
-      return a.patch_list ? a.patch_list[pidx] : pidx;
-    };
-    PatchHeader h;
-    int64_t words_end = 0;
-    int32_t ids[kIds];
-    auto fetch = [&](int j) {
-      const int pid = patch_of(j);
-      h = a.patches[pid];
-      words_end = a.patches[pid + 1].step_off;  // a sentinel header closes the last patch
-      const int32_t* hsrc = a.halo_ids + h.halo_off;
-#pragma unroll
-      for (int q = 0; q < kIds; ++q) {
-        const int k = lane + 32 * q;
-        ids[q] = k < h.n_halo ? hsrc[k] : 0;
+  if (tid >= n_active) {
+    // =========================== epilogue warps ===========================
+    // After the last round of a patch has been accumulated: vertex stage + seeds (pass A) or
+    // gradient rows + KKT dot products (pass B) of the owned vertices; the accumulator is zeroed
+    // on the way and handed back to the consumers.
+    const int lane = tid - n_active;   // 0 .. 32*n_epi_warps-1: one owned vertex per lane and sweep
+    const int epi_threads = 32 * n_epi_warps;
+    const bool willmore = (flags & MS_FLAG_WILLMORE) != 0;
+    for (int j = 0; want_epi && j < n_my; ++j) {
+      const int b = j & 1;
+      mbar_wait_relaxed(&bar_done[b], unsigned((j >> 1) & 1));   // every round accumulated, header mailed
+      const PatchHdrS hs = mail[b];
+      double* acc = reinterpret_cast<double*>(smem + P::oAcc + size_t(b) * P::kAccBytes);
+      const int Pn = hs.n_owned;
+      LocalA la;
+      if (PASS == 0) {
+        la.pos = nullptr;
+        la.bfl = nullptr;  // boundary flags of the owned rows come from global memory below
+        la.t2 = nullptr;
+        la.acc = acc;
+        la.P = Pn;
       }
-    };
-    if (n_my > 0) fetch(0);
-    for (int j = 0; j < n_my; ++j) {
-      const int b = j % n_buf;
-      if (j >= n_buf) mbar_wait_relaxed(&bar_empty[b], unsigned((j / n_buf - 1) & 1));
-      unsigned char* in = smem + size_t(b) * pl.in_bytes;
-      double* pos = reinterpret_cast<double*>(in + pl.oPos);
-      double* seed = reinterpret_cast<double*>(in + pl.oSeed);
-      const int Pn = h.n_owned, Hn = h.n_halo, v_lo = h.v_lo;
-      const int32_t* hsrc = a.halo_ids + h.halo_off;
-      // rows [0, Pb) of the owned range move as bulk copies (16-byte aligned start, even row count)
-      const int Pb = (v_lo & 1) ? 0 : (Pn & ~1);
-      if (lane == 0) {
-        PatchHdrS* hs = reinterpret_cast<PatchHdrS*>(in + pl.oHdr);
-        hs->v_lo = h.v_lo; hs->n_owned = h.n_owned; hs->n_halo = h.n_halo; hs->n_steps = h.n_steps;
-        hs->n_events = h.n_events; hs->n_fac = h.n_fac; hs->halo_off = h.halo_off; hs->reserved = 0;
-        hs->step_off = h.step_off; hs->fac_off = h.fac_off;
-        const unsigned ptr_bytes = up16(unsigned(Pn + 1) * 2u);
-        const unsigned word_bytes = unsigned(words_end - h.step_off) * 4u;
-        unsigned tx = ptr_bytes + word_bytes + unsigned(Pb) * 24u;
-        if (pf.seed) tx += unsigned(Pb) * 40u;
-        mbar_expect_tx(&bar_full[b], tx);
-        bulk_copy(in + pl.oPtr, a.evt_ptr + h.evt_off, ptr_bytes, &bar_full[b]);
-        if (word_bytes) bulk_copy(in + pl.oWords, a.steps + h.step_off, word_bytes, &bar_full[b]);
-        if (Pb) {
-          bulk_copy(pos, a.pos + size_t(v_lo) * 3, unsigned(Pb) * 24u, &bar_full[b]);
-          if (pf.seed) bulk_copy(seed, a.seeds + size_t(v_lo) * kSeedStride, unsigned(Pb) * 40u, &bar_full[b]);
+      double* accAb = ab_base ? ab_base + size_t(b) * kACap : nullptr;
+      for (int i = lane; i < Pn; i += epi_threads) {
+        const size_t row = size_t(hs.v_lo) + i;
+        if (PASS == 0) {
+          const double kap = (!FAST && a.kappa) ? a.kappa[row] : a.kappa_u;
+          const double c0 = (!FAST && a.c0) ? a.c0[row] : a.c0_u;
+          auto normal_of = [&](int v) { return vertex_normal_global(a, hs, v); };
+          const bool on_boundary = has_boundary && a.is_boundary[row] != 0;
+          const VertexSeed sd = vertex_body_a(ST, i, la, on_boundary, normal_of, kap, c0, willmore);
+          sums[PS_E_BENDING] += sd.E;
+          if (a.seeds) {
+            double* o = a.seeds + row * kSeedStride;
+            o[0] = sd.fK.x; o[1] = sd.fK.y; o[2] = sd.fK.z; o[3] = sd.fAe; o[4] = sd.fAv;
+          }
+          if (!FAST) {
+            if (a.k_vecs) {
+              a.k_vecs[3 * row] = acc[i];
+              a.k_vecs[3 * row + 1] = acc[kACap + i];
+              a.k_vecs[3 * row + 2] = acc[2 * kACap + i];
+            }
+            if (a.a_vor) a.a_vor[row] = acc[3 * kACap + i];
+            if (a.a_eff) a.a_eff[row] = acc[4 * kACap + i];
+            if (a.e_vertex) a.e_vertex[row] = sd.E;
+          }
+#pragma unroll
+          for (int c = 0; c < 5; ++c) acc[c * kACap + i] = 0.0;
+        } else {
+          const double gx = acc[i], gy = acc[kACap + i], gz = acc[2 * kACap + i];
+          double* go = a.grad + 3 * row;
+          go[0] = gx; go[1] = gy; go[2] = gz;
+          sums[PS_G_G] += gx * gx + gy * gy + gz * gz;
+          acc[i] = 0.0; acc[kACap + i] = 0.0; acc[2 * kACap + i] = 0.0;
+          if (do_volume && a.volgrad) {
+            const double sixth = 1.0 / 6.0;  // the facets accumulated 6 dV/dx
+            const double vx = sixth * acc[3 * kACap + i], vy = sixth * acc[4 * kACap + i], vz = sixth * acc[5 * kACap + i];
+            double* vo = a.volgrad + 3 * row;
+            vo[0] = vx; vo[1] = vy; vo[2] = vz;
+            sums[PS_G_GC] += gx * vx + gy * vy + gz * vz;
+            sums[PS_GC_GC] += vx * vx + vy * vy + vz * vz;
+            acc[3 * kACap + i] = 0.0; acc[4 * kACap + i] = 0.0; acc[5 * kACap + i] = 0.0;
+          }
+          if (do_tilt && accAb) {
+            if (a.tilt_grad) {  // tilt.py:163-170: dE/dt_v = k_t t_v A_bary(v)
+              const double ab = accAb[i];
+              a.tilt_grad[3 * row] = a.k_tilt * a.tilts[3 * row] * ab;
+              a.tilt_grad[3 * row + 1] = a.k_tilt * a.tilts[3 * row + 1] * ab;
+              a.tilt_grad[3 * row + 2] = a.k_tilt * a.tilts[3 * row + 2] * ab;
+            }
+            accAb[i] = 0.0;
+          }
         }
       }
-      int32_t* bf = pf.bfl ? reinterpret_cast<int32_t*>(in + pl.oBfl) : nullptr;
-      double* t2 = pf.t2 ? reinterpret_cast<double*>(in + pl.oT2) : nullptr;
-      auto stage_row = [&](int i, size_t row) {  // one vertex row with 8-byte asynchronous copies
-        const double* prow = a.pos + row * 3;
-        cp_async8(pos + 3 * i, prow);
-        cp_async8(pos + 3 * i + 1, prow + 1);
-        cp_async8(pos + 3 * i + 2, prow + 2);
-        if (pf.seed) {
-          const double* srow = a.seeds + row * kSeedStride;
-#pragma unroll
-          for (int c = 0; c < kSeedStride; ++c) cp_async8(seed + kSeedStride * i + c, srow + c);
-        }
-        if (bf) cp_async4(bf + i, a.boundary32 + row);
-        if (t2) cp_async8(t2 + i, a.tilt_sq + row);
-      };
-#pragma unroll
-      for (int q = 0; q < kIds; ++q) {  // halo rows whose ids are already in registers
-        const int k = lane + 32 * q;
-        if (k < Hn) stage_row(Pn + k, size_t(ids[q]));
-      }
-      for (int k = lane + 32 * kIds; k < Hn; k += 32) stage_row(Pn + k, size_t(hsrc[k]));
-      for (int i = Pb + lane; i < Pn; i += 32) stage_row(i, size_t(v_lo) + i);  // owned rows outside the bulk copy
-      if (bf || t2) {  // flags (int32) and |t|^2 of the bulk-copied rows
-        for (int i = lane; i < Pb; i += 32) {
-          if (bf) cp_async4(bf + i, a.boundary32 + v_lo + i);
-          if (t2) cp_async8(t2 + i, a.tilt_sq + v_lo + i);
-        }
-      }
-      if (j + 1 < n_my) fetch(j + 1);  // in flight while the copies land
-      cp_async_wait_all();
-      mbar_arrive(&bar_full[b]);
+      mbar_arrive(&bar_free[b]);
     }
   } else {
     // ============================= consumers =============================
-    const int team = tid / lanes, lt = tid - team * lanes;
-    const int bar_id = 1 + team;
-    const bool willmore = (flags & MS_FLAG_WILLMORE) != 0;
-    StepCtx cx;
-    cx.modules = modules;
-    cx.flags = flags;
-    cx.gamma_u = a.gamma_u;
-    cx.k_tilt = a.k_tilt;
-    cx.step_gamma = (!FAST && a.step_gamma) ? a.step_gamma : nullptr;
-    cx.scalars_here = scalars_here;
-    unsigned char* evb = smem + pl.oEv + size_t(team) * pl.ev_bytes;
-    for (int j = team; j < n_my; j += n_teams) {
-      const int b = j % n_buf;
-      mbar_wait(&bar_full[b], unsigned((j / n_buf) & 1));
-      unsigned char* in = smem + size_t(b) * pl.in_bytes;
-      const PatchHdrS& hs = *reinterpret_cast<const PatchHdrS*>(in + pl.oHdr);  // fields are read where they are needed
-      const uint16_t* ptr = reinterpret_cast<const uint16_t*>(in + pl.oPtr);
-      const uint32_t* words = reinterpret_cast<const uint32_t*>(in + pl.oWords) + lt;
-      const double* gam = cx.step_gamma ? cx.step_gamma + hs.step_off + lt : nullptr;
+    const int grp = tid / T, lane = tid - grp * T;
+    const int bar_mine = 1 + grp, bar_next = 1 + (grp + 1 == G ? 0 : grp + 1);
+    const int ring = 2 * T;
+    const bool use_ring = G > 1;
+    if (use_ring && grp == G - 1) named_arrive(1, ring);  // group 0 owns the first token
+    int t_rel = grp;   // my next round, relative to the first round of the current patch
+    int64_t turns_done = 0;
+    for (int j = 0; j < n_my; ++j) {
+      const int b = j & 1;
+      mbar_wait(&bar_full[b], unsigned((j >> 1) & 1));
+      if (want_epi && j >= 2) mbar_wait(&bar_free[b], unsigned(((j >> 1) - 1) & 1));  // accumulator drained
+      unsigned char* in = smem + size_t(b) * P::kInBytes;
+      const PatchHdrS hs = *reinterpret_cast<const PatchHdrS*>(in + P::oHdr);
+      const FacetRec* recs = reinterpret_cast<const FacetRec*>(in + P::oRecs);
+      double* acc = reinterpret_cast<double*>(smem + P::oAcc + size_t(b) * P::kAccBytes);
       const int Pn = hs.n_owned;
+      // a patch without facets still takes one (empty) round so that its epilogue is triggered
+      const int n_turns = hs.n_rounds > 0 ? hs.n_rounds : 1;
+      const double* slot_gamma = (!FAST && a.slot_gamma) ? a.slot_gamma + hs.slot_off : nullptr;
+
+      LocalA la;
+      LocalB lb;
       if (PASS == 0) {
-        LocalA la;
-        la.pos = reinterpret_cast<const double*>(in + pl.oPos);
-        la.bfl = pf.bfl ? reinterpret_cast<const int32_t*>(in + pl.oBfl) : nullptr;
-        la.t2 = pf.t2 ? reinterpret_cast<const double*>(in + pl.oT2) : nullptr;
-        la.evA = reinterpret_cast<double*>(evb + pl.oEvA);
-        la.evV = reinterpret_cast<double*>(evb + pl.oEvV);
-        if (do_bending) {
-          if (vg_here) walk_a<true, true>(words, lanes, hs.n_steps, la, cx, gam, sums);
-          else walk_a<true, false>(words, lanes, hs.n_steps, la, cx, gam, sums);
-        } else {
-          walk_a<false, false>(words, lanes, hs.n_steps, la, cx, gam, sums);
-        }
-        if (want_epi) {
-          named_sync(bar_id, lanes);
-          // vertex stage + seeds (+ dV/dx rows) of the owned vertices
-          for (int i = lt; i < Pn; i += lanes) {
-            const size_t row = size_t(hs.v_lo) + i;
-            const VertexSumsA vs = vg_here ? vertex_sums_a<true, true>(la, ptr[i], ptr[i + 1])
-                                           : vertex_sums_a<true, false>(la, ptr[i], ptr[i + 1]);
-            const double kap = (!FAST && a.kappa) ? a.kappa[row] : a.kappa_u;
-            const double c0 = (!FAST && a.c0) ? a.c0[row] : a.c0_u;
-            const bool on_boundary = has_boundary && a.is_boundary[row] != 0;
-            auto normal_fn = [&]() { return vertex_normal_global(a, hs, i); };
-            const VertexSeed sd = vertex_body_a(vs, on_boundary, normal_fn, kap, c0, willmore);
-            sums[PS_E_BENDING] += sd.E;
-            if (a.seeds) {
-              double* o = a.seeds + row * kSeedStride;
-              o[0] = sd.fK.x; o[1] = sd.fK.y; o[2] = sd.fK.z; o[3] = sd.fAe; o[4] = sd.fAv;
-            }
-            if (vg_here) st3(a.volgrad, row, (1.0 / 6.0) * vs.vg);
-            if (!FAST) {
-              if (a.k_vecs) st3(a.k_vecs, row, vs.K);
-              if (a.a_vor) a.a_vor[row] = vs.va;
-              if (a.a_eff) a.a_eff[row] = vs.ve;
-              if (a.e_vertex) a.e_vertex[row] = sd.E;
-            }
-          }
-          named_sync(bar_id, lanes);  // every event row has been read: the next patch may overwrite them
-        }
+        la.pos = reinterpret_cast<const double*>(in + P::oPos);
+        la.bfl = has_boundary ? bfl_base + size_t(b) * kPatchLocalCap : nullptr;
+        la.t2 = do_tilt ? t2_base + size_t(b) * kPatchLocalCap : nullptr;
+        la.acc = acc;
+        la.P = Pn;
       } else {
-        LocalB lb;
-        lb.pos = reinterpret_cast<const double*>(in + pl.oPos);
-        lb.seed = reinterpret_cast<const double*>(in + pl.oSeed);
-        lb.bfl = pf.bfl ? reinterpret_cast<const int32_t*>(in + pl.oBfl) : nullptr;
-        lb.t2 = pf.t2 ? reinterpret_cast<const double*>(in + pl.oT2) : nullptr;
-        lb.evG = reinterpret_cast<double*>(evb + pl.oEvG);
-        lb.evV = reinterpret_cast<double*>(evb + pl.oEvV);
-        lb.evT = reinterpret_cast<double*>(evb + pl.oEvT);
-        if (KIND == 0) {
-          if (do_bending) {
-            if (do_tilt) walk_b<true, false, true>(words, lanes, hs.n_steps, lb, cx, gam, sums);
-            else walk_b<true, false, false>(words, lanes, hs.n_steps, lb, cx, gam, sums);
-          } else if (vg_here) {
-            if (do_tilt) walk_b<false, true, true>(words, lanes, hs.n_steps, lb, cx, gam, sums);
-            else walk_b<false, true, false>(words, lanes, hs.n_steps, lb, cx, gam, sums);
-          } else {
-            if (do_tilt) walk_b<false, false, true>(words, lanes, hs.n_steps, lb, cx, gam, sums);
-            else walk_b<false, false, false>(words, lanes, hs.n_steps, lb, cx, gam, sums);
-          }
-        } else if (KIND == 2) {
-          if (vg_here) walk_b<false, true, false>(words, lanes, hs.n_steps, lb, cx, gam, sums);
-          else walk_b<false, false, false>(words, lanes, hs.n_steps, lb, cx, gam, sums);
-        } else {
-          walk_b<true, false, false>(words, lanes, hs.n_steps, lb, cx, gam, sums);
-        }
-        named_sync(bar_id, lanes);
-        // dV/dx rows written by pass A (bending evaluations): issued ahead of the event sums that hide their latency
-        // (not ahead of the barrier: a register reload in front of it would wait for these loads)
-        constexpr int kPre = 3;
-        d3 vg_pre[kPre];
-        const bool vg_from_a = !vg_here && do_volume && a.volgrad != nullptr;
-        if (vg_from_a) {
-#pragma unroll
-          for (int q = 0; q < kPre; ++q) {
-            const int i = lt + q * lanes;
-            vg_pre[q] = i < Pn ? ld3(a.volgrad + 3 * size_t(hs.v_lo), i) : make_d3(0, 0, 0);
-          }
-        }
-        // gradient (+ dV/dx) rows of the owned vertices and the three KKT dot products
-        auto vertex_b = [&](int i, d3& g_out) {
-          const size_t row = size_t(hs.v_lo) + i;
-          VertexSumsB vs;
-          if (vg_here) vs = do_tilt ? vertex_sums_b<true, true>(lb, ptr[i], ptr[i + 1]) : vertex_sums_b<true, false>(lb, ptr[i], ptr[i + 1]);
-          else vs = do_tilt ? vertex_sums_b<false, true>(lb, ptr[i], ptr[i + 1]) : vertex_sums_b<false, false>(lb, ptr[i], ptr[i + 1]);
-          st3(a.grad, row, vs.g);
-          sums[PS_G_G] += dot(vs.g, vs.g);
-          g_out = vs.g;
-          if (vg_here) {
-            const d3 vg = (1.0 / 6.0) * vs.vg;
-            st3(a.volgrad, row, vg);
-            sums[PS_G_GC] += dot(vs.g, vg);
-            sums[PS_GC_GC] += dot(vg, vg);
-          }
-          if (do_tilt && a.tilt_grad) {  // tilt.py:163-170: dE/dt_v = k_t t_v A_bary(v)
-            a.tilt_grad[3 * row] = a.k_tilt * a.tilts[3 * row] * vs.ab;
-            a.tilt_grad[3 * row + 1] = a.k_tilt * a.tilts[3 * row + 1] * vs.ab;
-            a.tilt_grad[3 * row + 2] = a.k_tilt * a.tilts[3 * row + 2] * vs.ab;
-          }
-        };
-        d3 g_pre[kPre];
-#pragma unroll
-        for (int q = 0; q < kPre; ++q) {
-          const int i = lt + q * lanes;
-          g_pre[q] = make_d3(0, 0, 0);
-          if (i < Pn) vertex_b(i, g_pre[q]);
-        }
-        if (vg_from_a) {
-#pragma unroll
-          for (int q = 0; q < kPre; ++q) {  // rows beyond the patch carry zeros on both sides
-            sums[PS_G_GC] += dot(g_pre[q], vg_pre[q]);
-            sums[PS_GC_GC] += dot(vg_pre[q], vg_pre[q]);
-          }
-        }
-        for (int i = lt + kPre * lanes; i < Pn; i += lanes) {  // patches with more than kPre vertices per lane
-          d3 g;
-          vertex_b(i, g);
-          if (vg_from_a) {
-            const d3 vg = ld3(a.volgrad + 3 * size_t(hs.v_lo), i);
-            sums[PS_G_GC] += dot(g, vg);
-            sums[PS_GC_GC] += dot(vg, vg);
-          }
-        }
-        named_sync(bar_id, lanes);
+        lb.pos = reinterpret_cast<const double*>(in + P::oPos);
+        lb.seed = reinterpret_cast<const double*>(in + P::oSeed);
+        lb.bfl = has_boundary ? bfl_base + size_t(b) * kPatchLocalCap : nullptr;
+        lb.t2 = do_tilt ? t2_base + size_t(b) * kPatchLocalCap : nullptr;
+        lb.acc = acc;
+        lb.accAb = ab_base ? ab_base + size_t(b) * kACap : nullptr;
+        lb.P = Pn;
       }
-      // leaving the patch: its staging buffer may be refilled
+
+      for (; t_rel < n_turns; t_rel += G) {
+        const int slot = t_rel * T + lane;
+        FacetRec rec;
+        rec.a = rec.b = rec.c = 0; rec.flags = 0;
+        if (slot < hs.n_slots) rec = load_rec(recs + slot);
+        const bool valid = (rec.flags & REC_VALID) != 0;
+        if (PASS == 0) {
+          CornerA ca;
+          if (valid) {
+            const double gam = slot_gamma ? slot_gamma[slot] : a.gamma_u;
+            ca = facet_compute_a(ST, rec, gam, la, modules, a.k_tilt, sums);
+          }
+          if (use_ring) named_sync(bar_mine, ring); else named_sync(1, T);
+          if (valid && do_bending) facet_accumulate_a(ST, rec, ca, la, modules);
+        } else {
+          FacetOutB out;
+          if (valid) {
+            const double gam = slot_gamma ? slot_gamma[slot] : a.gamma_u;
+            out = do_bending ? facet_compute_b<true>(ST, rec, gam, lb, modules, flags, a.k_tilt, scalars_here, sums)
+                             : facet_compute_b<false>(ST, rec, gam, lb, modules, flags, a.k_tilt, scalars_here, sums);
+          }
+          if (use_ring) named_sync(bar_mine, ring); else named_sync(1, T);
+          if (valid) facet_accumulate_b(ST, rec, out, lb, do_volume, do_tilt);
+        }
+        // the last round of the patch hands the accumulator (and the header) to the epilogue warps
+        if (want_epi && t_rel == n_turns - 1) {
+          if (lane == 0) mail[b] = hs;
+          mbar_arrive(&bar_done[b]);
+        }
+        if (use_ring) named_arrive(bar_next, ring);
+      }
+      t_rel -= n_turns;
+      turns_done += n_turns;
+      // leaving the patch: its input buffer may be refilled
       __syncwarp();
       if ((tid & 31) == 0) mbar_arrive(&bar_empty[b]);
     }
+    // swallow the token left over by the last turn
+    if (use_ring && int(turns_done % G) == grp) named_sync(bar_mine, ring);
   }
 
-  block_sum<PS_COUNT>(sums, red, n_cons + 32, 15);
+  block_sum<PS_COUNT>(sums, red, NC + 32, 15);
   if (tid == 0) {
     double* p = a.partials + (size_t(a.partial_row0) + blockIdx.x) * kPartialStride;
 #pragma unroll
@@ -731,6 +628,9 @@ __device__ __forceinline__ bool soup_facet(const SoupArgs& s, int f, int& i0, in
   return i0 >= 0 && i0 < s.nv && i1 >= 0 && i1 < s.nv && i2 >= 0 && i2 < s.nv;
 }
 
+__device__ __forceinline__ void st3(double* p, size_t i, d3 v) {
+  p[3 * i] = v.x; p[3 * i + 1] = v.y; p[3 * i + 2] = v.z;
+}
 
 __global__ void k_soup_surface(SoupArgs s, const double* __restrict__ gamma, double* corner,
                                double* facet_e) {
@@ -1422,75 +1322,27 @@ int g_num_sms = 0;
 // compile-time kernel kind of a launch (see k_patch)
 int kernel_kind(const PatchLaunch& a) {
   const bool diag = a.k_vecs || a.a_vor || a.a_eff || a.e_vertex;
-  if (a.modules == kFastModules && a.flags == 0 && !a.is_boundary && !a.step_gamma && !a.kappa && !a.c0 && !diag &&
+  if (a.modules == kFastModules && a.flags == 0 && !a.is_boundary && !a.slot_gamma && !a.kappa && !a.c0 && !diag &&
       a.seeds && a.volgrad)
     return 1;
-  if ((a.modules & ~uint32_t(MS_MOD_SURFACE | MS_MOD_VOLUME)) == 0 && a.modules != 0 && !a.step_gamma && !diag &&
+  if ((a.modules & ~uint32_t(MS_MOD_SURFACE | MS_MOD_VOLUME)) == 0 && a.modules != 0 && !a.slot_gamma && !diag &&
       a.volgrad)
     return 2;
   if (!(a.modules & MS_MOD_TILT) && (a.modules & MS_MOD_BENDING) && a.seeds) return 3;  // run-time parameters, no tilt
   return 0;
 }
 
-// the staging / event arrays a launch needs: the same decisions as inside k_patch
-// template KIND a launch runs with
-int launched_kind(int pass, const PatchLaunch& a, bool bending, bool scalars_here) {
-  const int kind = kernel_kind(a);
-  if (pass == 0) return kind;
-  if (kind == 1 && bending && !scalars_here) return 1;
-  if (kind == 2 && !bending) return 2;
-  if (kind == 3 && bending && !scalars_here) return 3;
-  return 0;
-}
-
-PlanFlags plan_flags(int pass, int kind, const PatchLaunch& a, bool bending_b) {
-  const bool fast = kind == 1 || kind == 2;
-  const uint32_t modules = kind == 1 ? kFastModules : kind == 2 ? (a.modules & (MS_MOD_SURFACE | MS_MOD_VOLUME)) : a.modules;
-  const bool do_tilt = kind == 0 && (modules & MS_MOD_TILT) && a.tilts != nullptr;
-  const bool has_boundary = !fast && a.is_boundary != nullptr;
-  const bool do_bending = (kind == 1 || kind == 3) ? true
-                          : kind == 2 ? false
-                          : (pass == 0 ? (modules & (MS_MOD_BENDING | MS_MOD_BENDING_TILT)) != 0 : bending_b);
-  const bool do_volume = kind == 1 ? true : (modules & MS_MOD_VOLUME) != 0;
-  const bool vg_here = pass == 0 ? (do_bending && do_volume && a.volgrad_in_a != 0 && a.volgrad != nullptr)
-                                 : (!do_bending && do_volume && a.volgrad != nullptr);
-  PlanFlags f;
-  f.seed = pass == 1 && do_bending;
-  f.bfl = has_boundary;
-  f.t2 = do_tilt;
-  f.evA = pass == 0 && do_bending;
-  f.evV = vg_here;
-  f.evG = pass == 1;
-  f.evT = pass == 1 && do_tilt;
-  return f;
-}
-
-size_t patch_smem_bytes(int pass, const PatchLaunch& a, bool bending_b, int teams) {
-  const int warps = teams * (a.threads / 32);
-  const int kind = launched_kind(pass, a, bending_b, !bending_b);  // the callers sum the scalars in pass B iff pass A does not run
-  return make_plan(plan_flags(pass, kind, a, bending_b), a.max_local, a.max_owned, a.max_events, a.max_words, teams + 1, teams, warps + 1).total;
-}
-
-// Largest number of teams (of a.threads lanes) a pass can run with: bounded by the warps of a CTA and by the
-// shared memory its staging and event buffers need.  0: the patches do not fit at all.
-int fit_teams(int pass, const PatchLaunch& a, bool bending) {
-  const int w = a.threads / 32;
-  if (w <= 0) return 0;
-  int teams = (kPatchThreads / 32 - 1) / w;
-  if (teams > kMaxBuffers - 1) teams = kMaxBuffers - 1;
-  static const int forced = [] { const char* e = std::getenv("MS_TEAMS"); return e ? std::atoi(e) : 0; }();
-  if (forced > 0 && forced < teams) teams = forced;
-  while (teams > 0 && patch_smem_bytes(pass, a, bending, teams) > size_t(kPatchSmemBytes)) --teams;
-  return teams;
+template <int PASS>
+size_t patch_smem_bytes(const PatchLaunch& a) {
+  if (kernel_kind(a) == 1 || kernel_kind(a) == 2) return Plan<PASS>::oOpt;
+  const bool tilt = (a.modules & MS_MOD_TILT) && a.tilts;
+  return Plan<PASS>::oOpt + opt_bytes(a.is_boundary != nullptr, tilt, tilt && PASS == 1);
 }
 
 }  // namespace
 
-int patch_teams(int pass, const PatchLaunch& a, bool bending) { return fit_teams(pass, a, bending); }
-size_t patch_smem(int pass, const PatchLaunch& a, bool bending) {
-  const int t = fit_teams(pass, a, bending);
-  return t > 0 ? patch_smem_bytes(pass, a, bending, t) : 0;
-}
+size_t pass_a_smem_bytes(const PatchLaunch& a) { return patch_smem_bytes<0>(a); }
+size_t pass_b_smem_bytes(const PatchLaunch& a) { return patch_smem_bytes<1>(a); }
 
 cudaError_t configure_kernels() {
   int dev = 0;
@@ -1498,11 +1350,13 @@ cudaError_t configure_kernels() {
   if (e != cudaSuccess) return e;
   e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   if (e != cudaSuccess) return e;
-  const void* fns[] = {(const void*)k_patch<0, 0>, (const void*)k_patch<0, 1>, (const void*)k_patch<0, 2>,
-                       (const void*)k_patch<0, 3>, (const void*)k_patch<1, 0>, (const void*)k_patch<1, 1>,
-                       (const void*)k_patch<1, 2>, (const void*)k_patch<1, 3>};
+  const int max_dyn = 227 * 1024;
+  const void* fns[] = {(const void*)k_patch<0, 0, kConsumerThreads>, (const void*)k_patch<0, 1, kConsumerThreads>,
+                       (const void*)k_patch<0, 2, kConsumerThreads>, (const void*)k_patch<1, 0, kConsumerThreads>,
+                       (const void*)k_patch<1, 1, kConsumerThreads>, (const void*)k_patch<1, 2, kConsumerThreads>,
+                       (const void*)k_patch<0, 3, kConsumerThreads>, (const void*)k_patch<1, 3, kConsumerThreads>};
   for (const void* f : fns) {
-    e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kPatchSmemBytes);
+    e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
     if (e != cudaSuccess) return e;
   }
   return cudaSuccess;
@@ -1514,43 +1368,32 @@ int patch_grid(const PatchLaunch& a) {
   return a.patch_count < sms ? a.patch_count : sms;
 }
 
-cudaError_t launch_pass_a(const PatchLaunch& a_in, cudaStream_t st) {
-  if (a_in.patch_count <= 0) return cudaSuccess;
-  PatchLaunch a = a_in;
-  a.teams = fit_teams(0, a, false);
-  if (a.teams <= 0) return cudaErrorInvalidConfiguration;
-  const size_t smem = patch_smem_bytes(0, a, false, a.teams);
+cudaError_t launch_pass_a(const PatchLaunch& a, cudaStream_t st) {
+  if (a.patch_count <= 0) return cudaSuccess;
+  const size_t smem = patch_smem_bytes<0>(a);
   const int grid = patch_grid(a);
-  const int block = a.teams * a.threads + 32;
-  const int kind = kernel_kind(a);
-  const PlanFlags pf = plan_flags(0, kind, a, false);
-  const Plan pl = make_plan(pf, a.max_local, a.max_owned, a.max_events, a.max_words, a.teams + 1, a.teams, a.teams * (a.threads / 32) + 1);
-  switch (kind) {
-    case 1: k_patch<0, 1><<<grid, block, smem, st>>>(a, pf, pl, true, false); break;
-    case 2: k_patch<0, 2><<<grid, block, smem, st>>>(a, pf, pl, false, false); break;
-    case 3: k_patch<0, 3><<<grid, block, smem, st>>>(a, pf, pl, false, false); break;
-    default: k_patch<0, 0><<<grid, block, smem, st>>>(a, pf, pl, false, false);
+  switch (kernel_kind(a)) {
+    case 1: k_patch<0, 1, kConsumerThreads><<<grid, kConsumerThreads + 64, smem, st>>>(a, true, false); break;
+    case 2: k_patch<0, 2, kConsumerThreads><<<grid, kConsumerThreads + 64, smem, st>>>(a, false, false); break;
+    case 3: k_patch<0, 3, kConsumerThreads><<<grid, kConsumerThreads + 64, smem, st>>>(a, false, false); break;
+    default: k_patch<0, 0, kConsumerThreads><<<grid, kConsumerThreads + 64, smem, st>>>(a, false, false);
   }
   return cudaGetLastError();
 }
 
-cudaError_t launch_pass_b(const PatchLaunch& a_in, bool bending, bool scalars_here, cudaStream_t st) {
-  if (a_in.patch_count <= 0) return cudaSuccess;
-  PatchLaunch a = a_in;
-  a.teams = fit_teams(1, a, bending);
-  if (a.teams <= 0) return cudaErrorInvalidConfiguration;
-  const size_t smem = patch_smem_bytes(1, a, bending, a.teams);
+cudaError_t launch_pass_b(const PatchLaunch& a, bool bending, bool scalars_here, cudaStream_t st) {
+  if (a.patch_count <= 0) return cudaSuccess;
+  const size_t smem = patch_smem_bytes<1>(a);
   const int grid = patch_grid(a);
-  const int block = a.teams * a.threads + 32;
-  const int kind = launched_kind(1, a, bending, scalars_here);
-  const PlanFlags pf = plan_flags(1, kind, a, bending);
-  const Plan pl = make_plan(pf, a.max_local, a.max_owned, a.max_events, a.max_words, a.teams + 1, a.teams, a.teams * (a.threads / 32) + 1);
-  switch (kind) {
-    case 1: k_patch<1, 1><<<grid, block, smem, st>>>(a, pf, pl, true, false); break;
-    case 2: k_patch<1, 2><<<grid, block, smem, st>>>(a, pf, pl, false, scalars_here); break;
-    case 3: k_patch<1, 3><<<grid, block, smem, st>>>(a, pf, pl, bending, scalars_here); break;
-    default: k_patch<1, 0><<<grid, block, smem, st>>>(a, pf, pl, bending, scalars_here);
-  }
+  const int kind = kernel_kind(a);
+  if (kind == 1 && bending && !scalars_here)
+    k_patch<1, 1, kConsumerThreads><<<grid, kConsumerThreads + 64, smem, st>>>(a, true, false);
+  else if (kind == 2 && !bending)
+    k_patch<1, 2, kConsumerThreads><<<grid, kConsumerThreads + 64, smem, st>>>(a, false, scalars_here);
+  else if (kind == 3 && bending && !scalars_here)
+    k_patch<1, 3, kConsumerThreads><<<grid, kConsumerThreads + 64, smem, st>>>(a, bending, scalars_here);
+  else
+    k_patch<1, 0, kConsumerThreads><<<grid, kConsumerThreads + 64, smem, st>>>(a, bending, scalars_here);
   return cudaGetLastError();
 }
 

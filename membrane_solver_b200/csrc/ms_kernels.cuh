@@ -31,32 +31,31 @@ constexpr int kPartialStride = 12;  // per-patch partial sums: slots 0..11 above
 
 constexpr int kSeedStride = 5;  // per-vertex pass-A output: fK(3), fA_eff, fA_vor
 
-// CTA shape of the patch kernels: n_teams teams of `threads` lanes (consumer warps) + one producer warp.
-#ifndef MS_PATCH_THREADS
-#define MS_PATCH_THREADS 416
+// Compile-time capacities of a patch in shared memory (strides of the structure-of-arrays
+// staging buffers).  The run-time pack parameters must not exceed them.
+constexpr int kPatchOwnedCap = 512;   // owned vertices per patch
+constexpr int kPatchLocalCap = 896;   // owned + halo vertices per patch
+constexpr int kPatchSlotCap = 1536;   // record slots per patch (rounds x threads)
+#ifndef MS_CONSUMER_THREADS
+#define MS_CONSUMER_THREADS 448
 #endif
-// upper bound of the CTA size: consumer warps + the producer warp.  13 warps leave 128 registers per thread
-// (4 warps on one scheduler); 12 warps (-DMS_PATCH_THREADS=384) leave 168.
-constexpr int kPatchThreads = MS_PATCH_THREADS;
-constexpr int kMaxConsumerWarps = 12;
-constexpr int kPatchSmemBytes = 227 * 1024;
+constexpr int kConsumerThreads = MS_CONSUMER_THREADS;  // + one epilogue warp + one producer warp per CTA
+constexpr int kMaxConsumerWarps = kConsumerThreads / 32;
+constexpr int kMaxGroups = 14;        // thread groups taking turns (named barriers 1..14)
 
 struct PatchLaunch {
   // packed topology (device)
-  const PatchHeader* patches;  // n_patches + 1 entries: a sentinel closes the step-word range of the last patch
+  const PatchHeader* patches;  // n_patches + 1 entries: a sentinel closes the slot ranges
   const int32_t* halo_ids;
-  const uint32_t* steps;      // step words (ms_pack.h), padded behind the last patch
-  const uint16_t* evt_ptr;    // per patch n_owned + 1 event offsets
-  const FacetRec* recs;       // compact facet records (flat-vertex normals only)
-  const double* step_gamma;   // per step word: surface tension of its facet, or nullptr -> gamma_u
+  const FacetRec* recs;
+  const double* slot_gamma;   // per-slot surface tension, or nullptr -> gamma_u
   int32_t patch_begin, patch_count;
   const int32_t* patch_list;  // optional indirection: the launch walks patch_list[patch_begin + i], i < patch_count
   int32_t partial_row0;       // first row of `partials` this launch writes (one row per CTA)
   int32_t max_ctas;           // > 0: launch at most this many persistent CTAs (leave SMs to NCCL kernels)
-  int32_t threads;            // lanes of one team = lanes the mesh was packed for
-  int32_t teams;              // teams of consumer warps per CTA (set by the launch functions)
-  int32_t max_owned, max_local, max_events, max_steps, max_words;  // largest patch of the packed mesh
-  int32_t volgrad_in_a;       // pass A also produces dV/dx (a gradient evaluation with bending follows)
+  int32_t threads;            // record slots per round = lanes of one consumer group
+  int32_t max_owned, max_local;
+  int32_t max_slots, max_rounds;  // largest record count / round count of any patch
   // mesh state (device)
   const double* pos;          // (nv,3)
   const double* tilts;        // (nv,3) or nullptr
@@ -80,11 +79,8 @@ struct PatchLaunch {
   double* e_vertex;   // nv   per-vertex bending energy (bending.compute_energy_array)
 };
 
-// Teams of consumer warps (of a.threads lanes each) pass 0 / 1 runs with for this launch -- bounded by the warps of
-// a CTA and by the shared memory its staging and event buffers need; 0: the patches do not fit -- and the
-// dynamic shared memory of that launch.
-int patch_teams(int pass, const PatchLaunch& a, bool bending);
-size_t patch_smem(int pass, const PatchLaunch& a, bool bending);
+size_t pass_a_smem_bytes(const PatchLaunch& a);
+size_t pass_b_smem_bytes(const PatchLaunch& a);
 int patch_grid(const PatchLaunch& a);  // persistent CTAs launched for this patch range (= partial rows)
 
 // scalars_here: also sum the per-facet scalars (surface energy, area, volume).

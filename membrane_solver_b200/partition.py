@@ -380,7 +380,7 @@ def bench_multi_gpu(args, rank: int, world: int, local_rank: int, bench):
     pm = PartitionedMesh(local, local_rank, body_mask=np.ones(local.tri.shape[0], np.uint8),
                          reserve_sms=int(os.environ.get("MS_RESERVE_SMS", "0")),
                          pack=dict(threads=args.threads, max_owned=args.max_owned, max_local=args.max_local,
-                                   max_events=args.max_events, trim=args.trim))
+                                   fill_pct=args.fill, repair_sweeps=args.repair))
     dm = pm.dm
     dm.set_surface_tension(1.0)
     dm.set_bending_params(1.0, 0.0)

@@ -30,29 +30,24 @@ int emul_eval(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* is_boun
               double k_tilt, uint32_t modules, uint32_t flags, int32_t want_grad, int32_t threads,
               int32_t max_owned, int32_t max_local, double* scalars8, double* grad, double* volgrad,
               double* tilt_grad, double* seeds, double* k_vecs, double* a_vor, double* a_eff,
-              double* e_vertex, int64_t* pack_stats /*[n_patches,n_lane_steps,n_listed,max_steps,max_local,n_events,gather_groups,gather_excess,n_pieces,n_strips,n_warp_compute,max_events]*/,
+              double* e_vertex, int64_t* pack_stats /*[n_patches,n_slots,n_listed,max_rounds,max_local,lane_conflicts,hw_groups,hw_excess]*/,
               int32_t n_owned /* -1: all */, int32_t phase /* 0: A+B, 1: A only, 2: B only (seeds are input) */) {
   PackParams prm;
   prm.threads = threads;
   prm.max_owned = max_owned;
   prm.max_local = max_local;
-  prm.max_events = 4 * max_local;
   PackedMesh pk;
   const int rc = pack_patches(nv, nf, tri, body_mask, prm, pk, n_owned);
   if (rc) return rc;
   if (pack_stats) {
     pack_stats[0] = int64_t(pk.patches.size());
-    pack_stats[1] = pk.n_lane_steps;
+    pack_stats[1] = int64_t(pk.recs.size());
     pack_stats[2] = pk.n_listed;
-    pack_stats[3] = pk.max_steps;
+    pack_stats[3] = pk.max_rounds;
     pack_stats[4] = pk.max_local;
-    pack_stats[5] = pk.n_events;
-    pack_stats[6] = pk.n_gather_groups;
-    pack_stats[7] = pk.n_gather_excess;
-    pack_stats[8] = pk.n_pieces;
-    pack_stats[9] = pk.n_strips;
-    pack_stats[10] = pk.n_warp_compute;
-    pack_stats[11] = pk.max_events;
+    pack_stats[5] = pk.n_lane_conflicts;
+    pack_stats[6] = pk.n_hw_groups;
+    pack_stats[7] = pk.n_hw_excess;
   }
   const bool bt = (modules & MS_MOD_BENDING_TILT) != 0;
   const bool bending = (modules & (MS_MOD_BENDING | MS_MOD_BENDING_TILT)) != 0;
@@ -65,11 +60,7 @@ int emul_eval(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* is_boun
   }
   if (bt) modules = (modules & ~uint32_t(MS_MOD_BENDING_TILT)) | MS_MOD_BENDING;
   const bool do_tilt = (modules & MS_MOD_TILT) && tilts;
-  if (!do_tilt) modules &= ~uint32_t(MS_MOD_TILT);
-  const bool do_volume = (modules & MS_MOD_VOLUME) != 0;
   const bool willmore = (flags & MS_FLAG_WILLMORE) != 0;
-  // like the device path: pass A produces dV/dx when it runs for a gradient evaluation, else pass B does
-  const bool vg_in_a = bending && want_grad && do_volume;
   std::vector<double> seed_store(size_t(nv) * kSeedStrideBody, 0.0);
   if (phase == 2 && seeds) std::memcpy(seed_store.data(), seeds, seed_store.size() * sizeof(double));
   double total[PS_COUNT] = {0};
@@ -78,15 +69,17 @@ int emul_eval(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* is_boun
   // ---- pass A -------------------------------------------------------------
   if ((bending || !want_grad) && phase != 2) {
     for (const PatchHeader& h : pk.patches) {
-      const int P = h.n_owned, L = h.n_owned + h.n_halo, E = h.n_events;
-      const uint32_t* words = pk.steps.data() + size_t(h.step_off);
-      const uint16_t* ptr = pk.evt_ptr.data() + size_t(h.evt_off);
-      const FacetRec* recs = pk.recs.data() + size_t(h.fac_off);
-      std::vector<double> lpos(3 * size_t(L)), t2(size_t(L), 0.0), evA(5 * size_t(E) + 1, 0.0), evV(3 * size_t(E) + 1, 0.0);
+      const int P = h.n_owned, L = h.n_owned + h.n_halo;
+      DynamicStrides st;
+      st.L = L;
+      st.A = (P + 15) / 16 * 16 + kDumpRows;
+      const int n_slots = h.n_rounds * T;
+      const FacetRec* recs = pk.recs.data() + size_t(h.slot_off);
+      std::vector<double> lpos(3 * size_t(L)), t2(size_t(L), 0.0), acc(5 * size_t(st.A), 0.0);
       std::vector<int32_t> bfl(size_t(L), 0);
       for (int j = 0; j < L; ++j) {
         const int row = local_row(pk, h, j);
-        for (int k = 0; k < 3; ++k) lpos[3 * size_t(j) + k] = pos[3 * size_t(row) + k];
+        for (int k = 0; k < 3; ++k) lpos[size_t(k) * L + j] = pos[3 * size_t(row) + k];
         bfl[size_t(j)] = is_boundary ? is_boundary[row] : 0;
         if (do_tilt) {
           const double* t = tilts + 3 * size_t(row);
@@ -95,41 +88,28 @@ int emul_eval(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* is_boun
       }
       LocalA loc;
       loc.pos = lpos.data(); loc.bfl = bfl.data(); loc.t2 = do_tilt ? t2.data() : nullptr;
-      loc.evA = evA.data(); loc.evV = evV.data();
+      loc.acc = acc.data(); loc.P = P;
       double sums[PS_COUNT] = {0};
-      for (int lane = 0; lane < T; ++lane) {
-        SlotA sl[3];
-        for (auto& q : sl) { q.p = make_d3(0, 0, 0); q.bnd = 0; q.t2 = 0.0; slot_clear_a(q); }
-        auto load = [&](int k, int i) { slot_load_a(sl[k], loc, i); };
-        auto flush = [&](int k, int e) {
-          if (bending && vg_in_a) slot_flush_a<true, true>(sl[k], loc, e);
-          else if (bending) slot_flush_a<true, false>(sl[k], loc, e);
-        };
-        auto compute = [&](uint32_t w, int s) {
-          const size_t wi = size_t(h.step_off) + size_t(s) * size_t(T) + size_t(lane);
-          const double gam = gamma ? gamma[pk.step_facet[wi]] : gamma_u;
-          if (bending && vg_in_a) step_compute_a<true, true>(sl[0], sl[1], sl[2], w, gam, modules, k_tilt, sums);
-          else if (bending) step_compute_a<true, false>(sl[0], sl[1], sl[2], w, gam, modules, k_tilt, sums);
-          else step_compute_a<false, false>(sl[0], sl[1], sl[2], w, gam, modules, k_tilt, sums);
-        };
-        walk_lane(words + lane, T, h.n_steps, load, flush, compute);
+      for (int slot = 0; slot < n_slots; ++slot) {
+        const FacetRec rec = recs[slot];
+        if (!(rec.flags & REC_VALID)) continue;
+        const double gam = gamma ? gamma[pk.slot_facet[size_t(h.slot_off) + slot]] : gamma_u;
+        const CornerA c = facet_compute_a(st, rec, gam, loc, modules, k_tilt, sums);
+        facet_accumulate_a(st, rec, c, loc, modules);
       }
       if (bending) {
         for (int i = 0; i < P; ++i) {
           const size_t row = size_t(h.v_lo) + i;
-          const VertexSumsA a = vg_in_a ? vertex_sums_a<true, true>(loc, ptr[i], ptr[i + 1])
-                                        : vertex_sums_a<true, false>(loc, ptr[i], ptr[i + 1]);
-          auto normal_of = [&]() { return vertex_normal_scan(recs, h.n_fac, lpos.data(), i); };
-          const VertexSeed sd = vertex_body_a(a, bfl[size_t(i)] != 0, normal_of, kappa ? kappa[row] : kappa_u,
+          auto normal_of = [&](int v) { return vertex_normal_scan(st, recs, n_slots, lpos.data(), v); };
+          const VertexSeed sd = vertex_body_a(st, i, loc, bfl[size_t(i)] != 0, normal_of, kappa ? kappa[row] : kappa_u,
                                               c0 ? c0[row] : c0_u, willmore);
           sums[PS_E_BENDING] += sd.E;
           double* o = seed_store.data() + row * kSeedStrideBody;
           o[0] = sd.fK.x; o[1] = sd.fK.y; o[2] = sd.fK.z; o[3] = sd.fAe; o[4] = sd.fAv;
-          if (k_vecs) st3(k_vecs, int(row), a.K);
-          if (a_vor) a_vor[row] = a.va;
-          if (a_eff) a_eff[row] = a.ve;
+          if (k_vecs) for (int k = 0; k < 3; ++k) k_vecs[3 * row + k] = acc[size_t(k) * st.A + i];
+          if (a_vor) a_vor[row] = acc[3 * size_t(st.A) + i];
+          if (a_eff) a_eff[row] = acc[4 * size_t(st.A) + i];
           if (e_vertex) e_vertex[row] = sd.E;
-          if (vg_in_a && volgrad) st3(volgrad, int(row), (1.0 / 6.0) * a.vg);
         }
       }
       for (int k = 0; k < PS_COUNT; ++k) total[k] += sums[k];
@@ -156,20 +136,23 @@ int emul_eval(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* is_boun
   // ---- pass B -------------------------------------------------------------
   if (want_grad && phase != 1) {
     const bool scalars_here = !bending;
-    const bool vg_in_b = do_volume && !bending;
+    const bool do_volume = (modules & MS_MOD_VOLUME) != 0;
     double total_b[PS_COUNT] = {0};
     for (const PatchHeader& h : pk.patches) {
-      const int P = h.n_owned, L = h.n_owned + h.n_halo, E = h.n_events;
-      const uint32_t* words = pk.steps.data() + size_t(h.step_off);
-      const uint16_t* ptr = pk.evt_ptr.data() + size_t(h.evt_off);
-      std::vector<double> lpos(3 * size_t(L)), lseed(size_t(kSeedStrideBody) * size_t(L), 0.0), t2(size_t(L), 0.0),
-          evG(3 * size_t(E) + 1, 0.0), evV(3 * size_t(E) + 1, 0.0), evT(size_t(E) + 1, 0.0);
+      const int P = h.n_owned, L = h.n_owned + h.n_halo;
+      DynamicStrides st;
+      st.L = L;
+      st.A = (P + 15) / 16 * 16 + kDumpRows;
+      const int n_slots = h.n_rounds * T;
+      const FacetRec* recs = pk.recs.data() + size_t(h.slot_off);
+      std::vector<double> lpos(3 * size_t(L)), lseed(size_t(kSeedStrideBody) * size_t(L), 0.0),
+          t2(size_t(L), 0.0), acc(6 * size_t(st.A), 0.0), accAb(size_t(st.A), 0.0);
       std::vector<int32_t> bfl(size_t(L), 0);
       for (int j = 0; j < L; ++j) {
         const int row = local_row(pk, h, j);
-        for (int k = 0; k < 3; ++k) lpos[3 * size_t(j) + k] = pos[3 * size_t(row) + k];
+        for (int k = 0; k < 3; ++k) lpos[size_t(k) * L + j] = pos[3 * size_t(row) + k];
         for (int k = 0; k < kSeedStrideBody; ++k)
-          lseed[size_t(kSeedStrideBody) * j + k] = seed_store[size_t(row) * kSeedStrideBody + k];
+          lseed[size_t(k) * L + j] = seed_store[size_t(row) * kSeedStrideBody + k];
         bfl[size_t(j)] = is_boundary ? is_boundary[row] : 0;
         if (do_tilt) {
           const double* t = tilts + 3 * size_t(row);
@@ -179,41 +162,24 @@ int emul_eval(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* is_boun
       LocalB loc;
       loc.pos = lpos.data(); loc.seed = lseed.data(); loc.bfl = bfl.data();
       loc.t2 = do_tilt ? t2.data() : nullptr;
-      loc.evG = evG.data(); loc.evV = evV.data(); loc.evT = evT.data();
+      loc.acc = acc.data(); loc.accAb = accAb.data(); loc.P = P;
       double sums[PS_COUNT] = {0};
-      for (int lane = 0; lane < T; ++lane) {
-        SlotB sl[3];
-        for (auto& q : sl) {
-          q.p = q.f = make_d3(0, 0, 0); q.fe = q.fv = q.t2 = 0.0; q.bnd = 0; slot_clear_b(q);
+      for (int slot = 0; slot < n_slots; ++slot) {
+        const FacetRec rec = recs[slot];
+        if (!(rec.flags & REC_VALID)) continue;
+        const double gam = gamma ? gamma[pk.slot_facet[size_t(h.slot_off) + slot]] : gamma_u;
+        const FacetOutB o = bending
+            ? facet_compute_b<true>(st, rec, gam, loc, modules, flags, k_tilt, scalars_here, sums)
+            : facet_compute_b<false>(st, rec, gam, loc, modules, flags, k_tilt, scalars_here, sums);
+        facet_accumulate_b(st, rec, o, loc, do_volume, do_tilt);
+      }
+      for (int i = 0; i < P; ++i)
+        for (int k = 0; k < 3; ++k) {
+          const size_t o = (size_t(h.v_lo) + i) * 3 + size_t(k);
+          if (grad) grad[o] = acc[size_t(k) * st.A + i];
+          if (volgrad && do_volume) volgrad[o] = (1.0 / 6.0) * acc[size_t(3 + k) * st.A + i];
+          if (tilt_grad && do_tilt) tilt_grad[o] = k_tilt * tilts[o] * accAb[size_t(i)];
         }
-        auto load = [&](int k, int i) {
-          if (bending) slot_load_b<true>(sl[k], loc, i); else slot_load_b<false>(sl[k], loc, i);
-        };
-        auto flush = [&](int k, int e) { slot_flush_b<true, true>(sl[k], loc, e); };
-        auto compute = [&](uint32_t w, int s) {
-          const size_t wi = size_t(h.step_off) + size_t(s) * size_t(T) + size_t(lane);
-          const double gam = gamma ? gamma[pk.step_facet[wi]] : gamma_u;
-          if (bending) {
-            if (do_tilt) step_compute_b<true, false, true>(sl[0], sl[1], sl[2], w, gam, modules, flags, k_tilt, scalars_here, sums);
-            else step_compute_b<true, false, false>(sl[0], sl[1], sl[2], w, gam, modules, flags, k_tilt, scalars_here, sums);
-          } else if (vg_in_b) {
-            if (do_tilt) step_compute_b<false, true, true>(sl[0], sl[1], sl[2], w, gam, modules, flags, k_tilt, scalars_here, sums);
-            else step_compute_b<false, true, false>(sl[0], sl[1], sl[2], w, gam, modules, flags, k_tilt, scalars_here, sums);
-          } else {
-            if (do_tilt) step_compute_b<false, false, true>(sl[0], sl[1], sl[2], w, gam, modules, flags, k_tilt, scalars_here, sums);
-            else step_compute_b<false, false, false>(sl[0], sl[1], sl[2], w, gam, modules, flags, k_tilt, scalars_here, sums);
-          }
-        };
-        walk_lane(words + lane, T, h.n_steps, load, flush, compute);
-      }
-      for (int i = 0; i < P; ++i) {
-        const VertexSumsB a = vertex_sums_b<true, true>(loc, ptr[i], ptr[i + 1]);
-        const size_t row = size_t(h.v_lo) + i;
-        if (grad) st3(grad, int(row), a.g);
-        if (volgrad && vg_in_b) st3(volgrad, int(row), (1.0 / 6.0) * a.vg);
-        if (tilt_grad && do_tilt)
-          for (int k = 0; k < 3; ++k) tilt_grad[3 * row + k] = k_tilt * tilts[3 * row + k] * a.ab;
-      }
       for (int k = 0; k < PS_COUNT; ++k) total_b[k] += sums[k];
     }
     if (scalars_here)

@@ -90,7 +90,7 @@ def emulate(pos, tri, *, modules, flags=0, want_grad=True, is_boundary=None, bod
                seeds=(np.zeros((nv, 5)) if seeds is None else np.ascontiguousarray(seeds, dtype=np.float64).copy()),
                k_vecs=np.zeros((nv, 3)), a_vor=np.zeros(nv),
                a_eff=np.zeros(nv), e_vertex=np.zeros(nv))
-    stats = np.zeros(12, dtype=np.int64)
+    stats = np.zeros(8, dtype=np.int64)
     rc = _EMUL.emul_eval(
         ctypes.c_int32(nv), ctypes.c_int32(nf), tri.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
         bptr(u8(is_boundary)), bptr(u8(body_mask)), dptr(pos), dptr(f64(tilts)), dptr(f64(gamma)),
@@ -105,10 +105,9 @@ def emulate(pos, tri, *, modules, flags=0, want_grad=True, is_boundary=None, bod
         raise RuntimeError(f"emul_eval failed: {rc}")
     out.update(E_surface=scal[0], area=scal[1], volume=scal[2], E_bending=scal[3], E_tilt=scal[4],
                E_bending_tilt=scal[5],
-               pack=dict(n_patches=int(stats[0]), n_lane_steps=int(stats[1]), n_listed=int(stats[2]),
-                         max_steps=int(stats[3]), max_local=int(stats[4]), n_events=int(stats[5]),
-                         gather_groups=int(stats[6]), gather_excess=int(stats[7]), n_pieces=int(stats[8]),
-                         n_strips=int(stats[9]), n_warp_compute=int(stats[10]), max_events=int(stats[11])))
+               pack=dict(n_patches=int(stats[0]), n_slots=int(stats[1]), n_listed=int(stats[2]),
+                         max_rounds=int(stats[3]), max_local=int(stats[4]),
+                         lane_conflicts=int(stats[5]), hw_groups=int(stats[6]), hw_excess=int(stats[7])))
     return out
 
 

@@ -88,8 +88,7 @@ def _worker(rank, world, port, out_path):
     sc = torch.tensor([a["E_surface"], a["area"], a["volume"], a["E_bending"]], dtype=torch.float64)
     dist.all_reduce(sc)
     grads = [None] * world
-    # dV/dx of the owned rows comes out of pass A when a bending gradient evaluation follows (ms_kernels.cu)
-    dist.all_gather_object(grads, (local.lo, b["grad"][:local.n_owned], a["volgrad"][:local.n_owned]))
+    dist.all_gather_object(grads, (local.lo, b["grad"][:local.n_owned], b["volgrad"][:local.n_owned]))
     if rank == 0:
         g = np.zeros((nv, 3))
         vg = np.zeros((nv, 3))
