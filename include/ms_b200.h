@@ -47,6 +47,7 @@ extern "C" {
 #define MS_SC_G_GC           9
 #define MS_SC_GC_GC          10
 #define MS_SC_LAMBDA         11
+#define MS_SC_COEF           12 /* projected gradient = g + MS_SC_COEF * gC */
 #define MS_SC_COUNT          16
 
 /* ---- device arrays addressable through ms_ctx_device_ptr / ms_ctx_get_array --- */
@@ -293,16 +294,23 @@ MS_API int ms_ctx_allreduce_scalars(ms_ctx* ctx, int32_t count);
 /* 0 while every pull found its flags in time; 1 after a pull gave up waiting (~2 s) */
 MS_API int ms_ctx_halo_error(ms_ctx* ctx, int32_t* error);
 
-/* One evaluation with everything resident: pass A (+ pass B when want_grad), scalar
- * reduction, optional KKT/penalty/fixed post-processing.  Asynchronous on the context
- * stream; results stay on the device. */
+/* One evaluation with everything resident: pass A (+ pass B when want_grad); the last CTA of the last pass adds
+ * up the per-CTA sums in fixed order and writes the scalars and the KKT / penalty coefficient (no reduce or
+ * project launch).  The constraint projection g + MS_SC_COEF * gC and the fixed-row mask are DEFERRED: they are
+ * applied by the consumer of the gradient (ms_ctx_direction_from_gradient, ms_ctx_line_search_stats) or, in
+ * place, by the first call that exposes MS_ARR_GRAD (ms_ctx_get_array, ms_ctx_device_ptr, ms_ctx_eval_host, ...),
+ * so every caller of the ABI sees the projected gradient of runtime/constraint_manager.py:294-301.
+ * Asynchronous on the context stream; results stay on the device. */
 MS_API int ms_ctx_eval_async(ms_ctx* ctx, const ms_eval_opts* opts);
+/* the same in two calls (timing, overlap): stage 0 = pass A, stage 1 = pass B + finalisation */
+MS_API int ms_ctx_eval_stage(ms_ctx* ctx, const ms_eval_opts* opts, int32_t stage);
 /* the two halves, for the multi-GPU path (seed halo exchange happens between them) */
 MS_API int ms_ctx_eval_pass_a(ms_ctx* ctx, const ms_eval_opts* opts);
 MS_API int ms_ctx_eval_pass_b(ms_ctx* ctx, const ms_eval_opts* opts);
 MS_API int ms_ctx_eval_finish(ms_ctx* ctx, const ms_eval_opts* opts);
 /* ms_ctx_eval_finish = reduce (per-CTA running sums -> 12 scalars on the device) followed by
- * project (KKT / penalty / fixed mask).  Multi-GPU: all-reduce MS_ARR_SCALARS[0..11] between. */
+ * project (KKT / penalty coefficient from the scalars; the projection itself is deferred, see
+ * ms_ctx_eval_async).  Multi-GPU: all-reduce MS_ARR_SCALARS[0..11] between. */
 MS_API int ms_ctx_eval_reduce(ms_ctx* ctx, const ms_eval_opts* opts);
 MS_API int ms_ctx_eval_project(ms_ctx* ctx, const ms_eval_opts* opts);
 /* synchronise and copy the 16 scalars to the host */

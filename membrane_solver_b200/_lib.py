@@ -23,7 +23,7 @@ FLAG_WILLMORE, FLAG_APPROX = 1, 2
 PATCHES_ALL, PATCHES_INTERIOR, PATCHES_BOUNDARY = -1, -2, -3
 
 SC_E_SURFACE, SC_AREA, SC_VOLUME, SC_E_BENDING, SC_E_TILT, SC_E_BENDING_TILT = 0, 1, 2, 3, 4, 5
-SC_G_G, SC_G_GC, SC_GC_GC, SC_LAMBDA, SC_COUNT = 8, 9, 10, 11, 16
+SC_G_G, SC_G_GC, SC_GC_GC, SC_LAMBDA, SC_COEF, SC_COUNT = 8, 9, 10, 11, 12, 16
 
 ARR_POSITIONS, ARR_GRAD, ARR_VOLGRAD, ARR_SEEDS, ARR_TILTS, ARR_TILT_GRAD = 0, 1, 2, 3, 4, 5
 ARR_SCALARS, ARR_K_VECS, ARR_A_VOR, ARR_A_EFF, ARR_E_VERTEX, ARR_TRIAL, ARR_DIRECTION = 6, 7, 8, 9, 10, 11, 12
@@ -128,6 +128,7 @@ SIGNATURES = {
     "ms_ctx_array_len": (_i64, [_V, ctypes.c_int]),
     "ms_ctx_set_stream": (ctypes.c_int, [_V, _V]),
     "ms_ctx_eval_async": (ctypes.c_int, [_V, ctypes.POINTER(EvalOpts)]),
+    "ms_ctx_eval_stage": (ctypes.c_int, [_V, ctypes.POINTER(EvalOpts), _i32]),
     "ms_ctx_eval_pass_a": (ctypes.c_int, [_V, ctypes.POINTER(EvalOpts)]),
     "ms_ctx_eval_pass_b": (ctypes.c_int, [_V, ctypes.POINTER(EvalOpts)]),
     "ms_ctx_eval_finish": (ctypes.c_int, [_V, ctypes.POINTER(EvalOpts)]),

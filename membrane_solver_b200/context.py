@@ -337,6 +337,10 @@ class DeviceMesh:
     def eval_async(self, opts: L.EvalOpts) -> None:
         L.check(self._lib.ms_ctx_eval_async(self._h, ctypes.byref(opts)))
 
+    def eval_stage(self, opts: L.EvalOpts, stage: int) -> None:
+        """Stage 0 = pass A, stage 1 = pass B + fused finalisation (ms_ctx_eval_async in two calls)."""
+        L.check(self._lib.ms_ctx_eval_stage(self._h, ctypes.byref(opts), int(stage)))
+
     def eval_pass_a(self, opts: L.EvalOpts) -> None:
         L.check(self._lib.ms_ctx_eval_pass_a(self._h, ctypes.byref(opts)))
 

@@ -80,6 +80,13 @@ struct ms_ctx {
   DevBuf<double> d_pos, d_trial, d_dir, d_tilts, d_seeds, d_partials_a, d_partials_b, d_grad, d_volgrad,
       d_tilt_grad, d_scalars, d_dot_partials, d_kvecs, d_avor, d_aeff, d_evert;
   bool ran_pass_a = false;  // the last evaluation ran pass A (its per-CTA sums are current)
+  // Deferred KKT projection: MS_ARR_GRAD holds the raw energy gradient and scalars[SC_COEF] the coefficient; the
+  // projected gradient g + coef * gC (fixed rows zeroed) is formed by whoever consumes it (direction, dots) or
+  // materialised in place on first access through the ABI (flush_projection).
+  struct PendingProjection {
+    bool active = false, use_gc = false, use_fixed = false;
+  } proj;
+  DevBuf<unsigned int> d_ticket;  // last-CTA ticket of the fused finalisation
   bool has_gamma = false, has_kappa = false, has_c0 = false, has_boundary = false,
        has_fixed = false, has_body = false;
   double gamma_u = 1.0, kappa_u = 0.0, c0_u = 0.0, k_tilt = 0.0;
@@ -161,6 +168,15 @@ int check_ctx(const ms_ctx* c, bool need_topology) {
   if (!c) return fail(-1, "null context");
   if (need_topology && !c->have_topology) return fail(-2, "ms_ctx_set_topology has not been called");
   return use_device(c);
+}
+
+// Materialise a deferred projection in MS_ARR_GRAD (see ms_ctx::proj).
+int flush_projection(ms_ctx* c) {
+  if (!c->proj.active) return 0;
+  c->proj.active = false;
+  CU(ms::launch_apply_projection(c->d_grad.p, c->proj.use_gc ? c->d_volgrad.p : nullptr,
+                                 c->proj.use_fixed ? c->d_fixed.p : nullptr, c->n_owned, c->d_scalars.p, c->stream));
+  return 0;
 }
 
 double* array_ptr(ms_ctx* c, int which, int64_t* len) {
@@ -540,6 +556,7 @@ int ms_ctx_set_topology_partition(ms_ctx* c, int32_t nv, int32_t n_owned, int32_
   if (nv < 0 || nf < 0 || (nf > 0 && !tri) || n_owned < 0 || n_owned > nv)
     return fail(-1, "bad topology arguments");
   c->have_topology = false;
+  c->proj.active = false;
   c->n_owned = n_owned;
   // internal vertex order from the hint (single-context meshes only; partitions arrive ordered)
   c->perm.clear();
@@ -772,6 +789,7 @@ int ms_ctx_set_tilt_rigidity(ms_ctx* c, double k_tilt) {
 
 int ms_ctx_upload(ms_ctx* c, int which, const double* host, int64_t offset, int64_t count) {
   if (int rc = check_ctx(c, true)) return rc;
+  if (which == MS_ARR_GRAD) c->proj.active = false;
   if (!host && count > 0) return fail(-1, "null host pointer");
   if (int rc = ensure_array(c, which)) return rc;
   int64_t len = 0;
@@ -791,6 +809,8 @@ int ms_ctx_upload(ms_ctx* c, int which, const double* host, int64_t offset, int6
 
 int ms_ctx_get_array(ms_ctx* c, int which, double* host, int64_t offset, int64_t count) {
   if (int rc = check_ctx(c, true)) return rc;
+  if (which == MS_ARR_GRAD)
+    if (int rc = flush_projection(c)) return rc;
   if (!host && count > 0) return fail(-1, "null host pointer");
   int64_t len = 0;
   double* d = array_ptr(c, which, &len);
@@ -810,6 +830,7 @@ void* ms_ctx_device_ptr(ms_ctx* c, int which) {
   if (!c || !c->have_topology) return nullptr;
   if (use_device(c)) return nullptr;
   if (ensure_array(c, which)) return nullptr;
+  if (which == MS_ARR_GRAD && flush_projection(c)) return nullptr;  // the caller sees the projected gradient
   int64_t len = 0;
   return array_ptr(c, which, &len);
 }
@@ -829,7 +850,48 @@ int ms_ctx_set_tilts(ms_ctx* c, const double* tilts_host) {
   return ms_ctx_upload(c, MS_ARR_TILTS, tilts_host, 0, 3 * int64_t(c ? c->nv : 0));
 }
 
-int ms_ctx_eval_pass_a(ms_ctx* c, const ms_eval_opts* o) {
+// b_mask of the fixed-order sum: which scalar slots come from pass B's rows (see reduce_rows)
+static unsigned reduce_b_mask(const ms_eval_opts* o) {
+  const bool ran_a = needs_bending(o) || !o->want_grad;
+  unsigned b_mask = 0;
+  if (o->want_grad) {
+    b_mask = (1u << MS_SC_G_G) | (1u << MS_SC_G_GC) | (1u << MS_SC_GC_GC);
+    if (!ran_a) b_mask = 0xfffu;
+  }
+  return b_mask;
+}
+
+// the constraint / fixed-row projection an evaluation asks for
+static void projection_of(const ms_ctx* c, const ms_eval_opts* o, bool& use_gc, bool& use_fixed) {
+  use_gc = o->want_grad && o->constraint_mode >= 0 && (o->modules & MS_MOD_VOLUME);
+  use_fixed = o->want_grad && o->apply_fixed && c->has_fixed;
+}
+
+// fused finalisation: the last CTA of `a`'s launch reduces the rows and writes the KKT coefficient
+static int attach_finalize(ms_ctx* c, const ms_eval_opts* o, ms::PatchLaunch& a) {
+  if (!c->d_ticket.p) {
+    if (int rc = c->d_ticket.ensure(4)) return rc;
+    CU(cudaMemsetAsync(c->d_ticket.p, 0, 4 * sizeof(unsigned int), c->stream));
+  }
+  const bool ran_a = needs_bending(o) || !o->want_grad;
+  const int rows = ms::patch_grid(a);
+  bool use_gc, use_fixed;
+  projection_of(c, o, use_gc, use_fixed);
+  a.fin.ticket = c->d_ticket.p;
+  a.fin.partials_a = c->d_partials_a.p;
+  a.fin.partials_b = c->d_partials_b.p;
+  a.fin.rows_a = ran_a ? rows : 0;
+  a.fin.rows_b = o->want_grad ? rows : 0;
+  a.fin.b_mask = reduce_b_mask(o);
+  a.fin.constraint_mode = o->constraint_mode;
+  a.fin.has_gc = use_gc ? 1 : 0;
+  a.fin.k_vol = o->k_vol;
+  a.fin.v_target = o->v_target;
+  a.fin.scalars = c->d_scalars.p;
+  return 0;
+}
+
+static int eval_pass_a_impl(ms_ctx* c, const ms_eval_opts* o, bool finalize) {
   if (int rc = check_ctx(c, true)) return rc;
   if (!o) return fail(-1, "null options");
   ms::PatchLaunch a;
@@ -838,6 +900,8 @@ int ms_ctx_eval_pass_a(ms_ctx* c, const ms_eval_opts* o) {
   // gradient evaluations do everything in pass B.
   a.partials = c->d_partials_a.p;
   c->ran_pass_a = needs_bending(o) || !o->want_grad;
+  if (finalize)
+    if (int rc = attach_finalize(c, o, a)) return rc;
   if (c->ran_pass_a) CU(ms::launch_pass_a(a, c->stream));
   if (has_bt(o)) {
     ms::BtMesh m;
@@ -849,7 +913,7 @@ int ms_ctx_eval_pass_a(ms_ctx* c, const ms_eval_opts* o) {
   return 0;
 }
 
-int ms_ctx_eval_pass_b(ms_ctx* c, const ms_eval_opts* o) {
+static int eval_pass_b_impl(ms_ctx* c, const ms_eval_opts* o, bool finalize) {
   if (int rc = check_ctx(c, true)) return rc;
   if (!o) return fail(-1, "null options");
   // a tilt-only evaluation (want_grad == 0, want_tilt_grad == 1) still needs pass B for the tilt
@@ -859,10 +923,13 @@ int ms_ctx_eval_pass_b(ms_ctx* c, const ms_eval_opts* o) {
   if (int rc = fill_launch(c, o, a)) return rc;
   a.partials = c->d_partials_b.p;
   if (run_b) {
+    c->proj.active = false;  // MS_ARR_GRAD is overwritten with a new raw gradient
     if ((o->modules & MS_MOD_TILT) && !a.tilt_grad) {
       if (int rc = ensure_array(c, MS_ARR_TILT_GRAD)) return rc;
       a.tilt_grad = c->d_tilt_grad.p;
     }
+    if (finalize)
+      if (int rc = attach_finalize(c, o, a)) return rc;
     CU(ms::launch_pass_b(a, needs_bending(o), !needs_bending(o), c->stream));
   }
   if (has_bt(o) && wants_tilt_grad(o)) {
@@ -874,6 +941,9 @@ int ms_ctx_eval_pass_b(ms_ctx* c, const ms_eval_opts* o) {
   return 0;
 }
 
+int ms_ctx_eval_pass_a(ms_ctx* c, const ms_eval_opts* o) { return eval_pass_a_impl(c, o, false); }
+int ms_ctx_eval_pass_b(ms_ctx* c, const ms_eval_opts* o) { return eval_pass_b_impl(c, o, false); }
+
 int ms_ctx_eval_finish(ms_ctx* c, const ms_eval_opts* o) {
   if (int rc = ms_ctx_eval_reduce(c, o)) return rc;
   return ms_ctx_eval_project(c, o);
@@ -883,11 +953,7 @@ static int reduce_rows(ms_ctx* c, const ms_eval_opts* o, int rows_a, int rows_b)
   // energies, area, volume come from pass A when it ran, else from pass B; <g,g>, <g,gC>, <gC,gC>
   // and the tilt energy come from pass B when a gradient was requested -- one fixed-order sum
   const bool ran_a = needs_bending(o) || !o->want_grad;
-  unsigned b_mask = 0;
-  if (o->want_grad) {
-    b_mask = (1u << MS_SC_G_G) | (1u << MS_SC_G_GC) | (1u << MS_SC_GC_GC);
-    if (!ran_a) b_mask = 0xfffu;
-  }
+  const unsigned b_mask = reduce_b_mask(o);
   CU(ms::launch_reduce_partials(c->d_partials_a.p, ran_a ? rows_a : 0, c->d_partials_b.p, o->want_grad ? rows_b : 0,
                                 b_mask, c->d_scalars.p, c->stream));
   if (has_bt(o)) CU(ms::launch_bt_finalize(c->d_bt_e.p, c->d_scalars.p, c->stream));
@@ -913,20 +979,46 @@ int ms_ctx_eval_reduce(ms_ctx* c, const ms_eval_opts* o) {
 int ms_ctx_eval_project(ms_ctx* c, const ms_eval_opts* o) {
   if (int rc = check_ctx(c, true)) return rc;
   if (!o) return fail(-1, "null options");
-  if (o->want_grad && (o->constraint_mode >= 0 || o->apply_fixed)) {
-    const double* gc = (o->constraint_mode >= 0 && (o->modules & MS_MOD_VOLUME)) ? c->d_volgrad.p : nullptr;
-    const uint8_t* fixed = (o->apply_fixed && c->has_fixed) ? c->d_fixed.p : nullptr;
-    if (gc || fixed)
-      CU(ms::launch_project(c->d_grad.p, gc, fixed, c->n_owned, c->d_scalars.p, o->constraint_mode,
-                            o->k_vol, o->v_target, c->stream));
-  }
+  bool use_gc, use_fixed;
+  projection_of(c, o, use_gc, use_fixed);
+  // one thread: scalars[SC_COEF], scalars[SC_LAMBDA]; the projection itself is applied by the consumer of the
+  // gradient (direction, dot products) or materialised on first access (flush_projection)
+  CU(ms::launch_kkt_coefficient(c->d_scalars.p, o->constraint_mode, use_gc ? 1 : 0, o->k_vol, o->v_target, c->stream));
+  c->proj.active = use_gc || use_fixed;
+  c->proj.use_gc = use_gc;
+  c->proj.use_fixed = use_fixed;
   return 0;
 }
 
+int ms_ctx_eval_stage(ms_ctx* c, const ms_eval_opts* o, int32_t stage);
+
 int ms_ctx_eval_async(ms_ctx* c, const ms_eval_opts* o) {
-  if (int rc = ms_ctx_eval_pass_a(c, o)) return rc;
-  if (int rc = ms_ctx_eval_pass_b(c, o)) return rc;
-  return ms_ctx_eval_finish(c, o);
+  if (!c || !o) return fail(-1, "null argument");
+  // whole-mesh evaluations finalise inside the last pass (last-CTA ticket): no reduce / project launches
+  const bool fuse = o->patch_count == -1 && c->have_topology && !c->packed.patches.empty();
+  if (!fuse) {
+    if (int rc = ms_ctx_eval_pass_a(c, o)) return rc;
+    if (int rc = ms_ctx_eval_pass_b(c, o)) return rc;
+    return ms_ctx_eval_finish(c, o);
+  }
+  if (int rc = ms_ctx_eval_stage(c, o, 0)) return rc;
+  return ms_ctx_eval_stage(c, o, 1);
+}
+
+int ms_ctx_eval_stage(ms_ctx* c, const ms_eval_opts* o, int32_t stage) {
+  if (!c || !o) return fail(-1, "null argument");
+  if (stage < 0 || stage > 1) return fail(-1, "stage must be 0 (pass A) or 1 (pass B + finalisation)");
+  if (o->patch_count != -1 || !c->have_topology || c->packed.patches.empty())
+    return fail(-1, "ms_ctx_eval_stage evaluates whole, non-empty meshes");
+  if (stage == 0) return eval_pass_a_impl(c, o, !o->want_grad);
+  if (int rc = eval_pass_b_impl(c, o, o->want_grad != 0)) return rc;
+  if (has_bt(o)) CU(ms::launch_bt_finalize(c->d_bt_e.p, c->d_scalars.p, c->stream));
+  bool use_gc, use_fixed;
+  projection_of(c, o, use_gc, use_fixed);
+  c->proj.active = use_gc || use_fixed;
+  c->proj.use_gc = use_gc;
+  c->proj.use_fixed = use_fixed;
+  return 0;
 }
 
 int ms_ctx_read_scalars(ms_ctx* c, double* scalars16) {
@@ -1004,6 +1096,8 @@ static void fill_leaflet_mesh(ms_ctx* c, ms_ctx::Leaflet& L, bool use_trial, ms:
 int ms_ctx_eval_leaflet(ms_ctx* c, int32_t leaflet, uint32_t modules, int32_t want_grad, int32_t want_tilt_grad,
                         uint32_t accumulate, int32_t use_trial, double* energies3) {
   if (int rc = check_ctx(c, true)) return rc;
+  if (want_grad)
+    if (int rc = flush_projection(c)) return rc;
   if (leaflet < 0 || leaflet > 2) return fail(-1, "bad leaflet index");
   ms_ctx::Leaflet& L = c->leaflet[leaflet];
   if (!L.set) return fail(-4, "ms_ctx_set_leaflet has not been called for this leaflet (or the topology changed)");
@@ -1116,6 +1210,8 @@ int ms_ctx_leaflet_gradient_norm2(ms_ctx* c, int32_t leaflet, double* norm2) {
 int ms_ctx_eval_leaflet_pair(ms_ctx* c, uint32_t modules, int32_t want_grad, int32_t want_tilt_grad, uint32_t accumulate,
                              int32_t use_trial) {
   if (int rc = check_ctx(c, true)) return rc;
+  if (want_grad)
+    if (int rc = flush_projection(c)) return rc;
   ms_ctx::Leaflet& A = c->leaflet[0];
   ms_ctx::Leaflet& B = c->leaflet[1];
   static const bool fused_off = std::getenv("MS_LEAFLET_NO_FUSE") != nullptr;
@@ -1620,8 +1716,10 @@ int ms_ctx_eval_host(ms_ctx* c, const ms_eval_opts* o, const double* pos_host, d
       if (int rc = ms_ctx_upload(c, o->use_trial ? MS_ARR_TRIAL : MS_ARR_POSITIONS, pos_host, 0, n3)) return rc;
     if (int rc = ms_ctx_eval_async(c, o)) return rc;
   }
-  if (o->want_grad && grad_host && n3)
+  if (o->want_grad && grad_host && n3) {
+    if (int rc = flush_projection(c)) return rc;
     if (int rc = download_rows(c, c->d_grad.p, grad_host, 3)) return rc;
+  }
   if (o->want_grad && volgrad_host && n3 && (o->modules & MS_MOD_VOLUME))
     if (int rc = download_rows(c, c->d_volgrad.p, volgrad_host, 3)) return rc;
   if ((o->want_grad || o->want_tilt_grad) && tilt_grad_host && n3 && c->d_tilt_grad.p)
@@ -1642,6 +1740,8 @@ int ms_ctx_set_send_rows(ms_ctx* c, const int32_t* rows, int64_t n) {
 
 int ms_ctx_pack_send(ms_ctx* c, int which, void* out_device) {
   if (int rc = check_ctx(c, true)) return rc;
+  if (which == MS_ARR_GRAD)
+    if (int rc = flush_projection(c)) return rc;
   int64_t len = 0;
   const double* src = array_ptr(c, which, &len);
   if (!src || c->nv <= 0 || len % c->nv) return fail(-1, "array is not a per-vertex array");
@@ -1668,6 +1768,7 @@ int ms_ctx_accept_trial(ms_ctx* c) {
 
 int ms_ctx_dots(ms_ctx* c) {
   if (int rc = check_ctx(c, true)) return rc;
+  if (int rc = flush_projection(c)) return rc;
   CU(ms::launch_dots(c->d_grad.p, c->d_volgrad.p, 3 * int64_t(c->n_owned), c->d_dot_partials.p, kDotBlocks,
                      c->d_scalars.p, c->stream));
   return 0;
@@ -1676,12 +1777,22 @@ int ms_ctx_dots(ms_ctx* c) {
 int ms_ctx_direction_from_gradient(ms_ctx* c, double scale) {
   if (int rc = check_ctx(c, true)) return rc;
   if (int rc = ensure_array(c, MS_ARR_DIRECTION)) return rc;
+  if (c->proj.active) {  // d = scale * (g + coef gC), fixed rows zero: the projection rides the pass that forms d
+    if (c->n_owned < c->nv)
+      CU(cudaMemsetAsync(c->d_dir.p + 3 * size_t(c->n_owned), 0, 3 * size_t(c->nv - c->n_owned) * sizeof(double), c->stream));
+    CU(ms::launch_scale_projected(c->d_grad.p, c->proj.use_gc ? c->d_volgrad.p : nullptr,
+                                  c->proj.use_fixed ? c->d_fixed.p : nullptr, c->n_owned, c->d_scalars.p, scale, c->d_dir.p,
+                                  c->stream));
+    return 0;
+  }
   CU(ms::launch_scale(c->d_grad.p, scale, c->d_dir.p, 3 * int64_t(c->nv), c->stream));
   return 0;
 }
 
 int ms_ctx_axpy(ms_ctx* c, int dst, int src, double alpha, int32_t skip_fixed) {
   if (int rc = check_ctx(c, true)) return rc;
+  if (dst == MS_ARR_GRAD || src == MS_ARR_GRAD)
+    if (int rc = flush_projection(c)) return rc;
   int64_t ld = 0, ls = 0;
   double* d = array_ptr(c, dst, &ld);
   double* s = array_ptr(c, src, &ls);
@@ -1692,6 +1803,7 @@ int ms_ctx_axpy(ms_ctx* c, int dst, int src, double alpha, int32_t skip_fixed) {
 
 int ms_ctx_cg_direction(ms_ctx* c, int32_t restart) {
   if (int rc = check_ctx(c, true)) return rc;
+  if (int rc = flush_projection(c)) return rc;
   if (int rc = ensure_array(c, MS_ARR_DIRECTION)) return rc;
   const int64_t nv = c->nv;
   if (restart || !c->d_cg_prev_g.p || c->d_cg_prev_g.n < size_t(3 * nv)) {
@@ -1705,6 +1817,7 @@ int ms_ctx_cg_direction(ms_ctx* c, int32_t restart) {
 
 int ms_ctx_cg_commit(ms_ctx* c) {
   if (int rc = check_ctx(c, true)) return rc;
+  if (int rc = flush_projection(c)) return rc;
   if (!c->d_dir.p) return fail(-4, "no search direction exists");
   const size_t n3 = 3 * size_t(c->nv);
   if (int rc = c->d_cg_prev_g.ensure(n3 + 1)) return rc;
@@ -1729,8 +1842,13 @@ int ms_ctx_line_search_stats(ms_ctx* c, double* out4) {
   CU(ms::launch_min_edge2(c->d_tri.p, c->nf, c->nv, c->d_pos.p, c->d_ls_bits.p, c->stream));
   CU(ms::launch_max_row_norm2(c->d_dir.p, c->n_owned, c->d_ls_bits.p + 1, c->stream));
   // <g,g>, <g,d>, <d,d> with the deterministic two-level sum; they land in the scalar vector
-  CU(ms::launch_dots(c->d_grad.p, c->d_dir.p, 3 * int64_t(c->n_owned), c->d_dot_partials.p, kDotBlocks,
-                     c->d_scalars.p, c->stream));
+  if (c->proj.active)
+    CU(ms::launch_dots_projected(c->d_grad.p, c->proj.use_gc ? c->d_volgrad.p : nullptr,
+                                 c->proj.use_fixed ? c->d_fixed.p : nullptr, c->d_dir.p, c->n_owned, c->d_dot_partials.p,
+                                 kDotBlocks, c->d_scalars.p, c->stream));
+  else
+    CU(ms::launch_dots(c->d_grad.p, c->d_dir.p, 3 * int64_t(c->n_owned), c->d_dot_partials.p, kDotBlocks,
+                       c->d_scalars.p, c->stream));
   unsigned long long bits[4];
   double sc[MS_SC_COUNT];
   CU(cudaMemcpyAsync(bits, c->d_ls_bits.p, sizeof(bits), cudaMemcpyDeviceToHost, c->stream));

@@ -193,6 +193,45 @@ __device__ __forceinline__ FacetRec load_rec(const FacetRec* p) {
 // ---------------------------------------------------------------------------
 constexpr uint32_t kFastModules = MS_MOD_SURFACE | MS_MOD_BENDING | MS_MOD_VOLUME;
 
+// KKT coefficient of the single volume constraint (runtime/constraint_manager.py:294-301) or of the volume
+// penalty (geometry/body.py:223-238): projected gradient = g + coef * gC.
+__device__ __forceinline__ void kkt_coefficient(double* scalars, int mode, int has_gc, double k_vol, double v_target) {
+  double coef = 0.0;
+  if (has_gc) {
+    if (mode == 0) {
+      const double den = scalars[SC_GC_GC];
+      coef = den > 1.0e-18 ? -(scalars[SC_G_GC] / den) : 0.0;
+    } else if (mode == 1) {
+      coef = k_vol * (scalars[SC_VOLUME] - v_target);
+    }
+  }
+  scalars[SC_COEF] = coef;
+  scalars[SC_LAMBDA] = (mode == 0) ? -coef : coef;
+}
+
+// Fixed-order sum of the per-CTA rows by ONE CTA (the last one of the evaluation): thread (row, k) sums slot k of
+// rows row, row + kFinRows, ...; twelve threads then add the kFinRows row sums in index order.
+constexpr int kFinRows = 32;
+__device__ __forceinline__ void finalize_scalars(const PatchFinalize& f, double (*part)[kPartialStride], int tid) {
+  if (tid < kFinRows * kPartialStride) {
+    const int k = tid % kPartialStride, row = tid / kPartialStride;
+    const bool from_b = (f.b_mask >> k) & 1u;
+    const double* src = from_b ? f.partials_b : f.partials_a;
+    const int count = from_b ? f.rows_b : f.rows_a;
+    double v = 0.0;
+    for (int p = row; p < count; p += kFinRows) v += __ldcg(src + size_t(p) * kPartialStride + k);
+    part[row][k] = v;
+  }
+  __syncthreads();
+  if (tid < kPartialStride) {
+    double t = 0.0;
+    for (int r = 0; r < kFinRows; ++r) t += part[r][tid];
+    f.scalars[tid] = (tid == PS_VOLUME6) ? t / 6.0 : t;
+  }
+  __syncthreads();
+  if (tid == 0) kkt_coefficient(f.scalars, f.constraint_mode, f.has_gc, f.k_vol, f.v_target);
+}
+
 // Warp roles inside the 512-thread CTA: warps [0, NC/32) are consumers, warp NC/32 runs the
 // patch epilogues, the last warp is the producer.
 template <int PASS, int KIND, int NC>
@@ -499,6 +538,20 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
 #pragma unroll
     for (int k = 0; k < PS_COUNT; ++k) p[k] = sums[k];
   }
+  if (a.fin.ticket) {  // the last CTA to get here finalises the evaluation (warp-uniform: a kernel parameter)
+    __shared__ int s_last;
+    __shared__ double s_part[kFinRows][kPartialStride];
+    if (tid == 0) {
+      __threadfence();
+      s_last = atomicAdd(a.fin.ticket, 1u) == gridDim.x - 1 ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      finalize_scalars(a.fin, s_part, tid);
+      if (tid == 0) *a.fin.ticket = 0u;
+    }
+  }
 }
 
 // Fixed-order reduction of the per-CTA partial sums of pass A and pass B (one CTA of
@@ -587,6 +640,56 @@ __global__ void __launch_bounds__(256) k_project(double* g, const double* __rest
   if (gc) x += coef * gc[i];
   if (fixed && fixed[i / 3]) x = 0.0;
   g[i] = x;
+}
+
+__global__ void k_kkt_coefficient(double* scalars, int mode, int has_gc, double k_vol, double v_target) {
+  kkt_coefficient(scalars, mode, has_gc, k_vol, v_target);
+}
+
+__device__ __forceinline__ double projected_at(const double* __restrict__ g, const double* __restrict__ gc,
+                                               const uint8_t* __restrict__ fixed, double coef, int64_t i) {
+  if (fixed && fixed[i / 3]) return 0.0;
+  double x = g[i];
+  if (gc) x += coef * gc[i];
+  return x;
+}
+
+__global__ void __launch_bounds__(256) k_apply_projection(double* g, const double* __restrict__ gc,
+                                                          const uint8_t* __restrict__ fixed, int64_t nv,
+                                                          const double* __restrict__ scalars) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= 3 * nv) return;
+  g[i] = projected_at(g, gc, fixed, scalars[SC_COEF], i);
+}
+
+__global__ void __launch_bounds__(256) k_scale_projected(const double* __restrict__ g, const double* __restrict__ gc,
+                                                         const uint8_t* __restrict__ fixed, int64_t nv,
+                                                         const double* __restrict__ scalars, double scale, double* out) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= 3 * nv) return;
+  out[i] = scale * projected_at(g, gc, fixed, scalars[SC_COEF], i);
+}
+
+__global__ void __launch_bounds__(256) k_dots_projected(const double* __restrict__ g, const double* __restrict__ gc,
+                                                        const uint8_t* __restrict__ fixed, const double* __restrict__ d,
+                                                        int64_t n, const double* __restrict__ scalars, double* block_partials) {
+  __shared__ double red[32 * 3];
+  double v[3] = {0.0, 0.0, 0.0};
+  const double coef = scalars[SC_COEF];
+  const int64_t per = (n + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = per * blockIdx.x, hi = (lo + per < n) ? lo + per : n;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const double a = projected_at(g, gc, fixed, coef, i), b = d[i];
+    v[0] += a * a;
+    v[1] += a * b;
+    v[2] += b * b;
+  }
+  block_sum<3>(v, red, 256, 0);
+  if (threadIdx.x == 0) {
+    block_partials[3 * blockIdx.x] = v[0];
+    block_partials[3 * blockIdx.x + 1] = v[1];
+    block_partials[3 * blockIdx.x + 2] = v[2];
+  }
 }
 
 __global__ void __launch_bounds__(256) k_gather_rows(const double* __restrict__ src, int width,
@@ -1356,7 +1459,11 @@ cudaError_t configure_kernels() {
                        (const void*)k_patch<1, 1, kConsumerThreads>, (const void*)k_patch<1, 2, kConsumerThreads>,
                        (const void*)k_patch<0, 3, kConsumerThreads>, (const void*)k_patch<1, 3, kConsumerThreads>};
   for (const void* f : fns) {
-    e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
+    cudaFuncAttributes attr;
+    e = cudaFuncGetAttributes(&attr, f);
+    if (e != cudaSuccess) return e;
+    // static (finalisation scratch) + dynamic shared memory share the 227 KB a CTA may opt in to
+    e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn - int(attr.sharedSizeBytes));
     if (e != cudaSuccess) return e;
   }
   return cudaSuccess;
@@ -1415,6 +1522,32 @@ cudaError_t launch_project(double* g, const double* gc, const uint8_t* fixed, in
                            cudaStream_t st) {
   if (nv <= 0) return cudaSuccess;
   k_project<<<blocks_for(3 * nv, 256), 256, 0, st>>>(g, gc, fixed, nv, scalars, mode, k_vol, v_target);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_kkt_coefficient(double* scalars, int mode, int has_gc, double k_vol, double v_target, cudaStream_t st) {
+  k_kkt_coefficient<<<1, 1, 0, st>>>(scalars, mode, has_gc, k_vol, v_target);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_apply_projection(double* g, const double* gc, const uint8_t* fixed, int64_t nv, const double* scalars,
+                                    cudaStream_t st) {
+  if (nv <= 0) return cudaSuccess;
+  k_apply_projection<<<blocks_for(3 * nv, 256), 256, 0, st>>>(g, gc, fixed, nv, scalars);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_scale_projected(const double* g, const double* gc, const uint8_t* fixed, int64_t nv,
+                                   const double* scalars, double scale, double* out, cudaStream_t st) {
+  if (nv <= 0) return cudaSuccess;
+  k_scale_projected<<<blocks_for(3 * nv, 256), 256, 0, st>>>(g, gc, fixed, nv, scalars, scale, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dots_projected(const double* g, const double* gc, const uint8_t* fixed, const double* d, int64_t nv,
+                                  double* block_partials, int n_blocks, double* scalars, cudaStream_t st) {
+  k_dots_projected<<<n_blocks, 256, 0, st>>>(g, gc, fixed, d, 3 * nv, scalars, block_partials);
+  k_dots_final<<<1, 256, 0, st>>>(block_partials, n_blocks, scalars);
   return cudaGetLastError();
 }
 

@@ -25,6 +25,7 @@ enum ScalarSlot : int {
   SC_G_GC = 9,         // <g,gC>
   SC_GC_GC = 10,       // <gC,gC>
   SC_LAMBDA = 11,      // KKT multiplier applied
+  SC_COEF = 12,        // projected gradient = g + SC_COEF * gC (then fixed rows zeroed); 0 without a constraint
   SC_COUNT = 16,
 };
 constexpr int kPartialStride = 12;  // per-patch partial sums: slots 0..11 above
@@ -42,6 +43,20 @@ constexpr int kPatchSlotCap = 1536;   // record slots per patch (rounds x thread
 constexpr int kConsumerThreads = MS_CONSUMER_THREADS;  // + one epilogue warp + one producer warp per CTA
 constexpr int kMaxConsumerWarps = kConsumerThreads / 32;
 constexpr int kMaxGroups = 14;        // thread groups taking turns (named barriers 1..14)
+
+// Fused finalisation of an evaluation: the LAST persistent CTA of a pass to finish (ticket) adds up the per-CTA
+// rows of both passes in fixed order, writes the scalar vector and the KKT coefficient -- no reduce / project launches.
+struct PatchFinalize {
+  unsigned int* ticket;       // zeroed counter; nullptr: this launch does not finalise
+  const double* partials_a;   // per-CTA rows of pass A (rows_a of them; 0: pass A did not run)
+  const double* partials_b;   // per-CTA rows of pass B
+  int32_t rows_a, rows_b;
+  uint32_t b_mask;            // slot k comes from pass B's rows when bit k is set, else from pass A's
+  int32_t constraint_mode;    // -1 none; 0 lagrange; 1 penalty (constraint_manager.py:294-301, body.py:223-238)
+  int32_t has_gc;             // the volume gradient takes part in the projection
+  double k_vol, v_target;
+  double* scalars;
+};
 
 struct PatchLaunch {
   // packed topology (device)
@@ -77,6 +92,7 @@ struct PatchLaunch {
   double* a_vor;      // nv
   double* a_eff;      // nv
   double* e_vertex;   // nv   per-vertex bending energy (bending.compute_energy_array)
+  PatchFinalize fin;
 };
 
 size_t pass_a_smem_bytes(const PatchLaunch& a);
@@ -101,6 +117,18 @@ cudaError_t launch_dots(const double* g, const double* gc, int64_t n, double* bl
 cudaError_t launch_project(double* g, const double* gc, const uint8_t* fixed, int64_t nv,
                            double* scalars, int mode, double k_vol, double v_target,
                            cudaStream_t st);
+// scalars[SC_COEF], scalars[SC_LAMBDA] from the dot products / the volume (one thread): the projection itself is
+// applied by whoever consumes the gradient (launch_apply_projection, launch_scale_projected, launch_dots_projected)
+cudaError_t launch_kkt_coefficient(double* scalars, int mode, int has_gc, double k_vol, double v_target, cudaStream_t st);
+// g <- (g + scalars[SC_COEF] * gc) with fixed rows zeroed, in place (gc / fixed may be null)
+cudaError_t launch_apply_projection(double* g, const double* gc, const uint8_t* fixed, int64_t nv, const double* scalars,
+                                    cudaStream_t st);
+// out <- scale * projected(g) without touching g
+cudaError_t launch_scale_projected(const double* g, const double* gc, const uint8_t* fixed, int64_t nv,
+                                   const double* scalars, double scale, double* out, cudaStream_t st);
+// scalars[SC_G_G, SC_G_GC, SC_GC_GC] <- <p,p>, <p,d>, <d,d> with p = projected(g) formed on the fly
+cudaError_t launch_dots_projected(const double* g, const double* gc, const uint8_t* fixed, const double* d, int64_t nv,
+                                  double* block_partials, int n_blocks, double* scalars, cudaStream_t st);
 // out[i*width + c] = src[rows[i]*width + c]: packs the rows a neighbouring partition needs
 cudaError_t launch_gather_rows(const double* src, int width, const int32_t* rows, int64_t n,
                                double* out, cudaStream_t st);
