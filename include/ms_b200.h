@@ -153,6 +153,10 @@ MS_API int ms_ctx_set_topology_partition(ms_ctx* ctx, int32_t nv, int32_t n_owne
 MS_API int ms_ctx_set_send_rows(ms_ctx* ctx, const int32_t* rows, int64_t n);
 /* out_device[i, :] = array[send_rows[i], :] on the context stream (out is a DEVICE pointer) */
 MS_API int ms_ctx_pack_send(ms_ctx* ctx, int which, void* out_device);
+/* Replace the fixed-vertex mask (nv bytes, or NULL: no fixed vertex) without touching the packed topology: the
+ * reference invalidates its fixed mask on its own counter (Mesh._fixed_flags_version, geometry/mesh.py:211-231),
+ * independently of the topology versions. */
+MS_API int ms_ctx_set_fixed_mask(ms_ctx* ctx, const uint8_t* fixed_mask);
 MS_API int ms_ctx_pack_info(const ms_ctx* ctx, ms_pack_info* info);
 /* patch p owns vertex rows [v_lo[p], v_lo[p+1]); v_lo has n_patches+1 entries */
 MS_API int ms_ctx_patch_ranges(const ms_ctx* ctx, int32_t* v_lo);

@@ -125,6 +125,16 @@ class DeviceMesh:
         self.nv = int(nv)
         self.nf = int(tri.shape[0])
 
+    def set_fixed_mask(self, fixed_mask) -> None:
+        """Replace the fixed-vertex mask (None: no fixed vertex); the packed topology stays as it is."""
+        if fixed_mask is None:
+            L.check(self._lib.ms_ctx_set_fixed_mask(self._h, None))
+            return
+        m = np.ascontiguousarray(fixed_mask, dtype=np.uint8)
+        if m.shape != (self.nv,):
+            raise ValueError(f"mask must have shape ({self.nv},)")
+        L.check(self._lib.ms_ctx_set_fixed_mask(self._h, L.bptr(m)))
+
     def permutation(self) -> np.ndarray:
         """Internal row -> caller's vertex row."""
         out = np.empty(self.nv, dtype=np.int32)

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <numeric>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -60,6 +61,10 @@ bool g_configured[64] = {false};
 }  // namespace
 
 struct ms_ctx {
+  ~ms_ctx() {
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+  }
   int device = 0;
   cudaStream_t stream = nullptr;
   bool have_topology = false;
@@ -468,14 +473,14 @@ int ms_ctx_create(int device, ms_ctx** out) {
     CU(ms::configure_kernels());
     g_configured[device] = true;
   }
-  ms_ctx* c = new ms_ctx();
+  std::unique_ptr<ms_ctx> c(new ms_ctx());  // released on every failure path below
   c->device = device;
   CU(cudaEventCreate(&c->ev0));
   CU(cudaEventCreate(&c->ev1));
-  if (int rc = c->d_scalars.ensure(MS_SC_COUNT)) { delete c; return rc; }
+  if (int rc = c->d_scalars.ensure(MS_SC_COUNT)) return rc;
   CU(cudaMemset(c->d_scalars.p, 0, MS_SC_COUNT * sizeof(double)));
-  if (int rc = c->d_dot_partials.ensure(3 * kDotBlocks)) { delete c; return rc; }
-  *out = c;
+  if (int rc = c->d_dot_partials.ensure(3 * kDotBlocks)) return rc;
+  *out = c.release();
   return 0;
 }
 
@@ -483,8 +488,6 @@ int ms_ctx_destroy(ms_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
-  if (c->ev0) cudaEventDestroy(c->ev0);
-  if (c->ev1) cudaEventDestroy(c->ev1);
   for (cudaEvent_t e : c->events)
     if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : c->pipe_events)
@@ -597,8 +600,17 @@ int ms_ctx_set_topology_partition(ms_ctx* c, int32_t nv, int32_t n_owned, int32_
   c->bt_ready = false;
   c->tri_ready = false;
   c->pipe_ready = false;
-  for (auto& lf : c->leaflet) lf.set = lf.has_fixed = lf.has_minv = false;
+  for (auto& lf : c->leaflet) {  // per-leaflet arrays are sized for the previous vertex count
+    lf.set = lf.has_fixed = lf.has_minv = false;
+    lf.tilts.release(); lf.tilt_grad.release(); lf.trial.release(); lf.dir.release(); lf.minv.release();
+    lf.fixed.release();
+  }
   c->vnormals_ready = false;
+  c->d_vnormals.release();
+  c->d_rowsq.release();
+  c->d_lf_corner.release(); c->d_lf_vbuf.release(); c->d_lf_shape.release(); c->d_lf_tilt.release();
+  c->d_lf_corner2.release(); c->d_lf_vbuf2.release(); c->d_lf_shape2.release(); c->d_lf_tilt2.release();
+  c->d_lf_facet_e.release();
   const ms::PackedMesh& pk = c->packed;
   const size_t np = pk.patches.size();
   c->v_lo.resize(np + 1);
@@ -685,6 +697,24 @@ int ms_ctx_set_topology_partition(ms_ctx* c, int32_t nv, int32_t n_owned, int32_
   c->d_aeff.release();
   c->d_evert.release();
   c->have_topology = true;
+  return 0;
+}
+
+int ms_ctx_set_fixed_mask(ms_ctx* c, const uint8_t* fixed_mask) {
+  if (int rc = check_ctx(c, true)) return rc;
+  // the mask takes part in a pending projection: apply it with the OLD mask first
+  if (int rc = flush_projection(c)) return rc;
+  const size_t nv = size_t(c->nv);
+  c->has_fixed = fixed_mask != nullptr && nv > 0;
+  if (!c->has_fixed) return 0;
+  std::vector<uint8_t> tmp;
+  if (!c->perm.empty()) {
+    tmp = permuted(fixed_mask, c->perm);
+    fixed_mask = tmp.data();
+  }
+  if (int rc = c->d_fixed.ensure(nv)) return rc;
+  CU(cudaMemcpyAsync(c->d_fixed.p, fixed_mask, nv, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));  // tmp goes out of scope
   return 0;
 }
 
@@ -883,7 +913,7 @@ static int attach_finalize(ms_ctx* c, const ms_eval_opts* o, ms::PatchLaunch& a)
   a.fin.rows_a = ran_a ? rows : 0;
   a.fin.rows_b = o->want_grad ? rows : 0;
   a.fin.b_mask = reduce_b_mask(o);
-  a.fin.constraint_mode = o->constraint_mode;
+  a.fin.constraint_mode = o->want_grad ? o->constraint_mode : -2;
   a.fin.has_gc = use_gc ? 1 : 0;
   a.fin.k_vol = o->k_vol;
   a.fin.v_target = o->v_target;
@@ -979,6 +1009,7 @@ int ms_ctx_eval_reduce(ms_ctx* c, const ms_eval_opts* o) {
 int ms_ctx_eval_project(ms_ctx* c, const ms_eval_opts* o) {
   if (int rc = check_ctx(c, true)) return rc;
   if (!o) return fail(-1, "null options");
+  if (!o->want_grad) return 0;  // energy-only evaluation: a pending projection (and its coefficient) stays as it is
   bool use_gc, use_fixed;
   projection_of(c, o, use_gc, use_fixed);
   // one thread: scalars[SC_COEF], scalars[SC_LAMBDA]; the projection itself is applied by the consumer of the
@@ -1013,11 +1044,13 @@ int ms_ctx_eval_stage(ms_ctx* c, const ms_eval_opts* o, int32_t stage) {
   if (stage == 0) return eval_pass_a_impl(c, o, !o->want_grad);
   if (int rc = eval_pass_b_impl(c, o, o->want_grad != 0)) return rc;
   if (has_bt(o)) CU(ms::launch_bt_finalize(c->d_bt_e.p, c->d_scalars.p, c->stream));
-  bool use_gc, use_fixed;
-  projection_of(c, o, use_gc, use_fixed);
-  c->proj.active = use_gc || use_fixed;
-  c->proj.use_gc = use_gc;
-  c->proj.use_fixed = use_fixed;
+  if (o->want_grad) {
+    bool use_gc, use_fixed;
+    projection_of(c, o, use_gc, use_fixed);
+    c->proj.active = use_gc || use_fixed;
+    c->proj.use_gc = use_gc;
+    c->proj.use_fixed = use_fixed;
+  }
   return 0;
 }
 
@@ -1470,7 +1503,8 @@ int ms_ctx_halo_prepare(ms_ctx* c) {
 
 int ms_ctx_halo_signal(ms_ctx* c, int32_t flag_index) {
   if (int rc = check_ctx(c, true)) return rc;
-  if (flag_index < 0 || flag_index >= 4) return fail(-1, "bad flag index");
+  if (flag_index != MS_FLAG_POSITIONS && flag_index != MS_FLAG_SEEDS)  // words 2 / 3 belong to the all-reduce and the warm-up
+    return fail(-1, "flag index must be MS_FLAG_POSITIONS or MS_FLAG_SEEDS");
   if (int rc = ensure_flag_words(c)) return rc;
   CU(ms::launch_halo_signal(c->d_flag_words.p + flag_index, ++c->flag_epoch[flag_index], c->stream));
   return 0;
@@ -1478,7 +1512,8 @@ int ms_ctx_halo_signal(ms_ctx* c, int32_t flag_index) {
 
 int ms_ctx_halo_pull(ms_ctx* c, int32_t which, int32_t flag_index) {
   if (int rc = check_ctx(c, true)) return rc;
-  if (flag_index < 0 || flag_index >= 4) return fail(-1, "bad flag index");
+  if (flag_index != MS_FLAG_POSITIONS && flag_index != MS_FLAG_SEEDS)  // words 2 / 3 belong to the all-reduce and the warm-up
+    return fail(-1, "flag index must be MS_FLAG_POSITIONS or MS_FLAG_SEEDS");
   if (int rc = ensure_flag_words(c)) return rc;
   const int64_t n_ghost = int64_t(c->nv) - c->n_owned;
   if (n_ghost <= 0) return 0;

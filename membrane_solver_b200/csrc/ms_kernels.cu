@@ -229,7 +229,8 @@ __device__ __forceinline__ void finalize_scalars(const PatchFinalize& f, double 
     f.scalars[tid] = (tid == PS_VOLUME6) ? t / 6.0 : t;
   }
   __syncthreads();
-  if (tid == 0) kkt_coefficient(f.scalars, f.constraint_mode, f.has_gc, f.k_vol, f.v_target);
+  // energy-only evaluations (mode -2) leave the coefficient of the pending projection alone
+  if (tid == 0 && f.constraint_mode != -2) kkt_coefficient(f.scalars, f.constraint_mode, f.has_gc, f.k_vol, f.v_target);
 }
 
 // Warp roles inside the 512-thread CTA: warps [0, NC/32) are consumers, warp NC/32 runs the

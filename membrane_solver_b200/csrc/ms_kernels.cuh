@@ -52,7 +52,8 @@ struct PatchFinalize {
   const double* partials_b;   // per-CTA rows of pass B
   int32_t rows_a, rows_b;
   uint32_t b_mask;            // slot k comes from pass B's rows when bit k is set, else from pass A's
-  int32_t constraint_mode;    // -1 none; 0 lagrange; 1 penalty (constraint_manager.py:294-301, body.py:223-238)
+  int32_t constraint_mode;    // -2 leave the coefficient alone (energy-only evaluation); -1 none; 0 lagrange;
+                              // 1 penalty (constraint_manager.py:294-301, body.py:223-238)
   int32_t has_gc;             // the volume gradient takes part in the projection
   double k_vol, v_target;
   double* scalars;

@@ -97,6 +97,7 @@ class ArrayMesh:
         self._facet_loops_version = 0
         self._vertex_ids_version = 0
         self._topology_version = 0
+        self._fixed_flags_version = 0
         self._boundary = None
 
     # -- the Mesh surface ----------------------------------------------------------
@@ -134,6 +135,15 @@ class ArrayMesh:
     @property
     def fixed_mask(self):
         return self._fixed
+
+    def set_fixed(self, fixed) -> None:
+        """Fix / release vertices without touching the topology: bumps ``_fixed_flags_version`` like the
+        reference's ``Mesh`` does for its own fixed-mask cache (geometry/mesh.py:211-231)."""
+        fixed = np.asarray(fixed, dtype=bool)
+        if fixed.shape != self._fixed.shape:
+            raise ValueError("fixed must have one flag per vertex")
+        self._fixed = fixed.copy()
+        self._fixed_flags_version = int(getattr(self, "_fixed_flags_version", 0)) + 1
 
     @property
     def boundary_vertex_ids(self):

@@ -142,6 +142,10 @@ class DeviceMinimizer:
             if self.stepper == "cg":
                 restart = (not self._cg_have_history) or (self._cg_iter % self.restart_interval == 0)
                 self.dm.cg_direction(restart)
+                # remember gradient and direction NOW: the volume-only evaluations of the constraint
+                # enforcement inside the line search overwrite MS_ARR_GRAD (conjugate_gradient.py:104-119
+                # stores the gradient the step was computed from); a failed step discards the history below
+                self.dm.cg_commit()
             else:
                 self.dm.direction_from_gradient(-1.0)
             _, _, _, g_dot_g = self.dm.line_search_stats()
@@ -154,7 +158,6 @@ class DeviceMinimizer:
             self.history.append((i, float(accepted), float(step_in), bool(success)))
             if self.stepper == "cg":
                 if success:
-                    self.dm.cg_commit()
                     self._cg_have_history = True
                     self._cg_iter += 1
                 else:  # minimizer.py:1461-1463: a failed step resets the stepper

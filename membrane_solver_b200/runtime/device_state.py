@@ -15,6 +15,8 @@ reference's modules attach their memo attributes.
 
 from __future__ import annotations
 
+import weakref
+
 import numpy as np
 
 from .. import _lib as L
@@ -97,13 +99,16 @@ class DeviceState:
         self._tilt_key = None
         self._k_tilt = None
         self._leaflet_key = {}     # leaflet -> hash of the description held by the device
+        self._fixed_key = None     # (Mesh._fixed_flags_version, hash of the mask) the device holds
         self.uploads = 0           # topology uploads (tests assert residency with this)
+        self.fixed_uploads = 0     # fixed-mask uploads outside a topology upload
 
     # -- topology -------------------------------------------------------------
     def sync_topology(self, mesh, positions: np.ndarray) -> None:
         key = topology_key(mesh)
         nv = int(positions.shape[0])
         if key == self.key and nv == self.nv:
+            self._sync_fixed(mesh, nv)
             return
         tri = triangle_rows(mesh)
         bodies = body_entries(mesh)
@@ -115,12 +120,31 @@ class DeviceState:
             self.body_rows = bodies[0][1]
         self.boundary = boundary_mask(mesh, nv)
         self.has_boundary = self.boundary is not None
-        self.dm.set_topology(nv, tri, is_boundary=self.boundary, body_mask=body, fixed_mask=fixed_mask(mesh, nv),
-                             order_hint=positions)
+        fm = fixed_mask(mesh, nv)
+        self.dm.set_topology(nv, tri, is_boundary=self.boundary, body_mask=body, fixed_mask=fm, order_hint=positions)
+        self._fixed_key = self._fixed_signature(mesh, fm)
         self.key, self.nv, self.nf = key, nv, int(tri.shape[0])
         self._gamma_key = self._bend_key = self._tilt_key = self._k_tilt = None
         self._leaflet_key = {}
         self.uploads += 1
+
+    # -- fixed vertices: own counter in the reference (geometry/mesh.py:211-231) ----------------------
+    @staticmethod
+    def _fixed_signature(mesh, fm):
+        return (_version(mesh, "_fixed_flags_version"), None if fm is None else hash(fm.tobytes()))
+
+    def _sync_fixed(self, mesh, nv: int) -> None:
+        """Vertices fixed or released without a topology change: only the mask travels."""
+        ver = _version(mesh, "_fixed_flags_version")
+        if self._fixed_key is not None and hasattr(mesh, "_fixed_flags_version") and self._fixed_key[0] == ver:
+            return  # the reference bumps the counter on every change of a fixed flag
+        fm = fixed_mask(mesh, nv)
+        sig = self._fixed_signature(mesh, fm)
+        if sig != self._fixed_key:
+            if self._fixed_key is None or sig[1] != self._fixed_key[1]:
+                self.dm.set_fixed_mask(fm)
+                self.fixed_uploads += 1
+            self._fixed_key = sig
 
     # -- parameters (sent only when they change) ------------------------------
     def set_gamma(self, gamma) -> None:
@@ -193,13 +217,26 @@ def get_state(mesh, positions: np.ndarray) -> DeviceState:
     """The mesh's device state, with its topology brought up to date."""
     st = getattr(mesh, "_b200_state", None)
     if st is None:
+        st = _SIDE_TABLE.get(id(mesh))
+    if st is None:
         st = DeviceState()
         try:
             setattr(mesh, "_b200_state", st)
-        except AttributeError:  # slotted mesh objects: keep a side table
-            _SIDE_TABLE[id(mesh)] = st
+        except AttributeError:  # slotted mesh objects: keep a side table, emptied when the mesh dies
+            key = id(mesh)
+            _SIDE_TABLE[key] = st
+            try:
+                weakref.finalize(mesh, _drop_state, key)
+            except TypeError:  # not weak-referenceable either: the entry lives as long as the process
+                pass
     st.sync_topology(mesh, positions)
     return st
+
+
+def _drop_state(key: int) -> None:
+    st = _SIDE_TABLE.pop(key, None)
+    if st is not None:
+        st.dm.close()
 
 
 _SIDE_TABLE: dict[int, DeviceState] = {}

@@ -32,6 +32,9 @@ class FakeDeviceMesh:
         self.is_boundary, self.body_mask, self.fixed = is_boundary, body_mask, fixed_mask
         self.topology_uploads += 1
 
+    def set_fixed_mask(self, fixed_mask):
+        self.fixed = fixed_mask
+
     def set_surface_tension(self, gamma):
         self.gamma = gamma
 

@@ -308,6 +308,9 @@ def trajectory_vectors():
         # cached version but not the cached gradient, geometry/body.py:70-148 vs 401-410 -- so that trajectory is a
         # property of the reference's host-side cache, kept by the drop-in path but not by the device loop.)
         ("bcubep", os.path.join(REF, "meshes", "bending_cube.yaml"), 1, 5, "constrained_proj"),
+        # the same with the conjugate-gradient stepper: the volume-only evaluations of the Newton projection run
+        # between the direction and the history update
+        ("bcubepcg", os.path.join(REF, "meshes", "bending_cube.yaml"), 1, 8, "constrained_proj_cg"),
     ):
         mesh = _refined(path, levels)
         rng = np.random.default_rng(11)
@@ -321,7 +324,7 @@ def trajectory_vectors():
             gp.set("volume_constraint_mode", "penalty")
             if "volume" not in mesh.energy_modules:
                 mesh.energy_modules = list(mesh.energy_modules) + ["volume"]
-        if tweak == "cg":
+        if tweak in ("cg", "constrained_proj_cg"):
             from runtime.steppers.conjugate_gradient import ConjugateGradient
 
             stepper = ConjugateGradient()
@@ -329,14 +332,14 @@ def trajectory_vectors():
             stepper = GradientDescent()
         mini = Minimizer(mesh, gp, stepper, EnergyModuleManager(mesh.energy_modules),
                          ConstraintModuleManager(mesh.constraint_modules), quiet=True)
-        if tweak == "constrained_proj":
+        if tweak in ("constrained_proj", "constrained_proj_cg"):
             gp.set("volume_projection_during_minimization", True)
-        assert mini._has_enforceable_constraints == (tweak in ("constrained", "constrained_proj"))
+        assert mini._has_enforceable_constraints == (tweak in ("constrained", "constrained_proj", "constrained_proj_cg"))
         st = _dense_state(mesh)
         for k, v in st.items():
             out[f"{name}_{k}"] = v
         energies = []
-        if tweak == "cg":
+        if tweak in ("cg", "constrained_proj_cg"):
             # one call: the stepper keeps its history across the iterations of a single minimize()
             res = mini.minimize(n_steps=steps)
             energies = [res["energy"]] * steps

@@ -214,6 +214,31 @@ def test_residency_follows_the_version_counters(backend):
     assert st.uploads == 2 and st.nf == g["tri"].shape[0] - 2
 
 
+def test_fixed_flags_follow_their_own_counter(backend):
+    """Fixing / releasing vertices bumps only ``_fixed_flags_version`` (geometry/mesh.py:211-231): the device
+    mask follows it without a topology upload, and the projected gradient zeroes exactly the new rows."""
+    g = dict(np.load(H.GOLDEN + "/modules_cube_r2_jit.npz"))
+    mesh, gp, res = _mesh(g)
+    pos = mesh.positions_view()
+    ev = EvaluationManager(mesh=mesh, global_params=gp, param_resolver=res, energy_modules=[surface],
+                           energy_module_names=["surface"])
+    mesh.set_fixed(np.zeros(len(pos), bool))
+    _, g0, _ = ev.compute_energy_and_projected_gradient(positions=pos)
+    st = mesh._b200_state
+    assert st.uploads == 1 and np.all(np.abs(g0).sum(axis=1) > 0)
+    fixed = np.zeros(len(pos), bool)
+    fixed[[1, 4, 7]] = True
+    mesh.set_fixed(fixed)
+    _, g1, _ = ev.compute_energy_and_projected_gradient(positions=pos)
+    assert st.uploads == 1 and st.fixed_uploads >= 1
+    assert np.all(g1[fixed] == 0.0) and np.array_equal(g1[~fixed], g0[~fixed])
+    fixed2 = np.zeros(len(pos), bool)
+    fixed2[2] = True
+    mesh.set_fixed(fixed2)
+    _, g2, _ = ev.compute_energy_and_projected_gradient(positions=pos)
+    assert st.uploads == 1 and np.all(g2[2] == 0.0) and np.array_equal(g2[1], g0[1])
+
+
 def test_array_refinement_matches_reference_hierarchy():
     """1 -> 4 refinement on arrays: counts of the 24 * 4^k hierarchy, closedness,
     orientation (volume stays +1), inherited fixed flags."""
