@@ -148,32 +148,77 @@ def cpu_baseline(n_freq: int, reps: int, workers: int):
     return facets / secs / 1e9, 20 * n_freq * n_freq
 
 
+def _time_oracle_eval(pos, tri, reps_warm: int, reps: int):
+    """Seconds per whole evaluation (energies, gradient, dV/dx, KKT projection) of the CPU arm, one process."""
+    from oracle import ref_modules as ref
+
+    nv, nf = pos.shape[0], tri.shape[0]
+    gamma = np.ones(nf)
+    bnd = np.zeros(nv, bool)
+    times = []
+    for i in range(reps_warm + reps):
+        t0 = time.perf_counter()
+        out = ref.fused_surface_bending_volume(pos, tri, gamma, 1.0, 0.0, bnd)
+        ref.kkt_project_single(out["grad"], out["vol_grad"])
+        if i >= reps_warm:
+            times.append(time.perf_counter() - t0)
+    return times
+
+
 def run_reference(args):
+    """CPU arm: the reference's algorithm for this path on the host (oracle port with the C restatement of the
+    Fortran kernels = the 'Fortran-enabled' path; the reference itself cannot hold these meshes in its
+    dict-of-objects Mesh and gfortran is absent).  The reference's array path is single threaded, so `value` is ONE
+    process; one step = one evaluation of a bounded sample of the workload (a 1 003 520-facet perturbed icosphere,
+    same modules).  Extra keys: one evaluation of the full 10 M-facet mesh, and the all-core replica aggregate."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
         os.environ[k] = "1"  # the reference pins these too (tools/tilt_perf_guardrails.py:22-28)
+    from membrane_solver_b200.synthetic import frequency_for_facets, icosphere
+    from oracle import ckernels
+    from oracle import ref_modules as ref
+
+    ckernels.build()
+    ref.use_c_kernels(ckernels)
+    t_wall = time.perf_counter()
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    n_sample = 224
+    pos, tri = icosphere(n_sample)
+    nf = tri.shape[0]
+    times = _time_oracle_eval(pos, tri, warm, steps)
+    sec_step = float(np.mean(times))
+    value = nf / sec_step / 1e9
+    sample = (f"1 process, {steps} timed + {warm} warm-up evaluations of a {nf}-facet perturbed icosphere (a bounded "
+              "sample of the workload: same modules, energy + gradient + dV/dx + KKT projection); NumPy oracle with the C "
+              "restatement of fortran_kernels/*.f90 injected (gfortran absent)")
+    extra = {}
+    if not args.no_full_mesh:
+        try:  # the workload itself, once: the per-facet rate does not depend on the size
+            n_full = frequency_for_facets(args.facets)
+            pf, tf = icosphere(n_full)
+            t_full = _time_oracle_eval(pf, tf, 0, 1)[0]
+            extra["full_mesh"] = {"facets": int(tf.shape[0]), "seconds_per_evaluation": t_full,
+                                  "value": tf.shape[0] / t_full / 1e9, "unit": UNIT, "processes": 1}
+            del pf, tf
+        except MemoryError as exc:
+            extra["full_mesh"] = {"unavailable": str(exc)}
     cores = max(1, min(len(os.sched_getaffinity(0)), 64))
-    n_freq = 100  # 200 000 facets per worker
-    steps = max(1, args.steps)
-    warm = max(0, args.warmup)
-    del warm  # each worker does its own untimed first evaluation
-    reps = max(1, min(steps, 4))
-    t0 = time.perf_counter()
-    value, nf = cpu_baseline(n_freq, reps, cores)
-    wall = time.perf_counter() - t0
-    sample = (f"{cores} processes x {reps} evaluations of a {nf}-facet perturbed icosphere "
-              "(surface+bending+volume energy, gradient, dV/dx, KKT projection); NumPy oracle with "
-              "the C restatement of fortran_kernels/*.f90 injected (gfortran absent)")
+    if cores > 1:
+        agg, nf_rep = cpu_baseline(100, 2, cores)
+        extra["all_core_replicas"] = {"value": agg, "unit": UNIT, "processes": cores, "facets_per_process": nf_rep,
+                                      "note": "independent replicas on every host core: scales with the box, not the path"}
+    cfg = workload_config(args, args.gpus)
+    cfg["reference_sample"] = {"facets": int(nf), "frequency": n_sample, "processes": 1}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": reps, "warmup": 1, "ms_per_step": 1e3 * nf * cores / (value * 1e9) if value else None,
+        "steps": steps, "warmup": warm, "ms_per_step": 1e3 * sec_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": workload_config(args, args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0, "wall_s": wall,
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t_wall, **extra,
     }
     print(json.dumps(line))
     return 0
@@ -300,6 +345,39 @@ def run_b200(args):
     cpu_reps = 3
     cpu_val, cpu_nf = cpu_baseline(224, cpu_reps, 1) if not args.no_cpu else (None, 0)
 
+    # ---- strong-scaling leg: the north_star's 100 M-facet mesh on this one GPU (the N > 1 lines carry the same
+    #      mesh cut over N GPUs; speed-up = this ms_per_step / theirs) ----
+    strong = None
+    if args.strong_facets > 0:
+        dm.close()
+        t0 = time.perf_counter()
+        n_s = frequency_for_facets(args.strong_facets)
+        pos_s, tri_s = icosphere(n_s)
+        t_gen_s = time.perf_counter() - t0
+        dms = DeviceMesh(local, threads=args.threads, max_owned=args.max_owned, max_local=args.max_local,
+                         fill_pct=args.fill, repair_sweeps=args.repair)
+        t0 = time.perf_counter()
+        dms.set_topology(pos_s.shape[0], tri_s, body_mask=np.ones(tri_s.shape[0], np.uint8))
+        t_pack_s = time.perf_counter() - t0
+        dms.set_surface_tension(1.0)
+        dms.set_bending_params(1.0, 0.0)
+        dms.set_positions(pos_s)
+        for _ in range(3):
+            dms.eval_async(opts)
+        dms.sync()
+        s_steps = max(3, min(args.steps, 10))
+        dms.timer_start()
+        for _ in range(s_steps):
+            dms.eval_async(opts)
+        ms_s = dms.timer_stop() / s_steps
+        rs = dms.read_scalars()
+        strong = {"scaling": "strong", "facets": int(tri_s.shape[0]), "n_gpus": 1, "ms_per_step": ms_s,
+                  "value": tri_s.shape[0] / (ms_s * 1e-3) / 1e9, "unit": UNIT, "steps": s_steps,
+                  "energies": {"surface": rs.e_surface, "bending": rs.e_bending, "volume": rs.volume},
+                  "setup_seconds": t_gen_s + t_pack_s}
+        dms.close()
+        del pos_s, tri_s
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
@@ -314,12 +392,14 @@ def run_b200(args):
             "step_frac_72": B_STRICT * nf / (ms_step * 1e-3) / 1e9 / peak,
         },
         "kernels_ms": {"pass_a": t_a, "pass_b": t_b, "reduce+kkt": t_f},
-        "fp64": {"peak_tflops_measured": 33.9, "note": "tools/fp64_peak.cu on this pool's B200; the path is "
-                 "co-limited by fp64 issue rate, see DESIGN.md section 3.4"},
+        "fp64": {"peak_tflops_measured": 33.9, "note": "tools/fp64_peak.cu on this pool's B200; the kernels are "
+                 "instruction-issue / latency bound at 12 consumer warps per SM, see DESIGN.md section 3.4"},
         "cpu_baseline": None if cpu_val is None else {
             "value": cpu_val, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"{cpu_reps} evaluations of a {cpu_nf}-facet perturbed icosphere, same modules; NumPy oracle "
-                      "with the C restatement of fortran_kernels/*.f90 (gfortran absent), 1 process"},
+            "sample": f"1 process, {cpu_reps} evaluations of a {cpu_nf}-facet perturbed icosphere (a bounded sample of the "
+                      "workload, same modules); NumPy oracle with the C restatement of fortran_kernels/*.f90 (gfortran "
+                      "absent).  The reference's array path is single threaded: see --impl reference for the all-core "
+                      "replica figure"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pos.nbytes),
                 "d2h_bytes_per_step": int(grad.nbytes + 8 * L.SC_COUNT), "ms_per_step": ms_e2e,
                 "api": "ms_ctx_eval_host (pinned host positions in, projected gradient + scalars out)"},
@@ -328,8 +408,11 @@ def run_b200(args):
         "pack": {**info, "seconds": t_pack, "mesh_gen_seconds": t_gen},
         "energies": {"surface": res.e_surface, "bending": res.e_bending, "volume": res.volume},
     }
+    if strong is not None:
+        line["strong"] = strong
     print(json.dumps(line))
-    dm.close()
+    if strong is None:
+        dm.close()
     return 0
 
 
@@ -346,6 +429,10 @@ def main():
     ap.add_argument("--fill", type=int, default=None, help="packer: target percent of record slots holding a facet")
     ap.add_argument("--repair", type=int, default=None, help="packer: lane-placement repair passes")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--strong-facets", type=int, default=100_000_000,
+                    help="total facets of the strong-scaling leg (BASELINE.json north_star: 100 M); 0 = skip")
+    ap.add_argument("--no-full-mesh", action="store_true", help="reference arm: skip the one full-size evaluation")
+    ap.add_argument("--no-parity", action="store_true", help="N>1: skip the comparison with one GPU on the same mesh")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -152,6 +152,7 @@ SIGNATURES = {
     "ms_ctx_leaflet_cg_direction": (ctypes.c_int, [_V, _i32, _f64, _i32, _i32]),
     "ms_ctx_leaflet_swap_trial": (ctypes.c_int, [_V, _i32]),
     "ms_ctx_ipc_export": (ctypes.c_int, [_V, _i32, _B]),
+    "ms_ctx_peer_close": (ctypes.c_int, [_V]),
     "ms_ctx_peer_open": (ctypes.c_int, [_V, _i32, _i32, _B]),
     "ms_ctx_peer_set_pointer": (ctypes.c_int, [_V, _i32, _i32, _V]),
     "ms_ctx_flag_words_ptr": (_V, [_V]),

@@ -377,6 +377,9 @@ class DeviceMesh:
         L.check(self._lib.ms_ctx_ipc_export(self._h, int(which), buf))
         return bytes(buf)
 
+    def peer_close(self) -> None:
+        L.check(self._lib.ms_ctx_peer_close(self._h))
+
     def peer_open(self, slot: int, which: int, handle: bytes) -> None:
         if len(handle) != L.IPC_HANDLE_BYTES:
             raise ValueError("IPC handles are 64 bytes")

@@ -1410,6 +1410,15 @@ int ms_ctx_ipc_export(ms_ctx* c, int32_t which, uint8_t* handle64) {
 
 static int peer_register(ms_ctx* c, int32_t slot, int32_t which, void* p);
 
+int ms_ctx_peer_close(ms_ctx* c) {
+  if (int rc = check_ctx(c, false)) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  for (void* p : c->peers.opened)
+    if (p) cudaIpcCloseMemHandle(p);
+  c->peers = ms_ctx::PeerTable();
+  return 0;
+}
+
 int ms_ctx_peer_open(ms_ctx* c, int32_t slot, int32_t which, const uint8_t* handle64) {
   if (int rc = check_ctx(c, true)) return rc;
   if (!handle64 || slot < 0 || slot >= 4096) return fail(-1, "bad peer arguments");

@@ -204,6 +204,15 @@ class PartitionedMesh:
         self._side_stream = torch.cuda.Stream(device=self.device)
         self._compute_stream_handle = None  # the context's own stream (legacy default stream)
 
+    def close(self) -> None:
+        """Collective: every rank closes the peer arrays it opened, the ranks meet, then the contexts go."""
+        self.torch.cuda.synchronize(self.device)
+        self._views.clear()
+        if self.transport == "peer":
+            self.dm.peer_close()
+        self.dist.barrier()
+        self.dm.close()
+
     def view(self, which: int):
         t = self._views.get(which)
         if t is None:
@@ -345,23 +354,15 @@ class PartitionedMesh:
         return dm.read_scalars()
 
 
-def bench_multi_gpu(args, rank: int, world: int, local_rank: int, bench):
-    """N>1 arm of bench.py: weak scaling, ``args.facets`` facets per GPU."""
-    import json
+def _shared_mesh(n: int, rank: int, dist, tag: str):
+    """Frequency-n icosphere on every rank: generated once (rank 0), shared through /dev/shm."""
     import os
     import time
 
-    import torch
-    import torch.distributed as dist
+    from .synthetic import icosphere
 
-    from . import _lib as L
-    from .synthetic import frequency_for_facets, icosphere
-
-    torch.cuda.set_device(local_rank)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    n = frequency_for_facets(args.facets * world)
     shm = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
-    path = os.path.join(shm, f"ms_b200_bench_{os.environ.get('MASTER_PORT', '0')}_n{n}.npz")
+    path = os.path.join(shm, f"ms_b200_bench_{os.environ.get('MASTER_PORT', '0')}_{tag}_n{n}.npz")
     t0 = time.perf_counter()
     if rank == 0:
         pos, tri = icosphere(n)
@@ -373,10 +374,68 @@ def bench_multi_gpu(args, rank: int, world: int, local_rank: int, bench):
     dist.barrier()
     if rank == 0:
         os.remove(path)
-    t_gen = time.perf_counter() - t0
+    return pos, tri, time.perf_counter() - t0
+
+
+def _parity_vs_single_gpu(pm, local, pos, tri, opts, rank, world, dist, torch, L, sample_rows: int = 4096):
+    """Correctness of the partitioned evaluation against ONE GPU evaluating the same mesh (rank 0, its own
+    context): the all-reduced scalars, and the projected gradient on a random sample of every rank's owned rows.
+    Returns (dict, ok) on rank 0, (None, True) elsewhere."""
+    from .context import DeviceMesh
+
+    dm = pm.dm
+    pm.eval_async(opts)
+    torch.cuda.synchronize()
+    sc = dm.read_scalars().scalars.copy()
+    rng = np.random.default_rng(1234 + rank)
+    rows = np.sort(rng.choice(local.n_owned, size=min(sample_rows, local.n_owned), replace=False))
+    g_owned = dm.download(L.ARR_GRAD)[rows]
+    payload = (local.lo + rows, g_owned)
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(payload, gathered, dst=0)
+    if rank != 0:
+        return None, True
     nv, nf = pos.shape[0], tri.shape[0]
+    one = DeviceMesh(pm.device.index)
+    one.set_topology(nv, tri, body_mask=np.ones(nf, np.uint8))
+    one.set_surface_tension(1.0)
+    one.set_bending_params(1.0, 0.0)
+    one.set_positions(pos)
+    ref = one.eval(one.options(L.MOD_SURFACE | L.MOD_BENDING | L.MOD_VOLUME, constraint_mode=0))
+    g_ref = one.download(L.ARR_GRAD)
+    one.close()
+    names = {"E_surface": L.SC_E_SURFACE, "area": L.SC_AREA, "volume": L.SC_VOLUME, "E_bending": L.SC_E_BENDING,
+             "lambda": L.SC_LAMBDA}
+    err = {k: float(abs(sc[i] - ref.scalars[i]) / max(abs(ref.scalars[i]), 1e-300)) for k, i in names.items()}
+    scale = float(np.abs(g_ref).max())
+    g_err = 0.0
+    n_rows = 0
+    for ids, g in gathered:
+        g_err = max(g_err, float(np.abs(g - g_ref[ids]).max()) / scale)
+        n_rows += len(ids)
+    tol = 1e-12
+    ok = all(v <= 1e-11 if k == "lambda" else v <= tol for k, v in err.items()) and g_err <= tol
+    return {"against": "one GPU evaluating the same mesh (rank 0)", "scalar_rel_err": err,
+            "projected_grad_rel_err": g_err, "sampled_rows": n_rows, "tolerance": tol, "ok": bool(ok)}, bool(ok)
+
+
+def _measure_partitioned(args, rank, world, local_rank, bench, total_facets: int, tag: str, *, with_e2e: bool,
+                         with_parity: bool, steps: int):
+    """Build, partition and time one mesh of ~total_facets facets on `world` GPUs.  Returns a dict on rank 0."""
+    import os
+    import time
+
+    import torch
+    import torch.distributed as dist
+
+    from . import _lib as L
+    from .synthetic import frequency_for_facets
+
+    n = frequency_for_facets(total_facets)
+    pos, tri, t_gen = _shared_mesh(n, rank, dist, tag)
+    nv, nf = pos.shape[0], tri.shape[0]
+    t0 = time.perf_counter()
     local = split_mesh(nv, tri, world, rank)
-    del tri
     pm = PartitionedMesh(local, local_rank, body_mask=np.ones(local.tri.shape[0], np.uint8),
                          reserve_sms=int(os.environ.get("MS_RESERVE_SMS", "0")),
                          pack=dict(threads=args.threads, max_owned=args.max_owned, max_local=args.max_local,
@@ -386,7 +445,7 @@ def bench_multi_gpu(args, rank: int, world: int, local_rank: int, bench):
     dm.set_bending_params(1.0, 0.0)
     pos_local = pos[local.global_rows()]
     dm.set_positions(pos_local)
-    del pos
+    t_setup = time.perf_counter() - t0
     opts = dm.options(L.MOD_SURFACE | L.MOD_BENDING | L.MOD_VOLUME, constraint_mode=0)
 
     sampler = bench.ClockSampler(local_rank)
@@ -399,7 +458,7 @@ def bench_multi_gpu(args, rank: int, world: int, local_rank: int, bench):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.active.set()
     ev0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         pm.eval_async(opts, overlap=overlap)
     ev1.record()
     torch.cuda.synchronize()
@@ -408,8 +467,12 @@ def bench_multi_gpu(args, rank: int, world: int, local_rank: int, bench):
     sampler.active.clear()
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=pm.device)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_step = float(ms.item()) / args.steps
+    ms_step = float(ms.item()) / steps
     res = dm.read_scalars()
+    out = {"facets": nf, "vertices": nv, "frequency": n, "ms_per_step": ms_step, "steps": steps,
+           "value": nf / (ms_step * 1e-3) / 1e9, "mesh_seconds": t_gen, "partition_pack_seconds": t_setup,
+           "transport": pm.transport,
+           "energies": {"surface": res.e_surface, "bending": res.e_bending, "volume": res.volume}}
     phases = None
     if os.environ.get("MS_PHASES", "0") != "0":  # per-phase device times of this rank (diagnostic)
         names = ["halo(pos)", "pass A", "halo(seeds)", "pass B", "reduce", "all-reduce", "project"]
@@ -436,65 +499,113 @@ def bench_multi_gpu(args, rank: int, world: int, local_rank: int, bench):
         dist.all_gather(alls, stats)
         phases = {"names": names, "ms_per_rank": [[round(float(x), 4) for x in t.tolist()] for t in allp],
                   "listed_patches_facets_rows_per_rank": [[int(x) for x in t.tolist()] for t in alls]}
-    # ---- end to end: pinned host positions of the owned rows in, projected gradient out, every step ----
-    lib = L.lib()
-    pos_owned = np.ascontiguousarray(pos_local[:local.n_owned])
-    grad_owned = np.empty_like(pos_owned)
-    L.check(lib.ms_host_register(pos_owned.ctypes.data, pos_owned.nbytes))
-    L.check(lib.ms_host_register(grad_owned.ctypes.data, grad_owned.nbytes))
-    for _ in range(2):
-        pm.eval_host(opts, pos_owned, grad_owned)
-    e2e_steps = max(3, min(args.steps, 10))
-    torch.cuda.synchronize()
-    dist.barrier()
-    torch.cuda.synchronize()
-    ev0.record()
-    for _ in range(e2e_steps):
-        pm.eval_host(opts, pos_owned, grad_owned)
-    ev1.record()
-    torch.cuda.synchronize()
-    dist.barrier()
+        out["phases"] = phases
+    if with_e2e:
+        # ---- end to end: pinned host positions of the owned rows in, projected gradient out, every step ----
+        lib = L.lib()
+        pos_owned = np.ascontiguousarray(pos_local[:local.n_owned])
+        grad_owned = np.empty_like(pos_owned)
+        L.check(lib.ms_host_register(pos_owned.ctypes.data, pos_owned.nbytes))
+        L.check(lib.ms_host_register(grad_owned.ctypes.data, grad_owned.nbytes))
+        for _ in range(2):
+            pm.eval_host(opts, pos_owned, grad_owned)
+        e2e_steps = max(3, min(steps, 10))
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(e2e_steps):
+            pm.eval_host(opts, pos_owned, grad_owned)
+        ev1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        ms2 = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=pm.device)
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+        ms_e2e = float(ms2.item()) / e2e_steps
+        L.check(lib.ms_host_unregister(pos_owned.ctypes.data))
+        L.check(lib.ms_host_unregister(grad_owned.ctypes.data))
+        io = torch.tensor([pos_owned.nbytes, grad_owned.nbytes + 8 * L.SC_COUNT], dtype=torch.float64, device=pm.device)
+        dist.all_reduce(io, op=dist.ReduceOp.SUM)
+        out["e2e"] = {"value": nf / (ms_e2e * 1e-3) / 1e9, "unit": bench.UNIT, "h2d_bytes_per_step": int(io[0].item()),
+                      "d2h_bytes_per_step": int(io[1].item()), "ms_per_step": ms_e2e,
+                      "api": "PartitionedMesh.eval_host per rank (pinned owned positions in, halo exchange, "
+                             "projected gradient of the owned rows + scalars out)"}
     if pm.transport == "peer" and dm.halo_error():
         raise L.B200Error(f"rank {rank}: a peer-memory pull gave up waiting; the numbers of this run are void")
-    ms2 = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=pm.device)
-    dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    ms_e2e = float(ms2.item()) / e2e_steps
-    L.check(lib.ms_host_unregister(pos_owned.ctypes.data))
-    L.check(lib.ms_host_unregister(grad_owned.ctypes.data))
-    io = torch.tensor([pos_owned.nbytes, grad_owned.nbytes + 8 * L.SC_COUNT], dtype=torch.float64, device=pm.device)
-    dist.all_reduce(io, op=dist.ReduceOp.SUM)
     ghosts = torch.tensor([local.ghost_ids.size, pm.halo.send_rows.size], dtype=torch.float64, device=pm.device)
     dist.all_reduce(ghosts, op=dist.ReduceOp.MAX)
+    out["max_ghost_rows_per_rank"] = int(ghosts[0].item())
+    if with_parity:
+        parity, ok = _parity_vs_single_gpu(pm, local, pos, tri, opts, rank, world, dist, torch, L)
+        flag = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64, device=pm.device)
+        dist.broadcast(flag, src=0)
+        out["parity"] = parity
+        if flag.item() == 0.0 and rank == 0:
+            out["void"] = "the partitioned evaluation differs from the single-GPU evaluation: numbers of this run are void"
     sampler.close()
+    out["clocks"] = sampler.summary()
+    pm.close()
+    del pm, dm
+    torch.cuda.empty_cache()
+    return out
+
+
+def bench_multi_gpu(args, rank: int, world: int, local_rank: int, bench):
+    """N>1 arm of bench.py.  Weak scaling (``args.facets`` facets per GPU) is the headline line the driver's
+    scaling run reads; the same line carries ``strong``: the ``args.strong_facets``-facet mesh (BASELINE.json
+    north_star: 100 M facets) cut over the N GPUs, and ``parity``: the partitioned result against one GPU
+    evaluating the same mesh."""
+    import json
+
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    weak = _measure_partitioned(args, rank, world, local_rank, bench, args.facets * world, "weak", with_e2e=True,
+                                with_parity=not args.no_parity, steps=args.steps)
+    strong = None
+    if args.strong_facets > 0:
+        strong = _measure_partitioned(args, rank, world, local_rank, bench, args.strong_facets, "strong", with_e2e=False,
+                                      with_parity=False, steps=max(3, min(args.steps, 10)))
     if rank == 0:
         peak, peak_kind = bench._peaks()
-        value = nf / (ms_step * 1e-3) / 1e9
+        value = weak["value"]
+        peer = weak["transport"] == "peer"
         line = {
             "metric": bench.METRIC, "value": value, "unit": bench.UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
+            "warmup": max(3, args.warmup), "ms_per_step": weak["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {**bench.workload_config(args, world), "parallelism": f"vertex-partition x{world}, 1-ring ghosts",
-                       "max_ghost_rows_per_rank": int(ghosts[0].item())},
+                       "max_ghost_rows_per_rank": weak["max_ghost_rows_per_rank"]},
             "roofline": {"bound": "hbm", "kernel": "whole step (all ranks)", "achieved": bench.B_STEP * value,
                          "peak": peak * world, "unit": "GB/s", "frac": bench.B_STEP * value / (peak * world),
                          "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({peak_kind}) x {world} GPUs",
                          "bytes_per_facet": bench.B_STEP},
-            "e2e": {"value": nf / (ms_e2e * 1e-3) / 1e9, "unit": bench.UNIT, "h2d_bytes_per_step": int(io[0].item()),
-                    "d2h_bytes_per_step": int(io[1].item()), "ms_per_step": ms_e2e,
-                    "api": "PartitionedMesh.eval_host per rank (pinned owned positions in, halo exchange, "
-                           "projected gradient of the owned rows + scalars out)"},
-            "collectives_per_step": {"halo_exchanges": 2, "all_reduce": 1, "halo_transport": pm.transport,
-                                     "all_reduce_transport": "peer memory" if pm.transport == "peer" else "nccl",
-                                     "halo_bytes_per_rank": int(ghosts[0].item()) * (24 + 40)},
-            # pass A, pass B, reduce, project + per halo exchange: flag signal + pull (peer) or the row gather (nccl)
+            "e2e": weak["e2e"],
+            "collectives_per_step": {"halo_exchanges": 2, "all_reduce": 1, "halo_transport": weak["transport"],
+                                     "all_reduce_transport": "peer memory" if peer else "nccl",
+                                     "halo_bytes_per_rank": weak["max_ghost_rows_per_rank"] * (24 + 40)},
+            # pass A, pass B, reduce, coefficient + per halo exchange: flag signal + pull (peer) or the row gather (nccl)
             # + the peer all-reduce's publish and gather kernels
-            "gpu_launches": (4 + (6 if pm.transport == "peer" else 2)) * args.steps,
-            "clocks": sampler.summary(),
-            "energies": {"surface": res.e_surface, "bending": res.e_bending, "volume": res.volume},
-            "setup_seconds": t_gen,
+            "gpu_launches": (4 + (6 if peer else 2)) * args.steps,
+            "clocks": weak["clocks"],
+            "energies": weak["energies"],
+            "setup_seconds": weak["mesh_seconds"] + weak["partition_pack_seconds"],
+            "parity": weak.get("parity"),
         }
-        if phases is not None:
-            line["phases"] = phases
+        if "void" in weak:
+            line["void"] = weak["void"]
+        if "phases" in weak:
+            line["phases"] = weak["phases"]
+        if strong is not None:
+            # strong scaling: total work fixed; the N = 1 run of bench.py reports the same mesh on one GPU
+            line["strong"] = {"scaling": "strong", "facets": strong["facets"], "n_gpus": world,
+                              "ms_per_step": strong["ms_per_step"], "value": strong["value"], "unit": bench.UNIT,
+                              "steps": strong["steps"], "transport": strong["transport"],
+                              "energies": strong["energies"],
+                              "setup_seconds": strong["mesh_seconds"] + strong["partition_pack_seconds"],
+                              "note": "speed-up over one GPU = strong.ms_per_step of the --gpus 1 line / this ms_per_step"}
         print(json.dumps(line))
     dist.destroy_process_group()
     return 0

@@ -513,6 +513,124 @@ def test_full_size_invariants(L):
     dm.close()
 
 
+# -------------------------------------------------------------- parity at size (BASELINE.json configs[2], configs[4])
+def _volgrad_close(got, want, pos):
+    """dV/dx_v = 1/6 sum_i p_i x p_(i+1) cancels from O(|p|^2) summands down to O(h^2): on fine meshes the
+    reference's own result moves by more than 1e-12 of its magnitude when its sum is re-ordered.  The bound is
+    therefore 1e-12 relative to the size of the summands, and 1e-10 relative to max |dV/dx|."""
+    err = float(np.abs(np.asarray(got) - np.asarray(want)).max())
+    summand = float((np.asarray(pos) ** 2).sum(axis=1).max()) / 6.0
+    assert err <= TOL * summand, (err, summand)
+    assert err <= 1e-10 * float(np.abs(want).max()), (err, float(np.abs(want).max()))
+
+
+def test_million_facet_icosphere_vs_oracle(L):
+    """1 003 520 facets: the largest mesh on which the whole-mesh oracle runs in seconds; energies, gradient and
+    dV/dx of the fused evaluation and of the KKT-projected evaluation at 1e-12 relative."""
+    from membrane_solver_b200.synthetic import icosphere
+    from oracle import ref_modules as ref
+
+    pos, tri = icosphere(224)
+    nv, nf = pos.shape[0], tri.shape[0]
+    assert nf >= 1_000_000
+    want = ref.fused_surface_bending_volume(pos, tri, np.ones(nf), 1.0, 0.05, np.zeros(nv, bool))
+    dm = _ctx(nv, tri, body_mask=np.ones(nf, np.uint8))
+    dm.set_bending_params(1.0, 0.05)
+    dm.set_positions(pos)
+    mods = L.MOD_SURFACE | L.MOD_BENDING | L.MOD_VOLUME
+    r = dm.eval(dm.options(mods))
+    for got, name in ((r.e_surface, "E_surface"), (r.e_bending, "E_bending"), (r.volume, "volume"), (r.area, "area")):
+        _scalar_close(got, want[name])
+    g = dm.download(L.ARR_GRAD)
+    gv = dm.download(L.ARR_VOLGRAD)
+    assert rel_err(g, want["grad"]) <= TOL
+    _volgrad_close(gv, want["vol_grad"], pos)
+    rp = dm.eval(dm.options(mods, constraint_mode=0))
+    lam = float(np.vdot(want["grad"], want["vol_grad"]) / np.vdot(want["vol_grad"], want["vol_grad"]))
+    assert abs(rp.kkt_lambda - lam) <= 1e-10 * abs(lam)
+    assert rel_err(dm.download(L.ARR_GRAD), want["grad"] - lam * want["vol_grad"]) <= TOL
+    dm.close()
+
+
+def test_bending_cube_r8_vs_oracle(L):
+    """BASELINE.json configs[2] at its stated size: the cube of meshes/bending_cube.yaml refined to
+    24 * 4^8 = 1 572 864 facets (array refinement, geometry/refine.py), jittered so that no vertex is flat;
+    Helfrich bending + volume against the oracle."""
+    from membrane_solver_b200.geometry.refine import cube_mesh, refine_triangles
+    from oracle import ref_modules as ref
+
+    pos, tri = cube_mesh()
+    for _ in range(8):
+        pos, tri, _, _ = refine_triangles(pos, tri)
+    nv, nf = pos.shape[0], tri.shape[0]
+    assert nf == 1_572_864
+    rng = np.random.default_rng(8)
+    pos = pos + 2.0e-4 * rng.normal(size=pos.shape)
+    want = ref.fused_surface_bending_volume(pos, tri, np.zeros(nf), 1.0, 0.0, np.zeros(nv, bool))
+    dm = _ctx(nv, tri, body_mask=np.ones(nf, np.uint8), order_hint=pos)  # refinement order -> Morton order inside
+    dm.set_surface_tension(0.0)
+    dm.set_bending_params(1.0, 0.0)
+    dm.set_positions(pos)
+    r = dm.eval(dm.options(L.MOD_BENDING | L.MOD_VOLUME))
+    _scalar_close(r.e_bending, want["E_bending"])
+    _scalar_close(r.volume, want["volume"])
+    assert rel_err(dm.download(L.ARR_GRAD), want["grad"]) <= 2e-12
+    _volgrad_close(dm.download(L.ARR_VOLGRAD), want["vol_grad"], pos)
+    dm.close()
+
+
+def _sample_submeshes(tri, nv, n_seeds, radius, rng):
+    """Around each random seed vertex: the vertices within `radius` rings (the sample rows S0) and the facets touching
+    S0 or a neighbour of S0 -- everything the gradient rows of S0 depend on (seeds of the 1-ring need the 2-ring)."""
+    order = np.argsort(tri.reshape(-1), kind="stable")
+    corner_vertex = tri.reshape(-1)[order]
+    ptr = np.searchsorted(corner_vertex, np.arange(nv + 1))
+    facet_of = order // 3
+
+    def facets_of(vs):
+        return np.unique(np.concatenate([facet_of[ptr[v]:ptr[v + 1]] for v in vs]))
+
+    for seed in rng.integers(0, nv, size=n_seeds):
+        s0 = np.array([seed])
+        for _ in range(radius):
+            s0 = np.unique(tri[facets_of(s0)].reshape(-1))
+        s1 = np.unique(tri[facets_of(s0)].reshape(-1))
+        f = facets_of(s1)
+        yield s0, f
+
+
+def test_ten_million_facets_sampled_patches_vs_oracle(L):
+    """BASELINE.json configs[4] at 10 025 280 facets: the oracle cannot run on the whole mesh, so it runs on 48
+    random sub-meshes (each the closure the gradient rows of its sample vertices depend on) and the sampled
+    gradient / dV/dx rows of the full-size device evaluation must agree at 1e-12 relative to the mesh-wide scale."""
+    from membrane_solver_b200.synthetic import frequency_for_facets, icosphere
+    from oracle import ref_modules as ref
+
+    pos, tri = icosphere(frequency_for_facets(10_000_000))
+    nv, nf = pos.shape[0], tri.shape[0]
+    dm = _ctx(nv, tri, body_mask=np.ones(nf, np.uint8))
+    dm.set_bending_params(1.0, 0.05)
+    dm.set_positions(pos)
+    dm.eval(dm.options(L.MOD_SURFACE | L.MOD_BENDING | L.MOD_VOLUME))
+    g = dm.download(L.ARR_GRAD)
+    gv = dm.download(L.ARR_VOLGRAD)
+    dm.close()
+    g_scale, gv_scale = np.abs(g).max(), np.abs(gv).max()
+    rng = np.random.default_rng(2026)
+    n_rows = 0
+    for s0, f in _sample_submeshes(tri, nv, 48, 4, rng):
+        verts, local = np.unique(tri[f].reshape(-1), return_inverse=True)
+        sub_tri = local.reshape(-1, 3).astype(np.int32)
+        want = ref.fused_surface_bending_volume(pos[verts], sub_tri, np.ones(len(f)), 1.0, 0.05,
+                                                np.zeros(len(verts), bool))
+        rows = np.searchsorted(verts, s0)
+        assert np.abs(g[s0] - want["grad"][rows]).max() <= TOL * g_scale
+        assert np.abs(gv[s0] - want["vol_grad"][rows]).max() <= max(1e-10 * gv_scale, 0.0)
+        assert np.abs(gv[s0] - want["vol_grad"][rows]).max() <= TOL * float((pos ** 2).sum(axis=1).max()) / 6.0
+        n_rows += len(s0)
+    assert n_rows >= 48 * 30
+
+
 def test_pipelined_host_evaluation_matches_staged_path(L):
     """ms_ctx_eval_host on a large mesh overlaps the chunked position upload with the patch kernels
     (patches launched in the order their rows arrive).  The per-vertex sums do not depend on the launch
