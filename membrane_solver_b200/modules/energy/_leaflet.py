@@ -7,12 +7,14 @@ Numerics: ``csrc/ms_leaflet.cuh`` through ``ms_ctx_set_leaflet`` / ``ms_ctx_eval
 Selections: WHICH facets belong to a leaflet, WHICH rows carry a base term and the per-vertex leaflet
 parameters are mesh-option bookkeeping of the reference (``leaflet_presence.py``, ``bt_selection.py``,
 ``bt_params.py``, ``tilt_params.py``, ``tilt_utils.py``), not arithmetic.  They reach the device as plain
-masks (``struct ms_leaflet_desc``) from one of two sources:
+masks (``struct ms_leaflet_desc``) from one of three sources:
 
-* a mesh that answers ``leaflet_selection(leaflet)`` (``geometry.array_mesh.ArrayMesh``) supplies them
-  directly;
-* inside the reference process (after ``runtime.energy_manager.install()``) they are obtained from the
-  reference's own selection helpers, imported under their ``modules.energy.*`` names.
+* a mesh that answers ``leaflet_selection(leaflet)`` with ready-made arrays (``ArrayMesh(leaflets=...)``);
+* ``leaflet_selection.py``: this package's own derivation from the vertex options and the global parameters
+  (presets, base-term boundary group, assume-J0 rows, region modes, per-vertex moduli) -- the path of
+  BASELINE configs[3] and of any ``ArrayMesh(vertex_options=...)``;
+* for the reference's experimental rim / shell controls only (``leaflet_selection.needs_reference_helpers``):
+  the reference's own helpers, imported under their ``modules.energy.*`` names inside the reference process.
 
 The reference's experimental switches that change the arithmetic are refused loudly (no silent
 approximation): recovered / trace-reconstructed divergence, stage-A lanes, inner update modes, the
@@ -127,10 +129,30 @@ def _selection_from_reference(mesh, global_params, param_resolver, leaflet: str)
 
 
 def selection(mesh, global_params, param_resolver, leaflet: str) -> dict:
+    from . import leaflet_selection as LS
+
     own = getattr(mesh, "leaflet_selection", None)
-    if own is not None:
+    given = getattr(mesh, "leaflets", None)       # ArrayMesh: ready-made arrays per leaflet, possibly none
+    if own is not None and (given is None or leaflet in given):
         return own(leaflet)
-    return _selection_from_reference(mesh, global_params, param_resolver, leaflet)
+    if LS.needs_reference_helpers(global_params):
+        return _selection_from_reference(mesh, global_params, param_resolver, leaflet)
+    key = (int(getattr(mesh, "_vertex_ids_version", 0) or 0), int(getattr(mesh, "_topology_version", 0) or 0),
+           int(getattr(mesh, "_facet_loops_version", 0) or 0), int(getattr(mesh, "_version", 0) or 0), leaflet,
+           id(global_params))
+    cache = getattr(mesh, "_b200_leaflet_selection_cache", None)
+    if cache is None:
+        cache = {}
+        try:
+            setattr(mesh, "_b200_leaflet_selection_cache", cache)
+        except AttributeError:
+            pass
+    hit = cache.get(leaflet)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    spec = LS.leaflet_selection(mesh, global_params, param_resolver, leaflet)
+    cache[leaflet] = (key, spec)
+    return spec
 
 
 def _leaflet_tilts(mesh, leaflet: str, tilts) -> np.ndarray:

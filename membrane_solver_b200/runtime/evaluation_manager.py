@@ -179,6 +179,35 @@ class EvaluationManager:
                                                             **kwargs))
         return float(total)
 
+    def compute_energy_array_with_tilts(self, *, positions, tilts) -> float:
+        """Tilt-dependent energy for fixed positions and a given tilt field (``evaluation_manager.py:303-384``, the
+        accept / reject energy of the single-field tilt relaxation, ``runtime/minimizer.py:756-768``): only the
+        modules with ``USES_TILT`` take part; ``compute_energy_array`` is preferred, then the array gradient API
+        into a scratch gradient, then the legacy dict API -- the reference's order."""
+        index_map = self.mesh.vertex_index_to_row
+        names = self.energy_module_names
+        if len(names) != len(self.energy_modules):
+            names = [getattr(m, "__name__", m.__class__.__name__) for m in self.energy_modules]
+        total = 0.0
+        for name, mod in zip(names, self.energy_modules):
+            if not getattr(mod, "USES_TILT", False):
+                continue
+            scale = float(self.experimental_energy_scale_fn(str(name)))
+            if hasattr(mod, "compute_energy_array"):
+                e = self._call_fn(mod.compute_energy_array, positions=positions, index_map=index_map, tilts=tilts)
+            elif hasattr(mod, "compute_energy_and_gradient_array"):
+                dummy = None if hasattr(mod, "B200_MODULE") else np.zeros_like(np.asarray(positions, dtype=np.float64))
+                e = self._call_fn(mod.compute_energy_and_gradient_array, positions=positions, index_map=index_map,
+                                  grad_arr=dummy, tilts=tilts, tilt_grad_arr=None)
+            else:
+                try:
+                    e, _ = mod.compute_energy_and_gradient(self.mesh, self.global_params, self.param_resolver,
+                                                           compute_gradient=False)
+                except TypeError:
+                    e, _ = mod.compute_energy_and_gradient(self.mesh, self.global_params, self.param_resolver)
+            total += scale * float(e)
+        return float(total)
+
     def compute_energy_and_tilt_gradient_array(self, *, positions, tilts, tilt_grad_arr) -> float:
         """Tilt-dependent energy and dense tilt gradient (``evaluation_manager.py:386-462``): only the
         modules with ``USES_TILT`` take part; ``tilt_grad_arr`` is overwritten."""

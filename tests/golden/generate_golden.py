@@ -397,6 +397,31 @@ def leaflet_vectors():
         for vid in mesh.boundary_vertex_ids:
             isb[idx[vid]] = True
         out[f"{state}_pos"], out[f"{state}_tri"], out[f"{state}_is_boundary"] = pos, tri, isb
+        # the mesh options the selections are derived from (leaflet_selection.py re-derives them on arrays): the
+        # vertex presets / group tags / numeric overrides, the mesh's own positions and the global parameters
+        opt_keys = ("preset", "rim_slope_match_group", "tilt_thetaB_group", "tilt_thetaB_group_in",
+                    "tilt_thetaB_group_out", "bending_modulus", "bending_modulus_in", "bending_modulus_out",
+                    "spontaneous_curvature", "spontaneous_curvature_in", "spontaneous_curvature_out",
+                    "intrinsic_curvature")
+        vopts = {}
+        for row, vid in enumerate(mesh.vertex_ids):
+            o = getattr(mesh.vertices[int(vid)], "options", None) or {}
+            keep_o = {k: o[k] for k in opt_keys if k in o and o[k] is not None}
+            if keep_o:
+                vopts[int(row)] = keep_o
+        import json as _json
+
+        gp_dump = {}
+        for k in gp.to_dict() if hasattr(gp, "to_dict") else dict(getattr(gp, "_params", {})):
+            v = gp.get(k)
+            try:
+                _json.dumps(v)
+            except TypeError:
+                continue
+            gp_dump[k] = v
+        out[f"{state}_vertex_options_json"] = np.array(_json.dumps(vopts))
+        out[f"{state}_global_params_json"] = np.array(_json.dumps(gp_dump))
+        out[f"{state}_mesh_pos"] = np.array(mesh.positions_view())
         for leaf, sign, bt, tm, sm in (("in", -1.0, bending_tilt_in, tilt_in, tilt_smoothness_in),
                                        ("out", 1.0, bending_tilt_out, tilt_out, tilt_smoothness_out)):
             pre = f"{state}_{leaf}_"

@@ -231,6 +231,111 @@ def _array_mesh(gold, state):
                      leaflets=leaflets)
 
 
+def _options_mesh(gold, state):
+    """ArrayMesh carrying the mesh OPTIONS (vertex presets / group tags, global parameters) instead of ready-made
+    masks: the selections are derived by membrane_solver_b200/modules/energy/leaflet_selection.py."""
+    import json
+
+    from membrane_solver_b200.geometry.array_mesh import ArrayMesh, GlobalParams
+
+    vopts = {int(k): v for k, v in json.loads(str(gold[f"{state}_vertex_options_json"])).items()}
+    gp = GlobalParams(json.loads(str(gold[f"{state}_global_params_json"])))
+    return ArrayMesh(gold[f"{state}_mesh_pos"], gold[f"{state}_tri"], global_params=gp, vertex_options=vopts,
+                     tilts_in=gold[f"{state}_in_tilts"], tilts_out=gold[f"{state}_out_tilts"]), gp
+
+
+@pytest.mark.parametrize("state", STATES)
+def test_own_leaflet_selection_matches_reference_masks(gold, state):
+    """leaflet_presence.py:34-170, bt_selection.py:140-330, bt_params.py:40-318, tilt_params.py:6-24 re-derived on
+    arrays: every mask / parameter equals what the reference's helpers produced for its caveolin mesh."""
+    from membrane_solver_b200.geometry.array_mesh import ParamResolver
+    from membrane_solver_b200.modules.energy import _leaflet as LF
+    from membrane_solver_b200.modules.energy import leaflet_selection as LS
+
+    mesh, gp = _options_mesh(gold, state)
+    assert not LS.needs_reference_helpers(gp)
+    assert set(mesh.boundary_vertex_ids) == set(np.nonzero(gold[f"{state}_is_boundary"])[0].tolist())
+    for leaf in LEAFLETS:
+        spec = LF.selection(mesh, gp, ParamResolver(gp), leaf)
+        pre = f"{state}_{leaf}_"
+        assert np.array_equal(spec["keep_bt"], gold[pre + "keep"]) and np.array_equal(spec["keep_tilt"], gold[pre + "keep"])
+        assert np.array_equal(spec["interior"], gold[pre + "interior"])
+        assert np.array_equal(spec["base_zero"], gold[pre + "base_zero"])
+        assert np.array_equal(spec["kappa"], gold[pre + "kappa"]) and np.array_equal(spec["c0"], gold[pre + "c0"])
+        assert spec["k_tilt"] == float(gold[pre + "k_tilt"]) and spec["k_smooth"] == float(gold[pre + "k_smooth"])
+        assert spec["consistent"] == bool(gold[pre + "consistent"])
+        assert LF.selection(mesh, gp, ParamResolver(gp), leaf) is spec          # cached on the version counters
+    # the options that matter are really in play on this mesh (config 4): an absent outer leaflet on the disk,
+    # a tagged rim ring without base term, assume-J0 rows on the inner leaflet
+    assert not gold[f"{state}_out_keep"].all() and gold[f"{state}_in_keep"].all()
+    assert gold[f"{state}_in_base_zero"].any()
+    # variations the golden mesh does not use: radius clipping of the assume-J0 rows, a region mode, overrides
+    gp2 = type(gp)(dict(gp, bending_tilt_assume_J0_presets_radius_max=3.0,
+                        bending_tilt_base_term_region_mode="physical_disk_split_v1",
+                        bending_tilt_base_term_region_radius=5.0))
+    pos = mesh.positions_view()
+    r = np.linalg.norm(pos[:, :2], axis=1)
+    bz_in = LS.base_zero_mask(mesh, gp2, "in", pos)
+    assert np.array_equal(bz_in, gold[f"{state}_in_base_zero"] & ~(r > 3.0 + 1e-12))
+    bz_out = LS.base_zero_mask(mesh, gp2, "out", pos)
+    assert np.array_equal(bz_out, r <= 5.0 + 1e-12)
+    with pytest.raises(ValueError):
+        LS.base_zero_mask(mesh, type(gp)({"bending_tilt_base_term_region_mode": "physical_disk_split_v1"}), "out", pos)
+    assert LS.needs_reference_helpers(type(gp)({"rim_slope_match_mode": "shared_rim_staggered_v1"}))
+
+
+def test_per_vertex_leaflet_parameter_overrides():
+    """bt_params.py:233-318: leaflet key beats the generic key; c0 falls back from the leaflet key to
+    spontaneous_curvature to intrinsic_curvature; values that are not numbers are skipped."""
+    from membrane_solver_b200.geometry.array_mesh import ArrayMesh, GlobalParams
+    from membrane_solver_b200.modules.energy import leaflet_selection as LS
+
+    pos = np.zeros((5, 3))
+    tri = np.array([[0, 1, 2], [0, 2, 3], [0, 3, 4]], np.int32)
+    vopts = {0: {"bending_modulus": 2.0, "bending_modulus_in": 7.0, "spontaneous_curvature": 0.3},
+             1: {"bending_modulus": 3.0, "intrinsic_curvature": 0.4},
+             2: {"spontaneous_curvature_out": -0.2, "spontaneous_curvature": 0.9, "bending_modulus_out": "soft"},
+             3: {"preset": "disk"}}
+    gp = GlobalParams({"bending_modulus": 1.0, "bending_modulus_out": 1.5, "spontaneous_curvature": 0.1,
+                       "spontaneous_curvature_in": 0.05})
+    mesh = ArrayMesh(pos, tri, global_params=gp, vertex_options=vopts)
+    k_in, c_in = LS.per_vertex_params(mesh, gp, "in")
+    k_out, c_out = LS.per_vertex_params(mesh, gp, "out")
+    assert k_in.tolist() == [7.0, 3.0, 1.0, 1.0, 1.0] and k_out.tolist() == [2.0, 3.0, 1.5, 1.5, 1.5]
+    assert c_in.tolist() == [0.3, 0.4, 0.9, 0.05, 0.05] and c_out.tolist() == [0.3, 0.4, -0.2, 0.1, 0.1]
+    gp_abs = GlobalParams({"leaflet_out_absent_presets": ["disk", " "], "leaflet_in_absent_presets": None})
+    assert LS.absent_vertex_mask(mesh, gp_abs, "out").tolist() == [False, False, False, True, False]
+    assert not LS.absent_vertex_mask(mesh, gp_abs, "in").any()
+    assert LS.present_triangle_mask(tri, LS.absent_vertex_mask(mesh, gp_abs, "out")).tolist() == [True, False, False]
+
+
+def test_plugins_derive_their_selections_from_mesh_options(gold, monkeypatch):
+    """End to end on the emulated device: the leaflet plugins on a mesh that carries only OPTIONS reproduce the
+    reference's energies and gradients (the selections come from leaflet_selection.py, not from given masks)."""
+    import importlib
+
+    from fake_device import FakeDeviceMesh
+
+    from membrane_solver_b200.geometry.array_mesh import ParamResolver
+    from membrane_solver_b200.runtime import device_state
+
+    monkeypatch.setattr(device_state, "DEVICE_MESH_FACTORY", FakeDeviceMesh)
+    state = "r1"
+    mesh, gp = _options_mesh(gold, state)
+    pos = gold[f"{state}_pos"]                  # evaluation positions (jittered); the options use the mesh's own
+    res = ParamResolver(gp)
+    for leaf in LEAFLETS:
+        for name, tag in ((f"bending_tilt_{leaf}", "bt"), (f"tilt_{leaf}", "tilt"), (f"tilt_smoothness_{leaf}", "smooth")):
+            mod = importlib.import_module(f"membrane_solver_b200.modules.energy.{name}")
+            g = np.zeros_like(pos)
+            tg = np.zeros_like(pos)
+            e = mod.compute_energy_and_gradient_array(mesh, gp, res, positions=pos, index_map=mesh.vertex_index_to_row,
+                                                      grad_arr=g, **{f"tilt_{leaf}_grad_arr": tg})
+            pre = f"{state}_{leaf}_"
+            _close(e, float(gold[pre + f"E_{tag}"]))
+            assert rel_err(g, gold[pre + f"g_{tag}"]) <= 4 * TOL and rel_err(tg, gold[pre + f"tg_{tag}"]) <= 4 * TOL
+
+
 def _plugin_checks(gold, state):
     import importlib
 

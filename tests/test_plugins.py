@@ -144,6 +144,14 @@ def test_plugin_modules_vs_reference_golden(backend, path):
     assert rel_err(tg, g["tg_tilt"] + g["tgonly_bending_tilt_helfrich_analytic"]) <= TOL
     _close(ev.compute_total_energy_array_with_tilts(positions=pos, tilts=g["tilts"]),
            float(g["E_tilt"]) + float(g["E_bending_tilt_helfrich_analytic"]) + float(g["E_surface"]))
+    # tilt-dependent energy only (evaluation_manager.py:303-384): surface does not take part; at another tilt field
+    # the tilt magnitude scales quadratically
+    _close(ev.compute_energy_array_with_tilts(positions=pos, tilts=g["tilts"]),
+           float(g["E_tilt"]) + float(g["E_bending_tilt_helfrich_analytic"]))
+    ev_t = EvaluationManager(mesh=mesh, global_params=gp, param_resolver=res, energy_modules=[tilt, surface],
+                             energy_module_names=["tilt", "surface"],
+                             experimental_energy_scale_fn=lambda name: 0.5 if name == "tilt" else 1.0)
+    _close(ev_t.compute_energy_array_with_tilts(positions=pos, tilts=3.0 * g["tilts"]), 0.5 * 9.0 * float(g["E_tilt"]))
 
 
 def test_bending_finite_difference_mode_is_refused(backend):
