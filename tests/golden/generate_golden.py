@@ -464,6 +464,71 @@ def leaflet_vectors():
     np.savez_compressed(os.path.join(HERE, "leaflet.npz"), **out)
 
 
+def _replay(path, lines, *, step_size=None):
+    """Drive the UNMODIFIED reference through an instruction list the way its benchmarks do
+    (benchmarks/benchmark_profile_relax_light.py:12-31): yields (instruction, context) after every instruction."""
+    from commands.context import CommandContext
+    from commands.executor import execute_command_line
+
+    mesh = parse_geometry(load_data(path))
+    stepper = GradientDescent()
+    mini = Minimizer(mesh, mesh.global_parameters, stepper, EnergyModuleManager(mesh.energy_modules),
+                     ConstraintModuleManager(mesh.constraint_modules), quiet=True)
+    mini.step_size = mesh.global_parameters.get("step_size", 1e-3) if step_size is None else step_size
+    ctx = CommandContext(mesh, mini, stepper)
+    for line in lines:
+        execute_command_line(ctx, line)
+        yield line, ctx
+
+
+def replay_vectors():
+    """the instruction lists of the reference's own benchmark inputs, replayed through the
+    unmodified reference; the dense state after EVERY instruction (positions, triangles, masks, bodies), the
+    reference's per-module energies and its total projected gradient there.  The device path re-evaluates every
+    stored state (1e-12) and the end points are the survey's known answers (1e-9)."""
+    import json
+
+    cases = (
+        ("cube", os.path.join(REF, "benchmarks", "inputs", "bench_cube.json"), None),
+        ("catenoid", os.path.join(REF, "benchmarks", "inputs", "bench_catenoid.json"), None),
+        ("bcube", os.path.join(REF, "meshes", "bending_cube.yaml"), ["r", "u", "g 50", "r", "u", "g 100", "V"]),  # macro gogo
+    )
+    out = {}
+    for name, path, lines in cases:
+        if lines is None:
+            lines = [str(x) for x in load_data(path).get("instructions", [])]
+        k = 0
+        for line, ctx in _replay(path, lines):
+            mesh, mini = ctx.mesh, ctx.minimizer
+            gp = mesh.global_parameters
+            st = _dense_state(mesh)
+            pre = f"{name}_{k:02d}_"
+            for key, v in st.items():
+                out[pre + key] = v
+            bd = mini.compute_energy_breakdown()
+            for mod, e in bd.items():
+                out[pre + f"E_{mod}"] = np.float64(e)
+            e, g = mini.compute_energy_and_gradient_array()
+            out[pre + "E"], out[pre + "g"] = np.float64(e), np.array(g)
+            out[pre + "instruction"] = np.array(line)
+            out[pre + "modules"] = np.array(list(mesh.energy_modules))
+            out[pre + "constraints"] = np.array(list(mesh.constraint_modules))
+            for body in mesh.bodies.values():
+                out[pre + "volume"] = np.float64(body.compute_volume(mesh))
+                break
+            k += 1
+        out[f"{name}_count"] = np.int64(k)
+        out[f"{name}_params_json"] = np.array(json.dumps({
+            "surface_tension": gp.get("surface_tension", 1.0), "bending_modulus": gp.get("bending_modulus", 0.0) or 0.0,
+            "spontaneous_curvature": gp.get("spontaneous_curvature", gp.get("intrinsic_curvature", 0.0)) or 0.0,
+            "bending_energy_model": str(gp.get("bending_energy_model", "helfrich")),
+            "bending_gradient_mode": str(gp.get("bending_gradient_mode", "analytic")),
+            "volume_constraint_mode": str(gp.get("volume_constraint_mode", "lagrange")),
+            "volume_stiffness": gp.get("volume_stiffness", 0.0) or 0.0}))
+        print(name, k, "states; end:", {m: float(v) for m, v in bd.items()}, "nf", len(st["tri"]), "nv", len(st["pos"]))
+    np.savez_compressed(os.path.join(HERE, "replay.npz"), **out)
+
+
 def p1_vertex_vectors():
     """geometry/tilt_operators.py:414-465 on a jittered catenoid (open mesh) with a random tilt field."""
     from geometry.tilt_operators import p1_vertex_divergence
@@ -615,6 +680,7 @@ if __name__ == "__main__":
     module_vectors()
     minimizer_vectors()
     trajectory_vectors()
+    replay_vectors()
     leaflet_vectors()
     p1_vertex_vectors()
     tilt_relaxation_vectors()

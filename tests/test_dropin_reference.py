@@ -204,3 +204,54 @@ def test_reference_minimizer_config4_trajectory_on_b200_leaflet_plugins(b200_ins
     assert np.max(np.abs(p - p_ref)) <= 1e-9
     assert np.max(np.abs(ti - ti_ref)) <= 1e-9 and np.max(np.abs(to - to_ref)) <= 1e-9
     assert e[-1] < e[0]
+
+
+# ----------------------------------------------------------------------- instruction lists
+REPLAY = [
+    ("cube", "benchmarks/inputs/bench_cube.json", None, {"surface": 4.840039760362666}),
+    ("catenoid", "benchmarks/inputs/bench_catenoid.json", None, {"surface": 34.63728489557314}),
+    ("bcube", "meshes/bending_cube.yaml", ["r", "u", "g 50", "r", "u", "g 100", "V"], {"bending": 24.75545218783622}),
+]
+
+
+@pytest.mark.parametrize("name,path,lines,end", REPLAY, ids=[r[0] for r in REPLAY])
+def test_benchmark_instruction_lists_replay_on_b200_plugins(b200_installed, name, path, lines, end):
+    """The reference's own benchmark inputs (BASELINE configs[0..2]) driven through its own command language
+    (g / r / u / V / cg: refinement, equiangulation, vertex averaging, GD and CG steppers, constraint enforcement --
+    all the reference's) with the energy modules and the volume constraint gradient on the B200 plugins: the state
+    after EVERY instruction follows the unmodified reference's (tests/golden/replay.npz) and the end point is the
+    survey's known answer, within 1e-9 (north_star)."""
+    from commands.context import CommandContext
+    from commands.executor import execute_command_line
+
+    load_data, parse_geometry, CMM, EMM, Minimizer, refine, GD = _ref_imports()
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "replay.npz"))
+    bound = b200_installed()
+    assert "modules.energy.surface" in bound
+    data = load_data(os.path.join(REF, path))
+    mesh = parse_geometry(data)
+    stepper = GD()
+    mini = Minimizer(mesh, mesh.global_parameters, stepper, EMM(mesh.energy_modules), CMM(mesh.constraint_modules),
+                     quiet=True)
+    mini.step_size = mesh.global_parameters.get("step_size", 1e-3)
+    for mod in mini.energy_modules:
+        assert mod.__name__.startswith("membrane_solver_b200."), mod.__name__
+    ctx = CommandContext(mesh, mini, stepper)
+    if lines is None:
+        lines = [str(x) for x in data.get("instructions", [])]
+    assert int(gold[f"{name}_count"]) == len(lines)
+    for k, line in enumerate(lines):
+        execute_command_line(ctx, line)
+        m = ctx.mesh
+        pre = f"{name}_{k:02d}_"
+        assert str(gold[pre + "instruction"]) == line
+        pos = np.array(m.positions_view())
+        assert pos.shape == gold[pre + "pos"].shape, (line, pos.shape)
+        assert np.max(np.abs(pos - gold[pre + "pos"])) <= 1e-9, (k, line)
+        bd = ctx.minimizer.compute_energy_breakdown()
+        for mod, e in bd.items():
+            want = float(gold[pre + f"E_{mod}"])
+            assert abs(e - want) <= 1e-9 * max(1.0, abs(want)), (k, line, mod, e, want)
+    bd = ctx.minimizer.compute_energy_breakdown()
+    for mod, want in end.items():
+        assert abs(bd[mod] - want) <= 1e-9 * abs(want), (mod, bd[mod], want)

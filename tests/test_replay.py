@@ -1,0 +1,93 @@
+"""SURVEY.md appendix B / BASELINE configs[0..2]: the reference's benchmark instruction lists.
+
+``tests/golden/replay.npz`` (``generate_golden.py replay_vectors``) holds the dense state after EVERY instruction of
+``benchmarks/inputs/bench_cube.json``, ``bench_catenoid.json`` and the ``gogo`` macro of ``meshes/bending_cube.yaml``
+as the UNMODIFIED reference produced them, with its per-module energies and its total projected gradient.  Here every
+stored state is re-evaluated through the plugin layer (``EnergyModuleManager`` / ``EvaluationManager`` twins) -- on
+the host emulator in the CPU tier, on the device through the C ABI in the GPU tier -- at 1e-12, and the end points
+must be the survey's known answers.  The replay of the instruction lists THROUGH the plugins (reference command
+language, refinement, equiangulation, steppers) is ``test_dropin_reference.py`` (build container only)."""
+
+import json
+
+import numpy as np
+import pytest
+
+import ms_test_helpers as H
+from ms_test_helpers import rel_err
+
+from membrane_solver_b200 import _lib as L
+from membrane_solver_b200.geometry.array_mesh import ArrayBody, ArrayMesh, GlobalParams, ParamResolver
+from membrane_solver_b200.runtime import device_state
+from membrane_solver_b200.runtime.energy_manager import EnergyModuleManager
+from membrane_solver_b200.runtime.evaluation_manager import EvaluationManager
+
+END_POINTS = {"cube": ("surface", 4.840039760362666, 0.9999999999999997),
+              "catenoid": ("surface", 34.63728489557314, None),
+              "bcube": ("bending", 24.75545218783622, 1.0000000000000002)}
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(H.GOLDEN + "/replay.npz")
+
+
+@pytest.fixture(params=[pytest.param("emulator", id="emulator"),
+                        pytest.param("gpu", id="gpu", marks=pytest.mark.gpu)])
+def backend(request, monkeypatch):
+    if request.param == "emulator":
+        from fake_device import FakeDeviceMesh
+
+        monkeypatch.setattr(device_state, "DEVICE_MESH_FACTORY", FakeDeviceMesh)
+    elif L.device_count() < 1:
+        pytest.fail("no CUDA device visible: the gpu tier must run on the B200 box")
+    return request.param
+
+
+def _state(gold, name, k):
+    pre = f"{name}_{k:02d}_"
+    prm = json.loads(str(gold[f"{name}_params_json"]))
+    gp = GlobalParams(**prm)
+    bodies = {}
+    if pre + "body_rows_0" in gold.files:
+        t = float(gold[pre + "body_target_0"])
+        bodies[0] = ArrayBody(gold[pre + "body_rows_0"], target_volume=None if np.isnan(t) else t)
+    mesh = ArrayMesh(gold[pre + "pos"], gold[pre + "tri"], global_params=gp,
+                     facet_params={"surface_tension": gold[pre + "gamma"]}, bodies=bodies, fixed=gold[pre + "fixed"])
+    names = [str(x) for x in gold[pre + "modules"]]
+    mgr = EnergyModuleManager(names)
+    ev = EvaluationManager(mesh=mesh, global_params=gp, param_resolver=ParamResolver(gp),
+                           energy_modules=[mgr.get_module(n) for n in names], energy_module_names=names)
+    return pre, mesh, ev, names, [str(x) for x in gold[pre + "constraints"]]
+
+
+@pytest.mark.parametrize("name", ["cube", "catenoid", "bcube"])
+def test_every_replayed_state_re_evaluates_like_the_reference(backend, gold, name):
+    n = int(gold[f"{name}_count"])
+    assert n >= 7
+    for k in range(n):
+        pre, mesh, ev, names, cons = _state(gold, name, k)
+        pos = mesh.positions_view()
+        assert set(mesh.boundary_vertex_ids) == set(np.nonzero(gold[pre + "is_boundary"])[0].tolist())
+        if "volume" in cons:   # single volume constraint: KKT projection + fixed mask on the device
+            e, g, res = ev.compute_energy_and_projected_gradient(positions=pos)
+            assert abs(res.volume - float(gold[pre + "volume"])) <= 1e-12 * abs(float(gold[pre + "volume"]))
+        else:                  # catenoid: the pinned rims are fixed rows; no multiplier
+            e, g = ev.compute_energy_and_gradient_array(positions=pos)
+            g[np.asarray(gold[pre + "fixed"], bool)] = 0.0
+        want_e, want_g = float(gold[pre + "E"]), gold[pre + "g"]
+        assert abs(e - want_e) <= 1e-12 * max(1.0, abs(want_e)), (k, str(gold[pre + "instruction"]))
+        tol = 2e-12 if "bending" in names else 1e-12
+        assert rel_err(g, want_g) <= tol, (k, str(gold[pre + "instruction"]), rel_err(g, want_g))
+        bd = ev.compute_energy_breakdown(positions=pos)
+        for mod in names:
+            want = float(gold[pre + f"E_{mod}"])
+            assert abs(bd[mod] - want) <= 1e-12 * max(1.0, abs(want)), (k, mod)
+    # the end point is the survey's known answer (appendix B)
+    mod, e_end, v_end = END_POINTS[name]
+    pre, mesh, ev, names, cons = _state(gold, name, n - 1)
+    bd = ev.compute_energy_breakdown(positions=mesh.positions_view())
+    assert abs(bd[mod] - e_end) <= 1e-9 * abs(e_end), (bd[mod], e_end)
+    if v_end is not None:
+        _, _, res = ev.compute_energy_and_projected_gradient(positions=mesh.positions_view())
+        assert abs(res.volume - v_end) <= 1e-12
