@@ -526,6 +526,43 @@ def replay_vectors():
             "volume_constraint_mode": str(gp.get("volume_constraint_mode", "lagrange")),
             "volume_stiffness": gp.get("volume_stiffness", 0.0) or 0.0}))
         print(name, k, "states; end:", {m: float(v) for m, v in bd.items()}, "nf", len(st["tri"]), "nv", len(st["pos"]))
+    # BASELINE configs[3]: the caveolin free-disk mesh after its macro profile_relax_light:
+    # end state (positions, both tilt fields, the mesh options the leaflet selections derive from) and the
+    # reference's module energies there
+    import json as _json
+
+    path = os.path.join(REF, "meshes", "caveolin",
+                        "kozlov_1disk_3d_tensionless_single_leaflet_profile_hard_rim_R12_free_disk.yaml")
+    for line, ctx in _replay(path, ["profile_relax_light"]):
+        mesh, mini = ctx.mesh, ctx.minimizer
+    gp = mesh.global_parameters
+    st = _dense_state(mesh)
+    out["caveolin_pos"], out["caveolin_tri"], out["caveolin_is_boundary"] = st["pos"], st["tri"], st["is_boundary"]
+    out["caveolin_tilts_in"] = np.array(mesh.tilts_in_view())
+    out["caveolin_tilts_out"] = np.array(mesh.tilts_out_view())
+    opt_keys = ("preset", "rim_slope_match_group", "tilt_thetaB_group", "tilt_thetaB_group_in", "tilt_thetaB_group_out",
+                "bending_modulus", "bending_modulus_in", "bending_modulus_out", "spontaneous_curvature",
+                "spontaneous_curvature_in", "spontaneous_curvature_out", "intrinsic_curvature")
+    vopts = {}
+    for row, vid in enumerate(mesh.vertex_ids):
+        o = getattr(mesh.vertices[int(vid)], "options", None) or {}
+        keep_o = {k: o[k] for k in opt_keys if k in o and o[k] is not None}
+        if keep_o:
+            vopts[int(row)] = keep_o
+    gp_dump = {}
+    for k in gp.to_dict():
+        v = gp.get(k)
+        try:
+            _json.dumps(v)
+        except TypeError:
+            continue
+        gp_dump[k] = v
+    out["caveolin_vertex_options_json"] = np.array(_json.dumps(vopts))
+    out["caveolin_global_params_json"] = np.array(_json.dumps(gp_dump))
+    bd = mini.compute_energy_breakdown()
+    for mod, e in bd.items():
+        out[f"caveolin_E_{mod}"] = np.float64(e)
+    print("caveolin", len(st["pos"]), len(st["tri"]), {m: float(v) for m, v in bd.items()})
     np.savez_compressed(os.path.join(HERE, "replay.npz"), **out)
 
 

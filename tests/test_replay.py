@@ -91,3 +91,36 @@ def test_every_replayed_state_re_evaluates_like_the_reference(backend, gold, nam
     if v_end is not None:
         _, _, res = ev.compute_energy_and_projected_gradient(positions=mesh.positions_view())
         assert abs(res.volume - v_end) <= 1e-12
+
+
+CAVEOLIN_END = {"bending_tilt_in": 0.24157305138432794, "bending_tilt_out": 0.008943176191835553,
+                "tilt_in": 0.45430920811328745, "tilt_out": 0.0006887388044462964}
+
+
+def test_caveolin_end_state_module_energies(backend, gold):
+    """BASELINE configs[3]: the state the reference reaches with its macro ``profile_relax_light`` on the caveolin
+    free-disk mesh (1 129 vertices / 2 208 facets).  The four leaflet modules of the path, fed with the mesh OPTIONS
+    (selections derived by leaflet_selection.py), give the reference's energies -- the survey's known answers; the
+    fifth module of that mesh (tilt_thetaB_contact_in) is not on the path."""
+    import importlib
+
+    vopts = {int(k): v for k, v in json.loads(str(gold["caveolin_vertex_options_json"])).items()}
+    gp = GlobalParams(json.loads(str(gold["caveolin_global_params_json"])))
+    mesh = ArrayMesh(gold["caveolin_pos"], gold["caveolin_tri"], global_params=gp, vertex_options=vopts,
+                     tilts_in=gold["caveolin_tilts_in"], tilts_out=gold["caveolin_tilts_out"])
+    assert gold["caveolin_tri"].shape == (2208, 3) and gold["caveolin_pos"].shape == (1129, 3)
+    res = ParamResolver(gp)
+    pos = mesh.positions_view()
+    for name, want in CAVEOLIN_END.items():
+        mod = importlib.import_module(f"membrane_solver_b200.modules.energy.{name}")
+        e = mod.compute_energy_array(mesh, gp, res, positions=pos, index_map=mesh.vertex_index_to_row)
+        assert abs(e - float(gold[f"caveolin_E_{name}"])) <= 1e-12 * max(1.0, abs(want)), (name, e)
+        assert abs(e - want) <= 1e-9 * abs(want), (name, e, want)
+    # the manager's leaflet entry point sums them in one paired device evaluation
+    names = list(CAVEOLIN_END)
+    mgr = EnergyModuleManager(names)
+    ev = EvaluationManager(mesh=mesh, global_params=gp, param_resolver=res,
+                           energy_modules=[mgr.get_module(n) for n in names], energy_module_names=names)
+    total = ev.compute_tilt_dependent_energy_with_leaflet_tilts(positions=pos, tilts_in=mesh.tilts_in_view(),
+                                                                tilts_out=mesh.tilts_out_view())
+    assert abs(total - sum(CAVEOLIN_END.values())) <= 1e-9 * sum(CAVEOLIN_END.values())
