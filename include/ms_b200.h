@@ -320,6 +320,10 @@ MS_API int ms_ctx_eval_finish(ms_ctx* ctx, const ms_eval_opts* opts);
  * ms_ctx_eval_async).  Multi-GPU: all-reduce MS_ARR_SCALARS[0..11] between. */
 MS_API int ms_ctx_eval_reduce(ms_ctx* ctx, const ms_eval_opts* opts);
 MS_API int ms_ctx_eval_project(ms_ctx* ctx, const ms_eval_opts* opts);
+/* Self-check builds only (libms_b200_checked.so, -DMS_SELF_CHECK): violation counters of the patch kernels'
+ * hand-over protocol since the context was created -- [0] an accumulator row taken by two lanes at once, [1] a
+ * patch-local index out of range, [2] a row still locked when the epilogue reads it.  Other builds return -10. */
+MS_API int ms_ctx_self_check(ms_ctx* ctx, int32_t* counters3);
 /* synchronise and copy the 16 scalars to the host */
 MS_API int ms_ctx_read_scalars(ms_ctx* ctx, double* scalars16);
 /* ms_ctx_eval_async + ms_ctx_read_scalars */

@@ -129,6 +129,7 @@ SIGNATURES = {
     "ms_ctx_array_len": (_i64, [_V, ctypes.c_int]),
     "ms_ctx_set_stream": (ctypes.c_int, [_V, _V]),
     "ms_ctx_eval_async": (ctypes.c_int, [_V, ctypes.POINTER(EvalOpts)]),
+    "ms_ctx_self_check": (ctypes.c_int, [_V, ctypes.POINTER(ctypes.c_int32)]),
     "ms_ctx_eval_stage": (ctypes.c_int, [_V, ctypes.POINTER(EvalOpts), _i32]),
     "ms_ctx_eval_pass_a": (ctypes.c_int, [_V, ctypes.POINTER(EvalOpts)]),
     "ms_ctx_eval_pass_b": (ctypes.c_int, [_V, ctypes.POINTER(EvalOpts)]),

@@ -347,6 +347,12 @@ class DeviceMesh:
     def eval_async(self, opts: L.EvalOpts) -> None:
         L.check(self._lib.ms_ctx_eval_async(self._h, ctypes.byref(opts)))
 
+    def self_check(self) -> tuple[int, int, int]:
+        """Violation counters of a self-check build (libms_b200_checked.so); raises on other builds."""
+        out = (ctypes.c_int32 * 3)()
+        L.check(self._lib.ms_ctx_self_check(self._h, out))
+        return int(out[0]), int(out[1]), int(out[2])
+
     def eval_stage(self, opts: L.EvalOpts, stage: int) -> None:
         """Stage 0 = pass A, stage 1 = pass B + fused finalisation (ms_ctx_eval_async in two calls)."""
         L.check(self._lib.ms_ctx_eval_stage(self._h, ctypes.byref(opts), int(stage)))

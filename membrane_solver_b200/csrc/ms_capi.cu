@@ -2,6 +2,7 @@
 // the stateless per-kernel shims.  Replaces the dispatch of
 // fortran_kernels/loader.py for the energy+gradient path.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
 #include <cmath>
@@ -58,6 +59,12 @@ struct DevBuf {
 
 bool g_configured[64] = {false};
 
+// NVTX range around the launches of one phase (visible in Nsight Systems / ncu --nvtx; a no-op without a tool)
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+
 }  // namespace
 
 struct ms_ctx {
@@ -92,6 +99,7 @@ struct ms_ctx {
     bool active = false, use_gc = false, use_fixed = false;
   } proj;
   DevBuf<unsigned int> d_ticket;  // last-CTA ticket of the fused finalisation
+  DevBuf<int> d_self_check;       // violation counters of the self-check build (ms_ctx_self_check)
   bool has_gamma = false, has_kappa = false, has_c0 = false, has_boundary = false,
        has_fixed = false, has_body = false;
   double gamma_u = 1.0, kappa_u = 0.0, c0_u = 0.0, k_tilt = 0.0;
@@ -284,6 +292,7 @@ int fill_launch(ms_ctx* c, const ms_eval_opts* o, ms::PatchLaunch& a) {
   a.partials = nullptr;  // set by the pass entry points
   a.grad = c->d_grad.p;
   a.volgrad = c->d_volgrad.p;
+  a.self_check = c->d_self_check.p;
   if ((o->modules & MS_MOD_TILT)) {
     if (!c->d_tilts.p) return fail(-5, "tilt module requested but no tilts were uploaded");
     // |t|^2 per vertex for the producer's asynchronous staging (the tilts may have been changed through
@@ -480,6 +489,10 @@ int ms_ctx_create(int device, ms_ctx** out) {
   if (int rc = c->d_scalars.ensure(MS_SC_COUNT)) return rc;
   CU(cudaMemset(c->d_scalars.p, 0, MS_SC_COUNT * sizeof(double)));
   if (int rc = c->d_dot_partials.ensure(3 * kDotBlocks)) return rc;
+#ifdef MS_SELF_CHECK
+  if (int rc = c->d_self_check.ensure(4)) return rc;
+  CU(cudaMemset(c->d_self_check.p, 0, 4 * sizeof(int)));
+#endif
   *out = c.release();
   return 0;
 }
@@ -555,6 +568,7 @@ int ms_ctx_set_topology(ms_ctx* c, int32_t nv, int32_t nf, const int32_t* tri,
 int ms_ctx_set_topology_partition(ms_ctx* c, int32_t nv, int32_t n_owned, int32_t nf,
                                   const int32_t* tri, const uint8_t* is_boundary,
                                   const uint8_t* body_mask, const uint8_t* fixed_mask) {
+  NvtxRange range("ms_b200 set_topology (pack + upload)");
   if (int rc = check_ctx(c, false)) return rc;
   if (nv < 0 || nf < 0 || (nf > 0 && !tri) || n_owned < 0 || n_owned > nv)
     return fail(-1, "bad topology arguments");
@@ -648,6 +662,16 @@ int ms_ctx_set_topology_partition(ms_ctx* c, int32_t nv, int32_t n_owned, int32_
   }
   if (!pk.halo_ids.empty())
     CU(cudaMemcpy(c->d_halo.p, pk.halo_ids.data(), pk.halo_ids.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+#ifdef MS_SELF_CHECK
+  if (std::getenv("MS_SELF_CHECK_INJECT")) {
+    // negative control of the self-check: slot 1 of every patch's first round repeats slot 0, so two lanes of one
+    // warp read-modify-write the same owned rows at once -- the row locks must report it
+    ms::PackedMesh& bad = c->packed;
+    for (const ms::PatchHeader& h : bad.patches)
+      if (h.n_rounds > 0 && (bad.recs[size_t(h.slot_off)].flags & ms::REC_VALID))
+        bad.recs[size_t(h.slot_off) + 1] = bad.recs[size_t(h.slot_off)];
+  }
+#endif
   if (!pk.recs.empty())
     CU(cudaMemcpy(c->d_recs.p, pk.recs.data(), pk.recs.size() * sizeof(ms::FacetRec), cudaMemcpyHostToDevice));
 
@@ -922,6 +946,7 @@ static int attach_finalize(ms_ctx* c, const ms_eval_opts* o, ms::PatchLaunch& a)
 }
 
 static int eval_pass_a_impl(ms_ctx* c, const ms_eval_opts* o, bool finalize) {
+  NvtxRange range("ms_b200 pass A");
   if (int rc = check_ctx(c, true)) return rc;
   if (!o) return fail(-1, "null options");
   ms::PatchLaunch a;
@@ -944,6 +969,7 @@ static int eval_pass_a_impl(ms_ctx* c, const ms_eval_opts* o, bool finalize) {
 }
 
 static int eval_pass_b_impl(ms_ctx* c, const ms_eval_opts* o, bool finalize) {
+  NvtxRange range("ms_b200 pass B");
   if (int rc = check_ctx(c, true)) return rc;
   if (!o) return fail(-1, "null options");
   // a tilt-only evaluation (want_grad == 0, want_tilt_grad == 1) still needs pass B for the tilt
@@ -991,6 +1017,7 @@ static int reduce_rows(ms_ctx* c, const ms_eval_opts* o, int rows_a, int rows_b)
 }
 
 int ms_ctx_eval_reduce(ms_ctx* c, const ms_eval_opts* o) {
+  NvtxRange range("ms_b200 reduce");
   if (int rc = check_ctx(c, true)) return rc;
   if (!o) return fail(-1, "null options");
   ms::PatchLaunch a;
@@ -1007,6 +1034,7 @@ int ms_ctx_eval_reduce(ms_ctx* c, const ms_eval_opts* o) {
 }
 
 int ms_ctx_eval_project(ms_ctx* c, const ms_eval_opts* o) {
+  NvtxRange range("ms_b200 kkt coefficient");
   if (int rc = check_ctx(c, true)) return rc;
   if (!o) return fail(-1, "null options");
   if (!o->want_grad) return 0;  // energy-only evaluation: a pending projection (and its coefficient) stays as it is
@@ -1052,6 +1080,23 @@ int ms_ctx_eval_stage(ms_ctx* c, const ms_eval_opts* o, int32_t stage) {
     c->proj.use_fixed = use_fixed;
   }
   return 0;
+}
+
+int ms_ctx_self_check(ms_ctx* c, int32_t* counters3) {
+  if (int rc = check_ctx(c, false)) return rc;
+  if (!counters3) return fail(-1, "null argument");
+#ifdef MS_SELF_CHECK
+  if (!c->d_self_check.p) {
+    if (int rc = c->d_self_check.ensure(4)) return rc;
+    CU(cudaMemset(c->d_self_check.p, 0, 4 * sizeof(int)));
+  }
+  CU(cudaMemcpyAsync(counters3, c->d_self_check.p, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+#else
+  counters3[0] = counters3[1] = counters3[2] = -1;
+  return fail(-10, "this library was built without MS_SELF_CHECK (build membrane_solver_b200/libms_b200_checked.so)");
+#endif
 }
 
 int ms_ctx_read_scalars(ms_ctx* c, double* scalars16) {
@@ -1511,6 +1556,7 @@ int ms_ctx_halo_prepare(ms_ctx* c) {
 }
 
 int ms_ctx_halo_signal(ms_ctx* c, int32_t flag_index) {
+  NvtxRange range("ms_b200 halo signal");
   if (int rc = check_ctx(c, true)) return rc;
   if (flag_index != MS_FLAG_POSITIONS && flag_index != MS_FLAG_SEEDS)  // words 2 / 3 belong to the all-reduce and the warm-up
     return fail(-1, "flag index must be MS_FLAG_POSITIONS or MS_FLAG_SEEDS");
@@ -1520,6 +1566,7 @@ int ms_ctx_halo_signal(ms_ctx* c, int32_t flag_index) {
 }
 
 int ms_ctx_halo_pull(ms_ctx* c, int32_t which, int32_t flag_index) {
+  NvtxRange range("ms_b200 halo pull");
   if (int rc = check_ctx(c, true)) return rc;
   if (flag_index != MS_FLAG_POSITIONS && flag_index != MS_FLAG_SEEDS)  // words 2 / 3 belong to the all-reduce and the warm-up
     return fail(-1, "flag index must be MS_FLAG_POSITIONS or MS_FLAG_SEEDS");
@@ -1568,6 +1615,7 @@ int ms_ctx_set_rank_slot(ms_ctx* c, int32_t slot, int32_t n_slots) {
 }
 
 int ms_ctx_allreduce_scalars(ms_ctx* c, int32_t count) {
+  NvtxRange range("ms_b200 all-reduce (peer memory)");
   if (int rc = check_ctx(c, true)) return rc;
   if (count <= 0 || count > 16) return fail(-1, "between 1 and 16 scalars");
   if (int rc = ensure_flag_words(c)) return rc;
@@ -1746,6 +1794,7 @@ static int eval_pipelined(ms_ctx* c, const ms_eval_opts* o, const double* pos_ho
 
 int ms_ctx_eval_host(ms_ctx* c, const ms_eval_opts* o, const double* pos_host, double* scalars16,
                      double* grad_host, double* volgrad_host, double* tilt_grad_host) {
+  NvtxRange range("ms_b200 eval_host (H2D, evaluation, D2H)");
   if (int rc = check_ctx(c, true)) return rc;
   if (!o || !scalars16) return fail(-1, "null argument");
   const int64_t n3 = 3 * int64_t(c->nv);

@@ -193,6 +193,32 @@ __device__ __forceinline__ FacetRec load_rec(const FacetRec* p) {
 // ---------------------------------------------------------------------------
 constexpr uint32_t kFastModules = MS_MOD_SURFACE | MS_MOD_BENDING | MS_MOD_VOLUME;
 
+// ---- self-check build (-DMS_SELF_CHECK; libms_b200_checked.so): compute-sanitizer is closed on the GPU pool, so the
+// hand-over protocol checks itself.  Every read-modify-write of an owned accumulator row takes a per-row lock word
+// with atomicCAS and releases it afterwards: the packer promises that no two facets of a round write the same owned
+// row, and the token ring that no two groups accumulate at the same time, so the CAS can never fail; the epilogue
+// must find every lock free.  Local indices are bounds-checked.  Violations are counted in PatchLaunch::self_check
+// (0: rows locked twice, 1: index out of range, 2: lock held at the epilogue).
+#ifdef MS_SELF_CHECK
+__shared__ int s_row_lock[2][kPatchOwnedCap + 16];
+__device__ __forceinline__ void self_check_fail(const PatchLaunch& a, int which) {
+  if (a.self_check) atomicAdd(a.self_check + which, 1);
+}
+__device__ __forceinline__ void self_check_lock(const PatchLaunch& a, int b, FacetRec rec, int n_owned, int n_local, bool lock) {
+  const int idx[3] = {rec.a, rec.b, rec.c};
+  for (int k = 0; k < 3; ++k) {
+    if (idx[k] >= n_local) self_check_fail(a, 1);
+    if (idx[k] >= n_owned) continue;
+    if (lock) {
+      if (atomicCAS(&s_row_lock[b][idx[k]], 0, 1) != 0) self_check_fail(a, 0);
+    } else {
+      __threadfence_block();
+      atomicExch(&s_row_lock[b][idx[k]], 0);
+    }
+  }
+}
+#endif
+
 // KKT coefficient of the single volume constraint (runtime/constraint_manager.py:294-301) or of the volume
 // penalty (geometry/body.py:223-238): projected gradient = g + coef * gC.
 __device__ __forceinline__ void kkt_coefficient(double* scalars, int mode, int has_gc, double k_vol, double v_target) {
@@ -294,6 +320,9 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
     for (int j = tid; j < 2 * P::kAccRows * kACap; j += NC + 64) acc0[j] = 0.0;
     if (ab_base)
       for (int j = tid; j < 2 * kACap; j += NC + 64) ab_base[j] = 0.0;
+#ifdef MS_SELF_CHECK
+    for (int j = tid; j < 2 * (kPatchOwnedCap + 16); j += NC + 64) (&s_row_lock[0][0])[j] = 0;
+#endif
   }
   __syncthreads();
 
@@ -401,6 +430,9 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
       double* accAb = ab_base ? ab_base + size_t(b) * kACap : nullptr;
       for (int i = lane; i < Pn; i += epi_threads) {
         const size_t row = size_t(hs.v_lo) + i;
+#ifdef MS_SELF_CHECK
+        if (s_row_lock[b][i] != 0) self_check_fail(a, 2);
+#endif
         if (PASS == 0) {
           const double kap = (!FAST && a.kappa) ? a.kappa[row] : a.kappa_u;
           const double c0 = (!FAST && a.c0) ? a.c0[row] : a.c0_u;
@@ -505,7 +537,13 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
             ca = facet_compute_a(ST, rec, gam, la, modules, a.k_tilt, sums);
           }
           if (use_ring) named_sync(bar_mine, ring); else named_sync(1, T);
+#ifdef MS_SELF_CHECK
+          if (valid && do_bending) self_check_lock(a, b, rec, Pn, Pn + hs.n_halo, true);
+#endif
           if (valid && do_bending) facet_accumulate_a(ST, rec, ca, la, modules);
+#ifdef MS_SELF_CHECK
+          if (valid && do_bending) self_check_lock(a, b, rec, Pn, Pn + hs.n_halo, false);
+#endif
         } else {
           FacetOutB out;
           if (valid) {
@@ -514,7 +552,13 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
                              : facet_compute_b<false>(ST, rec, gam, lb, modules, flags, a.k_tilt, scalars_here, sums);
           }
           if (use_ring) named_sync(bar_mine, ring); else named_sync(1, T);
+#ifdef MS_SELF_CHECK
+          if (valid) self_check_lock(a, b, rec, Pn, Pn + hs.n_halo, true);
+#endif
           if (valid) facet_accumulate_b(ST, rec, out, lb, do_volume, do_tilt);
+#ifdef MS_SELF_CHECK
+          if (valid) self_check_lock(a, b, rec, Pn, Pn + hs.n_halo, false);
+#endif
         }
         // the last round of the patch hands the accumulator (and the header) to the epilogue warps
         if (want_epi && t_rel == n_turns - 1) {

@@ -94,6 +94,7 @@ struct PatchLaunch {
   double* a_eff;      // nv
   double* e_vertex;   // nv   per-vertex bending energy (bending.compute_energy_array)
   PatchFinalize fin;
+  int* self_check;    // -DMS_SELF_CHECK builds: three violation counters (device), else unused
 };
 
 size_t pass_a_smem_bytes(const PatchLaunch& a);
