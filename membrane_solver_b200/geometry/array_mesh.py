@@ -169,3 +169,14 @@ class ArrayMesh:
         self._boundary = None
         self._facet_loops_version += 1
         self._topology_version += 1
+
+    def equiangulate(self, max_iterations: int = 100) -> int:
+        """The ``u`` command on arrays (``runtime/equiangulation.py:11-148``): Delaunay edge flips in place; facets
+        keep their rows, edges between fixed vertices stay.  Returns the number of flips; a topology version bump
+        (the device re-packs on the next evaluation) only when something flipped."""
+        from .equiangulate import equiangulate_triangles
+
+        tri, flips = equiangulate_triangles(self._positions, self._tri, self._fixed, max_iterations=max_iterations)
+        if flips:
+            self.set_triangles(tri)
+        return flips

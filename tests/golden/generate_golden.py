@@ -566,6 +566,38 @@ def replay_vectors():
     np.savez_compressed(os.path.join(HERE, "replay.npz"), **out)
 
 
+def equiangulate_vectors():
+    """runtime/equiangulation.py on the jittered r2 catenoid (the case where the reference's traversal makes
+    consistent flips): input, the reference's output, and the flip criterion's violation counts (should_flip_edge
+    applied to every interior edge) before / after."""
+    from runtime.equiangulation import equiangulate_mesh, should_flip_edge
+
+    mesh = _refined(os.path.join(REF, "meshes", "catenoid.json"), 2)
+    rng = np.random.default_rng(3)
+    for v in mesh.vertices.values():
+        if not getattr(v, "fixed", False):
+            v.position = np.asarray(v.position, dtype=float) + 0.06 * rng.normal(size=3)
+    mesh.increment_version()
+
+    def violations(m):
+        m.build_connectivity_maps()
+        n = 0
+        for ei, edge in m.edges.items():
+            fs = m.get_facets_of_edge(ei)
+            if len(fs) == 2 and should_flip_edge(m, edge, fs[0], fs[1]):
+                n += 1
+        return n
+
+    st = _dense_state(mesh)
+    before = violations(mesh)
+    out = equiangulate_mesh(mesh)
+    st2 = _dense_state(out)
+    assert np.array_equal(st["pos"], st2["pos"])
+    np.savez_compressed(os.path.join(HERE, "equiangulate.npz"), pos=st["pos"], tri=st["tri"], fixed=st["fixed"],
+                        tri_ref=st2["tri"], violations_before=np.int64(before), violations_ref=np.int64(violations(out)))
+    print("equiangulate", len(st["tri"]), before, violations(out))
+
+
 def p1_vertex_vectors():
     """geometry/tilt_operators.py:414-465 on a jittered catenoid (open mesh) with a random tilt field."""
     from geometry.tilt_operators import p1_vertex_divergence
@@ -710,6 +742,12 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "vertexaverage":
         vertex_average_vectors()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "equiangulate":
+        equiangulate_vectors()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "replay":
+        replay_vectors()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "p1vertex":
         p1_vertex_vectors()
         sys.exit(0)
@@ -722,3 +760,4 @@ if __name__ == "__main__":
     p1_vertex_vectors()
     tilt_relaxation_vectors()
     vertex_average_vectors()
+    equiangulate_vectors()
