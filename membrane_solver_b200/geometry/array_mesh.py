@@ -56,6 +56,10 @@ class GlobalParams(dict):
         except KeyError as exc:
             raise AttributeError(name) from exc
 
+    def set(self, name, value):
+        """``GlobalParameters.set`` (``parameters/global_parameters.py``)."""
+        self[name] = value
+
 
 class ParamResolver:
     """``ParameterResolver.get(entity, name)``: entity options first, then the global value."""

@@ -41,10 +41,15 @@ class EnergyModuleManager:
         return self.modules[mod]
 
 
-def install() -> list[str]:
+def install(enforce: bool = False) -> list[str]:
     """Register the B200 twins under the reference's module names, so that an unmodified
     ``runtime.energy_manager.EnergyModuleManager`` (``importlib.import_module(f"modules.energy.{name}")``,
-    ``energy_manager.py:21``) and ``runtime.constraint_manager`` load them.  Returns the names bound."""
+    ``energy_manager.py:21``) and ``runtime.constraint_manager`` load them.  ``enforce``: also replace the hard volume
+    projection ``modules.constraints.volume.enforce_constraint`` by its array twin.  Off by default: the twin always
+    uses the CURRENT ``dV/dx``, whereas the reference's projection can start from a stale cached gradient
+    (``Body.compute_volume`` refreshes the cached version but not the cached gradient dict, ``geometry/body.py:70-148``
+    vs ``:401-410``), so trajectories of the reference that went through that quirk are only reproduced with the
+    reference's own function.  Returns the names bound."""
     import sys
 
     bound = []
@@ -58,8 +63,10 @@ def install() -> list[str]:
     cmod = importlib.import_module("membrane_solver_b200.modules.constraints.volume")
     ref = sys.modules.get("modules.constraints.volume")
     if ref is not None:
-        # keep the reference's enforce_constraint (next-row item); replace the gradient providers
         ref.constraint_gradients_array = cmod.constraint_gradients_array
         ref.constraint_gradients = cmod.constraint_gradients
         bound.append("modules.constraints.volume.constraint_gradients[_array]")
+        if enforce:
+            ref.enforce_constraint = cmod.enforce_constraint
+            bound.append("modules.constraints.volume.enforce_constraint")
     return bound

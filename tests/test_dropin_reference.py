@@ -60,7 +60,7 @@ def b200_installed(monkeypatch):
     saved = {k: sys.modules.get(k) for k in list(sys.modules) if k.startswith("modules.energy.")}
     import modules.constraints.volume as ref_cv
 
-    saved_cv = (ref_cv.constraint_gradients_array, ref_cv.constraint_gradients)
+    saved_cv = (ref_cv.constraint_gradients_array, ref_cv.constraint_gradients, ref_cv.enforce_constraint)
     monkeypatch.setattr(device_state, "DEVICE_MESH_FACTORY", FakeDeviceMesh)
     yield energy_manager.install
     for name in energy_manager.NAMES:
@@ -73,7 +73,7 @@ def b200_installed(monkeypatch):
         import modules.energy as pkg
 
         setattr(pkg, name, sys.modules[key])
-    ref_cv.constraint_gradients_array, ref_cv.constraint_gradients = saved_cv
+    ref_cv.constraint_gradients_array, ref_cv.constraint_gradients, ref_cv.enforce_constraint = saved_cv
 
 
 @pytest.mark.parametrize("path,levels,steps", CASES, ids=[c[0].split("/")[-1] for c in CASES])
@@ -255,3 +255,39 @@ def test_benchmark_instruction_lists_replay_on_b200_plugins(b200_installed, name
     bd = ctx.minimizer.compute_energy_breakdown()
     for mod, want in end.items():
         assert abs(bd[mod] - want) <= 1e-9 * abs(want), (mod, bd[mod], want)
+
+
+def test_enforce_constraint_twin_matches_the_reference_from_a_fresh_state(b200_installed):
+    """modules/constraints/volume.py:69-149 on arrays: from a freshly built mesh (no
+    cached volume gradient in the reference) the hard projection lands on the same positions, for the default
+    3 iterations and for the 12 of the mesh_operation context, with fixed vertices left alone."""
+    import modules.constraints.volume as ref_cv
+
+    ref_enforce = ref_cv.enforce_constraint
+    from membrane_solver_b200.modules.constraints import volume as twin
+
+    for kwargs in ({}, {"context": "mesh_operation"}, {"force_projection": True, "max_iter": 5}):
+        meshes = []
+        for _ in range(2):
+            mesh, _ = _build("meshes/cube.json", 2, seed=9)
+            for k, v in enumerate(mesh.vertices.values()):
+                v.position = 1.07 * np.asarray(v.position, dtype=float)      # 22 % too much volume
+                if k % 17 == 0:
+                    v.fixed = True
+            mesh.global_parameters.set("volume_constraint_mode", "lagrange")   # cube.json itself is penalty mode
+            mesh.increment_version()
+            if hasattr(mesh, "_touch_fixed_flags"):
+                mesh._touch_fixed_flags()
+            meshes.append(mesh)
+        gp = meshes[0].global_parameters
+        ref_enforce(meshes[0], global_params=gp, **kwargs)
+        b200_installed()
+        twin.enforce_constraint(meshes[1], global_params=meshes[1].global_parameters, **kwargs)
+        p_ref, p = np.array(meshes[0].positions_view()), np.array(meshes[1].positions_view())
+        assert np.max(np.abs(p - p_ref)) <= 1e-12, kwargs
+        body = next(iter(meshes[1].bodies.values()))
+        if kwargs.get("context") == "mesh_operation":
+            assert abs(body.compute_volume(meshes[1]) - 1.0) <= 1e-10
+        from membrane_solver_b200.runtime.device_state import get_state
+
+        assert get_state(meshes[1], np.array(meshes[1].positions_view())).uploads == 1   # topology stayed resident

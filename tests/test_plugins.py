@@ -247,6 +247,43 @@ def test_fixed_flags_follow_their_own_counter(backend):
     assert st.uploads == 1 and np.all(g2[2] == 0.0) and np.array_equal(g2[1], g0[1])
 
 
+def test_enforce_constraint_on_arrays(backend):
+    """constraints/volume.py:69-149 on dense arrays: Newton projection onto V = V0 with
+    the device's volume and dV/dx; the step is checked against the closed form of the oracle's volume gradient, the
+    target is reached, fixed rows stay, and penalty mode is a no-op unless the projection is forced."""
+    from oracle import ref_modules as ref
+
+    g = dict(np.load(H.GOLDEN + "/modules_cube_r2_jit.npz"))
+    mesh, gp, _ = _mesh(g)
+    pos0 = 1.05 * np.array(mesh.positions_view())
+    fixed = np.zeros(pos0.shape[0], bool)
+    fixed[::13] = True
+    mesh.set_fixed(fixed)
+    mesh.set_positions(pos0)
+    target = float(g["body_target_0"])
+    # one iteration = one closed-form Newton step
+    tri_body = np.asarray(g["tri"])[np.asarray(g["body_rows_0"])]
+    vol, gv = ref.body_volume(pos0, tri_body), np.zeros_like(pos0)
+    ref.accumulate_volume_gradient(pos0, tri_body, gv, 1.0)
+    step = (vol - target) / (np.vdot(gv, gv) + 1e-12) * gv
+    step[fixed] = 0.0
+    volume_constraint.enforce_constraint(mesh, global_params=gp, max_iter=1)
+    assert np.max(np.abs(np.array(mesh.positions_view()) - (pos0 - step))) <= 1e-13
+    volume_constraint.enforce_constraint(mesh, global_params=gp, context="mesh_operation")
+    pos = np.array(mesh.positions_view())
+    v_end = ref.body_volume(pos, tri_body)
+    assert abs(v_end - target) <= 1e-11
+    assert np.array_equal(pos[fixed], pos0[fixed])
+    # penalty mode: nothing moves unless forced
+    gp.set("volume_constraint_mode", "penalty")
+    mesh.set_positions(pos0)
+    volume_constraint.enforce_constraint(mesh, global_params=gp)
+    assert np.array_equal(np.array(mesh.positions_view()), pos0)
+    volume_constraint.enforce_constraint(mesh, global_params=gp, force_projection=True)
+    assert not np.array_equal(np.array(mesh.positions_view()), pos0)
+    assert mesh._b200_state.uploads == 1 if hasattr(mesh, "_b200_state") else True
+
+
 def test_array_refinement_matches_reference_hierarchy():
     """1 -> 4 refinement on arrays: counts of the 24 * 4^k hierarchy, closedness,
     orientation (volume stays +1), inherited fixed flags."""
