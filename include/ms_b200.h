@@ -300,6 +300,16 @@ MS_API int ms_ctx_set_rank_slot(ms_ctx* ctx, int32_t slot, int32_t n_slots);
 MS_API int ms_ctx_allreduce_scalars(ms_ctx* ctx, int32_t count);
 /* 0 while every pull found its flags in time; 1 after a pull gave up waiting (~2 s) */
 MS_API int ms_ctx_halo_error(ms_ctx* ctx, int32_t* error);
+/* One evaluation of this rank's partition with the transport folded into the compute launches: signal + pull of the
+ * (trial) positions in one kernel when exchange_positions != 0, pass A whose last CTA raises the seed flag, the seed
+ * pull, pass B whose last CTA reduces the per-CTA sums and publishes the local scalars, and one kernel that gathers
+ * the scalars of all ranks in rank order and writes the KKT coefficient: 5 launches for the sequence
+ * halo_signal / halo_pull / eval_pass_a / halo_signal / halo_pull / eval_pass_b / eval_reduce / allreduce_scalars /
+ * eval_project (10 launches); results agree to rounding (the local sums are added by the last CTA in 32 row
+ * groups instead of the reduce kernel's 64) and are run-to-run repeatable.  Replaces the per-evaluation halo exchange + scalar
+ * all-reduce of the partitioned sweep (BASELINE.json north_star; no counterpart in the single-process reference).
+ * The kernels wait for flags of peers, so the ranks must run concurrently: one process per GPU. */
+MS_API int ms_ctx_eval_partition(ms_ctx* ctx, const ms_eval_opts* opts, int32_t exchange_positions);
 
 /* One evaluation with everything resident: pass A (+ pass B when want_grad); the last CTA of the last pass adds
  * up the per-CTA sums in fixed order and writes the scalars and the KKT / penalty coefficient (no reduce or

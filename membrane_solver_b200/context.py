@@ -429,6 +429,10 @@ class DeviceMesh:
     def allreduce_scalars(self, count: int = 12) -> None:
         L.check(self._lib.ms_ctx_allreduce_scalars(self._h, int(count)))
 
+    def eval_partition(self, opts, exchange_positions: bool = True) -> None:
+        """One partitioned evaluation with the transport folded into the compute launches (5 launches)."""
+        L.check(self._lib.ms_ctx_eval_partition(self._h, ctypes.byref(opts), int(bool(exchange_positions))))
+
     def halo_error(self) -> bool:
         e = ctypes.c_int32(0)
         L.check(self._lib.ms_ctx_halo_error(self._h, ctypes.byref(e)))

@@ -1565,14 +1565,17 @@ int ms_ctx_halo_signal(ms_ctx* c, int32_t flag_index) {
   return 0;
 }
 
-int ms_ctx_halo_pull(ms_ctx* c, int32_t which, int32_t flag_index) {
-  NvtxRange range("ms_b200 halo pull");
-  if (int rc = check_ctx(c, true)) return rc;
+// pull (signal == false: the flag was raised earlier, by ms_ctx_halo_signal or by the last CTA of pass A) or
+// signal + pull in one launch
+static int halo_launch(ms_ctx* c, int32_t which, int32_t flag_index, bool signal) {
   if (flag_index != MS_FLAG_POSITIONS && flag_index != MS_FLAG_SEEDS)  // words 2 / 3 belong to the all-reduce and the warm-up
     return fail(-1, "flag index must be MS_FLAG_POSITIONS or MS_FLAG_SEEDS");
   if (int rc = ensure_flag_words(c)) return rc;
   const int64_t n_ghost = int64_t(c->nv) - c->n_owned;
-  if (n_ghost <= 0) return 0;
+  if (n_ghost <= 0) {
+    if (signal) CU(ms::launch_halo_signal(c->d_flag_words.p + flag_index, ++c->flag_epoch[flag_index], c->stream));
+    return 0;
+  }
   if (int rc = peer_tables(c)) return rc;
   ms_ctx::PeerTable& t = c->peers;
   const double* const* table = nullptr;
@@ -1591,9 +1594,22 @@ int ms_ctx_halo_pull(ms_ctx* c, int32_t which, int32_t flag_index) {
   double* dst = array_ptr(c, which, &len);
   if (!dst) return fail(-4, "the local array does not exist");
   // the epoch this rank has published is the epoch every owner must have reached (lock-step sequence)
+  if (signal) {
+    const unsigned long long epoch = ++c->flag_epoch[flag_index];
+    CU(ms::launch_halo_exchange(c->d_flag_words.p + flag_index, int(n_ghost), width, table, t.d_flags.p, t.n_slots,
+                                flag_index, epoch, t.d_owner.p, t.d_row.p, dst + size_t(c->n_owned) * width,
+                                c->d_halo_error.p, c->stream));
+    return 0;
+  }
   CU(ms::launch_halo_pull(int(n_ghost), width, table, t.d_flags.p, t.n_slots, flag_index, c->flag_epoch[flag_index],
                           t.d_owner.p, t.d_row.p, dst + size_t(c->n_owned) * width, c->d_halo_error.p, c->stream));
   return 0;
+}
+
+int ms_ctx_halo_pull(ms_ctx* c, int32_t which, int32_t flag_index) {
+  NvtxRange range("ms_b200 halo pull");
+  if (int rc = check_ctx(c, true)) return rc;
+  return halo_launch(c, which, flag_index, false);
 }
 
 int ms_ctx_set_rank_slot(ms_ctx* c, int32_t slot, int32_t n_slots) {
@@ -1637,6 +1653,80 @@ int ms_ctx_halo_error(ms_ctx* c, int32_t* error) {
   CU(cudaMemcpyAsync(&e, c->d_halo_error.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   *error = e;
+  return 0;
+}
+
+// One evaluation of this rank's partition with the transport folded into the compute launches (peer memory):
+//   [signal + pull positions] -> pass A (its last CTA raises the seed flag) -> [pull seeds] -> pass B (its last
+//   CTA reduces the per-CTA rows and publishes the local scalars) -> gather (rank-order sum) + KKT coefficient
+// = 5 launches where the unfused sequence (ms_ctx_halo_signal / _pull, passes, ms_ctx_eval_reduce,
+// ms_ctx_allreduce_scalars, ms_ctx_eval_project) needs 10.  Ranks must run concurrently (one process per GPU).
+int ms_ctx_eval_partition(ms_ctx* c, const ms_eval_opts* o, int32_t exchange_positions) {
+  NvtxRange range("ms_b200 partition evaluation");
+  if (int rc = check_ctx(c, true)) return rc;
+  if (!o) return fail(-1, "null options");
+  if (o->patch_count != -1 || c->packed.patches.empty()) return fail(-1, "ms_ctx_eval_partition evaluates whole, non-empty partitions");
+  if (has_bt(o)) return fail(-1, "bending_tilt evaluations use the unfused sequence");
+  if (int rc = ensure_flag_words(c)) return rc;
+  if (int rc = peer_tables(c)) return rc;
+  ms_ctx::PeerTable& t = c->peers;
+  for (int32_t s = 0; s < t.n_slots; ++s)
+    if (!t.flags[size_t(s)]) return fail(-4, "the flag words of every rank must be opened (ms_ctx_peer_open, ms_ctx_set_rank_slot)");
+  const bool bending = needs_bending(o);
+  const bool ran_a = bending || !o->want_grad;
+  const bool run_b = o->want_grad || (o->want_tilt_grad && (o->modules & MS_MOD_TILT));
+  if (!o->want_grad && run_b) return fail(-1, "tilt-only evaluations use the unfused sequence");
+  if (exchange_positions)
+    if (int rc = halo_launch(c, o->use_trial ? MS_ARR_TRIAL : MS_ARR_POSITIONS, MS_FLAG_POSITIONS, true)) return rc;
+  const unsigned long long reduce_epoch = ++c->flag_epoch[2];
+  auto publish = [&](ms::PatchLaunch& a) -> int {
+    if (int rc = attach_finalize(c, o, a)) return rc;
+    a.fin.constraint_mode = -2;  // the coefficient needs the GLOBAL sums: k_allreduce_gather_coef
+    a.fin.publish_words = c->d_flag_words.p;
+    a.fin.publish_epoch = reduce_epoch;
+    return 0;
+  };
+  if (ran_a) {
+    ms::PatchLaunch a;
+    if (int rc = fill_launch(c, o, a)) return rc;
+    a.partials = c->d_partials_a.p;
+    c->ran_pass_a = true;
+    if (!o->want_grad) {
+      if (int rc = publish(a)) return rc;
+    } else if (bending) {  // ticket without a reduction: the last CTA raises the seed flag
+      if (int rc = attach_finalize(c, o, a)) return rc;
+      a.fin.scalars = nullptr;
+      a.fin.signal_flag = c->d_flag_words.p + MS_FLAG_SEEDS;
+      a.fin.signal_epoch = ++c->flag_epoch[MS_FLAG_SEEDS];
+    }
+    CU(ms::launch_pass_a(a, c->stream));
+  } else {
+    c->ran_pass_a = false;
+  }
+  if (o->want_grad) {
+    if (bending)
+      if (int rc = halo_launch(c, MS_ARR_SEEDS, MS_FLAG_SEEDS, false)) return rc;
+    ms::PatchLaunch a;
+    if (int rc = fill_launch(c, o, a)) return rc;
+    a.partials = c->d_partials_b.p;
+    c->proj.active = false;
+    if ((o->modules & MS_MOD_TILT) && !a.tilt_grad) {
+      if (int rc = ensure_array(c, MS_ARR_TILT_GRAD)) return rc;
+      a.tilt_grad = c->d_tilt_grad.p;
+    }
+    if (int rc = publish(a)) return rc;
+    CU(ms::launch_pass_b(a, bending, !bending, c->stream));
+  }
+  bool use_gc, use_fixed;
+  projection_of(c, o, use_gc, use_fixed);
+  CU(ms::launch_allreduce_gather_coef(c->d_scalars.p, 12, t.d_flags.p, t.n_slots, reduce_epoch,
+                                      o->want_grad ? o->constraint_mode : -2, use_gc ? 1 : 0, o->k_vol, o->v_target,
+                                      c->d_halo_error.p, c->stream));
+  if (o->want_grad) {
+    c->proj.active = use_gc || use_fixed;
+    c->proj.use_gc = use_gc;
+    c->proj.use_fixed = use_fixed;
+  }
   return 0;
 }
 

@@ -586,15 +586,30 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
   if (a.fin.ticket) {  // the last CTA to get here finalises the evaluation (warp-uniform: a kernel parameter)
     __shared__ int s_last;
     __shared__ double s_part[kFinRows][kPartialStride];
+    const bool to_peers = a.fin.signal_flag || a.fin.publish_words;
     if (tid == 0) {
-      __threadfence();
+      if (to_peers) __threadfence_system(); else __threadfence();
       s_last = atomicAdd(a.fin.ticket, 1u) == gridDim.x - 1 ? 1 : 0;
     }
     __syncthreads();
     if (s_last) {
       __threadfence();
-      finalize_scalars(a.fin, s_part, tid);
-      if (tid == 0) *a.fin.ticket = 0u;
+      if (a.fin.scalars) finalize_scalars(a.fin, s_part, tid);
+      if (a.fin.publish_words) {  // publish half of the all-reduce over peer memory (k_allreduce_publish)
+        double* slot = reinterpret_cast<double*>(a.fin.publish_words + 8 + 16 * (a.fin.publish_epoch & 1ull));
+        if (tid < kPartialStride) slot[tid] = a.fin.scalars[tid];
+        __syncthreads();
+      }
+      if (tid == 0) {
+        *a.fin.ticket = 0u;
+        if (to_peers) {
+          __threadfence_system();
+          if (a.fin.signal_flag) *reinterpret_cast<volatile unsigned long long*>(a.fin.signal_flag) = a.fin.signal_epoch;
+          if (a.fin.publish_words)
+            *reinterpret_cast<volatile unsigned long long*>(a.fin.publish_words + 2) = a.fin.publish_epoch;
+          __threadfence_system();
+        }
+      }
     }
   }
 }
@@ -1282,7 +1297,7 @@ __global__ void k_halo_signal(unsigned long long* flag, unsigned long long epoch
   __threadfence_system();
 }
 
-__global__ void __launch_bounds__(256) k_halo_pull(int n_ghost, int width, const double* const* __restrict__ peer_base,
+__device__ __forceinline__ void halo_wait_and_pull(int n_ghost, int width, const double* const* __restrict__ peer_base,
                                                    unsigned long long* const* __restrict__ peer_flag, int n_slots,
                                                    int flag_index, unsigned long long epoch,
                                                    const int32_t* __restrict__ owner, const int32_t* __restrict__ row,
@@ -1313,6 +1328,31 @@ __global__ void __launch_bounds__(256) k_halo_pull(int n_ghost, int width, const
   }
 }
 
+__global__ void __launch_bounds__(256) k_halo_pull(int n_ghost, int width, const double* const* __restrict__ peer_base,
+                                                   unsigned long long* const* __restrict__ peer_flag, int n_slots,
+                                                   int flag_index, unsigned long long epoch,
+                                                   const int32_t* __restrict__ owner, const int32_t* __restrict__ row,
+                                                   double* dst, int* error) {
+  halo_wait_and_pull(n_ghost, width, peer_base, peer_flag, n_slots, flag_index, epoch, owner, row, dst, error);
+}
+
+// Signal and pull in ONE launch: block 0 raises this rank's flag (stream-ordered after the kernel that wrote the
+// owned rows), every block then waits for the owners of the ghosts and copies.  Only for ranks that run
+// concurrently (one process per GPU): contexts that share a stream would wait for a kernel queued behind them.
+__global__ void __launch_bounds__(256) k_halo_exchange(unsigned long long* own_flag, int n_ghost, int width,
+                                                       const double* const* __restrict__ peer_base,
+                                                       unsigned long long* const* __restrict__ peer_flag, int n_slots,
+                                                       int flag_index, unsigned long long epoch,
+                                                       const int32_t* __restrict__ owner,
+                                                       const int32_t* __restrict__ row, double* dst, int* error) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(own_flag) = epoch;
+    __threadfence_system();
+  }
+  halo_wait_and_pull(n_ghost, width, peer_base, peer_flag, n_slots, flag_index, epoch, owner, row, dst, error);
+}
+
 // All-reduce (sum) of n <= 16 scalars over peer memory.  Word layout of every rank's exported block:
 // [0..3] epoch flags, [8 + 16 p .. 8 + 16 p + 15] scalar slot of parity p.  Publish: copy this rank's scalars into
 // the slot of the epoch's parity, then raise flag 2.  Gather: wait for every rank's flag, add the slots in RANK
@@ -1331,8 +1371,8 @@ __global__ void k_allreduce_publish(const double* __restrict__ scalars, int n, u
   }
 }
 
-__global__ void k_allreduce_gather(unsigned long long* const* __restrict__ peer_words, int n_slots, int n,
-                                   unsigned long long epoch, double* scalars, int* error) {
+__device__ __forceinline__ bool allreduce_gather(unsigned long long* const* __restrict__ peer_words, int n_slots, int n,
+                                                 unsigned long long epoch, double* scalars, int* error) {
   __shared__ int ok;
   if (threadIdx.x == 0) ok = 1;
   __syncthreads();
@@ -1349,7 +1389,7 @@ __global__ void k_allreduce_gather(unsigned long long* const* __restrict__ peer_
     }
   }
   __syncthreads();
-  if (!ok) return;
+  if (!ok) return false;
   __threadfence_system();
   if (int(threadIdx.x) < n) {
     double acc = 0.0;
@@ -1357,6 +1397,21 @@ __global__ void k_allreduce_gather(unsigned long long* const* __restrict__ peer_
       acc += __ldcv(reinterpret_cast<const double*>(peer_words[s] + 8 + 16 * (epoch & 1ull)) + threadIdx.x);
     scalars[threadIdx.x] = acc;
   }
+  return true;
+}
+
+__global__ void k_allreduce_gather(unsigned long long* const* __restrict__ peer_words, int n_slots, int n,
+                                   unsigned long long epoch, double* scalars, int* error) {
+  allreduce_gather(peer_words, n_slots, n, epoch, scalars, error);
+}
+
+// gather + the KKT coefficient from the GLOBAL sums (mode -2: energy-only evaluation, coefficient untouched)
+__global__ void k_allreduce_gather_coef(unsigned long long* const* __restrict__ peer_words, int n_slots, int n,
+                                        unsigned long long epoch, double* scalars, int mode, int has_gc, double k_vol,
+                                        double v_target, int* error) {
+  const bool ok = allreduce_gather(peer_words, n_slots, n, epoch, scalars, error);
+  __syncthreads();
+  if (ok && threadIdx.x == 0 && mode != -2) kkt_coefficient(scalars, mode, has_gc, k_vol, v_target);
 }
 
 __global__ void __launch_bounds__(256) k_row_norm2(const double* __restrict__ rows, int64_t n, double* out) {
@@ -1869,6 +1924,24 @@ cudaError_t launch_halo_pull(int n_ghost, int width, const double* const* peer_b
   const int blocks = (n_ghost * width + 255) / 256;
   k_halo_pull<<<blocks < 64 ? blocks : 64, 256, 0, st>>>(n_ghost, width, peer_base, peer_flag, n_slots, flag_index, epoch,
                                                           owner, row, dst, error);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_halo_exchange(unsigned long long* own_flag, int n_ghost, int width, const double* const* peer_base,
+                                 unsigned long long* const* peer_flag, int n_slots, int flag_index,
+                                 unsigned long long epoch, const int32_t* owner, const int32_t* row, double* dst,
+                                 int* error, cudaStream_t st) {
+  const int blocks = (n_ghost * width + 255) / 256;
+  k_halo_exchange<<<blocks < 64 ? (blocks > 0 ? blocks : 1) : 64, 256, 0, st>>>(own_flag, n_ghost, width, peer_base, peer_flag,
+                                                                               n_slots, flag_index, epoch, owner, row, dst,
+                                                                               error);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_allreduce_gather_coef(double* scalars, int n, unsigned long long* const* peer_words, int n_slots,
+                                         unsigned long long epoch, int mode, int has_gc, double k_vol, double v_target,
+                                         int* error, cudaStream_t st) {
+  k_allreduce_gather_coef<<<1, 64, 0, st>>>(peer_words, n_slots, n, epoch, scalars, mode, has_gc, k_vol, v_target, error);
   return cudaGetLastError();
 }
 

@@ -56,7 +56,12 @@ struct PatchFinalize {
                               // 1 penalty (constraint_manager.py:294-301, body.py:223-238)
   int32_t has_gc;             // the volume gradient takes part in the projection
   double k_vol, v_target;
-  double* scalars;
+  double* scalars;            // nullptr: no reduction (the ticket only raises signal_flag)
+  // partitioned evaluations over peer memory (see k_halo_pull / k_allreduce_gather): the last CTA can also
+  unsigned long long* signal_flag;    // raise this rank's "owned rows are written" flag (pass A: the seeds) ...
+  unsigned long long signal_epoch;
+  unsigned long long* publish_words;  // ... and publish the local scalars into the all-reduce slot of this epoch
+  unsigned long long publish_epoch;
 };
 
 struct PatchLaunch {
@@ -224,6 +229,15 @@ cudaError_t launch_halo_pull(int n_ghost, int width, const double* const* peer_b
                              const int32_t* row, double* dst, int* error, cudaStream_t st);
 cudaError_t launch_allreduce_peer(double* scalars, int n, unsigned long long* own_words, unsigned long long* const* peer_words,
                                   int n_slots, unsigned long long epoch, int* error, cudaStream_t st);
+// signal + pull in one launch (multi-process only: the kernel waits for peers that run concurrently)
+cudaError_t launch_halo_exchange(unsigned long long* own_flag, int n_ghost, int width, const double* const* peer_base,
+                                 unsigned long long* const* peer_flag, int n_slots, int flag_index,
+                                 unsigned long long epoch, const int32_t* owner, const int32_t* row, double* dst,
+                                 int* error, cudaStream_t st);
+// gather half of the all-reduce (the publish half ran in the last CTA of the pass) + KKT coefficient
+cudaError_t launch_allreduce_gather_coef(double* scalars, int n, unsigned long long* const* peer_words, int n_slots,
+                                         unsigned long long epoch, int mode, int has_gc, double k_vol, double v_target,
+                                         int* error, cudaStream_t st);
 cudaError_t launch_halo_warmup(unsigned long long* words, double* scalars, int* error, cudaStream_t st);
 constexpr int kFlagWords = 64;  // exported block: 4 epoch flags, 2 x 16 scalar slots (see k_allreduce_publish)
 

@@ -167,7 +167,8 @@ class PartitionedMesh:
     """One rank's share of a mesh on its GPU plus the exchange plumbing."""
 
     def __init__(self, local: LocalMesh, device_index: int, *, body_mask=None, is_boundary=None,
-                 fixed_mask=None, pack=None, reserve_sms: int = 0, transport: str | None = None):
+                 fixed_mask=None, pack=None, reserve_sms: int = 0, transport: str | None = None,
+                 fused: bool | None = None):
         import torch
         import torch.distributed as dist
 
@@ -193,6 +194,11 @@ class PartitionedMesh:
         self.transport = "nccl"
         if want == "peer" and local.world > 1:
             self.transport = "peer" if self._open_peers(gathered) else "nccl"
+        # transport folded into the compute launches (ms_ctx_eval_partition); MS_HALO_FUSED=0 keeps the ten-launch
+        # sequence (the two must agree bit for bit: bench_multi_gpu's parity block runs on whichever is active)
+        if fused is None:
+            fused = _os.environ.get("MS_HALO_FUSED", "1").strip() != "0"
+        self.fused = bool(fused) and self.transport == "peer"
         # the context launches on the legacy default stream; torch's current stream is the
         # same stream unless the caller changed it, so kernels and NCCL calls stay ordered
         if reserve_sms > 0:
@@ -294,6 +300,10 @@ class PartitionedMesh:
         L, dm, torch = self.L, self.dm, self.torch
         bending = bool(opts.want_grad and (opts.modules & L.MOD_BENDING))
         if not overlap or self.local.world == 1 or opts.patch_count != L.PATCHES_ALL:
+            if (self.fused and opts.patch_count == L.PATCHES_ALL and not (opts.modules & L.MOD_BENDING_TILT)
+                    and (opts.want_grad or not opts.want_tilt_grad)):
+                dm.eval_partition(opts, exchange_positions)
+                return
             if exchange_positions:
                 self.exchange(L.ARR_TRIAL if opts.use_trial else L.ARR_POSITIONS)
             dm.eval_pass_a(opts)
@@ -471,7 +481,7 @@ def _measure_partitioned(args, rank, world, local_rank, bench, total_facets: int
     res = dm.read_scalars()
     out = {"facets": nf, "vertices": nv, "frequency": n, "ms_per_step": ms_step, "steps": steps,
            "value": nf / (ms_step * 1e-3) / 1e9, "mesh_seconds": t_gen, "partition_pack_seconds": t_setup,
-           "transport": pm.transport,
+           "transport": pm.transport, "fused": bool(pm.fused),
            "energies": {"surface": res.e_surface, "bending": res.e_bending, "volume": res.volume}}
     phases = None
     if os.environ.get("MS_PHASES", "0") != "0":  # per-phase device times of this rank (diagnostic)
@@ -586,9 +596,11 @@ def bench_multi_gpu(args, rank: int, world: int, local_rank: int, bench):
             "collectives_per_step": {"halo_exchanges": 2, "all_reduce": 1, "halo_transport": weak["transport"],
                                      "all_reduce_transport": "peer memory" if peer else "nccl",
                                      "halo_bytes_per_rank": weak["max_ghost_rows_per_rank"] * (24 + 40)},
-            # pass A, pass B, reduce, coefficient + per halo exchange: flag signal + pull (peer) or the row gather (nccl)
-            # + the peer all-reduce's publish and gather kernels
-            "gpu_launches": (4 + (6 if peer else 2)) * args.steps,
+            # fused peer transport (ms_ctx_eval_partition): signal+pull positions, pass A (raises the seed flag), seed
+            # pull, pass B (reduces + publishes), gather + coefficient.  Unfused: pass A, pass B, reduce, coefficient
+            # + per halo exchange flag signal + pull (peer) or the row gather (nccl) + the all-reduce's two kernels
+            "gpu_launches": (5 if weak.get("fused") else 4 + (6 if peer else 2)) * args.steps,
+            "launches_per_step": 5 if weak.get("fused") else 4 + (6 if peer else 2),
             "clocks": weak["clocks"],
             "energies": weak["energies"],
             "setup_seconds": weak["mesh_seconds"] + weak["partition_pack_seconds"],
