@@ -571,7 +571,15 @@ def bench_multi_gpu(args, rank: int, world: int, local_rank: int, bench):
     import torch.distributed as dist
 
     torch.cuda.set_device(local_rank)
+    # host buffers (pinned positions / gradients of the e2e leg, pack scratch) next to this rank's GPU
+    import os
+
+    from .numa import bind_to_gpu
+
+    numa = bind_to_gpu(local_rank) if os.environ.get("MS_NUMA_BIND", "1") != "0" else {"bound": False, "reason": "MS_NUMA_BIND=0"}
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    numa_all = [None] * world
+    dist.all_gather_object(numa_all, numa)
     weak = _measure_partitioned(args, rank, world, local_rank, bench, args.facets * world, "weak", with_e2e=True,
                                 with_parity=not args.no_parity, steps=args.steps)
     strong = None
@@ -592,7 +600,7 @@ def bench_multi_gpu(args, rank: int, world: int, local_rank: int, bench):
                          "peak": peak * world, "unit": "GB/s", "frac": bench.B_STEP * value / (peak * world),
                          "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({peak_kind}) x {world} GPUs",
                          "bytes_per_facet": bench.B_STEP},
-            "e2e": weak["e2e"],
+            "e2e": {**weak["e2e"], "numa": numa_all},
             "collectives_per_step": {"halo_exchanges": 2, "all_reduce": 1, "halo_transport": weak["transport"],
                                      "all_reduce_transport": "peer memory" if peer else "nccl",
                                      "halo_bytes_per_rank": weak["max_ghost_rows_per_rank"] * (24 + 40)},
