@@ -37,12 +37,13 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     pos, tri = icosphere(frequency_for_facets(facets))
     rng = np.random.default_rng(4)
-    pos = pos * (1.0 + 0.01 * rng.standard_normal((pos.shape[0], 1)))
+    edge = float(np.linalg.norm(pos[tri[:, 0]] - pos[tri[:, 1]], axis=1).mean())
+    pos = pos * (1.0 + 0.05 * edge * rng.standard_normal((pos.shape[0], 1)))   # 5 % of an edge: steps get accepted
     nv, nf = pos.shape[0], tri.shape[0]
     local = split_mesh(nv, tri, world, rank)
     rows = local.global_rows()
     mods = L.MOD_SURFACE | L.MOD_BENDING
-    common = dict(modules=mods, v_target=4.0, step_size=1e-3, k_vol=0.0)
+    common = dict(modules=mods, v_target=4.0, step_size=1e-3 * edge * edge, k_vol=0.0)
     out = {"n_gpus": world, "facets": int(nf), "steps": steps, "cases": {}}
     for name, kw in CASES.items():
         pm = PartitionedMesh(local, local_rank, body_mask=np.ones(local.tri.shape[0], np.uint8))
