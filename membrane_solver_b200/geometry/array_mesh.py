@@ -76,7 +76,8 @@ class ParamResolver:
 
 class ArrayMesh:
     def __init__(self, positions, tri, *, global_params=None, facet_params=None, bodies=None, fixed=None,
-                 tilts=None, vertex_options=None, tilts_in=None, tilts_out=None, leaflets=None):
+                 tilts=None, vertex_options=None, tilts_in=None, tilts_out=None, leaflets=None,
+                 tilt_fixed_in=None, tilt_fixed_out=None):
         self._positions = np.ascontiguousarray(positions, dtype=np.float64)
         self._tri = np.ascontiguousarray(tri, dtype=np.int32).reshape(-1, 3)
         nv = self._positions.shape[0]
@@ -94,6 +95,9 @@ class ArrayMesh:
         self._tilts = np.zeros((nv, 3)) if tilts is None else np.asarray(tilts, dtype=np.float64)
         self._tilts_in = np.zeros((nv, 3)) if tilts_in is None else np.asarray(tilts_in, dtype=np.float64)
         self._tilts_out = np.zeros((nv, 3)) if tilts_out is None else np.asarray(tilts_out, dtype=np.float64)
+        # rows whose leaflet tilt is clamped (the ``tilt_fixed_in`` / ``tilt_fixed_out`` vertex flags)
+        self.tilt_fixed_in_mask = np.zeros(nv, bool) if tilt_fixed_in is None else np.asarray(tilt_fixed_in, dtype=bool)
+        self.tilt_fixed_out_mask = np.zeros(nv, bool) if tilt_fixed_out is None else np.asarray(tilt_fixed_out, dtype=bool)
         # leaflet -> selections / parameters as plain arrays (keys of modules/energy/_leaflet.py: keep_bt, keep_tilt,
         # interior, base_zero, kappa, c0, k_tilt, consistent, row_weight, facet_consistent)
         self.leaflets = {k: dict(v) for k, v in (leaflets or {}).items()}
@@ -119,6 +123,12 @@ class ArrayMesh:
 
     def tilts_out_view(self):
         return self._tilts_out
+
+    def set_tilts_in_from_array(self, tilts):
+        self._tilts_in = np.array(tilts, dtype=np.float64).reshape(self._positions.shape)
+
+    def set_tilts_out_from_array(self, tilts):
+        self._tilts_out = np.array(tilts, dtype=np.float64).reshape(self._positions.shape)
 
     def leaflet_selection(self, leaflet: str) -> dict:
         """What the reference derives from mesh options (leaflet presence, base-term rows, per-vertex

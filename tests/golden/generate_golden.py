@@ -709,6 +709,140 @@ def tilt_relaxation_vectors():
     np.savez_compressed(os.path.join(HERE, "tilt_relaxation.npz"), **out)
 
 
+def tilt_relaxation_constrained_vectors():
+    """Row f3 with the tilt CONSTRAINT modules configs[3] ships (``tilt_thetaB_boundary_in``, ``rim_slope_match_out``
+    next to ``rigid_disk`` / ``pin_to_plane`` / ``pin_to_circle``): the reference's ``relax_leaflet_tilts`` on the
+    caveolin free-disk mesh with its constraint manager in place.  The two places where the constraint manager
+    touches the loop are recorded call by call -- arrays going in, arrays coming out -- so that the device relaxer
+    can be driven along the same trajectory without the reference: ``{case}_ghook_{k}_*`` for
+    ``apply_tilt_gradient_modifications_array`` and ``{case}_refresh_{k}_*`` for ``enforce_tilt_constraints``."""
+    from modules.energy.bt_params import (_assume_J0_center_xy, _assume_J0_presets, _assume_J0_radius_max,
+                                          _per_vertex_params_leaflet)
+    from modules.energy.bt_selection import _collect_preset_rows, _interior_mask_leaflet
+    from modules.energy.leaflet_presence import leaflet_absent_vertex_mask, leaflet_present_triangle_mask
+
+    path = os.path.join(REF, "meshes", "caveolin",
+                        "kozlov_1disk_3d_tensionless_single_leaflet_profile_hard_rim_R12_free_disk.yaml")
+    out = {}
+    for case, steps, step_size, solver, extra in (("cgd4", 4, 0.15, "gd", {}), ("ccg5", 5, 0.15, "cg", {}),
+                                                  ("cgd6i2", 6, 0.05, "gd", {"tilt_projection_interval": 2}),
+                                                  ("ccg4pass", 4, 0.15, "cg", {"tilt_projection_cadence": "per_pass"})):
+        mesh = _refined(path, 1)
+        gp = mesh.global_parameters
+        gp.set("tilt_solver", solver)
+        for k_extra, v_extra in extra.items():
+            gp.set(k_extra, v_extra)
+        gp.set("tilt_solve_mode", "nested")
+        gp.set("tilt_inner_steps", steps)
+        gp.set("tilt_step_size", step_size)
+        gp.set("tilt_tol", 0.0)
+        rng = np.random.default_rng(37)
+        nv = len(mesh.vertex_ids)
+        for row, vid in enumerate(mesh.vertex_ids):
+            v = mesh.vertices[int(vid)]
+            if not getattr(v, "fixed", False):
+                v.position = np.asarray(v.position, dtype=float) + np.array([0.0, 0.0, 0.02 * rng.standard_normal()])
+            if not getattr(v, "tilt_fixed_in", False):
+                v.tilt_in = 0.05 * rng.standard_normal(3)
+            if not getattr(v, "tilt_fixed_out", False):
+                v.tilt_out = 0.05 * rng.standard_normal(3)
+        mesh.increment_version()
+        if hasattr(mesh, "touch_tilts_in"):
+            mesh.touch_tilts_in()
+            mesh.touch_tilts_out()
+        names = ["bending_tilt_in", "bending_tilt_out", "tilt_in", "tilt_out"]
+        mesh.energy_modules = list(names)
+        cons = list(mesh.constraint_modules)
+        assert "tilt_thetaB_boundary_in" in cons and "rim_slope_match_out" in cons, cons
+        cm = ConstraintModuleManager(cons)
+        mini = Minimizer(mesh, gp, GradientDescent(), EnergyModuleManager(names), cm, quiet=True)
+        pos = np.array(mesh.positions_view())
+        idx = mesh.vertex_index_to_row
+        tri = np.ascontiguousarray(mesh.triangle_row_cache()[0], dtype=np.int32)
+        isb = np.zeros(nv, bool)
+        for vid in mesh.boundary_vertex_ids:
+            isb[idx[vid]] = True
+        pre = case + "_"
+        out[pre + "pos"], out[pre + "tri"], out[pre + "is_boundary"] = pos, tri, isb
+        out[pre + "tilts_in0"], out[pre + "tilts_out0"] = np.array(mesh.tilts_in_view()), np.array(mesh.tilts_out_view())
+        out[pre + "fixed_in"], out[pre + "fixed_out"] = np.array(mini._tilt_fixed_mask_in()), np.array(mini._tilt_fixed_mask_out())
+        for leaf in ("in", "out"):
+            am = leaflet_absent_vertex_mask(mesh, gp, leaflet=leaf)
+            keep = leaflet_present_triangle_mask(mesh, tri, absent_vertex_mask=am)
+            out[pre + f"{leaf}_keep"] = np.ones(len(tri), bool) if keep.size == 0 else np.asarray(keep, bool)
+            out[pre + f"{leaf}_interior"] = np.asarray(_interior_mask_leaflet(mesh, gp, cache_tag=leaf, index_map=idx), bool)
+            bz = np.zeros(nv, bool)
+            presets = _assume_J0_presets(gp, cache_tag=leaf)
+            if presets:
+                bz[_collect_preset_rows(mesh, presets=presets, cache_tag=leaf, index_map=idx,
+                                        radius_max=_assume_J0_radius_max(gp, cache_tag=leaf),
+                                        center_xy=_assume_J0_center_xy(gp))] = True
+            out[pre + f"{leaf}_base_zero"] = bz
+            kap, c0 = _per_vertex_params_leaflet(mesh, gp, model="helfrich", kappa_key=f"bending_modulus_{leaf}",
+                                                 cache_tag=leaf)
+            out[pre + f"{leaf}_kappa"], out[pre + f"{leaf}_c0"] = np.array(kap), np.array(c0)
+            out[pre + f"{leaf}_k_tilt"] = np.float64(gp.get(f"tilt_modulus_{leaf}"))
+        # -- record the two hooks call by call
+        ghook, refresh = [], []
+        orig_mod, orig_enf = cm.apply_tilt_gradient_modifications_array, cm.enforce_tilt_constraints
+
+        def rec_mod(g_in, g_out, *a, **kw):
+            before = (np.array(g_in), np.array(g_out), np.array(kw["tilts_in"]), np.array(kw["tilts_out"]))
+            orig_mod(g_in, g_out, *a, **kw)
+            ghook.append(before + (np.array(g_in), np.array(g_out)))
+
+        def rec_enf(m, **kw):
+            before = (np.array(m.tilts_in_view()), np.array(m.tilts_out_view()))
+            orig_enf(m, **kw)
+            refresh.append(before + (np.array(m.tilts_in_view()), np.array(m.tilts_out_view())))
+
+        cm.apply_tilt_gradient_modifications_array = rec_mod
+        cm.enforce_tilt_constraints = rec_enf
+        stats = mini._relax_leaflet_tilts(positions=mesh.positions_view(), mode="nested")
+        assert np.array_equal(np.array(mesh.positions_view()), pos), "the tilt block moved the geometry"
+        out[pre + "tilts_in1"], out[pre + "tilts_out1"] = np.array(mesh.tilts_in_view()), np.array(mesh.tilts_out_view())
+        out[pre + "n_ghook"], out[pre + "n_refresh"] = np.int64(len(ghook)), np.int64(len(refresh))
+        for k, (gi, go, ti, to, gi2, go2) in enumerate(ghook):
+            q = pre + f"ghook_{k}_"
+            if k < 2:      # full arrays for the first calls, then their norms + the rows that change (fixture size)
+                out[q + "g_in"], out[q + "g_out"], out[q + "t_in"], out[q + "t_out"] = gi, go, ti, to
+            out[q + "norms"] = np.array([np.linalg.norm(x) for x in (gi, go, ti, to)])
+            out[q + "old_in"], out[q + "old_out"] = gi[np.flatnonzero(np.any(gi2 != gi, axis=1))], go[np.flatnonzero(np.any(go2 != go, axis=1))]
+            rows_in = np.flatnonzero(np.any(gi2 != gi, axis=1))
+            rows_out = np.flatnonzero(np.any(go2 != go, axis=1))
+            out[q + "rows_in"], out[q + "new_in"] = rows_in, gi2[rows_in]        # sparse: a few rim rows change
+            out[q + "rows_out"], out[q + "new_out"] = rows_out, go2[rows_out]
+        for k, (ti, to, ti2, to2) in enumerate(refresh):
+            q = pre + f"refresh_{k}_"
+            if k < 2:
+                out[q + "t_in"], out[q + "t_out"] = ti, to
+            out[q + "norms"] = np.array([np.linalg.norm(x) for x in (ti, to)])
+            rows_in = np.flatnonzero(np.any(ti2 != ti, axis=1))
+            rows_out = np.flatnonzero(np.any(to2 != to, axis=1))
+            out[q + "old_in"], out[q + "old_out"] = ti[rows_in], to[rows_out]
+            out[q + "rows_in"], out[q + "new_in"] = rows_in, ti2[rows_in]
+            out[q + "rows_out"], out[q + "new_out"] = rows_out, to2[rows_out]
+        for k in ("accepted_steps", "backtracking_steps", "initial_energy", "final_energy", "initial_gradient_norm",
+                  "final_gradient_norm"):
+            out[pre + k] = np.float64(stats[k])
+        out[pre + "steps"], out[pre + "step_size"] = np.int64(steps), np.float64(step_size)
+        out[pre + "solver"] = np.array(solver)
+        out[pre + "interval"] = np.int64(extra.get("tilt_projection_interval", 1))
+        out[pre + "cadence"] = np.array(extra.get("tilt_projection_cadence", "per_step"))
+        out[pre + "preconditioner"] = np.bool_(True)
+        out[pre + "gd_fallback"] = np.bool_(False)
+        out[pre + "k_smooth_in"] = np.float64(gp.get("bending_modulus_in") or gp.get("bending_modulus") or 0.0)
+        out[pre + "k_smooth_out"] = np.float64(gp.get("bending_modulus_out") or gp.get("bending_modulus") or 0.0)
+        out[pre + "rejected_steps"] = np.float64(stats["rejected_steps"])
+        out[pre + "stop_reason"] = np.array(str(stats["stop_reason"]))
+        print(case, len(ghook), len(refresh),
+              {k: stats[k] for k in ("accepted_steps", "backtracking_steps", "stop_reason", "initial_energy",
+                                     "final_energy", "initial_gradient_norm", "final_gradient_norm")},
+              "changed rows per gradient hook", [int(len(out[pre + f"ghook_{k}_rows_in"])) for k in range(len(ghook))][:3],
+              [int(len(out[pre + f"ghook_{k}_rows_out"])) for k in range(len(ghook))][:3])
+    np.savez_compressed(os.path.join(HERE, "tilt_relaxation_constrained.npz"), **out)
+
+
 def vertex_average_vectors():
     """runtime/vertex_average.py on a jittered refined cube (closed) and on the catenoid (fixed rims)."""
     from runtime.vertex_average import vertex_average
@@ -739,6 +873,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "tiltrelax":
         tilt_relaxation_vectors()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "tilt_relaxation_constrained":
+        tilt_relaxation_constrained_vectors()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "vertexaverage":
         vertex_average_vectors()
         sys.exit(0)
@@ -759,5 +896,6 @@ if __name__ == "__main__":
     leaflet_vectors()
     p1_vertex_vectors()
     tilt_relaxation_vectors()
+    tilt_relaxation_constrained_vectors()
     vertex_average_vectors()
     equiangulate_vectors()

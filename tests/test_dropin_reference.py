@@ -206,6 +206,63 @@ def test_reference_minimizer_config4_trajectory_on_b200_leaflet_plugins(b200_ins
     assert e[-1] < e[0]
 
 
+@pytest.mark.parametrize("solver", ["gd", "cg"])
+def test_device_tilt_relaxer_with_the_references_constraint_manager(b200_installed, solver):
+    """Row f3 on configs[3] AS SHIPPED: the leaflet tilt inner solve of the caveolin free-disk mesh with its tilt
+    constraint modules (``tilt_thetaB_boundary_in``, ``rim_slope_match_out``).  The device relaxer
+    (``device_tilt_relaxer.relax_leaflet_tilts``) keeps fields, gradients and trials on the device and calls the
+    reference's OWN constraint manager through its two hooks; the result is the reference's
+    ``TiltRelaxationManager.relax_leaflet_tilts`` (tilt fields 1e-9, energies, step counts)."""
+    load_data, parse_geometry, CMM, EMM, Minimizer, refine, GD = _ref_imports()
+    from membrane_solver_b200.runtime.device_tilt_relaxer import relax_leaflet_tilts
+
+    def build():
+        mesh = refine(parse_geometry(load_data(os.path.join(REF, CAVEOLIN))))
+        gp = mesh.global_parameters
+        gp.set("tilt_solver", solver)
+        gp.set("tilt_solve_mode", "nested")
+        gp.set("tilt_inner_steps", 4)
+        gp.set("tilt_step_size", 0.15)
+        gp.set("tilt_tol", 0.0)
+        rng = np.random.default_rng(41)
+        for vid in mesh.vertex_ids:
+            v = mesh.vertices[int(vid)]
+            if not getattr(v, "fixed", False):
+                v.position = np.asarray(v.position, dtype=float) + np.array([0.0, 0.0, 0.02 * rng.standard_normal()])
+            if not getattr(v, "tilt_fixed_in", False):
+                v.tilt_in = 0.05 * rng.standard_normal(3)
+            if not getattr(v, "tilt_fixed_out", False):
+                v.tilt_out = 0.05 * rng.standard_normal(3)
+        mesh.increment_version()
+        mesh.touch_tilts_in()
+        mesh.touch_tilts_out()
+        names = ["bending_tilt_in", "bending_tilt_out", "tilt_in", "tilt_out"]
+        mesh.energy_modules = list(names)
+        cm = CMM(list(mesh.constraint_modules))
+        mini = Minimizer(mesh, gp, GD(), EMM(names), cm, quiet=True)
+        return mesh, gp, cm, mini
+
+    mesh_ref, _, _, mini_ref = build()
+    want = mini_ref._relax_leaflet_tilts(positions=mesh_ref.positions_view(), mode="nested")
+    ti_ref, to_ref = np.array(mesh_ref.tilts_in_view()), np.array(mesh_ref.tilts_out_view())
+    assert want["accepted_steps"] > 0
+
+    b200_installed()
+    mesh, gp, cm, mini = build()
+    start = np.array(mesh.tilts_in_view())
+    got = relax_leaflet_tilts(mesh, gp, mini.param_resolver, constraint_manager=cm,
+                              positions=np.array(mesh.positions_view()), mode="nested")
+    assert got["hook_calls"]["gradient"] >= 4 and got["hook_calls"]["refresh"] >= 2     # the constraint manager was in the loop
+    for k in ("accepted_steps", "backtracking_steps"):
+        assert got[k] == want[k], k
+    assert got["stop_reason"] == want["stop_reason"]
+    for k in ("initial_energy", "final_energy", "initial_gradient_norm", "final_gradient_norm"):
+        assert abs(got[k] - want[k]) <= 1e-10 * max(1.0, abs(want[k])), k
+    assert np.max(np.abs(np.array(mesh.tilts_in_view()) - ti_ref)) <= 1e-9
+    assert np.max(np.abs(np.array(mesh.tilts_out_view()) - to_ref)) <= 1e-9
+    assert np.max(np.abs(ti_ref - start)) > 1e-3
+
+
 # ----------------------------------------------------------------------- SURVEY.md appendix B: instruction lists
 REPLAY = [
     ("cube", "benchmarks/inputs/bench_cube.json", None, {"surface": 4.840039760362666}),

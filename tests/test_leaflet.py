@@ -741,3 +741,137 @@ def test_device_leaflet_pair_equals_two_evaluations(gold, state):
     assert rel_err(dm.download(L.ARR_TILT_GRAD_IN), tgi) <= TOL
     assert abs(res[L.LEAFLET_IN, 3] - float((dm.download(L.ARR_TILT_GRAD_IN) ** 2).sum())) <= 1e-10 * res[L.LEAFLET_IN, 3]
     dm.close()
+
+
+# ------------------------------------------------ leaflet tilt relaxation WITH tilt constraint modules (row f3)
+CONSTRAINED_CASES = ("cgd4", "ccg5", "cgd6i2", "ccg4pass")
+
+
+@pytest.fixture(scope="module")
+def constrained_gold():
+    return np.load(os.path.join(GOLDEN, "tilt_relaxation_constrained.npz"))
+
+
+class _ReplayedConstraintManager:
+    """The reference's constraint manager as recorded by ``generate_golden.py tilt_relaxation_constrained_vectors``:
+    call k of each hook checks that the arrays the device hands over are the ones the reference handed to its
+    constraint manager (1e-10 of the array's scale) and answers with what the reference's modules
+    (``tilt_thetaB_boundary_in``, ``rim_slope_match_out``) answered -- a few rim rows change."""
+
+    def __init__(self, g, case):
+        self.g, self.case, self.kg, self.kr = g, case, 0, 0
+
+    def _same(self, got, key):
+        want = self.g[key]
+        scale = max(1.0, float(np.abs(want).max()))
+        assert float(np.abs(got - want).max()) <= 1e-10 * scale, (key, float(np.abs(got - want).max()))
+
+    def _same_norms(self, arrays, key):
+        want = self.g[key]
+        got = np.array([np.linalg.norm(x) for x in arrays])
+        assert np.all(np.abs(got - want) <= 1e-10 * np.maximum(1.0, want)), (key, got, want)
+
+    def gradient_hook(self, g_in, g_out, t_in, t_out):
+        q = f"{self.case}_ghook_{self.kg}_"
+        assert self.kg < int(self.g[self.case + "_n_ghook"])
+        if q + "g_in" in self.g.files:      # the first calls are stored in full, later ones as norms + changed rows
+            self._same(g_in, q + "g_in"), self._same(g_out, q + "g_out")
+            self._same(t_in, q + "t_in"), self._same(t_out, q + "t_out")
+        self._same_norms((g_in, g_out, t_in, t_out), q + "norms")
+        self._same(g_in[self.g[q + "rows_in"]], q + "old_in"), self._same(g_out[self.g[q + "rows_out"]], q + "old_out")
+        g_in[self.g[q + "rows_in"]] = self.g[q + "new_in"]
+        g_out[self.g[q + "rows_out"]] = self.g[q + "new_out"]
+        self.kg += 1
+
+    def refresh_hook(self, t_in, t_out):
+        q = f"{self.case}_refresh_{self.kr}_"
+        assert self.kr < int(self.g[self.case + "_n_refresh"])
+        if q + "t_in" in self.g.files:
+            self._same(t_in, q + "t_in"), self._same(t_out, q + "t_out")
+        self._same_norms((t_in, t_out), q + "norms")
+        self._same(t_in[self.g[q + "rows_in"]], q + "old_in"), self._same(t_out[self.g[q + "rows_out"]], q + "old_out")
+        t_in, t_out = np.array(t_in), np.array(t_out)
+        t_in[self.g[q + "rows_in"]] = self.g[q + "new_in"]
+        t_out[self.g[q + "rows_out"]] = self.g[q + "new_out"]
+        self.kr += 1
+        return t_in, t_out
+
+
+def _constrained_device_relaxation(g, case, factory):
+    from membrane_solver_b200 import _lib as L
+    from membrane_solver_b200.runtime.device_tilt_relaxer import DeviceTiltRelaxer
+
+    p = case + "_"
+    pos, tri = g[p + "pos"], g[p + "tri"]
+    dm = factory(0)
+    dm.set_topology(pos.shape[0], tri, is_boundary=g[p + "is_boundary"].astype(np.uint8))
+    dm.set_positions(pos)
+    for leaf, d in _relax_leaflets(g, case).items():
+        which = L.LEAFLET_IN if leaf == "in" else L.LEAFLET_OUT
+        dm.set_leaflet(which, div_sign=-1.0 if leaf == "in" else 1.0, kappa=d["kappa"], c0=d["c0"], k_tilt=d["k_tilt"],
+                       facet_keep=d["keep"].astype(np.uint8), interior=d["interior"].astype(np.uint8),
+                       base_zero=d["base_zero"].astype(np.uint8))
+        dm.set_leaflet_fixed(which, g[p + f"fixed_{leaf}"].astype(np.uint8))
+        dm.upload(L.ARR_TILTS_IN if leaf == "in" else L.ARR_TILTS_OUT, g[p + f"tilts_{leaf}0"])
+    cm = _ReplayedConstraintManager(g, case)
+    relaxer = DeviceTiltRelaxer(dm, gradient_hook=cm.gradient_hook, refresh_hook=cm.refresh_hook,
+                                projection_interval=int(g[p + "interval"]), projection_cadence=str(g[p + "cadence"]))
+    st = relaxer.relax(max_iters=int(g[p + "steps"]), step_size=float(g[p + "step_size"]), solver=str(g[p + "solver"]),
+                       preconditioner=True, gd_fallback=False,
+                       k_smooth={"in": float(g[p + "k_smooth_in"]), "out": float(g[p + "k_smooth_out"])},
+                       area_kept_only={"out": not bool(np.all(g[p + "out_keep"]))})
+    # every recorded call of the reference's constraint manager was consumed, in order
+    assert (cm.kg, cm.kr) == (int(g[p + "n_ghook"]), int(g[p + "n_refresh"]))
+    assert relaxer.hook_calls == {"gradient": cm.kg, "refresh": cm.kr}
+    _relax_stats_match(st, g, case)
+    assert st["stop_reason"] == str(g[p + "stop_reason"])
+    assert np.max(np.abs(dm.download(L.ARR_TILTS_IN) - g[p + "tilts_in1"])) <= 1e-10
+    assert np.max(np.abs(dm.download(L.ARR_TILTS_OUT) - g[p + "tilts_out1"])) <= 1e-10
+    dm.close()
+
+
+@pytest.mark.parametrize("case", CONSTRAINED_CASES)
+def test_constrained_tilt_relaxer_on_emulated_device(constrained_gold, case):
+    from fake_device import FakeDeviceMesh
+
+    _constrained_device_relaxation(constrained_gold, case, FakeDeviceMesh)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CONSTRAINED_CASES)
+def test_constrained_tilt_relaxer_on_device(constrained_gold, case):
+    from membrane_solver_b200.context import DeviceMesh
+
+    _constrained_device_relaxation(constrained_gold, case, DeviceMesh)
+
+
+@pytest.mark.parametrize("backend", [pytest.param("emulator", id="emulator"),
+                                     pytest.param("gpu", id="gpu", marks=pytest.mark.gpu)])
+@pytest.mark.parametrize("case", ["gd5", "cg6"])
+def test_mesh_level_relax_leaflet_tilts(relax_gold, case, backend, monkeypatch):
+    """``device_tilt_relaxer.relax_leaflet_tilts``: the mesh-level call (global parameters in, relaxed fields written
+    back to the mesh) lands on the reference's relaxed fields."""
+    from membrane_solver_b200.geometry.array_mesh import ArrayMesh, GlobalParams, ParamResolver
+    from membrane_solver_b200.runtime import device_state
+    from membrane_solver_b200.runtime.device_tilt_relaxer import relax_leaflet_tilts
+
+    if backend == "emulator":
+        from fake_device import FakeDeviceMesh
+
+        monkeypatch.setattr(device_state, "DEVICE_MESH_FACTORY", FakeDeviceMesh)
+    g, p = relax_gold, case + "_"
+    leaflets = {}
+    for leaf, d in _relax_leaflets(g, case).items():
+        leaflets[leaf] = dict(keep_bt=d["keep"], keep_tilt=d["keep"], interior=d["interior"], base_zero=d["base_zero"],
+                              kappa=d["kappa"], c0=d["c0"], k_tilt=d["k_tilt"])
+    gp = GlobalParams(tilt_solver=str(g[p + "solver"]), tilt_inner_steps=int(g[p + "steps"]),
+                      tilt_step_size=float(g[p + "step_size"]), tilt_tol=0.0,
+                      bending_modulus_in=float(g[p + "k_smooth_in"]), bending_modulus_out=float(g[p + "k_smooth_out"]))
+    mesh = ArrayMesh(g[p + "pos"], g[p + "tri"], global_params=gp, tilts_in=g[p + "tilts_in0"],
+                     tilts_out=g[p + "tilts_out0"], leaflets=leaflets, tilt_fixed_in=g[p + "fixed_in"],
+                     tilt_fixed_out=g[p + "fixed_out"])
+    mesh._boundary = set(np.flatnonzero(g[p + "is_boundary"]).tolist())
+    st = relax_leaflet_tilts(mesh, gp, ParamResolver(gp))
+    _relax_stats_match(st, g, case)
+    assert np.max(np.abs(mesh.tilts_in_view() - g[p + "tilts_in1"])) <= 1e-10
+    assert np.max(np.abs(mesh.tilts_out_view() - g[p + "tilts_out1"])) <= 1e-10
