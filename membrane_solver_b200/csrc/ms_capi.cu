@@ -246,6 +246,12 @@ int fill_launch(ms_ctx* c, const ms_eval_opts* o, ms::PatchLaunch& a) {
   int count = o->patch_count < 0 ? n_patches : o->patch_count;
   if (begin < 0 || count < 0 || begin + count > n_patches) return fail(-3, "patch range out of bounds");
   std::memset(&a, 0, sizeof(a));
+#ifdef MS_DEBUG_VARIANTS
+  {
+    static const int dbg = [] { const char* e = std::getenv("MS_DEBUG_VARIANT"); return e ? std::atoi(e) : 0; }();
+    a.debug = dbg;
+  }
+#endif
   if (o->patch_count == MS_PATCHES_INTERIOR || o->patch_count == MS_PATCHES_BOUNDARY) {
     // the two halves of one evaluation: interior patches, then the patches that read ghost rows; their
     // per-CTA sums occupy consecutive partial rows: [0, grid_i) and [grid_i, grid_i + grid_b)

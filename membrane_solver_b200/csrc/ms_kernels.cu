@@ -76,6 +76,21 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
+// One contiguous global range -> shared memory (16-byte aligned on both sides, size a multiple of 16) by the copy
+// engine; completion is counted in bytes on the mbarrier (mbar_expect_tx).
+__device__ __forceinline__ void bulk_copy(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// all groups of this thread but the most recent one are complete
+__device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+// the mbarrier receives one arrival (counted in its init value) when every copy this thread has issued so far has
+// landed: the issuing warp does not wait for its own copies
+__device__ __forceinline__ void cp_async_arrive_on(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
 // ---- mbarriers (producer <-> consumers) and named barriers (token ring) ----
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
@@ -83,6 +98,11 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(smem_u32(bar)) : "memory");
+}
+// arrival that also announces `bytes` of bulk copies to come (they complete the phase together with the arrivals)
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
 }
 __device__ __forceinline__ bool mbar_try(unsigned addr, unsigned parity) {
   unsigned ok = 0;
@@ -102,7 +122,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
 // take issue slots from the consumers
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, unsigned parity) {
   const unsigned addr = smem_u32(bar);
-  while (!mbar_try(addr, parity)) __nanosleep(500);
+  while (!mbar_try(addr, parity)) __nanosleep(100);
 }
 __device__ __forceinline__ void named_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
@@ -148,11 +168,14 @@ __device__ d3 vertex_normal_global(const PatchLaunch& a, const PatchHdrS& hs, in
 
 template <int PASS>
 struct Plan {
-  static constexpr int kInDoubles = (PASS == 0 ? 3 : 3 + kSeedStride) * kPatchLocalCap;  // pos (+ seeds)
+  // positions (and seeds) as rows, two spare rows each: a patch whose first owned row is odd starts its bulk copy
+  // one row earlier (16-byte alignment) and its consumers address the rows from base + one row
+  static constexpr int kInRows = kPatchLocalCap + 2;
+  static constexpr int kInDoubles = (PASS == 0 ? 3 : 3 + kSeedStride) * kInRows;  // pos (+ seeds)
   static constexpr int kAccRows = PASS == 0 ? 5 : 6;
   // byte offsets inside one input buffer
   static constexpr size_t oPos = 0;
-  static constexpr size_t oSeed = size_t(3) * kPatchLocalCap * 8;
+  static constexpr size_t oSeed = size_t(3) * kInRows * 8;
   static constexpr size_t oRecs = size_t(kInDoubles) * 8;
   static constexpr size_t oIds = oRecs + size_t(kPatchSlotCap) * sizeof(FacetRec);
   static constexpr size_t oHdr = oIds + size_t(kPatchLocalCap) * 4;
@@ -309,7 +332,7 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
   PatchHdrS* mail = reinterpret_cast<PatchHdrS*>(smem + P::oMail);
   if (tid == 0) {
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&bar_full[b], 32);
+      mbar_init(&bar_full[b], 33);  // 32 asynchronous copy completions + the header write of lane 0
       mbar_init(&bar_empty[b], unsigned(n_active / 32));
       mbar_init(&bar_done[b], unsigned(T));
       mbar_init(&bar_free[b], 32u * unsigned(n_epi_warps));
@@ -329,59 +352,92 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
   if (tid >= NC + 32) {
     // =========================== producer warp ===========================
     const int lane = tid - (NC + 32);
+#ifdef MS_DEBUG_VARIANTS
+    const bool dbg_copy = !(a.debug & 8);   // 8: stage header, records and ids only (consumer-bound timing)
+#else
+    constexpr bool dbg_copy = true;
+#endif
+    // Software pipeline over the patches of this CTA.  The header of patch j+1 is loaded (registers) and its halo
+    // ids are copied (into the id area of the OTHER input buffer, which its consumers never read) while patch j is
+    // staged, so that the owned rows and the halo rows of a patch -- the latter need the ids -- are issued back to
+    // back: one memory round trip per patch instead of three (header, level 1, level 2).  Completion is signalled
+    // by the copies themselves (cp.async.mbarrier.arrive.noinc): the warp never waits for its bulk data, only for
+    // the small id copy of the next patch, and has both buffers' copies in flight.
+    auto patch_id = [&](int j) {
+      const int pidx = a.patch_begin + int(blockIdx.x) + j * int(gridDim.x);
+      return a.patch_list ? a.patch_list[pidx] : pidx;
+    };
+    auto stage_ids = [&](const PatchHeader& h, int b) {
+      int32_t* ids = reinterpret_cast<int32_t*>(smem + size_t(b) * P::kInBytes + P::oIds);
+      const int32_t* hsrc = a.halo_ids + h.halo_off;
+      for (int k = lane; k < h.n_halo; k += 32) cp_async4(ids + k, hsrc + k);
+    };
+    auto load_header = [&](int j, PatchHeader& h, int& n_slots) {
+      const int pid = patch_id(j);
+      h = a.patches[pid];
+      n_slots = int(a.patches[pid + 1].slot_off - h.slot_off);  // sentinel header at the end
+    };
+    PatchHeader h_cur{}, h_n1{}, h_n2{};
+    int slots_cur = 0, slots_n1 = 0, slots_n2 = 0;
+    if (n_my > 0) {
+      load_header(0, h_cur, slots_cur);
+      if (n_my > 1) load_header(1, h_n1, slots_n1);
+      stage_ids(h_cur, 0);
+      cp_async_wait_all();
+      __syncwarp();
+    }
     for (int j = 0; j < n_my; ++j) {
       const int b = j & 1;
-      const int pidx = a.patch_begin + int(blockIdx.x) + j * int(gridDim.x);
-      const int pid = a.patch_list ? a.patch_list[pidx] : pidx;
+      const PatchHeader h = h_cur;
+      const int n_slots = slots_cur;
+      if (j + 2 < n_my) load_header(j + 2, h_n2, slots_n2);  // in flight while this patch is being issued
       if (j >= 2) mbar_wait_relaxed(&bar_empty[b], unsigned(((j >> 1) - 1) & 1));
-      const PatchHeader h = a.patches[pid];
-      const int n_slots = int(a.patches[pid + 1].slot_off - h.slot_off);  // sentinel header at the end
+      // ids of the NEXT patch into the other buffer's id area (free: the data of patch j-1 there may still be in
+      // use, its ids are not).  Committed before this patch's bulk copies, so that wait_group 1 below waits for the
+      // ids only.
+      if (j + 1 < n_my) stage_ids(h_n1, b ^ 1);
+      cp_async_commit();
       unsigned char* in = smem + size_t(b) * P::kInBytes;
-      double* pos = reinterpret_cast<double*>(in + P::oPos);
-      double* seed = reinterpret_cast<double*>(in + P::oSeed);
       FacetRec* recs = reinterpret_cast<FacetRec*>(in + P::oRecs);
-      int32_t* ids = reinterpret_cast<int32_t*>(in + P::oIds);
+      const int32_t* ids = reinterpret_cast<const int32_t*>(in + P::oIds);  // arrived during the previous iteration
+      const int Pn = h.n_owned;
+      const bool with_seeds = PASS == 1 && do_bending;
+      // Owned rows: ONE bulk copy per array.  The copy engine wants 16-byte aligned addresses and sizes; a row is 24
+      // (40) bytes, so the copy starts at the even row v_lo - shift and covers an even number of rows; the consumers
+      // address local vertex i at row shift + i of the buffer.  A last odd row travels with the halo rows.
+      const int shift = h.v_lo & 1;
+      const int n_bulk = dbg_copy ? ((shift + Pn) & ~1) : 0;
+      double* pos = reinterpret_cast<double*>(in + P::oPos) + 3 * shift;
+      double* seed = reinterpret_cast<double*>(in + P::oSeed) + kSeedStride * shift;
       if (lane == 0) {
         PatchHdrS* hs = reinterpret_cast<PatchHdrS*>(in + P::oHdr);
         hs->v_lo = h.v_lo; hs->n_owned = h.n_owned; hs->n_halo = h.n_halo; hs->n_rounds = h.n_rounds;
         hs->n_slots = n_slots; hs->halo_off = h.halo_off; hs->slot_off = h.slot_off;
-      }
-      const int Pn = h.n_owned;
-      {  // level 1: records (16-byte copies: slot_off and n_slots are multiples of 32), halo ids, owned rows
-        const FacetRec* src = a.recs + h.slot_off;
-        for (int k = lane; k < (n_slots >> 1); k += 32) cp_async16(recs + 2 * k, src + 2 * k);
-        const int32_t* hsrc = a.halo_ids + h.halo_off;
-        for (int k = lane; k < h.n_halo; k += 32) cp_async4(ids + k, hsrc + k);
-        const double* prow = a.pos + size_t(h.v_lo) * 3;
-        for (int i = lane; i < Pn; i += 32) {
-          cp_async8(pos + i, prow + 3 * i);
-          cp_async8(pos + kPatchLocalCap + i, prow + 3 * i + 1);
-          cp_async8(pos + 2 * kPatchLocalCap + i, prow + 3 * i + 2);
-        }
-        if (PASS == 1 && do_bending) {
-          const double* srow = a.seeds + size_t(h.v_lo) * kSeedStride;
-          for (int i = lane; i < Pn; i += 32) {
-#pragma unroll
-            for (int c = 0; c < kSeedStride; ++c) cp_async8(seed + c * kPatchLocalCap + i, srow + kSeedStride * i + c);
-          }
+        const unsigned rec_bytes = unsigned(n_slots) * unsigned(sizeof(FacetRec));   // n_slots is a multiple of 32
+        const unsigned tx = rec_bytes + unsigned(n_bulk) * (with_seeds ? 64u : 24u);
+        // release (the header is visible to whoever sees the phase complete) + the bytes the copy engine will deliver
+        mbar_arrive_expect_tx(&bar_full[b], tx);
+        if (rec_bytes) bulk_copy(recs, a.recs + h.slot_off, rec_bytes, &bar_full[b]);
+        if (n_bulk) {
+          const size_t g0 = size_t(h.v_lo - shift);
+          bulk_copy(in + P::oPos, a.pos + g0 * 3, unsigned(n_bulk) * 24u, &bar_full[b]);
+          if (with_seeds) bulk_copy(in + P::oSeed, a.seeds + g0 * kSeedStride, unsigned(n_bulk) * 40u, &bar_full[b]);
         }
       }
-      cp_async_wait_all();
-      __syncwarp();
-      // level 2: halo rows
-      for (int k = lane; k < h.n_halo; k += 32) {
-        const size_t row = size_t(ids[k]);
-        const int i = Pn + k;
+      auto stage_row = [&](int i, size_t row) {  // one vertex row with 8-byte asynchronous copies
         const double* prow = a.pos + row * 3;
-        cp_async8(pos + i, prow);
-        cp_async8(pos + kPatchLocalCap + i, prow + 1);
-        cp_async8(pos + 2 * kPatchLocalCap + i, prow + 2);
-        if (PASS == 1 && do_bending) {
+        cp_async8(pos + 3 * i, prow);
+        cp_async8(pos + 3 * i + 1, prow + 1);
+        cp_async8(pos + 3 * i + 2, prow + 2);
+        if (with_seeds) {
           const double* srow = a.seeds + row * kSeedStride;
 #pragma unroll
-          for (int c = 0; c < kSeedStride; ++c) cp_async8(seed + c * kPatchLocalCap + i, srow + c);
+          for (int c = 0; c < kSeedStride; ++c) cp_async8(seed + kSeedStride * i + c, srow + c);
         }
-      }
+      };
+      // halo rows (gathered by id) and the owned rows the bulk copy did not cover
+      for (int k = lane; dbg_copy && k < h.n_halo; k += 32) stage_row(Pn + k, size_t(ids[k]));
+      for (int i = n_bulk - shift + lane; dbg_copy && i < Pn; i += 32) stage_row(i, size_t(h.v_lo) + i);
       if (has_boundary || do_tilt) {  // flags (int32) and |t|^2 ride the same asynchronous copies
         int32_t* bf = has_boundary ? bfl_base + size_t(b) * kPatchLocalCap : nullptr;
         double* t2 = do_tilt ? t2_base + size_t(b) * kPatchLocalCap : nullptr;
@@ -395,9 +451,14 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
           if (t2) cp_async8(t2 + Pn + k, a.tilt_sq + row);
         }
       }
-      cp_async_wait_all();
-      mbar_arrive(&bar_full[b]);
+      cp_async_arrive_on(&bar_full[b]);   // one arrival per lane, when this lane's row copies have landed
+      cp_async_commit();
+      cp_async_wait_but_one();  // the ids of patch j+1 have landed; the bulk copies of patch j stay in flight
+      __syncwarp();
+      h_cur = h_n1; slots_cur = slots_n1;
+      h_n1 = h_n2; slots_n1 = slots_n2;
     }
+    cp_async_wait_all();
     return;
   }
 
@@ -432,6 +493,12 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
         const size_t row = size_t(hs.v_lo) + i;
 #ifdef MS_SELF_CHECK
         if (s_row_lock[b][i] != 0) self_check_fail(a, 2);
+#endif
+#ifdef MS_DEBUG_VARIANTS
+        if (a.debug & 16) {  // 16: the epilogue only clears the accumulators
+          for (int c = 0; c < P::kAccRows; ++c) acc[c * kACap + i] = 0.0;
+          continue;
+        }
 #endif
         if (PASS == 0) {
           const double kap = (!FAST && a.kappa) ? a.kappa[row] : a.kappa_u;
@@ -489,7 +556,13 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
     const int grp = tid / T, lane = tid - grp * T;
     const int bar_mine = 1 + grp, bar_next = 1 + (grp + 1 == G ? 0 : grp + 1);
     const int ring = 2 * T;
-    const bool use_ring = G > 1;
+#ifdef MS_DEBUG_VARIANTS  // timing experiments (libms_b200_dbg.so): parts of the loop switched off, results wrong
+    const int dbg = a.debug;
+#else
+    constexpr int dbg = 0;
+#endif
+    const bool use_ring = G > 1 && !(dbg & 1);
+    const bool dbg_sync = !(dbg & 1), dbg_acc = !(dbg & 2), dbg_compute = !(dbg & 4);
     if (use_ring && grp == G - 1) named_arrive(1, ring);  // group 0 owns the first token
     int t_rel = grp;   // my next round, relative to the first round of the current patch
     int64_t turns_done = 0;
@@ -509,14 +582,14 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
       LocalA la;
       LocalB lb;
       if (PASS == 0) {
-        la.pos = reinterpret_cast<const double*>(in + P::oPos);
+        la.pos = reinterpret_cast<const double*>(in + P::oPos) + 3 * (hs.v_lo & 1);
         la.bfl = has_boundary ? bfl_base + size_t(b) * kPatchLocalCap : nullptr;
         la.t2 = do_tilt ? t2_base + size_t(b) * kPatchLocalCap : nullptr;
         la.acc = acc;
         la.P = Pn;
       } else {
-        lb.pos = reinterpret_cast<const double*>(in + P::oPos);
-        lb.seed = reinterpret_cast<const double*>(in + P::oSeed);
+        lb.pos = reinterpret_cast<const double*>(in + P::oPos) + 3 * (hs.v_lo & 1);
+        lb.seed = reinterpret_cast<const double*>(in + P::oSeed) + kSeedStride * (hs.v_lo & 1);
         lb.bfl = has_boundary ? bfl_base + size_t(b) * kPatchLocalCap : nullptr;
         lb.t2 = do_tilt ? t2_base + size_t(b) * kPatchLocalCap : nullptr;
         lb.acc = acc;
@@ -532,30 +605,30 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
         const bool valid = (rec.flags & REC_VALID) != 0;
         if (PASS == 0) {
           CornerA ca;
-          if (valid) {
+          if (valid && dbg_compute) {
             const double gam = slot_gamma ? slot_gamma[slot] : a.gamma_u;
             ca = facet_compute_a(ST, rec, gam, la, modules, a.k_tilt, sums);
           }
-          if (use_ring) named_sync(bar_mine, ring); else named_sync(1, T);
+          if (use_ring) named_sync(bar_mine, ring); else if (dbg_sync) named_sync(1, T);
 #ifdef MS_SELF_CHECK
           if (valid && do_bending) self_check_lock(a, b, rec, Pn, Pn + hs.n_halo, true);
 #endif
-          if (valid && do_bending) facet_accumulate_a(ST, rec, ca, la, modules);
+          if (valid && do_bending && dbg_acc) facet_accumulate_a(ST, rec, ca, la, modules);
 #ifdef MS_SELF_CHECK
           if (valid && do_bending) self_check_lock(a, b, rec, Pn, Pn + hs.n_halo, false);
 #endif
         } else {
           FacetOutB out;
-          if (valid) {
+          if (valid && dbg_compute) {
             const double gam = slot_gamma ? slot_gamma[slot] : a.gamma_u;
             out = do_bending ? facet_compute_b<true>(ST, rec, gam, lb, modules, flags, a.k_tilt, scalars_here, sums)
                              : facet_compute_b<false>(ST, rec, gam, lb, modules, flags, a.k_tilt, scalars_here, sums);
           }
-          if (use_ring) named_sync(bar_mine, ring); else named_sync(1, T);
+          if (use_ring) named_sync(bar_mine, ring); else if (dbg_sync) named_sync(1, T);
 #ifdef MS_SELF_CHECK
           if (valid) self_check_lock(a, b, rec, Pn, Pn + hs.n_halo, true);
 #endif
-          if (valid) facet_accumulate_b(ST, rec, out, lb, do_volume, do_tilt);
+          if (valid && dbg_acc) facet_accumulate_b(ST, rec, out, lb, do_volume, do_tilt);
 #ifdef MS_SELF_CHECK
           if (valid) self_check_lock(a, b, rec, Pn, Pn + hs.n_halo, false);
 #endif

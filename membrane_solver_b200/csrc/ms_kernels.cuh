@@ -99,6 +99,8 @@ struct PatchLaunch {
   double* a_eff;      // nv
   double* e_vertex;   // nv   per-vertex bending energy (bending.compute_energy_array)
   PatchFinalize fin;
+  int32_t debug;      // timing experiments only (MS_DEBUG_VARIANT; results are wrong): 1 no token ring, 2 no
+                      // accumulation, 4 no per-facet compute
   int* self_check;    // -DMS_SELF_CHECK builds: three violation counters (device), else unused
 };
 

@@ -3,9 +3,12 @@
 // compile-time strides) and the test-only host emulator (tests/emul/emul.cpp, heap
 // arrays, run-time strides) execute the very same code.
 //
-// Layout of a patch-local array family: component k of local vertex i lives at
-// base[k * stride + i].  With a compile-time stride every component of a vertex is
-// reached from ONE address register plus an immediate offset.
+// Layouts.  Patch-local INPUTS (positions, seeds) are arrays of structures, exactly as they lie in global
+// memory: row i of the positions at base[3 i .. 3 i + 2], of the seeds at base[5 i .. 5 i + 4] -- so the owned
+// rows of a patch arrive with ONE bulk copy per array, and a vertex is reached from one address register plus
+// immediate offsets.  A half-warp that gathers rows with distinct indices mod 16 is free of bank conflicts
+// (64-bit accesses, 3 and 5 are coprime to 16).  ACCUMULATORS are structure-of-arrays: component k of owned vertex
+// i at base[k * stride + i].
 #pragma once
 
 #include "../../include/ms_b200.h"
@@ -46,6 +49,8 @@ MS_HD d3 ld3(const double* p, int i) { return make_d3(p[3 * i], p[3 * i + 1], p[
 MS_HD d3 ld3s(const double* p, int stride, int i) {
   return make_d3(p[i], p[stride + i], p[2 * stride + i]);
 }
+// row i of a patch-local (n,3) input array
+MS_HD d3 ld3a(const double* p, int i) { return make_d3(p[3 * i], p[3 * i + 1], p[3 * i + 2]); }
 MS_HD void add3s(double* p, int stride, int i, d3 v) {
   p[i] += v.x;
   p[stride + i] += v.y;
@@ -59,7 +64,7 @@ MS_HD void add3s(double* p, int stride, int i, d3 v) {
 MS_HD int acc_row(int local, int P, int A) { return local < P ? local : (A - kDumpRows) + (local & (kDumpRows - 1)); }
 
 struct LocalA {
-  const double* pos;   // 3 x L
+  const double* pos;   // L x 3 (rows)
   const int32_t* bfl;  // L  boundary flags; nullptr = closed mesh (no boundary vertex)
   const double* t2;    // L  |tilt|^2 (tilt module only)
   double* acc;         // 5 x A: K.x K.y K.z A_vor A_eff
@@ -70,7 +75,7 @@ struct LocalA {
 template <class S>
 MS_HD CornerA facet_compute_a(const S& st, FacetRec rec, double gam, const LocalA& s, uint32_t modules,
                               double k_tilt, double* sums) {
-  const d3 v0 = ld3s(s.pos, st.L, rec.a), v1 = ld3s(s.pos, st.L, rec.b), v2 = ld3s(s.pos, st.L, rec.c);
+  const d3 v0 = ld3a(s.pos, rec.a), v1 = ld3a(s.pos, rec.b), v2 = ld3a(s.pos, rec.c);
   const FacetGeom g = facet_geom(v0, v1, v2);
   if (rec.flags & REC_PRIMARY) {
     const double T = 0.5 * g.S;
@@ -133,7 +138,7 @@ MS_HD d3 vertex_normal_scan(const S& st, const FacetRec* recs, int n_slots, cons
     const FacetRec rec = recs[k];
     if (!(rec.flags & REC_VALID)) continue;
     if (rec.a != i && rec.b != i && rec.c != i) continue;
-    const d3 v0 = ld3s(pos, st.L, rec.a), v1 = ld3s(pos, st.L, rec.b), v2 = ld3s(pos, st.L, rec.c);
+    const d3 v0 = ld3a(pos, rec.a), v1 = ld3a(pos, rec.b), v2 = ld3a(pos, rec.c);
     n = n + cross(v1 - v0, v2 - v0);
   }
   const double m = sqrt(dot(n, n));
@@ -154,8 +159,8 @@ MS_HD VertexSeed vertex_body_a(const S& st, int i, const LocalA& s, bool boundar
 }
 
 struct LocalB {
-  const double* pos;   // 3 x L
-  const double* seed;  // 5 x L   bending only: fK.x fK.y fK.z fA_eff fA_vor
+  const double* pos;   // L x 3 (rows)
+  const double* seed;  // L x 5 (rows)   bending only: fK.x fK.y fK.z fA_eff fA_vor
   const int32_t* bfl;  // L       bending only; nullptr = closed mesh
   const double* t2;    // L       tilt only
   double* acc;         // 6 x A: shape gradient (3), 6 dV/dx (3)
@@ -175,7 +180,7 @@ template <bool BENDING, class S>
 MS_HD FacetOutB facet_compute_b(const S& st, FacetRec rec, double gam, const LocalB& s, uint32_t modules,
                                 uint32_t flags, double k_tilt, bool scalars_here, double* sums) {
   FacetOutB o;
-  const d3 v0 = ld3s(s.pos, st.L, rec.a), v1 = ld3s(s.pos, st.L, rec.b), v2 = ld3s(s.pos, st.L, rec.c);
+  const d3 v0 = ld3a(s.pos, rec.a), v1 = ld3a(s.pos, rec.b), v2 = ld3a(s.pos, rec.c);
   const FacetGeom g = facet_geom(v0, v1, v2);
   const double T = 0.5 * g.S;
   const bool primary = (rec.flags & REC_PRIMARY) != 0;
@@ -198,9 +203,12 @@ MS_HD FacetOutB facet_compute_b(const S& st, FacetRec rec, double gam, const Loc
   BendIn b;
   if (BENDING) {
     const double* q = s.seed;
-    b.f0 = ld3s(q, st.L, rec.a); b.fe0 = q[3 * st.L + rec.a]; b.fv0 = q[4 * st.L + rec.a];
-    b.f1 = ld3s(q, st.L, rec.b); b.fe1 = q[3 * st.L + rec.b]; b.fv1 = q[4 * st.L + rec.b];
-    b.f2 = ld3s(q, st.L, rec.c); b.fe2 = q[3 * st.L + rec.c]; b.fv2 = q[4 * st.L + rec.c];
+    const double* q0 = q + kSeedStrideBody * rec.a;
+    const double* q1 = q + kSeedStrideBody * rec.b;
+    const double* q2 = q + kSeedStrideBody * rec.c;
+    b.f0 = make_d3(q0[0], q0[1], q0[2]); b.fe0 = q0[3]; b.fv0 = q0[4];
+    b.f1 = make_d3(q1[0], q1[1], q1[2]); b.fe1 = q1[3]; b.fv1 = q1[4];
+    b.f2 = make_d3(q2[0], q2[1], q2[2]); b.fe2 = q2[3]; b.fv2 = q2[4];
     if (s.bfl) {
       b.i0 = !s.bfl[rec.a]; b.i1 = !s.bfl[rec.b]; b.i2 = !s.bfl[rec.c];
     } else {

@@ -79,7 +79,7 @@ int emul_eval(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* is_boun
       std::vector<int32_t> bfl(size_t(L), 0);
       for (int j = 0; j < L; ++j) {
         const int row = local_row(pk, h, j);
-        for (int k = 0; k < 3; ++k) lpos[size_t(k) * L + j] = pos[3 * size_t(row) + k];
+        for (int k = 0; k < 3; ++k) lpos[3 * size_t(j) + k] = pos[3 * size_t(row) + k];
         bfl[size_t(j)] = is_boundary ? is_boundary[row] : 0;
         if (do_tilt) {
           const double* t = tilts + 3 * size_t(row);
@@ -150,9 +150,9 @@ int emul_eval(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t* is_boun
       std::vector<int32_t> bfl(size_t(L), 0);
       for (int j = 0; j < L; ++j) {
         const int row = local_row(pk, h, j);
-        for (int k = 0; k < 3; ++k) lpos[size_t(k) * L + j] = pos[3 * size_t(row) + k];
+        for (int k = 0; k < 3; ++k) lpos[3 * size_t(j) + k] = pos[3 * size_t(row) + k];
         for (int k = 0; k < kSeedStrideBody; ++k)
-          lseed[size_t(k) * L + j] = seed_store[size_t(row) * kSeedStrideBody + k];
+          lseed[size_t(kSeedStrideBody) * j + k] = seed_store[size_t(row) * kSeedStrideBody + k];
         bfl[size_t(j)] = is_boundary ? is_boundary[row] : 0;
         if (do_tilt) {
           const double* t = tilts + 3 * size_t(row);
