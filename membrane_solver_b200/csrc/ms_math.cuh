@@ -165,10 +165,15 @@ struct VertexSeed {
 MS_HD VertexSeed vertex_stage(d3 K, double a_vor, double a_eff, double kappa, double c0,
                               bool boundary, bool willmore, d3 normal, double tau_add) {
   VertexSeed s;
+  // one reciprocal square root and one reciprocal serve |K|, 1/|K|, H and A_eff / A_vor (the vertex stage runs on
+  // the epilogue warps next to the consumers: every fp64 division it saves is issue bandwidth for them)
   const double safe = fmax(a_vor, 1.0e-12);
-  const double kmag = sqrt(dot(K, K));
-  const double H = kmag / (2.0 * safe);
-  const double ratio = (safe > 1.0e-15) ? a_eff / safe : 0.0;
+  const double k2 = dot(K, K);
+  const double rk = (k2 > 1.0e-30) ? recip_sqrt(k2) : 0.0;   // |K| > 1e-15
+  const double kmag = k2 * rk;
+  const double inv_safe = 1.0 / safe;
+  const double H = 0.5 * (kmag * inv_safe);
+  const double ratio = a_eff * inv_safe;                // safe >= 1e-12 > 1e-15 always
   double scale;
   if (!willmore) {
     const double term = boundary ? 0.0 : (2.0 * H - c0) + tau_add;
@@ -183,7 +188,7 @@ MS_HD VertexSeed vertex_stage(d3 K, double a_vor, double a_eff, double kappa, do
     s.fAe = kappa * (He * He);
     s.fAv = -2.0 * kappa * (He * He) * ratio;
   }
-  d3 dir = (kmag > 1.0e-15) ? (1.0 / kmag) * K : normal;
+  d3 dir = (k2 > 1.0e-30) ? rk * K : normal;
   s.fK = scale * dir;
   s.H = H;
   return s;

@@ -153,7 +153,7 @@ MS_HD VertexSeed vertex_body_a(const S& st, int i, const LocalA& s, bool boundar
                                double c0, bool willmore) {
   const d3 K = ld3s(s.acc, st.A, i);
   d3 n = make_d3(0, 0, 0);
-  if (!(sqrt(dot(K, K)) > 1.0e-15) && !boundary) n = normal_of(i);
+  if (!(dot(K, K) > 1.0e-30) && !boundary) n = normal_of(i);
   return vertex_stage(K, s.acc[3 * st.A + i], s.acc[4 * st.A + i], kappa, willmore ? 0.0 : c0, boundary,
                       willmore, n, 0.0);
 }

@@ -6,7 +6,7 @@
 #   make -C membrane_solver_b200/csrc dbg && bash tools/loop_decomposition.sh > gpurun_out/loop_decomposition.txt
 export MS_B200_LIB=$PWD/membrane_solver_b200/libms_b200_dbg.so
 for v in ${VARIANTS:-0 1 2 3 4 5 6 7 8 16 24 31}; do
-  MS_DEBUG_VARIANT=$v python bench.py --steps 10 --warmup 3 --no-cpu --no-parity --no-full-mesh --strong-facets 0 2>/dev/null |
+  MS_DEBUG_VARIANT=$v timeout 90 python bench.py --steps 10 --warmup 3 --no-cpu --no-parity --no-full-mesh --strong-facets 0 2>/dev/null |
     python -c "
 import sys, json
 d = json.loads([l for l in sys.stdin if l.startswith('{')][-1])
