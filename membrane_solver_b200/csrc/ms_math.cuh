@@ -55,6 +55,16 @@ constexpr double kAreaClamp = 1.0e-12;     // curvature.py:271: 2A = max(|e1 x e
 constexpr double kCotGradEps = 1.0e-15;    // bending_derivatives.py:62: grad cot = 0 if S <= 1e-15
 constexpr double kP1Clamp = 1.0e-20;       // tilt_operators.py:164: max(|n|^2, 1e-20)
 
+// correctly rounded reciprocal: the device intrinsic is the short sequence (MUFU.RCP64H + Newton steps) without the
+// general division's slow path
+MS_HD double recip(double x) {
+#if defined(__CUDA_ARCH__)
+  return __drcp_rn(x);
+#else
+  return 1.0 / x;
+#endif
+}
+
 // Geometry every per-facet routine starts from.
 struct FacetGeom {
   d3 e0, e1, e2, n;
@@ -171,7 +181,7 @@ MS_HD VertexSeed vertex_stage(d3 K, double a_vor, double a_eff, double kappa, do
   const double k2 = dot(K, K);
   const double rk = (k2 > 1.0e-30) ? recip_sqrt(k2) : 0.0;   // |K| > 1e-15
   const double kmag = k2 * rk;
-  const double inv_safe = 1.0 / safe;
+  const double inv_safe = recip(safe);
   const double H = 0.5 * (kmag * inv_safe);
   const double ratio = a_eff * inv_safe;                // safe >= 1e-12 > 1e-15 always
   double scale;
