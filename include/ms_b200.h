@@ -310,6 +310,17 @@ MS_API int ms_ctx_halo_error(ms_ctx* ctx, int32_t* error);
  * all-reduce of the partitioned sweep (BASELINE.json north_star; no counterpart in the single-process reference).
  * The kernels wait for flags of peers, so the ranks must run concurrently: one process per GPU. */
 MS_API int ms_ctx_eval_partition(ms_ctx* ctx, const ms_eval_opts* opts, int32_t exchange_positions);
+/* PUSH form of the same transport (optional; ms_ctx_eval_partition uses it once the targets are set; measured no faster
+ * than the pull form on 2 x B200, PartitionedMesh enables it with MS_HALO_PUSH=1): for each of the n rows of
+ * this rank that another rank lists as a ghost -- that rank's slot, the row here (owned), the row in that rank's
+ * arrays.  The owner then STORES its rows into the peers' ghost slots (posted NVLink writes) and raises its arrival
+ * word in their flag blocks; receivers poll local memory only (inside the patch kernel, before its first patch), and
+ * the 12 evaluation scalars travel the same way from the last CTA of the last pass.  Needs every peer array and flag
+ * block opened (ms_ctx_peer_open) and ms_ctx_set_rank_slot; at most 16 ranks. */
+MS_API int ms_ctx_set_push_targets(ms_ctx* ctx, int32_t n, const int32_t* dst_slot, const int32_t* src_row,
+                                   const int32_t* dst_row);
+/* one push of MS_ARR_POSITIONS / MS_ARR_TRIAL (flag_index MS_FLAG_POSITIONS) or MS_ARR_SEEDS (MS_FLAG_SEEDS) */
+MS_API int ms_ctx_halo_push(ms_ctx* ctx, int32_t which, int32_t flag_index);
 
 /* One evaluation with everything resident: pass A (+ pass B when want_grad); the last CTA of the last pass adds
  * up the per-CTA sums in fixed order and writes the scalars and the KKT / penalty coefficient (no reduce or

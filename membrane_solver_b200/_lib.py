@@ -165,6 +165,8 @@ SIGNATURES = {
     "ms_ctx_allreduce_scalars": (ctypes.c_int, [_V, _i32]),
     "ms_ctx_halo_error": (ctypes.c_int, [_V, _I]),
     "ms_ctx_eval_partition": (ctypes.c_int, [_V, ctypes.POINTER(EvalOpts), _i32]),
+    "ms_ctx_set_push_targets": (ctypes.c_int, [_V, _i32, _I, _I, _I]),
+    "ms_ctx_halo_push": (ctypes.c_int, [_V, _i32, _i32]),
     "ms_ctx_make_trial": (ctypes.c_int, [_V, _f64]),
     "ms_ctx_accept_trial": (ctypes.c_int, [_V]),
     "ms_ctx_dots": (ctypes.c_int, [_V]),

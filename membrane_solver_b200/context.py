@@ -429,6 +429,15 @@ class DeviceMesh:
     def allreduce_scalars(self, count: int = 12) -> None:
         L.check(self._lib.ms_ctx_allreduce_scalars(self._h, int(count)))
 
+    def set_push_targets(self, dst_slot, src_row, dst_row) -> None:
+        a, b, c = (np.ascontiguousarray(x, dtype=np.int32) for x in (dst_slot, src_row, dst_row))
+        if not (a.shape == b.shape == c.shape):
+            raise ValueError("push target arrays must have the same length")
+        L.check(self._lib.ms_ctx_set_push_targets(self._h, int(a.size), L.iptr(a), L.iptr(b), L.iptr(c)))
+
+    def halo_push(self, which: int, flag: int) -> None:
+        L.check(self._lib.ms_ctx_halo_push(self._h, int(which), int(flag)))
+
     def eval_partition(self, opts, exchange_positions: bool = True) -> None:
         """One partitioned evaluation with the transport folded into the compute launches (5 launches)."""
         L.check(self._lib.ms_ctx_eval_partition(self._h, ctypes.byref(opts), int(bool(exchange_positions))))

@@ -159,6 +159,11 @@ struct ms_ctx {
     DevBuf<const double*> d_pos, d_trial, d_seeds;
     DevBuf<unsigned long long*> d_flags;
     DevBuf<int32_t> d_owner, d_row;
+    // push transport: for every row another rank lists as a ghost -- that rank's slot, the row here, the row there
+    DevBuf<int32_t> d_push_slot, d_push_src, d_push_dst;
+    int32_t n_push = 0, my_slot = -1;
+    uint64_t push_mask = 0;    // ranks this one pushes to == ranks it receives from (1-ring ghosts are symmetric)
+    bool push_ready = false;
     int32_t n_slots = 0;
     bool tables_current = false;
   } peers;
@@ -1631,6 +1636,7 @@ int ms_ctx_set_rank_slot(ms_ctx* c, int32_t slot, int32_t n_slots) {
     t.flags.resize(need, nullptr);
   }
   t.flags[size_t(slot)] = c->d_flag_words.p;  // this rank's own block takes part in the all-reduce
+  t.my_slot = slot;
   t.n_slots = n_slots;
   t.tables_current = false;
   return 0;
@@ -1662,6 +1668,79 @@ int ms_ctx_halo_error(ms_ctx* c, int32_t* error) {
   return 0;
 }
 
+int ms_ctx_set_push_targets(ms_ctx* c, int32_t n, const int32_t* dst_slot, const int32_t* src_row, const int32_t* dst_row) {
+  if (int rc = check_ctx(c, true)) return rc;
+  ms_ctx::PeerTable& t = c->peers;
+  if (n < 0 || (n > 0 && (!dst_slot || !src_row || !dst_row))) return fail(-1, "bad push target arguments");
+  if (t.n_slots <= 0 || t.my_slot < 0) return fail(-4, "ms_ctx_set_rank_slot has not been called");
+  if (t.n_slots > ms::kPushMaxRanks) return fail(-1, "the push transport holds up to 16 ranks");
+  uint64_t mask = 0;
+  for (int32_t i = 0; i < n; ++i) {
+    if (dst_slot[i] < 0 || dst_slot[i] >= t.n_slots || dst_slot[i] == t.my_slot || src_row[i] < 0 ||
+        src_row[i] >= c->n_owned || dst_row[i] < 0)
+      return fail(-1, "push target out of range");
+    mask |= 1ull << dst_slot[i];
+  }
+  if (int rc = t.d_push_slot.ensure(size_t(n) + 1)) return rc;
+  if (int rc = t.d_push_src.ensure(size_t(n) + 1)) return rc;
+  if (int rc = t.d_push_dst.ensure(size_t(n) + 1)) return rc;
+  if (n) {
+    CU(cudaMemcpy(t.d_push_slot.p, dst_slot, size_t(n) * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(t.d_push_src.p, src_row, size_t(n) * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(t.d_push_dst.p, dst_row, size_t(n) * sizeof(int32_t), cudaMemcpyHostToDevice));
+  }
+  t.n_push = n;
+  t.push_mask = mask;
+  t.push_ready = true;
+  return 0;
+}
+
+// push this rank's rows of `which` into the ghost slots of the ranks that list them and raise its arrival word there
+static int halo_push(ms_ctx* c, int32_t which, int kind) {
+  ms_ctx::PeerTable& t = c->peers;
+  if (!t.push_ready) return fail(-4, "ms_ctx_set_push_targets has not been called");
+  if (int rc = peer_tables(c)) return rc;
+  if (!c->d_ticket.p) {
+    if (int rc = c->d_ticket.ensure(4)) return rc;
+    CU(cudaMemsetAsync(c->d_ticket.p, 0, 4 * sizeof(unsigned int), c->stream));
+  }
+  double* const* table = nullptr;
+  int width = 3;
+  switch (which) {
+    case MS_ARR_POSITIONS: table = const_cast<double* const*>(reinterpret_cast<const double* const*>(t.d_pos.p)); break;
+    case MS_ARR_TRIAL: table = const_cast<double* const*>(reinterpret_cast<const double* const*>(t.d_trial.p)); break;
+    case MS_ARR_SEEDS:
+      table = const_cast<double* const*>(reinterpret_cast<const double* const*>(t.d_seeds.p));
+      width = ms::kSeedStride;
+      break;
+    default: return fail(-1, "only positions, trial positions and seeds travel through the halo");
+  }
+  int64_t len = 0;
+  const double* src = array_ptr(c, which, &len);
+  if (!src) return fail(-4, "the local array does not exist");
+  const unsigned long long epoch = ++c->flag_epoch[kind];
+  CU(ms::launch_halo_push(t.n_push, width, src, table, t.d_push_slot.p, t.d_push_src.p, t.d_push_dst.p, t.d_flags.p,
+                          t.n_slots, t.push_mask, t.my_slot, kind, epoch, c->d_ticket.p + 1, c->stream));
+  return 0;
+}
+
+int ms_ctx_halo_push(ms_ctx* c, int32_t which, int32_t flag_index) {
+  NvtxRange range("ms_b200 halo push");
+  if (int rc = check_ctx(c, true)) return rc;
+  if (flag_index != MS_FLAG_POSITIONS && flag_index != MS_FLAG_SEEDS)
+    return fail(-1, "flag index must be MS_FLAG_POSITIONS or MS_FLAG_SEEDS");
+  if (int rc = ensure_flag_words(c)) return rc;
+  return halo_push(c, which, flag_index);
+}
+
+// the patch kernel waits for the pushed rows of `kind` before it stages its first patch
+static void attach_wait(ms_ctx* c, ms::PatchLaunch& a, int kind) {
+  a.wait_flags = c->d_flag_words.p + ms::kPushFlagBase + 64 * kind;
+  a.wait_epoch = c->flag_epoch[kind];
+  a.wait_mask = c->peers.push_mask;
+  a.wait_error = c->d_halo_error.p;
+}
+
 // One evaluation of this rank's partition with the transport folded into the compute launches (peer memory):
 //   [signal + pull positions] -> pass A (its last CTA raises the seed flag) -> [pull seeds] -> pass B (its last
 //   CTA reduces the per-CTA rows and publishes the local scalars) -> gather (rank-order sum) + KKT coefficient
@@ -1682,14 +1761,28 @@ int ms_ctx_eval_partition(ms_ctx* c, const ms_eval_opts* o, int32_t exchange_pos
   const bool ran_a = bending || !o->want_grad;
   const bool run_b = o->want_grad || (o->want_tilt_grad && (o->modules & MS_MOD_TILT));
   if (!o->want_grad && run_b) return fail(-1, "tilt-only evaluations use the unfused sequence");
-  if (exchange_positions)
-    if (int rc = halo_launch(c, o->use_trial ? MS_ARR_TRIAL : MS_ARR_POSITIONS, MS_FLAG_POSITIONS, true)) return rc;
+  const bool push = t.push_ready;   // PUSH: owners store into the ghost slots, receivers poll local words only
+  bool wait_positions = false;
+  if (exchange_positions) {
+    if (push) {
+      if (int rc = halo_push(c, o->use_trial ? MS_ARR_TRIAL : MS_ARR_POSITIONS, MS_FLAG_POSITIONS)) return rc;
+      wait_positions = true;
+    } else if (int rc = halo_launch(c, o->use_trial ? MS_ARR_TRIAL : MS_ARR_POSITIONS, MS_FLAG_POSITIONS, true)) {
+      return rc;
+    }
+  }
   const unsigned long long reduce_epoch = ++c->flag_epoch[2];
   auto publish = [&](ms::PatchLaunch& a) -> int {
     if (int rc = attach_finalize(c, o, a)) return rc;
-    a.fin.constraint_mode = -2;  // the coefficient needs the GLOBAL sums: k_allreduce_gather_coef
-    a.fin.publish_words = c->d_flag_words.p;
+    a.fin.constraint_mode = -2;  // the coefficient needs the GLOBAL sums: k_allreduce_gather_coef / _local_coef
     a.fin.publish_epoch = reduce_epoch;
+    if (push) {
+      a.fin.push_words = t.d_flags.p;
+      a.fin.push_slots = t.n_slots;
+      a.fin.push_my_slot = t.my_slot;
+    } else {
+      a.fin.publish_words = c->d_flag_words.p;
+    }
     return 0;
   };
   if (ran_a) {
@@ -1699,23 +1792,32 @@ int ms_ctx_eval_partition(ms_ctx* c, const ms_eval_opts* o, int32_t exchange_pos
     c->ran_pass_a = true;
     if (!o->want_grad) {
       if (int rc = publish(a)) return rc;
-    } else if (bending) {  // ticket without a reduction: the last CTA raises the seed flag
+    } else if (bending && !push) {  // ticket without a reduction: the last CTA raises the seed flag
       if (int rc = attach_finalize(c, o, a)) return rc;
       a.fin.scalars = nullptr;
       a.fin.signal_flag = c->d_flag_words.p + MS_FLAG_SEEDS;
       a.fin.signal_epoch = ++c->flag_epoch[MS_FLAG_SEEDS];
     }
+    if (wait_positions) attach_wait(c, a, MS_FLAG_POSITIONS);
+    wait_positions = false;
     CU(ms::launch_pass_a(a, c->stream));
   } else {
     c->ran_pass_a = false;
   }
   if (o->want_grad) {
-    if (bending)
-      if (int rc = halo_launch(c, MS_ARR_SEEDS, MS_FLAG_SEEDS, false)) return rc;
+    if (bending) {
+      if (push) {
+        if (int rc = halo_push(c, MS_ARR_SEEDS, MS_FLAG_SEEDS)) return rc;
+      } else if (int rc = halo_launch(c, MS_ARR_SEEDS, MS_FLAG_SEEDS, false)) {
+        return rc;
+      }
+    }
     ms::PatchLaunch a;
     if (int rc = fill_launch(c, o, a)) return rc;
     a.partials = c->d_partials_b.p;
     c->proj.active = false;
+    if (push && bending) attach_wait(c, a, MS_FLAG_SEEDS);
+    else if (wait_positions) attach_wait(c, a, MS_FLAG_POSITIONS);   // surface / volume only: pass B is the first kernel
     if ((o->modules & MS_MOD_TILT) && !a.tilt_grad) {
       if (int rc = ensure_array(c, MS_ARR_TILT_GRAD)) return rc;
       a.tilt_grad = c->d_tilt_grad.p;
@@ -1725,9 +1827,14 @@ int ms_ctx_eval_partition(ms_ctx* c, const ms_eval_opts* o, int32_t exchange_pos
   }
   bool use_gc, use_fixed;
   projection_of(c, o, use_gc, use_fixed);
-  CU(ms::launch_allreduce_gather_coef(c->d_scalars.p, 12, t.d_flags.p, t.n_slots, reduce_epoch,
-                                      o->want_grad ? o->constraint_mode : -2, use_gc ? 1 : 0, o->k_vol, o->v_target,
-                                      c->d_halo_error.p, c->stream));
+  if (push)
+    CU(ms::launch_allreduce_local_coef(c->d_scalars.p, 12, c->d_flag_words.p, t.n_slots, reduce_epoch,
+                                       o->want_grad ? o->constraint_mode : -2, use_gc ? 1 : 0, o->k_vol, o->v_target,
+                                       c->d_halo_error.p, c->stream));
+  else
+    CU(ms::launch_allreduce_gather_coef(c->d_scalars.p, 12, t.d_flags.p, t.n_slots, reduce_epoch,
+                                        o->want_grad ? o->constraint_mode : -2, use_gc ? 1 : 0, o->k_vol, o->v_target,
+                                        c->d_halo_error.p, c->stream));
   if (o->want_grad) {
     c->proj.active = use_gc || use_fixed;
     c->proj.use_gc = use_gc;

@@ -347,6 +347,18 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
       mbar_init(&bar_free[b], 32u * unsigned(n_epi_warps));
     }
   }
+  if (a.wait_flags && tid < 64 && ((a.wait_mask >> tid) & 1ull)) {  // push transport: ghost rows in place?
+    const volatile unsigned long long* f = a.wait_flags + tid;
+    const long long t0 = clock64();
+    while (*f < a.wait_epoch) {
+      if (clock64() - t0 > 4000000000LL) {
+        atomicExch(a.wait_error, 1);
+        break;
+      }
+      __nanosleep(100);
+    }
+    __threadfence_system();
+  }
   {  // zero both accumulator buffers (and the tilt area accumulators)
     double* acc0 = reinterpret_cast<double*>(smem + P::oAcc);
     for (int j = tid; j < 2 * P::kAccRows * kACap; j += NC + 64) acc0[j] = 0.0;
@@ -668,7 +680,7 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
   if (a.fin.ticket) {  // the last CTA to get here finalises the evaluation (warp-uniform: a kernel parameter)
     __shared__ int s_last;
     __shared__ double s_part[kFinRows][kPartialStride];
-    const bool to_peers = a.fin.signal_flag || a.fin.publish_words;
+    const bool to_peers = a.fin.signal_flag || a.fin.publish_words || a.fin.push_words;
     if (tid == 0) {
       if (to_peers) __threadfence_system(); else __threadfence();
       s_last = atomicAdd(a.fin.ticket, 1u) == gridDim.x - 1 ? 1 : 0;
@@ -681,6 +693,21 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
         double* slot = reinterpret_cast<double*>(a.fin.publish_words + 8 + 16 * (a.fin.publish_epoch & 1ull));
         if (tid < kPartialStride) slot[tid] = a.fin.scalars[tid];
         __syncthreads();
+      }
+      if (a.fin.push_words) {  // push transport: scalars into this rank's slot of every rank's block, then its word
+        const unsigned long long e = a.fin.publish_epoch;
+        for (int i = tid; i < a.fin.push_slots * kPartialStride; i += NC + 64) {
+          const int s = i / kPartialStride, k = i - s * kPartialStride;
+          double* slot = reinterpret_cast<double*>(a.fin.push_words[s] + kPushScalarBase) +
+                         (16 * int(e & 1ull) + a.fin.push_my_slot) * 16;
+          slot[k] = a.fin.scalars[k];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid < a.fin.push_slots) {
+          *reinterpret_cast<volatile unsigned long long*>(a.fin.push_words[tid] + kPushScalarFlagBase + a.fin.push_my_slot) = e;
+          __threadfence_system();
+        }
       }
       if (tid == 0) {
         *a.fin.ticket = 0u;
@@ -2006,6 +2033,82 @@ cudaError_t launch_halo_pull(int n_ghost, int width, const double* const* peer_b
   const int blocks = (n_ghost * width + 255) / 256;
   k_halo_pull<<<blocks < 64 ? blocks : 64, 256, 0, st>>>(n_ghost, width, peer_base, peer_flag, n_slots, flag_index, epoch,
                                                           owner, row, dst, error);
+  return cudaGetLastError();
+}
+
+// ---- push transport --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_halo_push(int n_rows, int width, const double* __restrict__ src,
+                                                   double* const* __restrict__ peer_base,
+                                                   const int32_t* __restrict__ dst_slot, const int32_t* __restrict__ src_row,
+                                                   const int32_t* __restrict__ dst_row,
+                                                   unsigned long long* const* __restrict__ peer_flags, int n_slots,
+                                                   uint64_t dst_mask, int my_slot, int kind, unsigned long long epoch,
+                                                   unsigned int* ticket) {
+  const int total = n_rows * width;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int g = i / width, k = i - g * width;
+    peer_base[dst_slot[g]][size_t(dst_row[g]) * width + k] = src[size_t(src_row[g]) * width + k];
+  }
+  __threadfence_system();
+  __shared__ int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence_system();
+  if (threadIdx.x == 0) *ticket = 0u;
+  for (int s = threadIdx.x; s < n_slots; s += blockDim.x)
+    if ((dst_mask >> s) & 1ull) {
+      *reinterpret_cast<volatile unsigned long long*>(peer_flags[s] + kPushFlagBase + 64 * kind + my_slot) = epoch;
+    }
+  __threadfence_system();
+}
+
+__global__ void k_allreduce_local_coef(unsigned long long* own_words, int n_slots, int n, unsigned long long epoch,
+                                       double* scalars, int mode, int has_gc, double k_vol, double v_target, int* error) {
+  __shared__ int ok;
+  if (threadIdx.x == 0) ok = 1;
+  __syncthreads();
+  for (int s = threadIdx.x; s < n_slots; s += blockDim.x) {
+    const volatile unsigned long long* f = own_words + kPushScalarFlagBase + s;
+    const long long t0 = clock64();
+    while (*f < epoch) {
+      if (clock64() - t0 > 4000000000LL) {
+        atomicExch(error, 1);
+        ok = 0;
+        break;
+      }
+      __nanosleep(100);
+    }
+  }
+  __syncthreads();
+  if (!ok) return;
+  __threadfence_system();
+  if (int(threadIdx.x) < n) {
+    const volatile double* base = reinterpret_cast<const volatile double*>(own_words + kPushScalarBase);
+    double acc = 0.0;
+    for (int s = 0; s < n_slots; ++s) acc += base[(16 * int(epoch & 1ull) + s) * 16 + threadIdx.x];
+    scalars[threadIdx.x] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && mode != -2) kkt_coefficient(scalars, mode, has_gc, k_vol, v_target);
+}
+
+cudaError_t launch_halo_push(int n_rows, int width, const double* src, double* const* peer_base, const int32_t* dst_slot,
+                             const int32_t* src_row, const int32_t* dst_row, unsigned long long* const* peer_flags,
+                             int n_slots, uint64_t dst_mask, int my_slot, int kind, unsigned long long epoch,
+                             unsigned int* ticket, cudaStream_t st) {
+  int blocks = (n_rows * width + 255) / 256;
+  blocks = blocks < 1 ? 1 : (blocks > 64 ? 64 : blocks);
+  k_halo_push<<<blocks, 256, 0, st>>>(n_rows, width, src, peer_base, dst_slot, src_row, dst_row, peer_flags, n_slots,
+                                      dst_mask, my_slot, kind, epoch, ticket);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_allreduce_local_coef(double* scalars, int n, unsigned long long* own_words, int n_slots,
+                                        unsigned long long epoch, int mode, int has_gc, double k_vol, double v_target,
+                                        int* error, cudaStream_t st) {
+  k_allreduce_local_coef<<<1, 64, 0, st>>>(own_words, n_slots, n, epoch, scalars, mode, has_gc, k_vol, v_target, error);
   return cudaGetLastError();
 }
 

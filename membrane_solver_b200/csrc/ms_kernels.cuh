@@ -62,6 +62,10 @@ struct PatchFinalize {
   unsigned long long signal_epoch;
   unsigned long long* publish_words;  // ... and publish the local scalars into the all-reduce slot of this epoch
   unsigned long long publish_epoch;
+  // push transport: the local scalars go into the slot of this rank in EVERY rank's block (remote stores), then the
+  // arrival word of this rank there is raised
+  unsigned long long* const* push_words;   // flag blocks of all ranks (device table, own block included)
+  int32_t push_slots, push_my_slot;
 };
 
 struct PatchLaunch {
@@ -99,6 +103,12 @@ struct PatchLaunch {
   double* a_eff;      // nv
   double* e_vertex;   // nv   per-vertex bending energy (bending.compute_energy_array)
   PatchFinalize fin;
+  // push transport: before the first patch is staged the CTA waits until the arrival words of every source rank in
+  // wait_mask (LOCAL memory, written by the peers) have reached wait_epoch: the ghost rows are then in place
+  const unsigned long long* wait_flags;
+  unsigned long long wait_epoch;
+  uint64_t wait_mask;
+  int* wait_error;
   int32_t debug;      // timing experiments only (MS_DEBUG_VARIANT; results are wrong): 1 no token ring, 2 no
                       // accumulation, 4 no per-facet compute
   int* self_check;    // -DMS_SELF_CHECK builds: three violation counters (device), else unused
@@ -241,7 +251,23 @@ cudaError_t launch_allreduce_gather_coef(double* scalars, int n, unsigned long l
                                          unsigned long long epoch, int mode, int has_gc, double k_vol, double v_target,
                                          int* error, cudaStream_t st);
 cudaError_t launch_halo_warmup(unsigned long long* words, double* scalars, int* error, cudaStream_t st);
-constexpr int kFlagWords = 64;  // exported block: 4 epoch flags, 2 x 16 scalar slots (see k_allreduce_publish)
+constexpr int kFlagWords = 1024;  // exported block (words): [0..3] epoch flags of the pull transport, [8..39] 2 x 16 scalar
+                                  // slots of the pull all-reduce; push transport: [64 + 64 kind + src] arrival epochs of
+                                  // the halo rows (kind 0 positions, 1 seeds) and [192 + src] of the scalars pushed by
+                                  // rank src, [256 + (16 parity + src) 16 + k] those scalars (world <= 16)
+constexpr int kPushFlagBase = 64, kPushScalarFlagBase = 192, kPushScalarBase = 256, kPushMaxRanks = 16;
+// PUSH transport: the owner stores its rows straight into the ghost slots of the ranks that list them (posted NVLink
+// writes: nobody waits for a round trip) and then raises, in each of those ranks' flag blocks, the word that belongs to
+// it; the receiver polls LOCAL memory only.  One launch; the last block to finish raises the flags.
+cudaError_t launch_halo_push(int n_rows, int width, const double* src, double* const* peer_base, const int32_t* dst_slot,
+                             const int32_t* src_row, const int32_t* dst_row, unsigned long long* const* peer_flags,
+                             int n_slots, uint64_t dst_mask, int my_slot, int kind, unsigned long long epoch,
+                             unsigned int* ticket, cudaStream_t st);
+// gather of scalars that were PUSHED into this rank's block (k_patch's last CTA, PatchFinalize::push_*): local polls,
+// rank-order sum, KKT coefficient
+cudaError_t launch_allreduce_local_coef(double* scalars, int n, unsigned long long* own_words, int n_slots,
+                                        unsigned long long epoch, int mode, int has_gc, double k_vol, double v_target,
+                                        int* error, cudaStream_t st);
 
 // --- leaflet tilt relaxation helpers ---
 cudaError_t launch_vertex_normals(int32_t nv, const int32_t* tri, const int32_t* csr_ptr, const int32_t* csr_idx,

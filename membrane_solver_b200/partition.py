@@ -191,6 +191,11 @@ class PartitionedMesh:
         import os as _os
 
         want = (transport or _os.environ.get("MS_HALO", "peer")).strip().lower()
+        # MS_HALO_PUSH=1: owners STORE their rows into the neighbours' ghost slots and the receivers poll local words
+        # (ms_ctx_set_push_targets).  Measured on 2 x B200: 0.624 ms per step against 0.619 ms for the default, in
+        # which the neighbours pull -- remote polling was not the cost, the kernel boundaries are -- so it stays opt-in
+        self._want_push = _os.environ.get("MS_HALO_PUSH", "0").strip() == "1"
+        self.push = False
         self.transport = "nccl"
         if want == "peer" and local.world > 1:
             self.transport = "peer" if self._open_peers(gathered) else "nccl"
@@ -238,6 +243,8 @@ class PartitionedMesh:
             ok, err = 0, str(exc)
         table = [None] * local.world
         dist.all_gather_object(table, mine)
+        layout = [None] * local.world   # every rank's owned-row count and receive blocks (push targets)
+        dist.all_gather_object(layout, (int(local.n_owned), [tuple(int(x) for x in b) for b in local.recv_blocks]))
         if ok and all(t is not None for t in table):
             owners, rows = ghost_sources(local)
             try:
@@ -249,6 +256,9 @@ class PartitionedMesh:
                         dm.peer_open(r, L.IPC_FLAGS, table[r][3])
                 dm.set_rank_slot(local.rank, local.world)
                 dm.set_ghost_sources(local.world, owners, rows)
+                if self._want_push and local.world <= 16:
+                    dm.set_push_targets(*self._push_targets(layout))
+                    self.push = True
                 dm.halo_prepare()
             except L.B200Error as exc:
                 ok, err = 0, str(exc)
@@ -262,6 +272,24 @@ class PartitionedMesh:
             print(f"[ms_b200] rank {local.rank}: peer-memory halo unavailable ({err}); using NCCL send/recv",
                   file=sys.stderr)
         return int(flag.item()) == 1
+
+    def _push_targets(self, table):
+        """For every row of this rank that another rank lists as a ghost: (that rank, the row here, the row THERE).
+        A destination's ghosts are ordered by global id and grouped by source rank (``LocalMesh.recv_blocks``), and
+        ``send_lists`` gives this rank's rows for it in the same order."""
+        local = self.local
+        slots, src, dst = [], [], []
+        for d, rows in self.halo.sends:
+            n_owned_d, blocks_d = table[d]
+            first = [b[1] for b in blocks_d if b[0] == local.rank]
+            counts = [b[2] for b in blocks_d if b[0] == local.rank]
+            if len(first) != 1 or counts[0] != rows.size:
+                raise self.L.B200Error("send list and receive block of a neighbour disagree")
+            slots.append(np.full(rows.size, d, dtype=np.int32))
+            src.append(rows.astype(np.int32))
+            dst.append((n_owned_d + first[0] + np.arange(rows.size)).astype(np.int32))
+        cat = lambda xs: np.concatenate(xs) if xs else np.zeros(0, dtype=np.int32)  # noqa: E731
+        return cat(slots), cat(src), cat(dst)
 
     def exchange(self, which: int) -> None:
         if self.transport == "peer":
@@ -481,7 +509,7 @@ def _measure_partitioned(args, rank, world, local_rank, bench, total_facets: int
     res = dm.read_scalars()
     out = {"facets": nf, "vertices": nv, "frequency": n, "ms_per_step": ms_step, "steps": steps,
            "value": nf / (ms_step * 1e-3) / 1e9, "mesh_seconds": t_gen, "partition_pack_seconds": t_setup,
-           "transport": pm.transport, "fused": bool(pm.fused),
+           "transport": pm.transport, "fused": bool(pm.fused), "push": bool(pm.push),
            "energies": {"surface": res.e_surface, "bending": res.e_bending, "volume": res.volume}}
     phases = None
     if os.environ.get("MS_PHASES", "0") != "0":  # per-phase device times of this rank (diagnostic)
@@ -601,7 +629,8 @@ def bench_multi_gpu(args, rank: int, world: int, local_rank: int, bench):
                          "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({peak_kind}) x {world} GPUs",
                          "bytes_per_facet": bench.B_STEP},
             "e2e": {**weak["e2e"], "numa": numa_all},
-            "collectives_per_step": {"halo_exchanges": 2, "all_reduce": 1, "halo_transport": weak["transport"],
+            "collectives_per_step": {"halo_exchanges": 2, "all_reduce": 1,
+                                     "halo_transport": weak["transport"] + (" (push)" if weak.get("push") else ""),
                                      "all_reduce_transport": "peer memory" if peer else "nccl",
                                      "halo_bytes_per_rank": weak["max_ghost_rows_per_rank"] * (24 + 40)},
             # fused peer transport (ms_ctx_eval_partition): signal+pull positions, pass A (raises the seed flag), seed

@@ -38,6 +38,7 @@ def main():
     out = {}
     energy_opts = dm.options(L.MOD_SURFACE | L.MOD_BENDING | L.MOD_VOLUME, want_grad=False)
     sv_opts = dm.options(L.MOD_SURFACE | L.MOD_VOLUME, constraint_mode=0)
+    # "fused" = ms_ctx_eval_partition: with push targets set (default) the owners store into the ghost slots
     for transport in ("nccl", "peer", "fused", "nccl", "peer", "fused"):
         pm.transport = "nccl" if transport == "nccl" else "peer"
         pm.fused = transport == "fused"
@@ -89,7 +90,7 @@ def main():
     pm.transport, pm.fused = "peer", True
     if rank == 0:
         print(json.dumps({"n_gpus": world, "facets": int(tri.shape[0]), "ghost_rows": int(local.ghost_ids.size),
-                          "bitwise_equal": bitwise, "nccl_ms": out["nccl_ms"], "peer_ms": out["peer_ms"], "fused_ms": out["fused_ms"],
+                          "bitwise_equal": bitwise, "nccl_ms": out["nccl_ms"], "peer_ms": out["peer_ms"], "fused_ms": out["fused_ms"], "push": bool(pm.push),
                           "fused_vs_peer_scalar_rel_err": fused_scalar_err, "fused_vs_peer_grad_rel_err": fused_grad_err,
                           "E_surface": out["peer"][0][0], "E_bending": out["peer"][0][1]}), flush=True)
     dist.barrier()
