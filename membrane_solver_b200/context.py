@@ -438,9 +438,11 @@ class DeviceMesh:
     def halo_push(self, which: int, flag: int) -> None:
         L.check(self._lib.ms_ctx_halo_push(self._h, int(which), int(flag)))
 
-    def eval_partition(self, opts, exchange_positions: bool = True) -> None:
-        """One partitioned evaluation with the transport folded into the compute launches (5 launches)."""
-        L.check(self._lib.ms_ctx_eval_partition(self._h, ctypes.byref(opts), int(bool(exchange_positions))))
+    def eval_partition(self, opts, exchange_positions: bool = True, in_kernel: bool = False) -> None:
+        """One partitioned evaluation with the transport folded into the compute launches (5 launches), or, with
+        ``in_kernel``, carried out inside the patch kernels behind the interior patches (3 launches)."""
+        flags = int(bool(exchange_positions)) | (2 if in_kernel else 0)
+        L.check(self._lib.ms_ctx_eval_partition(self._h, ctypes.byref(opts), flags))
 
     def halo_error(self) -> bool:
         e = ctypes.c_int32(0)

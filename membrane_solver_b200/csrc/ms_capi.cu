@@ -98,7 +98,8 @@ struct ms_ctx {
   struct PendingProjection {
     bool active = false, use_gc = false, use_fixed = false;
   } proj;
-  DevBuf<unsigned int> d_ticket;  // last-CTA ticket of the fused finalisation
+  DevBuf<unsigned int> d_ticket;  // [0] last-CTA ticket of the fused finalisation, [1] push kernel, [2] in-kernel pulls
+  unsigned int pull_arrived = 0;  // host mirror of d_ticket[2]: CTAs that have reported so far
   DevBuf<int> d_self_check;       // violation counters of the self-check build (ms_ctx_self_check)
   bool has_gamma = false, has_kappa = false, has_c0 = false, has_boundary = false,
        has_fixed = false, has_body = false;
@@ -1741,6 +1742,53 @@ static void attach_wait(ms_ctx* c, ms::PatchLaunch& a, int kind) {
   a.wait_error = c->d_halo_error.p;
 }
 
+// in-kernel halo exchange (ms::HaloPull): the launch walks the interior patches first and pulls `which` meanwhile
+static int attach_pull(ms_ctx* c, ms::PatchLaunch& a, int32_t which, int32_t flag_index, bool signal_here) {
+  ms_ctx::PeerTable& t = c->peers;
+  const int64_t n_ghost = int64_t(c->nv) - c->n_owned;
+  const int n_patches = int(c->packed.patches.size());
+  a.patch_list = c->d_patch_order.p;   // interior patches, then the patches that read ghost rows
+  a.patch_begin = 0;
+  a.patch_count = n_patches;
+  if (signal_here) {
+    a.pull.own_flag = c->d_flag_words.p + flag_index;
+    ++c->flag_epoch[flag_index];
+  }
+  a.pull.epoch = c->flag_epoch[flag_index];
+  if (n_ghost <= 0) return 0;   // still signals: other ranks may hold ghosts of this one
+  int width = 3;
+  const double* const* table = nullptr;
+  switch (which) {
+    case MS_ARR_POSITIONS: table = t.d_pos.p; break;
+    case MS_ARR_TRIAL: table = t.d_trial.p; break;
+    case MS_ARR_SEEDS: table = t.d_seeds.p; width = ms::kSeedStride; break;
+    default: return fail(-1, "only positions, trial positions and seeds travel through the halo");
+  }
+  int64_t len = 0;
+  double* dst = array_ptr(c, which, &len);
+  if (!dst) return fail(-4, "the local array does not exist");
+  if (!c->d_ticket.p) {
+    if (int rc = c->d_ticket.ensure(4)) return rc;
+    CU(cudaMemsetAsync(c->d_ticket.p, 0, 4 * sizeof(unsigned int), c->stream));
+  }
+  a.pull.n_ghost = int32_t(n_ghost);
+  a.pull.width = width;
+  a.pull.peer_base = table;
+  a.pull.peer_flag = t.d_flags.p;
+  a.pull.n_slots = t.n_slots;
+  a.pull.flag_index = flag_index;
+  a.pull.owner = t.d_owner.p;
+  a.pull.row = t.d_row.p;
+  a.pull.dst = dst + size_t(c->n_owned) * width;
+  a.pull.arrived = c->d_ticket.p + 2;
+  c->pull_arrived += unsigned(ms::patch_grid(a));
+  a.pull.arrived_target = c->pull_arrived;
+  a.pull.first_boundary = c->n_interior;
+  a.pull.first_ghost_row = int32_t(c->n_owned);
+  a.pull.error = c->d_halo_error.p;
+  return 0;
+}
+
 // One evaluation of this rank's partition with the transport folded into the compute launches (peer memory):
 //   [signal + pull positions] -> pass A (its last CTA raises the seed flag) -> [pull seeds] -> pass B (its last
 //   CTA reduces the per-CTA rows and publishes the local scalars) -> gather (rank-order sum) + KKT coefficient
@@ -1762,9 +1810,15 @@ int ms_ctx_eval_partition(ms_ctx* c, const ms_eval_opts* o, int32_t exchange_pos
   const bool run_b = o->want_grad || (o->want_tilt_grad && (o->modules & MS_MOD_TILT));
   if (!o->want_grad && run_b) return fail(-1, "tilt-only evaluations use the unfused sequence");
   const bool push = t.push_ready;   // PUSH: owners store into the ghost slots, receivers poll local words only
+  // bit 1 of exchange_positions: exchange INSIDE the patch kernels (ms::HaloPull), hidden behind the interior patches
+  const bool overlap = (exchange_positions & 2) != 0 && !push && c->packed.params.threads >= 64;
+  exchange_positions &= 1;
   bool wait_positions = false;
+  bool pull_positions = false;
   if (exchange_positions) {
-    if (push) {
+    if (overlap) {
+      pull_positions = true;
+    } else if (push) {
       if (int rc = halo_push(c, o->use_trial ? MS_ARR_TRIAL : MS_ARR_POSITIONS, MS_FLAG_POSITIONS)) return rc;
       wait_positions = true;
     } else if (int rc = halo_launch(c, o->use_trial ? MS_ARR_TRIAL : MS_ARR_POSITIONS, MS_FLAG_POSITIONS, true)) {
@@ -1800,12 +1854,15 @@ int ms_ctx_eval_partition(ms_ctx* c, const ms_eval_opts* o, int32_t exchange_pos
     }
     if (wait_positions) attach_wait(c, a, MS_FLAG_POSITIONS);
     wait_positions = false;
+    if (pull_positions)
+      if (int rc = attach_pull(c, a, o->use_trial ? MS_ARR_TRIAL : MS_ARR_POSITIONS, MS_FLAG_POSITIONS, true)) return rc;
+    pull_positions = false;
     CU(ms::launch_pass_a(a, c->stream));
   } else {
     c->ran_pass_a = false;
   }
   if (o->want_grad) {
-    if (bending) {
+    if (bending && !overlap) {
       if (push) {
         if (int rc = halo_push(c, MS_ARR_SEEDS, MS_FLAG_SEEDS)) return rc;
       } else if (int rc = halo_launch(c, MS_ARR_SEEDS, MS_FLAG_SEEDS, false)) {
@@ -1816,6 +1873,11 @@ int ms_ctx_eval_partition(ms_ctx* c, const ms_eval_opts* o, int32_t exchange_pos
     if (int rc = fill_launch(c, o, a)) return rc;
     a.partials = c->d_partials_b.p;
     c->proj.active = false;
+    if (overlap && bending) {  // the seed flag was raised by the last CTA of pass A
+      if (int rc = attach_pull(c, a, MS_ARR_SEEDS, MS_FLAG_SEEDS, false)) return rc;
+    } else if (pull_positions) {  // surface / volume only: pass B is the first kernel
+      if (int rc = attach_pull(c, a, o->use_trial ? MS_ARR_TRIAL : MS_ARR_POSITIONS, MS_FLAG_POSITIONS, true)) return rc;
+    }
     if (push && bending) attach_wait(c, a, MS_FLAG_SEEDS);
     else if (wait_positions) attach_wait(c, a, MS_FLAG_POSITIONS);   // surface / volume only: pass B is the first kernel
     if ((o->modules & MS_MOD_TILT) && !a.tilt_grad) {

@@ -347,6 +347,11 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
       mbar_init(&bar_free[b], 32u * unsigned(n_epi_warps));
     }
   }
+  if (a.pull.own_flag && blockIdx.x == 0 && tid == 0) {  // in-kernel exchange: "my owned rows are written"
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(a.pull.own_flag) = a.pull.epoch;
+    __threadfence_system();
+  }
   if (a.wait_flags && tid < 64 && ((a.wait_mask >> tid) & 1ull)) {  // push transport: ghost rows in place?
     const volatile unsigned long long* f = a.wait_flags + tid;
     const long long t0 = clock64();
@@ -400,6 +405,7 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
     };
     PatchHeader h_cur{}, h_n1{}, h_n2{};
     int slots_cur = 0, slots_n1 = 0, slots_n2 = 0;
+    bool ghosts_in_place = false;
     if (n_my > 0) {
       load_header(0, h_cur, slots_cur);
       if (n_my > 1) load_header(1, h_n1, slots_n1);
@@ -413,6 +419,20 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
       const int n_slots = slots_cur;
       if (j + 2 < n_my) load_header(j + 2, h_n2, slots_n2);  // in flight while this patch is being issued
       if (j >= 2) mbar_wait_relaxed(&bar_empty[b], unsigned(((j >> 1) - 1) & 1));
+      if (a.pull.n_ghost > 0 && !ghosts_in_place && int(blockIdx.x) + j * int(gridDim.x) >= a.pull.first_boundary) {
+        // first patch of this CTA that reads ghost rows: every CTA must have copied its slice of them
+        const volatile unsigned int* cnt = a.pull.arrived;
+        const long long t0 = clock64();
+        while (int(*cnt - a.pull.arrived_target) < 0) {
+          if (clock64() - t0 > 4000000000LL) {
+            atomicExch(a.pull.error, 1);
+            break;
+          }
+          __nanosleep(100);
+        }
+        __threadfence();
+        ghosts_in_place = true;
+      }
       // ids of the NEXT patch into the other buffer's id area (free: the data of patch j-1 there may still be in
       // use, its ids are not).  Committed before this patch's bulk copies, so that wait_group 1 below waits for the
       // ids only.
@@ -446,6 +466,18 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
         }
       }
       auto stage_row = [&](int i, size_t row) {  // one vertex row with 8-byte asynchronous copies
+        if (a.pull.n_ghost > 0 && int(row) >= a.pull.first_ghost_row) {
+          // a ghost row copied by another CTA of THIS launch: LDGSTS.ca could hit an L1 line that an earlier patch
+          // brought in for the neighbouring owned rows (rows n_owned - 1 and n_owned share lines), so read around L1
+          const double* prow = a.pos + row * 3;
+          pos[3 * i] = __ldcg(prow); pos[3 * i + 1] = __ldcg(prow + 1); pos[3 * i + 2] = __ldcg(prow + 2);
+          if (with_seeds) {
+            const double* srow = a.seeds + row * kSeedStride;
+#pragma unroll
+            for (int c = 0; c < kSeedStride; ++c) seed[kSeedStride * i + c] = __ldcg(srow + c);
+          }
+          return;
+        }
         const double* prow = a.pos + row * 3;
         cp_async8(pos + 3 * i, prow);
         cp_async8(pos + 3 * i + 1, prow + 1);
@@ -472,6 +504,7 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
           if (t2) cp_async8(t2 + Pn + k, a.tilt_sq + row);
         }
       }
+      if (a.pull.n_ghost > 0) __threadfence_block();  // ghost rows were stored with plain stores (stage_row)
       cp_async_arrive_on(&bar_full[b]);   // one arrival per lane, when this lane's row copies have landed
       cp_async_commit();
       cp_async_wait_but_one();  // the ids of patch j+1 have landed; the bulk copies of patch j stay in flight
@@ -495,6 +528,33 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
     const int lane = tid - n_active;   // 0 .. 32*n_epi_warps-1: one owned vertex per lane and sweep
     const int epi_threads = 32 * n_epi_warps;
     const bool willmore = (flags & MS_FLAG_WILLMORE) != 0;
+    if (a.pull.n_ghost > 0) {
+      // In-kernel halo exchange (HaloPull): these warps have nothing to do until the first patch is accumulated.
+      // Wait for the owners' flags, copy this CTA's slice of the ghost rows out of the owners' arrays, report.
+      const HaloPull& hp = a.pull;
+      for (int s = lane; s < hp.n_slots; s += epi_threads) {
+        if (!hp.peer_flag[s] || !hp.peer_base[s]) continue;  // only the owners of this rank's ghosts
+        const volatile unsigned long long* f = hp.peer_flag[s] + hp.flag_index;
+        const long long t0 = clock64();
+        while (*f < hp.epoch) {
+          if (clock64() - t0 > 4000000000LL) {
+            atomicExch(hp.error, 1);
+            break;
+          }
+          __nanosleep(200);
+        }
+      }
+      named_sync(14, epi_threads);
+      __threadfence_system();
+      const int total = hp.n_ghost * hp.width;
+      for (int i = int(blockIdx.x) * epi_threads + lane; i < total; i += int(gridDim.x) * epi_threads) {
+        const int g = i / hp.width, k = i - g * hp.width;
+        hp.dst[i] = __ldcv(hp.peer_base[hp.owner[g]] + size_t(hp.row[g]) * hp.width + k);
+      }
+      __threadfence();
+      named_sync(14, epi_threads);
+      if (lane == 0) atomicAdd(hp.arrived, 1u);
+    }
     for (int j = 0; want_epi && j < n_my; ++j) {
       const int b = j & 1;
       mbar_wait_relaxed(&bar_done[b], unsigned((j >> 1) & 1));   // every round accumulated, header mailed

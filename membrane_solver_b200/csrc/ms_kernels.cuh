@@ -68,6 +68,29 @@ struct PatchFinalize {
   int32_t push_slots, push_my_slot;
 };
 
+// Halo exchange INSIDE a patch kernel (partitioned meshes, peer memory).  The launch walks the interior patches first
+// (patch_list); meanwhile the epilogue warps of every CTA wait for the owners' flags and copy a slice of the ghost rows
+// out of the owners' arrays; the producer warp of a CTA waits for `arrived` to reach `arrived_target` (every CTA has
+// copied its slice) only before it stages its first patch that reads ghost rows.  The exchange, the skew between the
+// ranks included, hides behind the interior patches, and no separate signal / pull launch is needed.
+struct HaloPull {
+  int32_t n_ghost, width;            // n_ghost == 0: nothing to pull
+  const double* const* peer_base;    // array of every owner slot
+  unsigned long long* const* peer_flag;
+  int32_t n_slots, flag_index;
+  unsigned long long epoch;          // what every owner's flag must have reached
+  const int32_t* owner;              // per ghost row: owner slot, row in the owner's array
+  const int32_t* row;
+  double* dst;                       // first ghost row of the local array
+  unsigned long long* own_flag;      // non-null: block 0 raises it (epoch) when the kernel starts -- the rows this rank
+                                     // owns were written by the previous kernel of the stream
+  unsigned int* arrived;             // monotonically increasing counter (one increment per CTA and launch)
+  unsigned int arrived_target;
+  int32_t first_boundary;            // position in the patch sequence of the first patch that reads ghost rows
+  int32_t first_ghost_row;           // local rows >= this are ghost rows (read around L1: see stage_row)
+  int* error;
+};
+
 struct PatchLaunch {
   // packed topology (device)
   const PatchHeader* patches;  // n_patches + 1 entries: a sentinel closes the slot ranges
@@ -105,6 +128,7 @@ struct PatchLaunch {
   PatchFinalize fin;
   // push transport: before the first patch is staged the CTA waits until the arrival words of every source rank in
   // wait_mask (LOCAL memory, written by the peers) have reached wait_epoch: the ghost rows are then in place
+  HaloPull pull;
   const unsigned long long* wait_flags;
   unsigned long long wait_epoch;
   uint64_t wait_mask;

@@ -195,6 +195,9 @@ class PartitionedMesh:
         # (ms_ctx_set_push_targets).  Measured on 2 x B200: 0.624 ms per step against 0.619 ms for the default, in
         # which the neighbours pull -- remote polling was not the cost, the kernel boundaries are -- so it stays opt-in
         self._want_push = _os.environ.get("MS_HALO_PUSH", "0").strip() == "1"
+        # exchange inside the patch kernels, hidden behind the interior patches (ms::HaloPull); MS_HALO_INKERNEL=0:
+        # separate signal + pull launches between the passes
+        self.in_kernel = _os.environ.get("MS_HALO_INKERNEL", "1").strip() != "0"
         self.push = False
         self.transport = "nccl"
         if want == "peer" and local.world > 1:
@@ -330,7 +333,7 @@ class PartitionedMesh:
         if not overlap or self.local.world == 1 or opts.patch_count != L.PATCHES_ALL:
             if (self.fused and opts.patch_count == L.PATCHES_ALL and not (opts.modules & L.MOD_BENDING_TILT)
                     and (opts.want_grad or not opts.want_tilt_grad)):
-                dm.eval_partition(opts, exchange_positions)
+                dm.eval_partition(opts, exchange_positions, in_kernel=self.in_kernel and not self.push)
                 return
             if exchange_positions:
                 self.exchange(L.ARR_TRIAL if opts.use_trial else L.ARR_POSITIONS)
@@ -510,6 +513,7 @@ def _measure_partitioned(args, rank, world, local_rank, bench, total_facets: int
     out = {"facets": nf, "vertices": nv, "frequency": n, "ms_per_step": ms_step, "steps": steps,
            "value": nf / (ms_step * 1e-3) / 1e9, "mesh_seconds": t_gen, "partition_pack_seconds": t_setup,
            "transport": pm.transport, "fused": bool(pm.fused), "push": bool(pm.push),
+           "in_kernel": bool(pm.fused and pm.in_kernel and not pm.push),
            "energies": {"surface": res.e_surface, "bending": res.e_bending, "volume": res.volume}}
     phases = None
     if os.environ.get("MS_PHASES", "0") != "0":  # per-phase device times of this rank (diagnostic)
@@ -630,14 +634,15 @@ def bench_multi_gpu(args, rank: int, world: int, local_rank: int, bench):
                          "bytes_per_facet": bench.B_STEP},
             "e2e": {**weak["e2e"], "numa": numa_all},
             "collectives_per_step": {"halo_exchanges": 2, "all_reduce": 1,
-                                     "halo_transport": weak["transport"] + (" (push)" if weak.get("push") else ""),
+                                     "halo_transport": weak["transport"] + (" (push)" if weak.get("push") else
+                                                                             " (inside the patch kernels)" if weak.get("in_kernel") else ""),
                                      "all_reduce_transport": "peer memory" if peer else "nccl",
                                      "halo_bytes_per_rank": weak["max_ghost_rows_per_rank"] * (24 + 40)},
             # fused peer transport (ms_ctx_eval_partition): signal+pull positions, pass A (raises the seed flag), seed
             # pull, pass B (reduces + publishes), gather + coefficient.  Unfused: pass A, pass B, reduce, coefficient
             # + per halo exchange flag signal + pull (peer) or the row gather (nccl) + the all-reduce's two kernels
-            "gpu_launches": (5 if weak.get("fused") else 4 + (6 if peer else 2)) * args.steps,
-            "launches_per_step": 5 if weak.get("fused") else 4 + (6 if peer else 2),
+            "gpu_launches": (3 if weak.get("in_kernel") else 5 if weak.get("fused") else 4 + (6 if peer else 2)) * args.steps,
+            "launches_per_step": 3 if weak.get("in_kernel") else 5 if weak.get("fused") else 4 + (6 if peer else 2),
             "clocks": weak["clocks"],
             "energies": weak["energies"],
             "setup_seconds": weak["mesh_seconds"] + weak["partition_pack_seconds"],

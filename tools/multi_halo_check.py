@@ -39,9 +39,10 @@ def main():
     energy_opts = dm.options(L.MOD_SURFACE | L.MOD_BENDING | L.MOD_VOLUME, want_grad=False)
     sv_opts = dm.options(L.MOD_SURFACE | L.MOD_VOLUME, constraint_mode=0)
     # "fused" = ms_ctx_eval_partition: with push targets set (default) the owners store into the ghost slots
-    for transport in ("nccl", "peer", "fused", "nccl", "peer", "fused"):
+    for transport in ("nccl", "peer", "fused", "inkernel", "nccl", "peer", "fused", "inkernel"):
         pm.transport = "nccl" if transport == "nccl" else "peer"
-        pm.fused = transport == "fused"
+        pm.fused = transport in ("fused", "inkernel")
+        pm.in_kernel = transport == "inkernel"
         dm.set_positions(start)
         res = pm.eval(opts)
         grad = dm.download(L.ARR_GRAD)[: local.n_owned]
@@ -86,11 +87,18 @@ def main():
     fused_scalar_err = float(np.max(np.abs(c - b) / np.maximum(1e-300, np.abs(b))))
     fused_grad_err = float(np.abs(out["fused"][1] - out["peer"][1]).max() / scale)
     assert fused_scalar_err <= 1e-12 and fused_grad_err <= 1e-13, (fused_scalar_err, fused_grad_err)
+    # the exchange inside the patch kernels changes the order in which a CTA walks its patches, hence the order of the
+    # per-CTA scalar sums: rounding-level differences in the scalars (and through lambda in the projected gradient)
+    d = np.array(out["inkernel"][0])
+    ik_scalar_err = float(np.max(np.abs(d - b) / np.maximum(1e-300, np.abs(b))))
+    ik_grad_err = float(np.abs(out["inkernel"][1] - out["peer"][1]).max() / scale)
+    assert ik_scalar_err <= 1e-12 and ik_grad_err <= 1e-13, (ik_scalar_err, ik_grad_err)
     # energy-only evaluation at trial positions (the line-search call) through the peer halo
-    pm.transport, pm.fused = "peer", True
+    pm.transport, pm.fused, pm.in_kernel = "peer", True, True
     if rank == 0:
         print(json.dumps({"n_gpus": world, "facets": int(tri.shape[0]), "ghost_rows": int(local.ghost_ids.size),
-                          "bitwise_equal": bitwise, "nccl_ms": out["nccl_ms"], "peer_ms": out["peer_ms"], "fused_ms": out["fused_ms"], "push": bool(pm.push),
+                          "bitwise_equal": bitwise, "nccl_ms": out["nccl_ms"], "peer_ms": out["peer_ms"], "fused_ms": out["fused_ms"], "inkernel_ms": out["inkernel_ms"], "push": bool(pm.push),
+                          "inkernel_vs_peer_scalar_rel_err": ik_scalar_err, "inkernel_vs_peer_grad_rel_err": ik_grad_err,
                           "fused_vs_peer_scalar_rel_err": fused_scalar_err, "fused_vs_peer_grad_rel_err": fused_grad_err,
                           "E_surface": out["peer"][0][0], "E_bending": out["peer"][0][1]}), flush=True)
     dist.barrier()
