@@ -309,6 +309,10 @@ MS_API int ms_ctx_halo_error(ms_ctx* ctx, int32_t* error);
  * groups instead of the reduce kernel's 64) and are run-to-run repeatable.  Replaces the per-evaluation halo exchange + scalar
  * all-reduce of the partitioned sweep (BASELINE.json north_star; no counterpart in the single-process reference).
  * The kernels wait for flags of peers, so the ranks must run concurrently: one process per GPU. */
+/* exchange_positions: bit 0 = exchange the (trial) positions for this evaluation; bit 1 = carry the exchanges out INSIDE
+ * the patch kernels (interior patches first; the epilogue warps pull the ghost rows meanwhile; the producer warps wait
+ * before their first patch that reads ghost rows): 3 launches, the exchanges hide behind the interior patches.  Needs
+ * rounds of at least 64 lanes (the default packing). */
 MS_API int ms_ctx_eval_partition(ms_ctx* ctx, const ms_eval_opts* opts, int32_t exchange_positions);
 /* PUSH form of the same transport (optional; ms_ctx_eval_partition uses it once the targets are set; measured no faster
  * than the pull form on 2 x B200, PartitionedMesh enables it with MS_HALO_PUSH=1): for each of the n rows of
