@@ -1836,6 +1836,12 @@ int ms_ctx_eval_partition(ms_ctx* c, const ms_eval_opts* o, int32_t exchange_pos
       a.fin.push_my_slot = t.my_slot;
     } else {
       a.fin.publish_words = c->d_flag_words.p;
+      if (overlap) {  // gather in the last CTA as well: no third launch
+        a.fin.gather_words = t.d_flags.p;
+        a.fin.gather_slots = t.n_slots;
+        a.fin.gather_mode = o->want_grad ? o->constraint_mode : -2;
+        a.fin.gather_error = c->d_halo_error.p;
+      }
     }
     return 0;
   };
@@ -1889,7 +1895,9 @@ int ms_ctx_eval_partition(ms_ctx* c, const ms_eval_opts* o, int32_t exchange_pos
   }
   bool use_gc, use_fixed;
   projection_of(c, o, use_gc, use_fixed);
-  if (push)
+  if (overlap) {
+    // gathered by the last CTA of the last pass
+  } else if (push)
     CU(ms::launch_allreduce_local_coef(c->d_scalars.p, 12, c->d_flag_words.p, t.n_slots, reduce_epoch,
                                        o->want_grad ? o->constraint_mode : -2, use_gc ? 1 : 0, o->k_vol, o->v_target,
                                        c->d_halo_error.p, c->stream));

@@ -779,6 +779,37 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
           __threadfence_system();
         }
       }
+      if (a.fin.gather_words) {  // the other half of the all-reduce, in place (k_allreduce_gather_coef)
+        __shared__ int s_ok;
+        const unsigned long long e = a.fin.publish_epoch;
+        if (tid == 0) s_ok = 1;
+        __syncthreads();
+        for (int s = tid; s < a.fin.gather_slots; s += NC + 64) {
+          const volatile unsigned long long* f = a.fin.gather_words[s] + 2;
+          const long long t0 = clock64();
+          while (*f < e) {
+            if (clock64() - t0 > 4000000000LL) {
+              atomicExch(a.fin.gather_error, 1);
+              s_ok = 0;
+              break;
+            }
+            __nanosleep(100);
+          }
+        }
+        __syncthreads();
+        if (s_ok) {
+          __threadfence_system();
+          if (tid < kPartialStride) {
+            double acc = 0.0;
+            for (int s = 0; s < a.fin.gather_slots; ++s)
+              acc += __ldcv(reinterpret_cast<const double*>(a.fin.gather_words[s] + 8 + 16 * (e & 1ull)) + tid);
+            a.fin.scalars[tid] = acc;
+          }
+          __syncthreads();
+          if (tid == 0 && a.fin.gather_mode != -2)
+            kkt_coefficient(a.fin.scalars, a.fin.gather_mode, a.fin.has_gc, a.fin.k_vol, a.fin.v_target);
+        }
+      }
     }
   }
 }

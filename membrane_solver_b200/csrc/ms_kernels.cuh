@@ -66,6 +66,12 @@ struct PatchFinalize {
   // arrival word of this rank there is raised
   unsigned long long* const* push_words;   // flag blocks of all ranks (device table, own block included)
   int32_t push_slots, push_my_slot;
+  // gather in the same CTA: after publishing, wait for every rank's publish flag, add the slots in rank order and
+  // write the KKT coefficient from the GLOBAL sums (mode gather_mode) -- the evaluation of a partition is then two
+  // launches, like the evaluation of a whole mesh
+  unsigned long long* const* gather_words;  // non-null: flag blocks of all ranks
+  int32_t gather_slots, gather_mode;
+  int* gather_error;
 };
 
 // Halo exchange INSIDE a patch kernel (partitioned meshes, peer memory).  The launch walks the interior patches first

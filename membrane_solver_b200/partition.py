@@ -638,11 +638,12 @@ def bench_multi_gpu(args, rank: int, world: int, local_rank: int, bench):
                                                                              " (inside the patch kernels)" if weak.get("in_kernel") else ""),
                                      "all_reduce_transport": "peer memory" if peer else "nccl",
                                      "halo_bytes_per_rank": weak["max_ghost_rows_per_rank"] * (24 + 40)},
-            # fused peer transport (ms_ctx_eval_partition): signal+pull positions, pass A (raises the seed flag), seed
+            # in-kernel exchange: pass A and pass B only (halo pulls by the epilogue warps behind the interior patches,
+            # scalars published and gathered by the last CTA).  Fused peer transport: signal+pull positions, pass A (raises the seed flag), seed
             # pull, pass B (reduces + publishes), gather + coefficient.  Unfused: pass A, pass B, reduce, coefficient
             # + per halo exchange flag signal + pull (peer) or the row gather (nccl) + the all-reduce's two kernels
-            "gpu_launches": (3 if weak.get("in_kernel") else 5 if weak.get("fused") else 4 + (6 if peer else 2)) * args.steps,
-            "launches_per_step": 3 if weak.get("in_kernel") else 5 if weak.get("fused") else 4 + (6 if peer else 2),
+            "gpu_launches": (2 if weak.get("in_kernel") else 5 if weak.get("fused") else 4 + (6 if peer else 2)) * args.steps,
+            "launches_per_step": 2 if weak.get("in_kernel") else 5 if weak.get("fused") else 4 + (6 if peer else 2),
             "clocks": weak["clocks"],
             "energies": weak["energies"],
             "setup_seconds": weak["mesh_seconds"] + weak["partition_pack_seconds"],
