@@ -311,7 +311,8 @@ MS_API int ms_ctx_halo_error(ms_ctx* ctx, int32_t* error);
  * The kernels wait for flags of peers, so the ranks must run concurrently: one process per GPU. */
 /* exchange_positions: bit 0 = exchange the (trial) positions for this evaluation; bit 1 = carry the exchanges out INSIDE
  * the patch kernels (interior patches first; the epilogue warps pull the ghost rows meanwhile; the producer warps wait
- * before their first patch that reads ghost rows): 3 launches, the exchanges hide behind the interior patches.  Needs
+ * before their first patch that reads ghost rows; the last CTA of the last pass publishes AND gathers the scalars):
+ * 2 launches, the exchanges hide behind the interior patches.  Needs
  * rounds of at least 64 lanes (the default packing). */
 MS_API int ms_ctx_eval_partition(ms_ctx* ctx, const ms_eval_opts* opts, int32_t exchange_positions);
 /* PUSH form of the same transport (optional; ms_ctx_eval_partition uses it once the targets are set; measured no faster
