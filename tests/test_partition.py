@@ -201,3 +201,57 @@ def test_partitioned_minimizer_facade_matches_single_domain(tmp_path):
     assert np.max(np.abs(got["pos"] - dm.pos)) <= 1e-12
     assert np.allclose(got["history"], np.array(mini.history, dtype=float), rtol=1e-12, atol=0)
     assert any(h[3] for h in mini.history)      # at least one accepted step: the loop really moved
+
+
+def _push_targets_worker(rank, world, port, out_dir):
+    """``PartitionedMesh._push_targets`` without a device: every rank computes, for the rows its neighbours list as
+    ghosts, (neighbour, row here, row there); applying all of them to per-rank arrays must fill every ghost row with
+    the owner's data -- the same result as the gloo halo exchange."""
+    import torch
+    import torch.distributed as dist
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    for p in (here, os.path.dirname(here)):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    pos, tri = icosphere(10)
+    nv = pos.shape[0]
+    local = part.split_mesh(nv, tri, world, rank)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, local.ghost_ids)
+    sends = part.send_lists(local, gathered)
+    layout = [None] * world
+    dist.all_gather_object(layout, (int(local.n_owned), [tuple(int(x) for x in b) for b in local.recv_blocks]))
+
+    class Shell:   # the two attributes _push_targets reads, no device behind them
+        pass
+
+    pm = Shell()
+    pm.local = local
+    pm.halo = part.HaloExchange(local, sends, dist, torch, torch.device("cpu"))
+    pm.L = __import__("membrane_solver_b200._lib", fromlist=["_lib"])
+    slots, src, dst = part.PartitionedMesh._push_targets(pm, layout)
+    assert slots.shape == src.shape == dst.shape and slots.size == pm.halo.send_rows.size
+    assert np.all(src < local.n_owned) and np.all(slots != rank)
+    rows = local.global_rows()
+    np.savez(os.path.join(out_dir, f"push_{rank}.npz"), slots=slots, src_global=rows[src], dst=dst, rows=rows,
+             n_owned=local.n_owned)
+    dist.destroy_process_group()
+
+
+def test_push_targets_fill_every_ghost_row(tmp_path):
+    import torch.multiprocessing as mp
+
+    world = 3
+    mp.spawn(_push_targets_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    data = [np.load(str(tmp_path / f"push_{r}.npz")) for r in range(world)]
+    # simulate the stores: the value is the global id of the owner's row
+    arrays = [np.where(np.arange(d["rows"].size) < int(d["n_owned"]), d["rows"], -1) for d in data]
+    for r, d in enumerate(data):
+        for slot, g, dst in zip(d["slots"], d["src_global"], d["dst"]):
+            assert dst >= int(data[slot]["n_owned"])          # lands in the ghost region of the neighbour
+            assert arrays[slot][dst] == -1                    # no ghost row is written twice
+            arrays[slot][dst] = g
+    for r, d in enumerate(data):
+        assert np.array_equal(arrays[r], d["rows"])           # every ghost row holds its owner's row
