@@ -112,10 +112,12 @@ static int pack_range(int32_t nv, int32_t nf, const int32_t* tri, const uint8_t*
     // --- schedule the facets into conflict-free rounds AND bank-conflict-free lanes ---
     // A facet may join a round if none of its OWNED corners is written in that round and the
     // round has a free slot.  Round r owns the T record slots [slot_off + r*T, slot_off + (r+1)*T),
-    // i.e. T/16 half-warps.  All patch-local arrays in shared memory are structure-of-arrays with
-    // 8-byte elements, so a 64-bit gather / read-modify-write by a half-warp is conflict free
-    // exactly when the local vertex indices it uses at one corner position are pairwise distinct
-    // modulo 16 (or identical -> broadcast).  ONE clash costs the whole half-warp an extra
+    // i.e. T/16 half-warps.  The patch-local arrays in shared memory hold 8-byte elements: the
+    // accumulators as structure-of-arrays (element i of a component), the staged positions / seeds
+    // as rows of 3 / 5 doubles (element 3 i + k, 5 i + k; 3 and 5 are coprime to 16).  Either way a
+    // 64-bit gather / read-modify-write by a half-warp is conflict free exactly when the local
+    // vertex indices it uses at one corner position are pairwise distinct modulo 16 (or identical
+    // -> broadcast).  ONE clash costs the whole half-warp an extra
     // wavefront, so the placement looks for a (round, half-warp, rotation) with NO clash at any of
     // the three corner positions -- the per-facet math is invariant under cyclic relabelling --
     // preferring the least-filled round; only when none exists does it take the cheapest one.
