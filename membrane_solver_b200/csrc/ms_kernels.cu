@@ -2235,6 +2235,12 @@ cudaError_t launch_halo_warmup(unsigned long long* words, double* scalars, int* 
   k_halo_pull<<<1, 256, 0, st>>>(0, 3, nullptr, nullptr, 0, 0, 0ull, nullptr, nullptr, nullptr, error);
   k_allreduce_publish<<<1, 32, 0, st>>>(scalars, 0, words, 0ull);
   k_allreduce_gather<<<1, 64, 0, st>>>(nullptr, 0, 0, 0ull, scalars, error);
+  // every kernel a lock-step sequence may launch for the first time while a peer's kernel is already waiting: the
+  // lazy load of a kernel can need the device, which a waiting kernel of the same process holds
+  k_allreduce_gather_coef<<<1, 64, 0, st>>>(nullptr, 0, 0, 0ull, scalars, -2, 0, 0.0, 0.0, error);
+  k_halo_exchange<<<1, 256, 0, st>>>(words + 3, 0, 3, nullptr, nullptr, 0, 0, 0ull, nullptr, nullptr, nullptr, error);
+  k_reduce_partials<<<1, kReduceRows * kPartialStride, 0, st>>>(nullptr, 0, nullptr, 0, 0u, scalars);
+  k_kkt_coefficient<<<1, 1, 0, st>>>(scalars, -1, 0, 0.0, 0.0);
   return cudaGetLastError();
 }
 

@@ -119,3 +119,48 @@ def test_ghost_sources_point_at_the_owners_rows():
                 owner = parts[int(o)]
                 assert np.all(rows[sel] < owner.n_owned)
                 assert np.array_equal(owner.global_rows()[rows[sel]], loc.ghost_ids[sel])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flags", [1, 3], ids=["separate-launches", "inside-the-patch-kernels"])
+def test_partition_entry_point_with_one_rank(flags):
+    """``ms_ctx_eval_partition`` on a "partition" that is the whole mesh (one rank, no ghost rows): the entry point
+    the multi-process path calls per evaluation runs in the 1-GPU tier too -- the rank's flag raised by the kernel,
+    interior-first patch order, the last CTA reducing, publishing AND gathering the scalars, the multiplier from
+    the gathered sums -- and must give the plain evaluation's results (scalars to rounding: the per-CTA sums are
+    taken over a different patch order; gradient rows bitwise)."""
+    from membrane_solver_b200 import _lib as L
+    from membrane_solver_b200.context import DeviceMesh
+    from membrane_solver_b200.synthetic import icosphere
+
+    pos, tri = icosphere(48)
+    rng = np.random.default_rng(5)
+    pos = pos * (1.0 + 0.02 * rng.standard_normal((pos.shape[0], 1)))
+    nv, nf = pos.shape[0], tri.shape[0]
+    mods = L.MOD_SURFACE | L.MOD_BENDING | L.MOD_VOLUME
+    dm = DeviceMesh(0)
+    dm.set_topology(nv, tri, body_mask=np.ones(nf, np.uint8))
+    dm.set_surface_tension(1.0)
+    dm.set_bending_params(1.2, 0.05)
+    dm.set_positions(pos)
+    opts = dm.options(mods, constraint_mode=0)
+    want = dm.eval(opts)
+    want_raw = dm.download(L.ARR_GRAD)            # projected gradient of the plain evaluation
+    dm.ipc_export(L.IPC_FLAGS)                    # allocates the flag words
+    dm.set_rank_slot(0, 1)
+    dm.set_ghost_sources(1, np.zeros(0, np.int32), np.zeros(0, np.int32))
+    dm.halo_prepare()
+    for _ in range(3):                            # epochs advance, the counters of the in-kernel form too
+        dm.eval_partition(opts, True, in_kernel=(flags == 3))
+    got = dm.read_scalars()
+    assert not dm.halo_error()
+    for name in ("e_surface", "e_bending", "volume", "area", "kkt_lambda"):
+        a, b = getattr(got, name), getattr(want, name)
+        assert abs(a - b) <= 1e-12 * max(1.0, abs(b)), (name, a, b)
+    assert rel_err(dm.download(L.ARR_GRAD), want_raw) <= 1e-13
+    # energy-only evaluation: pass A alone publishes and gathers
+    e_opts = dm.options(mods, want_grad=False)
+    dm.eval_partition(e_opts, True, in_kernel=(flags == 3))
+    e_only = dm.read_scalars()
+    assert abs(e_only.e_bending - want.e_bending) <= 1e-12 * abs(want.e_bending)
+    dm.close()
