@@ -124,3 +124,52 @@ def test_caveolin_end_state_module_energies(backend, gold):
     total = ev.compute_tilt_dependent_energy_with_leaflet_tilts(positions=pos, tilts_in=mesh.tilts_in_view(),
                                                                 tilts_out=mesh.tilts_out_view())
     assert abs(total - sum(CAVEOLIN_END.values())) <= 1e-9 * sum(CAVEOLIN_END.values())
+
+
+def test_mesh_operations_of_the_instruction_lists_on_arrays(backend, gold):
+    """Rows f2 / f4 on the benchmark sequences: every ``r`` and ``V`` instruction of the three lists, applied to the
+    reference's state BEFORE it with the array twins -- 1->4 refinement (``geometry/refine.py``), vertex averaging
+    (``geometry/vertex_average.py``) followed, as ``commands/mesh_ops.py:45-53`` does, by the hard volume projection
+    (``modules/constraints/volume.py::enforce_constraint`` with volume and dV/dx from the device, 12 iterations of the
+    ``mesh_operation`` context) -- must land on the reference's state AFTER it: vertex averaging 1e-12 on the
+    positions, refinement the same vertex set and facet count (the reference numbers the new vertices differently)
+    and the same energy."""
+    from membrane_solver_b200.geometry.refine import refine_triangles
+    from membrane_solver_b200.geometry.vertex_average import vertex_average_arrays
+    from membrane_solver_b200.modules.constraints import volume as volume_constraint
+
+    checked = {"r": 0, "V": 0}
+    for name in ("cube", "catenoid", "bcube"):
+        prm = json.loads(str(gold[f"{name}_params_json"]))
+        for k in range(1, int(gold[f"{name}_count"])):
+            ins = str(gold[f"{name}_{k:02d}_instruction"]).replace(" ", "")
+            a, b = f"{name}_{k - 1:02d}_", f"{name}_{k:02d}_"
+            pos, tri, fixed = gold[a + "pos"], gold[a + "tri"], np.asarray(gold[a + "fixed"], bool)
+            cons = [str(x) for x in gold[b + "constraints"]]
+            if ins[0] == "r":
+                p, t, f = pos, tri, fixed
+                for _ in range(int(ins[1:] or 1)):
+                    out = refine_triangles(p, t, f)
+                    p, t, f = out[0], out[1], (out[2] if len(out) > 2 else None)
+                want = gold[b + "pos"]
+                assert p.shape == want.shape and t.shape == gold[b + "tri"].shape
+                assert np.array_equal(p[: pos.shape[0]], pos)                  # old vertices keep their rows
+                key = lambda x: x[np.lexsort(np.round(x, 9).T[::-1])]          # noqa: E731
+                assert np.max(np.abs(key(p) - key(want))) <= 1e-12, (name, k)
+                checked["r"] += 1
+            elif ins[0] == "V" and cons in ([], ["volume"]):
+                if name == "catenoid":
+                    continue                        # its rims are pinned by pin_to_circle, which is not on the path
+                p = pos
+                for _ in range(int(ins[1:] or 1)):
+                    p = vertex_average_arrays(p, tri, movable=~fixed)
+                if cons == ["volume"]:
+                    gp = GlobalParams(**prm)
+                    mesh = ArrayMesh(p, tri, global_params=gp, fixed=fixed,
+                                     bodies={0: ArrayBody(gold[a + "body_rows_0"],
+                                                          target_volume=float(gold[a + "body_target_0"]))})
+                    volume_constraint.enforce_constraint(mesh, global_params=gp, context="mesh_operation")
+                    p = np.array(mesh.positions_view())
+                assert np.max(np.abs(p - gold[b + "pos"])) <= 1e-12, (name, k, ins)
+                checked["V"] += 1
+    assert checked["r"] >= 4 and checked["V"] >= 5, checked
