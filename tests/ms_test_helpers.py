@@ -151,3 +151,37 @@ def emulate_leaflet(pos, tri, tilts, *, sign, keep=None, is_boundary=None, inter
     if rc:
         raise RuntimeError(f"emul_leaflet failed: {rc}")
     return dict(E_bt=float(e2[0]), E_tilt=float(e2[1]), E_smooth=float(e2[2]), grad=grad, tilt_grad=tg)
+
+
+def odd_mesh(seed: int, nfan: int):
+    """A mesh the benchmark shapes never produce (see test_odd_topologies_against_the_oracle) with per-facet surface
+    tension, a partial body and the oracle's surface / volume results: (pos, tri, gamma, body, (E, g, V, dV/dx))."""
+    from membrane_solver_b200.synthetic import icosphere, open_sheet
+    from oracle import ref_modules as ref
+
+    rng = np.random.default_rng(seed)
+    pa, ta = icosphere(4)
+    pb, tb = open_sheet(5, 4, jitter=0.1)
+    pb = pb + np.array([3.0, 0.0, 0.0])
+    ring = np.stack([np.cos(np.linspace(0, 2 * np.pi, nfan, endpoint=False)),
+                     np.sin(np.linspace(0, 2 * np.pi, nfan, endpoint=False)), np.zeros(nfan)], axis=1)
+    pc = np.concatenate([[[0.0, 0.0, 0.4]], ring]) + np.array([0.0, 4.0, 0.0])
+    tc = np.stack([np.zeros(nfan, int), 1 + np.arange(nfan), 1 + (np.arange(nfan) + 1) % nfan], axis=1)
+    pos = np.concatenate([pa, pb, pc, rng.normal(size=(7, 3))])                 # 7 vertices nobody uses
+    tri = np.concatenate([ta, tb + len(pa), tc + len(pa) + len(pb)])
+    tri = np.concatenate([tri, tri[3:4], [[5, 5, 9], [2, 7, 2]]])               # duplicate facet, two degenerate ones
+    perm = rng.permutation(len(pos))                                            # random vertex order
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(len(pos))
+    pos, tri = pos[perm], inv[tri].astype(np.int32)
+    pos = pos + 0.01 * rng.normal(size=pos.shape)
+    nf = tri.shape[0]
+    gamma = rng.uniform(0.5, 1.5, size=nf)
+    body = (rng.uniform(size=nf) < 0.6).astype(np.uint8)
+    want_g = np.zeros_like(pos)
+    want_e = ref.surface_energy_and_gradient(pos, tri, gamma, want_g)
+    want_vg = np.zeros_like(pos)
+    tri_body = tri[body.astype(bool)]
+    want_v = ref.body_volume(pos, tri_body)
+    ref.accumulate_volume_gradient(pos, tri_body, want_vg, 1.0)
+    return pos, tri, gamma, body, (want_e, want_g, want_v, want_vg)

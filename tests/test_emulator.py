@@ -89,3 +89,22 @@ def test_emulated_bending_tilt_vs_reference_golden(path):
                          tilts=g["tilts"], kappa_u=float(kappa), c0_u=float(c0))
         assert abs(only["E_bending_tilt"] - e) <= TOL * max(1.0, abs(e)), tag
         assert rel_err(only["tilt_grad"], g[f"tgonly_bending_tilt_{tag}"]) <= TOL, tag
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_odd_topologies_against_the_oracle(seed):
+    """Packer and per-facet code on meshes the benchmark shapes never produce: a surface with unused vertices, a few
+    facets that name a vertex twice (zero area: never listed), a fan of valence 14 (14 rounds of 96 slots: close to the
+    slot capacity of a patch; ms_ctx_set_topology narrows the rounds beyond that), a
+    duplicated facet and two components, in random vertex order and with several pack geometries.  Surface and volume
+    modules (they are defined facet by facet, whatever the connectivity) against the oracle at 1e-12."""
+    pos, tri, gamma, body, want = H.odd_mesh(seed, nfan=14)
+    nf = tri.shape[0]
+    want_e, want_g, want_v, want_vg = want
+    for pack in (dict(), dict(threads=32, max_owned=16, max_local=120), dict(threads=64, max_owned=48, max_local=200)):
+        out = H.emulate(pos, tri, modules=H.MOD_SURFACE | H.MOD_VOLUME, body_mask=body, gamma=gamma, **pack)
+        assert abs(out["E_surface"] - want_e) <= TOL * abs(want_e), pack
+        assert rel_err(out["grad"], want_g) <= TOL, pack
+        assert abs(out["volume"] - want_v) <= TOL * max(1.0, abs(want_v)), pack
+        assert rel_err(out["volgrad"], want_vg) <= TOL, pack
+        assert out["pack"]["n_listed"] >= nf - 2          # the two degenerate facets are never listed

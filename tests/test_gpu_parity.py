@@ -759,3 +759,25 @@ def test_random_soups_with_repeated_and_wild_indices(L):
                 _scalar_close(r.volume, ref.body_volume(pos, tv), 1e-12)
                 assert rel_err(grad, want_g) <= 1e-11
                 dm.close()
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_odd_topologies_through_the_c_abi(L, seed):
+    """The mesh of tests/test_emulator.py::test_odd_topologies_against_the_oracle with a fan of valence 30 (more rounds
+    than a 96-lane patch can hold: ms_ctx_set_topology narrows the rounds), unused vertices, degenerate and duplicated
+    facets, two components, random vertex order, per-facet surface tension and a partial body -- with and without the
+    internal Morton re-ordering -- against the oracle at 1e-12."""
+    import ms_test_helpers as H
+
+    pos, tri, gamma, body, (want_e, want_g, want_v, want_vg) = H.odd_mesh(seed, nfan=30)
+    for hint in (None, pos):
+        dm = _ctx(pos.shape[0], tri, body_mask=body, order_hint=hint)
+        dm.set_surface_tension(gamma)
+        dm.set_positions(pos)
+        res = dm.eval(dm.options(L.MOD_SURFACE | L.MOD_VOLUME))
+        assert abs(res.e_surface - want_e) <= 1e-12 * abs(want_e)
+        assert abs(res.volume - want_v) <= 1e-12 * max(1.0, abs(want_v))
+        assert rel_err(dm.download(L.ARR_GRAD), want_g) <= 1e-12
+        assert rel_err(dm.download(L.ARR_VOLGRAD), want_vg) <= 1e-12
+        assert dm.pack_info()["threads"] < 96        # the fan forced narrower rounds
+        dm.close()
