@@ -298,7 +298,7 @@ MS_API int ms_ctx_set_rank_slot(ms_ctx* ctx, int32_t slot, int32_t n_slots);
  * rank); needs the flag words of EVERY rank opened.  Replaces the NCCL all-reduce of an evaluation and, like it,
  * is entered by every rank after its pulls. */
 MS_API int ms_ctx_allreduce_scalars(ms_ctx* ctx, int32_t count);
-/* 0 while every pull found its flags in time; 1 after a pull gave up waiting (~2 s) */
+/* 0 while every pull found its flags in time; 1 after a pull gave up waiting (~10 s) */
 MS_API int ms_ctx_halo_error(ms_ctx* ctx, int32_t* error);
 /* One evaluation of this rank's partition with the transport folded into the compute launches: signal + pull of the
  * (trial) positions in one kernel when exchange_positions != 0, pass A whose last CTA raises the seed flag, the seed

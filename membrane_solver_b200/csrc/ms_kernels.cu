@@ -62,6 +62,11 @@ __device__ __forceinline__ void block_sum(double (&v)[N], double* red, int n_thr
   }
 }
 
+// Bound of every wait for a peer's flag (clock64 cycles, about 10 s at 1.97 GHz): a rank that left the lock-step
+// sequence is reported through the error word instead of hanging the box; generous, because a peer's first launch of a
+// kernel includes its lazy load.
+constexpr long long kWaitCycles = 20000000000LL;
+
 // ---- asynchronous copies (LDGSTS): global -> shared without a register round trip ----
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return unsigned(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
@@ -356,7 +361,7 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
     const volatile unsigned long long* f = a.wait_flags + tid;
     const long long t0 = clock64();
     while (*f < a.wait_epoch) {
-      if (clock64() - t0 > 4000000000LL) {
+      if (clock64() - t0 > kWaitCycles) {
         atomicExch(a.wait_error, 1);
         break;
       }
@@ -424,7 +429,7 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
         const volatile unsigned int* cnt = a.pull.arrived;
         const long long t0 = clock64();
         while (int(*cnt - a.pull.arrived_target) < 0) {
-          if (clock64() - t0 > 4000000000LL) {
+          if (clock64() - t0 > kWaitCycles) {
             atomicExch(a.pull.error, 1);
             break;
           }
@@ -537,7 +542,7 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
         const volatile unsigned long long* f = hp.peer_flag[s] + hp.flag_index;
         const long long t0 = clock64();
         while (*f < hp.epoch) {
-          if (clock64() - t0 > 4000000000LL) {
+          if (clock64() - t0 > kWaitCycles) {
             atomicExch(hp.error, 1);
             break;
           }
@@ -788,7 +793,7 @@ __global__ void __launch_bounds__(NC + 64, 1) k_patch(PatchLaunch a, bool bendin
           const volatile unsigned long long* f = a.fin.gather_words[s] + 2;
           const long long t0 = clock64();
           while (*f < e) {
-            if (clock64() - t0 > 4000000000LL) {
+            if (clock64() - t0 > kWaitCycles) {
               atomicExch(a.fin.gather_error, 1);
               s_ok = 0;
               break;
@@ -1490,7 +1495,7 @@ __global__ void __launch_bounds__(256) k_tilt_cg_direction(int64_t nv, const dou
 // word (k_halo_signal, stream-ordered after the producing kernel).  A consumer waits until every owner's flag
 // has reached the epoch it expects and then copies its ghost rows straight out of the owners' arrays with
 // peer loads (k_halo_pull): one kernel, no staging buffer, no host round trip.  The wait is bounded: after
-// ~2 s without the flag the kernel records an error instead of spinning forever.
+// ~10 s (kWaitCycles) without the flag the kernel records an error instead of spinning forever.
 __global__ void k_halo_signal(unsigned long long* flag, unsigned long long epoch) {
   __threadfence_system();
   *reinterpret_cast<volatile unsigned long long*>(flag) = epoch;
@@ -1510,7 +1515,7 @@ __device__ __forceinline__ void halo_wait_and_pull(int n_ghost, int width, const
     const volatile unsigned long long* f = peer_flag[s] + flag_index;
     const long long t0 = clock64();
     while (*f < epoch) {
-      if (clock64() - t0 > 4000000000LL) {
+      if (clock64() - t0 > kWaitCycles) {
         atomicExch(error, 1);
         ok = 0;
         break;
@@ -1580,7 +1585,7 @@ __device__ __forceinline__ bool allreduce_gather(unsigned long long* const* __re
     const volatile unsigned long long* f = peer_words[s] + 2;
     const long long t0 = clock64();
     while (*f < epoch) {
-      if (clock64() - t0 > 4000000000LL) {
+      if (clock64() - t0 > kWaitCycles) {
         atomicExch(error, 1);
         ok = 0;
         break;
@@ -2164,7 +2169,7 @@ __global__ void k_allreduce_local_coef(unsigned long long* own_words, int n_slot
     const volatile unsigned long long* f = own_words + kPushScalarFlagBase + s;
     const long long t0 = clock64();
     while (*f < epoch) {
-      if (clock64() - t0 > 4000000000LL) {
+      if (clock64() - t0 > kWaitCycles) {
         atomicExch(error, 1);
         ok = 0;
         break;
