@@ -275,8 +275,9 @@ MS_API int ms_ctx_leaflet_swap_trial(ms_ctx* ctx, int32_t leaflet);
 #define MS_IPC_FLAGS        100   /* pseudo array id: the flag words */
 #define MS_IPC_HANDLE_BYTES 64
 #define MS_FLAG_POSITIONS   0     /* guards MS_ARR_POSITIONS and MS_ARR_TRIAL */
-#define MS_FLAG_SEEDS       1     /* close every peer array this context has opened (before ANY rank frees its arrays: every rank calls this,
- * the ranks meet at a barrier, then the contexts may be destroyed) */
+#define MS_FLAG_SEEDS       1     /* guards MS_ARR_SEEDS */
+/* close every peer array this context has opened (before ANY rank frees its arrays: every rank calls this, the ranks
+ * meet at a barrier, then the contexts may be destroyed) */
 MS_API int ms_ctx_peer_close(ms_ctx* ctx);
 /* guards MS_ARR_SEEDS */
 MS_API int ms_ctx_ipc_export(ms_ctx* ctx, int32_t which, uint8_t* handle64);
